@@ -1,0 +1,233 @@
+"""Seeded synthetic genomes and BLAST tables of the shapes BASELINE.json names.
+
+There is no network and the reference ships no data, so every
+measurement and every parity test runs on genomes made here.  The generator follows
+SURVEY.md section 8(d): an ancestral gene order; each genome is `k` fractionated
+sub-genome copies (retention 0.6) with random inversions and translocations, cut into
+the stated number of chromosomes; gene families with Zipf-like sizes give off-diagonal
+noise hits; 8 % tandem duplicates give near-diagonal hits; bit scores are integers so
+ties occur; rows are emitted per query in descending score like BLAST; sub-threshold
+rows, self hits and duplicated (id1, id2) rows are mixed in so that every filter of
+wgdi/base.py:178-180 fires.
+
+Two outputs are offered: integer-coded hit arrays (fast path for the benchmark) and real
+gff / lens / m8 / conf files that the unmodified reference can read.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field, replace
+
+import numpy as np
+
+
+@dataclass
+class SynthConfig:
+    name: str
+    seed: int
+    n_anc: int                  # ancestral genes
+    k: int                      # sub-genome copies per genome
+    n_chr1: int
+    n_chr2: int
+    self_cmp: bool              # genome 2 is genome 1
+    target_points: int          # graded points aimed at
+    retention: float = 0.6
+    tandem_frac: float = 0.08
+    grading: tuple = (50, 30, 25)
+    mg: tuple = (25, 25)
+    multiple: int = 1
+    pvalue: float = 1.0
+    repeat_number: int | None = None      # None -> 1.2 x target/genes
+    float_scores: bool = False            # a third of the bit scores get a decimal part
+
+
+# The five BASELINE.json configs (seeds 20260000 + config) and small cases.
+CONFIGS = {
+    "tiny": SynthConfig("tiny", 20260090, n_anc=260, k=2, n_chr1=3, n_chr2=3, self_cmp=True, target_points=6_000),
+    "small": SynthConfig("small", 20260091, n_anc=1100, k=2, n_chr1=4, n_chr2=4, self_cmp=True, target_points=40_000),
+    "cross": SynthConfig("cross", 20260092, n_anc=700, k=2, n_chr1=4, n_chr2=3, self_cmp=False, target_points=12_000,
+                         grading=(60, 35, 20), mg=(40, 30), multiple=2, pvalue=0.3, float_scores=True),
+    "C1": SynthConfig("C1", 20260001, n_anc=23_150, k=2, n_chr1=5, n_chr2=5, self_cmp=True, target_points=1_000_000),
+    "C2": SynthConfig("C2", 20260002, n_anc=15_430, k=3, n_chr1=19, n_chr2=19, self_cmp=True, target_points=2_000_000),
+    "C3": SynthConfig("C3", 20260003, n_anc=30_860, k=2, n_chr1=12, n_chr2=12, self_cmp=False, target_points=5_000_000),
+    "C4": SynthConfig("C4", 20260004, n_anc=56_580, k=3, n_chr1=21, n_chr2=21, self_cmp=True, target_points=10_000_000),
+}
+
+
+@dataclass
+class Genome:
+    prefix: str
+    anc: np.ndarray        # ancestral gene id per gene (genome order)
+    chr_idx: np.ndarray    # 0-based chromosome index per gene
+    order: np.ndarray      # 1-based gene order inside its chromosome
+    strand: np.ndarray     # '+' / '-'
+    chr_names: list
+
+    @property
+    def n(self):
+        return len(self.anc)
+
+    def ids(self):
+        return np.array([f"{self.prefix}{self.chr_names[c]}g{o:05d}" for c, o in zip(self.chr_idx, self.order)],
+                        dtype=object)
+
+
+def _make_genome(rng, cfg: SynthConfig, n_chr: int, prefix: str, chr_names=None) -> Genome:
+    subs = []
+    for _ in range(cfg.k):
+        order = np.flatnonzero(rng.random(cfg.n_anc) < cfg.retention)
+        n_events = max(2, len(order) // 1500)
+        for _ in range(n_events):                         # inversions
+            a, b = np.sort(rng.integers(0, len(order), 2))
+            order[a:b] = order[a:b][::-1].copy()
+        for _ in range(n_events // 2):                    # translocations
+            a, b = np.sort(rng.integers(0, len(order), 2))
+            seg, rest = order[a:b], np.r_[order[:a], order[b:]]
+            at = int(rng.integers(0, len(rest) + 1))
+            order = np.r_[rest[:at], seg, rest[at:]]
+        subs.append(order)
+    anc = np.concatenate(subs)
+    anc = np.repeat(anc, 1 + (rng.random(len(anc)) < cfg.tandem_frac))       # tandem duplicates
+    n = len(anc)
+    # unequal chromosome sizes (+-25 %)
+    w = rng.uniform(0.75, 1.25, n_chr)
+    bounds = np.r_[0, np.round(np.cumsum(w) / w.sum() * n).astype(np.int64)]
+    bounds[-1] = n
+    chr_idx = np.searchsorted(bounds, np.arange(n), side="right") - 1
+    order = np.arange(n) - bounds[chr_idx] + 1
+    strand = np.where(rng.random(n) < 0.5, "+", "-")
+    names = chr_names or [str(i + 1) for i in range(n_chr)]
+    return Genome(prefix, anc.astype(np.int64), chr_idx.astype(np.int64), order.astype(np.int64), strand, names)
+
+
+@dataclass
+class Dataset:
+    cfg: SynthConfig
+    g1: Genome
+    g2: Genome
+    q: np.ndarray          # query gene index (into g1) per BLAST row, file order
+    t: np.ndarray          # subject gene index (into g2)
+    bits: np.ndarray       # bit score (int64, or float64 when cfg.float_scores)
+    evalue: np.ndarray     # float64
+    repeat_number: int
+
+    def options(self, paths=None, savefile="out.collinearity.txt", process=8):
+        """`[collinearity]` options as configparser would return them (all strings)."""
+        p = paths or {}
+        c = self.cfg
+        return [
+            ("gff1", p.get("gff1", "")), ("gff2", p.get("gff2", "")),
+            ("lens1", p.get("lens1", "")), ("lens2", p.get("lens2", "")),
+            ("blast", p.get("blast", "")), ("blast_reverse", "false"),
+            ("comparison", "genomes"), ("multiple", str(c.multiple)), ("process", str(process)),
+            ("evalue", "1e-5"), ("score", "100"),
+            ("grading", ",".join(str(x) for x in c.grading)), ("mg", ",".join(str(x) for x in c.mg)),
+            ("pvalue", repr(float(c.pvalue)) if c.pvalue != 1 else "1"),
+            ("repeat_number", str(self.repeat_number)), ("positon", "order"),
+            ("savefile", savefile),
+        ]
+
+
+def make_dataset(cfg: SynthConfig | str, scale: float = 1.0) -> Dataset:
+    """Build genomes and the raw BLAST table.  `scale` < 1 shrinks genes and hits together
+    (used to take bounded samples of a named workload)."""
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    if scale != 1.0:
+        cfg = replace(cfg, n_anc=max(60, int(cfg.n_anc * scale)), target_points=max(500, int(cfg.target_points * scale)))
+    rng = np.random.default_rng(cfg.seed)
+    g1 = _make_genome(rng, cfg, cfg.n_chr1, "a")
+    g2 = g1 if cfg.self_cmp else _make_genome(rng, cfg, cfg.n_chr2, "b")
+
+    per_gene = cfg.target_points / g1.n
+    repeat_number = cfg.repeat_number or max(6, int(np.ceil(1.2 * per_gene)))
+
+    # --- homeolog hits: every pair of genes descending from the same ancestral gene ---------
+    o2 = np.argsort(g2.anc, kind="stable")
+    start2 = np.searchsorted(g2.anc[o2], np.arange(cfg.n_anc + 1))
+    cnt = (start2[1:] - start2[:-1])[g1.anc]
+    hq = np.repeat(np.arange(g1.n), cnt)
+    within = np.arange(len(hq)) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    ht = o2[start2[g1.anc][hq] + within]
+    hbits = np.clip(rng.normal(600, 150, len(hq)), 100, None)
+    if cfg.self_cmp:                                     # the self hit is the best hit, as in real BLAST
+        hbits = np.where(hq == ht, 2000.0, hbits)
+
+    # --- family / noise hits ---------------------------------------------------------------
+    fam_of_anc = np.minimum(rng.zipf(1.6, cfg.n_anc), 400) * 1000 + rng.integers(0, 60, cfg.n_anc)
+    fam2 = fam_of_anc[g2.anc]
+    f2 = np.argsort(fam2, kind="stable")
+    fam_sorted = fam2[f2]
+    lam = per_gene * 1.12
+    nn = rng.poisson(lam, g1.n)
+    nq = np.repeat(np.arange(g1.n), nn)
+    in_family = rng.random(len(nq)) < 0.35
+    fq = fam_of_anc[g1.anc][nq]
+    lo = np.searchsorted(fam_sorted, fq, side="left")
+    hi = np.searchsorted(fam_sorted, fq, side="right")
+    pick = lo + (rng.random(len(nq)) * np.maximum(hi - lo, 1)).astype(np.int64)
+    nt = np.where(in_family & (hi > lo), f2[np.minimum(pick, g2.n - 1)], rng.integers(0, g2.n, len(nq)))
+    nbits = 100 + rng.exponential(80, len(nq))
+
+    q = np.r_[hq, nq]
+    t = np.r_[ht, nt]
+    bits = np.r_[hbits, nbits]
+    # 5 % sub-threshold rows: half by score, half by evalue
+    ev = np.power(10.0, -np.minimum(bits, 1200) / 4.0)
+    sub = rng.random(len(q))
+    bits = np.where(sub < 0.025, rng.uniform(40, 99.4, len(q)), bits)
+    ev = np.where((sub >= 0.025) & (sub < 0.05), rng.uniform(2e-5, 1e-2, len(q)), ev)
+    ev = np.where((sub >= 0.05) & (sub < 0.052), 1e-5, ev)      # exactly the threshold: strict < drops it
+    if cfg.float_scores:
+        frac = np.where(rng.random(len(q)) < 0.33, 0.5, 0.0)
+        bits = np.round(bits) + frac
+    else:
+        bits = np.round(bits).astype(np.int64)
+    # duplicated (id1, id2) rows with a lower score, placed later in the query's block
+    dup = rng.random(len(q)) < 0.004
+    q = np.r_[q, q[dup]]
+    t = np.r_[t, t[dup]]
+    bits = np.r_[bits, np.maximum(bits[dup] - 7, 30)]
+    ev = np.r_[ev, ev[dup]]
+    # BLAST order: grouped by query, best hit first (stable: ties keep generation order)
+    o = np.lexsort((-bits, q))
+    return Dataset(cfg, g1, g2, q[o], t[o], bits[o], ev[o], repeat_number)
+
+
+def write_dataset(ds: Dataset, outdir: str, savefile: str | None = None, process: int = 8) -> str:
+    """Write gff/lens/m8 files + a conf the unmodified reference can run; returns the conf path."""
+    os.makedirs(outdir, exist_ok=True)
+    paths = {}
+    genomes = [("1", ds.g1)] + ([("2", ds.g2)] if not ds.cfg.self_cmp else [])
+    idcache = {}
+    for tag, g in genomes:
+        ids = g.ids()
+        idcache[tag] = ids
+        gff = os.path.join(outdir, f"genome{tag}.gff")
+        with open(gff, "w") as f:
+            for i in range(g.n):
+                st = 1000 * int(g.order[i])
+                f.write(f"{g.chr_names[g.chr_idx[i]]}\t{ids[i]}\t{st}\t{st + 800}\t{g.strand[i]}\t{int(g.order[i])}\t{ids[i]}.1\n")
+        lens = os.path.join(outdir, f"genome{tag}.lens")
+        with open(lens, "w") as f:
+            for c, name in enumerate(g.chr_names):
+                ng = int((g.chr_idx == c).sum())
+                f.write(f"{name}\t{ng * 1000 + 800}\t{ng}\n")
+        paths[f"gff{tag}"], paths[f"lens{tag}"] = gff, lens
+    if ds.cfg.self_cmp:
+        paths["gff2"], paths["lens2"] = paths["gff1"], paths["lens1"]
+        idcache["2"] = idcache["1"]
+    blast = os.path.join(outdir, "blast.m8")
+    i1, i2 = idcache["1"][ds.q], idcache["2"][ds.t]
+    with open(blast, "w") as f:
+        for a, b, s, e in zip(i1, i2, ds.bits, ds.evalue):
+            sc = f"{s:.1f}" if ds.cfg.float_scores and s != int(s) else f"{int(s)}"
+            f.write(f"{a}\t{b}\t87.50\t200\t20\t2\t1\t200\t1\t200\t{e:.2e}\t{sc}\n")
+    paths["blast"] = blast
+    conf = os.path.join(outdir, "icl.conf")
+    savefile = savefile or os.path.join(outdir, "out.collinearity.txt")
+    with open(conf, "w") as f:
+        f.write("[collinearity]\n")
+        for k, v in ds.options(paths, savefile, process):
+            f.write(f"{k} = {v}\n")
+    return conf
