@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the `wgdi -icl` hot path (BASELINE.json metric: BLAST hits chained per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2]
+
+A "step" is one pass of the hot path over one batch of synthetic input: all chromosome pairs of
+BASELINE.json config 2 (Vitis-sized self comparison, 19 chromosomes -> 361 chromosome pairs, ~2M graded
+BLAST hits) are sorted, chained in both directions, ranked with numpy (the reference's own unstable
+argsort, required for bit-exact tie order) and extracted into blocks with p values.
+
+  value   hits/s with the graded hits already resident in HBM (icl_dp + host rank + icl_extract)
+  e2e     hits/s through the engine's public call with HOST buffers: pinned inputs -> H2D -> ... -> blocks on host
+  roofline  the chaining-DP kernel against the measured HBM bandwidth (it is latency-bound: DESIGN.md)
+  cpu_baseline  the oracle's C restatement of the reference algorithm on all host cores (kind "port")
+
+With N > 1 (torchrun, one rank per GPU) the workload is N such comparisons (seeds differ); their 361*N chromosome
+pairs are pooled and assigned to ranks by longest-processing-time on point count; every rank uploads only its
+pairs; there is no data-path collective (scaling: weak).  NCCL is used for the barrier and the max-over-ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DP_BYTES_PER_POINT = 42          # 2 directions x [12 B read + 9 B written]
+METRIC = "blast_hits_chained_per_sec"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 6 or not c[0].isdigit():
+                continue
+            sm.append(int(c[0])); mx.append(int(c[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_points(workload, seed_shift=0, scale=1.0):
+    from dataclasses import replace
+    from wgdi_b200 import synth
+    cfg = synth.CONFIGS[workload]
+    if seed_shift:
+        cfg = replace(cfg, seed=cfg.seed + 1000 * seed_shift)
+    ds = synth.make_dataset(cfg, scale=scale)
+    pts = synth.graded_points(ds)
+    pts["cfg"] = ds.cfg
+    return pts
+
+
+def params_for(cfg):
+    from wgdi_b200.engine import ChainParams
+    return ChainParams(mg1=cfg.mg[0], mg2=cfg.mg[1], grading=tuple(cfg.grading), pvalue=cfg.pvalue)
+
+
+def cpu_port_pass(pts, prm, threads):
+    """One pass of the oracle's C restatement (chain both directions, numpy rank, extraction) on `threads` cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_oracle, icl_oracle
+    o = np.lexsort((pts["loc2"], pts["loc1"], pts["pair_id"]))
+    off = np.r_[0, np.cumsum(np.bincount(pts["pair_id"], minlength=pts["n_pairs"]))].astype(np.int64)
+    op = icl_oracle.IclParams([("grading", ",".join(map(str, prm.grading))), ("mg", f"{prm.mg1},{prm.mg2}")])
+    l1, l2, g = pts["loc1"][o], pts["loc2"][o], pts["grading"][o]
+    pool = ThreadPoolExecutor(threads) if threads > 1 else None
+    t0 = time.perf_counter()
+    bt = c_oracle.Batch(off, l1, l2, g, op, threads=threads)
+    bt.chain()
+    bt.rank(pool)
+    bt.extract()
+    dt = time.perf_counter() - t0
+    if pool:
+        pool.shutdown()
+    return dt, int(bt.n_blk[0].sum() + bt.n_blk[1].sum())
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's algorithm on the host cores.  The reference is pure Python (6-8 ms per point per core,
+    BASELINE.md) and does not exist on the GPU box, so this arm times the oracle's C port of it (kind "port"),
+    multi-threaded over chromosome pairs like the reference's worker pool."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    c_oracle.build()
+    pts = make_points(args.workload)
+    prm = params_for(pts["cfg"])
+    threads = os.cpu_count() or 1
+    n = len(pts["loc1"])
+    for _ in range(args.warmup):
+        cpu_port_pass(pts, prm, threads)
+    times = [cpu_port_pass(pts, prm, threads)[0] for _ in range(args.steps)]
+    T = float(np.sum(times))
+    value = n * args.steps / T
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "hits/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: BASELINE.json config 2 (Vitis-sized self comparison)", "graded_hits": n,
+                   "chromosome_pairs": pts["n_pairs"]},
+        "cpu_baseline": {"value": value, "unit": "hits/s", "cores": threads, "kind": "port",
+                         "sample": f"full {args.workload} workload per step ({n} hits), C port of the reference algorithm"},
+        "e2e": {"value": value, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from wgdi_b200 import shard
+    from wgdi_b200.engine import IclEngine
+
+    # ---- workload: one comparison per rank, pairs pooled and LPT-sharded over ranks --------------------------
+    mine = make_points(args.workload, seed_shift=rank)
+    prm = params_for(mine["cfg"])
+    if world > 1:
+        shm = f"/dev/shm/icl_bench_{os.environ.get('MASTER_PORT', '0')}"
+        os.makedirs(shm, exist_ok=True)
+        np.savez(os.path.join(shm, f"r{rank}.npz"), pair_id=mine["pair_id"], loc1=mine["loc1"], loc2=mine["loc2"],
+                 grading=mine["grading"], n_pairs=mine["n_pairs"])
+        barrier()
+        parts = [np.load(os.path.join(shm, f"r{r}.npz")) for r in range(world)]
+        base = np.r_[0, np.cumsum([int(p["n_pairs"]) for p in parts])]
+        pooled = dict(pair_id=np.concatenate([p["pair_id"] + base[r] for r, p in enumerate(parts)]).astype(np.int32),
+                      loc1=np.concatenate([p["loc1"] for p in parts]), loc2=np.concatenate([p["loc2"] for p in parts]),
+                      grading=np.concatenate([p["grading"] for p in parts]), n_pairs=int(base[-1]))
+        pts = shard.shard_points(pooled, rank, world)
+        total_points = len(pooled["loc1"])
+        total_pairs = pooled["n_pairs"]
+        del parts, pooled
+    else:
+        pts = mine
+        total_points = len(pts["loc1"])
+        total_pairs = pts["n_pairs"]
+    n_local = len(pts["loc1"])
+
+    eng = IclEngine(local)
+    # inputs in page-locked host memory (the e2e leg copies them every step)
+    host_in = {}
+    for k in ("pair_id", "loc1", "loc2", "grading"):
+        buf = eng._buf("in_" + k, n_local, np.int32)
+        buf[:] = pts[k]
+        host_in[k] = buf
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    dev_ms = {}
+
+    def step_resident():
+        blocks = eng.run_resident(prm)
+        for k, v in eng.timings().items():
+            dev_ms.setdefault(k, []).append(v)
+        dev_ms.setdefault("host_rank", []).append(eng.host_ms["rank"])
+        return blocks
+
+    def step_e2e():
+        return eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------------------
+    eng.upload(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"])
+    for _ in range(args.warmup):
+        step_resident()
+    dev_ms.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_res = 0.0
+    blocks = None
+    for _ in range(args.steps):
+        flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        blocks = step_resident()
+        torch.cuda.synchronize()
+        t_res += time.perf_counter() - t0
+    # ---- e2e: host buffers in, blocks on the host out ----------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        blocks = step_e2e()
+        torch.cuda.synchronize()
+        t_e2e += time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    counters = eng.counters()
+
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = t.tolist()
+        nb = torch.tensor([len(blocks)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(nb)
+        n_blocks = int(nb.item())
+    else:
+        n_blocks = len(blocks)
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        chain_ms = float(np.mean(dev_ms["chain"]))
+        achieved = DP_BYTES_PER_POINT * n_local / (chain_ms * 1e-3) / 1e9
+        d2h = 16 * n_local + int(len(blocks) * 64 + len(blocks.loc1) * 12)
+        line = {
+            "metric": METRIC, "value": total_points * args.steps / t_res, "unit": "hits/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: BASELINE.json config 2 (Vitis-sized self comparison), one comparison per GPU",
+                       "graded_hits": total_points, "chromosome_pairs": total_pairs, "blocks": n_blocks,
+                       "mg": list(mine["cfg"].mg), "grading": list(mine["cfg"].grading),
+                       "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
+                       "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
+                       "tie_order": "numpy argsort on host between the two device phases (reference-exact)"},
+            "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "h2d_bytes_per_step": 24 * n_local, "d2h_bytes_per_step": d2h},
+            "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
+            "roofline": {"kernel": "chain DP (both directions)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "kernel_ms": chain_ms, "algorithmic_bytes": DP_BYTES_PER_POINT * n_local,
+                         "note": "latency-bound integer DP with a serial dependency chain; see DESIGN.md"},
+            "phase_ms": {k: float(np.mean(v)) for k, v in dev_ms.items()},
+            "edges_per_step": counters["edges"],
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import c_oracle
+            c_oracle.build()
+            threads = os.cpu_count() or 1
+            cpu_port_pass(mine, prm, threads)
+            dt, nb_cpu = cpu_port_pass(mine, prm, threads)
+            line["cpu_baseline"] = {"value": len(mine["loc1"]) / dt, "unit": "hits/s", "cores": threads, "kind": "port",
+                                    "sample": f"full {args.workload} workload, 1 pass ({len(mine['loc1'])} hits, {nb_cpu} blocks), "
+                                              "oracle C port of the reference algorithm, pthread pool over chromosome pairs"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/*
+ * icl_b200.h — C ABI of the B200-native `wgdi -icl` chaining engine.
+ *
+ * The reference (SunPengChuan/wgdi 0.75) is pure Python and has no FFI; the seam this library
+ * replaces is the per-chromosome-pair call
+ *
+ *     collinearity(options, points).run()            wgdi/collinearity.py:5-70
+ *
+ * made from mycollinearity.single_pool (wgdi/run_colliearity.py:158-170) inside
+ * multiprocessing workers (wgdi/run_colliearity.py:123-136).  Instead of one Python call per
+ * chromosome pair, ALL pairs of a comparison are uploaded once and processed by CUDA kernels
+ * (sm_100a).  The binding a maintainer of the reference would add is the ctypes stub shown in
+ * INTEGRATION.md; wgdi_b200/_lib.py is the same stub as shipped here.
+ *
+ * Call sequence (one icl_ctx per GPU; a ctx is not thread-safe):
+ *
+ *   icl_create -> icl_upload -> icl_dp -> [host: numpy argsort of the scores] -> icl_extract
+ *              -> icl_free_blocks ... -> icl_destroy
+ *
+ * The split into icl_dp / icl_extract exists because the reference orders block extraction with
+ * pandas' sort_values(by=['score1'], ascending=False) (wgdi/collinearity.py:49,60), i.e. numpy's
+ * UNSTABLE argsort(kind='quicksort') whose tie permutation depends on the numpy build and the CPU
+ * (SURVEY.md hazard H1).  Bit-exact output therefore needs that very numpy call between the two
+ * device phases; the library never sorts scores itself.
+ *
+ * All functions return ICL_OK (0) or a negative error code; icl_last_error() gives the message.
+ * No exceptions cross the boundary.  Host input arrays are caller-owned and only read during the
+ * call; icl_blocks arrays are library-owned until icl_free_blocks().
+ */
+#ifndef ICL_B200_H
+#define ICL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICL_OK 0
+#define ICL_ERR_ARG (-1)    /* bad argument (null pointer, negative size, pair id out of range, ...) */
+#define ICL_ERR_CUDA (-2)   /* a CUDA runtime call failed; message holds cudaGetErrorString */
+#define ICL_ERR_STATE (-3)  /* call sequence violated (e.g. icl_extract before icl_dp) */
+#define ICL_ERR_LIMIT (-4)  /* input exceeds a documented limit (see icl_upload / icl_dp) */
+#define ICL_ERR_NOMEM (-5)  /* host allocation failed */
+
+typedef struct icl_ctx icl_ctx;
+
+/* Parameters of the DP engine: the typed subset of the `[collinearity]` options that
+ * wgdi/collinearity.py:6-28 parses.  gap_penalty is fixed at -1 (collinearity.py:8). */
+typedef struct icl_params {
+    int32_t mg1;             /* `mg` first value: window on loc1, exclusive (collinearity.py:24,76-79); 2..255 */
+    int32_t mg2;             /* `mg` second value: window on loc2; 2..255 */
+    int32_t g0;              /* grading[0], divisor in the p value (collinearity.py:152) */
+    int32_t over_gap;        /* minimum path length of a block, 3 in the reference (collinearity.py:13,129) */
+    double coverage_ratio;   /* collinearity.py:16,129 (strict >) */
+} icl_params;
+
+/* Blocks in the reference's emission order: chromosome pair ascending (the caller numbers pairs in
+ * the sorted (chr1, chr2) string order of wgdi/run_colliearity.py:118), forward blocks before
+ * anti-diagonal blocks (collinearity.py:49-68), acceptance order inside a direction.
+ * EVERY accepted block is returned (length >= over_gap); the caller applies
+ *   p = round(p_raw, 4); drop if p > pvalue      wgdi/collinearity.py:153,55-56
+ *   drop if m < 5                                wgdi/run_colliearity.py:178
+ * because those filters do not feed back into the extraction. */
+typedef struct icl_blocks {
+    int64_t n_blocks;
+    int64_t n_members;
+    int32_t *pair;        /* [n_blocks] chromosome-pair id as given to icl_upload */
+    int32_t *dir;         /* [n_blocks] 0 = forward (score1/path1), 1 = anti-diagonal (score2/path2) */
+    int64_t *score;       /* [n_blocks] score of the block's top point (full path score) */
+    int32_t *m;           /* [n_blocks] number of gene pairs in the block (len(self.path)) */
+    int32_t *L;           /* [n_blocks] full path length (self.over_length) */
+    int32_t *N;           /* [n_blocks] points inside the block's bounding box (collinearity.py:149) */
+    int64_t *N1;          /* [n_blocks] sum of `times` inside the box before the bump (collinearity.py:148) */
+    int32_t *L1;          /* [n_blocks] loc1 extent of the box */
+    int32_t *L2;          /* [n_blocks] loc2 extent of the box */
+    double *p_raw;        /* [n_blocks] unrounded p value `a` of collinearity.py:152 (binary64, left to right) */
+    int64_t *member_off;  /* [n_blocks + 1] offsets into loc1/loc2/member_idx */
+    int32_t *loc1;        /* [n_members] gene-order coordinate on genome 1, ascending inside a block */
+    int32_t *loc2;        /* [n_members] gene-order coordinate on genome 2 */
+    int32_t *member_idx;  /* [n_members] index of the point in the arrays given to icl_upload */
+} icl_blocks;
+
+/* Create a context on CUDA device `device`.  Fails with ICL_ERR_CUDA when no device is usable:
+ * there is no CPU fallback. */
+int icl_create(int device, icl_ctx **ctx);
+void icl_destroy(icl_ctx *ctx);
+
+/* Message of the most recent error on `ctx` (or of the last failed icl_create when ctx is NULL). */
+const char *icl_last_error(const icl_ctx *ctx);
+
+/* Page-locked host memory for the score / order arrays that cross PCIe between the two phases. */
+int icl_host_alloc(icl_ctx *ctx, int64_t bytes, void **ptr);
+int icl_host_free(icl_ctx *ctx, void *ptr);
+
+/*
+ * Copy the graded points of one comparison to the device (replaces the per-pair DataFrames that
+ * wgdi/run_colliearity.py:117-136 pickles to its workers).  Arrays are in any order (normally BLAST
+ * file order); pair_id[i] in [0, n_pairs).  The device orders the points of every pair by
+ * (loc1, loc2) with a stable radix sort, i.e. equal coordinates keep upload order like the stable
+ * lexsort of wgdi/run_colliearity.py:164-166.
+ * Limits: 0 <= loc < 2^26, n_points < 2^30, bits(n_pairs) + bits(max loc1) + bits(max loc2) <= 64.
+ */
+int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
+               const int32_t *pair_id, const int32_t *loc1, const int32_t *loc2, const int32_t *grading);
+
+/*
+ * Sort + chaining DP in both directions (wgdi/collinearity.py:72-115: forward :74-93, anti-diagonal
+ * :96-115).  Writes the final scores as int64, in (pair, loc1, loc2) order, into caller buffers of
+ * n_points elements — exactly the arrays the reference hands to numpy's argsort through pandas
+ * (collinearity.py:49,60).  May be called repeatedly on the same upload (e.g. a parameter sweep).
+ */
+int icl_dp(icl_ctx *ctx, const icl_params *params, int64_t *score_fwd, int64_t *score_rev);
+
+/* Layout produced by icl_dp: pair_off[n_pairs + 1] (points of pair p are sorted positions
+ * pair_off[p] .. pair_off[p+1]) and perm[n_points] (upload index of each sorted position).
+ * Either pointer may be NULL. */
+int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
+
+/*
+ * Block extraction + p values (wgdi/collinearity.py:42-70, 117-153).
+ * order_fwd / order_rev: for every pair segment pair_off[p]..pair_off[p+1] the pair-LOCAL indices of
+ * its points in the order pandas would examine them, i.e.
+ *     nargsort(score[pair segment], kind='quicksort', ascending=False)
+ * computed by the caller with numpy on the arrays icl_dp returned.
+ */
+int icl_extract(icl_ctx *ctx, const int32_t *order_fwd, const int32_t *order_rev, icl_blocks *out);
+void icl_free_blocks(icl_blocks *blocks);
+
+/* Test / diagnostics: DP state of one direction (0 forward, 1 anti-diagonal) in sorted point order.
+ * pred = sorted position of the last updating source (-1 for path roots), depth = path length,
+ * used = (usedtimes > 0).  Any pointer may be NULL. */
+int icl_debug_dp(icl_ctx *ctx, int32_t dir, int32_t *score, int32_t *pred, int32_t *depth, uint8_t *used);
+
+/* Device time (ms, CUDA events on the context's stream) of the phases of the most recent
+ * icl_dp / icl_extract calls; see ICL_T_* for the slots.  Returns the number of slots written. */
+#define ICL_T_SORT 0      /* key build + radix sort + layout */
+#define ICL_T_SETUP 1     /* row index, mirrored copy */
+#define ICL_T_EDGES 2     /* candidate (edge) enumeration */
+#define ICL_T_CHAIN 3     /* chaining DP, both directions */
+#define ICL_T_EXPORT 4    /* score export + D2H */
+#define ICL_T_EXTRACT 5   /* block extraction */
+#define ICL_T_PVALUE 6    /* times / p-value pass */
+#define ICL_T_GATHER 7    /* output compaction + D2H */
+#define ICL_T_COUNT 8
+int icl_timings(icl_ctx *ctx, double *ms, int32_t n_slots);
+
+/* Counters of the most recent icl_dp: [0] edges enumerated, [1] kernels launched by icl_dp,
+ * [2] kernels launched by icl_extract, [3] total dense rows. */
+int icl_counters(icl_ctx *ctx, int64_t *out, int32_t n_slots);
+
+/* "cuda" for the real library.  (A CPU emulation of the kernel bodies exists for the test-suite
+ * only and reports "emu"; wgdi_b200 refuses to load it.) */
+const char *icl_backend(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICL_B200_H */

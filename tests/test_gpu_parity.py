@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI) against the reference-generated fixtures and the oracle.
+Everything here needs a B200: run with `-m gpu`."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import (PORTABLE_ENV, ROOT, check_blocks_against_golden, check_dp_against_golden, oracle_batch,
+                      oracle_blocks, sorted_layout, stage_e2e)
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_with_oracle(blocks, exp):
+    assert len(blocks) == len(exp)
+    for b, (pair, d, l1, l2, a, sc) in enumerate(exp):
+        a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
+        assert blocks.pair[b] == pair and blocks.dir[b] == d and blocks.score[b] == sc, b
+        assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all(), b
+        assert blocks.p_raw[b] == a, (b, blocks.p_raw[b], a)       # fp64 bit-exact (tolerance stated: 0; spec allows 1e-9 rel)
+
+
+def test_backend_is_cuda(gpu_engine):
+    assert gpu_engine.lib.icl_backend() == b"cuda"
+
+
+def test_golden_clouds_dp_and_blocks(gpu_engine, clouds):
+    """Inner seam against the unmodified reference: DP state of both directions, then extraction + p values
+    driven by the tie order the reference used."""
+    from wgdi_b200.engine import ChainParams
+    eng = gpu_engine
+    for c in clouds:
+        n = len(c["loc1"])
+        prm = ChainParams.from_options(c["options"])
+        rng = np.random.default_rng(c["case"])
+        perm = np.arange(n) if c["case"] % 11 == 5 else rng.permutation(n)      # duplicates keep upload order (H22)
+        eng.upload(np.zeros(n, np.int32), c["loc1"][perm], c["loc2"][perm], c["grading"][perm], 1)
+        sf, sr = eng.dp(prm)
+        assert (sf == c["score1"]).all() and (sr == c["score2"]).all()
+        check_dp_against_golden(eng.debug_dp, c)
+        blocks = eng.extract(c["order1"].astype(np.int32), c["order2"].astype(np.int32))
+        check_blocks_against_golden(blocks, prm.pvalue, c)
+
+
+def test_all_clouds_as_one_batch(gpu_engine, clouds):
+    """The same clouds uploaded together as chromosome pairs of one comparison (shared parameters)."""
+    from wgdi_b200.engine import ChainParams
+    cs = [c for c in clouds if len(c["loc1"]) > 0]
+    pid = np.concatenate([np.full(len(c["loc1"]), i, np.int32) for i, c in enumerate(cs)])
+    pts = dict(pair_id=pid, loc1=np.concatenate([c["loc1"] for c in cs]).astype(np.int32),
+               loc2=np.concatenate([c["loc2"] for c in cs]).astype(np.int32),
+               grading=np.concatenate([c["grading"] for c in cs]).astype(np.int32), n_pairs=len(cs))
+    rng = np.random.default_rng(7)
+    sh = rng.permutation(len(pid))
+    for mg in ((25, 25), (40, 30), (7, 50)):
+        prm = ChainParams(mg1=mg[0], mg2=mg[1], grading=(50, 30, 25), coverage_ratio=0.8)
+        up = {k: (v[sh] if isinstance(v, np.ndarray) else v) for k, v in pts.items()}
+        # equal (loc1, loc2) must keep upload order: sort the shuffle inside duplicates away by using the oracle on
+        # the uploaded order itself
+        blocks = gpu_engine.chain(up["pair_id"], up["loc1"], up["loc2"], up["grading"], up["n_pairs"], prm)
+        _compare_with_oracle(blocks, oracle_blocks(up, prm))
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "cross"])
+def test_synthetic_comparison_matches_oracle(gpu_engine, name):
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    ds = synth.make_dataset(name)
+    pts = synth.graded_points(ds)
+    c = ds.cfg
+    prm = ChainParams(mg1=c.mg[0], mg2=c.mg[1], grading=tuple(c.grading), pvalue=c.pvalue)
+    blocks = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    exp = oracle_blocks(pts, prm)
+    assert len(exp) > 10
+    _compare_with_oracle(blocks, exp)
+    # DP state as well
+    bt, (off, l1, l2, g, o) = oracle_batch(pts, prm)
+    for d in (0, 1):
+        s, p, dp, u = gpu_engine.debug_dp(d)
+        assert (s == bt.dp[d]["score"]).all() and (u == bt.dp[d]["used"]).all()
+        # oracle pred is pair-local
+        pred_global = np.where(bt.dp[d]["pred"] >= 0, bt.dp[d]["pred"] + np.repeat(off[:-1], np.diff(off)), -1)
+        assert (p == pred_global).all() and (dp == bt.dp[d]["depth"]).all()
+
+
+_E2E_CHILD = r"""
+import sys, hashlib, json, io, contextlib, numpy as np
+sys.path.insert(0, %r)
+fp = hashlib.md5(np.argsort((np.arange(1000) * 7919 %% 5).astype(np.int64), kind="quicksort").tobytes()).hexdigest()
+if fp != json.load(open("meta.json"))["argsort_fingerprint"]:
+    print("SKIP fingerprint", fp); sys.exit(0)
+from wgdi_b200 import _lib, base
+from wgdi_b200.run_colliearity import mycollinearity
+conf = open("icl.conf").read().replace("expected.collinearity.txt", "got.txt")
+open("icl.conf", "w").write(conf)
+with contextlib.redirect_stdout(io.StringIO()):
+    try:
+        mycollinearity(base.load_conf("icl.conf", "collinearity")).run()
+    except SystemExit as e:
+        assert e.code == 0
+assert _lib.load().icl_backend() == b"cuda"
+print("OK" if open("got.txt").read() == open("expected.collinearity.txt").read() else "MISMATCH")
+"""
+
+
+@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev"])
+def test_drop_in_driver_writes_reference_file(case):
+    """Outer seam, conf in -> file out, byte-identical to what the unmodified reference wrote."""
+    with tempfile.TemporaryDirectory() as d:
+        stage_e2e(case, d)
+        env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+        r = subprocess.run([sys.executable, "-c", _E2E_CHILD % ROOT], cwd=d, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        if r.stdout.startswith("SKIP"):
+            pytest.skip("numpy scalar-sort fingerprint differs on this machine: " + r.stdout)
+        assert r.stdout.strip() == "OK", r.stdout + r.stderr
+
+
+def test_cli_end_to_end():
+    with tempfile.TemporaryDirectory() as d:
+        stage_e2e("tiny", d)
+        conf = open(os.path.join(d, "icl.conf")).read().replace("expected.collinearity.txt", "got.txt")
+        open(os.path.join(d, "icl.conf"), "w").write(conf)
+        env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-m", "wgdi_b200", "-icl", "icl.conf"], cwd=d, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "The filtered homologous gene pairs are" in r.stdout and "Running 1 vs 1" in r.stdout
+        got = open(os.path.join(d, "got.txt")).read()
+        assert got.startswith("# Alignment 1: score=")
+
+
+def test_inner_seam_class(gpu_engine, clouds):
+    """`collinearity(options, points).run()` returns the reference's structure."""
+    import pandas as pd
+    from oracle import c_oracle, icl_oracle
+    from wgdi_b200.collinearity import collinearity
+    for c in clouds[10:20]:
+        n = len(c["loc1"])
+        labels = np.arange(500, 500 + n)[::-1]
+        points = pd.DataFrame({"loc1": c["loc1"], "loc2": c["loc2"], "grading": c["grading"]}, index=labels)
+        data = collinearity(c["options"], points).run()
+        exp = c_oracle.collinearity_run(c["loc1"], c["loc2"], c["grading"], icl_oracle.IclParams(c["options"]))
+        assert len(data) == len(exp)
+        for (frame, p, score), (b1, b2, ep, esc, _d) in zip(data, exp):
+            assert list(frame.columns) == ["loc1", "loc2"]
+            assert (frame["loc1"].to_numpy() == b1).all() and (frame["loc2"].to_numpy() == b2).all()
+            assert p == ep and score == esc
+            # index carries the caller's row labels
+            assert (points.loc[frame.index, "loc1"].to_numpy() == b1).all()
+
+
+def test_edge_cases(gpu_engine):
+    from wgdi_b200._lib import IclError
+    from wgdi_b200.engine import ChainParams
+    eng = gpu_engine
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    z = np.zeros(0, np.int32)
+    # empty comparison
+    assert len(eng.chain(z, z, z, z, 0, prm)) == 0
+    assert len(eng.chain(z, z, z, z, 3, prm)) == 0
+    # one point, two points on a diagonal, three points = the smallest block
+    one = np.array([0], np.int32)
+    assert len(eng.chain(one, one + 5, one + 5, one + 50, 1, prm)) == 0
+    tri = eng.chain(np.zeros(3, np.int32), np.array([1, 2, 3], np.int32), np.array([1, 2, 3], np.int32),
+                    np.full(3, 50, np.int32), 1, prm)
+    assert len(tri) == 1 and tri.m[0] == 3 and tri.score[0] == 50 + 48 + 48 and tri.N[0] == 3
+    # pairs without points between pairs with points (ragged input)
+    pid = np.array([4, 4, 4, 0, 0, 0], np.int32)
+    l = np.array([1, 2, 3, 7, 8, 9], np.int32)
+    b = eng.chain(pid, l, l, np.full(6, 50, np.int32), 6, prm)
+    assert b.pair.tolist() == [0, 4]
+    # anti-diagonal only
+    b = eng.chain(np.zeros(4, np.int32), np.array([1, 2, 3, 4], np.int32), np.array([9, 8, 7, 6], np.int32),
+                  np.full(4, 50, np.int32), 1, prm)
+    assert b.dir.tolist() == [1] and b.loc1[:4].tolist() == [1, 2, 3, 4] and b.loc2[:4].tolist() == [9, 8, 7, 6]
+    # error behaviour: codes, not crashes
+    with pytest.raises(IclError) as e:
+        eng.upload(np.array([2], np.int32), one, one, one, 2)
+    assert e.value.code == -1
+    with pytest.raises(IclError) as e:
+        eng.upload(np.array([0], np.int32), -one - 1, one, one, 1)
+    assert e.value.code == -1
+    eng.upload(np.zeros(3, np.int32), l[:3], l[:3], np.full(3, 50, np.int32), 1)
+    with pytest.raises(IclError) as e:
+        eng.extract(np.zeros(3, np.int32), np.zeros(3, np.int32))
+    assert e.value.code == -3                                   # extract before dp
+    with pytest.raises(IclError) as e:
+        eng.dp(ChainParams(mg1=300, mg2=25))
+    assert e.value.code == -4
+    eng.dp(prm)
+    with pytest.raises(IclError) as e:
+        eng.extract(np.array([0, 1, 7], np.int32), np.array([0, 1, 2], np.int32))
+    assert e.value.code == -1                                   # order index outside its pair
+
+
+def test_window_bounds_are_exclusive(gpu_engine):
+    """Offsets 1..mg-1 chain, offset mg does not (collinearity.py:76-79), in both directions."""
+    from wgdi_b200.engine import ChainParams
+    for mg1, mg2 in ((5, 9), (9, 5)):
+        prm = ChainParams(mg1=mg1, mg2=mg2, grading=(50, 30, 25))
+        for dr, dc, linked in ((mg1 - 1, mg2 - 1, True), (mg1, 1, False), (1, mg2, False)):
+            l1 = np.array([10, 10 + dr], np.int32)
+            l2 = np.array([10, 10 + dc], np.int32)
+            gpu_engine.upload(np.zeros(2, np.int32), l1, l2, np.full(2, 50, np.int32), 1)
+            sf, _ = gpu_engine.dp(prm)
+            assert (sf[1] == 100 - dr - dc) == linked and (linked or sf[1] == 50)
+
+
+def test_sharded_equals_unsharded(gpu_engine):
+    """Chromosome pairs split over 2 and 3 ranks by LPT (ranks emulated one after another on this GPU)."""
+    from wgdi_b200 import shard, synth
+    from wgdi_b200.engine import ChainParams
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    whole = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            sp = shard.shard_points(pts, r, world)
+            b = gpu_engine.chain(sp["pair_id"], sp["loc1"], sp["loc2"], sp["grading"], sp["n_pairs"], prm)
+            b.pair = sp["global_pair"][b.pair]
+            b.member_idx = sp["rows"][b.member_idx].astype(np.int32)
+            parts.append(b)
+        merged = shard.merge_blocks(parts)
+        for f in ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
+            assert (getattr(merged, f) == getattr(whole, f)).all(), f
+
+
+def test_full_size_C2_matches_oracle_and_properties(gpu_engine):
+    """BASELINE.json config 2 (Vitis-sized self comparison, ~2M graded hits) at full size: identical to the C oracle,
+    plus size-independent properties."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    ds = synth.make_dataset("C2")
+    pts = synth.graded_points(ds)
+    assert pts["n_pairs"] == 361 and len(pts["loc1"]) > 1_500_000
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    blocks = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    again = gpu_engine.run_resident(prm)                          # idempotent on resident inputs
+    for f in ("pair", "dir", "score", "m", "p_raw", "member_off", "loc1", "loc2"):
+        assert (getattr(again, f) == getattr(blocks, f)).all()
+    _compare_with_oracle(blocks, oracle_blocks(pts, prm))
+    # properties: members ascend on loc1; forward blocks ascend / anti-diagonal descend on loc2; every point is in at
+    # most one block per direction; m <= L; N >= m; blocks ordered by (pair, dir)
+    seg = np.repeat(np.arange(len(blocks)), blocks.m)
+    d1 = np.diff(blocks.loc1.astype(np.int64)); d2 = np.diff(blocks.loc2.astype(np.int64)); same = np.diff(seg) == 0
+    assert (d1[same] > 0).all()
+    assert (d2[same & (blocks.dir[seg][1:] == 0)] > 0).all() and (d2[same & (blocks.dir[seg][1:] == 1)] < 0).all()
+    key = blocks.dir[seg].astype(np.int64) * len(pts["loc1"]) + blocks.member_idx
+    assert len(np.unique(key)) == len(key)
+    assert (blocks.m <= blocks.L).all() and (blocks.N >= blocks.m).all() and (blocks.m >= 3).all()
+    order_key = blocks.pair.astype(np.int64) * 2 + blocks.dir
+    assert (np.diff(order_key) >= 0).all()

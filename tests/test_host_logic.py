@@ -1,0 +1,194 @@
+"""Host-side logic and the ABI surface, without a GPU.  Device work is served by the `emu_backend`
+fixture (a g++ build of the same kernel bodies, injected by the test as a fake backend)."""
+import ctypes
+import io
+import contextlib
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, PORTABLE_ENV, ROOT, check_blocks_against_golden, check_dp_against_golden, stage_e2e
+from oracle import c_oracle, icl_oracle
+
+
+def test_library_exports_every_declared_symbol():
+    """The CUDA .so loads (no device needed) and exports exactly what include/icl_b200.h declares."""
+    from wgdi_b200 import _lib, build
+    so = build.build()
+    lib = ctypes.CDLL(so)
+    header = open(os.path.join(ROOT, "include", "icl_b200.h")).read()
+    declared = set(re.findall(r"\b(icl_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.icl_backend.restype = ctypes.c_char_p
+    assert lib.icl_backend() == b"cuda"
+
+
+def test_no_gpu_means_loud_failure():
+    """Without a device the product path raises; it does not fall back to anything."""
+    from conftest import have_gpu
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    from wgdi_b200 import _lib
+    from wgdi_b200.engine import IclEngine
+    _lib._LIB = None
+    with pytest.raises(_lib.IclError):
+        IclEngine(0)
+    _lib._LIB = None
+
+
+def test_package_refuses_emulation_library(tmp_path, monkeypatch):
+    from wgdi_b200 import _lib, build
+    so = build.build_emu(os.path.join(ROOT, "tests", "_emu"))
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", so)
+    with pytest.raises(_lib.IclError):
+        _lib.load()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "wgdi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "libicl_oracle" not in src, f
+
+
+def test_grade_hits_matches_oracle_with_ties():
+    from wgdi_b200.ingest import grade_hits
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        n, nq = int(rng.integers(1, 400)), int(rng.integers(1, 30))
+        q = rng.integers(0, nq, n)
+        bits = rng.integers(100, 104 + trial % 7 * 20, n).astype(np.int64 if trial % 3 else np.float64)
+        mult, rn = int(rng.integers(0, 4)), int(rng.integers(1, 25))
+        assert (grade_hits(q, bits, mult, rn, [50, 30, 25]) == icl_oracle.grade_hits(q, bits, mult, rn, [50, 30, 25])).all()
+
+
+def test_pair_ids_follow_string_order():
+    from wgdi_b200.ingest import pair_ids
+    names1, names2 = ["1", "10", "2", "B2"], ["1", "2", "3"]
+    c1 = np.array([0, 1, 2, 3, 1, 0]); c2 = np.array([0, 2, 1, 0, 2, 1])
+    pid, names = pair_ids(names1, names2, c1, c2)
+    assert names == sorted(names)
+    assert names == [("1", "1"), ("1", "2"), ("10", "3"), ("2", "2"), ("B2", "1")]
+    assert [names[p] for p in pid] == [(names1[a], names2[b]) for a, b in zip(c1, c2)]
+
+
+def test_nargsort_desc_is_pandas():
+    import pandas as pd
+    from wgdi_b200.engine import nargsort_desc
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 16, 33, 500, 5000):
+        a = rng.integers(0, 9, n).astype(np.int64)
+        exp = pd.DataFrame({"s": a}).sort_values(by=["s"], ascending=False).index.to_numpy()
+        assert (nargsort_desc(a) == exp).all()
+
+
+def test_lpt_assignment_balances():
+    from wgdi_b200.shard import lpt_assign
+    rng = np.random.default_rng(0)
+    sizes = (rng.pareto(1.2, 441) * 1000 + 50).astype(np.int64)
+    for bins in (1, 2, 4, 8):
+        owner = lpt_assign(sizes, bins)
+        load = np.bincount(owner, weights=sizes, minlength=bins)
+        assert load.max() <= sizes.sum() / bins + sizes.max()
+        assert set(owner.tolist()) <= set(range(bins))
+
+
+# ---- the whole host pipeline through the fake backend -----------------------------------------------
+
+def test_pipeline_on_golden_clouds_emu(emu_backend, clouds):
+    from wgdi_b200.engine import ChainParams, IclEngine
+    eng = IclEngine(0, sort_threads=1)
+    try:
+        for c in clouds:
+            n = len(c["loc1"])
+            prm = ChainParams.from_options(c["options"])
+            eng.upload(np.zeros(n, np.int32), c["loc1"], c["loc2"], c["grading"], 1)
+            eng.dp(prm)
+            check_dp_against_golden(lambda d: (lambda s, p, dp, u: (s, p, dp, u))(*eng.debug_dp(d)), c)
+            blocks = eng.extract(c["order1"].astype(np.int32), c["order2"].astype(np.int32))
+            check_blocks_against_golden(blocks, prm.pvalue, c)
+    finally:
+        eng.close()
+
+
+def test_multi_pair_batch_matches_c_oracle_emu(emu_backend):
+    """All chromosome pairs of a synthetic comparison in one upload vs the C oracle pair by pair."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    from conftest import oracle_blocks
+    ds = synth.make_dataset("tiny")
+    pts = synth.graded_points(ds)
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        blocks = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+        off, perm = eng.layout()
+    finally:
+        eng.close()
+    exp = oracle_blocks(pts, prm)
+    assert len(exp) == len(blocks) and len(blocks) > 20
+    for b, (pair, d, l1, l2, a, sc) in enumerate(exp):
+        a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
+        assert blocks.pair[b] == pair and blocks.dir[b] == d and blocks.score[b] == sc
+        assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all()
+        assert blocks.p_raw[b] == a
+
+
+_E2E_CHILD = r"""
+import sys, hashlib, json, ctypes, io, contextlib, numpy as np
+sys.path.insert(0, %r)
+fp = hashlib.md5(np.argsort((np.arange(1000) * 7919 %% 5).astype(np.int64), kind="quicksort").tobytes()).hexdigest()
+if fp != json.load(open("meta.json"))["argsort_fingerprint"]:
+    print("SKIP fingerprint", fp); sys.exit(0)
+from wgdi_b200 import _lib, base
+emu = %r
+if emu:
+    _lib._LIB = _lib._declare(ctypes.CDLL(emu))     # fake backend injected by the test
+from wgdi_b200.run_colliearity import mycollinearity
+conf = open("icl.conf").read().replace("expected.collinearity.txt", "got.txt")
+open("icl.conf", "w").write(conf)
+with contextlib.redirect_stdout(io.StringIO()):
+    try:
+        mycollinearity(base.load_conf("icl.conf", "collinearity")).run()
+    except SystemExit as e:
+        assert e.code == 0
+print("OK" if open("got.txt").read() == open("expected.collinearity.txt").read() else "MISMATCH")
+"""
+
+
+def run_e2e_child(case, emu_path):
+    with tempfile.TemporaryDirectory() as d:
+        stage_e2e(case, d)
+        env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+        r = subprocess.run([sys.executable, "-c", _E2E_CHILD % (ROOT, emu_path)], cwd=d, env=env,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        if r.stdout.startswith("SKIP"):
+            pytest.skip("numpy scalar-sort fingerprint differs on this machine: " + r.stdout)
+        assert r.stdout.strip() == "OK", r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev"])
+def test_drop_in_driver_writes_reference_file_emu(case):
+    """`mycollinearity(options).run()` (host parsing, grading, grouping, formatting) on the fake backend
+    reproduces the file the unmodified reference wrote."""
+    from wgdi_b200 import build
+    run_e2e_child(case, build.build_emu(os.path.join(ROOT, "tests", "_emu")))
+
+
+def test_cli_prints_example_and_missing_conf(capsys):
+    from wgdi_b200.run import main
+    assert main(["-icl", "?"]) == 0
+    assert "[collinearity]" in capsys.readouterr().out
+    assert main(["-icl", "/nonexistent.conf"]) == 0
+    assert "not exists" in capsys.readouterr().out

@@ -1,0 +1,57 @@
+"""Build the CUDA library in-tree: wgdi_b200/libicl_b200.so (sm_100a only).
+
+    python -m wgdi_b200.build            # nvcc, cross-compiles without a GPU
+    python -m wgdi_b200.build --emu DIR  # test-suite only: host emulation of the kernel bodies (g++)
+
+The emulation library is written outside the package (tests/_emu/) and is never loaded by wgdi_b200.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "icl_b200.cu")
+DEPS = [SRC, os.path.join(HERE, "csrc", "icl_platform.h"), os.path.join(os.path.dirname(HERE), "include", "icl_b200.h")]
+OUT = os.path.join(HERE, "libicl_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+]
+
+
+def _stale(out, deps):
+    return not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale(OUT, DEPS):
+        return OUT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++", "-o", OUT, SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return OUT
+
+
+def build_emu(outdir, force=False):
+    os.makedirs(outdir, exist_ok=True)
+    out = os.path.join(outdir, "libicl_b200_emu.so")
+    if not force and not _stale(out, DEPS):
+        return out
+    cmd = ["/usr/bin/g++", "-x", "c++", "-std=c++17", "-O2", "-DICL_EMU", "-fPIC", "-shared", "-o", out, SRC]
+    subprocess.check_call(cmd)
+    return out
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--emu":
+        print(build_emu(sys.argv[2], force=True))
+    else:
+        print(build(force=True, verbose=True))

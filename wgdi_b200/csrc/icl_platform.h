@@ -1,0 +1,212 @@
+// icl_platform.h — thin device layer of the icl_b200 library.
+//
+// Real build (nvcc, sm_100a): CUDA runtime + CUB.
+// ICL_EMU build (g++, test-suite only): the same kernel bodies run as host loops so that the
+// host-side logic (layout, compaction, ABI) can be exercised on a machine without a GPU.  The
+// emulation is never loaded by the wgdi_b200 package (see wgdi_b200/_lib.py).
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#ifndef ICL_EMU
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#define ICL_HD __host__ __device__ __forceinline__
+#define ICL_D __device__ __forceinline__
+#else
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+#include <vector>
+#define ICL_HD inline
+#define ICL_D inline
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+#define cudaSuccess 0
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
+#endif
+
+namespace icl {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+struct Status {
+    int code = 0;
+    std::string msg;
+    bool ok() const { return code == 0; }
+};
+
+#ifndef ICL_EMU
+#define ICL_CUDA(st, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (st).code = -2;                                                                        \
+            (st).msg = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return (st).code;                                                                      \
+        }                                                                                          \
+    } while (0)
+#else
+#define ICL_CUDA(st, call) do { (void)(call); } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------------
+#ifndef ICL_EMU
+inline cudaError_t dev_malloc(void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16); }
+inline cudaError_t dev_free(void *p) { return cudaFree(p); }
+inline cudaError_t h2d(void *d, const void *h, size_t b, cudaStream_t s) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s); }
+inline cudaError_t d2h(void *h, const void *d, size_t b, cudaStream_t s) { return cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s); }
+inline cudaError_t d2d(void *d, const void *s_, size_t b, cudaStream_t s) { return cudaMemcpyAsync(d, s_, b, cudaMemcpyDeviceToDevice, s); }
+inline cudaError_t dev_memset(void *d, int v, size_t b, cudaStream_t s) { return cudaMemsetAsync(d, v, b, s); }
+inline cudaError_t dev_sync(cudaStream_t s) { return cudaStreamSynchronize(s); }
+#else
+inline int dev_malloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 16); return *p ? 0 : 1; }
+inline int dev_free(void *p) { free(p); return 0; }
+inline int h2d(void *d, const void *h, size_t b, cudaStream_t) { memcpy(d, h, b); return 0; }
+inline int d2h(void *h, const void *d, size_t b, cudaStream_t) { memcpy(h, d, b); return 0; }
+inline int d2d(void *d, const void *s_, size_t b, cudaStream_t) { memcpy(d, s_, b); return 0; }
+inline int dev_memset(void *d, int v, size_t b, cudaStream_t) { memset(d, v, b); return 0; }
+inline int dev_sync(cudaStream_t) { return 0; }
+#endif
+
+// grow-only device buffer
+template <class T>
+struct Buf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(Status &st, size_t n) {
+        if (n <= cap && p) return 0;
+        if (p) dev_free(p);
+        p = nullptr;
+        size_t want = n + n / 8 + 64;
+        cap = 0;
+        ICL_CUDA(st, dev_malloc((void **)&p, want * sizeof(T)));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) dev_free(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch: grid-stride foreach over [0, n)
+// ------------------------------------------------------------------------------------------------
+#ifndef ICL_EMU
+template <class F>
+__global__ void __launch_bounds__(256) k_foreach(int64_t n, F f) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f(i);
+}
+// one element per block-thread group of `tpb` threads: used for one-thread-per-item kernels where
+// every item wants its own warp (no intra-warp divergence between unrelated items)
+template <class F>
+__global__ void k_foreach_warp(int64_t n, F f) {
+    int64_t i = blockIdx.x;
+    if (i < n && threadIdx.x == 0) f(i);
+}
+template <class F>
+inline cudaError_t foreach(cudaStream_t s, int64_t n, F f) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t maxb = 148 * 16;
+    if (blocks > maxb) blocks = maxb;
+    k_foreach<<<(unsigned)blocks, 256, 0, s>>>(n, f);
+    return cudaGetLastError();
+}
+template <class F>
+inline cudaError_t foreach_warp(cudaStream_t s, int64_t n, F f) {
+    if (n <= 0) return cudaSuccess;
+    k_foreach_warp<<<(unsigned)n, 32, 0, s>>>(n, f);
+    return cudaGetLastError();
+}
+#else
+template <class F> inline int foreach(cudaStream_t, int64_t n, F f) { for (int64_t i = 0; i < n; i++) f(i); return 0; }
+template <class F> inline int foreach_warp(cudaStream_t, int64_t n, F f) { for (int64_t i = 0; i < n; i++) f(i); return 0; }
+#endif
+
+ICL_HD void atomic_max_i32(int32_t *p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+ICL_HD void atomic_or_i32(int32_t *p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort / scan (CUB on the device, std:: in the emulation)
+// ------------------------------------------------------------------------------------------------
+#ifndef ICL_EMU
+inline int radix_sort_pairs(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, uint64_t *kout,
+                            const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, cudaStream_t s) {
+    size_t bytes = 0;
+    ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+    if (tmp.reserve(st, bytes)) return st.code;
+    ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+    return 0;
+}
+// out[0..n] = exclusive prefix sum of in[0..n) with the total in out[n]; `in` must have n+1 slots
+// (slot n is overwritten with 0 first)
+inline int exclusive_sum_u32(Status &st, Buf<uint8_t> &tmp, uint32_t *in, uint32_t *out, int64_t n, cudaStream_t s) {
+    size_t bytes = 0;
+    ICL_CUDA(st, dev_memset(in + n, 0, sizeof(uint32_t), s));
+    ICL_CUDA(st, cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)(n + 1), s));
+    if (tmp.reserve(st, bytes)) return st.code;
+    ICL_CUDA(st, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)(n + 1), s));
+    return 0;
+}
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool armed = false;
+    void start(cudaStream_t s) {
+        if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); }
+        cudaEventRecord(a, s);
+        armed = false;
+    }
+    void stop(cudaStream_t s) { cudaEventRecord(b, s); armed = true; }
+    double ms() {
+        if (!armed) return 0.0;
+        float t = 0;
+        if (cudaEventSynchronize(b) != cudaSuccess) return 0.0;
+        cudaEventElapsedTime(&t, a, b);
+        return t;
+    }
+    void destroy() { if (a) { cudaEventDestroy(a); cudaEventDestroy(b); a = b = nullptr; } }
+};
+#else
+inline int radix_sort_pairs(Status &, Buf<uint8_t> &, const uint64_t *kin, uint64_t *kout,
+                            const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, cudaStream_t) {
+    std::vector<uint32_t> o((size_t)n);
+    std::iota(o.begin(), o.end(), 0u);
+    uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
+    std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
+    for (int64_t i = 0; i < n; i++) { kout[i] = kin[o[i]]; vout[i] = vin[o[i]]; }
+    return 0;
+}
+inline int exclusive_sum_u32(Status &, Buf<uint8_t> &, uint32_t *in, uint32_t *out, int64_t n, cudaStream_t) {
+    uint32_t acc = 0;
+    for (int64_t i = 0; i < n; i++) { uint32_t v = in[i]; out[i] = acc; acc += v; }
+    out[n] = acc;
+    return 0;
+}
+struct Timer {
+    std::chrono::steady_clock::time_point a, b;
+    bool armed = false;
+    void start(cudaStream_t) { a = std::chrono::steady_clock::now(); armed = false; }
+    void stop(cudaStream_t) { b = std::chrono::steady_clock::now(); armed = true; }
+    double ms() { return armed ? std::chrono::duration<double, std::milli>(b - a).count() : 0.0; }
+    void destroy() {}
+};
+#endif
+
+}  // namespace icl

@@ -1,0 +1,248 @@
+"""Host driver of the CUDA chaining engine: one `IclEngine` per GPU.
+
+The engine takes the graded points of a whole comparison (all chromosome pairs), runs the
+two device phases of include/icl_b200.h and, between them, obtains the extraction order
+from numpy exactly the way the reference does through pandas
+(`sort_values(by=['score1'], ascending=False)`, wgdi/collinearity.py:49,60 ->
+pandas.core.sorting.nargsort -> numpy.argsort(kind='quicksort')).  That sort is unstable
+and CPU dependent for tied scores (SURVEY.md hazard H1), so it is not re-implemented: the
+very same numpy call is made on the int64 score arrays the device returns.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import IclError, icl_blocks, icl_params
+
+
+@dataclass
+class ChainParams:
+    """Typed `[collinearity]` options of the DP engine (wgdi/collinearity.py:6-28)."""
+    mg1: int = 40
+    mg2: int = 40
+    grading: tuple = (50, 40, 25)
+    pvalue: float = 1.0
+    coverage_ratio: float = 0.8
+    over_gap: int = 3            # inner over_gap (collinearity.py:13); not a usable conf key (string bug)
+
+    @classmethod
+    def from_options(cls, options):
+        o = {str(k): v for k, v in options}
+        p = cls()
+        if "grading" in o:
+            p.grading = tuple(int(k) for k in str(o["grading"]).split(","))
+        if "mg" in o:
+            p.mg1, p.mg2 = [int(k) for k in str(o["mg"]).split(",")]
+        p.pvalue = float(o.get("pvalue", 1))
+        p.coverage_ratio = float(o.get("coverage_ratio", 0.8))
+        return p
+
+
+def nargsort_desc(a: np.ndarray) -> np.ndarray:
+    """pandas.core.sorting.nargsort(a, kind='quicksort', ascending=False) for NaN-free `a`:
+    reverse, numpy's unstable argsort, map back, reverse (collinearity.py:49,60; run_colliearity.py:67)."""
+    n = len(a)
+    r = a[::-1].argsort(kind="quicksort")
+    return (n - 1 - r)[::-1]
+
+
+@dataclass
+class Blocks:
+    """All accepted blocks of a comparison in the reference's emission order (see icl_blocks)."""
+    pair: np.ndarray
+    dir: np.ndarray
+    score: np.ndarray
+    m: np.ndarray
+    L: np.ndarray
+    N: np.ndarray
+    N1: np.ndarray
+    L1: np.ndarray
+    L2: np.ndarray
+    p_raw: np.ndarray
+    member_off: np.ndarray
+    loc1: np.ndarray
+    loc2: np.ndarray
+    member_idx: np.ndarray
+
+    def __len__(self):
+        return len(self.pair)
+
+    def p_value(self):
+        """round(a, 4) with numpy's float64 rounding, as collinearity.py:153 does."""
+        return np.round(self.p_raw, 4)
+
+
+class _Pinned:
+    """numpy view of page-locked host memory owned by the library."""
+
+    def __init__(self, eng, n, dtype):
+        self.eng = eng
+        self.ptr = C.c_void_p()
+        nbytes = max(int(n), 1) * np.dtype(dtype).itemsize
+        eng._check(eng.lib.icl_host_alloc(eng.ctx, nbytes, C.byref(self.ptr)))
+        buf = (C.c_char * nbytes).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.eng.lib.icl_host_free(self.eng.ctx, self.ptr)
+            self.ptr = None
+
+
+class IclEngine:
+    def __init__(self, device: int = 0, sort_threads: int | None = None):
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.icl_create(int(device), C.byref(self.ctx))
+        if rc != 0:
+            raise IclError(rc, self.lib.icl_last_error(None).decode())
+        self.device = device
+        self.n = 0
+        self.n_pairs = 0
+        self._pinned = {}
+        self.sort_threads = sort_threads or min(32, os.cpu_count() or 1)
+        self._pool = ThreadPoolExecutor(self.sort_threads) if self.sort_threads > 1 else None
+        self.host_ms = {}
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise IclError(rc, self.lib.icl_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            for p in self._pinned.values():
+                p.free()
+            self._pinned = {}
+            self.lib.icl_destroy(self.ctx)
+            self.ctx = None
+        if self._pool:
+            self._pool.shutdown()
+            self._pool = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _buf(self, name, n, dtype):
+        p = self._pinned.get(name)
+        if p is None or len(p.array) < n:
+            if p is not None:
+                p.free()
+            p = _Pinned(self, int(n * 1.1) + 16, dtype)
+            self._pinned[name] = p
+        return p.array[:n]
+
+    # ---- device phases -------------------------------------------------------------------------
+    def upload(self, pair_id, loc1, loc2, grading, n_pairs):
+        a = [np.ascontiguousarray(x, np.int32) for x in (pair_id, loc1, loc2, grading)]
+        n = len(a[0])
+        if not all(len(x) == n for x in a):
+            raise ValueError("pair_id, loc1, loc2, grading must have equal length")
+        self._check(self.lib.icl_upload(self.ctx, n, int(n_pairs), *[x.ctypes.data for x in a]))
+        self.n, self.n_pairs = n, int(n_pairs)
+
+    def dp(self, params: ChainParams):
+        """Both DP directions; returns (score_fwd, score_rev) int64 views in (pair, loc1, loc2) order."""
+        prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
+                         float(params.coverage_ratio))
+        sf, sr = self._buf("score_fwd", self.n, np.int64), self._buf("score_rev", self.n, np.int64)
+        self._check(self.lib.icl_dp(self.ctx, C.byref(prm), sf.ctypes.data, sr.ctypes.data))
+        self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
+        self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
+        return sf, sr
+
+    def layout(self):
+        perm = np.zeros(self.n, np.int32)
+        off = np.zeros(self.n_pairs + 1, np.int64)
+        self._check(self.lib.icl_layout(self.ctx, off.ctypes.data, perm.ctypes.data))
+        return off, perm
+
+    def rank(self, score_fwd, score_rev):
+        """The reference's descending-score permutation per (pair, direction), pair-local indices."""
+        of, orv = self._buf("order_fwd", self.n, np.int32), self._buf("order_rev", self.n, np.int32)
+        off = self.pair_off
+        sizes = np.diff(off)
+        pairs = np.argsort(-sizes, kind="stable")
+        pairs = pairs[sizes[pairs] > 0]
+
+        def work(chunk):
+            for p in chunk:
+                a, b = off[p], off[p + 1]
+                of[a:b] = nargsort_desc(score_fwd[a:b])
+                orv[a:b] = nargsort_desc(score_rev[a:b])
+
+        if self._pool is None or len(pairs) < 2:
+            work(pairs)
+        else:
+            # longest pairs first, one per task; the small tail is batched to bound task overhead
+            big = [[p] for p in pairs[sizes[pairs] >= 4096]]
+            small = pairs[sizes[pairs] < 4096]
+            step = max(1, len(small) // (4 * self.sort_threads) + 1)
+            chunks = big + [small[i:i + step] for i in range(0, len(small), step)]
+            list(self._pool.map(work, chunks))
+        return of, orv
+
+    def extract(self, order_fwd, order_rev) -> Blocks:
+        out = icl_blocks()
+        self._check(self.lib.icl_extract(self.ctx, order_fwd.ctypes.data, order_rev.ctypes.data, C.byref(out)))
+        try:
+            nb, nm = out.n_blocks, out.n_members
+
+            def arr(ptr, n, dt):
+                if n == 0:
+                    return np.zeros(0, dt)
+                return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True)
+            res = Blocks(arr(out.pair, nb, np.int32), arr(out.dir, nb, np.int32), arr(out.score, nb, np.int64),
+                         arr(out.m, nb, np.int32), arr(out.L, nb, np.int32), arr(out.N, nb, np.int32),
+                         arr(out.N1, nb, np.int64), arr(out.L1, nb, np.int32), arr(out.L2, nb, np.int32),
+                         arr(out.p_raw, nb, np.float64), arr(out.member_off, nb + 1, np.int64),
+                         arr(out.loc1, nm, np.int32), arr(out.loc2, nm, np.int32), arr(out.member_idx, nm, np.int32))
+        finally:
+            self.lib.icl_free_blocks(C.byref(out))
+        return res
+
+    def debug_dp(self, direction):
+        n = self.n
+        score, pred, depth = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        used = np.zeros(n, np.uint8)
+        self._check(self.lib.icl_debug_dp(self.ctx, int(direction), score.ctypes.data, pred.ctypes.data,
+                                          depth.ctypes.data, used.ctypes.data))
+        return score, pred, depth, used
+
+    def timings(self):
+        ms = np.zeros(len(_lib.ICL_T_NAMES), np.float64)
+        self.lib.icl_timings(self.ctx, ms.ctypes.data, len(ms))
+        return dict(zip(_lib.ICL_T_NAMES, ms.tolist()))
+
+    def counters(self):
+        c = np.zeros(4, np.int64)
+        self.lib.icl_counters(self.ctx, c.ctypes.data, 4)
+        return dict(edges=int(c[0]), launches_dp=int(c[1]), launches_extract=int(c[2]), rows=int(c[3]))
+
+    # ---- whole hot path ------------------------------------------------------------------------
+    def run_resident(self, params: ChainParams, orders=None) -> Blocks:
+        """Hot path on points already uploaded: sort + DP -> host rank -> extraction + p values."""
+        t0 = time.perf_counter()
+        sf, sr = self.dp(params)
+        t1 = time.perf_counter()
+        of, orv = orders if orders is not None else self.rank(sf, sr)
+        t2 = time.perf_counter()
+        blocks = self.extract(of, orv)
+        t3 = time.perf_counter()
+        self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3, extract=(t3 - t2) * 1e3)
+        return blocks
+
+    def chain(self, pair_id, loc1, loc2, grading, n_pairs, params: ChainParams) -> Blocks:
+        self.upload(pair_id, loc1, loc2, grading, n_pairs)
+        return self.run_resident(params)

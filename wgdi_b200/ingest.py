@@ -1,0 +1,68 @@
+"""Vectorised host grading of BLAST hits (wgdi/run_colliearity.py:59-86, `deal_blast_for_genomes`).
+
+The reference loops over query genes in Python (0.45 ms per gene); here the per-query rank
+comes from one stable lexsort.  The reference's rank, however, comes from pandas'
+single-key `sort_values`, i.e. numpy's UNSTABLE argsort (SURVEY.md hazard H2): hits with
+equal bit scores may be permuted.  Only the grading class of a hit matters, so a query needs
+the exact numpy call only when a run of tied scores straddles one of the class boundaries
+(rank `multiple`, `multiple+4`, `repeat_number`); those few queries are re-ranked with the
+same numpy call the reference makes, on the same array (the query's hits in file order).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import nargsort_desc
+
+
+def grade_hits(q, bits, multiple, repeat_number, grading):
+    """Grading per hit (0 = dropped).  q: query gene code per hit in file order; bits: column 11."""
+    q = np.asarray(q)
+    bits = np.asarray(bits)
+    n = len(q)
+    out = np.zeros(n, np.int64)
+    if n == 0:
+        return out
+    rn = int(repeat_number)
+    red = min(int(multiple), rn)                      # [:repeat_number] is applied first (:67)
+    blue = min(4 + int(multiple), rn)                 # bluenum = 4 + rednum (:64)
+    o = np.lexsort((-bits, q))                        # stable: ties keep file order
+    qs, bs = q[o], bits[o]
+    start = np.flatnonzero(np.r_[True, qs[1:] != qs[:-1]])
+    gid = np.cumsum(np.r_[True, qs[1:] != qs[:-1]]) - 1
+    rank = np.arange(n) - start[gid]
+    g = np.zeros(n, np.int64)
+    g[rank < rn] = grading[2]
+    g[rank < blue] = grading[1]
+    g[rank < red] = grading[0]
+    out[o] = g
+    # queries whose class assignment depends on the tie order
+    amb = np.zeros(len(start), bool)
+    same_next = np.r_[(qs[1:] == qs[:-1]) & (bs[1:] == bs[:-1]), False]     # element i ties with i+1 in its group
+    for b in {red, blue, rn}:
+        if b > 0:
+            hit = same_next & (rank == b - 1)
+            amb[gid[hit]] = True
+    if amb.any():
+        end = np.r_[start[1:], n]
+        for gi in np.flatnonzero(amb):
+            rows = np.sort(o[start[gi]:end[gi]])       # the query's hits in file order (:66 groupby keeps row order)
+            ranked = rows[nargsort_desc(bits[rows])][:rn]
+            out[rows] = 0
+            out[ranked[:red]] = grading[0]
+            out[ranked[red:blue]] = grading[1]
+            out[ranked[blue:rn]] = grading[2]
+    return out
+
+
+def pair_ids(chr1_names, chr2_names, c1, c2):
+    """Chromosome-pair id per hit, numbered in the sorted (chr1, chr2) STRING order pandas' groupby
+    iterates (wgdi/run_colliearity.py:118).  Returns (pair_id, [(chr1, chr2) per pair])."""
+    nc2 = max(len(chr2_names), 1)
+    code = c1.astype(np.int64) * nc2 + c2
+    uniq, inv = np.unique(code, return_inverse=True)
+    names = [(str(chr1_names[u // nc2]), str(chr2_names[u % nc2])) for u in uniq]
+    order = sorted(range(len(uniq)), key=lambda i: names[i])
+    rank = np.empty(len(uniq), np.int32)
+    rank[order] = np.arange(len(uniq), dtype=np.int32)
+    return rank[inv].astype(np.int32), [names[i] for i in order]

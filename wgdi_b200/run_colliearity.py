@@ -1,0 +1,133 @@
+"""Drop-in for the reference's `-icl` driver: `mycollinearity(options).run()`
+(wgdi/run_colliearity.py:13-200).  Same `[collinearity]` options, same printed lines, same
+output file; the per-chromosome-pair Python/pandas work of the reference's worker processes
+(`single_pool`, :158-200 -> wgdi/collinearity.py) runs on the GPU for all pairs at once.
+
+Differences a user can observe: `process` is accepted and ignored (there is no worker pool:
+chromosome pairs are work items of one CUDA launch, or shards over several GPUs, see
+wgdi_b200/shard.py), and `comparison = chromosomes` is not offered (the reference itself
+raises KeyError there under pandas >= 3, SURVEY.md hazard H19).
+"""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+
+from . import base
+from .engine import ChainParams, IclEngine
+from .ingest import grade_hits, pair_ids
+
+
+class mycollinearity():
+    def __init__(self, options):
+        # defaults of wgdi/run_colliearity.py:16-22
+        self.repeat_number = 10
+        self.multiple = 1
+        self.score = 100
+        self.evalue = 1e-5
+        self.blast_reverse = False
+        self.over_gap = 5
+        self.comparison = 'genomes'
+        self.options = options
+        for k, v in options:
+            setattr(self, str(k), v)
+            print(f"{str(k)} = {v}")                      # :27
+        self.position = 'order'                           # :28 — `position` is read and overridden
+        if hasattr(self, 'grading'):
+            self.grading = [int(k) for k in self.grading.split(',')]
+        else:
+            self.grading = [50, 40, 25]
+        self.process = int(self.process) if hasattr(self, 'process') else 4
+        self.over_gap = int(self.over_gap)
+        self.device = int(getattr(self, 'device', 0))     # extra, optional key: CUDA device index
+        self.timing = {}
+
+    # ---- ingest: wgdi/run_colliearity.py:88-121 -------------------------------------------------
+    def load_points(self):
+        """Read lens/gff/blast, filter, grade and group: returns a dict with the graded points
+        (pair_id, loc1, loc2, grading), the pair names in output order and the gene tables."""
+        lens1 = base.newlens(self.lens1, 'order')
+        lens2 = base.newlens(self.lens2, 'order')
+        gff1 = base.newgff(self.gff1)
+        gff2 = base.newgff(self.gff2)
+        gff1 = gff1[gff1['chr'].isin(lens1.index)]        # :96-97
+        gff2 = gff2[gff2['chr'].isin(lens2.index)]
+        blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
+        if self.comparison.lower() != 'genomes':
+            raise NotImplementedError("comparison = chromosomes is not offered (the reference raises KeyError "
+                                      "there under pandas >= 3; SURVEY.md H19)")
+        g1, g2 = blast['g1'].to_numpy(), blast['g2'].to_numpy()
+        grade = grade_hits(g1, blast[11].to_numpy(), int(self.multiple), int(self.repeat_number), self.grading)
+        ok = grade > 0                                    # :86
+        g1, g2, grade = g1[ok], g2[ok], grade[ok]
+        print(f"The filtered homologous gene pairs are {len(g1)}.\n")      # :112
+        if len(g1) < 1:
+            print("Stopped!\n\nIt may be that the id1 and id2 in the BLAST file do not match with (gff1, lens1) and (gff2, lens2).")
+            sys.exit(1)                                   # :113-115
+        t1 = _gene_table(gff1)
+        t2 = _gene_table(gff2)
+        pid, names = pair_ids(t1['chr_names'], t2['chr_names'], t1['chr_code'][g1], t2['chr_code'][g2])
+        return dict(pair_id=pid, loc1=t1['order'][g1].astype(np.int32), loc2=t2['order'][g2].astype(np.int32),
+                    grading=grade.astype(np.int32), pair_names=names, genes1=t1, genes2=t2)
+
+    # ---- wgdi/run_colliearity.py:88-156 ----------------------------------------------------------
+    def run(self):
+        t0 = time.perf_counter()
+        pts = self.load_points()
+        t1 = time.perf_counter()
+        params = ChainParams.from_options(self.options)
+        eng = IclEngine(self.device)
+        try:
+            for c1, c2 in pts['pair_names']:
+                print(f'Running {c1} vs {c2}')            # :162
+            blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params)
+            self.timing['device_ms'] = eng.timings()
+            self.timing['host_ms'] = dict(eng.host_ms)
+        finally:
+            eng.close()
+        t2 = time.perf_counter()
+        text = format_blocks(blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue, self.over_gap)
+        with open(self.savefile, 'w') as fout:
+            fout.write(text)
+        t3 = time.perf_counter()
+        self.timing.update(ingest_s=t1 - t0, chain_s=t2 - t1, write_s=t3 - t2)
+        sys.exit(0)                                       # :156
+
+
+def _gene_table(gff):
+    """Per-genome lookup tables: chromosome code per gene row, (chromosome, order) -> name / strand."""
+    chr_names, chr_code = np.unique(gff['chr'].to_numpy().astype(str), return_inverse=True)
+    order = gff['order'].to_numpy().astype(np.int64)
+    maxo = int(order.max()) + 1 if len(order) else 1
+    row_of = np.full(len(chr_names) * maxo, -1, np.int64)
+    # like Series.map on an index with duplicates would, the first gene of an order wins
+    key = chr_code.astype(np.int64) * maxo + order
+    row_of[key[::-1]] = np.arange(len(order))[::-1]
+    return dict(chr_names=list(chr_names), chr_code=chr_code.astype(np.int64), order=order, maxo=maxo, row_of=row_of,
+                name=gff.index.to_numpy().astype(str), strand=gff['strand'].to_numpy().astype(str))
+
+
+def format_blocks(blocks, pair_names, genes1, genes2, pvalue, over_gap):
+    """The collinearity file body (wgdi/run_colliearity.py:143-155, 174-199)."""
+    p = blocks.p_value()                                  # round(a, 4), collinearity.py:153
+    emit = np.flatnonzero(~(p > pvalue) & (blocks.m >= over_gap))          # collinearity.py:55-56, run_colliearity.py:178
+    c1code = {name: i for i, name in enumerate(genes1['chr_names'])}
+    c2code = {name: i for i, name in enumerate(genes2['chr_names'])}
+    out = []
+    num = 1
+    for b in emit:
+        a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
+        x, y = blocks.loc1[a0:a1], blocks.loc2[a0:a1]
+        chr1, chr2 = pair_names[blocks.pair[b]]
+        mark = 'plus' if y[0] < y[1] else 'minus'         # :194-195
+        tail = f" score={int(blocks.score[b])} pvalue={p[b]} N={a1 - a0} {chr1}&{chr2} {mark}"
+        out.append(f"# Alignment {num}:" + tail.split(':')[0])             # :147-151 re-cuts the header at ':'
+        num += 1
+        r1 = genes1['row_of'][c1code[chr1] * genes1['maxo'] + x]
+        r2 = genes2['row_of'][c2code[chr2] * genes2['maxo'] + y]
+        n1, n2 = genes1['name'][r1], genes2['name'][r2]
+        s = np.where(genes1['strand'][r1] == genes2['strand'][r2], '1', '-1')        # :185-187
+        out.extend(f"{a} {i} {c} {j} {k}" for a, i, c, j, k in zip(n1, x.tolist(), n2, y.tolist(), s))
+    return "\n".join(out) + "\n" if out else ""

@@ -1,0 +1,61 @@
+"""Sharding of chromosome pairs over GPUs.
+
+The reference distributes chromosome pairs over worker processes in static contiguous chunks
+(`n = ceil(len(total) / process)`, wgdi/run_colliearity.py:123-136), which balances badly because the
+heavy pairs cluster.  Pairs are independent units of work, so here they are assigned by
+longest-processing-time (LPT) on their point count; every rank uploads only its own pairs, there is no
+data-path collective, and the per-rank block lists are merged on the host in pair order.
+"""
+from __future__ import annotations
+
+import heapq
+
+import numpy as np
+
+
+def lpt_assign(sizes, n_bins: int) -> np.ndarray:
+    """owner bin of every pair: pairs in descending size go to the currently least-loaded bin."""
+    sizes = np.asarray(sizes, np.int64)
+    owner = np.zeros(len(sizes), np.int32)
+    heap = [(0, b) for b in range(n_bins)]
+    heapq.heapify(heap)
+    for p in np.argsort(-sizes, kind="stable"):
+        load, b = heapq.heappop(heap)
+        owner[p] = b
+        heapq.heappush(heap, (load + int(sizes[p]), b))
+    return owner
+
+
+def shard_points(points: dict, rank: int, world: int):
+    """The sub-problem of `rank`: its pairs renumbered densely, plus the map back to global pair ids."""
+    sizes = np.bincount(points["pair_id"], minlength=points["n_pairs"])
+    owner = lpt_assign(sizes, world)
+    mine = np.flatnonzero(owner == rank).astype(np.int32)
+    local_of = np.full(points["n_pairs"], -1, np.int32)
+    local_of[mine] = np.arange(len(mine), dtype=np.int32)
+    sel = np.flatnonzero(owner[points["pair_id"]] == rank)
+    return dict(pair_id=local_of[points["pair_id"][sel]], loc1=points["loc1"][sel], loc2=points["loc2"][sel],
+                grading=points["grading"][sel], n_pairs=len(mine), global_pair=mine, rows=sel)
+
+
+def merge_blocks(parts):
+    """Merge per-rank `Blocks` (with `.pair` already mapped to global pair ids) into emission order:
+    pair ascending; inside a pair the rank-local order (direction, acceptance) is already right."""
+    from .engine import Blocks
+    parts = [p for p in parts if p is not None]
+    pair = np.concatenate([p.pair for p in parts])
+    order = np.argsort(pair, kind="stable")
+    m = np.concatenate([p.m for p in parts])
+    starts = np.concatenate([p.member_off[:-1] + off for p, off in
+                             zip(parts, np.cumsum([0] + [len(p.loc1) for p in parts[:-1]]))]) if len(pair) else np.zeros(0, np.int64)
+    loc1 = np.concatenate([p.loc1 for p in parts])
+    loc2 = np.concatenate([p.loc2 for p in parts])
+    midx = np.concatenate([p.member_idx for p in parts])
+    mo = m[order].astype(np.int64)
+    new_off = np.r_[0, np.cumsum(mo)]
+    gather = np.concatenate([np.arange(starts[b], starts[b] + m[b]) for b in order]) if len(order) else np.zeros(0, np.int64)
+
+    def cat(name):
+        return np.concatenate([getattr(p, name) for p in parts])[order]
+    return Blocks(pair[order], cat("dir"), cat("score"), m[order], cat("L"), cat("N"), cat("N1"), cat("L1"), cat("L2"),
+                  cat("p_raw"), new_off, loc1[gather], loc2[gather], midx[gather])

@@ -231,3 +231,29 @@ def write_dataset(ds: Dataset, outdir: str, savefile: str | None = None, process
         for k, v in ds.options(paths, savefile, process):
             f.write(f"{k} = {v}\n")
     return conf
+
+
+def graded_points(ds: Dataset) -> dict:
+    """Host ingest of the integer-coded BLAST table: the filters of wgdi/base.py:178-180, the grading of
+    wgdi/run_colliearity.py:59-86 and the (chr1, chr2) grouping of :117-121, vectorised — the same code
+    path `mycollinearity.load_points` takes after parsing the files."""
+    import pandas as pd
+    from .ingest import grade_hits, pair_ids
+    c = ds.cfg
+    keep = (ds.bits >= 100) & (ds.evalue < 1e-5)
+    if c.self_cmp:
+        keep &= ds.q != ds.t
+    rows = np.flatnonzero(keep)
+    q, t = ds.q[rows], ds.t[rows]
+    first = ~pd.Series(q.astype(np.int64) * ds.g2.n + t).duplicated(keep="first").to_numpy()
+    rows, q, t = rows[first], q[first], t[first]
+    grade = grade_hits(q, ds.bits[rows], c.multiple, ds.repeat_number, list(c.grading))
+    ok = grade > 0
+    q, t, grade = q[ok], t[ok], grade[ok]
+    names1 = sorted(ds.g1.chr_names)
+    names2 = sorted(ds.g2.chr_names)
+    code1 = np.array([names1.index(x) for x in ds.g1.chr_names])[ds.g1.chr_idx[q]]
+    code2 = np.array([names2.index(x) for x in ds.g2.chr_names])[ds.g2.chr_idx[t]]
+    pid, names = pair_ids(names1, names2, code1, code2)
+    return dict(pair_id=pid, loc1=ds.g1.order[q].astype(np.int32), loc2=ds.g2.order[t].astype(np.int32),
+                grading=grade.astype(np.int32), n_pairs=len(names), pair_names=names)
