@@ -221,14 +221,14 @@ def main():
     dev_ms = {}
 
     def step_resident():
-        blocks = eng.run_resident(prm)
+        blocks = eng.run_resident(prm, min_members=5)       # what the file writer keeps (run_colliearity.py:178)
         for k, v in eng.timings().items():
             dev_ms.setdefault(k, []).append(v)
         dev_ms.setdefault("host_rank", []).append(eng.host_ms["rank"])
         return blocks
 
     def step_e2e():
-        return eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm)
+        return eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm, min_members=5)
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     eng.upload(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"])
@@ -287,7 +287,7 @@ def main():
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
                        "tie_order": "numpy argsort on host between the two device phases (reference-exact)"},
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "h2d_bytes_per_step": 24 * n_local, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": 16 * n_local + 8 * n_local, "d2h_bytes_per_step": d2h},
             "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
             "roofline": {"kernel": "chain DP (both directions)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,

@@ -14,7 +14,7 @@
  *
  * Call sequence (one icl_ctx per GPU; a ctx is not thread-safe):
  *
- *   icl_create -> icl_upload -> icl_dp -> [host: numpy argsort of the scores] -> icl_extract
+ *   icl_create -> icl_upload -> icl_dp -> [host: numpy.argsort of every pair segment] -> icl_extract
  *              -> icl_free_blocks ... -> icl_destroy
  *
  * The split into icl_dp / icl_extract exists because the reference orders block extraction with
@@ -25,7 +25,7 @@
  *
  * All functions return ICL_OK (0) or a negative error code; icl_last_error() gives the message.
  * No exceptions cross the boundary.  Host input arrays are caller-owned and only read during the
- * call; icl_blocks arrays are library-owned until icl_free_blocks().
+ * call; icl_blocks arrays are owned by the context (see icl_extract).
  */
 #ifndef ICL_B200_H
 #define ICL_B200_H
@@ -106,11 +106,14 @@ int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
 
 /*
  * Sort + chaining DP in both directions (wgdi/collinearity.py:72-115: forward :74-93, anti-diagonal
- * :96-115).  Writes the final scores as int64, in (pair, loc1, loc2) order, into caller buffers of
- * n_points elements — exactly the arrays the reference hands to numpy's argsort through pandas
- * (collinearity.py:49,60).  May be called repeatedly on the same upload (e.g. a parameter sweep).
+ * :96-115).  Writes, for every pair segment pair_off[p]..pair_off[p+1] (see icl_layout), the final int64
+ * scores of the segment's points in REVERSED (loc1, loc2) order into caller buffers of n_points elements.
+ * That is exactly the array pandas' nargsort(ascending=False) hands to numpy.argsort
+ * (it reverses the column first; collinearity.py:49,60 -> pandas/core/sorting.py nargsort), so the caller
+ * can sort each segment in place without copying.  May be called repeatedly on the same upload
+ * (e.g. a parameter sweep).
  */
-int icl_dp(icl_ctx *ctx, const icl_params *params, int64_t *score_fwd, int64_t *score_rev);
+int icl_dp(icl_ctx *ctx, const icl_params *params, int64_t *key_fwd, int64_t *key_rev);
 
 /* Layout produced by icl_dp: pair_off[n_pairs + 1] (points of pair p are sorted positions
  * pair_off[p] .. pair_off[p+1]) and perm[n_points] (upload index of each sorted position).
@@ -119,12 +122,19 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
 
 /*
  * Block extraction + p values (wgdi/collinearity.py:42-70, 117-153).
- * order_fwd / order_rev: for every pair segment pair_off[p]..pair_off[p+1] the pair-LOCAL indices of
- * its points in the order pandas would examine them, i.e.
- *     nargsort(score[pair segment], kind='quicksort', ascending=False)
- * computed by the caller with numpy on the arrays icl_dp returned.
+ * argsort_fwd / argsort_rev: for every pair segment the UNMODIFIED result of
+ *     numpy.argsort(key[pair_off[p]:pair_off[p+1]], kind='quicksort')
+ * on the arrays icl_dp returned, narrowed to int32 (segment-local indices).  The library undoes pandas' two
+ * reversals itself.  The sort must be numpy's: it is unstable and its tie permutation decides which blocks
+ * are extracted first (SURVEY.md hazard H1).
+ * min_members: only blocks with at least that many gene pairs are returned (1 = everything the inner seam
+ * `collinearity.run()` returns, 5 = what the file writer keeps, run_colliearity.py:178); smaller accepted
+ * blocks still take part in the `times` accounting of the p value (collinearity.py:150).
+ * The arrays of `out` live in page-locked staging owned by `ctx`: valid until the next icl_extract or
+ * icl_destroy on that context; icl_free_blocks only clears the view.
  */
-int icl_extract(icl_ctx *ctx, const int32_t *order_fwd, const int32_t *order_rev, icl_blocks *out);
+int icl_extract(icl_ctx *ctx, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
+                icl_blocks *out);
 void icl_free_blocks(icl_blocks *blocks);
 
 /* Test / diagnostics: DP state of one direction (0 forward, 1 anti-diagonal) in sorted point order.

@@ -38,10 +38,10 @@ def test_golden_clouds_dp_and_blocks(gpu_engine, clouds):
         rng = np.random.default_rng(c["case"])
         perm = np.arange(n) if c["case"] % 11 == 5 else rng.permutation(n)      # duplicates keep upload order (H22)
         eng.upload(np.zeros(n, np.int32), c["loc1"][perm], c["loc2"][perm], c["grading"][perm], 1)
-        sf, sr = eng.dp(prm)
-        assert (sf == c["score1"]).all() and (sr == c["score2"]).all()
+        kf, kr = eng.dp(prm)
+        assert (kf[::-1] == c["score1"]).all() and (kr[::-1] == c["score2"]).all()      # one pair: reversed segment
         check_dp_against_golden(eng.debug_dp, c)
-        blocks = eng.extract(c["order1"].astype(np.int32), c["order2"].astype(np.int32))
+        blocks = eng.extract(eng.raw_from_order(c["order1"]), eng.raw_from_order(c["order2"]))
         check_blocks_against_golden(blocks, prm.pvalue, c)
 
 
@@ -193,7 +193,10 @@ def test_edge_cases(gpu_engine):
     eng.dp(prm)
     with pytest.raises(IclError) as e:
         eng.extract(np.array([0, 1, 7], np.int32), np.array([0, 1, 2], np.int32))
-    assert e.value.code == -1                                   # order index outside its pair
+    assert e.value.code == -1                                   # argsort index outside its pair
+    with pytest.raises(IclError) as e:
+        eng.extract(np.array([0, 1, 1], np.int32), np.array([0, 1, 2], np.int32))
+    assert e.value.code == -1                                   # not a permutation
 
 
 def test_window_bounds_are_exclusive(gpu_engine):
@@ -205,8 +208,8 @@ def test_window_bounds_are_exclusive(gpu_engine):
             l1 = np.array([10, 10 + dr], np.int32)
             l2 = np.array([10, 10 + dc], np.int32)
             gpu_engine.upload(np.zeros(2, np.int32), l1, l2, np.full(2, 50, np.int32), 1)
-            sf, _ = gpu_engine.dp(prm)
-            assert (sf[1] == 100 - dr - dc) == linked and (linked or sf[1] == 50)
+            kf, _ = gpu_engine.dp(prm)
+            assert (kf[0] == 100 - dr - dc) == linked and (linked or kf[0] == 50)       # keys are reversed per segment
 
 
 def test_sharded_equals_unsharded(gpu_engine):

@@ -115,7 +115,7 @@ def test_pipeline_on_golden_clouds_emu(emu_backend, clouds):
             eng.upload(np.zeros(n, np.int32), c["loc1"], c["loc2"], c["grading"], 1)
             eng.dp(prm)
             check_dp_against_golden(lambda d: (lambda s, p, dp, u: (s, p, dp, u))(*eng.debug_dp(d)), c)
-            blocks = eng.extract(c["order1"].astype(np.int32), c["order2"].astype(np.int32))
+            blocks = eng.extract(eng.raw_from_order(c["order1"]), eng.raw_from_order(c["order2"]))
             check_blocks_against_golden(blocks, prm.pvalue, c)
     finally:
         eng.close()

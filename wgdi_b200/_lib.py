@@ -51,7 +51,7 @@ def _declare(lib):
     lib.icl_upload.argtypes = [vp, i64, i32, vp, vp, vp, vp]
     lib.icl_dp.argtypes = [vp, C.POINTER(icl_params), vp, vp]
     lib.icl_layout.argtypes = [vp, vp, vp]
-    lib.icl_extract.argtypes = [vp, vp, vp, C.POINTER(icl_blocks)]
+    lib.icl_extract.argtypes = [vp, vp, vp, i32, C.POINTER(icl_blocks)]
     lib.icl_free_blocks.argtypes = [C.POINTER(icl_blocks)]
     lib.icl_free_blocks.restype = None
     lib.icl_debug_dp.argtypes = [vp, i32, vp, vp, vp, vp]

@@ -40,6 +40,20 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_npsort(force=False):
+    """CPython helper that calls numpy's own argsort routine from a thread pool (csrc/npsort.c)."""
+    import sysconfig
+    import numpy
+    src = os.path.join(HERE, "csrc", "npsort.c")
+    out = os.path.join(HERE, "_npsort" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not force and not _stale(out, [src]):
+        return out
+    cmd = ["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-pthread", "-I", sysconfig.get_paths()["include"],
+           "-I", numpy.get_include(), "-o", out, src]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build_emu(outdir, force=False):
     os.makedirs(outdir, exist_ok=True)
     out = os.path.join(outdir, "libicl_b200_emu.so")
@@ -55,3 +69,4 @@ if __name__ == "__main__":
         print(build_emu(sys.argv[2], force=True))
     else:
         print(build(force=True, verbose=True))
+        print(build_npsort(force=True))

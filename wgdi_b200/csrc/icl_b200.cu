@@ -67,15 +67,19 @@ struct icl_ctx {
     Buf<uint8_t> used;
     Buf<int64_t> score64;
     // extraction
-    Buf<int32_t> order_in, tops, members, blk_top, blk_m, blk_L, blk_ms, blk_N, blk_L1, blk_L2, nblk, times;
-    Buf<int64_t> blk_N1, d_out_base;
-    Buf<double> blk_a;
+    Buf<int32_t> order_in, rankpos, rank2v, acc_L, members, times;
+    Buf<uint32_t> tree_v, acc_m, acc_flag, blkidx, moff;
     Buf<uint8_t> present;
-    // gather
-    Buf<int32_t> o_pair, o_dir, o_m, o_L, o_N, o_L1, o_L2, o_loc1, o_loc2, o_idx, o_slot;
-    Buf<int64_t> o_score, o_N1;
-    Buf<double> o_a;
-    Buf<uint32_t> o_mcnt, o_moff;
+    int64_t NB = 0, NM = 0;
+    Buf<int32_t> b_top, b_m, b_L, b_j0, b_j1, b_l2min, b_l2max, b_L1, b_item, b_N;
+    Buf<uint32_t> b_moff;
+    Buf<int64_t> b_N1;
+    Buf<double> b_a;
+    // output selection + staging
+    Buf<uint32_t> o_flag, o_bidx, o_mcnt, o_moff, o_src, o_mout, o_moff2;
+    Buf<uint8_t> d_stage;
+    uint8_t *h_stage = nullptr;
+    size_t h_stage_cap = 0;
 
     Timer timers[ICL_T_COUNT];
     int64_t counters[4] = {0, 0, 0, 0};
@@ -200,13 +204,18 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release();
     c->S.release(); c->pred.release(); c->depth.release(); c->used.release(); c->score64.release();
-    c->order_in.release(); c->tops.release(); c->members.release(); c->blk_top.release(); c->blk_m.release();
-    c->blk_L.release(); c->blk_ms.release(); c->blk_N.release(); c->blk_L1.release(); c->blk_L2.release();
-    c->nblk.release(); c->times.release(); c->blk_N1.release(); c->d_out_base.release(); c->blk_a.release();
-    c->present.release();
-    c->o_pair.release(); c->o_dir.release(); c->o_m.release(); c->o_L.release(); c->o_N.release(); c->o_L1.release();
-    c->o_L2.release(); c->o_loc1.release(); c->o_loc2.release(); c->o_idx.release(); c->o_slot.release();
-    c->o_score.release(); c->o_N1.release(); c->o_a.release(); c->o_mcnt.release(); c->o_moff.release();
+    c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
+    c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
+    c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
+    c->b_j1.release(); c->b_l2min.release(); c->b_l2max.release(); c->b_L1.release(); c->b_item.release();
+    c->b_N.release(); c->b_moff.release(); c->b_N1.release(); c->b_a.release();
+    c->o_flag.release(); c->o_bidx.release(); c->o_mcnt.release(); c->o_moff.release(); c->d_stage.release();
+    c->o_src.release(); c->o_mout.release(); c->o_moff2.release();
+#ifndef ICL_EMU
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+#else
+    free(c->h_stage);
+#endif
     for (auto &t : c->timers) t.destroy();
 #ifndef ICL_EMU
     cudaStreamDestroy(c->stream);
@@ -580,11 +589,15 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int64_t *score_fwd, int
     c->timers[ICL_T_EXPORT].start(s);
     if (c->score64.reserve(st, 2 * n)) return st.code;
     {
-        const int32_t *S = c->S.p, *mmap = c->mmap.p;
+        // per pair segment in REVERSED point order: the array pandas' nargsort(ascending=False) hands to numpy
+        const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
+        const int64_t *off = c->d_pair_off.p;
         int64_t *o = c->score64.p;
         ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
-            o[i] = S[i];
-            o[n + i] = S[mmap[i]];
+            int32_t p = ps[i];
+            int64_t src = off[p] + (off[p + 1] - 1 - i);
+            o[i] = S[src];
+            o[n + i] = S[mmap[src]];
         }));
     }
     if (n > 0) {
@@ -655,88 +668,176 @@ extern "C" int icl_debug_dp(icl_ctx *c, int32_t dir, int32_t *score, int32_t *pr
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase: extraction (collinearity.py:49-68 with max_path :117-144).  Tops are visited in the caller's
-// rank order; a top that is still present is either accepted with the present part of its path
+// phase: extraction (collinearity.py:49-68 with max_path :117-144).
+//
+// Reference semantics: tops are visited in descending-score order (the caller's numpy permutation); a top
+// that is still present is either accepted together with the present part of its path
 // (L >= over_gap and m / L > coverage_ratio, :129) or removed alone (:143).
-// The removed members of a path always form a root-side prefix (an ancestor has a strictly smaller
-// score than its descendants, so it can only have been removed as part of an accepted block, which
-// removes every present ancestor as well); hence the present members are the walk from the top up to
-// the first removed node.
+//
+// Two facts make this parallel without changing a single decision:
+//  * The removed members of a path always form a root-side prefix: an ancestor has a strictly smaller score
+//    than its descendants (every DP step adds s > 0), so it is examined after them and can only have been
+//    removed as part of an accepted block — which removes every present ancestor as well.  Hence the present
+//    members of a path are the walk from the top up to the first removed node.
+//  * A decision only reads and writes `present` flags of the top's own predecessor tree.  Trees are therefore
+//    independent; only the ORDER in which accepted blocks are emitted (and bump `times`, phase B) is global.
+// So: key every used point by (tree root, rank position), radix sort, let one thread run each tree in rank
+// order, record accepted blocks at their rank position, and recover the reference's acceptance order with a
+// prefix sum over rank positions.
 // ------------------------------------------------------------------------------------------------
 static int phase_extract(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    const int64_t nslots = V / 3 + 2 * (int64_t)P + 2;
-    if (c->tops.reserve(st, V) || c->members.reserve(st, V) || c->present.reserve(st, V) || c->nblk.reserve(st, 2 * P + 1) ||
-        c->blk_top.reserve(st, nslots) || c->blk_m.reserve(st, nslots) || c->blk_L.reserve(st, nslots) ||
-        c->blk_ms.reserve(st, nslots) || c->stats.reserve(st, 4))
+    if (c->rankpos.reserve(st, V) || c->present.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) ||
+        c->idx_a.reserve(st, V) || c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) ||
+        c->acc_flag.reserve(st, V + 2) || c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->stats.reserve(st, 4))
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
-    const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *imap = c->imap.p, *ord = c->order_in.p;
+    ICL_CUDA(st, dev_memset(c->rankpos.p, 0xFF, (size_t)V * sizeof(int32_t), s));
+    ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
+    const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
     const int64_t *off = c->d_pair_off.p;
-    int32_t *tops = c->tops.p, *stats = c->stats.p;
+    int32_t *rankpos = c->rankpos.p, *stats = c->stats.p;
+    // The caller's arrays are numpy.argsort of the REVERSED segment (what pandas' nargsort(ascending=False) feeds
+    // numpy); undo the two reversals: descending position (np-1-j) holds point (np-1-r[j]).
     ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
         int32_t p = ps[i];
-        int64_t a = off[p], np_ = off[p + 1] - a;
-        int32_t of = ord[i], orv = ord[n + i];
-        if (of < 0 || of >= np_ || orv < 0 || orv >= np_) { atomic_or_i32(&stats[2], 1); of = 0; orv = 0; }
-        tops[i] = (int32_t)(a + of);
-        tops[n + i] = mmap[a + orv];
+        int64_t a = off[p], np_ = off[p + 1] - a, j = i - a;
+        int32_t rf = ord[i], rr = ord[n + i];
+        if (rf < 0 || rf >= np_ || rr < 0 || rr >= np_) { atomic_or_i32(&stats[2], 1); return; }
+        int32_t pos = (int32_t)(np_ - 1 - j);
+        rankpos[a + (np_ - 1 - rf)] = pos;
+        rankpos[mmap[a + (np_ - 1 - rr)]] = pos;
     }));
     ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));      // drop usedtimes < 1 (:50 / :61)
-    const int32_t *S = c->S.p, *G = c->G.p, *pred = c->pred.p, *depth = c->depth.p, *order = c->d_item_order.p;
-    uint8_t *present = c->present.p;
-    int32_t *members = c->members.p, *blk_top = c->blk_top.p, *blk_m = c->blk_m.p, *blk_L = c->blk_L.p, *blk_ms = c->blk_ms.p;
-    int32_t *nblk = c->nblk.p;
-    const int32_t over_gap = c->prm.over_gap;
-    const double cov = c->prm.coverage_ratio;
-    ICL_CUDA(st, foreach_warp(s, 2 * (int64_t)P, ICL_LAMBDA(int64_t j) {
-        int32_t it = order[j];
-        int32_t p = it >= P ? it - P : it;
-        int64_t a = off[p] + (it >= P ? n : 0), b = off[p + 1] + (it >= P ? n : 0);
-        int64_t slot = a / 3 + it;
-        int64_t cursor = a;
-        int32_t nb = 0;
-        for (int64_t t = a; t < b; t++) {
-            int32_t top = tops[t];
-            if (!present[top]) continue;
-            int32_t L = (S[top] != G[top]) ? depth[top] : 1;
-            int32_t m = 0;
-            int32_t q = top;
-            while (true) {                                  // present part of the path
-                m++;
-                if (S[q] == G[q]) break;                    // root
-                q = pred[q];
-                if (!present[q]) break;
-            }
-            if (L >= over_gap && (double)m / (double)L > cov) {
-                q = top;
-                for (int32_t k = 0; k < m; k++) {           // members by loc1 ascending (:140)
-                    present[q] = 0;
-                    if (it >= P) members[cursor + k] = imap[q - n];
-                    else members[cursor + (m - 1 - k)] = q;
+    const int32_t *S = c->S.p, *G = c->G.p, *pred = c->pred.p, *depth = c->depth.p, *itemof = c->itemof.p;
+    const uint8_t *used = c->used.p;
+    // key = (root, rank position); unused points sort behind everything
+    int maxnp = 1;
+    for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
+    const int rb = bits_for(maxnp), vb = bits_for(V);
+    {
+        uint64_t *key = c->key_a.p;
+        uint32_t *idx = c->idx_a.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
+            idx[v] = (uint32_t)v;
+            if (!used[v]) { key[v] = (uint64_t)V << rb; return; }
+            int32_t rp = rankpos[v];
+            if (rp < 0) { atomic_or_i32(&stats[2], 1); key[v] = (uint64_t)V << rb; return; }   // not a permutation
+            int32_t q = (int32_t)v;
+            while (S[q] != G[q]) q = pred[q];                    // root of the predecessor tree
+            key[v] = ((uint64_t)(uint32_t)q << rb) | (uint32_t)rp;
+        }));
+    }
+    if (V > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, rb + vb, s)) return st.code;
+    {
+        const uint64_t *key = c->key_b.p;
+        const uint32_t *tv = c->tree_v.p;
+        uint8_t *present = c->present.p;
+        uint32_t *acc_m = c->acc_m.p;
+        int32_t *acc_L = c->acc_L.p;
+        const int32_t over_gap = c->prm.over_gap;
+        const double cov = c->prm.coverage_ratio;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+            uint64_t root = key[t] >> rb;
+            if (root >= (uint64_t)V) return;                                    // unused tail
+            if (t > 0 && (key[t - 1] >> rb) == root) return;                    // not the head of its tree
+            for (int64_t u = t; u < V && (key[u] >> rb) == root; u++) {         // the tree's points in rank order
+                int32_t top = (int32_t)tv[u];
+                if (!present[top]) continue;
+                int32_t L = (S[top] != G[top]) ? depth[top] : 1;
+                int32_t m = 0, q = top;
+                while (true) {                                                  // present part of the path
+                    m++;
+                    if (S[q] == G[q]) break;
                     q = pred[q];
+                    if (!present[q]) break;
                 }
-                blk_top[slot + nb] = top;
-                blk_m[slot + nb] = m;
-                blk_L[slot + nb] = L;
-                blk_ms[slot + nb] = (int32_t)cursor;
-                cursor += m;
-                nb++;
-            } else {
-                present[top] = 0;
+                if (L >= over_gap && (double)m / (double)L > cov) {             // :129
+                    q = top;
+                    for (int32_t k = 0; k < m; k++) { present[q] = 0; q = pred[q]; }     // :130
+                    int32_t it = itemof[top];
+                    int64_t pos = (it >= P ? n : 0) + off[it >= P ? it - P : it] + (int64_t)(key[u] & ((1ull << rb) - 1));
+                    acc_m[pos] = (uint32_t)m;
+                    acc_L[pos] = L;
+                } else {
+                    present[top] = 0;                                           // :143
+                }
             }
-        }
-        nblk[it] = nb;
-    }));
+        }));
+    }
+    // acceptance order = rank order: block index and member offset by prefix sums over rank positions
+    {
+        const uint32_t *acc_m = c->acc_m.p;
+        uint32_t *flag = c->acc_flag.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) { flag[t] = acc_m[t] ? 1u : 0u; }));
+    }
+    if (exclusive_sum_u32(st, c->tmp, c->acc_flag.p, c->blkidx.p, V, s)) return st.code;
+    if (exclusive_sum_u32(st, c->tmp, c->acc_m.p, c->moff.p, V, s)) return st.code;
+    uint32_t tot[2] = {0, 0};
+    int32_t hs[4] = {0, 0, 0, 0};
+    ICL_CUDA(st, d2h(&tot[0], c->blkidx.p + V, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(&tot[1], c->moff.p + V, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), s));
+    ICL_CUDA(st, dev_sync(s));
+    if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_extract: argsort array is not a permutation of its pair segment");
+    c->NB = tot[0];
+    c->NM = tot[1];
+    const int64_t NB = c->NB;
+    if (c->members.reserve(st, c->NM) || c->b_top.reserve(st, NB) || c->b_m.reserve(st, NB) || c->b_L.reserve(st, NB) ||
+        c->b_moff.reserve(st, NB + 1) || c->b_j0.reserve(st, NB) || c->b_j1.reserve(st, NB) || c->b_l2min.reserve(st, NB) ||
+        c->b_l2max.reserve(st, NB) || c->b_L1.reserve(st, NB) || c->b_item.reserve(st, NB))
+        return st.code;
+    {
+        // one thread per accepted block: members by loc1 ascending (:140), bounding box (:131), row slice of the box
+        const uint32_t *acc_m = c->acc_m.p, *blkidx = c->blkidx.p, *moff = c->moff.p;
+        const int32_t *acc_L = c->acc_L.p, *imap = c->imap.p, *l1 = c->loc1s.p, *l2 = c->loc2s.p, *rowptr = c->rowptr.p;
+        const int32_t *rmin = c->d_rmin.p;
+        const int64_t *rb_ = c->d_rb.p;
+        const int32_t *itemof_pos = c->itemof.p;       // item of a V position == item of the point stored there
+        const int32_t *rank2v = c->rank2v.p;
+        int32_t *members = c->members.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_j0 = c->b_j0.p;
+        int32_t *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_L1 = c->b_L1.p, *b_item = c->b_item.p;
+        uint32_t *b_moff = c->b_moff.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+            uint32_t m = acc_m[t];
+            if (!m) return;
+            uint32_t b = blkidx[t], mo = moff[t];
+            int32_t it = itemof_pos[t];
+            int32_t p = it >= P ? it - P : it;
+            int32_t top = rank2v[t];
+            int32_t q = top, l2min = 0x7fffffff, l2max = -1;
+            for (uint32_t k = 0; k < m; k++) {
+                int32_t i = it >= P ? imap[q - n] : q;                           // forward sorted position
+                members[mo + (it >= P ? k : m - 1 - k)] = i;
+                int32_t y = l2[i];
+                l2min = y < l2min ? y : l2min;
+                l2max = y > l2max ? y : l2max;
+                q = pred[q];
+            }
+            int32_t l1min = l1[members[mo]], l1max = l1[members[mo + m - 1]];
+            b_top[b] = top;
+            b_m[b] = (int32_t)m;
+            b_L[b] = acc_L[t];
+            b_moff[b] = mo;
+            b_item[b] = it;
+            b_l2min[b] = l2min;
+            b_l2max[b] = l2max;
+            b_L1[b] = l1max - l1min + 1;
+            b_j0[b] = rowptr[rb_[p] + (l1min - rmin[p])];
+            b_j1[b] = rowptr[rb_[p] + (l1max - rmin[p]) + 1];
+        }));
+    }
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase: times / p value (collinearity.py:131-139, 146-153), one chromosome pair per worker because
-// `times` is shared by the pair's two directions and by all of its blocks, in acceptance order.
+// phase: times / p value (collinearity.py:131-139, 146-153).  `times` is shared by the two directions of
+// a chromosome pair and by all of its blocks in acceptance order, so one warp owns a pair and walks its
+// blocks (forward then anti-diagonal); the box scan over the contiguous row slice is lane-parallel and
+// `times` lives in shared memory (uint16) when the pair fits.
 // ------------------------------------------------------------------------------------------------
 ICL_HD double icl_p_raw(int64_t score, int32_t m, int32_t g0, int64_t N1, int32_t N, int32_t L1, int32_t L2) {
 #if defined(__CUDA_ARCH__)
@@ -761,76 +862,139 @@ ICL_HD double icl_p_raw(int64_t score, int32_t m, int32_t g0, int64_t N1, int32_
 #endif
 }
 
+struct PvalArgs {
+    int64_t n;
+    int32_t P, g0, smem_cap;
+    const int32_t *pair_order, *l2, *S, *b_top, *b_m, *b_j0, *b_j1, *b_l2min, *b_l2max, *b_L1;
+    const int64_t *off;
+    const uint32_t *blkidx;
+    int32_t *times, *b_N;
+    int64_t *b_N1;
+    double *b_a;
+};
+
+#ifndef ICL_EMU
+template <bool SMEM>
+__device__ __forceinline__ void pvalue_pair(const PvalArgs &A, int32_t p, uint16_t *tsm) {
+    const int lane = threadIdx.x;
+    const int64_t a = A.off[p], np_ = A.off[p + 1] - a;
+    if (SMEM) {
+        for (int64_t i = lane; i < np_; i += 32) tsm[i] = 1;                     // get_matrix :34
+    } else {
+        for (int64_t i = lane; i < np_; i += 32) A.times[a + i] = 1;
+    }
+    __syncwarp();
+    volatile int32_t *tg = A.times;
+    for (int d = 0; d < 2; d++) {
+        const uint32_t b0 = A.blkidx[(d ? A.n : 0) + a], b1 = A.blkidx[(d ? A.n : 0) + a + np_];
+        if (b0 == b1) continue;
+        int32_t j0 = A.b_j0[b0], j1 = A.b_j1[b0], lo = A.b_l2min[b0], hi = A.b_l2max[b0];
+        for (uint32_t b = b0; b < b1; b++) {
+            int32_t nj0 = 0, nj1 = 0, nlo = 0, nhi = 0;
+            if (b + 1 < b1) { nj0 = A.b_j0[b + 1]; nj1 = A.b_j1[b + 1]; nlo = A.b_l2min[b + 1]; nhi = A.b_l2max[b + 1]; }
+            int32_t N = 0;
+            int64_t N1 = 0;
+            for (int32_t q = j0 + lane; q < j1; q += 32) {                        // :134-137 inclusive box
+                int32_t y = __ldg(A.l2 + q);
+                if (y >= lo && y <= hi) {
+                    int32_t t;
+                    if (SMEM) { t = tsm[q - a]; tsm[q - a] = (uint16_t)(t + 1); }
+                    else { t = tg[q]; tg[q] = t + 1; }
+                    N1 += t;                                                      // :148
+                    N++;                                                          // :149, times += 1 :150
+                }
+            }
+            N = __reduce_add_sync(0xffffffffu, N);
+            for (int o = 16; o > 0; o >>= 1) N1 += __shfl_xor_sync(0xffffffffu, N1, o);
+            __syncwarp();                                                         // times of this block visible to the next
+            if (lane == 0) {
+                int32_t m = A.b_m[b], L1 = A.b_L1[b], L2 = hi - lo + 1;
+                A.b_N[b] = N;
+                A.b_N1[b] = N1;
+                A.b_a[b] = icl_p_raw((int64_t)A.S[A.b_top[b]], m, A.g0, N1, N, L1, L2);
+            }
+            j0 = nj0; j1 = nj1; lo = nlo; hi = nhi;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) k_pvalue(PvalArgs A) {
+    extern __shared__ uint16_t tsm[];
+    const int32_t p = A.pair_order[blockIdx.x];
+    const int64_t np_ = A.off[p + 1] - A.off[p];
+    const uint32_t nb = A.blkidx[A.n + A.off[p + 1]] - A.blkidx[A.n + A.off[p]] + A.blkidx[A.off[p + 1]] - A.blkidx[A.off[p]];
+    if (np_ <= A.smem_cap && nb < 65000u) pvalue_pair<true>(A, p, tsm);
+    else pvalue_pair<false>(A, p, tsm);
+}
+#endif
+
 static int phase_pvalue(icl_ctx *c) {
     Status &st = c->st;
-    const int64_t n = c->n, V = 2 * n;
+    const int64_t n = c->n, NB = c->NB;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    const int64_t nslots = V / 3 + 2 * (int64_t)P + 2;
-    if (c->times.reserve(st, n) || c->blk_N.reserve(st, nslots) || c->blk_N1.reserve(st, nslots) ||
-        c->blk_L1.reserve(st, nslots) || c->blk_L2.reserve(st, nslots) || c->blk_a.reserve(st, nslots))
-        return st.code;
-    int32_t *times = c->times.p;
-    ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) { times[i] = 1; }));       // get_matrix :34
-    const int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p, *S = c->S.p, *rowptr = c->rowptr.p, *rmin = c->d_rmin.p;
-    const int32_t *members = c->members.p, *blk_top = c->blk_top.p, *blk_m = c->blk_m.p, *blk_ms = c->blk_ms.p;
-    const int32_t *nblk = c->nblk.p, *porder = c->d_pair_order.p;
-    const int64_t *off = c->d_pair_off.p, *rb = c->d_rb.p;
-    int32_t *bN = c->blk_N.p, *bL1 = c->blk_L1.p, *bL2 = c->blk_L2.p;
-    int64_t *bN1 = c->blk_N1.p;
-    double *ba = c->blk_a.p;
-    const int32_t g0 = c->prm.g0;
-    ICL_CUDA(st, foreach_warp(s, (int64_t)P, ICL_LAMBDA(int64_t j) {
-        int32_t p = porder[j];
-        for (int32_t d = 0; d < 2; d++) {
-            int32_t it = d * P + p;
-            int64_t a = off[p] + (d ? n : 0);
-            int64_t slot = a / 3 + it;
-            for (int32_t bi = 0; bi < nblk[it]; bi++) {
-                int32_t m = blk_m[slot + bi], ms = blk_ms[slot + bi];
-                int32_t l1min = l1[members[ms]], l1max = l1[members[ms + m - 1]];     // members are loc1-ascending
-                int32_t l2min = l2[members[ms]], l2max = l2min;
-                for (int32_t k = 1; k < m; k++) {
-                    int32_t y = l2[members[ms + k]];
-                    l2min = y < l2min ? y : l2min;
-                    l2max = y > l2max ? y : l2max;
-                }
-                int32_t j0 = rowptr[rb[p] + (l1min - rmin[p])], j1 = rowptr[rb[p] + (l1max - rmin[p]) + 1];
-                int32_t N = 0;
+    if (c->times.reserve(st, n) || c->b_N.reserve(st, NB) || c->b_N1.reserve(st, NB) || c->b_a.reserve(st, NB)) return st.code;
+    PvalArgs A;
+    A.n = n; A.P = P; A.g0 = c->prm.g0;
+    A.pair_order = c->d_pair_order.p; A.l2 = c->loc2s.p; A.S = c->S.p; A.b_top = c->b_top.p; A.b_m = c->b_m.p;
+    A.b_j0 = c->b_j0.p; A.b_j1 = c->b_j1.p; A.b_l2min = c->b_l2min.p; A.b_l2max = c->b_l2max.p; A.b_L1 = c->b_L1.p;
+    A.off = c->d_pair_off.p; A.blkidx = c->blkidx.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p; A.b_a = c->b_a.p;
+    if (P == 0) return 0;
+#ifndef ICL_EMU
+    int64_t maxnp = 1;
+    for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
+    const int64_t cap_limit = 100 * 1024;                      // uint16 entries: 200 KB of the 227 KB
+    A.smem_cap = (int32_t)std::min<int64_t>(maxnp, cap_limit);
+    size_t smem = (size_t)A.smem_cap * sizeof(uint16_t);
+    ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    k_pvalue<<<(unsigned)P, 32, smem, s>>>(A);
+    ICL_CUDA(st, cudaGetLastError());
+#else
+    A.smem_cap = 0;
+    for (int32_t jp = 0; jp < P; jp++) {
+        int32_t p = A.pair_order[jp];
+        int64_t a = A.off[p], np_ = A.off[p + 1] - a;
+        for (int64_t i = 0; i < np_; i++) A.times[a + i] = 1;
+        for (int d = 0; d < 2; d++) {
+            uint32_t b0 = A.blkidx[(d ? n : 0) + a], b1 = A.blkidx[(d ? n : 0) + a + np_];
+            for (uint32_t b = b0; b < b1; b++) {
+                int32_t N = 0, lo = A.b_l2min[b], hi = A.b_l2max[b];
                 int64_t N1 = 0;
-                for (int32_t q = j0; q < j1; q++) {                                      // :134-137 inclusive box
-                    int32_t y = l2[q];
-                    if (y >= l2min && y <= l2max) { N1 += times[q]; N++; times[q]++; }   // :148-150
-                }
-                int32_t L1 = l1max - l1min + 1, L2 = l2max - l2min + 1;
-                bN[slot + bi] = N;
-                bN1[slot + bi] = N1;
-                bL1[slot + bi] = L1;
-                bL2[slot + bi] = L2;
-                ba[slot + bi] = icl_p_raw((int64_t)S[blk_top[slot + bi]], m, g0, N1, N, L1, L2);
+                for (int32_t q = A.b_j0[b]; q < A.b_j1[b]; q++)
+                    if (A.l2[q] >= lo && A.l2[q] <= hi) { N1 += A.times[q]; N++; A.times[q]++; }
+                A.b_N[b] = N;
+                A.b_N1[b] = N1;
+                A.b_a[b] = icl_p_raw((int64_t)A.S[A.b_top[b]], A.b_m[b], A.g0, N1, N, A.b_L1[b], hi - lo + 1);
             }
         }
-    }));
+    }
+#endif
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // ABI: icl_extract
 // ------------------------------------------------------------------------------------------------
-template <class T>
-static T *host_array(int64_t n) { return (T *)malloc((size_t)(n > 0 ? n : 1) * sizeof(T)); }
-
 extern "C" void icl_free_blocks(icl_blocks *b) {
-    if (!b) return;
-    free(b->pair); free(b->dir); free(b->score); free(b->m); free(b->L); free(b->N); free(b->N1);
-    free(b->L1); free(b->L2); free(b->p_raw); free(b->member_off); free(b->loc1); free(b->loc2); free(b->member_idx);
-    memset(b, 0, sizeof(*b));
+    if (b) memset(b, 0, sizeof(*b));        // the arrays live in page-locked staging owned by the context
 }
 
-extern "C" int icl_extract(icl_ctx *c, const int32_t *order_fwd, const int32_t *order_rev, icl_blocks *out) {
+struct Stage {                               // bump allocator over the context's pinned staging buffer
+    uint8_t *base;
+    size_t used;
+    template <class T> T *take(int64_t count) {
+        used = (used + 63) & ~(size_t)63;
+        T *p = (T *)(base + used);
+        used += (size_t)(count > 0 ? count : 1) * sizeof(T);
+        return p;
+    }
+};
+
+extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
+                           icl_blocks *out) {
     if (!c) return ICL_ERR_ARG;
     if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_extract: icl_dp has not succeeded");
-    if (!out || (c->n > 0 && (!order_fwd || !order_rev))) return fail(c, ICL_ERR_ARG, "icl_extract: null argument");
+    if (!out || (c->n > 0 && (!argsort_fwd || !argsort_rev))) return fail(c, ICL_ERR_ARG, "icl_extract: null argument");
     memset(out, 0, sizeof(*out));
     Status &st = c->st;
     st.code = 0;
@@ -838,13 +1002,25 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *order_fwd, const int32_t *
     ICL_CUDA(st, cudaSetDevice(c->device));
 #endif
     cudaStream_t s = c->stream;
-    const int64_t n = c->n;
+    const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     c->timers[ICL_T_EXTRACT].start(s);
-    if (c->order_in.reserve(st, 2 * n)) return st.code;
+    if (c->order_in.reserve(st, 2 * n) || c->rank2v.reserve(st, V)) return st.code;
     if (n > 0) {
-        ICL_CUDA(st, h2d(c->order_in.p, order_fwd, (size_t)n * sizeof(int32_t), s));
-        ICL_CUDA(st, h2d(c->order_in.p + n, order_rev, (size_t)n * sizeof(int32_t), s));
+        ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)n * sizeof(int32_t), s));
+        ICL_CUDA(st, h2d(c->order_in.p + n, argsort_rev, (size_t)n * sizeof(int32_t), s));
+        // rank2v[V position] = point examined at that rank position of its item
+        const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
+        const int64_t *off = c->d_pair_off.p;
+        int32_t *rank2v = c->rank2v.p;
+        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
+            int32_t p = ps[i];
+            int64_t a = off[p], np_ = off[p + 1] - a, j = i - a;
+            int32_t rf = ord[i], rr = ord[n + i];
+            if (rf < 0 || rf >= np_ || rr < 0 || rr >= np_) return;               // reported by phase_extract
+            rank2v[a + (np_ - 1 - j)] = (int32_t)(a + (np_ - 1 - rf));
+            rank2v[n + a + (np_ - 1 - j)] = mmap[a + (np_ - 1 - rr)];
+        }));
     }
     if (phase_extract(c)) return st.code;
     c->timers[ICL_T_EXTRACT].stop(s);
@@ -852,116 +1028,114 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *order_fwd, const int32_t *
     if (phase_pvalue(c)) return st.code;
     c->timers[ICL_T_PVALUE].stop(s);
     c->timers[ICL_T_GATHER].start(s);
-    // per-item block counts -> output offsets in (pair, direction) order
-    std::vector<int32_t> h_nblk(2 * (size_t)P + 1, 0);
-    int32_t hs[4] = {0, 0, 0, 0};
-    if (P > 0) ICL_CUDA(st, d2h(h_nblk.data(), c->nblk.p, (size_t)2 * P * sizeof(int32_t), s));
-    ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), s));
-    ICL_CUDA(st, dev_sync(s));
-    if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_extract: order array holds an index outside its pair segment");
-    std::vector<int64_t> h_out_base(2 * (size_t)P + 1, 0);      // output rank r = 2*pair + dir
-    for (int32_t r = 0; r < 2 * P; r++) {
-        int32_t it = (r & 1) * P + (r >> 1);
-        h_out_base[r + 1] = h_out_base[r] + h_nblk[it];
-    }
-    const int64_t NB = h_out_base[2 * (size_t)P];
-    if (c->d_out_base.reserve(st, 2 * P + 1)) return st.code;
-    ICL_CUDA(st, h2d(c->d_out_base.p, h_out_base.data(), (size_t)(2 * P + 1) * sizeof(int64_t), s));
-    if (c->o_pair.reserve(st, NB) || c->o_dir.reserve(st, NB) || c->o_m.reserve(st, NB) || c->o_L.reserve(st, NB) ||
-        c->o_N.reserve(st, NB) || c->o_L1.reserve(st, NB) || c->o_L2.reserve(st, NB) || c->o_slot.reserve(st, NB) ||
-        c->o_score.reserve(st, NB) || c->o_N1.reserve(st, NB) || c->o_a.reserve(st, NB) ||
-        c->o_mcnt.reserve(st, NB + 2) || c->o_moff.reserve(st, NB + 2))
+    // select the blocks the caller wants (m >= min_members); every accepted block has already bumped `times`
+    const int64_t NB = c->NB;
+    if (c->o_flag.reserve(st, NB + 2) || c->o_bidx.reserve(st, NB + 2) || c->o_mcnt.reserve(st, NB + 2) || c->o_moff.reserve(st, NB + 2))
         return st.code;
     {
-        const int64_t *ob = c->d_out_base.p, *off = c->d_pair_off.p;
-        const int32_t *S = c->S.p, *blk_top = c->blk_top.p, *blk_m = c->blk_m.p, *blk_L = c->blk_L.p, *bN = c->blk_N.p;
-        const int32_t *bL1 = c->blk_L1.p, *bL2 = c->blk_L2.p;
-        const int64_t *bN1 = c->blk_N1.p;
-        const double *ba = c->blk_a.p;
-        int32_t *o_pair = c->o_pair.p, *o_dir = c->o_dir.p, *o_m = c->o_m.p, *o_L = c->o_L.p, *o_N = c->o_N.p;
-        int32_t *o_L1 = c->o_L1.p, *o_L2 = c->o_L2.p, *o_slot = c->o_slot.p;
-        int64_t *o_score = c->o_score.p, *o_N1 = c->o_N1.p;
-        double *o_a = c->o_a.p;
-        uint32_t *o_mcnt = c->o_mcnt.p;
-        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t g) {
-            int32_t lo = 0, hi = 2 * P;                 // last rank with ob[r] <= g
-            while (lo < hi) {
-                int32_t mid = lo + ((hi - lo + 1) >> 1);
-                if (ob[mid] <= g) lo = mid; else hi = mid - 1;
-            }
-            int32_t r = lo, p = r >> 1, d = r & 1, it = d * P + p;
-            int64_t a = off[p] + (d ? n : 0);
-            int64_t sl = a / 3 + it + (g - ob[r]);
-            o_pair[g] = p;
-            o_dir[g] = d;
-            o_m[g] = blk_m[sl];
-            o_mcnt[g] = (uint32_t)blk_m[sl];
-            o_L[g] = blk_L[sl];
-            o_N[g] = bN[sl];
-            o_N1[g] = bN1[sl];
-            o_L1[g] = bL1[sl];
-            o_L2[g] = bL2[sl];
-            o_a[g] = ba[sl];
-            o_score[g] = S[blk_top[sl]];
-            o_slot[g] = (int32_t)sl;
+        const int32_t *b_m = c->b_m.p;
+        uint32_t *flag = c->o_flag.p, *mcnt = c->o_mcnt.p;
+        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
+            bool keep = b_m[b] >= min_members;
+            flag[b] = keep ? 1u : 0u;
+            mcnt[b] = keep ? (uint32_t)b_m[b] : 0u;
         }));
     }
+    if (exclusive_sum_u32(st, c->tmp, c->o_flag.p, c->o_bidx.p, NB, s)) return st.code;
     if (exclusive_sum_u32(st, c->tmp, c->o_mcnt.p, c->o_moff.p, NB, s)) return st.code;
-    uint32_t NM = 0;
-    ICL_CUDA(st, d2h(&NM, c->o_moff.p + NB, sizeof(uint32_t), s));
+    uint32_t tot[2] = {0, 0};
+    ICL_CUDA(st, d2h(&tot[0], c->o_bidx.p + NB, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(&tot[1], c->o_moff.p + NB, sizeof(uint32_t), s));
     ICL_CUDA(st, dev_sync(s));
-    if (c->o_loc1.reserve(st, NM) || c->o_loc2.reserve(st, NM) || c->o_idx.reserve(st, NM)) return st.code;
+    const int64_t NBo = tot[0], NMo = tot[1];
+    // device staging, one allocation, same layout as the pinned host staging
+    Stage ds{nullptr, 0}, hs{nullptr, 0};
+    auto layout = [&](Stage &g, icl_blocks &o) {
+        o.pair = g.take<int32_t>(NBo); o.dir = g.take<int32_t>(NBo); o.score = g.take<int64_t>(NBo);
+        o.m = g.take<int32_t>(NBo); o.L = g.take<int32_t>(NBo); o.N = g.take<int32_t>(NBo); o.N1 = g.take<int64_t>(NBo);
+        o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo); o.p_raw = g.take<double>(NBo);
+        o.member_off = g.take<int64_t>(NBo + 1); o.loc1 = g.take<int32_t>(NMo); o.loc2 = g.take<int32_t>(NMo);
+        o.member_idx = g.take<int32_t>(NMo);
+    };
+    icl_blocks dv{}, probe{};
+    layout(ds, probe);                                         // size only
+    const size_t bytes = ds.used + 64;
+    if (c->d_stage.reserve(st, bytes)) return st.code;
+    if (bytes > c->h_stage_cap) {
+#ifndef ICL_EMU
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_cap = 0;
+        ICL_CUDA(st, cudaHostAlloc((void **)&c->h_stage, bytes + bytes / 4, cudaHostAllocDefault));
+#else
+        free(c->h_stage);
+        c->h_stage = (uint8_t *)malloc(bytes + bytes / 4);
+        if (!c->h_stage) return fail(c, ICL_ERR_NOMEM, "icl_extract: out of host memory");
+#endif
+        c->h_stage_cap = bytes + bytes / 4;
+    }
+    ds = Stage{c->d_stage.p, 0};
+    hs = Stage{c->h_stage, 0};
+    layout(ds, dv);
+    layout(hs, *out);
+    // Emission order is pair-major (pair, direction, acceptance order) while block indices are direction-major
+    // (V space): permute the selected blocks, then lay their members out with a prefix sum in output order.
+    if (c->o_src.reserve(st, NBo + 1) || c->o_mout.reserve(st, NBo + 2) || c->o_moff2.reserve(st, NBo + 2)) return st.code;
     {
-        const uint32_t *moff = c->o_moff.p, *perm = c->perm.p;
-        const int32_t *o_slot = c->o_slot.p, *blk_ms = c->blk_ms.p, *members = c->members.p, *l1 = c->loc1s.p, *l2 = c->loc2s.p;
-        int32_t *o_loc1 = c->o_loc1.p, *o_loc2 = c->o_loc2.p, *o_idx = c->o_idx.p;
-        ICL_CUDA(st, foreach(s, (int64_t)NM, ICL_LAMBDA(int64_t g) {
-            int64_t lo = 0, hi = NB;                    // last block with moff[b] <= g (blocks have m >= 1)
-            while (lo < hi) {
-                int64_t mid = lo + ((hi - lo + 1) >> 1);
-                if ((int64_t)moff[mid] <= g) lo = mid; else hi = mid - 1;
-            }
-            int32_t i = members[blk_ms[o_slot[lo]] + (g - moff[lo])];
-            o_loc1[g] = l1[i];
-            o_loc2[g] = l2[i];
-            o_idx[g] = (int32_t)perm[i];
+        const uint32_t *flag = c->o_flag.p, *sel = c->o_bidx.p, *blkidx = c->blkidx.p;
+        const int32_t *b_m = c->b_m.p, *b_item = c->b_item.p;
+        const int64_t *off = c->d_pair_off.p;
+        uint32_t *o_src = c->o_src.p, *o_mout = c->o_mout.p;
+        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
+            if (!flag[b]) return;
+            int32_t it = b_item[b];
+            uint32_t selF = sel[blkidx[n]];                      // selected forward blocks in total
+            uint32_t g;
+            if (it < P) g = (sel[blkidx[n + off[it]]] - selF) + sel[b];                 // anti-diagonal blocks of earlier pairs
+            else g = sel[blkidx[off[it - P + 1]]] + (sel[b] - selF);                    // forward blocks of pairs <= p
+            o_src[g] = (uint32_t)b;
+            o_mout[g] = (uint32_t)b_m[b];
         }));
     }
-    out->n_blocks = NB;
-    out->n_members = NM;
-    out->pair = host_array<int32_t>(NB); out->dir = host_array<int32_t>(NB); out->score = host_array<int64_t>(NB);
-    out->m = host_array<int32_t>(NB); out->L = host_array<int32_t>(NB); out->N = host_array<int32_t>(NB);
-    out->N1 = host_array<int64_t>(NB); out->L1 = host_array<int32_t>(NB); out->L2 = host_array<int32_t>(NB);
-    out->p_raw = host_array<double>(NB); out->member_off = host_array<int64_t>(NB + 1);
-    out->loc1 = host_array<int32_t>(NM); out->loc2 = host_array<int32_t>(NM); out->member_idx = host_array<int32_t>(NM);
-    if (!out->pair || !out->dir || !out->score || !out->m || !out->L || !out->N || !out->N1 || !out->L1 || !out->L2 ||
-        !out->p_raw || !out->member_off || !out->loc1 || !out->loc2 || !out->member_idx) {
-        icl_free_blocks(out);
-        return fail(c, ICL_ERR_NOMEM, "icl_extract: out of host memory");
+    if (exclusive_sum_u32(st, c->tmp, c->o_mout.p, c->o_moff2.p, NBo, s)) return st.code;
+    {
+        const uint32_t *o_src = c->o_src.p, *omoff = c->o_moff2.p, *b_moff = c->b_moff.p, *perm = c->perm.p;
+        const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;
+        const int32_t *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_item = c->b_item.p, *members = c->members.p;
+        const int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p;
+        const int64_t *b_N1 = c->b_N1.p;
+        const double *b_a = c->b_a.p;
+        icl_blocks o = dv;
+        ICL_CUDA(st, foreach(s, NBo, ICL_LAMBDA(int64_t g) {
+            if (g == NBo - 1) o.member_off[NBo] = NMo;
+            uint32_t b = o_src[g];
+            int32_t it = b_item[b];
+            o.pair[g] = it >= P ? it - P : it;
+            o.dir[g] = it >= P ? 1 : 0;
+            o.score[g] = S[b_top[b]];
+            o.m[g] = b_m[b];
+            o.L[g] = b_L[b];
+            o.N[g] = b_N[b];
+            o.N1[g] = b_N1[b];
+            o.L1[g] = b_L1[b];
+            o.L2[g] = b_l2max[b] - b_l2min[b] + 1;
+            o.p_raw[g] = b_a[b];
+            o.member_off[g] = omoff[g];
+            uint32_t src = b_moff[b], dst = omoff[g];
+            for (int32_t k = 0; k < b_m[b]; k++) {
+                int32_t i = members[src + k];
+                o.loc1[dst + k] = l1[i];
+                o.loc2[dst + k] = l2[i];
+                o.member_idx[dst + k] = (int32_t)perm[i];
+            }
+        }));
+        if (NBo == 0) ICL_CUDA(st, dev_memset(dv.member_off, 0, sizeof(int64_t), s));
     }
-    std::vector<uint32_t> h_moff((size_t)NB + 1, 0);
-    if (NB > 0) {
-        ICL_CUDA(st, d2h(out->pair, c->o_pair.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->dir, c->o_dir.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->score, c->o_score.p, (size_t)NB * 8, s));
-        ICL_CUDA(st, d2h(out->m, c->o_m.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->L, c->o_L.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->N, c->o_N.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->N1, c->o_N1.p, (size_t)NB * 8, s));
-        ICL_CUDA(st, d2h(out->L1, c->o_L1.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->L2, c->o_L2.p, (size_t)NB * 4, s));
-        ICL_CUDA(st, d2h(out->p_raw, c->o_a.p, (size_t)NB * 8, s));
-    }
-    ICL_CUDA(st, d2h(h_moff.data(), c->o_moff.p, (size_t)(NB + 1) * 4, s));
-    if (NM > 0) {
-        ICL_CUDA(st, d2h(out->loc1, c->o_loc1.p, (size_t)NM * 4, s));
-        ICL_CUDA(st, d2h(out->loc2, c->o_loc2.p, (size_t)NM * 4, s));
-        ICL_CUDA(st, d2h(out->member_idx, c->o_idx.p, (size_t)NM * 4, s));
-    }
+    ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, ds.used, s));
     c->timers[ICL_T_GATHER].stop(s);
     ICL_CUDA(st, dev_sync(s));
-    for (int64_t b = 0; b <= NB; b++) out->member_off[b] = h_moff[b];
-    c->counters[2] = 7;   // tops, extract, times init, pvalue, gather blocks, gather members + CUB scan
+    out->n_blocks = NBo;
+    out->n_members = NMo;
+    c->counters[2] = 11;   // rank2v, rankpos, root keys, tree walk, flags, emit, pvalue, select, gather + CUB sort/scans
     return ICL_OK;
 }
 

@@ -1,0 +1,120 @@
+/*
+ * npsort.c — segmented argsort that calls NUMPY'S OWN argsort routine, without the GIL.
+ *
+ * The reference orders block extraction with pandas' sort_values(by=['score1'], ascending=False)
+ * (wgdi/collinearity.py:49,60), which ends in numpy.argsort(kind='quicksort') on an int64 array.  That
+ * sort is unstable and its tie permutation depends on the numpy build and on the CPU (AVX-512 / AVX2 /
+ * scalar kernels differ; SURVEY.md hazard H1), so it cannot be re-implemented — it has to be the same
+ * routine.  numpy.argsort on a contiguous aligned 1-D int64 array does exactly this
+ * (numpy/_core/src/multiarray/item_selection.c, _new_argsortlike): fill the index array with 0..n-1 and
+ * call   PyDataType_GetArrFuncs(descr)->argsort[NPY_QUICKSORT](values, index, n, arr).
+ * This module fetches that function pointer from the running numpy and calls it for every chromosome-pair
+ * segment from a pthread pool.  The Python side verifies on start-up that the result is identical to
+ * numpy.argsort and otherwise falls back to one numpy call per segment (wgdi_b200/engine.py).
+ *
+ * Python API:  seg_argsort(keys:int64[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads:int) -> 0
+ *   out[off[s] + j] = argsort(keys[off[s]:off[s+1]], kind='quicksort')[j]   (narrowed to int32)
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#include <numpy/arrayobject.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+typedef struct {
+    PyArray_ArgSortFunc *fn;
+    const int64_t *keys;
+    const int64_t *off;
+    const int32_t *seg_order;
+    int32_t *out;
+    int64_t n_seg;
+    volatile int64_t next;
+    volatile int err;
+} job_t;
+
+static void *worker(void *vp)
+{
+    job_t *j = (job_t *)vp;
+    npy_intp *idx = NULL;
+    int64_t cap = 0;
+    for (;;) {
+        int64_t s = __sync_fetch_and_add(&j->next, 1);
+        if (s >= j->n_seg) break;
+        int64_t seg = j->seg_order ? j->seg_order[s] : s;
+        int64_t a = j->off[seg], n = j->off[seg + 1] - a;
+        if (n <= 0) continue;
+        if (n > cap) {
+            free(idx);
+            cap = n + n / 4 + 64;
+            idx = (npy_intp *)malloc((size_t)cap * sizeof(npy_intp));
+            if (!idx) { j->err = 1; break; }
+        }
+        for (int64_t i = 0; i < n; i++) idx[i] = i;                    /* as _new_argsortlike does */
+        if (j->fn((void *)(j->keys + a), idx, (npy_intp)n, NULL) < 0) { j->err = 2; break; }
+        int32_t *o = j->out + a;
+        for (int64_t i = 0; i < n; i++) o[i] = (int32_t)idx[i];
+    }
+    free(idx);
+    return NULL;
+}
+
+static PyObject *seg_argsort(PyObject *self, PyObject *args)
+{
+    PyArrayObject *keys, *off, *order, *out;
+    int threads;
+    if (!PyArg_ParseTuple(args, "O!O!O!O!i", &PyArray_Type, &keys, &PyArray_Type, &off, &PyArray_Type, &order,
+                          &PyArray_Type, &out, &threads))
+        return NULL;
+    if (PyArray_TYPE(keys) != NPY_INT64 || PyArray_TYPE(off) != NPY_INT64 || PyArray_TYPE(order) != NPY_INT32 ||
+        PyArray_TYPE(out) != NPY_INT32 || !PyArray_IS_C_CONTIGUOUS(keys) || !PyArray_IS_C_CONTIGUOUS(off) ||
+        !PyArray_IS_C_CONTIGUOUS(order) || !PyArray_IS_C_CONTIGUOUS(out) || !PyArray_ISALIGNED(keys) ||
+        PyArray_NDIM(keys) != 1 || PyArray_NDIM(out) != 1 || PyArray_SIZE(out) < PyArray_SIZE(keys) ||
+        PyArray_SIZE(off) < 1 || PyArray_SIZE(order) != PyArray_SIZE(off) - 1) {
+        PyErr_SetString(PyExc_TypeError, "seg_argsort(keys:int64[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads)");
+        return NULL;
+    }
+    PyArray_ArgSortFunc *fn = PyDataType_GetArrFuncs(PyArray_DESCR(keys))->argsort[NPY_QUICKSORT];
+    if (!fn) {
+        PyErr_SetString(PyExc_RuntimeError, "numpy exposes no int64 quicksort argsort routine");
+        return NULL;
+    }
+    job_t j;
+    j.fn = fn;
+    j.keys = (const int64_t *)PyArray_DATA(keys);
+    j.off = (const int64_t *)PyArray_DATA(off);
+    j.seg_order = (const int32_t *)PyArray_DATA(order);
+    j.out = (int32_t *)PyArray_DATA(out);
+    j.n_seg = PyArray_SIZE(off) - 1;
+    j.next = 0;
+    j.err = 0;
+    if (threads < 1) threads = 1;
+    if (threads > 128) threads = 128;
+    if (threads > j.n_seg) threads = (int)(j.n_seg > 0 ? j.n_seg : 1);
+    Py_BEGIN_ALLOW_THREADS
+    pthread_t th[128];
+    int started = 0;
+    for (int t = 1; t < threads; t++)
+        if (pthread_create(&th[started], NULL, worker, &j) == 0) started++;
+    worker(&j);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    Py_END_ALLOW_THREADS
+    if (j.err) {
+        PyErr_SetString(PyExc_RuntimeError, j.err == 1 ? "seg_argsort: out of memory" : "seg_argsort: numpy argsort failed");
+        return NULL;
+    }
+    return PyLong_FromLong(0);
+}
+
+static PyMethodDef methods[] = {
+    {"seg_argsort", seg_argsort, METH_VARARGS, "segmented numpy argsort(kind='quicksort') on int64, multi-threaded"},
+    {NULL, NULL, 0, NULL}};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_npsort", NULL, -1, methods, NULL, NULL, NULL, NULL};
+
+PyMODINIT_FUNC PyInit__npsort(void)
+{
+    import_array();
+    return PyModule_Create(&moddef);
+}

@@ -21,6 +21,33 @@ import numpy as np
 from . import _lib
 from ._lib import IclError, icl_blocks, icl_params
 
+try:                                    # numpy's own argsort routine, GIL-free (wgdi_b200/csrc/npsort.c)
+    from . import _npsort
+except ImportError:                     # not built: one numpy call per segment instead (same results)
+    _npsort = None
+_NPSORT_OK = None
+
+
+def _npsort_ok():
+    """True when the helper reproduces numpy.argsort(kind='quicksort') on tie-heavy int64 arrays of several
+    sizes in this process (checked once); any difference disables it."""
+    global _NPSORT_OK
+    if _NPSORT_OK is None:
+        ok = _npsort is not None
+        if ok:
+            rng = np.random.default_rng(12345)
+            sizes = np.array([0, 1, 2, 7, 16, 17, 64, 129, 255, 256, 257, 1000, 5000, 40000], np.int64)
+            off = np.r_[0, np.cumsum(sizes)].astype(np.int64)
+            keys = rng.integers(25, 60, int(off[-1])).astype(np.int64)
+            out = np.empty(len(keys), np.int32)
+            try:
+                _npsort.seg_argsort(keys, off, np.arange(len(sizes), dtype=np.int32), out, 3)
+                ok = all((out[a:b] == keys[a:b].argsort(kind="quicksort")).all() for a, b in zip(off[:-1], off[1:]))
+            except Exception:
+                ok = False
+        _NPSORT_OK = ok
+    return _NPSORT_OK
+
 
 @dataclass
 class ChainParams:
@@ -153,7 +180,8 @@ class IclEngine:
         self.n, self.n_pairs = n, int(n_pairs)
 
     def dp(self, params: ChainParams):
-        """Both DP directions; returns (score_fwd, score_rev) int64 views in (pair, loc1, loc2) order."""
+        """Both DP directions; returns (key_fwd, key_rev): int64 scores, every pair segment in REVERSED point
+        order (the array pandas' nargsort(ascending=False) hands to numpy.argsort)."""
         prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
                          float(params.coverage_ratio))
         sf, sr = self._buf("score_fwd", self.n, np.int64), self._buf("score_rev", self.n, np.int64)
@@ -168,48 +196,66 @@ class IclEngine:
         self._check(self.lib.icl_layout(self.ctx, off.ctypes.data, perm.ctypes.data))
         return off, perm
 
-    def rank(self, score_fwd, score_rev):
-        """The reference's descending-score permutation per (pair, direction), pair-local indices."""
-        of, orv = self._buf("order_fwd", self.n, np.int32), self._buf("order_rev", self.n, np.int32)
+    def rank(self, key_fwd, key_rev):
+        """numpy.argsort(kind='quicksort') of every pair segment of the arrays `dp` returned — the very sort the
+        reference reaches through pandas (collinearity.py:49,60).  Uses numpy's own compiled routine from a
+        thread pool without the GIL when the helper module is available (verified against numpy.argsort at
+        start-up), otherwise one numpy call per segment."""
+        af, ar = self._buf("argsort_fwd", self.n, np.int32), self._buf("argsort_rev", self.n, np.int32)
         off = self.pair_off
         sizes = np.diff(off)
+        if _npsort_ok():
+            order = np.argsort(-sizes, kind="stable").astype(np.int32)
+            _npsort.seg_argsort(key_fwd, off, order, af, self.sort_threads)
+            _npsort.seg_argsort(key_rev, off, order, ar, self.sort_threads)
+            return af, ar
         pairs = np.argsort(-sizes, kind="stable")
         pairs = pairs[sizes[pairs] > 0]
 
         def work(chunk):
             for p in chunk:
                 a, b = off[p], off[p + 1]
-                of[a:b] = nargsort_desc(score_fwd[a:b])
-                orv[a:b] = nargsort_desc(score_rev[a:b])
+                af[a:b] = key_fwd[a:b].argsort(kind="quicksort")
+                ar[a:b] = key_rev[a:b].argsort(kind="quicksort")
 
         if self._pool is None or len(pairs) < 2:
             work(pairs)
         else:
-            # longest pairs first, one per task; the small tail is batched to bound task overhead
             big = [[p] for p in pairs[sizes[pairs] >= 4096]]
             small = pairs[sizes[pairs] < 4096]
             step = max(1, len(small) // (4 * self.sort_threads) + 1)
             chunks = big + [small[i:i + step] for i in range(0, len(small), step)]
             list(self._pool.map(work, chunks))
-        return of, orv
+        return af, ar
 
-    def extract(self, order_fwd, order_rev) -> Blocks:
+    def raw_from_order(self, order):
+        """Convert a descending-score permutation (pair-local indices per segment, what
+        `sort_values(ascending=False)` yields) into the raw argsort-of-reversed-segment form `extract` takes."""
+        order = np.asarray(order)
+        out = np.empty(self.n, np.int32)
+        off = self.pair_off
+        for p in range(self.n_pairs):
+            a, b = off[p], off[p + 1]
+            out[a:b] = (b - a - 1) - order[a:b][::-1]
+        return out
+
+    def extract(self, argsort_fwd, argsort_rev, min_members: int = 1) -> Blocks:
         out = icl_blocks()
-        self._check(self.lib.icl_extract(self.ctx, order_fwd.ctypes.data, order_rev.ctypes.data, C.byref(out)))
-        try:
-            nb, nm = out.n_blocks, out.n_members
+        af = np.ascontiguousarray(argsort_fwd, np.int32)
+        ar = np.ascontiguousarray(argsort_rev, np.int32)
+        self._check(self.lib.icl_extract(self.ctx, af.ctypes.data, ar.ctypes.data, int(min_members), C.byref(out)))
+        nb, nm = out.n_blocks, out.n_members
 
-            def arr(ptr, n, dt):
-                if n == 0:
-                    return np.zeros(0, dt)
-                return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True)
-            res = Blocks(arr(out.pair, nb, np.int32), arr(out.dir, nb, np.int32), arr(out.score, nb, np.int64),
-                         arr(out.m, nb, np.int32), arr(out.L, nb, np.int32), arr(out.N, nb, np.int32),
-                         arr(out.N1, nb, np.int64), arr(out.L1, nb, np.int32), arr(out.L2, nb, np.int32),
-                         arr(out.p_raw, nb, np.float64), arr(out.member_off, nb + 1, np.int64),
-                         arr(out.loc1, nm, np.int32), arr(out.loc2, nm, np.int32), arr(out.member_idx, nm, np.int32))
-        finally:
-            self.lib.icl_free_blocks(C.byref(out))
+        def arr(ptr, n, dt):          # the staging is reused by the next call: copy out
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+        res = Blocks(arr(out.pair, nb, np.int32), arr(out.dir, nb, np.int32), arr(out.score, nb, np.int64),
+                     arr(out.m, nb, np.int32), arr(out.L, nb, np.int32), arr(out.N, nb, np.int32),
+                     arr(out.N1, nb, np.int64), arr(out.L1, nb, np.int32), arr(out.L2, nb, np.int32),
+                     arr(out.p_raw, nb, np.float64), arr(out.member_off, nb + 1, np.int64),
+                     arr(out.loc1, nm, np.int32), arr(out.loc2, nm, np.int32), arr(out.member_idx, nm, np.int32))
+        self.lib.icl_free_blocks(C.byref(out))
         return res
 
     def debug_dp(self, direction):
@@ -231,18 +277,18 @@ class IclEngine:
         return dict(edges=int(c[0]), launches_dp=int(c[1]), launches_extract=int(c[2]), rows=int(c[3]))
 
     # ---- whole hot path ------------------------------------------------------------------------
-    def run_resident(self, params: ChainParams, orders=None) -> Blocks:
+    def run_resident(self, params: ChainParams, min_members: int = 1) -> Blocks:
         """Hot path on points already uploaded: sort + DP -> host rank -> extraction + p values."""
         t0 = time.perf_counter()
-        sf, sr = self.dp(params)
+        kf, kr = self.dp(params)
         t1 = time.perf_counter()
-        of, orv = orders if orders is not None else self.rank(sf, sr)
+        af, ar = self.rank(kf, kr)
         t2 = time.perf_counter()
-        blocks = self.extract(of, orv)
+        blocks = self.extract(af, ar, min_members)
         t3 = time.perf_counter()
         self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3, extract=(t3 - t2) * 1e3)
         return blocks
 
-    def chain(self, pair_id, loc1, loc2, grading, n_pairs, params: ChainParams) -> Blocks:
+    def chain(self, pair_id, loc1, loc2, grading, n_pairs, params: ChainParams, min_members: int = 1) -> Blocks:
         self.upload(pair_id, loc1, loc2, grading, n_pairs)
-        return self.run_resident(params)
+        return self.run_resident(params, min_members)
