@@ -294,7 +294,7 @@ def main():
                          "kernel_ms": chain_ms, "algorithmic_bytes": DP_BYTES_PER_POINT * n_local,
                          "note": "latency-bound integer DP with a serial dependency chain; see DESIGN.md"},
             "phase_ms": {k: float(np.mean(v)) for k, v in dev_ms.items()},
-            "edges_per_step": counters["edges"],
+            "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

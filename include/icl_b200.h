@@ -156,7 +156,8 @@ int icl_debug_dp(icl_ctx *ctx, int32_t dir, int32_t *score, int32_t *pred, int32
 int icl_timings(icl_ctx *ctx, double *ms, int32_t n_slots);
 
 /* Counters of the most recent icl_dp: [0] edges enumerated, [1] kernels launched by icl_dp,
- * [2] kernels launched by icl_extract, [3] total dense rows. */
+ * [2] kernels launched by icl_extract, [3] total dense rows, [4] largest window span (positions),
+ * [5] DP kernel used (1 = shared-memory ring, 0 = generic). */
 int icl_counters(icl_ctx *ctx, int64_t *out, int32_t n_slots);
 
 /* "cuda" for the real library.  (A CPU emulation of the kernel bodies exists for the test-suite

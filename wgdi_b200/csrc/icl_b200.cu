@@ -62,6 +62,9 @@ struct icl_ctx {
     Buf<uint32_t> ecnt, eoff;
     Buf<uint2> edges;
     int64_t n_edges = 0;
+    int32_t max_span = 0;            // largest (target position - source position) over all edges
+    int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
+    bool force_generic_chain = false;
     // DP state (V space)
     Buf<int32_t> S, pred, depth;
     Buf<uint8_t> used;
@@ -83,6 +86,7 @@ struct icl_ctx {
 
     Timer timers[ICL_T_COUNT];
     int64_t counters[4] = {0, 0, 0, 0};
+    int64_t counters_ext[2] = {0, 0};
 };
 
 static std::string g_create_error;
@@ -186,6 +190,8 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
 #endif
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
+    const char *gen = getenv("ICL_B200_GENERIC_CHAIN");      // diagnostics: A/B the two DP kernels
+    c->force_generic_chain = gen && gen[0] == '1';
     *out = c;
     return ICL_OK;
 }
@@ -492,66 +498,286 @@ static int phase_edges(icl_ctx *c) {
     if (c->edges.reserve(st, (size_t)total + 1)) return st.code;
     const uint32_t *eoff = c->eoff.p;
     uint2 *edges = c->edges.p;
+    int32_t *stats = c->stats.p;
+    ICL_CUDA(st, dev_memset(c->stats.p + 3, 0, sizeof(int32_t), s));
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t e = eoff[v];
+        int32_t span = 0;
         ee.run(v, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
             edges[e++] = make_uint2((uint32_t)(k - (int32_t)v), (uint32_t)dr | ((uint32_t)dc << 8) | ((uint32_t)sc << 16));
+            span = k - (int32_t)v;                    // candidates are visited in increasing position
         });
+        // largest distance a source reaches ahead: sizes the shared-memory window of the DP kernel.
+        // Monotonic max: the plain read filters almost every atomic away.
+        if (span > stats[3]) atomic_max_i32(&stats[3], span);
     }));
+    int32_t span = 0;
+    ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
+    ICL_CUDA(st, dev_sync(s));
+    c->max_span = span;
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // phase: chaining DP (collinearity.py:81-93 / :103-115), one work item = (pair, direction).
-// v0: one thread walks the item's sources in order; the state machine is the reference's, verbatim:
+//
+// The sweep is order-dependent (strict `<` first-writer-wins, and a `break` whose state changes only on
+// updates), so the sources of an item are processed strictly in the reference's order by ONE executor
+// thread; the state machine is the reference's, verbatim:
 //   gap = mg2, row_old = row; for each candidate: if dc > gap and row_k beyond row_old: break;
 //   if s > 0 and score_k < score_i + s: update, gap = min(dc, gap), row_old = row_k.
+// What makes it fast is that nothing on the executor's dependency chain touches HBM or L2:
+//  * scores and path lengths of the mg-bounded window live in a shared-memory ring indexed by the point's
+//    position (a source only reaches points at most `span` positions ahead: the next mg1-1 rows are a
+//    contiguous slice of the sorted arrays);
+//  * a helper warp keeps the ring filled ahead of the executor (TMA bulk copies for the aligned interior,
+//    plain coalesced loads at the ends), writes final scores back behind it, and pulls the executor's
+//    read-only streams (edge offsets, edge records) into L1 ahead of use;
+//  * pred / depth / used are store-only for the executor (fire and forget).
+// Items are independent, so all (pair, direction) items of a comparison run concurrently, one CTA each,
+// longest item first.  k_chain_generic is the same loop on global memory (oversized windows, emulation).
 // ------------------------------------------------------------------------------------------------
+struct ChainArgs {
+    int64_t n;
+    int32_t P, mg2, RS, span;
+    const int32_t *order, *G;
+    const int64_t *off;
+    const uint32_t *eoff;
+    const uint2 *edges;
+    int32_t *S, *pred, *depth;
+    uint8_t *used;
+};
+
+ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
+    int32_t it = A.order[j];
+    int32_t p = it >= A.P ? it - A.P : it;
+    int64_t a = A.off[p] + (it >= A.P ? A.n : 0), b = A.off[p + 1] + (it >= A.P ? A.n : 0);
+    for (int64_t v = a; v < b; v++) {
+        int32_t Sv = A.S[v];
+        int32_t dv = (Sv != A.G[v]) ? A.depth[v] : 1;
+        int32_t gap = A.mg2, dr_old = 0;
+        bool uv = false;
+        for (uint32_t e = A.eoff[v], e1 = A.eoff[v + 1]; e < e1; e++) {
+            uint2 rec = A.edges[e];
+            int32_t dr = rec.y & 255, dc = (rec.y >> 8) & 255, sc = (int32_t)(rec.y >> 16);
+            if (dc > gap && dr > dr_old) break;
+            if (sc > 0) {
+                int64_t k = v + (int32_t)rec.x;
+                if (A.S[k] < Sv + sc) {
+                    A.S[k] = Sv + sc;
+                    A.pred[k] = (int32_t)v;
+                    A.depth[k] = dv + 1;
+                    A.used[k] = 1;
+                    uv = true;
+                    gap = dc < gap ? dc : gap;
+                    dr_old = dr;
+                }
+            }
+        }
+        if (uv) A.used[v] = 1;
+    }
+}
+
+#ifndef ICL_EMU
+#define ICL_CHAIN_CH 128            // TMA chunk: 128 points = 512 B
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void l1_touch(const void *p) {      // pull a line into L1 through the read-only path
+    uint32_t sink;
+    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(sink) : "l"(p) : "memory");
+    (void)sink;
+}
+
+__global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
+    extern __shared__ __align__(128) int32_t ring[];
+    int32_t *Sr = ring, *Dr = ring + A.RS;
+    __shared__ volatile long long ctl_loaded, ctl_retired;
+    __shared__ __align__(8) uint64_t bar;
+    const int32_t it = A.order[blockIdx.x];
+    const int32_t p = it >= A.P ? it - A.P : it;
+    const int64_t a = A.off[p] + (it >= A.P ? A.n : 0), b = A.off[p + 1] + (it >= A.P ? A.n : 0);
+    if (a == b) return;
+    const uint32_t M = (uint32_t)A.RS - 1;
+    if (threadIdx.x == 0) {
+        ctl_loaded = a;
+        ctl_retired = a;
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        // ---------------------------------------------------------------- executor (one thread)
+        if (lane != 0) return;
+        long long loaded = a;
+        const int32_t mg2 = A.mg2;
+        uint32_t e = __ldg(A.eoff + a);
+        for (int64_t v = a; v < b; v++) {
+            long long need = v + A.span + 1;
+            need = need < b ? need : b;
+            if (need > loaded) {                                  // the window of this source is not staged yet
+                do { loaded = ctl_loaded; } while (loaded < need);
+                __threadfence_block();
+            }
+            const uint32_t e1 = __ldg(A.eoff + v + 1);
+            const int32_t Sv = Sr[(uint32_t)v & M];
+            const int32_t dv = Dr[(uint32_t)v & M];
+            int32_t gap = mg2, dr_old = 0;
+            bool uv = false;
+            for (; e < e1; e++) {
+                const uint2 rec = __ldg(A.edges + e);
+                const int32_t dr = rec.y & 255, dc = (rec.y >> 8) & 255, sc = (int32_t)(rec.y >> 16);
+                if (dc > gap && dr > dr_old) break;               // collinearity.py:83-84
+                if (sc > 0) {
+                    const int64_t k = v + (int32_t)rec.x;
+                    const uint32_t slot = (uint32_t)k & M;
+                    if (Sr[slot] < Sv + sc) {                     // :87 strict <
+                        Sr[slot] = Sv + sc;
+                        Dr[slot] = dv + 1;
+                        A.pred[k] = (int32_t)v;
+                        A.depth[k] = dv + 1;
+                        A.used[k] = 1;
+                        uv = true;
+                        gap = dc < gap ? dc : gap;                // :92
+                        dr_old = dr;                              // :93
+                    }
+                }
+            }
+            e = e1;
+            if (uv) A.used[v] = 1;
+            if (((uint32_t)v & 31u) == 31u) {                     // let the helper retire finished points
+                __threadfence_block();
+                ctl_retired = v + 1;
+            }
+        }
+        __threadfence_block();
+        ctl_retired = b;
+        return;
+    }
+    // -------------------------------------------------------------------- helper warp
+    int64_t wb = a, ld = a, pf_src = a;
+    uint32_t parity = 0;
+    uint32_t pf_edge = 0;
+    bool pf_edge_init = false;
+    while (wb < b) {
+        long long r = 0;
+        if (lane == 0) r = ctl_retired;
+        r = __shfl_sync(0xffffffffu, r, 0);
+        __threadfence_block();
+        bool progress = false;
+        // 1. final scores of retired points -> HBM (coalesced)
+        if (r > wb) {
+            for (int64_t v = wb + lane; v < r; v += 32) A.S[v] = Sr[(uint32_t)v & M];
+            wb = r;
+            progress = true;
+        }
+        // 2. stage the initial scores (= grading, get_matrix :35-36) of the next points into the ring
+        int64_t lim = wb + A.RS;
+        lim = lim < b ? lim : b;
+        if (ld < lim) {
+            __syncwarp();
+            int64_t head_end = (ld + ICL_CHAIN_CH - 1) / ICL_CHAIN_CH * ICL_CHAIN_CH;      // first chunk boundary >= ld
+            int64_t body_end = lim / ICL_CHAIN_CH * ICL_CHAIN_CH;
+            if (head_end > lim) head_end = lim;
+            if (body_end < head_end) body_end = head_end;
+            for (int64_t v = ld + lane; v < head_end; v += 32) Sr[(uint32_t)v & M] = A.G[v];
+            for (int64_t v = body_end + lane; v < lim; v += 32) Sr[(uint32_t)v & M] = A.G[v];
+            for (int64_t v = ld + lane; v < lim; v += 32) Dr[(uint32_t)v & M] = 1;       // path = [label], :37
+            if (body_end > head_end) {
+                // ring slots being overwritten were read by the write-back above: order generic -> async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    uint32_t bytes = (uint32_t)(body_end - head_end) * 4u;
+                    mbar_expect_tx(&bar, bytes);
+                    uint32_t s0 = (uint32_t)head_end & M;
+                    uint32_t first = (uint32_t)A.RS - s0;            // points until the ring wraps
+                    uint32_t cnt = (uint32_t)(body_end - head_end);
+                    if (first > cnt) first = cnt;
+                    tma_load_1d(Sr + s0, A.G + head_end, first * 4u, &bar);
+                    if (cnt > first) tma_load_1d(Sr, A.G + head_end + first, (cnt - first) * 4u, &bar);
+                    mbar_wait(&bar, parity);
+                }
+                parity ^= 1;
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) ctl_loaded = lim;
+            ld = lim;
+            progress = true;
+        }
+        // 3. pull the executor's read-only streams into L1 ahead of it: 2 KB of edge offsets, 8 KB of edges
+        {
+            int64_t want = r + 512;
+            want = want < b ? want : b;
+            if (pf_src < r) pf_src = r;
+            for (int64_t v = pf_src + (int64_t)lane * 32; v < want; v += 32 * 32) l1_touch(A.eoff + v);
+            if (want > pf_src) pf_src = want;
+            uint32_t ecur = __ldg(A.eoff + r), eend = __ldg(A.eoff + b);
+            if (!pf_edge_init || pf_edge < ecur) { pf_edge = ecur; pf_edge_init = true; }
+            uint32_t ewant = ecur + 1024 < eend ? ecur + 1024 : eend;
+            for (uint32_t x = pf_edge + (uint32_t)lane * 16; x < ewant; x += 32 * 16) l1_touch(A.edges + x);
+            if (ewant > pf_edge) pf_edge = ewant;
+        }
+        if (!progress) __nanosleep(64);
+    }
+}
+#endif
+
 static int phase_chain(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
     if (c->S.reserve(st, V) || c->pred.reserve(st, V) || c->depth.reserve(st, V) || c->used.reserve(st, V)) return st.code;
-    ICL_CUDA(st, d2d(c->S.p, c->G.p, (size_t)V * sizeof(int32_t), s));            // get_matrix: score = grading
     ICL_CUDA(st, dev_memset(c->pred.p, 0xFF, (size_t)V * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->used.p, 0, (size_t)V, s));
-    int32_t *S = c->S.p, *pred = c->pred.p, *depth = c->depth.p;
-    uint8_t *used = c->used.p;
-    const int32_t *G = c->G.p, *order = c->d_item_order.p;
-    const int64_t *off = c->d_pair_off.p;
-    const uint32_t *eoff = c->eoff.p;
-    const uint2 *edges = c->edges.p;
-    const int32_t mg2 = c->prm.mg2;
-    ICL_CUDA(st, foreach_warp(s, 2 * (int64_t)P, ICL_LAMBDA(int64_t j) {
-        int32_t it = order[j];
-        int32_t p = it >= P ? it - P : it;
-        int64_t a = off[p] + (it >= P ? n : 0), b = off[p + 1] + (it >= P ? n : 0);
-        for (int64_t v = a; v < b; v++) {
-            int32_t Sv = S[v];
-            int32_t dv = (Sv != G[v]) ? depth[v] : 1;
-            int32_t gap = mg2, dr_old = 0;
-            bool uv = false;
-            for (uint32_t e = eoff[v], e1 = eoff[v + 1]; e < e1; e++) {
-                uint2 rec = edges[e];
-                int32_t dr = rec.y & 255, dc = (rec.y >> 8) & 255, sc = (int32_t)(rec.y >> 16);
-                if (dc > gap && dr > dr_old) break;
-                if (sc > 0) {
-                    int64_t k = v + (int32_t)rec.x;
-                    if (S[k] < Sv + sc) {
-                        S[k] = Sv + sc;
-                        pred[k] = (int32_t)v;
-                        depth[k] = dv + 1;
-                        used[k] = 1;
-                        uv = true;
-                        gap = dc < gap ? dc : gap;
-                        dr_old = dr;
-                    }
-                }
-            }
-            if (uv) used[v] = 1;
-        }
-    }));
+    ChainArgs A;
+    A.n = n; A.P = P; A.mg2 = c->prm.mg2; A.RS = 0; A.span = c->max_span;
+    A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
+    A.S = c->S.p; A.pred = c->pred.p; A.depth = c->depth.p; A.used = c->used.p;
+    if (P == 0 || n == 0) return 0;
+#ifndef ICL_EMU
+    // ring: window span + two TMA chunks of slack + what the helper needs to stay ahead, power of two
+    int64_t want = (int64_t)c->max_span + 4 * ICL_CHAIN_CH + 64;
+    int64_t RS = 512;
+    while (RS < want) RS <<= 1;
+    if (RS <= 16384 && !c->force_generic_chain) {
+        A.RS = (int32_t)RS;
+        size_t smem = (size_t)RS * 2 * sizeof(int32_t);
+        ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
+        k_chain_ring<<<(unsigned)(2 * P), 64, smem, s>>>(A);
+        ICL_CUDA(st, cudaGetLastError());
+        c->chain_kernel = 1;
+        return 0;
+    }
+#endif
+    ICL_CUDA(st, d2d(c->S.p, c->G.p, (size_t)V * sizeof(int32_t), s));            // get_matrix: score = grading
+    ICL_CUDA(st, foreach_warp(s, 2 * (int64_t)P, ICL_LAMBDA(int64_t j) { chain_generic_item(A, j); }));
+    c->chain_kernel = 0;
     return 0;
 }
 
@@ -610,6 +836,8 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int64_t *score_fwd, int
     c->counters[1] = 13;   // kernels launched by icl_dp (stats excluded): key, decode, pair_off, pair_meta, rowptr x2,
                            // mirror, rowptr_rev, edge count, edge fill, chain, export + CUB passes
     c->counters[3] = c->R;
+    c->counters_ext[0] = c->max_span;
+    c->counters_ext[1] = c->chain_kernel;
     c->dp_done = true;
     return ICL_OK;
 }
@@ -1148,7 +1376,7 @@ extern "C" int icl_timings(icl_ctx *c, double *ms, int32_t n_slots) {
 
 extern "C" int icl_counters(icl_ctx *c, int64_t *out, int32_t n_slots) {
     if (!c || !out) return ICL_ERR_ARG;
-    int32_t k = n_slots < 4 ? n_slots : 4;
-    for (int32_t i = 0; i < k; i++) out[i] = c->counters[i];
+    int32_t k = n_slots < 6 ? n_slots : 6;
+    for (int32_t i = 0; i < k; i++) out[i] = i < 4 ? c->counters[i] : c->counters_ext[i - 4];
     return k;
 }
