@@ -99,7 +99,9 @@ int icl_host_free(icl_ctx *ctx, void *ptr);
  * file order); pair_id[i] in [0, n_pairs).  The device orders the points of every pair by
  * (loc1, loc2) with a stable radix sort, i.e. equal coordinates keep upload order like the stable
  * lexsort of wgdi/run_colliearity.py:164-166.
- * Limits: 0 <= loc < 2^26, n_points < 2^30, bits(n_pairs) + bits(max loc1) + bits(max loc2) <= 64.
+ * Limits: 0 <= loc < 2^26, grading <= 255, n_points < 2^30, fewer than 2^24 points per pair,
+ * bits(n_pairs) + bits(max loc1) + bits(max loc2) <= 64; icl_dp additionally requires that no window of
+ * mg1 consecutive rows of a pair holds more than 65535 points.
  */
 int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
                const int32_t *pair_id, const int32_t *loc1, const int32_t *loc2, const int32_t *grading);

@@ -60,6 +60,7 @@ struct icl_ctx {
     Buf<int32_t> loc1s, loc2s, pair_s, rowptr, X1, X2, G, itemof, mmap, imap;
     // edges
     Buf<uint32_t> ecnt, eoff;
+    Buf<int32_t> lastsrc;
     Buf<uint2> edges;
     int64_t n_edges = 0;
     int32_t max_span = 0;            // largest (target position - source position) over all edges
@@ -118,20 +119,23 @@ static int bits_for(int64_t maxval) {
 // ------------------------------------------------------------------------------------------------
 #ifndef ICL_EMU
 __global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const int32_t *pair, const int32_t *l1,
-                                                     const int32_t *l2, int32_t *stats) {
-    int32_t m1 = 0, m2 = 0, bad = 0;
+                                                     const int32_t *l2, const int32_t *gr, int32_t *stats) {
+    int32_t m1 = 0, m2 = 0, mg = 0, bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int32_t a = l1[i], b = l2[i], p = pair[i];
         bad |= (a < 0) | (b < 0) | (p < 0) | (p >= P);
         m1 = max(m1, a);
         m2 = max(m2, b);
+        mg = max(mg, gr[i]);
     }
     m1 = __reduce_max_sync(0xffffffffu, m1);
     m2 = __reduce_max_sync(0xffffffffu, m2);
+    mg = __reduce_max_sync(0xffffffffu, mg);
     bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&stats[0], m1);
         atomicMax(&stats[1], m2);
+        atomicMax(&stats[3], mg);
         if (bad) atomicOr(&stats[2], 1);
     }
 }
@@ -143,7 +147,7 @@ static int input_stats(icl_ctx *c) {
 #ifndef ICL_EMU
     if (c->n > 0) {
         int64_t blocks = std::min<int64_t>((c->n + 255) / 256, 148 * 8);
-        k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, c->P, c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->stats.p);
+        k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, c->P, c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p, c->stats.p);
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
@@ -152,6 +156,7 @@ static int input_stats(icl_ctx *c) {
         if (a < 0 || b < 0 || p < 0 || p >= c->P) c->stats.p[2] = 1;
         c->stats.p[0] = std::max(c->stats.p[0], a);
         c->stats.p[1] = std::max(c->stats.p[1], b);
+        c->stats.p[3] = std::max(c->stats.p[3], c->in_grad.p[i]);
     }
 #endif
     return 0;
@@ -208,7 +213,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
-    c->ecnt.release(); c->eoff.release(); c->edges.release();
+    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release();
     c->S.release(); c->pred.release(); c->depth.release(); c->used.release(); c->score64.release();
     c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
@@ -284,6 +289,7 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
     ICL_CUDA(st, dev_sync(c->stream));
     if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_upload: negative coordinate or pair id outside [0, n_pairs)");
     if (hs[0] >= (1 << 26) || hs[1] >= (1 << 26)) return fail(c, ICL_ERR_LIMIT, "icl_upload: coordinates must be < 2^26");
+    if (hs[3] > 255) return fail(c, ICL_ERR_LIMIT, "icl_upload: grading values must be <= 255");
     c->bits1 = bits_for(hs[0]);
     c->bits2 = bits_for(hs[1]);
     c->bitsp = bits_for(P > 0 ? P - 1 : 0);
@@ -360,6 +366,9 @@ static int phase_sort(icl_ctx *c) {
     c->h_rb.assign(P + 1, 0);
     for (int32_t p = 0; p < P; p++) c->h_rb[p + 1] = c->h_rb[p] + c->h_nrows[p] + 1;
     c->R = c->h_rb[P];
+    for (int32_t p = 0; p < P; p++)
+        if (c->h_pair_off[p + 1] - c->h_pair_off[p] >= (1 << 24))
+            return fail(c, ICL_ERR_LIMIT, "icl_dp: a chromosome pair must hold fewer than 2^24 points");
     if (2 * c->R >= (1ll << 31)) return fail(c, ICL_ERR_LIMIT, "icl_dp: dense row index too large (sparse gene orders?)");
     c->h_pair_order.resize(P);
     std::iota(c->h_pair_order.begin(), c->h_pair_order.end(), 0);
@@ -478,34 +487,56 @@ struct EdgeEnum {
     }
 };
 
+// Edge record (8 bytes) of the flat per-item edge stream the DP kernel consumes:
+//   x = koff (bits 0-15: target position - source position) | dr << 16 | dc << 24
+//   y = s (bits 0-7: grading_k - (dr + dc), 0 when it cannot update) | adv << 8
+// adv (24 bits) is set on the first record of a source: how far the source position advances from the
+// previous source that has records (or from the item start).  Sources without candidates have no records and
+// cost the DP kernel nothing.
+#define ICL_EDGE_CHUNK 512           // records per TMA chunk (4 KB)
+
 static int phase_edges(icl_ctx *c) {
     Status &st = c->st;
-    const int64_t V = 2 * c->n;
+    const int64_t n = c->n, V = 2 * n;
+    const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->ecnt.reserve(st, V + 2) || c->eoff.reserve(st, V + 2)) return st.code;
+    if (c->ecnt.reserve(st, V + 2) || c->eoff.reserve(st, V + 2) || c->lastsrc.reserve(st, V + 2)) return st.code;
     EdgeEnum ee{c->X1.p, c->X2.p, c->G.p, c->itemof.p, c->rowptr.p, c->d_nrows.p, c->d_rb.p, c->R, c->P, c->prm.mg1, c->prm.mg2};
     uint32_t *ecnt = c->ecnt.p;
+    int32_t *lastsrc = c->lastsrc.p;
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t cnt = 0;
         ee.run(v, [&](int32_t, int32_t, int32_t, int32_t) { cnt++; });
         ecnt[v] = cnt;
+        lastsrc[v] = cnt ? (int32_t)v : -1;
     }));
     if (exclusive_sum_u32(st, c->tmp, c->ecnt.p, c->eoff.p, V, s)) return st.code;
+    if (inclusive_max_i32(st, c->tmp, c->lastsrc.p, V, s)) return st.code;      // last source <= v that has records
     uint32_t total = 0;
     ICL_CUDA(st, d2h(&total, c->eoff.p + V, sizeof(uint32_t), s));
     ICL_CUDA(st, dev_sync(s));
     c->n_edges = total;
-    if (c->edges.reserve(st, (size_t)total + 1)) return st.code;
+    if (c->edges.reserve(st, (size_t)total + 2 * ICL_EDGE_CHUNK + 16)) return st.code;
     const uint32_t *eoff = c->eoff.p;
     uint2 *edges = c->edges.p;
     int32_t *stats = c->stats.p;
+    const int32_t *itemof = c->itemof.p;
+    const int64_t *off = c->d_pair_off.p;
     ICL_CUDA(st, dev_memset(c->stats.p + 3, 0, sizeof(int32_t), s));
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t e = eoff[v];
+        if (eoff[v + 1] == e) return;
+        int32_t it = itemof[v];
+        int64_t a = off[it >= P ? it - P : it] + (it >= P ? n : 0);
+        int64_t prev = v > 0 ? lastsrc[v - 1] : -1;
+        if (prev < a) prev = a;
+        uint32_t adv = (uint32_t)(v - prev);
         int32_t span = 0;
         ee.run(v, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
-            edges[e++] = make_uint2((uint32_t)(k - (int32_t)v), (uint32_t)dr | ((uint32_t)dc << 8) | ((uint32_t)sc << 16));
             span = k - (int32_t)v;                    // candidates are visited in increasing position
+            edges[e++] = make_uint2(((uint32_t)span & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                                    ((uint32_t)sc & 0xffu) | (adv << 8));
+            adv = 0;
         });
         // largest distance a source reaches ahead: sizes the shared-memory window of the DP kernel.
         // Monotonic max: the plain read filters almost every atomic away.
@@ -515,6 +546,7 @@ static int phase_edges(icl_ctx *c) {
     ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
     c->max_span = span;
+    if (span >= 65536) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 65535 points inside one mg1-row window of a chromosome pair");
     return 0;
 }
 
@@ -548,38 +580,44 @@ struct ChainArgs {
     uint8_t *used;
 };
 
+// the reference sweep over the flat edge stream of one item, on global memory (oversized windows, emulation)
 ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
     int32_t it = A.order[j];
     int32_t p = it >= A.P ? it - A.P : it;
     int64_t a = A.off[p] + (it >= A.P ? A.n : 0), b = A.off[p + 1] + (it >= A.P ? A.n : 0);
-    for (int64_t v = a; v < b; v++) {
-        int32_t Sv = A.S[v];
-        int32_t dv = (Sv != A.G[v]) ? A.depth[v] : 1;
-        int32_t gap = A.mg2, dr_old = 0;
-        bool uv = false;
-        for (uint32_t e = A.eoff[v], e1 = A.eoff[v + 1]; e < e1; e++) {
-            uint2 rec = A.edges[e];
-            int32_t dr = rec.y & 255, dc = (rec.y >> 8) & 255, sc = (int32_t)(rec.y >> 16);
-            if (dc > gap && dr > dr_old) break;
-            if (sc > 0) {
-                int64_t k = v + (int32_t)rec.x;
-                if (A.S[k] < Sv + sc) {
-                    A.S[k] = Sv + sc;
-                    A.pred[k] = (int32_t)v;
-                    A.depth[k] = dv + 1;
-                    A.used[k] = 1;
-                    uv = true;
-                    gap = dc < gap ? dc : gap;
-                    dr_old = dr;
-                }
-            }
+    if (a == b) return;
+    int64_t v = a;
+    int32_t Sv = A.S[v], dv = 1, gap = A.mg2, dr_old = 0;
+    bool uv = false, broken = false;
+    for (uint32_t e = A.eoff[a], e1 = A.eoff[b]; e < e1; e++) {
+        uint2 rec = A.edges[e];
+        uint32_t adv = rec.y >> 8;
+        if (adv) {                                               // next source that has candidates
+            if (uv) A.used[v] = 1;
+            v += adv;
+            Sv = A.S[v];
+            dv = (Sv != A.G[v]) ? A.depth[v] : 1;
+            gap = A.mg2; dr_old = 0; uv = false; broken = false;
         }
-        if (uv) A.used[v] = 1;
+        int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
+        broken = broken || (dc > gap && dr > dr_old);            // collinearity.py:83-84 (break: stays broken)
+        int64_t k = v + (rec.x & 0xffffu);
+        if (!broken && sc > 0 && A.S[k] < Sv + sc) {              // :87 strict <
+            A.S[k] = Sv + sc;
+            A.pred[k] = (int32_t)v;
+            A.depth[k] = dv + 1;
+            A.used[k] = 1;
+            uv = true;
+            gap = dc < gap ? dc : gap;                            // :92
+            dr_old = dr;                                          // :93
+        }
     }
+    if (uv) A.used[v] = 1;
 }
 
 #ifndef ICL_EMU
-#define ICL_CHAIN_CH 128            // TMA chunk: 128 points = 512 B
+#define ICL_EDGE_NCH 4               // edge ring: 4 chunks of 512 records = 16 KB
+#define ICL_USED_FLAG 0x80000000u
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -605,26 +643,28 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void l1_touch(const void *p) {      // pull a line into L1 through the read-only path
-    uint32_t sink;
-    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(sink) : "l"(p) : "memory");
-    (void)sink;
-}
 
+// One CTA per (pair, direction) item: warp 0 lane 0 is the executor, warp 1 the helper.
+//   ring[RS]  : 16-byte slots {score, depth | used-as-source flag, pred, -} of the points inside the window
+//   ering     : the item's edge records, streamed by TMA in 4 KB chunks (4-deep), consumed strictly in order
 __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
-    extern __shared__ __align__(128) int32_t ring[];
-    int32_t *Sr = ring, *Dr = ring + A.RS;
-    __shared__ volatile long long ctl_loaded, ctl_retired;
-    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    uint2 *ering = (uint2 *)dyn;                                           // ICL_EDGE_NCH * ICL_EDGE_CHUNK records
+    int4 *ring = (int4 *)(dyn + ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2));
+    __shared__ volatile uint32_t ctl_loaded, ctl_retired, ctl_echunk;
+    __shared__ __align__(8) uint64_t ebar[ICL_EDGE_NCH];
     const int32_t it = A.order[blockIdx.x];
     const int32_t p = it >= A.P ? it - A.P : it;
-    const int64_t a = A.off[p] + (it >= A.P ? A.n : 0), b = A.off[p + 1] + (it >= A.P ? A.n : 0);
+    const uint32_t a = (uint32_t)(A.off[p] + (it >= A.P ? A.n : 0)), b = (uint32_t)(A.off[p + 1] + (it >= A.P ? A.n : 0));
     if (a == b) return;
-    const uint32_t M = (uint32_t)A.RS - 1;
+    const uint32_t e0 = A.eoff[a], e1 = A.eoff[b];
+    const uint32_t c0 = e0 / ICL_EDGE_CHUNK;
+    const uint32_t M = (uint32_t)A.RS - 1, EM = ICL_EDGE_NCH * ICL_EDGE_CHUNK - 1;
     if (threadIdx.x == 0) {
         ctl_loaded = a;
         ctl_retired = a;
-        mbar_init(&bar, 1);
+        ctl_echunk = c0;
+        for (int i = 0; i < ICL_EDGE_NCH; i++) mbar_init(&ebar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -632,117 +672,115 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
     if (threadIdx.x < 32) {
         // ---------------------------------------------------------------- executor (one thread)
         if (lane != 0) return;
-        long long loaded = a;
+        uint32_t loaded = a, v = a, vpub = a;
         const int32_t mg2 = A.mg2;
-        uint32_t e = __ldg(A.eoff + a);
-        for (int64_t v = a; v < b; v++) {
-            long long need = v + A.span + 1;
-            need = need < b ? need : b;
-            if (need > loaded) {                                  // the window of this source is not staged yet
-                do { loaded = ctl_loaded; } while (loaded < need);
-                __threadfence_block();
-            }
-            const uint32_t e1 = __ldg(A.eoff + v + 1);
-            const int32_t Sv = Sr[(uint32_t)v & M];
-            const int32_t dv = Dr[(uint32_t)v & M];
-            int32_t gap = mg2, dr_old = 0;
-            bool uv = false;
-            for (; e < e1; e++) {
-                const uint2 rec = __ldg(A.edges + e);
-                const int32_t dr = rec.y & 255, dc = (rec.y >> 8) & 255, sc = (int32_t)(rec.y >> 16);
-                if (dc > gap && dr > dr_old) break;               // collinearity.py:83-84
-                if (sc > 0) {
-                    const int64_t k = v + (int32_t)rec.x;
-                    const uint32_t slot = (uint32_t)k & M;
-                    if (Sr[slot] < Sv + sc) {                     // :87 strict <
-                        Sr[slot] = Sv + sc;
-                        Dr[slot] = dv + 1;
-                        A.pred[k] = (int32_t)v;
-                        A.depth[k] = dv + 1;
-                        A.used[k] = 1;
-                        uv = true;
-                        gap = dc < gap ? dc : gap;                // :92
-                        dr_old = dr;                              // :93
+        while (loaded <= v) loaded = ctl_loaded;                  // the item's first point is staged
+        __threadfence_block();
+        int4 sl = ring[v & M];
+        int32_t Sv = sl.x, dv = sl.y, gap = mg2, dr_old = 0;
+        bool uv = false, broken = false;
+        uint32_t e = e0;
+        while (e < e1) {
+            // ---- enter the chunk that holds record e: free the previous ones, wait for the TMA bytes
+            const uint32_t ch = e / ICL_EDGE_CHUNK;
+            __threadfence_block();
+            ctl_echunk = ch;
+            mbar_wait(&ebar[ch % ICL_EDGE_NCH], ((ch - c0) / ICL_EDGE_NCH) & 1u);
+            uint32_t cend = (ch + 1) * ICL_EDGE_CHUNK;
+            cend = cend < e1 ? cend : e1;
+            uint2 nxt = ering[e & EM];
+            for (; e < cend; e++) {
+                const uint2 rec = nxt;
+                nxt = ering[(e + 1) & EM];                        // next record early (unused at a chunk end)
+                const uint32_t adv = rec.y >> 8;
+                if (adv) {                                        // next source that has candidates
+                    if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+                    v += adv;
+                    if (v >= loaded) {
+                        do { loaded = ctl_loaded; } while (loaded <= v);
+                        __threadfence_block();
+                    }
+                    sl = ring[v & M];
+                    Sv = sl.x; dv = sl.y;
+                    gap = mg2; dr_old = 0; uv = false; broken = false;
+                    if ((v ^ vpub) >> 5) {                        // let the helper retire finished points
+                        __threadfence_block();
+                        ctl_retired = v;
+                        vpub = v;
                     }
                 }
-            }
-            e = e1;
-            if (uv) A.used[v] = 1;
-            if (((uint32_t)v & 31u) == 31u) {                     // let the helper retire finished points
-                __threadfence_block();
-                ctl_retired = v + 1;
+                const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
+                broken = broken || (dc > gap && dr > dr_old);     // collinearity.py:83-84
+                const uint32_t k = v + (rec.x & 0xffffu);
+                if (k >= loaded) {                                // the target is not staged yet
+                    do { loaded = ctl_loaded; } while (loaded <= k);
+                    __threadfence_block();
+                }
+                const uint32_t slot = k & M;
+                const int32_t cand = Sv + sc;
+                if (!broken && sc > 0 && ring[slot].x < cand) {   // :87 strict <
+                    ring[slot] = make_int4(cand, dv + 1, (int32_t)v, 0);
+                    uv = true;
+                    gap = dc < gap ? dc : gap;                    // :92
+                    dr_old = dr;                                  // :93
+                }
             }
         }
+        if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
         __threadfence_block();
         ctl_retired = b;
         return;
     }
     // -------------------------------------------------------------------- helper warp
-    int64_t wb = a, ld = a, pf_src = a;
-    uint32_t parity = 0;
-    uint32_t pf_edge = 0;
-    bool pf_edge_init = false;
+    uint32_t wb = a, ld = a;
+    uint32_t next_chunk = c0;
+    const uint32_t last_chunk = e1 > e0 ? (e1 - 1) / ICL_EDGE_CHUNK : c0;
+    const bool has_edges = e1 > e0;
     while (wb < b) {
-        long long r = 0;
-        if (lane == 0) r = ctl_retired;
+        uint32_t r = 0, ech = 0;
+        if (lane == 0) { r = ctl_retired; ech = ctl_echunk; }
         r = __shfl_sync(0xffffffffu, r, 0);
+        ech = __shfl_sync(0xffffffffu, ech, 0);
         __threadfence_block();
         bool progress = false;
-        // 1. final scores of retired points -> HBM (coalesced)
+        // 1. edge chunks: keep the 4-deep ring full (chunks < ech are consumed)
+        if (has_edges && lane == 0) {
+            while (next_chunk <= last_chunk && next_chunk < ech + ICL_EDGE_NCH) {
+                uint64_t *bar = &ebar[next_chunk % ICL_EDGE_NCH];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // executor's reads of the slot -> TMA write
+                mbar_expect_tx(bar, ICL_EDGE_CHUNK * (uint32_t)sizeof(uint2));
+                tma_load_1d(ering + (next_chunk % ICL_EDGE_NCH) * ICL_EDGE_CHUNK, A.edges + (size_t)next_chunk * ICL_EDGE_CHUNK,
+                            ICL_EDGE_CHUNK * (uint32_t)sizeof(uint2), bar);
+                next_chunk++;
+            }
+        }
+        next_chunk = __shfl_sync(0xffffffffu, next_chunk, 0);
+        // 2. results of retired points -> HBM (coalesced): score, pred, depth, used
+        if (r > ld) r = ld;
         if (r > wb) {
-            for (int64_t v = wb + lane; v < r; v += 32) A.S[v] = Sr[(uint32_t)v & M];
+            for (uint32_t v = wb + lane; v < r; v += 32) {
+                const int4 sl = ring[v & M];
+                const int32_t g = A.G[v];
+                A.S[v] = sl.x;
+                if (sl.x != g) { A.pred[v] = sl.z; A.depth[v] = sl.y & 0x7fffffff; }
+                A.used[v] = (sl.x != g) || (sl.y < 0);
+            }
             wb = r;
             progress = true;
         }
-        // 2. stage the initial scores (= grading, get_matrix :35-36) of the next points into the ring
-        int64_t lim = wb + A.RS;
+        // 3. stage the next points of the window: score = grading, path length 1 (get_matrix :35-37)
+        uint32_t lim = wb + (uint32_t)A.RS;
         lim = lim < b ? lim : b;
         if (ld < lim) {
             __syncwarp();
-            int64_t head_end = (ld + ICL_CHAIN_CH - 1) / ICL_CHAIN_CH * ICL_CHAIN_CH;      // first chunk boundary >= ld
-            int64_t body_end = lim / ICL_CHAIN_CH * ICL_CHAIN_CH;
-            if (head_end > lim) head_end = lim;
-            if (body_end < head_end) body_end = head_end;
-            for (int64_t v = ld + lane; v < head_end; v += 32) Sr[(uint32_t)v & M] = A.G[v];
-            for (int64_t v = body_end + lane; v < lim; v += 32) Sr[(uint32_t)v & M] = A.G[v];
-            for (int64_t v = ld + lane; v < lim; v += 32) Dr[(uint32_t)v & M] = 1;       // path = [label], :37
-            if (body_end > head_end) {
-                // ring slots being overwritten were read by the write-back above: order generic -> async proxy
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    uint32_t bytes = (uint32_t)(body_end - head_end) * 4u;
-                    mbar_expect_tx(&bar, bytes);
-                    uint32_t s0 = (uint32_t)head_end & M;
-                    uint32_t first = (uint32_t)A.RS - s0;            // points until the ring wraps
-                    uint32_t cnt = (uint32_t)(body_end - head_end);
-                    if (first > cnt) first = cnt;
-                    tma_load_1d(Sr + s0, A.G + head_end, first * 4u, &bar);
-                    if (cnt > first) tma_load_1d(Sr, A.G + head_end + first, (cnt - first) * 4u, &bar);
-                    mbar_wait(&bar, parity);
-                }
-                parity ^= 1;
-            }
+            for (uint32_t v = ld + lane; v < lim; v += 32) ring[v & M] = make_int4(A.G[v], 1, -1, 0);
             __syncwarp();
             __threadfence_block();
             if (lane == 0) ctl_loaded = lim;
             ld = lim;
             progress = true;
         }
-        // 3. pull the executor's read-only streams into L1 ahead of it: 2 KB of edge offsets, 8 KB of edges
-        {
-            int64_t want = r + 512;
-            want = want < b ? want : b;
-            if (pf_src < r) pf_src = r;
-            for (int64_t v = pf_src + (int64_t)lane * 32; v < want; v += 32 * 32) l1_touch(A.eoff + v);
-            if (want > pf_src) pf_src = want;
-            uint32_t ecur = __ldg(A.eoff + r), eend = __ldg(A.eoff + b);
-            if (!pf_edge_init || pf_edge < ecur) { pf_edge = ecur; pf_edge_init = true; }
-            uint32_t ewant = ecur + 1024 < eend ? ecur + 1024 : eend;
-            for (uint32_t x = pf_edge + (uint32_t)lane * 16; x < ewant; x += 32 * 16) l1_touch(A.edges + x);
-            if (ewant > pf_edge) pf_edge = ewant;
-        }
-        if (!progress) __nanosleep(64);
+        if (!progress) __nanosleep(100);
     }
 }
 #endif
@@ -753,22 +791,20 @@ static int phase_chain(icl_ctx *c) {
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
     if (c->S.reserve(st, V) || c->pred.reserve(st, V) || c->depth.reserve(st, V) || c->used.reserve(st, V)) return st.code;
-    ICL_CUDA(st, dev_memset(c->pred.p, 0xFF, (size_t)V * sizeof(int32_t), s));
-    ICL_CUDA(st, dev_memset(c->used.p, 0, (size_t)V, s));
     ChainArgs A;
     A.n = n; A.P = P; A.mg2 = c->prm.mg2; A.RS = 0; A.span = c->max_span;
     A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
     A.S = c->S.p; A.pred = c->pred.p; A.depth = c->depth.p; A.used = c->used.p;
     if (P == 0 || n == 0) return 0;
 #ifndef ICL_EMU
-    // ring: window span + two TMA chunks of slack + what the helper needs to stay ahead, power of two
-    int64_t want = (int64_t)c->max_span + 4 * ICL_CHAIN_CH + 64;
-    int64_t RS = 512;
+    // ring: window span + what the executor may run ahead of the last retire point, power of two
+    int64_t want = (int64_t)c->max_span + 128;
+    int64_t RS = 256;
     while (RS < want) RS <<= 1;
-    if (RS <= 16384 && !c->force_generic_chain) {
+    if (RS <= 8192 && !c->force_generic_chain) {
         A.RS = (int32_t)RS;
-        size_t smem = (size_t)RS * 2 * sizeof(int32_t);
-        ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
+        size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2);
+        ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         k_chain_ring<<<(unsigned)(2 * P), 64, smem, s>>>(A);
         ICL_CUDA(st, cudaGetLastError());
         c->chain_kernel = 1;
@@ -776,6 +812,7 @@ static int phase_chain(icl_ctx *c) {
     }
 #endif
     ICL_CUDA(st, d2d(c->S.p, c->G.p, (size_t)V * sizeof(int32_t), s));            // get_matrix: score = grading
+    ICL_CUDA(st, dev_memset(c->used.p, 0, (size_t)V, s));
     ICL_CUDA(st, foreach_warp(s, 2 * (int64_t)P, ICL_LAMBDA(int64_t j) { chain_generic_item(A, j); }));
     c->chain_kernel = 0;
     return 0;

@@ -165,6 +165,18 @@ inline int exclusive_sum_u32(Status &st, Buf<uint8_t> &tmp, uint32_t *in, uint32
     ICL_CUDA(st, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)(n + 1), s));
     return 0;
 }
+struct MaxI32 {
+    __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+// in place: a[i] = max(a[0..i])
+inline int inclusive_max_i32(Status &st, Buf<uint8_t> &tmp, int32_t *a, int64_t n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    size_t bytes = 0;
+    ICL_CUDA(st, cub::DeviceScan::InclusiveScan(nullptr, bytes, a, a, MaxI32(), (int)n, s));
+    if (tmp.reserve(st, bytes)) return st.code;
+    ICL_CUDA(st, cub::DeviceScan::InclusiveScan(tmp.p, bytes, a, a, MaxI32(), (int)n, s));
+    return 0;
+}
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     bool armed = false;
@@ -197,6 +209,10 @@ inline int exclusive_sum_u32(Status &, Buf<uint8_t> &, uint32_t *in, uint32_t *o
     uint32_t acc = 0;
     for (int64_t i = 0; i < n; i++) { uint32_t v = in[i]; out[i] = acc; acc += v; }
     out[n] = acc;
+    return 0;
+}
+inline int inclusive_max_i32(Status &, Buf<uint8_t> &, int32_t *a, int64_t n, cudaStream_t) {
+    for (int64_t i = 1; i < n; i++) a[i] = a[i] > a[i - 1] ? a[i] : a[i - 1];
     return 0;
 }
 struct Timer {
