@@ -108,14 +108,15 @@ int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
 
 /*
  * Sort + chaining DP in both directions (wgdi/collinearity.py:72-115: forward :74-93, anti-diagonal
- * :96-115).  Writes, for every pair segment pair_off[p]..pair_off[p+1] (see icl_layout), the final int64
+ * :96-115).  Writes, for every pair segment pair_off[p]..pair_off[p+1] (see icl_layout), the final
  * scores of the segment's points in REVERSED (loc1, loc2) order into caller buffers of n_points elements.
- * That is exactly the array pandas' nargsort(ascending=False) hands to numpy.argsort
- * (it reverses the column first; collinearity.py:49,60 -> pandas/core/sorting.py nargsort), so the caller
- * can sort each segment in place without copying.  May be called repeatedly on the same upload
- * (e.g. a parameter sweep).
+ * Widened to int64 that is exactly the array pandas' nargsort(ascending=False) hands to numpy.argsort
+ * (it reverses the column first; collinearity.py:49,60 -> pandas/core/sorting.py nargsort).  They cross
+ * PCIe as int32 (scores are < 2^31); the caller MUST widen each segment to int64 before sorting because
+ * numpy's sort kernels, and with them the tie permutation, differ per dtype and the reference's column is
+ * int64.  May be called repeatedly on the same upload (e.g. a parameter sweep).
  */
-int icl_dp(icl_ctx *ctx, const icl_params *params, int64_t *key_fwd, int64_t *key_rev);
+int icl_dp(icl_ctx *ctx, const icl_params *params, int32_t *key_fwd, int32_t *key_rev);
 
 /* Layout produced by icl_dp: pair_off[n_pairs + 1] (points of pair p are sorted positions
  * pair_off[p] .. pair_off[p+1]) and perm[n_points] (upload index of each sorted position).
@@ -125,7 +126,7 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
 /*
  * Block extraction + p values (wgdi/collinearity.py:42-70, 117-153).
  * argsort_fwd / argsort_rev: for every pair segment the UNMODIFIED result of
- *     numpy.argsort(key[pair_off[p]:pair_off[p+1]], kind='quicksort')
+ *     numpy.argsort(key[pair_off[p]:pair_off[p+1]].astype(int64), kind='quicksort')
  * on the arrays icl_dp returned, narrowed to int32 (segment-local indices).  The library undoes pandas' two
  * reversals itself.  The sort must be numpy's: it is unstable and its tie permutation decides which blocks
  * are extracted first (SURVEY.md hazard H1).

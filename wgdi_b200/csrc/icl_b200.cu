@@ -67,9 +67,10 @@ struct icl_ctx {
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
     bool force_generic_chain = false;
     // DP state (V space)
-    Buf<int32_t> S, pred, depth;
+    Buf<int32_t> S;
+    Buf<int2> pd;                    // per point: {pred (-1 for path roots), path length}
     Buf<uint8_t> used;
-    Buf<int64_t> score64;
+    Buf<int32_t> score32;
     // extraction
     Buf<int32_t> order_in, rankpos, rank2v, acc_L, members, times;
     Buf<uint32_t> tree_v, acc_m, acc_flag, blkidx, moff;
@@ -214,7 +215,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release();
-    c->S.release(); c->pred.release(); c->depth.release(); c->used.release(); c->score64.release();
+    c->S.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
     c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
@@ -576,7 +577,8 @@ struct ChainArgs {
     const int64_t *off;
     const uint32_t *eoff;
     const uint2 *edges;
-    int32_t *S, *pred, *depth;
+    int32_t *S;
+    int2 *pd;
     uint8_t *used;
 };
 
@@ -596,7 +598,7 @@ ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
             if (uv) A.used[v] = 1;
             v += adv;
             Sv = A.S[v];
-            dv = (Sv != A.G[v]) ? A.depth[v] : 1;
+            dv = (Sv != A.G[v]) ? A.pd[v].y : 1;
             gap = A.mg2; dr_old = 0; uv = false; broken = false;
         }
         int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
@@ -604,8 +606,7 @@ ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
         int64_t k = v + (rec.x & 0xffffu);
         if (!broken && sc > 0 && A.S[k] < Sv + sc) {              // :87 strict <
             A.S[k] = Sv + sc;
-            A.pred[k] = (int32_t)v;
-            A.depth[k] = dv + 1;
+            A.pd[k] = make_int2((int32_t)v, dv + 1);
             A.used[k] = 1;
             uv = true;
             gap = dc < gap ? dc : gap;                            // :92
@@ -762,7 +763,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 const int4 sl = ring[v & M];
                 const int32_t g = A.G[v];
                 A.S[v] = sl.x;
-                if (sl.x != g) { A.pred[v] = sl.z; A.depth[v] = sl.y & 0x7fffffff; }
+                A.pd[v] = (sl.x != g) ? make_int2(sl.z, sl.y & 0x7fffffff) : make_int2(-1, 1);
                 A.used[v] = (sl.x != g) || (sl.y < 0);
             }
             wb = r;
@@ -790,11 +791,11 @@ static int phase_chain(icl_ctx *c) {
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->S.reserve(st, V) || c->pred.reserve(st, V) || c->depth.reserve(st, V) || c->used.reserve(st, V)) return st.code;
+    if (c->S.reserve(st, V) || c->pd.reserve(st, V) || c->used.reserve(st, V)) return st.code;
     ChainArgs A;
     A.n = n; A.P = P; A.mg2 = c->prm.mg2; A.RS = 0; A.span = c->max_span;
     A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
-    A.S = c->S.p; A.pred = c->pred.p; A.depth = c->depth.p; A.used = c->used.p;
+    A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p;
     if (P == 0 || n == 0) return 0;
 #ifndef ICL_EMU
     // ring: window span + what the executor may run ahead of the last retire point, power of two
@@ -814,6 +815,11 @@ static int phase_chain(icl_ctx *c) {
     ICL_CUDA(st, d2d(c->S.p, c->G.p, (size_t)V * sizeof(int32_t), s));            // get_matrix: score = grading
     ICL_CUDA(st, dev_memset(c->used.p, 0, (size_t)V, s));
     ICL_CUDA(st, foreach_warp(s, 2 * (int64_t)P, ICL_LAMBDA(int64_t j) { chain_generic_item(A, j); }));
+    {
+        const int32_t *S = c->S.p, *G = c->G.p;
+        int2 *pd = c->pd.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (S[v] == G[v]) pd[v] = make_int2(-1, 1); }));
+    }
     c->chain_kernel = 0;
     return 0;
 }
@@ -821,7 +827,7 @@ static int phase_chain(icl_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // ABI: icl_dp
 // ------------------------------------------------------------------------------------------------
-extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int64_t *score_fwd, int64_t *score_rev) {
+extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t *score_rev) {
     if (!c) return ICL_ERR_ARG;
     if (!c->uploaded) return fail(c, ICL_ERR_STATE, "icl_dp: icl_upload has not succeeded");
     if (!prm || (c->n > 0 && (!score_fwd || !score_rev))) return fail(c, ICL_ERR_ARG, "icl_dp: null argument");
@@ -850,12 +856,12 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int64_t *score_fwd, int
     if (phase_chain(c)) return st.code;
     c->timers[ICL_T_CHAIN].stop(s);
     c->timers[ICL_T_EXPORT].start(s);
-    if (c->score64.reserve(st, 2 * n)) return st.code;
+    if (c->score32.reserve(st, 2 * n)) return st.code;
     {
         // per pair segment in REVERSED point order: the array pandas' nargsort(ascending=False) hands to numpy
         const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
         const int64_t *off = c->d_pair_off.p;
-        int64_t *o = c->score64.p;
+        int32_t *o = c->score32.p;
         ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
             int32_t p = ps[i];
             int64_t src = off[p] + (off[p + 1] - 1 - i);
@@ -864,8 +870,8 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int64_t *score_fwd, int
         }));
     }
     if (n > 0) {
-        ICL_CUDA(st, d2h(score_fwd, c->score64.p, (size_t)n * sizeof(int64_t), s));
-        ICL_CUDA(st, d2h(score_rev, c->score64.p + n, (size_t)n * sizeof(int64_t), s));
+        ICL_CUDA(st, d2h(score_fwd, c->score32.p, (size_t)n * sizeof(int32_t), s));
+        ICL_CUDA(st, d2h(score_rev, c->score32.p + n, (size_t)n * sizeof(int32_t), s));
     }
     c->timers[ICL_T_EXPORT].stop(s);
     ICL_CUDA(st, dev_sync(s));
@@ -909,17 +915,17 @@ extern "C" int icl_debug_dp(icl_ctx *c, int32_t dir, int32_t *score, int32_t *pr
     Buf<uint8_t> t4;
     if (t1.reserve(st, n) || t2.reserve(st, n) || t3.reserve(st, n) || t4.reserve(st, n)) return st.code;
     {
-        const int32_t *S = c->S.p, *G = c->G.p, *pr = c->pred.p, *dp = c->depth.p, *mmap = c->mmap.p, *imap = c->imap.p;
+        const int32_t *S = c->S.p, *mmap = c->mmap.p, *imap = c->imap.p;
+        const int2 *pd = c->pd.p;
         const uint8_t *us = c->used.p;
         int32_t *o1 = t1.p, *o2 = t2.p, *o3 = t3.p;
         uint8_t *o4 = t4.p;
         ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
             int64_t v = dir ? mmap[i] : i;
-            bool root = S[v] == G[v];
             o1[i] = S[v];
-            int32_t q = root ? -1 : pr[v];
+            int32_t q = pd[v].x;
             o2[i] = (q < 0) ? -1 : (dir ? imap[q - n] : q);
-            o3[i] = root ? 1 : dp[v];
+            o3[i] = pd[v].y;
             o4[i] = us[v];
         }));
     }
@@ -977,7 +983,8 @@ static int phase_extract(icl_ctx *c) {
         rankpos[mmap[a + (np_ - 1 - rr)]] = pos;
     }));
     ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));      // drop usedtimes < 1 (:50 / :61)
-    const int32_t *S = c->S.p, *G = c->G.p, *pred = c->pred.p, *depth = c->depth.p, *itemof = c->itemof.p;
+    const int2 *pd = c->pd.p;
+    const int32_t *itemof = c->itemof.p;
     const uint8_t *used = c->used.p;
     // key = (root, rank position); unused points sort behind everything
     int maxnp = 1;
@@ -992,7 +999,7 @@ static int phase_extract(icl_ctx *c) {
             int32_t rp = rankpos[v];
             if (rp < 0) { atomic_or_i32(&stats[2], 1); key[v] = (uint64_t)V << rb; return; }   // not a permutation
             int32_t q = (int32_t)v;
-            while (S[q] != G[q]) q = pred[q];                    // root of the predecessor tree
+            for (int32_t up = pd[q].x; up >= 0; up = pd[q].x) q = up;       // root of the predecessor tree
             key[v] = ((uint64_t)(uint32_t)q << rb) | (uint32_t)rp;
         }));
     }
@@ -1012,17 +1019,13 @@ static int phase_extract(icl_ctx *c) {
             for (int64_t u = t; u < V && (key[u] >> rb) == root; u++) {         // the tree's points in rank order
                 int32_t top = (int32_t)tv[u];
                 if (!present[top]) continue;
-                int32_t L = (S[top] != G[top]) ? depth[top] : 1;
-                int32_t m = 0, q = top;
-                while (true) {                                                  // present part of the path
-                    m++;
-                    if (S[q] == G[q]) break;
-                    q = pred[q];
-                    if (!present[q]) break;
-                }
+                const int2 nd = pd[top];
+                int32_t L = nd.y;
+                int32_t m = 1, q = nd.x;
+                while (q >= 0 && present[q]) { m++; q = pd[q].x; }              // present part of the path
                 if (L >= over_gap && (double)m / (double)L > cov) {             // :129
                     q = top;
-                    for (int32_t k = 0; k < m; k++) { present[q] = 0; q = pred[q]; }     // :130
+                    for (int32_t k = 0; k < m; k++) { present[q] = 0; q = pd[q].x; }     // :130
                     int32_t it = itemof[top];
                     int64_t pos = (it >= P ? n : 0) + off[it >= P ? it - P : it] + (int64_t)(key[u] & ((1ull << rb) - 1));
                     acc_m[pos] = (uint32_t)m;
@@ -1080,7 +1083,7 @@ static int phase_extract(icl_ctx *c) {
                 int32_t y = l2[i];
                 l2min = y < l2min ? y : l2min;
                 l2max = y > l2max ? y : l2max;
-                q = pred[q];
+                q = pd[q].x;
             }
             int32_t l1min = l1[members[mo]], l1max = l1[members[mo + m - 1]];
             b_top[b] = top;
@@ -1139,12 +1142,15 @@ struct PvalArgs {
 };
 
 #ifndef ICL_EMU
-template <bool SMEM>
-__device__ __forceinline__ void pvalue_pair(const PvalArgs &A, int32_t p, uint16_t *tsm) {
+// MODE 0: times (uint16) and loc2 of the pair in shared memory; 1: times only; 2: everything in global memory
+template <int MODE>
+__device__ __forceinline__ void pvalue_pair(const PvalArgs &A, int32_t p, uint16_t *tsm, int32_t *l2sm) {
     const int lane = threadIdx.x;
     const int64_t a = A.off[p], np_ = A.off[p + 1] - a;
-    if (SMEM) {
+    if (MODE <= 1) {
         for (int64_t i = lane; i < np_; i += 32) tsm[i] = 1;                     // get_matrix :34
+        if (MODE == 0)
+            for (int64_t i = lane; i < np_; i += 32) l2sm[i] = A.l2[a + i];
     } else {
         for (int64_t i = lane; i < np_; i += 32) A.times[a + i] = 1;
     }
@@ -1152,44 +1158,57 @@ __device__ __forceinline__ void pvalue_pair(const PvalArgs &A, int32_t p, uint16
     volatile int32_t *tg = A.times;
     for (int d = 0; d < 2; d++) {
         const uint32_t b0 = A.blkidx[(d ? A.n : 0) + a], b1 = A.blkidx[(d ? A.n : 0) + a + np_];
-        if (b0 == b1) continue;
-        int32_t j0 = A.b_j0[b0], j1 = A.b_j1[b0], lo = A.b_l2min[b0], hi = A.b_l2max[b0];
-        for (uint32_t b = b0; b < b1; b++) {
-            int32_t nj0 = 0, nj1 = 0, nlo = 0, nhi = 0;
-            if (b + 1 < b1) { nj0 = A.b_j0[b + 1]; nj1 = A.b_j1[b + 1]; nlo = A.b_l2min[b + 1]; nhi = A.b_l2max[b + 1]; }
-            int32_t N = 0;
-            int64_t N1 = 0;
-            for (int32_t q = j0 + lane; q < j1; q += 32) {                        // :134-137 inclusive box
-                int32_t y = __ldg(A.l2 + q);
-                if (y >= lo && y <= hi) {
-                    int32_t t;
-                    if (SMEM) { t = tsm[q - a]; tsm[q - a] = (uint16_t)(t + 1); }
-                    else { t = tg[q]; tg[q] = t + 1; }
-                    N1 += t;                                                      // :148
-                    N++;                                                          // :149, times += 1 :150
+        // block records are fetched 32 at a time (one per lane, coalesced) and handed out by shuffle
+        int32_t rj0 = 0, rj1 = 0, rlo = 0, rhi = 0;
+        if (b0 + lane < b1) { rj0 = A.b_j0[b0 + lane]; rj1 = A.b_j1[b0 + lane]; rlo = A.b_l2min[b0 + lane]; rhi = A.b_l2max[b0 + lane]; }
+        for (uint32_t base = b0; base < b1; base += 32) {
+            const int32_t cj0 = rj0, cj1 = rj1, clo = rlo, chi = rhi;
+            const uint32_t nb = base + 32 + lane;
+            if (nb < b1) { rj0 = A.b_j0[nb]; rj1 = A.b_j1[nb]; rlo = A.b_l2min[nb]; rhi = A.b_l2max[nb]; }
+            const uint32_t cnt = b1 - base < 32 ? b1 - base : 32;
+            int32_t myN = 0;
+            unsigned long long myN1 = 0;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const int32_t j0 = __shfl_sync(0xffffffffu, cj0, i), j1 = __shfl_sync(0xffffffffu, cj1, i);
+                const int32_t lo = __shfl_sync(0xffffffffu, clo, i), hi = __shfl_sync(0xffffffffu, chi, i);
+                uint32_t N = 0;
+                unsigned long long N1 = 0;
+                for (int32_t q = j0 + lane; q < j1; q += 32) {                    // :134-137 inclusive box
+                    const int32_t y = MODE == 0 ? l2sm[q - a] : __ldg(A.l2 + q);
+                    if (y >= lo && y <= hi) {
+                        uint32_t t;
+                        if (MODE <= 1) { t = tsm[q - a]; tsm[q - a] = (uint16_t)(t + 1); }
+                        else { t = (uint32_t)tg[q]; tg[q] = (int32_t)t + 1; }
+                        N1 += t;                                                  // :148
+                        N++;                                                      // :149, times += 1 :150
+                    }
                 }
+                N = __reduce_add_sync(0xffffffffu, N);
+                if (MODE <= 1) {                                  // uint16 counters over <= 102 400 points: the sum fits 32 bits
+                    N1 = __reduce_add_sync(0xffffffffu, (uint32_t)N1);
+                } else {
+                    for (int o = 16; o > 0; o >>= 1) N1 += __shfl_xor_sync(0xffffffffu, N1, o);
+                }
+                __syncwarp();                                                     // times of this block visible to the next
+                if (lane == (int)i) { myN = (int32_t)N; myN1 = N1; }
             }
-            N = __reduce_add_sync(0xffffffffu, N);
-            for (int o = 16; o > 0; o >>= 1) N1 += __shfl_xor_sync(0xffffffffu, N1, o);
-            __syncwarp();                                                         // times of this block visible to the next
-            if (lane == 0) {
-                int32_t m = A.b_m[b], L1 = A.b_L1[b], L2 = hi - lo + 1;
-                A.b_N[b] = N;
-                A.b_N1[b] = N1;
-                A.b_a[b] = icl_p_raw((int64_t)A.S[A.b_top[b]], m, A.g0, N1, N, L1, L2);
-            }
-            j0 = nj0; j1 = nj1; lo = nlo; hi = nhi;
+            if ((uint32_t)lane < cnt) { A.b_N[base + lane] = myN; A.b_N1[base + lane] = (int64_t)myN1; }
         }
     }
 }
 
-__global__ void __launch_bounds__(32) k_pvalue(PvalArgs A) {
-    extern __shared__ uint16_t tsm[];
+__global__ void __launch_bounds__(32) k_pvalue(PvalArgs A, int32_t l2_cap) {
+    extern __shared__ __align__(16) unsigned char psm[];
     const int32_t p = A.pair_order[blockIdx.x];
     const int64_t np_ = A.off[p + 1] - A.off[p];
     const uint32_t nb = A.blkidx[A.n + A.off[p + 1]] - A.blkidx[A.n + A.off[p]] + A.blkidx[A.off[p + 1]] - A.blkidx[A.off[p]];
-    if (np_ <= A.smem_cap && nb < 65000u) pvalue_pair<true>(A, p, tsm);
-    else pvalue_pair<false>(A, p, tsm);
+    if (nb == 0) return;
+    uint16_t *tsm = (uint16_t *)psm;
+    int32_t *l2sm = (int32_t *)(psm + (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15));
+    // uint16 counters: a point is covered by fewer boxes than the pair has blocks
+    if (np_ <= l2_cap && nb < 65000u) pvalue_pair<0>(A, p, tsm, l2sm);
+    else if (np_ <= A.smem_cap && nb < 65000u) pvalue_pair<1>(A, p, tsm, l2sm);
+    else pvalue_pair<2>(A, p, tsm, l2sm);
 }
 #endif
 
@@ -1208,11 +1227,12 @@ static int phase_pvalue(icl_ctx *c) {
 #ifndef ICL_EMU
     int64_t maxnp = 1;
     for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
-    const int64_t cap_limit = 100 * 1024;                      // uint16 entries: 200 KB of the 227 KB
-    A.smem_cap = (int32_t)std::min<int64_t>(maxnp, cap_limit);
-    size_t smem = (size_t)A.smem_cap * sizeof(uint16_t);
-    ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    k_pvalue<<<(unsigned)P, 32, smem, s>>>(A);
+    // shared memory per CTA: uint16 times for up to smem_cap points (+ int32 loc2 for up to l2_cap points)
+    A.smem_cap = (int32_t)std::min<int64_t>(maxnp, 100 * 1024);
+    int32_t l2_cap = (int32_t)std::min<int64_t>(maxnp, 12 * 1024);              // keeps >= 3 CTAs per SM
+    size_t smem = (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15) + (size_t)l2_cap * 4;
+    ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    k_pvalue<<<(unsigned)P, 32, smem, s>>>(A, l2_cap);
     ICL_CUDA(st, cudaGetLastError());
 #else
     A.smem_cap = 0;
@@ -1229,11 +1249,21 @@ static int phase_pvalue(icl_ctx *c) {
                     if (A.l2[q] >= lo && A.l2[q] <= hi) { N1 += A.times[q]; N++; A.times[q]++; }
                 A.b_N[b] = N;
                 A.b_N1[b] = N1;
-                A.b_a[b] = icl_p_raw((int64_t)A.S[A.b_top[b]], A.b_m[b], A.g0, N1, N, A.b_L1[b], hi - lo + 1);
             }
         }
     }
 #endif
+    {
+        // p value of every accepted block, one thread each (collinearity.py:152 in binary64, left to right)
+        const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;
+        const int32_t *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p;
+        const int64_t *b_N1 = c->b_N1.p;
+        double *b_a = c->b_a.p;
+        const int32_t g0 = c->prm.g0;
+        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
+            b_a[b] = icl_p_raw((int64_t)S[b_top[b]], b_m[b], g0, b_N1[b], b_N[b], b_L1[b], b_l2max[b] - b_l2min[b] + 1);
+        }));
+    }
     return 0;
 }
 

@@ -27,6 +27,8 @@ typedef void *cudaStream_t;
 #define cudaSuccess 0
 struct uint2 { uint32_t x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
+struct int2 { int32_t x, y; };
+static inline int2 make_int2(int32_t x, int32_t y) { int2 r = {x, y}; return r; }
 #endif
 
 namespace icl {

@@ -12,8 +12,10 @@
  * segment from a pthread pool.  The Python side verifies on start-up that the result is identical to
  * numpy.argsort and otherwise falls back to one numpy call per segment (wgdi_b200/engine.py).
  *
- * Python API:  seg_argsort(keys:int64[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads:int) -> 0
- *   out[off[s] + j] = argsort(keys[off[s]:off[s+1]], kind='quicksort')[j]   (narrowed to int32)
+ * Python API:  seg_argsort(keys:int32[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads:int) -> 0
+ *   out[off[s] + j] = argsort(keys[off[s]:off[s+1]].astype(int64), kind='quicksort')[j]   (narrowed to int32)
+ * The keys cross PCIe as int32 and are widened per segment here: the reference's score column is int64 and
+ * numpy's sort kernels (hence the tie permutation) are dtype specific.
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
@@ -25,7 +27,7 @@
 
 typedef struct {
     PyArray_ArgSortFunc *fn;
-    const int64_t *keys;
+    const int32_t *keys;
     const int64_t *off;
     const int32_t *seg_order;
     int32_t *out;
@@ -38,6 +40,7 @@ static void *worker(void *vp)
 {
     job_t *j = (job_t *)vp;
     npy_intp *idx = NULL;
+    int64_t *wide = NULL;
     int64_t cap = 0;
     for (;;) {
         int64_t s = __sync_fetch_and_add(&j->next, 1);
@@ -47,16 +50,20 @@ static void *worker(void *vp)
         if (n <= 0) continue;
         if (n > cap) {
             free(idx);
+            free(wide);
             cap = n + n / 4 + 64;
             idx = (npy_intp *)malloc((size_t)cap * sizeof(npy_intp));
-            if (!idx) { j->err = 1; break; }
+            wide = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+            if (!idx || !wide) { j->err = 1; break; }
         }
-        for (int64_t i = 0; i < n; i++) idx[i] = i;                    /* as _new_argsortlike does */
-        if (j->fn((void *)(j->keys + a), idx, (npy_intp)n, NULL) < 0) { j->err = 2; break; }
+        const int32_t *k32 = j->keys + a;
+        for (int64_t i = 0; i < n; i++) { idx[i] = i; wide[i] = k32[i]; }   /* index fill as _new_argsortlike does */
+        if (j->fn((void *)wide, idx, (npy_intp)n, NULL) < 0) { j->err = 2; break; }
         int32_t *o = j->out + a;
         for (int64_t i = 0; i < n; i++) o[i] = (int32_t)idx[i];
     }
     free(idx);
+    free(wide);
     return NULL;
 }
 
@@ -67,22 +74,24 @@ static PyObject *seg_argsort(PyObject *self, PyObject *args)
     if (!PyArg_ParseTuple(args, "O!O!O!O!i", &PyArray_Type, &keys, &PyArray_Type, &off, &PyArray_Type, &order,
                           &PyArray_Type, &out, &threads))
         return NULL;
-    if (PyArray_TYPE(keys) != NPY_INT64 || PyArray_TYPE(off) != NPY_INT64 || PyArray_TYPE(order) != NPY_INT32 ||
+    if (PyArray_TYPE(keys) != NPY_INT32 || PyArray_TYPE(off) != NPY_INT64 || PyArray_TYPE(order) != NPY_INT32 ||
         PyArray_TYPE(out) != NPY_INT32 || !PyArray_IS_C_CONTIGUOUS(keys) || !PyArray_IS_C_CONTIGUOUS(off) ||
         !PyArray_IS_C_CONTIGUOUS(order) || !PyArray_IS_C_CONTIGUOUS(out) || !PyArray_ISALIGNED(keys) ||
         PyArray_NDIM(keys) != 1 || PyArray_NDIM(out) != 1 || PyArray_SIZE(out) < PyArray_SIZE(keys) ||
         PyArray_SIZE(off) < 1 || PyArray_SIZE(order) != PyArray_SIZE(off) - 1) {
-        PyErr_SetString(PyExc_TypeError, "seg_argsort(keys:int64[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads)");
+        PyErr_SetString(PyExc_TypeError, "seg_argsort(keys:int32[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads)");
         return NULL;
     }
-    PyArray_ArgSortFunc *fn = PyDataType_GetArrFuncs(PyArray_DESCR(keys))->argsort[NPY_QUICKSORT];
+    PyArray_Descr *d64 = PyArray_DescrFromType(NPY_INT64);
+    PyArray_ArgSortFunc *fn = PyDataType_GetArrFuncs(d64)->argsort[NPY_QUICKSORT];
+    Py_DECREF(d64);
     if (!fn) {
         PyErr_SetString(PyExc_RuntimeError, "numpy exposes no int64 quicksort argsort routine");
         return NULL;
     }
     job_t j;
     j.fn = fn;
-    j.keys = (const int64_t *)PyArray_DATA(keys);
+    j.keys = (const int32_t *)PyArray_DATA(keys);
     j.off = (const int64_t *)PyArray_DATA(off);
     j.seg_order = (const int32_t *)PyArray_DATA(order);
     j.out = (int32_t *)PyArray_DATA(out);

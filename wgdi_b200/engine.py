@@ -38,11 +38,12 @@ def _npsort_ok():
             rng = np.random.default_rng(12345)
             sizes = np.array([0, 1, 2, 7, 16, 17, 64, 129, 255, 256, 257, 1000, 5000, 40000], np.int64)
             off = np.r_[0, np.cumsum(sizes)].astype(np.int64)
-            keys = rng.integers(25, 60, int(off[-1])).astype(np.int64)
+            keys = rng.integers(25, 60, int(off[-1])).astype(np.int32)
             out = np.empty(len(keys), np.int32)
             try:
                 _npsort.seg_argsort(keys, off, np.arange(len(sizes), dtype=np.int32), out, 3)
-                ok = all((out[a:b] == keys[a:b].argsort(kind="quicksort")).all() for a, b in zip(off[:-1], off[1:]))
+                ok = all((out[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all()
+                         for a, b in zip(off[:-1], off[1:]))
             except Exception:
                 ok = False
         _NPSORT_OK = ok
@@ -180,11 +181,11 @@ class IclEngine:
         self.n, self.n_pairs = n, int(n_pairs)
 
     def dp(self, params: ChainParams):
-        """Both DP directions; returns (key_fwd, key_rev): int64 scores, every pair segment in REVERSED point
-        order (the array pandas' nargsort(ascending=False) hands to numpy.argsort)."""
+        """Both DP directions; returns (key_fwd, key_rev): int32 scores, every pair segment in REVERSED point
+        order (widened to int64: the array pandas' nargsort(ascending=False) hands to numpy.argsort)."""
         prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
                          float(params.coverage_ratio))
-        sf, sr = self._buf("score_fwd", self.n, np.int64), self._buf("score_rev", self.n, np.int64)
+        sf, sr = self._buf("key_fwd", self.n, np.int32), self._buf("key_rev", self.n, np.int32)
         self._check(self.lib.icl_dp(self.ctx, C.byref(prm), sf.ctypes.data, sr.ctypes.data))
         self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
         self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
@@ -215,8 +216,8 @@ class IclEngine:
         def work(chunk):
             for p in chunk:
                 a, b = off[p], off[p + 1]
-                af[a:b] = key_fwd[a:b].argsort(kind="quicksort")
-                ar[a:b] = key_rev[a:b].argsort(kind="quicksort")
+                af[a:b] = key_fwd[a:b].astype(np.int64).argsort(kind="quicksort")      # the reference sorts int64
+                ar[a:b] = key_rev[a:b].astype(np.int64).argsort(kind="quicksort")
 
         if self._pool is None or len(pairs) < 2:
             work(pairs)
