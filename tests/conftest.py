@@ -133,3 +133,25 @@ def oracle_blocks(pts, prm):
         for mm, a, sc, d in bt.blocks(p):
             out.append((p, 0 if d > 0 else 1, l1[mm], l2[mm], a, sc))
     return out
+
+
+def forked_chain_points(prefix=60, arm=200, arms=3):
+    """One long diagonal prefix that forks into several long arms: after the best arm is extracted together with
+    the prefix, every point of the other arms is examined and rejected one by one (coverage <= 0.8) — the case the
+    extraction kernel's removed-ancestor memo exists for."""
+    l1, l2 = list(range(1, prefix + 1)), list(range(1, prefix + 1))
+    for a in range(arms):
+        r, c = prefix, prefix + 3 * a
+        for i in range(arm - 20 * a):
+            r += 1
+            c += 1 + (a if i == 0 else 0) * 2
+            l1.append(r)
+            l2.append(c)
+            if a and i % 7 == 3:          # side twigs
+                l1.append(r)
+                l2.append(c + 9)
+    pts = sorted(set(zip(l1, l2)))
+    l1 = np.array([x for x, _ in pts], np.int32)
+    l2 = np.array([y for _, y in pts], np.int32)
+    g = np.where(np.arange(len(l1)) % 5 == 0, 50, 30).astype(np.int32)
+    return dict(pair_id=np.zeros(len(l1), np.int32), loc1=l1, loc2=l2, grading=g, n_pairs=1)

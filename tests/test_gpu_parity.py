@@ -212,6 +212,18 @@ def test_window_bounds_are_exclusive(gpu_engine):
             assert (kf[0] == 100 - dr - dc) == linked and (linked or kf[0] == 50)       # keys are reversed per segment
 
 
+def test_forked_chains(gpu_engine):
+    """Long paths sharing a root-side prefix: exercises the removed-ancestor memo of the extraction kernel."""
+    from conftest import forked_chain_points
+    from wgdi_b200.engine import ChainParams
+    for prefix, arm in ((60, 200), (400, 900)):
+        pts = forked_chain_points(prefix, arm)
+        for cov in (0.8, 0.5):
+            prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25), coverage_ratio=cov)
+            blocks = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], 1, prm)
+            _compare_with_oracle(blocks, oracle_blocks(pts, prm))
+
+
 def test_sharded_equals_unsharded(gpu_engine):
     """Chromosome pairs split over 2 and 3 ranks by LPT (ranks emulated one after another on this GPU)."""
     from wgdi_b200 import shard, synth

@@ -144,6 +144,24 @@ def test_multi_pair_batch_matches_c_oracle_emu(emu_backend):
         assert blocks.p_raw[b] == a
 
 
+def test_forked_chains_emu(emu_backend):
+    from conftest import forked_chain_points, oracle_blocks
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = forked_chain_points()
+    eng = IclEngine(0, sort_threads=1)
+    try:
+        for cov in (0.8, 0.5):
+            prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25), coverage_ratio=cov)
+            blocks = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], 1, prm)
+            exp = oracle_blocks(pts, prm)
+            assert len(blocks) == len(exp) and len(exp) >= 2
+            for b, (pair, d, l1, l2, a, sc) in enumerate(exp):
+                a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
+                assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all() and blocks.p_raw[b] == a
+    finally:
+        eng.close()
+
+
 _E2E_CHILD = r"""
 import sys, hashlib, json, ctypes, io, contextlib, numpy as np
 sys.path.insert(0, %r)

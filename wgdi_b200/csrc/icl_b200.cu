@@ -67,7 +67,7 @@ struct icl_ctx {
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
     bool force_generic_chain = false;
     // DP state (V space)
-    Buf<int32_t> S;
+    Buf<int32_t> S, root;            // root = first point of the path (root of the predecessor tree)
     Buf<int2> pd;                    // per point: {pred (-1 for path roots), path length}
     Buf<uint8_t> used;
     Buf<int32_t> score32;
@@ -75,6 +75,7 @@ struct icl_ctx {
     Buf<int32_t> order_in, rankpos, rank2v, acc_L, members, times;
     Buf<uint32_t> tree_v, acc_m, acc_flag, blkidx, moff;
     Buf<uint8_t> present;
+    Buf<int2> hint;                  // per point: {depth of the nearest removed ancestor, tree version} memo
     int64_t NB = 0, NM = 0;
     Buf<int32_t> b_top, b_m, b_L, b_j0, b_j1, b_l2min, b_l2max, b_L1, b_item, b_N;
     Buf<uint32_t> b_moff;
@@ -215,7 +216,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release();
-    c->S.release(); c->pd.release(); c->used.release(); c->score32.release();
+    c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
     c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
@@ -473,6 +474,21 @@ struct EdgeEnum {
         int64_t base = rb[p] + (it >= P ? R : 0);
         int32_t nr = nrows[p];
         int32_t x1 = X1[v], x2 = X2[v];
+        int32_t lastrow = x1 + mg1 - 1 < nr - 1 ? x1 + mg1 - 1 : nr - 1;
+        if (lastrow <= x1) return;
+        const int32_t k0 = rowptr[base + x1 + 1], k1 = rowptr[base + lastrow + 1];
+        if (k1 - k0 <= 384) {
+            // the next mg1-1 rows are one contiguous slice sorted by (row, column): scan it once
+            for (int32_t k = k0; k < k1; k++) {
+                int32_t dc = X2[k] - x2;
+                if (dc <= 0 || dc >= mg2) continue;
+                int32_t dr = X1[k] - x1;
+                int32_t s = G[k] - (dr + dc);
+                bool last = (k + 1 == k1) || X1[k + 1] != X1[k] || (X2[k + 1] - x2 >= mg2);
+                if (s > 0 || last) emit(k, dr, dc, s > 0 ? s : 0);
+            }
+            return;
+        }
         for (int32_t dr = 1; dr < mg1 && x1 + dr < nr; dr++) {
             int32_t lo = rowptr[base + x1 + dr], hi = rowptr[base + x1 + dr + 1];
             if (lo == hi) continue;
@@ -577,7 +593,7 @@ struct ChainArgs {
     const int64_t *off;
     const uint32_t *eoff;
     const uint2 *edges;
-    int32_t *S;
+    int32_t *S, *root;
     int2 *pd;
     uint8_t *used;
 };
@@ -589,7 +605,7 @@ ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
     int64_t a = A.off[p] + (it >= A.P ? A.n : 0), b = A.off[p + 1] + (it >= A.P ? A.n : 0);
     if (a == b) return;
     int64_t v = a;
-    int32_t Sv = A.S[v], dv = 1, gap = A.mg2, dr_old = 0;
+    int32_t Sv = A.S[v], dv = 1, rootv = (int32_t)v, gap = A.mg2, dr_old = 0;
     bool uv = false, broken = false;
     for (uint32_t e = A.eoff[a], e1 = A.eoff[b]; e < e1; e++) {
         uint2 rec = A.edges[e];
@@ -599,6 +615,7 @@ ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
             v += adv;
             Sv = A.S[v];
             dv = (Sv != A.G[v]) ? A.pd[v].y : 1;
+            rootv = (Sv != A.G[v]) ? A.root[v] : (int32_t)v;
             gap = A.mg2; dr_old = 0; uv = false; broken = false;
         }
         int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
@@ -607,6 +624,7 @@ ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
         if (!broken && sc > 0 && A.S[k] < Sv + sc) {              // :87 strict <
             A.S[k] = Sv + sc;
             A.pd[k] = make_int2((int32_t)v, dv + 1);
+            A.root[k] = rootv;
             A.used[k] = 1;
             uv = true;
             gap = dc < gap ? dc : gap;                            // :92
@@ -646,7 +664,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 
 // One CTA per (pair, direction) item: warp 0 lane 0 is the executor, warp 1 the helper.
-//   ring[RS]  : 16-byte slots {score, depth | used-as-source flag, pred, -} of the points inside the window
+//   ring[RS]  : 16-byte slots {score, depth | used-as-source flag, pred, tree root} of the points inside the window
 //   ering     : the item's edge records, streamed by TMA in 4 KB chunks (4-deep), consumed strictly in order
 __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
     extern __shared__ __align__(128) unsigned char dyn[];
@@ -678,7 +696,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         while (loaded <= v) loaded = ctl_loaded;                  // the item's first point is staged
         __threadfence_block();
         int4 sl = ring[v & M];
-        int32_t Sv = sl.x, dv = sl.y, gap = mg2, dr_old = 0;
+        int32_t Sv = sl.x, dv = sl.y, rootv = sl.w, gap = mg2, dr_old = 0;
         bool uv = false, broken = false;
         uint32_t e = e0;
         while (e < e1) {
@@ -702,7 +720,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                         __threadfence_block();
                     }
                     sl = ring[v & M];
-                    Sv = sl.x; dv = sl.y;
+                    Sv = sl.x; dv = sl.y; rootv = sl.w;
                     gap = mg2; dr_old = 0; uv = false; broken = false;
                     if ((v ^ vpub) >> 5) {                        // let the helper retire finished points
                         __threadfence_block();
@@ -720,7 +738,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 const uint32_t slot = k & M;
                 const int32_t cand = Sv + sc;
                 if (!broken && sc > 0 && ring[slot].x < cand) {   // :87 strict <
-                    ring[slot] = make_int4(cand, dv + 1, (int32_t)v, 0);
+                    ring[slot] = make_int4(cand, dv + 1, (int32_t)v, rootv);
                     uv = true;
                     gap = dc < gap ? dc : gap;                    // :92
                     dr_old = dr;                                  // :93
@@ -764,6 +782,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 const int32_t g = A.G[v];
                 A.S[v] = sl.x;
                 A.pd[v] = (sl.x != g) ? make_int2(sl.z, sl.y & 0x7fffffff) : make_int2(-1, 1);
+                A.root[v] = sl.w;
                 A.used[v] = (sl.x != g) || (sl.y < 0);
             }
             wb = r;
@@ -774,7 +793,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         lim = lim < b ? lim : b;
         if (ld < lim) {
             __syncwarp();
-            for (uint32_t v = ld + lane; v < lim; v += 32) ring[v & M] = make_int4(A.G[v], 1, -1, 0);
+            for (uint32_t v = ld + lane; v < lim; v += 32) ring[v & M] = make_int4(A.G[v], 1, -1, (int32_t)v);
             __syncwarp();
             __threadfence_block();
             if (lane == 0) ctl_loaded = lim;
@@ -791,11 +810,11 @@ static int phase_chain(icl_ctx *c) {
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->S.reserve(st, V) || c->pd.reserve(st, V) || c->used.reserve(st, V)) return st.code;
+    if (c->S.reserve(st, V) || c->pd.reserve(st, V) || c->used.reserve(st, V) || c->root.reserve(st, V)) return st.code;
     ChainArgs A;
     A.n = n; A.P = P; A.mg2 = c->prm.mg2; A.RS = 0; A.span = c->max_span;
     A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
-    A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p;
+    A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p; A.root = c->root.p;
     if (P == 0 || n == 0) return 0;
 #ifndef ICL_EMU
     // ring: window span + what the executor may run ahead of the last retire point, power of two
@@ -818,7 +837,8 @@ static int phase_chain(icl_ctx *c) {
     {
         const int32_t *S = c->S.p, *G = c->G.p;
         int2 *pd = c->pd.p;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (S[v] == G[v]) pd[v] = make_int2(-1, 1); }));
+        int32_t *root = c->root.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (S[v] == G[v]) { pd[v] = make_int2(-1, 1); root[v] = (int32_t)v; } }));
     }
     c->chain_kernel = 0;
     return 0;
@@ -968,6 +988,8 @@ static int phase_extract(icl_ctx *c) {
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->rankpos.p, 0xFF, (size_t)V * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
+    if (c->hint.reserve(st, V)) return st.code;
+    ICL_CUDA(st, dev_memset(c->hint.p, 0xFF, (size_t)V * sizeof(int2), s));
     const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
     const int64_t *off = c->d_pair_off.p;
     int32_t *rankpos = c->rankpos.p, *stats = c->stats.p;
@@ -984,7 +1006,7 @@ static int phase_extract(icl_ctx *c) {
     }));
     ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));      // drop usedtimes < 1 (:50 / :61)
     const int2 *pd = c->pd.p;
-    const int32_t *itemof = c->itemof.p;
+    const int32_t *itemof = c->itemof.p, *root = c->root.p;
     const uint8_t *used = c->used.p;
     // key = (root, rank position); unused points sort behind everything
     int maxnp = 1;
@@ -998,9 +1020,7 @@ static int phase_extract(icl_ctx *c) {
             if (!used[v]) { key[v] = (uint64_t)V << rb; return; }
             int32_t rp = rankpos[v];
             if (rp < 0) { atomic_or_i32(&stats[2], 1); key[v] = (uint64_t)V << rb; return; }   // not a permutation
-            int32_t q = (int32_t)v;
-            for (int32_t up = pd[q].x; up >= 0; up = pd[q].x) q = up;       // root of the predecessor tree
-            key[v] = ((uint64_t)(uint32_t)q << rb) | (uint32_t)rp;
+            key[v] = ((uint64_t)(uint32_t)root[v] << rb) | (uint32_t)rp;   // root of the predecessor tree (from the DP)
         }));
     }
     if (V > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, rb + vb, s)) return st.code;
@@ -1010,28 +1030,39 @@ static int phase_extract(icl_ctx *c) {
         uint8_t *present = c->present.p;
         uint32_t *acc_m = c->acc_m.p;
         int32_t *acc_L = c->acc_L.p;
+        int2 *hint = c->hint.p;
         const int32_t over_gap = c->prm.over_gap;
         const double cov = c->prm.coverage_ratio;
         ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
             uint64_t root = key[t] >> rb;
             if (root >= (uint64_t)V) return;                                    // unused tail
             if (t > 0 && (key[t - 1] >> rb) == root) return;                    // not the head of its tree
+            int32_t ver = 0;                                                    // accepted blocks of this tree so far
             for (int64_t u = t; u < V && (key[u] >> rb) == root; u++) {         // the tree's points in rank order
                 int32_t top = (int32_t)tv[u];
                 if (!present[top]) continue;
                 const int2 nd = pd[top];
-                int32_t L = nd.y;
-                int32_t m = 1, q = nd.x;
-                while (q >= 0 && present[q]) { m++; q = pd[q].x; }              // present part of the path
+                const int2 h = hint[top];
+                int32_t L = nd.y, m, q;
+                if (h.y == ver) {
+                    m = L - h.x;                                                // boundary known from a rejected child
+                } else {
+                    m = 1; q = nd.x;
+                    while (q >= 0 && present[q]) { m++; q = pd[q].x; }          // present part of the path
+                }
                 if (L >= over_gap && (double)m / (double)L > cov) {             // :129
                     q = top;
                     for (int32_t k = 0; k < m; k++) { present[q] = 0; q = pd[q].x; }     // :130
+                    ver++;                                                      // removed ancestors changed: memos expire
                     int32_t it = itemof[top];
                     int64_t pos = (it >= P ? n : 0) + off[it >= P ? it - P : it] + (int64_t)(key[u] & ((1ull << rb) - 1));
                     acc_m[pos] = (uint32_t)m;
                     acc_L[pos] = L;
                 } else {
                     present[top] = 0;                                           // :143
+                    // the parent sees the same removed ancestor until the next accepted block of this tree;
+                    // without the memo a long path whose root side was taken by another block costs O(L^2) hops
+                    if (m > 1) hint[nd.x] = make_int2(L - m, ver);
                 }
             }
         }));
