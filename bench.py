@@ -205,7 +205,8 @@ def main():
         total_pairs = pts["n_pairs"]
     n_local = len(pts["loc1"])
 
-    eng = IclEngine(local)
+    # the host rank (numpy's argsort) is per-rank host work: split the box's cores between the ranks
+    eng = IclEngine(local, sort_threads=max(1, (os.cpu_count() or 1) // world))
     # inputs in page-locked host memory (the e2e leg copies them every step)
     host_in = {}
     for k in ("pair_id", "loc1", "loc2", "grading"):
