@@ -65,7 +65,9 @@ struct icl_ctx {
     int64_t n_edges = 0;
     int32_t max_span = 0;            // largest (target position - source position) over all edges
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
-    bool force_generic_chain = false;
+    int32_t chain_mode = 2;          // 2 = wave kernel, 1 = single-executor ring kernel, 0 = generic (env ICL_B200_CHAIN)
+    int32_t wave_span = 0;           // most points inside 64 + mg1 consecutive rows of an item
+    Buf<int2> rowtab;                // per dense row: {first edge record, first source that has records | -1}
     // DP state (V space)
     Buf<int32_t> S, root;            // root = first point of the path (root of the predecessor tree)
     Buf<int2> pd;                    // per point: {pred (-1 for path roots), path length}
@@ -197,8 +199,8 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
 #endif
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
-    const char *gen = getenv("ICL_B200_GENERIC_CHAIN");      // diagnostics: A/B the two DP kernels
-    c->force_generic_chain = gen && gen[0] == '1';
+    const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
+    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "ring") ? 1 : 2;
     *out = c;
     return ICL_OK;
 }
@@ -215,7 +217,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
-    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release();
+    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release();
     c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
@@ -559,9 +561,39 @@ static int phase_edges(icl_ctx *c) {
         // Monotonic max: the plain read filters almost every atomic away.
         if (span > stats[3]) atomic_max_i32(&stats[3], span);
     }));
-    int32_t span = 0;
-    ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
+    // row table for the wave kernel: first record and first source with records of every dense row, and the
+    // largest number of points inside (64 + mg1) consecutive rows (sizes its shared-memory window)
+    const int64_t R2 = 2 * c->R;
+    if (c->rowtab.reserve(st, R2 + 2)) return st.code;
+    {
+        int2 *rowtab = c->rowtab.p;
+        const int32_t *rowptr = c->rowptr.p;
+        const int32_t reach = 64 + c->prm.mg1;
+        ICL_CUDA(st, dev_memset(c->stats.p + 2, 0, sizeof(int32_t), s));
+        ICL_CUDA(st, foreach(s, R2, ICL_LAMBDA(int64_t g) {
+            int32_t v0 = rowptr[g], v1 = g + 1 < R2 ? rowptr[g + 1] : v0;
+            uint32_t es = eoff[v0];
+            int32_t first = -1;
+            if (v1 > v0 && eoff[v1] > es) {                     // first source of the row whose records start at es
+                int32_t lo = v0, hi = v1 - 1;
+                while (lo < hi) {
+                    int32_t mid = lo + ((hi - lo) >> 1);
+                    if (eoff[mid + 1] > es) hi = mid; else lo = mid + 1;
+                }
+                first = lo;
+            }
+            rowtab[g] = make_int2((int32_t)es, first);
+            const int64_t top = (g < R2 / 2 ? R2 / 2 : R2) - 1;          // stay inside the forward / mirrored half
+            int64_t g2 = g + reach < top ? g + reach : top;
+            int32_t w = rowptr[g2] - v0;
+            if (w > stats[2]) atomic_max_i32(&stats[2], w);
+        }));
+    }
+    int32_t span2[2] = {0, 0};
+    ICL_CUDA(st, d2h(span2, c->stats.p + 2, 2 * sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
+    int32_t span = span2[1];
+    c->wave_span = span2[0];
     c->max_span = span;
     if (span >= 65536) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 65535 points inside one mg1-row window of a chromosome pair");
     return 0;
@@ -803,7 +835,257 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         if (!progress) __nanosleep(100);
     }
 }
+// ------------------------------------------------------------------------------------------------
+// k_chain_wave: the same order-exact sweep with 32 rows of the item in flight (one lane per row, lock-step).
+//
+// Which sources may run concurrently?  Two sources interact only if one is a candidate of the other or they
+// share a candidate, i.e. only if their rows are less than mg1 apart and their columns less than mg2 apart.
+// A source at (row r, column c) may therefore run as soon as every earlier row still in flight has finished
+// all of its sources with column < c + mg2, and its own row everything left of c (validated
+// there against the reference with a randomised asynchronous pipeline).  Sources that run in the same step
+// have disjoint windows, and every conflicting pair of sources runs in the reference's order, so the result is
+// the reference's bit for bit.
+//
+// Lane l owns the dense rows l, l+32, l+64, ... in increasing order.  With the progress key
+//     K_l = row_l * B + column of the lane's next source that has candidates        (B > any column + mg2)
+// the condition for lane l is   min over d = 1..31 of ( K_{(l-d) mod 32} + d * B )  >=  K_l + mg2 :
+// lane l-d holds row r-d (compare columns), a later row r-d+32 (always true) or an earlier row r-d-32
+// (always false: row r-d has not started).  The min-plus is a 5-step cyclic scan with warp shuffles.
+// The lane with the smallest key always passes, so the wave never stalls.
+//
+// Shared memory: ring[RS] window slots (as k_chain_ring), colring[RS] source columns, rowring[256] row table
+// {first record, first source with records, first point}, ering edge records (TMA chunks).  The helper warp
+// stages all four ahead of the wave and writes finished points back behind it.
+// ------------------------------------------------------------------------------------------------
+#define ICL_WAVE_ROWS 256            // staged row-table entries (power of two)
+#define ICL_WAVE_REC 4               // records a lane handles per lock-step round
+
+struct WaveArgs {
+    ChainArgs c;
+    const int32_t *X2, *rowptr, *nrows;
+    const int2 *rowtab;
+    const int64_t *rb;
+    int64_t R;
+};
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
+    const ChainArgs &A = W.c;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    uint2 *ering = (uint2 *)dyn;
+    int4 *ring = (int4 *)(dyn + ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2));
+    int4 *rowring = ring + A.RS;
+    int32_t *colring = (int32_t *)(rowring + ICL_WAVE_ROWS);
+    __shared__ volatile uint32_t ctl_loaded, ctl_retired, ctl_eloaded, ctl_emin, ctl_rowloaded, ctl_xmin;
+    __shared__ __align__(8) uint64_t ebar[ICL_EDGE_NCH];
+    const int32_t it = A.order[blockIdx.x];
+    const int32_t p = it >= A.P ? it - A.P : it;
+    const uint32_t a = (uint32_t)(A.off[p] + (it >= A.P ? A.n : 0)), b = (uint32_t)(A.off[p + 1] + (it >= A.P ? A.n : 0));
+    if (a == b) return;
+    const int64_t rbase = W.rb[p] + (it >= A.P ? W.R : 0);
+    const uint32_t nrows = (uint32_t)W.nrows[p];
+    const uint32_t e0 = A.eoff[a], e1 = A.eoff[b];
+    const uint32_t c0 = e0 / ICL_EDGE_CHUNK;
+    const uint32_t M = (uint32_t)A.RS - 1, EM = ICL_EDGE_NCH * ICL_EDGE_CHUNK - 1, RM = ICL_WAVE_ROWS - 1;
+    if (threadIdx.x == 0) {
+        ctl_loaded = a; ctl_retired = a; ctl_eloaded = e0; ctl_emin = e0; ctl_rowloaded = 0; ctl_xmin = 0;
+        for (int i = 0; i < ICL_EDGE_NCH; i++) mbar_init(&ebar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    if (threadIdx.x < 32) {
+        // ---------------------------------------------------------------- the wave: one lane per row in flight
+        const long long B = 1ll << 27;
+        const long long KINF = 0x3fffffffffffffffll;
+        const int32_t mg2 = A.mg2;
+        uint32_t x = (uint32_t)lane;                      // dense row owned right now
+        uint32_t e = e0, e_end = e0, v = a, rs = a;       // next record, end of the row's records, source, row start
+        bool need_row = true, done = false, in_src = false, fresh = false;
+        int32_t Sv = 0, dv = 0, rootv = 0, gap = 0, dr_old = 0;
+        bool uv = false, broken = false;
+        uint32_t round = 0;
+        while (true) {
+            const uint32_t loaded = ctl_loaded, rowloaded = ctl_rowloaded, eloaded = ctl_eloaded;
+            __threadfence_block();
+            // 1. lanes between rows enter their next row that has records (a few empty rows per round)
+            for (int t = 0; t < 4; t++) {
+                if (!need_row || done) break;
+                if (x >= nrows) { done = true; break; }
+                if (x + 1 >= rowloaded) break;                       // row table not staged yet
+                const int4 ent = rowring[x & RM];
+                if (ent.y < 0) { x += 32; continue; }                // no source of this row has candidates
+                e = (uint32_t)ent.x; v = (uint32_t)ent.y; rs = (uint32_t)ent.z;
+                e_end = (uint32_t)rowring[(x + 1) & RM].x;
+                need_row = false; fresh = true;                      // the first record's adv is replaced by v
+            }
+            if (__all_sync(FULL, done)) break;
+            // 2. progress keys and readiness
+            // window of the source is in the ring (the ring never holds points beyond the item)
+            const bool staged = !done && !need_row && (v + (uint32_t)A.span < loaded || loaded >= b);
+            long long K = KINF;
+            if (!done) K = (long long)x * B + (staged ? (long long)colring[v & M] : 0ll);
+            bool ready = staged;
+            if (ready) {
+                uint32_t last = e + ICL_WAVE_REC < e_end ? e + ICL_WAVE_REC : e_end;
+                ready = last <= eloaded;                              // records of this round are in the edge ring
+            }
+            // 3. may a lane start its next source?  cyclic min-plus scan over the other 31 lanes
+            long long val = __shfl_sync(FULL, K, (lane - 1) & 31) + B;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                long long other = __shfl_sync(FULL, val, (lane - d) & 31) + (long long)d * B;
+                val = other < val ? other : val;
+            }
+            if (ready && !in_src && val >= K + mg2) {
+                const int4 sl = ring[v & M];
+                Sv = sl.x; dv = sl.y; rootv = sl.w;
+                gap = mg2; dr_old = 0; uv = false; broken = false;
+                in_src = true;
+            }
+            // 4. lanes inside a source replay up to ICL_WAVE_REC of its records
+            bool src_end = false;
+            if (in_src && ready) {
+#pragma unroll
+                for (int r = 0; r < ICL_WAVE_REC; r++) {
+                    if (e >= e_end) { src_end = true; break; }
+                    const uint2 rec = ering[e & EM];
+                    if (!fresh && (rec.y >> 8)) { src_end = true; break; }          // record of the next source
+                    fresh = false;
+                    const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
+                    broken = broken || (dc > gap && dr > dr_old);     // collinearity.py:83-84
+                    const uint32_t slot = (v + (rec.x & 0xffffu)) & M;
+                    const int32_t cand = Sv + sc;
+                    if (!broken && sc > 0 && ring[slot].x < cand) {   // :87 strict <
+                        ring[slot] = make_int4(cand, dv + 1, (int32_t)v, rootv);
+                        uv = true;
+                        gap = dc < gap ? dc : gap;                    // :92
+                        dr_old = dr;                                  // :93
+                    }
+                    e++;
+                }
+                if (!src_end && e >= e_end) src_end = true;
+                if (!src_end) {                                        // does the next record open a new source?
+                    // only decidable when that record is staged; otherwise stay in the source one more round
+                    if (e < eloaded && (ering[e & EM].y >> 8)) src_end = true;
+                }
+                if (src_end) {
+                    if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+                    in_src = false;
+                    if (e < e_end) { v += ering[e & EM].y >> 8; fresh = true; }      // next source of the row
+                    else { need_row = true; x += 32; }
+                }
+            }
+            // 5. publish the trailing edge of the wave so the helper can retire / refill
+            if ((++round & 3u) == 0) {
+                uint32_t rmin = __reduce_min_sync(FULL, done ? b : rs);
+                uint32_t emin = __reduce_min_sync(FULL, done ? e1 : e);
+                uint32_t xmin = __reduce_min_sync(FULL, done ? nrows : x);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) { ctl_retired = rmin; ctl_emin = emin; ctl_xmin = xmin; }
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) { ctl_retired = b; ctl_emin = e1; ctl_xmin = nrows; }
+        return;
+    }
+    // -------------------------------------------------------------------- helper warp
+    uint32_t wb = a, ld = a, rld = 0;
+    uint32_t issued = c0, confirmed = c0;
+    const uint32_t last_chunk = e1 > e0 ? (e1 - 1) / ICL_EDGE_CHUNK : c0;
+    const bool has_edges = e1 > e0;
+    while (wb < b) {
+        uint32_t r = 0, emin = 0, xmin = 0;
+        if (lane == 0) { r = ctl_retired; emin = ctl_emin; xmin = ctl_xmin; }
+        r = __shfl_sync(FULL, r, 0);
+        emin = __shfl_sync(FULL, emin, 0);
+        xmin = __shfl_sync(FULL, xmin, 0);
+        __threadfence_block();
+        bool progress = false;
+        // 1. edge chunks by TMA: issue while a ring slot is free, confirm completed ones in order
+        if (has_edges && lane == 0) {
+            const uint32_t ech = emin / ICL_EDGE_CHUNK;
+            while (issued <= last_chunk && issued < ech + ICL_EDGE_NCH) {
+                uint64_t *bar = &ebar[issued % ICL_EDGE_NCH];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, ICL_EDGE_CHUNK * (uint32_t)sizeof(uint2));
+                tma_load_1d(ering + (issued % ICL_EDGE_NCH) * ICL_EDGE_CHUNK, A.edges + (size_t)issued * ICL_EDGE_CHUNK,
+                            ICL_EDGE_CHUNK * (uint32_t)sizeof(uint2), bar);
+                issued++;
+            }
+            bool any = false;
+            while (confirmed < issued && mbar_test(&ebar[confirmed % ICL_EDGE_NCH], ((confirmed - c0) / ICL_EDGE_NCH) & 1u)) {
+                confirmed++;
+                any = true;
+            }
+            if (any) {
+                __threadfence_block();
+                ctl_eloaded = confirmed * ICL_EDGE_CHUNK;
+            }
+        }
+        // 2. row table entries {first record, first source with records, first point}
+        {
+            uint32_t rlim = xmin + ICL_WAVE_ROWS;
+            rlim = rlim < nrows + 1 ? rlim : nrows + 1;
+            if (rld < rlim) {
+                for (uint32_t xr = rld + lane; xr < rlim; xr += 32) {
+                    const int2 t = W.rowtab[rbase + xr];
+                    rowring[xr & RM] = make_int4(t.x, t.y, W.rowptr[rbase + xr], 0);
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) ctl_rowloaded = rlim;
+                rld = rlim;
+                progress = true;
+            }
+        }
+        // 3. results of retired points -> HBM (coalesced): score, pred/length, root, used
+        if (r > ld) r = ld;
+        if (r > wb) {
+            for (uint32_t v = wb + lane; v < r; v += 32) {
+                const int4 sl = ring[v & M];
+                const int32_t g = A.G[v];
+                A.S[v] = sl.x;
+                A.pd[v] = (sl.x != g) ? make_int2(sl.z, sl.y & 0x7fffffff) : make_int2(-1, 1);
+                A.root[v] = sl.w;
+                A.used[v] = (sl.x != g) || (sl.y < 0);
+            }
+            wb = r;
+            progress = true;
+        }
+        // 4. stage the next points of the window: score = grading, path length 1 (get_matrix :35-37), columns
+        uint32_t lim = wb + (uint32_t)A.RS;
+        lim = lim < b ? lim : b;
+        if (ld < lim) {
+            __syncwarp();
+            for (uint32_t v = ld + lane; v < lim; v += 32) {
+                ring[v & M] = make_int4(A.G[v], 1, -1, (int32_t)v);
+                colring[v & M] = W.X2[v];
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) ctl_loaded = lim;
+            ld = lim;
+            progress = true;
+        }
+        if (!progress) __nanosleep(40);
+    }
+}
 #endif
+
 
 static int phase_chain(icl_ctx *c) {
     Status &st = c->st;
@@ -817,18 +1099,36 @@ static int phase_chain(icl_ctx *c) {
     A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p; A.root = c->root.p;
     if (P == 0 || n == 0) return 0;
 #ifndef ICL_EMU
-    // ring: window span + what the executor may run ahead of the last retire point, power of two
-    int64_t want = (int64_t)c->max_span + 128;
-    int64_t RS = 256;
-    while (RS < want) RS <<= 1;
-    if (RS <= 8192 && !c->force_generic_chain) {
-        A.RS = (int32_t)RS;
-        size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2);
-        ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        k_chain_ring<<<(unsigned)(2 * P), 64, smem, s>>>(A);
-        ICL_CUDA(st, cudaGetLastError());
-        c->chain_kernel = 1;
-        return 0;
+    if (c->chain_mode != 0) {
+        // ---- wave kernel: needs the row table and a window over (64 + mg1) rows
+        if (c->chain_mode == 2 && c->wave_span + 256 <= 8192) {
+            int64_t RS = 512;
+            while (RS < (int64_t)c->wave_span + 256) RS <<= 1;
+            A.RS = (int32_t)RS;
+            WaveArgs W;
+            W.c = A; W.X2 = c->X2.p; W.rowptr = c->rowptr.p; W.nrows = c->d_nrows.p; W.rowtab = c->rowtab.p;
+            W.rb = c->d_rb.p; W.R = c->R;
+            size_t smem = (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2) + (size_t)RS * sizeof(int4) +
+                          (size_t)ICL_WAVE_ROWS * sizeof(int4) + (size_t)RS * sizeof(int32_t);
+            ICL_CUDA(st, cudaFuncSetAttribute(k_chain_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_chain_wave<<<(unsigned)(2 * P), 64, smem, s>>>(W);
+            ICL_CUDA(st, cudaGetLastError());
+            c->chain_kernel = 2;
+            return 0;
+        }
+        // ---- single-executor ring kernel: window span + what the executor may run ahead of the last retire point
+        int64_t want = (int64_t)c->max_span + 128;
+        int64_t RS = 256;
+        while (RS < want) RS <<= 1;
+        if (RS <= 8192) {
+            A.RS = (int32_t)RS;
+            size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2);
+            ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            k_chain_ring<<<(unsigned)(2 * P), 64, smem, s>>>(A);
+            ICL_CUDA(st, cudaGetLastError());
+            c->chain_kernel = 1;
+            return 0;
+        }
     }
 #endif
     ICL_CUDA(st, d2d(c->S.p, c->G.p, (size_t)V * sizeof(int32_t), s));            // get_matrix: score = grading
