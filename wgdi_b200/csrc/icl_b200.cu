@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
 // stages all four ahead of the wave and writes finished points back behind it.
 // ------------------------------------------------------------------------------------------------
 #define ICL_WAVE_ROWS 256            // staged row-table entries (power of two)
-#define ICL_WAVE_REC 4               // records a lane handles per lock-step round
+#define ICL_WAVE_REC 6               // lock-step record iterations per round
 
 struct WaveArgs {
     ChainArgs c;
@@ -907,8 +907,10 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
     const uint32_t FULL = 0xffffffffu;
     if (threadIdx.x < 32) {
         // ---------------------------------------------------------------- the wave: one lane per row in flight
-        const long long B = 1ll << 27;
-        const long long KINF = 0x3fffffffffffffffll;
+        // 32-bit progress keys: (row - xbase) << 20 | column, xbase = last published minimum row of the wave.
+        // A lane only enters rows less than 3000 above xbase, so entered lanes have exact keys; lanes further
+        // ahead are clamped to row 4000, which is later than every entered row, exactly what they are.
+        const uint32_t B = 1u << 20, KINF = 0xFC000000u;
         const int32_t mg2 = A.mg2;
         uint32_t x = (uint32_t)lane;                      // dense row owned right now
         uint32_t e = e0, e_end = e0, v = a, rs = a;       // next record, end of the row's records, source, row start
@@ -917,13 +919,14 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
         bool uv = false, broken = false;
         uint32_t round = 0;
         while (true) {
-            const uint32_t loaded = ctl_loaded, rowloaded = ctl_rowloaded, eloaded = ctl_eloaded;
+            const uint32_t loaded = ctl_loaded, rowloaded = ctl_rowloaded, eloaded = ctl_eloaded, xbase = ctl_xmin;
             __threadfence_block();
-            // 1. lanes between rows enter their next row that has records (a few empty rows per round)
-            for (int t = 0; t < 4; t++) {
+            // 1. lanes between rows enter their next row that has records (two empty rows per round at most)
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
                 if (!need_row || done) break;
                 if (x >= nrows) { done = true; break; }
-                if (x + 1 >= rowloaded) break;                       // row table not staged yet
+                if (x + 1 >= rowloaded || x - xbase >= 3000u) break;  // row table not staged / too far ahead of the wave
                 const int4 ent = rowring[x & RM];
                 if (ent.y < 0) { x += 32; continue; }                // no source of this row has candidates
                 e = (uint32_t)ent.x; v = (uint32_t)ent.y; rs = (uint32_t)ent.z;
@@ -931,38 +934,42 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
                 need_row = false; fresh = true;                      // the first record's adv is replaced by v
             }
             if (__all_sync(FULL, done)) break;
-            // 2. progress keys and readiness
-            // window of the source is in the ring (the ring never holds points beyond the item)
-            const bool staged = !done && !need_row && (v + (uint32_t)A.span < loaded || loaded >= b);
-            long long K = KINF;
-            if (!done) K = (long long)x * B + (staged ? (long long)colring[v & M] : 0ll);
-            bool ready = staged;
-            if (ready) {
-                uint32_t last = e + ICL_WAVE_REC < e_end ? e + ICL_WAVE_REC : e_end;
-                ready = last <= eloaded;                              // records of this round are in the edge ring
-            }
-            // 3. may a lane start its next source?  cyclic min-plus scan over the other 31 lanes
-            long long val = __shfl_sync(FULL, K, (lane - 1) & 31) + B;
+            // 2. progress key of the lane's next (or current) source
+            const uint32_t elim = e_end < eloaded ? e_end : eloaded;  // records of the row that are in the edge ring
+            bool staged = !done && !need_row && (v + (uint32_t)A.span < loaded || loaded >= b);
+            const uint32_t xr = x - xbase < 4000u ? x - xbase : 4000u;
+            uint32_t K = done ? KINF : (xr << 20) | (staged ? (uint32_t)colring[v & M] : 0u);
+            // 3. cyclic min-plus scan over the other 31 lanes: val = min_d (K[(l-d) mod 32] + d * B)
+            uint32_t val = __shfl_sync(FULL, K, (lane - 1) & 31) + B;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                long long other = __shfl_sync(FULL, val, (lane - d) & 31) + (long long)d * B;
+                const uint32_t other = __shfl_sync(FULL, val, (lane - d) & 31) + (uint32_t)d * B;
                 val = other < val ? other : val;
             }
-            if (ready && !in_src && val >= K + mg2) {
-                const int4 sl = ring[v & M];
-                Sv = sl.x; dv = sl.y; rootv = sl.w;
-                gap = mg2; dr_old = 0; uv = false; broken = false;
-                in_src = true;
-            }
-            // 4. lanes inside a source replay up to ICL_WAVE_REC of its records
-            bool src_end = false;
-            if (in_src && ready) {
-#pragma unroll
-                for (int r = 0; r < ICL_WAVE_REC; r++) {
-                    if (e >= e_end) { src_end = true; break; }
+            // 4. up to ICL_WAVE_REC lock-step iterations: start a source when allowed, replay one record
+            //    (keys of the other lanes only grow, so `val` stays a valid lower bound within the round)
+#pragma unroll 1
+            for (int r = 0; r < ICL_WAVE_REC; r++) {
+                if (!in_src && staged && e < elim && val >= K + (uint32_t)mg2) {
+                    const int4 sl = ring[v & M];
+                    Sv = sl.x; dv = sl.y; rootv = sl.w;
+                    gap = mg2; dr_old = 0; uv = false; broken = false;
+                    in_src = true;
+                }
+                const bool work = in_src && e < elim;
+                if (!__any_sync(FULL, work)) break;
+                if (work) {
                     const uint2 rec = ering[e & EM];
-                    if (!fresh && (rec.y >> 8)) { src_end = true; break; }          // record of the next source
-                    fresh = false;
+                    if (!fresh && (rec.y >> 8)) {
+                        // this record opens the next source of the row (its predecessor ended while the
+                        // record was not staged yet): close the current source, replay nothing
+                        if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+                        in_src = false;
+                        v += rec.y >> 8; fresh = true;
+                        staged = v + (uint32_t)A.span < loaded || loaded >= b;
+                        K = (xr << 20) | (staged ? (uint32_t)colring[v & M] : 0u);
+                        continue;
+                    }
                     const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
                     broken = broken || (dc > gap && dr > dr_old);     // collinearity.py:83-84
                     const uint32_t slot = (v + (rec.x & 0xffffu)) & M;
@@ -974,27 +981,32 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
                         dr_old = dr;                                  // :93
                     }
                     e++;
-                }
-                if (!src_end && e >= e_end) src_end = true;
-                if (!src_end) {                                        // does the next record open a new source?
-                    // only decidable when that record is staged; otherwise stay in the source one more round
-                    if (e < eloaded && (ering[e & EM].y >> 8)) src_end = true;
-                }
-                if (src_end) {
-                    if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
-                    in_src = false;
-                    if (e < e_end) { v += ering[e & EM].y >> 8; fresh = true; }      // next source of the row
-                    else { need_row = true; x += 32; }
+                    fresh = false;
+                    // end of the source: end of the row, or the next record (if staged) opens another source
+                    uint32_t adv = 0;
+                    const bool row_end = e >= e_end;
+                    if (!row_end && e < eloaded) adv = ering[e & EM].y >> 8;
+                    if (row_end || adv) {
+                        if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+                        in_src = false;
+                        if (row_end) { need_row = true; x += 32; staged = false; }
+                        else {
+                            v += adv; fresh = true;
+                            staged = v + (uint32_t)A.span < loaded || loaded >= b;
+                            K = (xr << 20) | (staged ? (uint32_t)colring[v & M] : 0u);
+                        }
+                    }
                 }
             }
             // 5. publish the trailing edge of the wave so the helper can retire / refill
-            if ((++round & 3u) == 0) {
-                uint32_t rmin = __reduce_min_sync(FULL, done ? b : rs);
-                uint32_t emin = __reduce_min_sync(FULL, done ? e1 : e);
-                uint32_t xmin = __reduce_min_sync(FULL, done ? nrows : x);
+            if ((++round & 7u) == 0) {
+                const uint32_t rmin = __reduce_min_sync(FULL, done ? b : rs);
+                const uint32_t emin = __reduce_min_sync(FULL, done ? e1 : e);
+                const uint32_t xmin = __reduce_min_sync(FULL, done ? nrows : x);
                 __syncwarp();
                 __threadfence_block();
                 if (lane == 0) { ctl_retired = rmin; ctl_emin = emin; ctl_xmin = xmin; }
+                __syncwarp();                                         // every lane reads the same xbase next round
             }
         }
         __syncwarp();
@@ -1101,7 +1113,7 @@ static int phase_chain(icl_ctx *c) {
 #ifndef ICL_EMU
     if (c->chain_mode != 0) {
         // ---- wave kernel: needs the row table and a window over (64 + mg1) rows
-        if (c->chain_mode == 2 && c->wave_span + 256 <= 8192) {
+        if (c->chain_mode == 2 && c->wave_span + 256 <= 8192 && c->bits2 <= 19) {   // 32-bit progress keys: columns < 2^19
             int64_t RS = 512;
             while (RS < (int64_t)c->wave_span + 256) RS <<= 1;
             A.RS = (int32_t)RS;
