@@ -918,27 +918,41 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
         int32_t Sv = 0, dv = 0, rootv = 0, gap = 0, dr_old = 0;
         bool uv = false, broken = false;
         uint32_t round = 0;
+        uint32_t loaded = a, rowloaded = 0, eloaded = e0, xbase = 0;
+        uint32_t col = 0;                                 // column of source v (valid when staged)
+        bool staged = false;
         while (true) {
-            const uint32_t loaded = ctl_loaded, rowloaded = ctl_rowloaded, eloaded = ctl_eloaded, xbase = ctl_xmin;
-            __threadfence_block();
-            // 1. lanes between rows enter their next row that has records (two empty rows per round at most)
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                if (!need_row || done) break;
-                if (x >= nrows) { done = true; break; }
-                if (x + 1 >= rowloaded || x - xbase >= 3000u) break;  // row table not staged / too far ahead of the wave
-                const int4 ent = rowring[x & RM];
-                if (ent.y < 0) { x += 32; continue; }                // no source of this row has candidates
-                e = (uint32_t)ent.x; v = (uint32_t)ent.y; rs = (uint32_t)ent.z;
-                e_end = (uint32_t)rowring[(x + 1) & RM].x;
-                need_row = false; fresh = true;                      // the first record's adv is replaced by v
+            __syncwarp();                                 // ring stores of the previous round are visible to every lane
+            // 0. control words of the helper, every 4th round (stale values only delay a lane)
+            if ((round & 3u) == 0) {
+                loaded = ctl_loaded; rowloaded = ctl_rowloaded; eloaded = ctl_eloaded; xbase = ctl_xmin;
+                __threadfence_block();
+                if (__all_sync(FULL, done)) break;
             }
-            if (__all_sync(FULL, done)) break;
+            // 1. a lane between rows tries to enter its next row (one attempt per round)
+            if (need_row && !done) {
+                if (x >= nrows) done = true;
+                else if (x + 1 < rowloaded && x - xbase < 3000u) {   // row table staged, not too far ahead of the wave
+                    const int4 ent = rowring[x & RM];
+                    if (ent.y < 0) x += 32;                          // no source of this row has candidates
+                    else {
+                        e = (uint32_t)ent.x; v = (uint32_t)ent.y; rs = (uint32_t)ent.z;
+                        e_end = (uint32_t)rowring[(x + 1) & RM].x;
+                        need_row = false; fresh = true; staged = false;   // the first record's adv is replaced by v
+                    }
+                }
+            }
             // 2. progress key of the lane's next (or current) source
             const uint32_t elim = e_end < eloaded ? e_end : eloaded;  // records of the row that are in the edge ring
-            bool staged = !done && !need_row && (v + (uint32_t)A.span < loaded || loaded >= b);
+            if (!staged && !done && !need_row && (v + (uint32_t)A.span < loaded || loaded >= b)) {
+                staged = true;
+                col = (uint32_t)colring[v & M];
+            }
             const uint32_t xr = x - xbase < 4000u ? x - xbase : 4000u;
-            uint32_t K = done ? KINF : (xr << 20) | (staged ? (uint32_t)colring[v & M] : 0u);
+            const uint32_t K = done ? KINF : (xr << 20) | (staged ? col : 0u);
+            // speculative operand loads (always valid addresses) so that they overlap the scan
+            const int4 sl = ring[v & M];
+            uint2 rec = ering[e & EM];
             // 3. cyclic min-plus scan over the other 31 lanes: val = min_d (K[(l-d) mod 32] + d * B)
             uint32_t val = __shfl_sync(FULL, K, (lane - 1) & 31) + B;
 #pragma unroll
@@ -946,30 +960,21 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
                 const uint32_t other = __shfl_sync(FULL, val, (lane - d) & 31) + (uint32_t)d * B;
                 val = other < val ? other : val;
             }
-            // 4. up to ICL_WAVE_REC lock-step iterations: start a source when allowed, replay one record
-            //    (keys of the other lanes only grow, so `val` stays a valid lower bound within the round)
-#pragma unroll 1
-            for (int r = 0; r < ICL_WAVE_REC; r++) {
-                if (!in_src && staged && e < elim && val >= K + (uint32_t)mg2) {
-                    const int4 sl = ring[v & M];
-                    Sv = sl.x; dv = sl.y; rootv = sl.w;
-                    gap = mg2; dr_old = 0; uv = false; broken = false;
-                    in_src = true;
-                }
-                const bool work = in_src && e < elim;
-                if (!__any_sync(FULL, work)) break;
-                if (work) {
-                    const uint2 rec = ering[e & EM];
-                    if (!fresh && (rec.y >> 8)) {
-                        // this record opens the next source of the row (its predecessor ended while the
-                        // record was not staged yet): close the current source, replay nothing
-                        if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
-                        in_src = false;
-                        v += rec.y >> 8; fresh = true;
-                        staged = v + (uint32_t)A.span < loaded || loaded >= b;
-                        K = (xr << 20) | (staged ? (uint32_t)colring[v & M] : 0u);
-                        continue;
-                    }
+            // 4. start the source when allowed, replay up to two of its records
+            if (!in_src && staged && e < elim && val >= K + (uint32_t)mg2) {
+                Sv = sl.x; dv = sl.y; rootv = sl.w;
+                gap = mg2; dr_old = 0; uv = false; broken = false;
+                in_src = true;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (!(in_src && e < elim)) break;
+                if (r) rec = ering[e & EM];
+                bool close = false;
+                uint32_t adv = rec.y >> 8;
+                if (!fresh && adv) {
+                    close = true;                                     // this record opens the next source of the row
+                } else {
                     const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
                     broken = broken || (dc > gap && dr > dr_old);     // collinearity.py:83-84
                     const uint32_t slot = (v + (rec.x & 0xffffu)) & M;
@@ -982,20 +987,16 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
                     }
                     e++;
                     fresh = false;
-                    // end of the source: end of the row, or the next record (if staged) opens another source
-                    uint32_t adv = 0;
-                    const bool row_end = e >= e_end;
-                    if (!row_end && e < eloaded) adv = ering[e & EM].y >> 8;
-                    if (row_end || adv) {
-                        if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
-                        in_src = false;
-                        if (row_end) { need_row = true; x += 32; staged = false; }
-                        else {
-                            v += adv; fresh = true;
-                            staged = v + (uint32_t)A.span < loaded || loaded >= b;
-                            K = (xr << 20) | (staged ? (uint32_t)colring[v & M] : 0u);
-                        }
-                    }
+                    adv = 0;
+                    if (e >= e_end) close = true;                     // end of the row
+                    else if (e < eloaded) { adv = ering[e & EM].y >> 8; close = adv != 0; }
+                }
+                if (close) {
+                    if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+                    in_src = false;
+                    staged = false;
+                    if (e >= e_end) { need_row = true; x += 32; }
+                    else { v += adv; fresh = true; }
                 }
             }
             // 5. publish the trailing edge of the wave so the helper can retire / refill
@@ -1006,7 +1007,7 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
                 __syncwarp();
                 __threadfence_block();
                 if (lane == 0) { ctl_retired = rmin; ctl_emin = emin; ctl_xmin = xmin; }
-                __syncwarp();                                         // every lane reads the same xbase next round
+                __syncwarp();                                         // every lane reads the same xbase next time
             }
         }
         __syncwarp();
