@@ -21,6 +21,7 @@
 #include "icl_platform.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <numeric>
 #include <vector>
 
@@ -65,7 +66,8 @@ struct icl_ctx {
     int64_t n_edges = 0;
     int32_t max_span = 0;            // largest (target position - source position) over all edges
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
-    int32_t chain_mode = 2;          // 2 = wave kernel, 1 = single-executor ring kernel, 0 = generic (env ICL_B200_CHAIN)
+    int32_t chain_mode = 1;          // 1 = single-executor ring kernel (default), 2 = wave kernel, 0 = generic (env ICL_B200_CHAIN)
+    Buf<long long> chain_dbg;
     int32_t wave_span = 0;           // most points inside 64 + mg1 consecutive rows of an item
     Buf<int2> rowtab;                // per dense row: {first edge record, first source that has records | -1}
     // DP state (V space)
@@ -200,7 +202,7 @@ extern "C" int icl_create(int device, icl_ctx **out) {
 #endif
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
-    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "ring") ? 1 : 2;
+    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "wave") ? 2 : 1;
     *out = c;
     return ICL_OK;
 }
@@ -217,7 +219,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
-    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release();
+    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release(); c->chain_dbg.release();
     c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
@@ -628,6 +630,7 @@ struct ChainArgs {
     int32_t *S, *root;
     int2 *pd;
     uint8_t *used;
+    long long *dbg;                  // optional per-item {rounds, cycles} (diagnostics), may be NULL
 };
 
 // the reference sweep over the flat edge stream of one item, on global memory (oversized windows, emulation)
@@ -918,6 +921,7 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
         int32_t Sv = 0, dv = 0, rootv = 0, gap = 0, dr_old = 0;
         bool uv = false, broken = false;
         uint32_t round = 0;
+        const long long t_start = clock64();
         uint32_t loaded = a, rowloaded = 0, eloaded = e0, xbase = 0;
         uint32_t col = 0;                                 // column of source v (valid when staged)
         bool staged = false;
@@ -1012,6 +1016,7 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
         }
         __syncwarp();
         __threadfence_block();
+        if (lane == 0 && A.dbg) { A.dbg[2 * blockIdx.x] = round; A.dbg[2 * blockIdx.x + 1] = clock64() - t_start; }
         if (lane == 0) { ctl_retired = b; ctl_emin = e1; ctl_xmin = nrows; }
         return;
     }
@@ -1110,6 +1115,12 @@ static int phase_chain(icl_ctx *c) {
     A.n = n; A.P = P; A.mg2 = c->prm.mg2; A.RS = 0; A.span = c->max_span;
     A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
     A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p; A.root = c->root.p;
+    A.dbg = nullptr;
+    if (getenv("ICL_B200_CHAIN_DEBUG")) {
+        if (c->chain_dbg.reserve(st, 4 * (size_t)P + 4)) return st.code;
+        ICL_CUDA(st, dev_memset(c->chain_dbg.p, 0, (4 * (size_t)P + 4) * sizeof(long long), s));
+        A.dbg = c->chain_dbg.p;
+    }
     if (P == 0 || n == 0) return 0;
 #ifndef ICL_EMU
     if (c->chain_mode != 0) {
@@ -1208,6 +1219,19 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
     }
     c->timers[ICL_T_EXPORT].stop(s);
     ICL_CUDA(st, dev_sync(s));
+    if (getenv("ICL_B200_CHAIN_DEBUG") && c->chain_dbg.p && c->P > 0) {
+        std::vector<long long> h(4 * (size_t)c->P);
+        ICL_CUDA(st, d2h(h.data(), c->chain_dbg.p, h.size() * sizeof(long long), s));
+        ICL_CUDA(st, dev_sync(s));
+        FILE *f = fopen(getenv("ICL_B200_CHAIN_DEBUG"), "w");
+        if (f) {
+            for (int32_t j = 0; j < 2 * c->P; j++) {
+                int32_t it = c->h_item_order[j], p = it >= c->P ? it - c->P : it;
+                fprintf(f, "%d %d %lld %d %lld %lld\n", j, it, (long long)(c->h_pair_off[p + 1] - c->h_pair_off[p]), c->h_nrows[p], h[2 * j], h[2 * j + 1]);
+            }
+            fclose(f);
+        }
+    }
     c->counters[0] = c->n_edges;
     c->counters[1] = 13;   // kernels launched by icl_dp (stats excluded): key, decode, pair_off, pair_meta, rowptr x2,
                            // mirror, rowptr_rev, edge count, edge fill, chain, export + CUB passes
