@@ -726,13 +726,18 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
     if (threadIdx.x < 32) {
         // ---------------------------------------------------------------- executor (one thread)
         if (lane != 0) return;
-        uint32_t loaded = a, v = a, vpub = a;
+        uint32_t loaded = a, v = a;
         const int32_t mg2 = A.mg2;
-        while (loaded <= v) loaded = ctl_loaded;                  // the item's first point is staged
+        const uint32_t span = (uint32_t)A.span;
+        // the window of the current source ([v, v + span]) is staged before any of its records is replayed,
+        // so the record loop itself never looks at the helper's progress
+        while (loaded < b && loaded <= v + span) loaded = ctl_loaded;
         __threadfence_block();
         int4 sl = ring[v & M];
-        int32_t Sv = sl.x, dv = sl.y, rootv = sl.w, gap = mg2, dr_old = 0;
-        bool uv = false, broken = false;
+        int32_t Sv = sl.x, dv1 = sl.y + 1, rootv = sl.w, gap = mg2, dr_old = 0;
+        uint32_t uv = 0;
+        bool broken = false;
+        int32_t pub = 32;
         uint32_t e = e0;
         while (e < e1) {
             // ---- enter the chunk that holds record e: free the previous ones, wait for the TMA bytes
@@ -748,39 +753,37 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 nxt = ering[(e + 1) & EM];                        // next record early (unused at a chunk end)
                 const uint32_t adv = rec.y >> 8;
                 if (adv) {                                        // next source that has candidates
-                    if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+                    ring[v & M].y = (dv1 - 1) | (int32_t)uv;      // used-as-source flag of the finished source
                     v += adv;
-                    if (v >= loaded) {
-                        do { loaded = ctl_loaded; } while (loaded <= v);
+                    if (loaded < b && loaded <= v + span) {       // the new source's window is not staged yet:
+                        __threadfence_block();                    // retire everything before v so the helper can move on
+                        ctl_retired = v;
+                        pub = 32;
+                        do { loaded = ctl_loaded; } while (loaded < b && loaded <= v + span);
                         __threadfence_block();
                     }
                     sl = ring[v & M];
-                    Sv = sl.x; dv = sl.y; rootv = sl.w;
-                    gap = mg2; dr_old = 0; uv = false; broken = false;
-                    if ((v ^ vpub) >> 5) {                        // let the helper retire finished points
+                    Sv = sl.x; dv1 = sl.y + 1; rootv = sl.w;
+                    gap = mg2; dr_old = 0; uv = 0; broken = false;
+                    if (--pub == 0) {                             // let the helper retire finished points
+                        pub = 32;
                         __threadfence_block();
                         ctl_retired = v;
-                        vpub = v;
                     }
                 }
                 const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
                 broken = broken || (dc > gap && dr > dr_old);     // collinearity.py:83-84
-                const uint32_t k = v + (rec.x & 0xffffu);
-                if (k >= loaded) {                                // the target is not staged yet
-                    do { loaded = ctl_loaded; } while (loaded <= k);
-                    __threadfence_block();
-                }
-                const uint32_t slot = k & M;
+                const uint32_t slot = (v + (rec.x & 0xffffu)) & M;
                 const int32_t cand = Sv + sc;
                 if (!broken && sc > 0 && ring[slot].x < cand) {   // :87 strict <
-                    ring[slot] = make_int4(cand, dv + 1, (int32_t)v, rootv);
-                    uv = true;
+                    ring[slot] = make_int4(cand, dv1, (int32_t)v, rootv);
+                    uv = ICL_USED_FLAG;
                     gap = dc < gap ? dc : gap;                    // :92
                     dr_old = dr;                                  // :93
                 }
             }
         }
-        if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
+        ring[v & M].y = (dv1 - 1) | (int32_t)uv;
         __threadfence_block();
         ctl_retired = b;
         return;
