@@ -244,6 +244,39 @@ def test_sharded_equals_unsharded(gpu_engine):
             assert (getattr(merged, f) == getattr(whole, f)).all(), f
 
 
+@pytest.mark.parametrize("name,scale,mg", [("C1", 1.0, (25, 25)), ("C3", 0.3, (40, 40)), ("C4", 0.25, (50, 50))])
+def test_other_baseline_configs_match_oracle(gpu_engine, name, scale, mg):
+    """BASELINE.json configs 1 (full size: 25 pairs of ~40k points), 3 (cross-species) and 4 (wheat-like) at a
+    bounded scale, with the three `mg` settings of config 5's sweep: block lists identical to the C oracle."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    ds = synth.make_dataset(name, scale=scale)
+    pts = synth.graded_points(ds)
+    prm = ChainParams(mg1=mg[0], mg2=mg[1], grading=tuple(ds.cfg.grading))
+    blocks = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    _compare_with_oracle(blocks, oracle_blocks(pts, prm))
+    assert gpu_engine.counters()["chain_kernel"] == "ring"
+
+
+def test_wave_and_generic_kernels_agree(clouds):
+    """The alternative DP kernels (ICL_B200_CHAIN=wave / generic) give the same blocks as the default ring kernel."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    exp = oracle_blocks(pts, prm)
+    for mode in ("wave", "generic"):
+        os.environ["ICL_B200_CHAIN"] = mode
+        try:
+            eng = IclEngine(0)
+            blocks = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+            assert eng.counters()["chain_kernel"] == mode
+            eng.close()
+        finally:
+            del os.environ["ICL_B200_CHAIN"]
+        _compare_with_oracle(blocks, exp)
+
+
 def test_full_size_C2_matches_oracle_and_properties(gpu_engine):
     """BASELINE.json config 2 (Vitis-sized self comparison, ~2M graded hits) at full size: identical to the C oracle,
     plus size-independent properties."""
