@@ -115,6 +115,43 @@ def cpu_port_pass(pts, prm, threads):
     return dt, int(bt.n_blk[0].sum() + bt.n_blk[1].sum())
 
 
+def icl_wall_time(workload, device):
+    """`-icl` wall time per genome pair: conf in -> collinearity file out through the drop-in driver
+    (`mycollinearity(options).run()`: parse gff/lens/m8, filter, grade, GPU chaining, write the file)."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    from wgdi_b200 import base, synth
+    from wgdi_b200.run_colliearity import mycollinearity
+    root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="icl_wall_", dir=root)
+    try:
+        ds = synth.make_dataset(workload)
+        conf = synth.write_dataset(ds, d)
+        blast_mb = os.path.getsize(os.path.join(d, "blast.m8")) / 1e6
+        best, timing, native = None, None, None
+        for _ in range(2):
+            opts = list(base.load_conf(conf, "collinearity")) + [("device", str(device))]
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = mycollinearity(opts)
+                try:
+                    m.run()
+                except SystemExit:
+                    pass
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, timing, native = dt, m.timing, m.native
+        out_mb = os.path.getsize(dict(opts)["savefile"]) / 1e6
+        return {"value": best, "unit": "s", "what": "conf in -> collinearity file out, best of 2, files in tmpfs",
+                "blast_rows": int(len(ds.q)), "blast_mb": round(blast_mb, 1), "out_mb": round(out_mb, 1),
+                "ingest_s": timing.get("ingest_s"), "chain_s": timing.get("chain_s"), "write_s": timing.get("write_s"),
+                "host_path": "native (libicl_host.so)" if native else "pandas"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference_arm(args, rank, world):
     """The reference's algorithm on the host cores.  The reference is pure Python (6-8 ms per point per core,
     BASELINE.md) and does not exist on the GPU box, so this arm times the oracle's C port of it (kind "port"),
@@ -154,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wall", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -298,6 +336,9 @@ def main():
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }
+        if not args.no_wall and world == 1:
+            eng.close()
+            line["icl_wall"] = icl_wall_time(args.workload, local)
         if not args.no_cpu_baseline and world == 1:
             from oracle import c_oracle
             c_oracle.build()

@@ -1,0 +1,79 @@
+/*
+ * icl_host.h — native host-side helpers of the `-icl` path (ingest and writer).
+ *
+ * Plain C ABI, no CUDA: libicl_host.so is built with g++ and is independent of libicl_b200.so.
+ * What each entry point replaces in the reference:
+ *
+ *   icl_host_read_m8       wgdi/base.py:172-183 (newblast: pandas.read_csv + the row filters + drop_duplicates)
+ *                          and the id -> gene lookups of wgdi/run_colliearity.py:103-106
+ *   icl_host_grade         wgdi/run_colliearity.py:59-86 (deal_blast_for_genomes), except for queries whose tied
+ *                          bit scores straddle a class boundary: those are reported and re-ranked by the caller
+ *                          with numpy's own unstable argsort (SURVEY.md hazard H2)
+ *   icl_host_write_blocks  wgdi/run_colliearity.py:143-155,181-199 (gene names, strands, text assembly, file)
+ *
+ * All functions return 0 or a negative code and fill `err` (NUL-terminated, truncated to errlen).
+ */
+#ifndef ICL_HOST_H
+#define ICL_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct icl_hits {
+    int64_t n;             /* rows that survive the filters of wgdi/base.py:178-180 */
+    int64_t n_rows_file;   /* data rows in the file (blank lines are skipped like pandas does) */
+    int32_t bits_is_int;   /* 1 when every column-11 token is an integer literal: pandas infers int64, else float64 */
+    int64_t *row;          /* [n] 0-based row number in the file = the reference's row label */
+    int32_t *g1;           /* [n] row of id1 in the genome-1 gene table */
+    int32_t *g2;           /* [n] row of id2 in the genome-2 gene table */
+    double *bits;          /* [n] column 11 (bit score) */
+} icl_hits;
+
+/*
+ * Parse a BLAST -outfmt 6 / m8 table (tab separated, >= 12 columns, no header) with `threads` threads and keep
+ * the rows the reference keeps: bitscore >= min_score and evalue < max_evalue and id1 != id2 (base.py:178),
+ * both ids present in the gene tables (:179), first occurrence of every (id1, id2) in file order (:180).
+ * reverse != 0 swaps the two id columns first (base.py:176-177; the caller passes 1 only for the exact string
+ * 'true').  Gene tables: concatenated id bytes + offsets[n+1].
+ */
+int icl_host_read_m8(const char *path, int32_t reverse, double min_score, double max_evalue,
+                     const char *ids1, const int64_t *off1, int64_t n1,
+                     const char *ids2, const int64_t *off2, int64_t n2,
+                     int32_t threads, icl_hits *out, char *err, int32_t errlen);
+void icl_host_free_hits(icl_hits *hits);
+
+/*
+ * Grading by per-query hit rank (run_colliearity.py:59-86): for every query (all target chromosomes together)
+ * hits are ranked by bit score descending; rank < multiple -> grading[0]; rank < multiple+4 -> grading[1];
+ * rank < repeat_number -> grading[2]; others 0.  Ties are broken by file order here; a query whose class
+ * assignment depends on the tie order (equal scores on both sides of a boundary) is flagged in
+ * ambiguous[query] so that the caller can apply numpy's permutation to exactly those queries.
+ */
+int icl_host_grade(int64_t n, const int32_t *query, const double *bits, int32_t n_query,
+                   int32_t multiple, int32_t repeat_number, const int32_t *grading3,
+                   int32_t *grade_out, uint8_t *ambiguous, int32_t threads, char *err, int32_t errlen);
+
+/*
+ * Write the collinearity file.  For every selected block b (already filtered and ordered by the caller):
+ *   header[b]                                   "# Alignment k: score=.. pvalue=.. N=.. chr1&chr2 plus|minus"
+ *   one line per member   name1 loc1 name2 loc2 strand      strand = "1" iff the two strand strings are equal
+ * Genes are found by (chromosome code, order): row = row_of[code * maxo + order].
+ */
+int icl_host_write_blocks(const char *path, int64_t n_sel,
+                          const char *headers, const int64_t *header_off,
+                          const int64_t *mem_begin, const int64_t *mem_end,
+                          const int32_t *loc1, const int32_t *loc2,
+                          const int32_t *chr1_code, const int32_t *chr2_code,
+                          const int64_t *row_of1, int64_t maxo1, const char *names1, const int64_t *name_off1,
+                          const int32_t *strand_code1,
+                          const int64_t *row_of2, int64_t maxo2, const char *names2, const int64_t *name_off2,
+                          const int32_t *strand_code2,
+                          int32_t threads, char *err, int32_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICL_HOST_H */

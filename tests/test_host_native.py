@@ -1,0 +1,118 @@
+"""Native host helpers (libicl_host.so: m8 ingest, grading, writer) against the pandas readers that mirror the
+reference and against the oracle.  CPU only."""
+import contextlib
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, stage_e2e
+from oracle import icl_oracle
+
+
+@pytest.fixture(scope="module")
+def host():
+    from wgdi_b200 import _host, build
+    build.build_host()
+    _host._LIB = None
+    return _host
+
+
+def test_host_library_exports_declared_symbols(host):
+    lib = ctypes.CDLL(host.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "icl_host.h")).read()
+    declared = set(re.findall(r"\b(icl_host_[a-z_0-9]+)\s*\(", header))
+    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks"}
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def _write(path, rows):
+    with open(path, "w", newline="") as f:
+        f.write(rows)
+
+
+def test_read_m8_filters_like_newblast(host, tmp_path):
+    import pandas as pd
+    from wgdi_b200 import base
+    genes = [f"g{i}" for i in range(8)]
+    gff = pd.DataFrame({"chr": ["1"] * 8}, index=pd.Index(genes))
+    rows = [
+        ("g0", "g1", "1e-30", "250"), ("g0", "g1", "1e-20", "200"),      # duplicate pair: first kept
+        ("g0", "g0", "0", "900"),                                       # self hit
+        ("g1", "g2", "1.00e-05", "300"),                                # evalue == threshold: strict <
+        ("g1", "g3", "9.99e-06", "100"),                                # score == threshold: >=
+        ("g1", "g4", "1e-50", "99"), ("zz", "g1", "1e-50", "500"), ("g1", "zz", "1e-50", "500"),
+        ("g2", "g5", "3e-12", "120"), ("g7", "g6", "2e-9", "101"),
+    ]
+    def table(score_fmt=lambda s: s, sep="\n", blank=False, extra=False):
+        out = []
+        for a, b, ev, sc in rows:
+            cols = [a, b, "90.1", "100", "1", "0", "1", "100", "1", "100", ev, score_fmt(sc)] + (["x"] if extra else [])
+            out.append("\t".join(cols))
+            if blank:
+                out.append("")
+        return sep.join(out) + sep
+    ids = host.pack_strings(genes)
+    for kind, text in (("int", table()), ("crlf+blank", table(sep="\r\n", blank=True)),
+                       ("float", table(score_fmt=lambda s: s + ".5" if s == "120" else s))):
+        p = tmp_path / f"{kind}.m8"
+        _write(p, text)
+        got = host.read_m8(str(p), False, 100, 1e-5, ids, ids, threads=3)
+        exp = base.newblast(str(p), 100, 1e-5, gff, gff, "false")
+        assert (got["g1"] == exp["g1"].to_numpy()).all() and (got["g2"] == exp["g2"].to_numpy()).all(), kind
+        assert got["bits"].dtype == exp[11].to_numpy().dtype and (got["bits"] == exp[11].to_numpy()).all(), kind
+        assert (got["row"] == exp.index.to_numpy()).all(), kind
+    # reverse swaps the id columns first
+    p = tmp_path / "rev.m8"
+    _write(p, table())
+    got = host.read_m8(str(p), True, 100, 1e-5, ids, ids)
+    exp = base.newblast(str(p), 100, 1e-5, gff, gff, "true")
+    assert (got["g1"] == exp["g1"].to_numpy()).all() and (got["g2"] == exp["g2"].to_numpy()).all()
+    # malformed rows are an error, a missing file too
+    _write(tmp_path / "bad.m8", "g0\tg1\t1\n")
+    with pytest.raises(host.HostError):
+        host.read_m8(str(tmp_path / "bad.m8"), False, 100, 1e-5, ids, ids)
+    with pytest.raises(host.HostError):
+        host.read_m8(str(tmp_path / "missing.m8"), False, 100, 1e-5, ids, ids)
+    # empty file
+    _write(tmp_path / "empty.m8", "")
+    assert len(host.read_m8(str(tmp_path / "empty.m8"), False, 100, 1e-5, ids, ids)["g1"]) == 0
+
+
+def test_native_grading_matches_oracle_with_ties(host):
+    from wgdi_b200.ingest import grade_hits_native
+    rng = np.random.default_rng(21)
+    for trial in range(150):
+        n, nq = int(rng.integers(1, 500)), int(rng.integers(1, 40))
+        q = rng.integers(0, nq, n).astype(np.int32)
+        bits = rng.integers(100, 104 + trial % 7 * 20, n).astype(np.int64 if trial % 3 else np.float64)
+        mult, rn = int(rng.integers(0, 4)), int(rng.integers(1, 25))
+        got = grade_hits_native(q, bits, nq, mult, rn, [50, 30, 25])
+        assert (got == icl_oracle.grade_hits(q, bits, mult, rn, [50, 30, 25])).all()
+
+
+@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev"])
+def test_native_and_pandas_paths_write_the_same_file(host, emu_backend, case, tmp_path):
+    """conf in -> file out through the native parser / writer and through the pandas readers (fake device backend)."""
+    from wgdi_b200 import base
+    from wgdi_b200.run_colliearity import mycollinearity
+    stage_e2e(case, str(tmp_path))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        texts = {}
+        for mode in ("native", "pandas"):
+            opts = [(k, v if k != "savefile" else f"{mode}.txt") for k, v in base.load_conf("icl.conf", "collinearity")]
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = mycollinearity(opts + [("ingest", mode)])
+                assert m.native == (mode == "native")
+                with pytest.raises(SystemExit):
+                    m.run()
+            texts[mode] = open(f"{mode}.txt").read()
+        assert texts["native"] == texts["pandas"] and len(texts["native"]) > 1000
+    finally:
+        os.chdir(cwd)

@@ -1,0 +1,117 @@
+"""ctypes binding of libicl_host.so (include/icl_host.h): native m8 ingest, grading and file writer.
+
+Host-only C++ (no CUDA).  When the library is not built the driver uses the pandas readers of
+`wgdi_b200.base`, which mirror the reference's; both produce identical points and files.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicl_host.so")
+_LIB = None
+
+
+class icl_hits(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_rows_file", C.c_int64), ("bits_is_int", C.c_int32),
+                ("row", C.POINTER(C.c_int64)), ("g1", C.POINTER(C.c_int32)), ("g2", C.POINTER(C.c_int32)),
+                ("bits", C.POINTER(C.c_double))]
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        lib.icl_host_read_m8.argtypes = [C.c_char_p, i32, dbl, dbl, vp, vp, i64, vp, vp, i64, i32, C.POINTER(icl_hits), vp, i32]
+        lib.icl_host_free_hits.argtypes = [C.POINTER(icl_hits)]
+        lib.icl_host_free_hits.restype = None
+        lib.icl_host_grade.argtypes = [i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32]
+        lib.icl_host_write_blocks.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
+                                              vp, i64, vp, vp, vp, i32, vp, i32]
+        _LIB = lib
+    return _LIB
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _call(fn, *args):
+    err = C.create_string_buffer(512)
+    rc = fn(*args, err, 512)
+    if rc != 0:
+        raise HostError(f"icl_host error {rc}: {err.value.decode(errors='replace')}")
+
+
+def pack_strings(values):
+    """(bytes, offsets[n+1]) of a sequence of str."""
+    enc = [str(v).encode() for v in values]
+    off = np.zeros(len(enc) + 1, np.int64)
+    np.cumsum([len(b) for b in enc], out=off[1:])
+    return b"".join(enc), off
+
+
+def threads_default():
+    return min(32, os.cpu_count() or 1)
+
+
+def read_m8(path, reverse, min_score, max_evalue, ids1, ids2, threads=None):
+    """Rows of the m8 table that survive wgdi/base.py:176-180.  ids1/ids2: (bytes, offsets) gene tables.
+    Returns dict(row, g1, g2, bits) with bits typed like pandas would infer column 11."""
+    lib = load()
+    out = icl_hits()
+    b1, o1 = ids1
+    b2, o2 = ids2
+    same = ids1 is ids2
+    p1 = C.cast(C.c_char_p(b1), C.c_void_p)
+    p2 = p1 if same else C.cast(C.c_char_p(b2), C.c_void_p)
+    _call(lib.icl_host_read_m8, str(path).encode(), 1 if reverse else 0, float(min_score), float(max_evalue),
+          p1, o1.ctypes.data, len(o1) - 1, p2, (o1 if same else o2).ctypes.data, len(o2) - 1,
+          int(threads or threads_default()), C.byref(out))
+    try:
+        n = out.n
+
+        def arr(ptr, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        bits = arr(out.bits, np.float64)
+        if out.bits_is_int:
+            bits = bits.astype(np.int64)
+        return dict(row=arr(out.row, np.int64), g1=arr(out.g1, np.int32), g2=arr(out.g2, np.int32), bits=bits,
+                    n_rows_file=int(out.n_rows_file))
+    finally:
+        lib.icl_host_free_hits(C.byref(out))
+
+
+def grade(query, bits, n_query, multiple, repeat_number, grading, threads=None):
+    """(grading per hit, ambiguous flag per query) — see icl_host_grade."""
+    lib = load()
+    q = np.ascontiguousarray(query, np.int32)
+    b = np.ascontiguousarray(bits, np.float64)
+    g3 = np.ascontiguousarray(grading[:3], np.int32)
+    out = np.zeros(len(q), np.int32)
+    amb = np.zeros(max(int(n_query), 1), np.uint8)
+    _call(lib.icl_host_grade, len(q), q.ctypes.data, b.ctypes.data, int(n_query), int(multiple), int(repeat_number),
+          g3.ctypes.data, out.ctypes.data, amb.ctypes.data, int(threads or threads_default()))
+    return out, amb[:n_query].astype(bool)
+
+
+def write_blocks(path, headers, mem_begin, mem_end, loc1, loc2, chr1_code, chr2_code, genes1, genes2, threads=None):
+    lib = load()
+    hb, ho = pack_strings(headers)
+    a = [np.ascontiguousarray(x, dt) for x, dt in ((mem_begin, np.int64), (mem_end, np.int64), (loc1, np.int32),
+                                                  (loc2, np.int32), (chr1_code, np.int32), (chr2_code, np.int32))]
+    _call(lib.icl_host_write_blocks, str(path).encode(), len(headers), C.cast(C.c_char_p(hb), C.c_void_p), ho.ctypes.data,
+          *[x.ctypes.data for x in a],
+          genes1["row_of"].ctypes.data, int(genes1["maxo"]), C.cast(C.c_char_p(genes1["name_bytes"]), C.c_void_p),
+          genes1["name_off"].ctypes.data, genes1["strand_code"].ctypes.data,
+          genes2["row_of"].ctypes.data, int(genes2["maxo"]), C.cast(C.c_char_p(genes2["name_bytes"]), C.c_void_p),
+          genes2["name_off"].ctypes.data, genes2["strand_code"].ctypes.data,
+          int(threads or threads_default()))

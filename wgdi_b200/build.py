@@ -54,6 +54,16 @@ def build_npsort(force=False):
     return out
 
 
+def build_host(force=False):
+    """Native host helpers (m8 ingest, grading, writer): g++, no CUDA."""
+    src = os.path.join(HERE, "csrc", "icl_host.cpp")
+    out = os.path.join(HERE, "libicl_host.so")
+    if not force and not _stale(out, [src, os.path.join(os.path.dirname(HERE), "include", "icl_host.h")]):
+        return out
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-o", out, src])
+    return out
+
+
 def build_emu(outdir, force=False):
     os.makedirs(outdir, exist_ok=True)
     out = os.path.join(outdir, "libicl_b200_emu.so")
@@ -70,3 +80,4 @@ if __name__ == "__main__":
     else:
         print(build(force=True, verbose=True))
         print(build_npsort(force=True))
+        print(build_host(force=True))

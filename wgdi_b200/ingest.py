@@ -55,6 +55,18 @@ def grade_hits(q, bits, multiple, repeat_number, grading):
     return out
 
 
+def grade_hits_native(q, bits, n_query, multiple, repeat_number, grading):
+    """`grade_hits` with the per-query ranking done by libicl_host.so (stable order); queries whose class
+    assignment depends on numpy's tie permutation are re-graded by `grade_hits` on exactly their hits."""
+    from . import _host
+    out, amb = _host.grade(q, bits, n_query, multiple, repeat_number, grading)
+    out = out.astype(np.int64)
+    if amb.any():
+        sel = np.flatnonzero(amb[q])
+        out[sel] = grade_hits(np.asarray(q)[sel], np.asarray(bits)[sel], multiple, repeat_number, grading)
+    return out
+
+
 def pair_ids(chr1_names, chr2_names, c1, c2):
     """Chromosome-pair id per hit, numbered in the sorted (chr1, chr2) STRING order pandas' groupby
     iterates (wgdi/run_colliearity.py:118).  Returns (pair_id, [(chr1, chr2) per pair])."""

@@ -15,9 +15,9 @@ import time
 
 import numpy as np
 
-from . import base
+from . import _host, base
 from .engine import ChainParams, IclEngine
-from .ingest import grade_hits, pair_ids
+from .ingest import grade_hits, grade_hits_native, pair_ids
 
 
 class mycollinearity():
@@ -42,6 +42,9 @@ class mycollinearity():
         self.process = int(self.process) if hasattr(self, 'process') else 4
         self.over_gap = int(self.over_gap)
         self.device = int(getattr(self, 'device', 0))     # extra, optional key: CUDA device index
+        # extra, optional key: `ingest = pandas` forces the reference-like pandas readers of wgdi_b200.base;
+        # the default uses the native parser / writer (libicl_host.so) when it is built.  Same results.
+        self.native = getattr(self, 'ingest', 'native').lower() != 'pandas' and _host.available()
         self.timing = {}
 
     # ---- ingest: wgdi/run_colliearity.py:88-121 -------------------------------------------------
@@ -54,12 +57,19 @@ class mycollinearity():
         gff2 = base.newgff(self.gff2)
         gff1 = gff1[gff1['chr'].isin(lens1.index)]        # :96-97
         gff2 = gff2[gff2['chr'].isin(lens2.index)]
-        blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
         if self.comparison.lower() != 'genomes':
             raise NotImplementedError("comparison = chromosomes is not offered (the reference raises KeyError "
                                       "there under pandas >= 3; SURVEY.md H19)")
-        g1, g2 = blast['g1'].to_numpy(), blast['g2'].to_numpy()
-        grade = grade_hits(g1, blast[11].to_numpy(), int(self.multiple), int(self.repeat_number), self.grading)
+        if self.native:
+            ids1 = _host.pack_strings(gff1.index)
+            ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
+            hits = _host.read_m8(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2)
+            g1, g2 = hits['g1'], hits['g2']
+            grade = grade_hits_native(g1, hits['bits'], len(gff1), int(self.multiple), int(self.repeat_number), self.grading)
+        else:
+            blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
+            g1, g2 = blast['g1'].to_numpy(), blast['g2'].to_numpy()
+            grade = grade_hits(g1, blast[11].to_numpy(), int(self.multiple), int(self.repeat_number), self.grading)
         ok = grade > 0                                    # :86
         g1, g2, grade = g1[ok], g2[ok], grade[ok]
         print(f"The filtered homologous gene pairs are {len(g1)}.\n")      # :112
@@ -89,9 +99,13 @@ class mycollinearity():
         finally:
             eng.close()
         t2 = time.perf_counter()
-        text = format_blocks(blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue, self.over_gap)
-        with open(self.savefile, 'w') as fout:
-            fout.write(text)
+        if self.native:
+            write_blocks_native(self.savefile, blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue,
+                                self.over_gap)
+        else:
+            text = format_blocks(blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue, self.over_gap)
+            with open(self.savefile, 'w') as fout:
+                fout.write(text)
         t3 = time.perf_counter()
         self.timing.update(ingest_s=t1 - t0, chain_s=t2 - t1, write_s=t3 - t2)
         sys.exit(0)                                       # :156
@@ -106,8 +120,40 @@ def _gene_table(gff):
     # like Series.map on an index with duplicates would, the first gene of an order wins
     key = chr_code.astype(np.int64) * maxo + order
     row_of[key[::-1]] = np.arange(len(order))[::-1]
+    strand = gff['strand'].to_numpy().astype(str)
     return dict(chr_names=list(chr_names), chr_code=chr_code.astype(np.int64), order=order, maxo=maxo, row_of=row_of,
-                name=gff.index.to_numpy().astype(str), strand=gff['strand'].to_numpy().astype(str))
+                name=gff.index.to_numpy().astype(str), strand=strand)
+
+
+def _native_gene_tables(genes1, genes2):
+    """Tables for icl_host_write_blocks: packed names and strand codes over a vocabulary shared by both genomes."""
+    vocab = {v: i for i, v in enumerate(sorted(set(genes1['strand'].tolist()) | set(genes2['strand'].tolist())))}
+    for g in (genes1, genes2):
+        if 'name_bytes' not in g:
+            g['name_bytes'], g['name_off'] = _host.pack_strings(g['name'])
+            g['strand_code'] = np.array([vocab[v] for v in g['strand']], np.int32)
+            g['row_of'] = np.ascontiguousarray(g['row_of'], np.int64)
+
+
+def write_blocks_native(path, blocks, pair_names, genes1, genes2, pvalue, over_gap):
+    """Same file as `format_blocks`, assembled and written by libicl_host.so."""
+    p = blocks.p_value()                                  # numpy rounding, collinearity.py:153
+    emit = np.flatnonzero(~(p > pvalue) & (blocks.m >= over_gap))
+    _native_gene_tables(genes1, genes2)
+    c1code = {name: i for i, name in enumerate(genes1['chr_names'])}
+    c2code = {name: i for i, name in enumerate(genes2['chr_names'])}
+    pc1 = np.array([c1code[a] for a, _ in pair_names], np.int32)
+    pc2 = np.array([c2code[b] for _, b in pair_names], np.int32)
+    beg, end = blocks.member_off[emit], blocks.member_off[emit + 1]
+    y0, y1 = blocks.loc2[beg], blocks.loc2[beg + 1]      # emitted blocks have >= over_gap >= 2 members
+    headers = []
+    for num, (b, s, pv, m, a, c) in enumerate(zip(emit.tolist(), blocks.score[emit].tolist(), p[emit], (end - beg).tolist(),
+                                                  y0.tolist(), y1.tolist()), start=1):
+        chr1, chr2 = pair_names[blocks.pair[b]]
+        tail = f" score={s} pvalue={pv} N={m} {chr1}&{chr2} {'plus' if a < c else 'minus'}"
+        headers.append(f"# Alignment {num}:" + tail.split(':')[0])             # :147-151 re-cuts the header at ':'
+    _host.write_blocks(path, headers, beg, end, blocks.loc1, blocks.loc2, pc1[blocks.pair[emit]], pc2[blocks.pair[emit]],
+                       genes1, genes2)
 
 
 def format_blocks(blocks, pair_names, genes1, genes2, pvalue, over_gap):
