@@ -260,14 +260,14 @@ def main():
     dev_ms = {}
 
     def step_resident():
-        blocks = eng.run_resident(prm, min_members=5)       # what the file writer keeps (run_colliearity.py:178)
+        blocks = eng.run_resident(prm, min_members=5, copy=False)       # what the file writer keeps (run_colliearity.py:178)
         for k, v in eng.timings().items():
             dev_ms.setdefault(k, []).append(v)
         dev_ms.setdefault("host_rank", []).append(eng.host_ms["rank"])
         return blocks
 
     def step_e2e():
-        return eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm, min_members=5)
+        return eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm, min_members=5, copy=False)
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     eng.upload(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"])

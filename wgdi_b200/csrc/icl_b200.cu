@@ -1786,13 +1786,18 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
             o.L2[g] = b_l2max[b] - b_l2min[b] + 1;
             o.p_raw[g] = b_a[b];
             o.member_off[g] = omoff[g];
-            uint32_t src = b_moff[b], dst = omoff[g];
-            for (int32_t k = 0; k < b_m[b]; k++) {
-                int32_t i = members[src + k];
-                o.loc1[dst + k] = l1[i];
-                o.loc2[dst + k] = l2[i];
-                o.member_idx[dst + k] = (int32_t)perm[i];
+        }));
+        // members: one thread per gene pair of the output (binary search for its block)
+        ICL_CUDA(st, foreach(s, NMo, ICL_LAMBDA(int64_t t) {
+            int64_t lo = 0, hi = NBo - 1;                       // last block with omoff[g] <= t
+            while (lo < hi) {
+                int64_t mid = lo + ((hi - lo + 1) >> 1);
+                if ((int64_t)omoff[mid] <= t) lo = mid; else hi = mid - 1;
             }
+            const int32_t i = members[b_moff[o_src[lo]] + (uint32_t)(t - omoff[lo])];
+            o.loc1[t] = l1[i];
+            o.loc2[t] = l2[i];
+            o.member_idx[t] = (int32_t)perm[i];
         }));
         if (NBo == 0) ICL_CUDA(st, dev_memset(dv.member_off, 0, sizeof(int64_t), s));
     }

@@ -240,17 +240,20 @@ class IclEngine:
             out[a:b] = (b - a - 1) - order[a:b][::-1]
         return out
 
-    def extract(self, argsort_fwd, argsort_rev, min_members: int = 1) -> Blocks:
+    def extract(self, argsort_fwd, argsort_rev, min_members: int = 1, copy: bool = True) -> Blocks:
+        """copy=False returns views of the context's page-locked staging: valid until the next `extract` on this
+        engine (what the file writer and the benchmark use); copy=True detaches the arrays."""
         out = icl_blocks()
         af = np.ascontiguousarray(argsort_fwd, np.int32)
         ar = np.ascontiguousarray(argsort_rev, np.int32)
         self._check(self.lib.icl_extract(self.ctx, af.ctypes.data, ar.ctypes.data, int(min_members), C.byref(out)))
         nb, nm = out.n_blocks, out.n_members
 
-        def arr(ptr, n, dt):          # the staging is reused by the next call: copy out
+        def arr(ptr, n, dt):          # the staging is reused by the next call
             if n == 0:
                 return np.zeros(0, dt)
-            return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+            a = np.ctypeslib.as_array(ptr, shape=(n,))
+            return a.copy() if copy else a
         res = Blocks(arr(out.pair, nb, np.int32), arr(out.dir, nb, np.int32), arr(out.score, nb, np.int64),
                      arr(out.m, nb, np.int32), arr(out.L, nb, np.int32), arr(out.N, nb, np.int32),
                      arr(out.N1, nb, np.int64), arr(out.L1, nb, np.int32), arr(out.L2, nb, np.int32),
@@ -279,18 +282,19 @@ class IclEngine:
                     max_span=int(c[4]), chain_kernel={0: "generic", 1: "ring", 2: "wave"}[int(c[5])])
 
     # ---- whole hot path ------------------------------------------------------------------------
-    def run_resident(self, params: ChainParams, min_members: int = 1) -> Blocks:
+    def run_resident(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
         """Hot path on points already uploaded: sort + DP -> host rank -> extraction + p values."""
         t0 = time.perf_counter()
         kf, kr = self.dp(params)
         t1 = time.perf_counter()
         af, ar = self.rank(kf, kr)
         t2 = time.perf_counter()
-        blocks = self.extract(af, ar, min_members)
+        blocks = self.extract(af, ar, min_members, copy)
         t3 = time.perf_counter()
         self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3, extract=(t3 - t2) * 1e3)
         return blocks
 
-    def chain(self, pair_id, loc1, loc2, grading, n_pairs, params: ChainParams, min_members: int = 1) -> Blocks:
+    def chain(self, pair_id, loc1, loc2, grading, n_pairs, params: ChainParams, min_members: int = 1,
+              copy: bool = True) -> Blocks:
         self.upload(pair_id, loc1, loc2, grading, n_pairs)
-        return self.run_resident(params, min_members)
+        return self.run_resident(params, min_members, copy)

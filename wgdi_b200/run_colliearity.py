@@ -93,7 +93,7 @@ class mycollinearity():
             for c1, c2 in pts['pair_names']:
                 print(f'Running {c1} vs {c2}')            # :162
             blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params,
-                               min_members=self.over_gap)
+                               min_members=self.over_gap, copy=True)
             self.timing['device_ms'] = eng.timings()
             self.timing['host_ms'] = dict(eng.host_ms)
         finally:
