@@ -265,7 +265,7 @@ def test_wave_and_generic_kernels_agree(clouds):
     pts = synth.graded_points(synth.make_dataset("small"))
     prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
     exp = oracle_blocks(pts, prm)
-    for mode in ("wave", "generic"):
+    for mode in ("wave", "generic", "single"):
         os.environ["ICL_B200_CHAIN"] = mode
         try:
             eng = IclEngine(0)

@@ -66,7 +66,7 @@ struct icl_ctx {
     int64_t n_edges = 0;
     int32_t max_span = 0;            // largest (target position - source position) over all edges
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
-    int32_t chain_mode = 1;          // 1 = single-executor ring kernel (default), 2 = wave kernel, 0 = generic (env ICL_B200_CHAIN)
+    int32_t chain_mode = 1;          // 1 = batch ring kernel (default), 3 = single-executor ring kernel, 2 = wave kernel, 0 = generic (env ICL_B200_CHAIN)
     Buf<long long> chain_dbg;
     int32_t wave_span = 0;           // most points inside 64 + mg1 consecutive rows of an item
     Buf<int2> rowtab;                // per dense row: {first edge record, first source that has records | -1}
@@ -202,7 +202,7 @@ extern "C" int icl_create(int device, icl_ctx **out) {
 #endif
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
-    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "wave") ? 2 : 1;
+    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "wave") ? 2 : !strcmp(mode, "single") ? 3 : 1;
     *out = c;
     return ICL_OK;
 }
@@ -701,6 +701,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 // One CTA per (pair, direction) item: warp 0 lane 0 is the executor, warp 1 the helper.
 //   ring[RS]  : 16-byte slots {score, depth | used-as-source flag, pred, tree root} of the points inside the window
 //   ering     : the item's edge records, streamed by TMA in 4 KB chunks (4-deep), consumed strictly in order
+template <bool BATCH>
 __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
     extern __shared__ __align__(128) unsigned char dyn[];
     uint2 *ering = (uint2 *)dyn;                                           // ICL_EDGE_NCH * ICL_EDGE_CHUNK records
@@ -724,6 +725,130 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
     __syncthreads();
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 32) {
+        if (BATCH) {
+            // ------------------------------------------------------------ executor warp: 32 records per round
+            // Lane l replays record e + l speculatively against the ring as it stands at the start of the round.
+            // * the sweep state inside a source (gap, row_old, break — collinearity.py:81-93) is resolved with
+            //   segmented warp scans over the would-update flags (legal: SURVEY.md A.3, the break position only
+            //   depends on the records before it);
+            // * a lane is stale if an earlier lane of the round really updates the slot it read as its source or
+            //   as its target (claim table: atomicMin of the lane id per ring slot).  The round commits the
+            //   records before the first stale lane — lane 0 is never stale — and restarts at that lane, so
+            //   every record is evaluated exactly as in the reference's sequential order.
+            uint32_t *claim = (uint32_t *)(ring + A.RS);
+            const uint32_t FULLM = 0xffffffffu;
+            const int32_t mg2 = A.mg2;
+            for (uint32_t i = lane; i < (uint32_t)A.RS; i += 32) claim[i] = 0xffffffffu;
+            uint32_t loaded = a;
+            while (loaded < b && loaded <= a + (uint32_t)A.span) loaded = ctl_loaded;
+            __threadfence_block();
+            __syncwarp();
+            // state of the source that is open when a round starts (all lanes hold the same values)
+            uint32_t cur_v = a;
+            int4 sl0 = ring[a & M];
+            int32_t cSv = sl0.x, cdv = sl0.y, croot = sl0.w, cgap = mg2, cdr = 0;
+            bool cbroken = false;
+            uint32_t e = e0, ready = c0 * ICL_EDGE_CHUNK, pubchunk = c0, rounds = 0;
+            while (e < e1) {
+                __syncwarp();                                     // commits of the previous round are visible
+                const uint32_t bend = e + 32 < e1 ? e + 32 : e1;
+                if (e / ICL_EDGE_CHUNK != pubchunk) {             // chunks before the one holding e are consumed
+                    pubchunk = e / ICL_EDGE_CHUNK;
+                    __threadfence_block();
+                    if (lane == 0) ctl_echunk = pubchunk;
+                }
+                while (ready < bend) {                            // TMA bytes of the chunks this round touches
+                    const uint32_t ch = ready / ICL_EDGE_CHUNK;
+                    mbar_wait(&ebar[ch % ICL_EDGE_NCH], ((ch - c0) / ICL_EDGE_NCH) & 1u);
+                    ready = (ch + 1) * ICL_EDGE_CHUNK;
+                }
+                bool valid = e + lane < bend;
+                const uint2 rec = ering[(e + lane) & EM];
+                const uint32_t adv = valid ? rec.y >> 8 : 0u;
+                // source position of every lane: inclusive scan of the advances
+                uint32_t pre = adv;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULLM, pre, d);
+                    if (lane >= d) pre += t;
+                }
+                const uint32_t v = cur_v + pre;
+                const uint32_t firstmask = __ballot_sync(FULLM, adv != 0);
+                const uint32_t upto = (2u << lane) - 1u;          // lanes 0..lane
+                const uint32_t below = firstmask & upto;
+                const int head = below ? 31 - __clz(below) : -1;  // lane that opens my source, -1: open since before the round
+                const int seg_start = head < 0 ? 0 : head;
+                const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
+                const uint32_t k = v + (rec.x & 0xffffu);
+                // a round only reaches as far as the ring can hold behind its first source
+                const uint32_t v0 = __shfl_sync(FULLM, v, 0);
+                valid = valid && k < v0 + (uint32_t)A.RS - 64u;
+                const uint32_t kmax = __reduce_max_sync(FULLM, valid ? k : 0u);
+                if (loaded < b && loaded <= kmax) {               // the targets are not staged yet
+                    __threadfence_block();
+                    if (lane == 0) ctl_retired = v0;              // everything before the round's first source is final
+                    do { loaded = ctl_loaded; } while (loaded < b && loaded <= kmax);
+                    __threadfence_block();
+                }
+                // operands
+                int32_t Sv = cSv, dv = cdv, rootv = croot;
+                if (head >= 0) {
+                    const int4 sl = ring[v & M];
+                    Sv = sl.x; dv = sl.y; rootv = sl.w;
+                }
+                const uint32_t slot = k & M;
+                const int32_t cand = Sv + sc;
+                const bool up = valid && sc > 0 && ring[slot].x < cand;      // :87, ignoring the break for now
+                // sweep state before each record: segmented scans over the would-update flags
+                int32_t x = up ? dc : 255, y = up ? dr : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int32_t xo = __shfl_up_sync(FULLM, x, d), yo = __shfl_up_sync(FULLM, y, d);
+                    if (lane - d >= seg_start) { x = xo < x ? xo : x; y = yo > y ? yo : y; }
+                }
+                int32_t gx = __shfl_up_sync(FULLM, x, 1), gy = __shfl_up_sync(FULLM, y, 1);
+                if (lane - 1 < seg_start) { gx = 255; gy = 0; }
+                const int32_t ig = head < 0 ? cgap : mg2, idr = head < 0 ? cdr : 0;
+                const int32_t gap_b = gx < ig ? gx : ig, dr_b = gy > idr ? gy : idr;
+                const bool brk = valid && dc > gap_b && dr > dr_b;            // :83-84
+                const uint32_t brkmask = __ballot_sync(FULLM, brk);
+                const uint32_t segmask = upto & ~((1u << seg_start) - 1u);    // lanes seg_start..lane
+                const bool dead = (brkmask & segmask) != 0 || (head < 0 && cbroken);
+                const bool u = up && !dead;
+                // stale lanes: an earlier lane of the round updates a slot this lane read
+                if (u) atomicMin(&claim[slot], (uint32_t)lane);
+                __syncwarp();
+                const uint32_t c2 = claim[slot];
+                const uint32_t c1 = head >= 0 ? claim[v & M] : 0xffffffffu;
+                const bool stale = c1 < (uint32_t)lane || c2 < (uint32_t)lane;
+                __syncwarp();
+                if (u) claim[slot] = 0xffffffffu;
+                const uint32_t stop = __ballot_sync(FULLM, stale || !valid);
+                const int f = stop ? __ffs(stop) - 1 : 32;        // records committed this round (>= 1)
+                if (lane < f && u) {
+                    ring[slot] = make_int4(cand, dv + 1, (int32_t)v, rootv);
+                    ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;  // used-as-source (same value from every lane of a source)
+                }
+                // the source that is open after the last committed record
+                const int32_t gap_a = u ? (dc < gap_b ? dc : gap_b) : gap_b, dr_a = u ? dr : dr_b;
+                cgap = __shfl_sync(FULLM, gap_a, f - 1);
+                cdr = __shfl_sync(FULLM, dr_a, f - 1);
+                cbroken = __shfl_sync(FULLM, (int)dead, f - 1) != 0;
+                cur_v = __shfl_sync(FULLM, v, f - 1);
+                cSv = __shfl_sync(FULLM, Sv, f - 1);
+                cdv = __shfl_sync(FULLM, dv, f - 1);
+                croot = __shfl_sync(FULLM, rootv, f - 1);
+                e += (uint32_t)f;
+                if ((++rounds & 7u) == 0) {                       // let the helper retire finished points
+                    __threadfence_block();
+                    if (lane == 0) ctl_retired = cur_v;
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) ctl_retired = b;
+            return;
+        }
         // ---------------------------------------------------------------- executor (one thread)
         if (lane != 0) return;
         uint32_t loaded = a, v = a;
@@ -1143,17 +1268,24 @@ static int phase_chain(icl_ctx *c) {
             c->chain_kernel = 2;
             return 0;
         }
-        // ---- single-executor ring kernel: window span + what the executor may run ahead of the last retire point
-        int64_t want = (int64_t)c->max_span + 128;
-        int64_t RS = 256;
+        // ---- ring kernels: window span + what a round / the executor may run ahead of the last retire point
+        int64_t want = (int64_t)c->max_span + 256;
+        int64_t RS = 512;
         while (RS < want) RS <<= 1;
         if (RS <= 8192) {
             A.RS = (int32_t)RS;
-            size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2);
-            ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            k_chain_ring<<<(unsigned)(2 * P), 64, smem, s>>>(A);
+            const bool batch = c->chain_mode == 1;
+            size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2) +
+                          (batch ? (size_t)RS * sizeof(uint32_t) : 0);
+            if (batch) {
+                ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                k_chain_ring<true><<<(unsigned)(2 * P), 64, smem, s>>>(A);
+            } else {
+                ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                k_chain_ring<false><<<(unsigned)(2 * P), 64, smem, s>>>(A);
+            }
             ICL_CUDA(st, cudaGetLastError());
-            c->chain_kernel = 1;
+            c->chain_kernel = batch ? 1 : 3;
             return 0;
         }
     }
