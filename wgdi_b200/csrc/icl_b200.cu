@@ -76,8 +76,10 @@ struct icl_ctx {
     Buf<uint8_t> used;
     Buf<int32_t> score32;
     // extraction
-    Buf<int32_t> order_in, rankpos, rank2v, acc_L, members, times;
-    Buf<uint32_t> tree_v, acc_m, acc_flag, blkidx, moff;
+    Buf<int32_t> order_in, rank2v, acc_L, members, times, mscr;
+    Buf<uint32_t> tree_v, acc_m, acc_ms, acc_flag, blkidx, moff;
+    Buf<int4> acc_box;               // per accepted rank position: {loc1 min, loc1 max, loc2 min, loc2 max}
+    Buf<uint8_t> seen;
     Buf<uint8_t> present;
     Buf<int2> hint;                  // per point: {depth of the nearest removed ancestor, tree version} memo
     int64_t NB = 0, NM = 0;
@@ -221,7 +223,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release(); c->chain_dbg.release();
     c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
-    c->order_in.release(); c->rankpos.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
+    c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
     c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
     c->b_j1.release(); c->b_l2min.release(); c->b_l2max.release(); c->b_L1.release(); c->b_item.release();
@@ -1453,83 +1455,95 @@ static int phase_extract(icl_ctx *c) {
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->rankpos.reserve(st, V) || c->present.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) ||
-        c->idx_a.reserve(st, V) || c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) ||
-        c->acc_flag.reserve(st, V + 2) || c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->stats.reserve(st, 4))
+    if (c->present.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
+        c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) || c->acc_ms.reserve(st, V) ||
+        c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->acc_flag.reserve(st, V + 2) ||
+        c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4))
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
-    ICL_CUDA(st, dev_memset(c->rankpos.p, 0xFF, (size_t)V * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
-    if (c->hint.reserve(st, V)) return st.code;
+    ICL_CUDA(st, dev_memset(c->seen.p, 0, (size_t)V, s));
     ICL_CUDA(st, dev_memset(c->hint.p, 0xFF, (size_t)V * sizeof(int2), s));
-    const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
-    const int64_t *off = c->d_pair_off.p;
-    int32_t *rankpos = c->rankpos.p, *stats = c->stats.p;
-    // The caller's arrays are numpy.argsort of the REVERSED segment (what pandas' nargsort(ascending=False) feeds
-    // numpy); undo the two reversals: descending position (np-1-j) holds point (np-1-r[j]).
-    ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
-        int32_t p = ps[i];
-        int64_t a = off[p], np_ = off[p + 1] - a, j = i - a;
-        int32_t rf = ord[i], rr = ord[n + i];
-        if (rf < 0 || rf >= np_ || rr < 0 || rr >= np_) { atomic_or_i32(&stats[2], 1); return; }
-        int32_t pos = (int32_t)(np_ - 1 - j);
-        rankpos[a + (np_ - 1 - rf)] = pos;
-        rankpos[mmap[a + (np_ - 1 - rr)]] = pos;
-    }));
     ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));      // drop usedtimes < 1 (:50 / :61)
     const int2 *pd = c->pd.p;
-    const int32_t *itemof = c->itemof.p, *root = c->root.p;
+    const int32_t *root = c->root.p, *rank2v = c->rank2v.p;
     const uint8_t *used = c->used.p;
-    // key = (root, rank position); unused points sort behind everything
-    int maxnp = 1;
-    for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
-    const int rb = bits_for(maxnp), vb = bits_for(V);
+    int32_t *stats = c->stats.p;
+    // Rank positions are item-major and already in examination order, so a STABLE sort by tree root alone
+    // groups every predecessor tree with its points in rank order.  Unused points sort behind everything.
+    const int vb = bits_for(V);
     {
         uint64_t *key = c->key_a.p;
         uint32_t *idx = c->idx_a.p;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
-            idx[v] = (uint32_t)v;
-            if (!used[v]) { key[v] = (uint64_t)V << rb; return; }
-            int32_t rp = rankpos[v];
-            if (rp < 0) { atomic_or_i32(&stats[2], 1); key[v] = (uint64_t)V << rb; return; }   // not a permutation
-            key[v] = ((uint64_t)(uint32_t)root[v] << rb) | (uint32_t)rp;   // root of the predecessor tree (from the DP)
+        uint8_t *seen = c->seen.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+            idx[t] = (uint32_t)t;
+            const int32_t v = rank2v[t];
+            if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = (uint64_t)V; return; }   // not a permutation
+            seen[v] = 1;
+            key[t] = used[v] ? (uint64_t)(uint32_t)root[v] : (uint64_t)V;
         }));
+        // a duplicate may slip through the unsynchronised test above, but then some point is never seen
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (!seen[v]) atomic_or_i32(&stats[2], 1); }));
     }
-    if (V > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, rb + vb, s)) return st.code;
+    if (V > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, vb, s)) return st.code;
     {
         const uint64_t *key = c->key_b.p;
-        const uint32_t *tv = c->tree_v.p;
+        const uint32_t *tpos = c->tree_v.p;            // rank position of every sorted entry
+        const int32_t *imap = c->imap.p, *l1 = c->loc1s.p, *l2 = c->loc2s.p;
         uint8_t *present = c->present.p;
-        uint32_t *acc_m = c->acc_m.p;
-        int32_t *acc_L = c->acc_L.p;
+        uint32_t *acc_m = c->acc_m.p, *acc_ms = c->acc_ms.p;
+        int32_t *acc_L = c->acc_L.p, *mscr = c->mscr.p;
+        int4 *acc_box = c->acc_box.p;
         int2 *hint = c->hint.p;
         const int32_t over_gap = c->prm.over_gap;
         const double cov = c->prm.coverage_ratio;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
-            uint64_t root = key[t] >> rb;
-            if (root >= (uint64_t)V) return;                                    // unused tail
-            if (t > 0 && (key[t - 1] >> rb) == root) return;                    // not the head of its tree
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t0) {
+            const uint64_t rt = key[t0];
+            if (rt >= (uint64_t)V) return;                                      // unused tail
+            if (t0 > 0 && key[t0 - 1] == rt) return;                            // not the head of its tree
             int32_t ver = 0;                                                    // accepted blocks of this tree so far
-            for (int64_t u = t; u < V && (key[u] >> rb) == root; u++) {         // the tree's points in rank order
-                int32_t top = (int32_t)tv[u];
+            uint32_t cursor = (uint32_t)t0;                                     // member scratch: the tree's own slice
+            for (int64_t u = t0; u < V && key[u] == rt; u++) {                  // the tree's points in rank order
+                const uint32_t t = tpos[u];
+                const int32_t top = rank2v[t];
                 if (!present[top]) continue;
-                const int2 nd = pd[top];
-                const int2 h = hint[top];
-                int32_t L = nd.y, m, q;
-                if (h.y == ver) {
-                    m = L - h.x;                                                // boundary known from a rejected child
+                const int2 nd = ICL_LDG(pd + top);
+                const int32_t L = nd.y;
+                int32_t m, q;
+                if (ver == 0) {
+                    m = L;                                                      // nothing of this tree removed yet
                 } else {
-                    m = 1; q = nd.x;
-                    while (q >= 0 && present[q]) { m++; q = pd[q].x; }          // present part of the path
+                    const int2 h = hint[top];
+                    if (h.y == ver) m = L - h.x;                                // boundary known from a rejected child
+                    else {
+                        m = 1; q = nd.x;
+                        while (q >= 0 && present[q]) { m++; q = ICL_LDG(pd + q).x; }     // present part of the path
+                    }
                 }
                 if (L >= over_gap && (double)m / (double)L > cov) {             // :129
+                    // remove the members (:130), list them, bounding box (:131)
+                    const bool rev = top >= n;
+                    int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
                     q = top;
-                    for (int32_t k = 0; k < m; k++) { present[q] = 0; q = pd[q].x; }     // :130
+                    for (int32_t k = 0; k < m; k++) {
+                        present[q] = 0;
+                        const int32_t i = rev ? imap[q - n] : q;                // forward sorted position
+                        mscr[cursor + k] = i;
+                        const int32_t yv = l2[i];
+                        l2min = yv < l2min ? yv : l2min;
+                        l2max = yv > l2max ? yv : l2max;
+                        if (k == 0) ifirst = i;
+                        ilast = i;
+                        q = ICL_LDG(pd + q).x;
+                    }
                     ver++;                                                      // removed ancestors changed: memos expire
-                    int32_t it = itemof[top];
-                    int64_t pos = (it >= P ? n : 0) + off[it >= P ? it - P : it] + (int64_t)(key[u] & ((1ull << rb) - 1));
-                    acc_m[pos] = (uint32_t)m;
-                    acc_L[pos] = L;
+                    const int32_t la = l1[ifirst], lb = l1[ilast];
+                    acc_m[t] = (uint32_t)m;
+                    acc_L[t] = L;
+                    acc_ms[t] = cursor;
+                    acc_box[t] = make_int4(la < lb ? la : lb, la < lb ? lb : la, l2min, l2max);
+                    cursor += (uint32_t)m;
                 } else {
                     present[top] = 0;                                           // :143
                     // the parent sees the same removed ancestor until the next accepted block of this tree;
@@ -1562,43 +1576,36 @@ static int phase_extract(icl_ctx *c) {
         c->b_l2max.reserve(st, NB) || c->b_L1.reserve(st, NB) || c->b_item.reserve(st, NB))
         return st.code;
     {
-        // one thread per accepted block: members by loc1 ascending (:140), bounding box (:131), row slice of the box
-        const uint32_t *acc_m = c->acc_m.p, *blkidx = c->blkidx.p, *moff = c->moff.p;
-        const int32_t *acc_L = c->acc_L.p, *imap = c->imap.p, *l1 = c->loc1s.p, *l2 = c->loc2s.p, *rowptr = c->rowptr.p;
+        // one thread per accepted block: members by loc1 ascending (:140), row slice of the bounding box
+        const uint32_t *acc_m = c->acc_m.p, *blkidx = c->blkidx.p, *moff = c->moff.p, *acc_ms = c->acc_ms.p;
+        const int32_t *acc_L = c->acc_L.p, *rowptr = c->rowptr.p, *mscr = c->mscr.p;
+        const int4 *acc_box = c->acc_box.p;
         const int32_t *rmin = c->d_rmin.p;
         const int64_t *rb_ = c->d_rb.p;
         const int32_t *itemof_pos = c->itemof.p;       // item of a V position == item of the point stored there
-        const int32_t *rank2v = c->rank2v.p;
         int32_t *members = c->members.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_j0 = c->b_j0.p;
         int32_t *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_L1 = c->b_L1.p, *b_item = c->b_item.p;
         uint32_t *b_moff = c->b_moff.p;
         ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
-            uint32_t m = acc_m[t];
+            const uint32_t m = acc_m[t];
             if (!m) return;
-            uint32_t b = blkidx[t], mo = moff[t];
-            int32_t it = itemof_pos[t];
-            int32_t p = it >= P ? it - P : it;
-            int32_t top = rank2v[t];
-            int32_t q = top, l2min = 0x7fffffff, l2max = -1;
-            for (uint32_t k = 0; k < m; k++) {
-                int32_t i = it >= P ? imap[q - n] : q;                           // forward sorted position
-                members[mo + (it >= P ? k : m - 1 - k)] = i;
-                int32_t y = l2[i];
-                l2min = y < l2min ? y : l2min;
-                l2max = y > l2max ? y : l2max;
-                q = pd[q].x;
-            }
-            int32_t l1min = l1[members[mo]], l1max = l1[members[mo + m - 1]];
-            b_top[b] = top;
+            const uint32_t b = blkidx[t], mo = moff[t], ms = acc_ms[t];
+            const int32_t it = itemof_pos[t];
+            const int32_t p = it >= P ? it - P : it;
+            // the walk went from the top towards the root: loc1 descending forward, ascending on the anti-diagonal
+            if (it >= P) for (uint32_t k = 0; k < m; k++) members[mo + k] = mscr[ms + k];
+            else for (uint32_t k = 0; k < m; k++) members[mo + k] = mscr[ms + m - 1 - k];
+            const int4 box = acc_box[t];
+            b_top[b] = rank2v[t];
             b_m[b] = (int32_t)m;
             b_L[b] = acc_L[t];
             b_moff[b] = mo;
             b_item[b] = it;
-            b_l2min[b] = l2min;
-            b_l2max[b] = l2max;
-            b_L1[b] = l1max - l1min + 1;
-            b_j0[b] = rowptr[rb_[p] + (l1min - rmin[p])];
-            b_j1[b] = rowptr[rb_[p] + (l1max - rmin[p]) + 1];
+            b_l2min[b] = box.z;
+            b_l2max[b] = box.w;
+            b_L1[b] = box.y - box.x + 1;
+            b_j0[b] = rowptr[rb_[p] + (box.x - rmin[p])];
+            b_j1[b] = rowptr[rb_[p] + (box.y - rmin[p]) + 1];
         }));
     }
     return 0;
@@ -1811,11 +1818,12 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
         const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
         const int64_t *off = c->d_pair_off.p;
         int32_t *rank2v = c->rank2v.p;
+        ICL_CUDA(st, dev_memset(c->rank2v.p, 0xFF, (size_t)V * sizeof(int32_t), s));
         ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
             int32_t p = ps[i];
             int64_t a = off[p], np_ = off[p + 1] - a, j = i - a;
             int32_t rf = ord[i], rr = ord[n + i];
-            if (rf < 0 || rf >= np_ || rr < 0 || rr >= np_) return;               // reported by phase_extract
+            if (rf < 0 || rf >= np_ || rr < 0 || rr >= np_) return;               // stays -1: reported by phase_extract
             rank2v[a + (np_ - 1 - j)] = (int32_t)(a + (np_ - 1 - rf));
             rank2v[n + a + (np_ - 1 - j)] = mmap[a + (np_ - 1 - rr)];
         }));

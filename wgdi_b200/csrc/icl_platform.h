@@ -15,6 +15,11 @@
 #include <cub/cub.cuh>
 #define ICL_HD __host__ __device__ __forceinline__
 #define ICL_D __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+#define ICL_LDG(p) __ldg(p)          // read-only data through L1
+#else
+#define ICL_LDG(p) (*(p))
+#endif
 #else
 #include <algorithm>
 #include <chrono>
@@ -22,6 +27,7 @@
 #include <vector>
 #define ICL_HD inline
 #define ICL_D inline
+#define ICL_LDG(p) (*(p))
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 #define cudaSuccess 0
@@ -29,6 +35,8 @@ struct uint2 { uint32_t x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
 struct int2 { int32_t x, y; };
 static inline int2 make_int2(int32_t x, int32_t y) { int2 r = {x, y}; return r; }
+struct int4 { int32_t x, y, z, w; };
+static inline int4 make_int4(int32_t x, int32_t y, int32_t z, int32_t w) { int4 r = {x, y, z, w}; return r; }
 #endif
 
 namespace icl {
