@@ -68,6 +68,9 @@ struct icl_ctx {
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
     int32_t chain_mode = 1;          // 1 = batch ring kernel (default), 3 = single-executor ring kernel, 2 = wave kernel, 0 = generic (env ICL_B200_CHAIN)
     Buf<long long> chain_dbg;
+    int32_t pvalue_mode = 0;         // 0 = incidence sort (default), 1 = sequential warp-per-pair kernel (env ICL_B200_PVALUE=seq)
+    Buf<uint32_t> inc_cnt, inc_off;
+    Buf<int32_t> inc_start;
     int32_t wave_span = 0;           // most points inside 64 + mg1 consecutive rows of an item
     Buf<int2> rowtab;                // per dense row: {first edge record, first source that has records | -1}
     // DP state (V space)
@@ -204,6 +207,8 @@ extern "C" int icl_create(int device, icl_ctx **out) {
 #endif
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
+    const char *pvm = getenv("ICL_B200_PVALUE");
+    if (pvm && !strcmp(pvm, "seq")) c->pvalue_mode = 1;
     if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "wave") ? 2 : !strcmp(mode, "single") ? 3 : 1;
     *out = c;
     return ICL_OK;
@@ -221,7 +226,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
-    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release(); c->chain_dbg.release();
+    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
     c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
@@ -1722,6 +1727,75 @@ __global__ void __launch_bounds__(32) k_pvalue(PvalArgs A, int32_t l2_cap) {
 }
 #endif
 
+// Order-free form of the `times` accounting: times[q] before block b = 1 + number of blocks accepted earlier in
+// the same pair whose box contains q, so  N1(b) = N(b) + sum over the points q of box(b) of rank_q(b),  where
+// rank_q(b) counts the earlier blocks containing q.  Enumerate the (point, block) incidences of all boxes in
+// parallel, radix-sort them by (point, block index) — block indices grow in acceptance order inside a pair,
+// forward blocks before anti-diagonal ones — and the rank is the position inside the point's run.
+// Returns handled = false when the incidence list would be unreasonably large (then the sequential kernel runs).
+static int phase_pvalue_incidence(icl_ctx *c, bool *handled) {
+    Status &st = c->st;
+    const int64_t NB = c->NB;
+    cudaStream_t s = c->stream;
+    *handled = false;
+    if (NB == 0) { *handled = true; return 0; }
+    if (c->inc_cnt.reserve(st, NB + 2) || c->inc_off.reserve(st, NB + 2)) return st.code;
+    const int32_t *l2 = c->loc2s.p, *b_j0 = c->b_j0.p, *b_j1 = c->b_j1.p, *b_lo = c->b_l2min.p, *b_hi = c->b_l2max.p;
+    int32_t *b_N = c->b_N.p;
+    int64_t *b_N1 = c->b_N1.p;
+    {
+        uint32_t *cnt = c->inc_cnt.p;
+        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
+            const int32_t lo = b_lo[b], hi = b_hi[b];
+            int32_t N = 0;
+            for (int32_t q = b_j0[b]; q < b_j1[b]; q++) {                  // :134-137 inclusive box over the row slice
+                const int32_t y = l2[q];
+                N += (y >= lo && y <= hi);
+            }
+            b_N[b] = N;                                                     // :149
+            cnt[b] = (uint32_t)N;
+            b_N1[b] = N;                                                    // every point of the box counts once (times = 1)
+        }));
+    }
+    if (exclusive_sum_u32(st, c->tmp, c->inc_cnt.p, c->inc_off.p, NB, s)) return st.code;
+    uint32_t total = 0;
+    ICL_CUDA(st, d2h(&total, c->inc_off.p + NB, sizeof(uint32_t), s));
+    ICL_CUDA(st, dev_sync(s));
+    const int64_t I = total;
+    if (I > (1ll << 28)) return 0;                                          // pathological nesting: sequential kernel instead
+    *handled = true;
+    if (I == 0) return 0;
+    if (c->key_a.reserve(st, I) || c->key_b.reserve(st, I) || c->inc_start.reserve(st, I + 2)) return st.code;
+    const int sb = bits_for(NB);
+    {
+        const uint32_t *ioff = c->inc_off.p;
+        uint64_t *key = c->key_a.p;
+        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
+            const int32_t lo = b_lo[b], hi = b_hi[b];
+            uint32_t e = ioff[b];
+            for (int32_t q = b_j0[b]; q < b_j1[b]; q++) {
+                const int32_t y = l2[q];
+                if (y >= lo && y <= hi) key[e++] = ((uint64_t)(uint32_t)q << sb) | (uint64_t)b;
+            }
+        }));
+    }
+    if (radix_sort_keys(st, c->tmp, c->key_a.p, c->key_b.p, I, sb + bits_for(c->n), s)) return st.code;
+    {
+        const uint64_t *key = c->key_b.p;
+        int32_t *start = c->inc_start.p;
+        ICL_CUDA(st, foreach(s, I, ICL_LAMBDA(int64_t j) {
+            start[j] = (j == 0 || (key[j] >> sb) != (key[j - 1] >> sb)) ? (int32_t)j : 0;
+        }));
+        if (inclusive_max_i32(st, c->tmp, c->inc_start.p, I, s)) return st.code;  // first incidence of the point's run
+        const uint64_t bmask = (1ull << sb) - 1;
+        ICL_CUDA(st, foreach(s, I, ICL_LAMBDA(int64_t j) {
+            const int64_t rank = j - start[j];                              // earlier blocks of the pair containing the point
+            if (rank) atomic_add_i64(&b_N1[key[j] & bmask], rank);          // :148 with :150 of the earlier blocks
+        }));
+    }
+    return 0;
+}
+
 static int phase_pvalue(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n, NB = c->NB;
@@ -1734,6 +1808,9 @@ static int phase_pvalue(icl_ctx *c) {
     A.b_j0 = c->b_j0.p; A.b_j1 = c->b_j1.p; A.b_l2min = c->b_l2min.p; A.b_l2max = c->b_l2max.p; A.b_L1 = c->b_L1.p;
     A.off = c->d_pair_off.p; A.blkidx = c->blkidx.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p; A.b_a = c->b_a.p;
     if (P == 0) return 0;
+    bool handled = false;
+    if (c->pvalue_mode != 1 && phase_pvalue_incidence(c, &handled)) return st.code;
+    if (!handled) {
 #ifndef ICL_EMU
     int64_t maxnp = 1;
     for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
@@ -1763,6 +1840,7 @@ static int phase_pvalue(icl_ctx *c) {
         }
     }
 #endif
+    }
     {
         // p value of every accepted block, one thread each (collinearity.py:152 in binary64, left to right)
         const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;

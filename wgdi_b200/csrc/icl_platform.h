@@ -145,6 +145,13 @@ ICL_HD void atomic_max_i32(int32_t *p, int32_t v) {
     if (v > *p) *p = v;
 #endif
 }
+ICL_HD void atomic_add_i64(int64_t *p, int64_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd((unsigned long long *)p, (unsigned long long)v);
+#else
+    *p += v;
+#endif
+}
 ICL_HD void atomic_or_i32(int32_t *p, int32_t v) {
 #if defined(__CUDA_ARCH__)
     atomicOr(p, v);
@@ -163,6 +170,15 @@ inline int radix_sort_pairs(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, 
     ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
     if (tmp.reserve(st, bytes)) return st.code;
     ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+    return 0;
+}
+inline int radix_sort_keys(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, uint64_t *kout, int64_t n, int end_bit,
+                           cudaStream_t s) {
+    size_t bytes = 0;
+    if (end_bit > 64) end_bit = 64;
+    ICL_CUDA(st, cub::DeviceRadixSort::SortKeys(nullptr, bytes, kin, kout, (int)n, 0, end_bit, s));
+    if (tmp.reserve(st, bytes)) return st.code;
+    ICL_CUDA(st, cub::DeviceRadixSort::SortKeys(tmp.p, bytes, kin, kout, (int)n, 0, end_bit, s));
     return 0;
 }
 // out[0..n] = exclusive prefix sum of in[0..n) with the total in out[n]; `in` must have n+1 slots
@@ -213,6 +229,13 @@ inline int radix_sort_pairs(Status &, Buf<uint8_t> &, const uint64_t *kin, uint6
     uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
     std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
     for (int64_t i = 0; i < n; i++) { kout[i] = kin[o[i]]; vout[i] = vin[o[i]]; }
+    return 0;
+}
+inline int radix_sort_keys(Status &, Buf<uint8_t> &, const uint64_t *kin, uint64_t *kout, int64_t n, int end_bit, cudaStream_t) {
+    uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
+    std::vector<uint64_t> o(kin, kin + n);
+    std::stable_sort(o.begin(), o.end(), [&](uint64_t a, uint64_t b) { return (a & mask) < (b & mask); });
+    for (int64_t i = 0; i < n; i++) kout[i] = o[i];
     return 0;
 }
 inline int exclusive_sum_u32(Status &, Buf<uint8_t> &, uint32_t *in, uint32_t *out, int64_t n, cudaStream_t) {
