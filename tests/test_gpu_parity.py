@@ -277,6 +277,23 @@ def test_wave_and_generic_kernels_agree(clouds):
         _compare_with_oracle(blocks, exp)
 
 
+@pytest.mark.parametrize("mode", ["seq", "inc"])
+def test_both_pvalue_paths_agree_with_oracle(mode):
+    """The sequential warp-per-pair `times` kernel and the order-free incidence path, both forced on one input."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    os.environ["ICL_B200_PVALUE"] = mode
+    try:
+        eng = IclEngine(0)
+        blocks = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+        eng.close()
+    finally:
+        del os.environ["ICL_B200_PVALUE"]
+    _compare_with_oracle(blocks, oracle_blocks(pts, prm))
+
+
 def test_full_size_C2_matches_oracle_and_properties(gpu_engine):
     """BASELINE.json config 2 (Vitis-sized self comparison, ~2M graded hits) at full size: identical to the C oracle,
     plus size-independent properties."""

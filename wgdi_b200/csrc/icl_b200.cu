@@ -68,7 +68,7 @@ struct icl_ctx {
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
     int32_t chain_mode = 1;          // 1 = batch ring kernel (default), 3 = single-executor ring kernel, 2 = wave kernel, 0 = generic (env ICL_B200_CHAIN)
     Buf<long long> chain_dbg;
-    int32_t pvalue_mode = 0;         // 0 = incidence sort (default), 1 = sequential warp-per-pair kernel (env ICL_B200_PVALUE=seq)
+    int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
     int32_t wave_span = 0;           // most points inside 64 + mg1 consecutive rows of an item
@@ -208,7 +208,7 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
     const char *pvm = getenv("ICL_B200_PVALUE");
-    if (pvm && !strcmp(pvm, "seq")) c->pvalue_mode = 1;
+    if (pvm) c->pvalue_mode = !strcmp(pvm, "seq") ? 1 : !strcmp(pvm, "inc") ? 2 : 0;
     if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "wave") ? 2 : !strcmp(mode, "single") ? 3 : 1;
     *out = c;
     return ICL_OK;
@@ -1808,8 +1808,13 @@ static int phase_pvalue(icl_ctx *c) {
     A.b_j0 = c->b_j0.p; A.b_j1 = c->b_j1.p; A.b_l2min = c->b_l2min.p; A.b_l2max = c->b_l2max.p; A.b_L1 = c->b_L1.p;
     A.off = c->d_pair_off.p; A.blkidx = c->blkidx.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p; A.b_a = c->b_a.p;
     if (P == 0) return 0;
+    // Small pairs (times and loc2 of the pair fit in shared memory, few blocks per pair) are fastest on the
+    // sequential warp-per-pair kernel; large pairs serialise there and take the order-free incidence path.
+    int64_t maxnp_all = 1;
+    for (int32_t p = 0; p < P; p++) maxnp_all = std::max<int64_t>(maxnp_all, c->h_pair_off[p + 1] - c->h_pair_off[p]);
+    const bool prefer_seq = c->pvalue_mode == 1 || (c->pvalue_mode == 0 && maxnp_all <= 12 * 1024);
     bool handled = false;
-    if (c->pvalue_mode != 1 && phase_pvalue_incidence(c, &handled)) return st.code;
+    if (!prefer_seq && phase_pvalue_incidence(c, &handled)) return st.code;
     if (!handled) {
 #ifndef ICL_EMU
     int64_t maxnp = 1;
