@@ -121,8 +121,11 @@ def test_pipeline_on_golden_clouds_emu(emu_backend, clouds):
         eng.close()
 
 
-def test_multi_pair_batch_matches_c_oracle_emu(emu_backend):
-    """All chromosome pairs of a synthetic comparison in one upload vs the C oracle pair by pair."""
+@pytest.mark.parametrize("pvalue_path", ["seq", "inc"])
+def test_multi_pair_batch_matches_c_oracle_emu(emu_backend, pvalue_path, monkeypatch):
+    """All chromosome pairs of a synthetic comparison in one upload vs the C oracle pair by pair, with both
+    `times` accounting paths (sequential per pair / order-free incidence sort)."""
+    monkeypatch.setenv("ICL_B200_PVALUE", pvalue_path)
     from wgdi_b200 import synth
     from wgdi_b200.engine import ChainParams, IclEngine
     from conftest import oracle_blocks
