@@ -329,9 +329,13 @@ def main():
                     "h2d_bytes_per_step": 16 * n_local + 8 * n_local, "d2h_bytes_per_step": d2h},
             "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
             "roofline": {"kernel": "chain DP (both directions)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": 70.6e6 if (args.workload == "C2" and world == 1) else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_chain_ring on this "
+                                           "workload (profiles/r01_chain_batch_ncu_summary.md)",
+                         "peak_source": peak_kind,
                          "kernel_ms": chain_ms, "algorithmic_bytes": DP_BYTES_PER_POINT * n_local,
-                         "note": "latency-bound integer DP with a serial dependency chain; see DESIGN.md"},
+                         "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
             "phase_ms": {k: float(np.mean(v)) for k, v in dev_ms.items()},
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
