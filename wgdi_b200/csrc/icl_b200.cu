@@ -806,15 +806,17 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 const uint32_t slot = k & M;
                 const int32_t cand = Sv + sc;
                 const bool up = valid && sc > 0 && ring[slot].x < cand;      // :87, ignoring the break for now
-                // sweep state before each record: segmented scans over the would-update flags
-                int32_t x = up ? dc : 255, y = up ? dr : 0;
+                // sweep state before each record: ONE segmented scan over the would-update flags, min(dc) and
+                // max(dr) packed as two 16-bit halves {255 - dc, dr} combined with a per-halfword max
+                uint32_t pk = up ? (((uint32_t)(255 - dc) << 16) | (uint32_t)dr) : 0u;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const int32_t xo = __shfl_up_sync(FULLM, x, d), yo = __shfl_up_sync(FULLM, y, d);
-                    if (lane - d >= seg_start) { x = xo < x ? xo : x; y = yo > y ? yo : y; }
+                    const uint32_t po = __shfl_up_sync(FULLM, pk, d);
+                    if (lane - d >= seg_start) pk = __vmaxu2(pk, po);
                 }
-                int32_t gx = __shfl_up_sync(FULLM, x, 1), gy = __shfl_up_sync(FULLM, y, 1);
-                if (lane - 1 < seg_start) { gx = 255; gy = 0; }
+                uint32_t pe = __shfl_up_sync(FULLM, pk, 1);
+                if (lane - 1 < seg_start) pe = 0u;
+                const int32_t gx = 255 - (int32_t)(pe >> 16), gy = (int32_t)(pe & 0xffffu);
                 const int32_t ig = head < 0 ? cgap : mg2, idr = head < 0 ? cdr : 0;
                 const int32_t gap_b = gx < ig ? gx : ig, dr_b = gy > idr ? gy : idr;
                 const bool brk = valid && dc > gap_b && dr > dr_b;            // :83-84
@@ -838,9 +840,10 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 }
                 // the source that is open after the last committed record
                 const int32_t gap_a = u ? (dc < gap_b ? dc : gap_b) : gap_b, dr_a = u ? dr : dr_b;
-                cgap = __shfl_sync(FULLM, gap_a, f - 1);
-                cdr = __shfl_sync(FULLM, dr_a, f - 1);
-                cbroken = __shfl_sync(FULLM, (int)dead, f - 1) != 0;
+                const uint32_t st = __shfl_sync(FULLM, (uint32_t)gap_a | ((uint32_t)dr_a << 8) | ((uint32_t)dead << 16), f - 1);
+                cgap = (int32_t)(st & 255u);
+                cdr = (int32_t)((st >> 8) & 255u);
+                cbroken = (st >> 16) != 0;
                 cur_v = __shfl_sync(FULLM, v, f - 1);
                 cSv = __shfl_sync(FULLM, Sv, f - 1);
                 cdv = __shfl_sync(FULLM, dv, f - 1);
