@@ -756,6 +756,8 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
             int32_t cSv = sl0.x, cdv = sl0.y, croot = sl0.w, cgap = mg2, cdr = 0;
             bool cbroken = false;
             uint32_t e = e0, ready = c0 * ICL_EDGE_CHUNK, pubchunk = c0, rounds = 0;
+            const long long t_begin = A.dbg ? clock64() : 0;
+            long long t_wait = 0;
             while (e < e1) {
                 __syncwarp();                                     // commits of the previous round are visible
                 const uint32_t bend = e + 32 < e1 ? e + 32 : e1;
@@ -766,7 +768,9 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 }
                 while (ready < bend) {                            // TMA bytes of the chunks this round touches
                     const uint32_t ch = ready / ICL_EDGE_CHUNK;
+                    const long long tw = A.dbg ? clock64() : 0;
                     mbar_wait(&ebar[ch % ICL_EDGE_NCH], ((ch - c0) / ICL_EDGE_NCH) & 1u);
+                    if (A.dbg) t_wait += clock64() - tw;
                     ready = (ch + 1) * ICL_EDGE_CHUNK;
                 }
                 bool valid = e + lane < bend;
@@ -794,7 +798,9 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 if (loaded < b && loaded <= kmax) {               // the targets are not staged yet
                     __threadfence_block();
                     if (lane == 0) ctl_retired = v0;              // everything before the round's first source is final
+                    const long long tw = A.dbg ? clock64() : 0;
                     do { loaded = ctl_loaded; } while (loaded < b && loaded <= kmax);
+                    if (A.dbg) t_wait += clock64() - tw;
                     __threadfence_block();
                 }
                 // operands
@@ -856,6 +862,10 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
             }
             __syncwarp();
             __threadfence_block();
+            if (lane == 0 && A.dbg) {
+                A.dbg[4 * blockIdx.x] = rounds; A.dbg[4 * blockIdx.x + 1] = clock64() - t_begin;
+                A.dbg[4 * blockIdx.x + 2] = t_wait; A.dbg[4 * blockIdx.x + 3] = e1 - e0;
+            }
             if (lane == 0) ctl_retired = b;
             return;
         }
@@ -1154,7 +1164,7 @@ __global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
         }
         __syncwarp();
         __threadfence_block();
-        if (lane == 0 && A.dbg) { A.dbg[2 * blockIdx.x] = round; A.dbg[2 * blockIdx.x + 1] = clock64() - t_start; }
+        if (lane == 0 && A.dbg) { A.dbg[4 * blockIdx.x] = round; A.dbg[4 * blockIdx.x + 1] = clock64() - t_start; }
         if (lane == 0) { ctl_retired = b; ctl_emin = e1; ctl_xmin = nrows; }
         return;
     }
@@ -1255,8 +1265,8 @@ static int phase_chain(icl_ctx *c) {
     A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p; A.root = c->root.p;
     A.dbg = nullptr;
     if (getenv("ICL_B200_CHAIN_DEBUG")) {
-        if (c->chain_dbg.reserve(st, 4 * (size_t)P + 4)) return st.code;
-        ICL_CUDA(st, dev_memset(c->chain_dbg.p, 0, (4 * (size_t)P + 4) * sizeof(long long), s));
+        if (c->chain_dbg.reserve(st, 8 * (size_t)P + 8)) return st.code;
+        ICL_CUDA(st, dev_memset(c->chain_dbg.p, 0, (8 * (size_t)P + 8) * sizeof(long long), s));
         A.dbg = c->chain_dbg.p;
     }
     if (P == 0 || n == 0) return 0;
@@ -1365,14 +1375,14 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
     c->timers[ICL_T_EXPORT].stop(s);
     ICL_CUDA(st, dev_sync(s));
     if (getenv("ICL_B200_CHAIN_DEBUG") && c->chain_dbg.p && c->P > 0) {
-        std::vector<long long> h(4 * (size_t)c->P);
+        std::vector<long long> h(8 * (size_t)c->P);
         ICL_CUDA(st, d2h(h.data(), c->chain_dbg.p, h.size() * sizeof(long long), s));
         ICL_CUDA(st, dev_sync(s));
         FILE *f = fopen(getenv("ICL_B200_CHAIN_DEBUG"), "w");
         if (f) {
             for (int32_t j = 0; j < 2 * c->P; j++) {
                 int32_t it = c->h_item_order[j], p = it >= c->P ? it - c->P : it;
-                fprintf(f, "%d %d %lld %d %lld %lld\n", j, it, (long long)(c->h_pair_off[p + 1] - c->h_pair_off[p]), c->h_nrows[p], h[2 * j], h[2 * j + 1]);
+                fprintf(f, "%d %d %lld %d %lld %lld %lld %lld\n", j, it, (long long)(c->h_pair_off[p + 1] - c->h_pair_off[p]), c->h_nrows[p], h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
             }
             fclose(f);
         }
