@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wall", action="store_true")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ICL_BENCH_LANES", "1")),
+                    help="pipelined lanes per GPU (wgdi_b200/pipeline.py); 1 = plain engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -244,7 +246,12 @@ def main():
     n_local = len(pts["loc1"])
 
     # the host rank (numpy's argsort) is per-rank host work: split the box's cores between the ranks
-    eng = IclEngine(local, sort_threads=max(1, (os.cpu_count() or 1) // world))
+    sort_threads = max(1, (os.cpu_count() or 1) // world)
+    if args.lanes > 1:
+        from wgdi_b200.pipeline import PipelinedEngine
+        eng = PipelinedEngine(local, lanes=args.lanes, sort_threads=sort_threads)
+    else:
+        eng = IclEngine(local, sort_threads=sort_threads)
     # inputs in page-locked host memory (the e2e leg copies them every step)
     host_in = {}
     for k in ("pair_id", "loc1", "loc2", "grading"):
@@ -323,6 +330,7 @@ def main():
                        "graded_hits": total_points, "chromosome_pairs": total_pairs, "blocks": n_blocks,
                        "mg": list(mine["cfg"].mg), "grading": list(mine["cfg"].grading),
                        "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
+                       "lanes_per_gpu": args.lanes,
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
                        "tie_order": "numpy argsort on host between the two device phases (reference-exact)"},
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,

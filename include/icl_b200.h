@@ -106,6 +106,17 @@ int icl_host_free(icl_ctx *ctx, void *ptr);
 int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
                const int32_t *pair_id, const int32_t *loc1, const int32_t *loc2, const int32_t *grading);
 
+/* Points per chromosome pair of the current upload (host array of n_pairs elements). */
+int icl_pair_counts(icl_ctx *ctx, int64_t *counts);
+
+/*
+ * Fill `dst` with the points of `src`'s current upload whose pair id lies in [pair_lo, pair_hi), in upload order,
+ * pair ids renumbered from 0 (device to device; both contexts on the same GPU).  Chromosome pairs are independent,
+ * so a comparison can be cut into lanes that run icl_dp / icl_extract on their own streams while the host sorts
+ * another lane (wgdi_b200/pipeline.py).  `member_idx` of blocks extracted from `dst` refers to `src`'s upload.
+ */
+int icl_upload_from(icl_ctx *dst, icl_ctx *src, int32_t pair_lo, int32_t pair_hi);
+
 /*
  * Sort + chaining DP in both directions (wgdi/collinearity.py:72-115: forward :74-93, anti-diagonal
  * :96-115).  Writes, for every pair segment pair_off[p]..pair_off[p+1] (see icl_layout), the final

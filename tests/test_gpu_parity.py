@@ -224,6 +224,25 @@ def test_forked_chains(gpu_engine):
             _compare_with_oracle(blocks, oracle_blocks(pts, prm))
 
 
+def test_pipelined_lanes_equal_single_engine(gpu_engine):
+    """Pipelined lanes (several contexts and streams on one GPU, host rank taking turns) give the same blocks."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    from wgdi_b200.pipeline import PipelinedEngine
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    whole = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    for lanes in (2, 4, 7):
+        pe = PipelinedEngine(0, lanes=lanes)
+        try:
+            for _ in range(3):
+                got = pe.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+                for f in ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
+                    assert (getattr(got, f) == getattr(whole, f)).all(), (lanes, f)
+        finally:
+            pe.close()
+
+
 def test_sharded_equals_unsharded(gpu_engine):
     """Chromosome pairs split over 2 and 3 ranks by LPT (ranks emulated one after another on this GPU)."""
     from wgdi_b200 import shard, synth

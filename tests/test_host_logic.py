@@ -165,6 +165,29 @@ def test_forked_chains_emu(emu_backend):
         eng.close()
 
 
+def test_pipelined_lanes_equal_single_engine_emu(emu_backend):
+    """K lanes of consecutive pair ranges (device-side split of one upload) reproduce the single-engine result,
+    including lanes without pairs."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    from wgdi_b200.pipeline import PipelinedEngine
+    pts = synth.graded_points(synth.make_dataset("tiny"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    e1 = IclEngine(0, sort_threads=2)
+    whole = e1.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    e1.close()
+    for lanes in (1, 2, 3, 12):
+        pe = PipelinedEngine(0, lanes=lanes, sort_threads=2)
+        try:
+            got = pe.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+            again = pe.run_resident(prm)
+        finally:
+            pe.close()
+        for f in ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
+            assert (getattr(got, f) == getattr(whole, f)).all(), (lanes, f)
+            assert (getattr(again, f) == getattr(whole, f)).all(), (lanes, f)
+
+
 _E2E_CHILD = r"""
 import sys, hashlib, json, ctypes, io, contextlib, numpy as np
 sys.path.insert(0, %r)

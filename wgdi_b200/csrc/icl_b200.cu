@@ -47,7 +47,8 @@ struct icl_ctx {
     int bits1 = 1, bits2 = 1, bitsp = 1;
 
     // inputs in upload order
-    Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats;
+    Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats, src_index;
+    bool has_src_index = false;      // upload came from icl_upload_from: src_index maps to the source context's upload
     // sort
     Buf<uint64_t> key_a, key_b;
     Buf<uint32_t> idx_a, perm;
@@ -220,7 +221,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
 #endif
-    c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release();
+    c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release(); c->src_index.release();
     c->key_a.release(); c->key_b.release(); c->idx_a.release(); c->perm.release(); c->tmp.release();
     c->d_pair_off.release(); c->d_rb.release(); c->d_rmin.release(); c->d_nrows.release();
     c->d_item_order.release(); c->d_pair_order.release();
@@ -289,6 +290,7 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
 #endif
     c->n = n;
     c->P = P;
+    c->has_src_index = false;
     if (c->in_pair.reserve(st, n) || c->in_loc1.reserve(st, n) || c->in_loc2.reserve(st, n) || c->in_grad.reserve(st, n))
         return st.code;
     size_t b = (size_t)n * sizeof(int32_t);
@@ -308,6 +310,81 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
     c->bitsp = bits_for(P > 0 ? P - 1 : 0);
     if (c->bits1 + c->bits2 + c->bitsp > 64) return fail(c, ICL_ERR_LIMIT, "icl_upload: key does not fit 64 bits");
     c->uploaded = true;
+    st.code = 0;
+    return ICL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: split one upload over several contexts of the same device (pipelined lanes, see wgdi_b200/pipeline.py)
+// ------------------------------------------------------------------------------------------------
+extern "C" int icl_pair_counts(icl_ctx *c, int64_t *counts) {
+    if (!c || !counts) return ICL_ERR_ARG;
+    if (!c->uploaded) return fail(c, ICL_ERR_STATE, "icl_pair_counts: icl_upload has not succeeded");
+    Status &st = c->st;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaSetDevice(c->device));
+#endif
+    const int32_t P = c->P;
+    if (P == 0) return ICL_OK;
+    Buf<int32_t> cnt;
+    if (cnt.reserve(st, P)) return st.code;
+    ICL_CUDA(st, dev_memset(cnt.p, 0, (size_t)P * sizeof(int32_t), c->stream));
+    {
+        const int32_t *ip = c->in_pair.p;
+        int32_t *d = cnt.p;
+        ICL_CUDA(st, foreach(c->stream, c->n, ICL_LAMBDA(int64_t i) { atomic_add_i32(&d[ip[i]], 1); }));
+    }
+    std::vector<int32_t> h((size_t)P);
+    ICL_CUDA(st, d2h(h.data(), cnt.p, (size_t)P * sizeof(int32_t), c->stream));
+    ICL_CUDA(st, dev_sync(c->stream));
+    cnt.release();
+    for (int32_t p = 0; p < P; p++) counts[p] = h[p];
+    return ICL_OK;
+}
+
+extern "C" int icl_upload_from(icl_ctx *dst, icl_ctx *src, int32_t pair_lo, int32_t pair_hi) {
+    if (!dst || !src || dst == src) return ICL_ERR_ARG;
+    dst->uploaded = dst->dp_done = false;
+    if (!src->uploaded) return fail(dst, ICL_ERR_STATE, "icl_upload_from: the source context has no upload");
+    if (dst->device != src->device) return fail(dst, ICL_ERR_ARG, "icl_upload_from: contexts live on different devices");
+    if (pair_lo < 0 || pair_hi < pair_lo || pair_hi > src->P) return fail(dst, ICL_ERR_ARG, "icl_upload_from: bad pair range");
+    Status &st = dst->st;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaSetDevice(dst->device));
+#endif
+    cudaStream_t s = dst->stream;
+    const int64_t n = src->n;
+    if (dst->acc_flag.reserve(st, n + 2) || dst->blkidx.reserve(st, n + 2)) return st.code;
+    {
+        const int32_t *ip = src->in_pair.p;
+        uint32_t *flag = dst->acc_flag.p;
+        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) { flag[i] = (ip[i] >= pair_lo && ip[i] < pair_hi) ? 1u : 0u; }));
+    }
+    if (exclusive_sum_u32(st, dst->tmp, dst->acc_flag.p, dst->blkidx.p, n, s)) return st.code;
+    uint32_t m = 0;
+    ICL_CUDA(st, d2h(&m, dst->blkidx.p + n, sizeof(uint32_t), s));
+    ICL_CUDA(st, dev_sync(s));
+    dst->n = m;
+    dst->P = pair_hi - pair_lo;
+    if (dst->in_pair.reserve(st, m) || dst->in_loc1.reserve(st, m) || dst->in_loc2.reserve(st, m) || dst->in_grad.reserve(st, m) ||
+        dst->src_index.reserve(st, m))
+        return st.code;
+    {
+        // order-preserving compaction: equal coordinates keep the source's upload order (stable sort later, H22)
+        const int32_t *ip = src->in_pair.p, *i1 = src->in_loc1.p, *i2 = src->in_loc2.p, *ig = src->in_grad.p;
+        const uint32_t *pos = dst->blkidx.p;
+        int32_t *op = dst->in_pair.p, *o1 = dst->in_loc1.p, *o2 = dst->in_loc2.p, *og = dst->in_grad.p, *oi = dst->src_index.p;
+        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
+            if (ip[i] < pair_lo || ip[i] >= pair_hi) return;
+            const uint32_t k = pos[i];
+            op[k] = ip[i] - pair_lo; o1[k] = i1[i]; o2[k] = i2[i]; og[k] = ig[i]; oi[k] = (int32_t)i;
+        }));
+    }
+    dst->bits1 = src->bits1;
+    dst->bits2 = src->bits2;
+    dst->bitsp = bits_for(dst->P > 0 ? dst->P - 1 : 0);
+    dst->has_src_index = true;
+    dst->uploaded = true;
     st.code = 0;
     return ICL_OK;
 }
@@ -2004,6 +2081,7 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
         const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;
         const int32_t *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_item = c->b_item.p, *members = c->members.p;
         const int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p;
+        const int32_t *srcidx = c->has_src_index ? c->src_index.p : nullptr;
         const int64_t *b_N1 = c->b_N1.p;
         const double *b_a = c->b_a.p;
         icl_blocks o = dv;
@@ -2033,7 +2111,7 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
             const int32_t i = members[b_moff[o_src[lo]] + (uint32_t)(t - omoff[lo])];
             o.loc1[t] = l1[i];
             o.loc2[t] = l2[i];
-            o.member_idx[t] = (int32_t)perm[i];
+            o.member_idx[t] = srcidx ? srcidx[perm[i]] : (int32_t)perm[i];
         }));
         if (NBo == 0) ICL_CUDA(st, dev_memset(dv.member_off, 0, sizeof(int64_t), s));
     }

@@ -145,6 +145,13 @@ ICL_HD void atomic_max_i32(int32_t *p, int32_t v) {
     if (v > *p) *p = v;
 #endif
 }
+ICL_HD void atomic_add_i32(int32_t *p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
 ICL_HD void atomic_add_i64(int64_t *p, int64_t v) {
 #if defined(__CUDA_ARCH__)
     atomicAdd((unsigned long long *)p, (unsigned long long)v);
