@@ -1446,8 +1446,12 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
         }));
     }
     if (n > 0) {
-        ICL_CUDA(st, d2h(score_fwd, c->score32.p, (size_t)n * sizeof(int32_t), s));
-        ICL_CUDA(st, d2h(score_rev, c->score32.p + n, (size_t)n * sizeof(int32_t), s));
+        if (score_rev == score_fwd + n) {                      // one buffer of 2n: a single transfer
+            ICL_CUDA(st, d2h(score_fwd, c->score32.p, (size_t)2 * n * sizeof(int32_t), s));
+        } else {
+            ICL_CUDA(st, d2h(score_fwd, c->score32.p, (size_t)n * sizeof(int32_t), s));
+            ICL_CUDA(st, d2h(score_rev, c->score32.p + n, (size_t)n * sizeof(int32_t), s));
+        }
     }
     c->timers[ICL_T_EXPORT].stop(s);
     ICL_CUDA(st, dev_sync(s));
@@ -1985,8 +1989,12 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     c->timers[ICL_T_EXTRACT].start(s);
     if (c->order_in.reserve(st, 2 * n) || c->rank2v.reserve(st, V)) return st.code;
     if (n > 0) {
-        ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)n * sizeof(int32_t), s));
-        ICL_CUDA(st, h2d(c->order_in.p + n, argsort_rev, (size_t)n * sizeof(int32_t), s));
+        if (argsort_rev == argsort_fwd + n) {
+            ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)2 * n * sizeof(int32_t), s));
+        } else {
+            ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)n * sizeof(int32_t), s));
+            ICL_CUDA(st, h2d(c->order_in.p + n, argsort_rev, (size_t)n * sizeof(int32_t), s));
+        }
         // rank2v[V position] = point examined at that rank position of its item
         const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
         const int64_t *off = c->d_pair_off.p;

@@ -185,7 +185,8 @@ class IclEngine:
         order (widened to int64: the array pandas' nargsort(ascending=False) hands to numpy.argsort)."""
         prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
                          float(params.coverage_ratio))
-        sf, sr = self._buf("key_fwd", self.n, np.int32), self._buf("key_rev", self.n, np.int32)
+        keys = self._buf("keys", 2 * self.n, np.int32)               # forward | anti-diagonal, one pinned buffer
+        sf, sr = keys[:self.n], keys[self.n:]
         self._check(self.lib.icl_dp(self.ctx, C.byref(prm), sf.ctypes.data, sr.ctypes.data))
         self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
         self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
@@ -202,10 +203,18 @@ class IclEngine:
         reference reaches through pandas (collinearity.py:49,60).  Uses numpy's own compiled routine from a
         thread pool without the GIL when the helper module is available (verified against numpy.argsort at
         start-up), otherwise one numpy call per segment."""
-        af, ar = self._buf("argsort_fwd", self.n, np.int32), self._buf("argsort_rev", self.n, np.int32)
+        both = self._buf("argsort", 2 * self.n, np.int32)           # forward | anti-diagonal, one pinned buffer
+        af, ar = both[:self.n], both[self.n:]
         off = self.pair_off
         sizes = np.diff(off)
         if _npsort_ok():
+            # one pass over all 2P segments (longest first) so that the pool drains evenly
+            if key_rev.ctypes.data == key_fwd.ctypes.data + 4 * self.n:
+                keys2 = np.frombuffer((C.c_int32 * (2 * self.n)).from_address(key_fwd.ctypes.data), np.int32) if self.n else key_fwd
+                off2 = np.concatenate([off, off[1:] + self.n])
+                order = np.argsort(-np.concatenate([sizes, sizes]), kind="stable").astype(np.int32)
+                _npsort.seg_argsort(keys2, off2, order, both, self.sort_threads)
+                return af, ar
             order = np.argsort(-sizes, kind="stable").astype(np.int32)
             _npsort.seg_argsort(key_fwd, off, order, af, self.sort_threads)
             _npsort.seg_argsort(key_rev, off, order, ar, self.sort_threads)
