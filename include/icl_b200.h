@@ -162,11 +162,12 @@ int icl_debug_dp(icl_ctx *ctx, int32_t dir, int32_t *score, int32_t *pred, int32
 #define ICL_T_SETUP 1     /* row index, mirrored copy */
 #define ICL_T_EDGES 2     /* candidate (edge) enumeration */
 #define ICL_T_CHAIN 3     /* chaining DP, both directions */
-#define ICL_T_EXPORT 4    /* score export + D2H */
+#define ICL_T_EXPORT 4    /* score export kernel */
 #define ICL_T_EXTRACT 5   /* block extraction */
 #define ICL_T_PVALUE 6    /* times / p-value pass */
 #define ICL_T_GATHER 7    /* output compaction + D2H */
-#define ICL_T_COUNT 8
+#define ICL_T_D2H 8       /* scores device -> host */
+#define ICL_T_COUNT 9
 int icl_timings(icl_ctx *ctx, double *ms, int32_t n_slots);
 
 /* Counters of the most recent icl_dp: [0] edges enumerated, [1] kernels launched by icl_dp,

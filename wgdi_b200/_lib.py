@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicl_b200.so")
 
-ICL_T_NAMES = ("sort", "setup", "edges", "chain", "export", "extract", "pvalue", "gather")
+ICL_T_NAMES = ("sort", "setup", "edges", "chain", "export", "extract", "pvalue", "gather", "keys_d2h")
 
 
 class IclError(RuntimeError):

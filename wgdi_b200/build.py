@@ -48,7 +48,7 @@ def build_npsort(force=False):
     out = os.path.join(HERE, "_npsort" + sysconfig.get_config_var("EXT_SUFFIX"))
     if not force and not _stale(out, [src]):
         return out
-    cmd = ["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-pthread", "-I", sysconfig.get_paths()["include"],
+    cmd = ["/usr/bin/gcc", "-O2", "-mclflushopt", "-fPIC", "-shared", "-pthread", "-I", sysconfig.get_paths()["include"],
            "-I", numpy.get_include(), "-o", out, src]
     subprocess.check_call(cmd)
     return out

@@ -1445,6 +1445,8 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
             o[n + i] = S[mmap[src]];
         }));
     }
+    c->timers[ICL_T_EXPORT].stop(s);
+    c->timers[ICL_T_D2H].start(s);
     if (n > 0) {
         if (score_rev == score_fwd + n) {                      // one buffer of 2n: a single transfer
             ICL_CUDA(st, d2h(score_fwd, c->score32.p, (size_t)2 * n * sizeof(int32_t), s));
@@ -1453,7 +1455,7 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
             ICL_CUDA(st, d2h(score_rev, c->score32.p + n, (size_t)n * sizeof(int32_t), s));
         }
     }
-    c->timers[ICL_T_EXPORT].stop(s);
+    c->timers[ICL_T_D2H].stop(s);
     ICL_CUDA(st, dev_sync(s));
     if (getenv("ICL_B200_CHAIN_DEBUG") && c->chain_dbg.p && c->P > 0) {
         std::vector<long long> h(8 * (size_t)c->P);

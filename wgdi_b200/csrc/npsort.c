@@ -21,6 +21,7 @@
 #include <Python.h>
 #define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
 #include <numpy/arrayobject.h>
+#include <immintrin.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -34,6 +35,7 @@ typedef struct {
     int64_t n_seg;
     volatile int64_t next;
     volatile int err;
+    int flush;
 } job_t;
 
 static void *worker(void *vp)
@@ -57,10 +59,23 @@ static void *worker(void *vp)
             if (!idx || !wide) { j->err = 1; break; }
         }
         const int32_t *k32 = j->keys + a;
+        if (j->flush == 2) {                   /* non-temporal prefetch: the keys pass through L1 only */
+            for (int64_t i = 0; i < n; i += 16) _mm_prefetch((const char *)(k32 + i), _MM_HINT_NTA);
+        }
         for (int64_t i = 0; i < n; i++) { idx[i] = i; wide[i] = k32[i]; }   /* index fill as _new_argsortlike does */
+        /* The key buffer is the target of the next device-to-host DMA: drop its lines from the CPU caches now so
+           that the DMA writes do not have to snoop them out (measured: 15 MB in 0.70 ms with cached lines vs
+           0.28 ms for untouched pinned memory). */
+        if (j->flush == 1)
+            for (const char *q = (const char *)((uintptr_t)k32 & ~(uintptr_t)63); q < (const char *)(k32 + n); q += 64) _mm_clflush(q);
+#ifdef __CLFLUSHOPT__
+        if (j->flush == 3)
+            for (const char *q = (const char *)((uintptr_t)k32 & ~(uintptr_t)63); q < (const char *)(k32 + n); q += 64) _mm_clflushopt((void *)q);
+#endif
         if (j->fn((void *)wide, idx, (npy_intp)n, NULL) < 0) { j->err = 2; break; }
         int32_t *o = j->out + a;
-        for (int64_t i = 0; i < n; i++) o[i] = (int32_t)idx[i];
+        /* streaming stores: the argsort goes to the device next, keep it out of the caches */
+        for (int64_t i = 0; i < n; i++) _mm_stream_si32((int *)&o[i], (int)idx[i]);
     }
     free(idx);
     free(wide);
@@ -70,9 +85,9 @@ static void *worker(void *vp)
 static PyObject *seg_argsort(PyObject *self, PyObject *args)
 {
     PyArrayObject *keys, *off, *order, *out;
-    int threads;
-    if (!PyArg_ParseTuple(args, "O!O!O!O!i", &PyArray_Type, &keys, &PyArray_Type, &off, &PyArray_Type, &order,
-                          &PyArray_Type, &out, &threads))
+    int threads, flush = 0;
+    if (!PyArg_ParseTuple(args, "O!O!O!O!i|i", &PyArray_Type, &keys, &PyArray_Type, &off, &PyArray_Type, &order,
+                          &PyArray_Type, &out, &threads, &flush))
         return NULL;
     if (PyArray_TYPE(keys) != NPY_INT32 || PyArray_TYPE(off) != NPY_INT64 || PyArray_TYPE(order) != NPY_INT32 ||
         PyArray_TYPE(out) != NPY_INT32 || !PyArray_IS_C_CONTIGUOUS(keys) || !PyArray_IS_C_CONTIGUOUS(off) ||
@@ -98,6 +113,7 @@ static PyObject *seg_argsort(PyObject *self, PyObject *args)
     j.n_seg = PyArray_SIZE(off) - 1;
     j.next = 0;
     j.err = 0;
+    j.flush = flush;
     if (threads < 1) threads = 1;
     if (threads > 128) threads = 128;
     if (threads > j.n_seg) threads = (int)(j.n_seg > 0 ? j.n_seg : 1);
@@ -108,6 +124,7 @@ static PyObject *seg_argsort(PyObject *self, PyObject *args)
         if (pthread_create(&th[started], NULL, worker, &j) == 0) started++;
     worker(&j);
     for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+    _mm_sfence();
     Py_END_ALLOW_THREADS
     if (j.err) {
         PyErr_SetString(PyExc_RuntimeError, j.err == 1 ? "seg_argsort: out of memory" : "seg_argsort: numpy argsort failed");
@@ -116,7 +133,18 @@ static PyObject *seg_argsort(PyObject *self, PyObject *args)
     return PyLong_FromLong(0);
 }
 
+/* CPUID.(EAX=7,ECX=0):EBX bit 23 */
+static PyObject *has_clflushopt(PyObject *self, PyObject *args)
+{
+    unsigned a = 7, b = 0, c = 0, d = 0;
+#if defined(__x86_64__)
+    __asm__ volatile("cpuid" : "+a"(a), "=b"(b), "+c"(c), "=d"(d));
+#endif
+    return PyBool_FromLong((b >> 23) & 1u);
+}
+
 static PyMethodDef methods[] = {
+    {"has_clflushopt", has_clflushopt, METH_NOARGS, "CPU supports CLFLUSHOPT"},
     {"seg_argsort", seg_argsort, METH_VARARGS, "segmented numpy argsort(kind='quicksort') on int64, multi-threaded"},
     {NULL, NULL, 0, NULL}};
 

@@ -137,6 +137,10 @@ class IclEngine:
         self.n_pairs = 0
         self._pinned = {}
         self.sort_threads = sort_threads or min(32, os.cpu_count() or 1)
+        # After sorting, the helper drops the key buffer's lines from the CPU caches (CLFLUSHOPT) so that the next
+        # device-to-host DMA does not have to snoop them out: 15 MB in 0.29 ms instead of 0.84 ms (csrc/npsort.c).
+        default_flush = "3" if (_npsort is not None and hasattr(_npsort, "has_clflushopt") and _npsort.has_clflushopt()) else "0"
+        self.flush_keys = int(os.environ.get("ICL_B200_FLUSH_KEYS", default_flush))
         self._pool = ThreadPoolExecutor(self.sort_threads) if self.sort_threads > 1 else None
         self.host_ms = {}
 
@@ -213,7 +217,7 @@ class IclEngine:
                 keys2 = np.frombuffer((C.c_int32 * (2 * self.n)).from_address(key_fwd.ctypes.data), np.int32) if self.n else key_fwd
                 off2 = np.concatenate([off, off[1:] + self.n])
                 order = np.argsort(-np.concatenate([sizes, sizes]), kind="stable").astype(np.int32)
-                _npsort.seg_argsort(keys2, off2, order, both, self.sort_threads)
+                _npsort.seg_argsort(keys2, off2, order, both, self.sort_threads, self.flush_keys)
                 return af, ar
             order = np.argsort(-sizes, kind="stable").astype(np.int32)
             _npsort.seg_argsort(key_fwd, off, order, af, self.sort_threads)
