@@ -555,24 +555,32 @@ struct EdgeEnum {
     const int64_t *rb;
     int64_t R;
     int32_t P, mg1, mg2;
-    template <class Emit>
-    ICL_HD void run(int64_t v, Emit emit) const {
+    // band of source v: the points of the next mg1-1 rows, one contiguous slice [k0, k1) of V space
+    ICL_HD bool band(int64_t v, int32_t &k0, int32_t &k1, int32_t &x1, int32_t &x2, int64_t &base, int32_t &nr) const {
         int32_t it = itemof[v];
         int32_t p = it >= P ? it - P : it;
-        int64_t base = rb[p] + (it >= P ? R : 0);
-        int32_t nr = nrows[p];
-        int32_t x1 = X1[v], x2 = X2[v];
+        base = rb[p] + (it >= P ? R : 0);
+        nr = nrows[p];
+        x1 = X1[v];
+        x2 = X2[v];
         int32_t lastrow = x1 + mg1 - 1 < nr - 1 ? x1 + mg1 - 1 : nr - 1;
-        if (lastrow <= x1) return;
-        const int32_t k0 = rowptr[base + x1 + 1], k1 = rowptr[base + lastrow + 1];
+        if (lastrow <= x1) { k0 = k1 = 0; return false; }
+        k0 = rowptr[base + x1 + 1];
+        k1 = rowptr[base + lastrow + 1];
+        return k1 > k0;
+    }
+    // candidates of source v in visiting order; pX1/pX2/pG are indexed by V position (global arrays or a staged tile)
+    template <class Emit>
+    ICL_HD void scan(int32_t k0, int32_t k1, int32_t x1, int32_t x2, int64_t base, int32_t nr,
+                     const int32_t *pX1, const int32_t *pX2, const int32_t *pG, Emit emit) const {
         if (k1 - k0 <= 384) {
             // the next mg1-1 rows are one contiguous slice sorted by (row, column): scan it once
             for (int32_t k = k0; k < k1; k++) {
-                int32_t dc = X2[k] - x2;
+                int32_t dc = pX2[k] - x2;
                 if (dc <= 0 || dc >= mg2) continue;
-                int32_t dr = X1[k] - x1;
-                int32_t s = G[k] - (dr + dc);
-                bool last = (k + 1 == k1) || X1[k + 1] != X1[k] || (X2[k + 1] - x2 >= mg2);
+                int32_t dr = pX1[k] - x1;
+                int32_t s = pG[k] - (dr + dc);
+                bool last = (k + 1 == k1) || pX1[k + 1] != pX1[k] || (pX2[k + 1] - x2 >= mg2);
                 if (s > 0 || last) emit(k, dr, dc, s > 0 ? s : 0);
             }
             return;
@@ -590,6 +598,13 @@ struct EdgeEnum {
             }
         }
     }
+    template <class Emit>
+    ICL_HD void run(int64_t v, Emit emit) const {
+        int32_t k0, k1, x1, x2, nr;
+        int64_t base;
+        if (!band(v, k0, k1, x1, x2, base, nr)) return;
+        scan(k0, k1, x1, x2, base, nr, X1, X2, G, emit);
+    }
 };
 
 // Edge record (8 bytes) of the flat per-item edge stream the DP kernel consumes:
@@ -600,6 +615,60 @@ struct EdgeEnum {
 // cost the DP kernel nothing.
 #define ICL_EDGE_CHUNK 512           // records per TMA chunk (4 KB)
 
+#ifndef ICL_EMU
+// Edge enumeration, one thread per source, 256 consecutive sources per CTA.  Consecutive sources have heavily
+// overlapping bands (the points are sorted), so the CTA stages the union of its bands — a contiguous slice of
+// X1 / X2 / G — in shared memory once and every thread scans its own band from there.
+#define ICL_EDGE_TILE 1536
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_edges_tile(EdgeEnum ee, int64_t V, int64_t n, uint32_t *ecnt, int32_t *lastsrc,
+                                                    const uint32_t *eoff, uint2 *edges, const int64_t *off, int32_t *stats) {
+    __shared__ int32_t sX1[ICL_EDGE_TILE], sX2[ICL_EDGE_TILE], sG[ICL_EDGE_TILE];
+    __shared__ int32_t s_kmin, s_kmax;
+    const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (threadIdx.x == 0) { s_kmin = 0x7fffffff; s_kmax = 0; }
+    __syncthreads();
+    int32_t k0 = 0, k1 = 0, x1 = 0, x2 = 0, nr = 0;
+    int64_t base = 0;
+    bool has = false;
+    if (v < V) has = ee.band(v, k0, k1, x1, x2, base, nr);
+    const bool small = has && (k1 - k0 <= 384);
+    if (small) { atomicMin(&s_kmin, k0); atomicMax(&s_kmax, k1); }
+    __syncthreads();
+    const int32_t kmin = s_kmin, kmax = s_kmax;
+    const bool tiled = kmax > kmin && kmax - kmin <= ICL_EDGE_TILE;
+    if (tiled) {
+        for (int32_t k = kmin + threadIdx.x; k < kmax; k += 256) { sX1[k - kmin] = ee.X1[k]; sX2[k - kmin] = ee.X2[k]; sG[k - kmin] = ee.G[k]; }
+    }
+    __syncthreads();
+    if (v >= V) return;
+    const int32_t *pX1 = (tiled && small) ? sX1 - kmin : ee.X1, *pX2 = (tiled && small) ? sX2 - kmin : ee.X2,
+                  *pG = (tiled && small) ? sG - kmin : ee.G;
+    if (!FILL) {
+        uint32_t cnt = 0;
+        if (has) ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t, int32_t, int32_t, int32_t) { cnt++; });
+        ecnt[v] = cnt;
+        lastsrc[v] = cnt ? (int32_t)v : -1;
+    } else {
+        uint32_t e = eoff[v];
+        if (eoff[v + 1] == e) return;
+        const int32_t it = ee.itemof[v];
+        const int64_t a = off[it >= ee.P ? it - ee.P : it] + (it >= ee.P ? n : 0);
+        int64_t prev = v > 0 ? lastsrc[v - 1] : -1;
+        if (prev < a) prev = a;
+        uint32_t adv = (uint32_t)(v - prev);
+        int32_t span = 0;
+        ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
+            span = k - (int32_t)v;                    // candidates are visited in increasing position
+            edges[e++] = make_uint2(((uint32_t)span & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                                    ((uint32_t)sc & 0xffu) | (adv << 8));
+            adv = 0;
+        });
+        if (span > stats[3]) atomicMax(&stats[3], span);
+    }
+}
+#endif
+
 static int phase_edges(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n, V = 2 * n;
@@ -609,12 +678,20 @@ static int phase_edges(icl_ctx *c) {
     EdgeEnum ee{c->X1.p, c->X2.p, c->G.p, c->itemof.p, c->rowptr.p, c->d_nrows.p, c->d_rb.p, c->R, c->P, c->prm.mg1, c->prm.mg2};
     uint32_t *ecnt = c->ecnt.p;
     int32_t *lastsrc = c->lastsrc.p;
+#ifndef ICL_EMU
+    const unsigned eblocks = (unsigned)((V + 255) / 256);
+    if (V > 0) {
+        k_edges_tile<false><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, lastsrc, nullptr, nullptr, c->d_pair_off.p, c->stats.p);
+        ICL_CUDA(st, cudaGetLastError());
+    }
+#else
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t cnt = 0;
         ee.run(v, [&](int32_t, int32_t, int32_t, int32_t) { cnt++; });
         ecnt[v] = cnt;
         lastsrc[v] = cnt ? (int32_t)v : -1;
     }));
+#endif
     if (exclusive_sum_u32(st, c->tmp, c->ecnt.p, c->eoff.p, V, s)) return st.code;
     if (inclusive_max_i32(st, c->tmp, c->lastsrc.p, V, s)) return st.code;      // last source <= v that has records
     uint32_t total = 0;
@@ -628,6 +705,12 @@ static int phase_edges(icl_ctx *c) {
     const int32_t *itemof = c->itemof.p;
     const int64_t *off = c->d_pair_off.p;
     ICL_CUDA(st, dev_memset(c->stats.p + 3, 0, sizeof(int32_t), s));
+#ifndef ICL_EMU
+    if (V > 0) {
+        k_edges_tile<true><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, lastsrc, eoff, edges, off, stats);
+        ICL_CUDA(st, cudaGetLastError());
+    }
+#else
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t e = eoff[v];
         if (eoff[v + 1] == e) return;
@@ -647,6 +730,7 @@ static int phase_edges(icl_ctx *c) {
         // Monotonic max: the plain read filters almost every atomic away.
         if (span > stats[3]) atomic_max_i32(&stats[3], span);
     }));
+#endif
     // row table for the wave kernel: first record and first source with records of every dense row, and the
     // largest number of points inside (64 + mg1) consecutive rows (sizes its shared-memory window)
     const int64_t R2 = 2 * c->R;
