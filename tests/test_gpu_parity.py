@@ -199,6 +199,36 @@ def test_edge_cases(gpu_engine):
     assert e.value.code == -1                                   # not a permutation
 
 
+def test_documented_limits_are_errors(gpu_engine):
+    from wgdi_b200._lib import IclError
+    from wgdi_b200.engine import ChainParams, IclEngine
+    one = np.array([0], np.int32)
+    with pytest.raises(IclError) as e:
+        gpu_engine.upload(one, one + 1, one + 1, one + 300, 1)          # grading > 255
+    assert e.value.code == -4
+    with pytest.raises(IclError) as e:
+        gpu_engine.upload(one, one + (1 << 26), one + 1, one + 50, 1)   # coordinate >= 2^26
+    assert e.value.code == -4
+    # icl_upload_from: bad range / same context / no upload
+    import ctypes as C
+    other = IclEngine(0)
+    try:
+        lib = gpu_engine.lib
+        assert lib.icl_upload_from(other.ctx, other.ctx, 0, 0) == -1
+        fresh = IclEngine(0)
+        assert lib.icl_upload_from(other.ctx, fresh.ctx, 0, 0) == -3
+        fresh.close()
+        l = np.array([1, 2, 3, 7, 8, 9], np.int32)
+        gpu_engine.upload(np.array([0, 0, 0, 1, 1, 1], np.int32), l, l, np.full(6, 50, np.int32), 2)
+        assert lib.icl_upload_from(other.ctx, gpu_engine.ctx, 1, 3) == -1
+        assert lib.icl_upload_from(other.ctx, gpu_engine.ctx, 1, 2) == 0
+        other.n, other.n_pairs = 3, 1
+        b = other.run_resident(ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))
+        assert len(b) == 1 and b.loc1[:3].tolist() == [7, 8, 9] and b.member_idx[:3].tolist() == [3, 4, 5]
+    finally:
+        other.close()
+
+
 def test_window_bounds_are_exclusive(gpu_engine):
     """Offsets 1..mg-1 chain, offset mg does not (collinearity.py:76-79), in both directions."""
     from wgdi_b200.engine import ChainParams
