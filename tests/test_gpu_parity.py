@@ -307,14 +307,14 @@ def test_other_baseline_configs_match_oracle(gpu_engine, name, scale, mg):
     assert gpu_engine.counters()["chain_kernel"] == "ring"
 
 
-def test_wave_and_generic_kernels_agree(clouds):
-    """The alternative DP kernels (ICL_B200_CHAIN=wave / generic) give the same blocks as the default ring kernel."""
+def test_alternative_dp_kernels_agree(clouds):
+    """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth
     from wgdi_b200.engine import ChainParams, IclEngine
     pts = synth.graded_points(synth.make_dataset("small"))
     prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
     exp = oracle_blocks(pts, prm)
-    for mode in ("wave", "generic", "single"):
+    for mode in ("generic", "single"):
         os.environ["ICL_B200_CHAIN"] = mode
         try:
             eng = IclEngine(0)

@@ -62,18 +62,15 @@ struct icl_ctx {
     Buf<int32_t> loc1s, loc2s, pair_s, rowptr, X1, X2, G, itemof, mmap, imap;
     // edges
     Buf<uint32_t> ecnt, eoff;
-    Buf<int32_t> lastsrc;
     Buf<uint2> edges;
     int64_t n_edges = 0;
     int32_t max_span = 0;            // largest (target position - source position) over all edges
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
-    int32_t chain_mode = 1;          // 1 = batch ring kernel (default), 3 = single-executor ring kernel, 2 = wave kernel, 0 = generic (env ICL_B200_CHAIN)
+    int32_t chain_mode = 1;          // 1 = batch ring kernel (default), 3 = single-executor ring kernel, 0 = generic (env ICL_B200_CHAIN)
     Buf<long long> chain_dbg;
     int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
-    int32_t wave_span = 0;           // most points inside 64 + mg1 consecutive rows of an item
-    Buf<int2> rowtab;                // per dense row: {first edge record, first source that has records | -1}
     // DP state (V space)
     Buf<int32_t> S, root;            // root = first point of the path (root of the predecessor tree)
     Buf<int2> pd;                    // per point: {pred (-1 for path roots), path length}
@@ -210,7 +207,7 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
     const char *pvm = getenv("ICL_B200_PVALUE");
     if (pvm) c->pvalue_mode = !strcmp(pvm, "seq") ? 1 : !strcmp(pvm, "inc") ? 2 : 0;
-    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "wave") ? 2 : !strcmp(mode, "single") ? 3 : 1;
+    if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "single") ? 3 : 1;
     *out = c;
     return ICL_OK;
 }
@@ -227,7 +224,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
-    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->lastsrc.release(); c->rowtab.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
+    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
     c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
@@ -609,10 +606,10 @@ struct EdgeEnum {
 
 // Edge record (8 bytes) of the flat per-item edge stream the DP kernel consumes:
 //   x = koff (bits 0-15: target position - source position) | dr << 16 | dc << 24
-//   y = s (bits 0-7: grading_k - (dr + dc), 0 when it cannot update) | adv << 8
-// adv (24 bits) is set on the first record of a source: how far the source position advances from the
-// previous source that has records (or from the item start).  Sources without candidates have no records and
-// cost the DP kernel nothing.
+//   y = s (bits 0-7: grading_k - (dr + dc), 0 when it cannot update) | srel << 8
+// srel (24 bits) = source position relative to the first point of the item, so a record is self-contained: a
+// warp can replay 32 consecutive records without first scanning for their sources.  Sources without
+// candidates have no records and cost the DP kernel nothing.
 #define ICL_EDGE_CHUNK 512           // records per TMA chunk (4 KB)
 
 #ifndef ICL_EMU
@@ -621,7 +618,7 @@ struct EdgeEnum {
 // X1 / X2 / G — in shared memory once and every thread scans its own band from there.
 #define ICL_EDGE_TILE 1536
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_edges_tile(EdgeEnum ee, int64_t V, int64_t n, uint32_t *ecnt, int32_t *lastsrc,
+__global__ void __launch_bounds__(256) k_edges_tile(EdgeEnum ee, int64_t V, int64_t n, uint32_t *ecnt,
                                                     const uint32_t *eoff, uint2 *edges, const int64_t *off, int32_t *stats) {
     __shared__ int32_t sX1[ICL_EDGE_TILE], sX2[ICL_EDGE_TILE], sG[ICL_EDGE_TILE];
     __shared__ int32_t s_kmin, s_kmax;
@@ -646,25 +643,22 @@ __global__ void __launch_bounds__(256) k_edges_tile(EdgeEnum ee, int64_t V, int6
                   *pG = (tiled && small) ? sG - kmin : ee.G;
     if (!FILL) {
         uint32_t cnt = 0;
-        if (has) ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t, int32_t, int32_t, int32_t) { cnt++; });
+        int32_t span = 0;
+        if (has) ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t k, int32_t, int32_t, int32_t) { cnt++; span = k - (int32_t)v; });
         ecnt[v] = cnt;
-        lastsrc[v] = cnt ? (int32_t)v : -1;
+        // largest distance a source reaches ahead (candidates are visited in increasing position): sizes the
+        // shared-memory window of the DP kernel.  Monotonic max: the plain read filters almost every atomic away.
+        if (span > stats[3]) atomicMax(&stats[3], span);
     } else {
         uint32_t e = eoff[v];
         if (eoff[v + 1] == e) return;
         const int32_t it = ee.itemof[v];
         const int64_t a = off[it >= ee.P ? it - ee.P : it] + (it >= ee.P ? n : 0);
-        int64_t prev = v > 0 ? lastsrc[v - 1] : -1;
-        if (prev < a) prev = a;
-        uint32_t adv = (uint32_t)(v - prev);
-        int32_t span = 0;
+        const uint32_t srel = (uint32_t)(v - a) << 8;
         ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
-            span = k - (int32_t)v;                    // candidates are visited in increasing position
-            edges[e++] = make_uint2(((uint32_t)span & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
-                                    ((uint32_t)sc & 0xffu) | (adv << 8));
-            adv = 0;
+            edges[e++] = make_uint2(((uint32_t)(k - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                                    ((uint32_t)sc & 0xffu) | srel);
         });
-        if (span > stats[3]) atomicMax(&stats[3], span);
     }
 }
 #endif
@@ -674,98 +668,59 @@ static int phase_edges(icl_ctx *c) {
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->ecnt.reserve(st, V + 2) || c->eoff.reserve(st, V + 2) || c->lastsrc.reserve(st, V + 2)) return st.code;
+    if (c->ecnt.reserve(st, V + 2) || c->eoff.reserve(st, V + 2)) return st.code;
     EdgeEnum ee{c->X1.p, c->X2.p, c->G.p, c->itemof.p, c->rowptr.p, c->d_nrows.p, c->d_rb.p, c->R, c->P, c->prm.mg1, c->prm.mg2};
     uint32_t *ecnt = c->ecnt.p;
-    int32_t *lastsrc = c->lastsrc.p;
+    int32_t *stats = c->stats.p;
+    ICL_CUDA(st, dev_memset(c->stats.p + 3, 0, sizeof(int32_t), s));
 #ifndef ICL_EMU
     const unsigned eblocks = (unsigned)((V + 255) / 256);
     if (V > 0) {
-        k_edges_tile<false><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, lastsrc, nullptr, nullptr, c->d_pair_off.p, c->stats.p);
+        k_edges_tile<false><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, nullptr, nullptr, c->d_pair_off.p, stats);
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t cnt = 0;
-        ee.run(v, [&](int32_t, int32_t, int32_t, int32_t) { cnt++; });
+        int32_t span = 0;
+        ee.run(v, [&](int32_t k, int32_t, int32_t, int32_t) { cnt++; span = k - (int32_t)v; });
         ecnt[v] = cnt;
-        lastsrc[v] = cnt ? (int32_t)v : -1;
+        if (span > stats[3]) atomic_max_i32(&stats[3], span);
     }));
 #endif
     if (exclusive_sum_u32(st, c->tmp, c->ecnt.p, c->eoff.p, V, s)) return st.code;
-    if (inclusive_max_i32(st, c->tmp, c->lastsrc.p, V, s)) return st.code;      // last source <= v that has records
     uint32_t total = 0;
+    int32_t span = 0;
     ICL_CUDA(st, d2h(&total, c->eoff.p + V, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
     c->n_edges = total;
+    c->max_span = span;
+    if (span >= 65536) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 65535 points inside one mg1-row window of a chromosome pair");
     if (c->edges.reserve(st, (size_t)total + 2 * ICL_EDGE_CHUNK + 16)) return st.code;
     const uint32_t *eoff = c->eoff.p;
     uint2 *edges = c->edges.p;
-    int32_t *stats = c->stats.p;
-    const int32_t *itemof = c->itemof.p;
-    const int64_t *off = c->d_pair_off.p;
-    ICL_CUDA(st, dev_memset(c->stats.p + 3, 0, sizeof(int32_t), s));
 #ifndef ICL_EMU
     if (V > 0) {
-        k_edges_tile<true><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, lastsrc, eoff, edges, off, stats);
+        k_edges_tile<true><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, eoff, edges, c->d_pair_off.p, stats);
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
+    const int32_t *itemof = c->itemof.p;
+    const int64_t *off = c->d_pair_off.p;
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t e = eoff[v];
         if (eoff[v + 1] == e) return;
         int32_t it = itemof[v];
         int64_t a = off[it >= P ? it - P : it] + (it >= P ? n : 0);
-        int64_t prev = v > 0 ? lastsrc[v - 1] : -1;
-        if (prev < a) prev = a;
-        uint32_t adv = (uint32_t)(v - prev);
-        int32_t span = 0;
+        const uint32_t srel = (uint32_t)(v - a) << 8;
         ee.run(v, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
-            span = k - (int32_t)v;                    // candidates are visited in increasing position
-            edges[e++] = make_uint2(((uint32_t)span & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
-                                    ((uint32_t)sc & 0xffu) | (adv << 8));
-            adv = 0;
+            edges[e++] = make_uint2(((uint32_t)(k - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                                    ((uint32_t)sc & 0xffu) | srel);
         });
-        // largest distance a source reaches ahead: sizes the shared-memory window of the DP kernel.
-        // Monotonic max: the plain read filters almost every atomic away.
-        if (span > stats[3]) atomic_max_i32(&stats[3], span);
     }));
 #endif
-    // row table for the wave kernel: first record and first source with records of every dense row, and the
-    // largest number of points inside (64 + mg1) consecutive rows (sizes its shared-memory window)
-    const int64_t R2 = 2 * c->R;
-    if (c->rowtab.reserve(st, R2 + 2)) return st.code;
-    {
-        int2 *rowtab = c->rowtab.p;
-        const int32_t *rowptr = c->rowptr.p;
-        const int32_t reach = 64 + c->prm.mg1;
-        ICL_CUDA(st, dev_memset(c->stats.p + 2, 0, sizeof(int32_t), s));
-        ICL_CUDA(st, foreach(s, R2, ICL_LAMBDA(int64_t g) {
-            int32_t v0 = rowptr[g], v1 = g + 1 < R2 ? rowptr[g + 1] : v0;
-            uint32_t es = eoff[v0];
-            int32_t first = -1;
-            if (v1 > v0 && eoff[v1] > es) {                     // first source of the row whose records start at es
-                int32_t lo = v0, hi = v1 - 1;
-                while (lo < hi) {
-                    int32_t mid = lo + ((hi - lo) >> 1);
-                    if (eoff[mid + 1] > es) hi = mid; else lo = mid + 1;
-                }
-                first = lo;
-            }
-            rowtab[g] = make_int2((int32_t)es, first);
-            const int64_t top = (g < R2 / 2 ? R2 / 2 : R2) - 1;          // stay inside the forward / mirrored half
-            int64_t g2 = g + reach < top ? g + reach : top;
-            int32_t w = rowptr[g2] - v0;
-            if (w > stats[2]) atomic_max_i32(&stats[2], w);
-        }));
-    }
-    int32_t span2[2] = {0, 0};
-    ICL_CUDA(st, d2h(span2, c->stats.p + 2, 2 * sizeof(int32_t), s));
-    ICL_CUDA(st, dev_sync(s));
-    int32_t span = span2[1];
-    c->wave_span = span2[0];
-    c->max_span = span;
-    if (span >= 65536) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 65535 points inside one mg1-row window of a chromosome pair");
+    (void)P;
     return 0;
 }
 
@@ -812,10 +767,10 @@ ICL_HD void chain_generic_item(const ChainArgs &A, int64_t j) {
     bool uv = false, broken = false;
     for (uint32_t e = A.eoff[a], e1 = A.eoff[b]; e < e1; e++) {
         uint2 rec = A.edges[e];
-        uint32_t adv = rec.y >> 8;
-        if (adv) {                                               // next source that has candidates
+        const int64_t nv = a + (rec.y >> 8);
+        if (nv != v) {                                           // next source that has candidates
             if (uv) A.used[v] = 1;
-            v += adv;
+            v = nv;
             Sv = A.S[v];
             dv = (Sv != A.G[v]) ? A.pd[v].y : 1;
             rootv = (Sv != A.G[v]) ? A.root[v] : (int32_t)v;
@@ -869,7 +824,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 // One CTA per (pair, direction) item: warp 0 lane 0 is the executor, warp 1 the helper.
 //   ring[RS]  : 16-byte slots {score, depth | used-as-source flag, pred, tree root} of the points inside the window
 //   ering     : the item's edge records, streamed by TMA in 4 KB chunks (4-deep), consumed strictly in order
-template <bool BATCH>
+template <bool BATCH, bool DBG>
 __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
     extern __shared__ __align__(128) unsigned char dyn[];
     uint2 *ering = (uint2 *)dyn;                                           // ICL_EDGE_NCH * ICL_EDGE_CHUNK records
@@ -896,31 +851,35 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         if (BATCH) {
             // ------------------------------------------------------------ executor warp: 32 records per round
             // Lane l replays record e + l speculatively against the ring as it stands at the start of the round.
+            // * a record names its source (srel), so every lane finds its operands with two shared-memory loads;
             // * the sweep state inside a source (gap, row_old, break — collinearity.py:81-93) is resolved with
-            //   segmented warp scans over the would-update flags (legal: SURVEY.md A.3, the break position only
+            //   one segmented warp scan over the would-update flags (legal: SURVEY.md A.3, the break position only
             //   depends on the records before it);
             // * a lane is stale if an earlier lane of the round really updates the slot it read as its source or
-            //   as its target (claim table: atomicMin of the lane id per ring slot).  The round commits the
-            //   records before the first stale lane — lane 0 is never stale — and restarts at that lane, so
-            //   every record is evaluated exactly as in the reference's sequential order.
+            //   as its target.  Claim table: atomicMax of {round, 31 - lane} per ring slot — the round stamp makes
+            //   older claims lose, so the table is never reset.  The round commits the records before the first
+            //   stale lane — lane 0 is never stale — and restarts at that lane, so every record is evaluated
+            //   exactly as in the reference's sequential order.
             uint32_t *claim = (uint32_t *)(ring + A.RS);
             const uint32_t FULLM = 0xffffffffu;
             const int32_t mg2 = A.mg2;
-            for (uint32_t i = lane; i < (uint32_t)A.RS; i += 32) claim[i] = 0xffffffffu;
+            for (uint32_t i = lane; i < (uint32_t)A.RS; i += 32) claim[i] = 0u;
             uint32_t loaded = a;
             while (loaded < b && loaded <= a + (uint32_t)A.span) loaded = ctl_loaded;
             __threadfence_block();
             __syncwarp();
-            // state of the source that is open when a round starts (all lanes hold the same values)
+            // sweep state of the source that is open when a round starts (all lanes hold the same values)
             uint32_t cur_v = a;
-            int4 sl0 = ring[a & M];
-            int32_t cSv = sl0.x, cdv = sl0.y, croot = sl0.w, cgap = mg2, cdr = 0;
+            int32_t cgap = mg2, cdr = 0;
             bool cbroken = false;
             uint32_t e = e0, ready = c0 * ICL_EDGE_CHUNK, pubchunk = c0, rounds = 0;
-            const long long t_begin = A.dbg ? clock64() : 0;
+            const uint32_t upto = (2u << lane) - 1u;              // lanes 0..lane
+            const uint32_t ringlim = (uint32_t)A.RS - 64u;
+            const long long t_begin = DBG ? clock64() : 0;
             long long t_wait = 0;
             while (e < e1) {
                 __syncwarp();                                     // commits of the previous round are visible
+                ++rounds;
                 const uint32_t bend = e + 32 < e1 ? e + 32 : e1;
                 if (e / ICL_EDGE_CHUNK != pubchunk) {             // chunks before the one holding e are consumed
                     pubchunk = e / ICL_EDGE_CHUNK;
@@ -929,60 +888,67 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 }
                 while (ready < bend) {                            // TMA bytes of the chunks this round touches
                     const uint32_t ch = ready / ICL_EDGE_CHUNK;
-                    const long long tw = A.dbg ? clock64() : 0;
+                    const long long tw = DBG ? clock64() : 0;
                     mbar_wait(&ebar[ch % ICL_EDGE_NCH], ((ch - c0) / ICL_EDGE_NCH) & 1u);
-                    if (A.dbg) t_wait += clock64() - tw;
+                    if (DBG) t_wait += clock64() - tw;
                     ready = (ch + 1) * ICL_EDGE_CHUNK;
                 }
                 bool valid = e + lane < bend;
                 const uint2 rec = ering[(e + lane) & EM];
-                const uint32_t adv = valid ? rec.y >> 8 : 0u;
-                // source position of every lane: inclusive scan of the advances
-                uint32_t pre = adv;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULLM, pre, d);
-                    if (lane >= d) pre += t;
-                }
-                const uint32_t v = cur_v + pre;
-                const uint32_t firstmask = __ballot_sync(FULLM, adv != 0);
-                const uint32_t upto = (2u << lane) - 1u;          // lanes 0..lane
-                const uint32_t below = firstmask & upto;
-                const int head = below ? 31 - __clz(below) : -1;  // lane that opens my source, -1: open since before the round
-                const int seg_start = head < 0 ? 0 : head;
-                const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
+                const uint32_t ypre = ering[(e + lane - 1) & EM].y;            // previous record (lane 0: unused)
+                const uint32_t v0 = a + (ering[e & EM].y >> 8);               // first source of the round (broadcast)
+                const uint32_t v = a + (rec.y >> 8);
                 const uint32_t k = v + (rec.x & 0xffffu);
+                // operands: issued first, everything up to `up` overlaps their latency (re-read in the rare case
+                // that the staging check below fails)
+                const uint32_t vslot = v & M, slot = k & M;
+                int4 sl = ring[vslot];
+                int32_t tx = ring[slot].x;
+                const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
                 // a round only reaches as far as the ring can hold behind its first source
-                const uint32_t v0 = __shfl_sync(FULLM, v, 0);
-                valid = valid && k < v0 + (uint32_t)A.RS - 64u;
+                valid = valid && k < v0 + ringlim;
                 const uint32_t kmax = __reduce_max_sync(FULLM, valid ? k : 0u);
+                // segments = records of one source; head = lane that opens mine, -1: open since before the round
+                const bool first = lane == 0 ? (v != cur_v) : ((rec.y ^ ypre) >> 8) != 0;
+                const uint32_t firstmask = __ballot_sync(FULLM, first);
+                const uint32_t below = firstmask & upto;
+                const int head = below ? 31 - __clz(below) : -1;
+                const int seg_start = head < 0 ? 0 : head;
+                const int segpos = lane - seg_start;
+                const bool need8 = __any_sync(FULLM, valid && segpos >= 8);
                 if (loaded < b && loaded <= kmax) {               // the targets are not staged yet
                     __threadfence_block();
                     if (lane == 0) ctl_retired = v0;              // everything before the round's first source is final
-                    const long long tw = A.dbg ? clock64() : 0;
+                    const long long tw = DBG ? clock64() : 0;
                     do { loaded = ctl_loaded; } while (loaded < b && loaded <= kmax);
-                    if (A.dbg) t_wait += clock64() - tw;
+                    if (DBG) t_wait += clock64() - tw;
                     __threadfence_block();
+                    sl = ring[vslot];
+                    tx = ring[slot].x;
                 }
-                // operands
-                int32_t Sv = cSv, dv = cdv, rootv = croot;
-                if (head >= 0) {
-                    const int4 sl = ring[v & M];
-                    Sv = sl.x; dv = sl.y; rootv = sl.w;
-                }
-                const uint32_t slot = k & M;
+                const int32_t Sv = sl.x, dv = sl.y & 0x7fffffff, rootv = sl.w;
                 const int32_t cand = Sv + sc;
-                const bool up = valid && sc > 0 && ring[slot].x < cand;      // :87, ignoring the break for now
+                const bool up = valid && sc > 0 && tx < cand;                // :87, ignoring the break for now
                 // sweep state before each record: ONE segmented scan over the would-update flags, min(dc) and
-                // max(dr) packed as two 16-bit halves {255 - dc, dr} combined with a per-halfword max
+                // max(dr) packed as two 16-bit halves {255 - dc, dr} combined with a per-halfword max; the steps
+                // beyond the longest segment of the round are skipped (warp-uniform)
                 uint32_t pk = up ? (((uint32_t)(255 - dc) << 16) | (uint32_t)dr) : 0u;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t po = __shfl_up_sync(FULLM, pk, d);
-                    if (lane - d >= seg_start) pk = __vmaxu2(pk, po);
+                {
+                    uint32_t po = __shfl_up_sync(FULLM, pk, 1);
+                    if (segpos >= 1) pk = __vmaxu2(pk, po);
+                    po = __shfl_up_sync(FULLM, pk, 2);
+                    if (segpos >= 2) pk = __vmaxu2(pk, po);
+                    po = __shfl_up_sync(FULLM, pk, 4);
+                    if (segpos >= 4) pk = __vmaxu2(pk, po);
+                    if (need8) {
+                        po = __shfl_up_sync(FULLM, pk, 8);
+                        if (segpos >= 8) pk = __vmaxu2(pk, po);
+                        po = __shfl_up_sync(FULLM, pk, 16);
+                        if (segpos >= 16) pk = __vmaxu2(pk, po);
+                    }
                 }
                 uint32_t pe = __shfl_up_sync(FULLM, pk, 1);
-                if (lane - 1 < seg_start) pe = 0u;
+                if (segpos < 1) pe = 0u;
                 const int32_t gx = 255 - (int32_t)(pe >> 16), gy = (int32_t)(pe & 0xffffu);
                 const int32_t ig = head < 0 ? cgap : mg2, idr = head < 0 ? cdr : 0;
                 const int32_t gap_b = gx < ig ? gx : ig, dr_b = gy > idr ? gy : idr;
@@ -992,18 +958,16 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 const bool dead = (brkmask & segmask) != 0 || (head < 0 && cbroken);
                 const bool u = up && !dead;
                 // stale lanes: an earlier lane of the round updates a slot this lane read
-                if (u) atomicMin(&claim[slot], (uint32_t)lane);
+                const uint32_t stamp = (rounds << 5) | (uint32_t)(31 - lane);
+                if (u) atomicMax(&claim[slot], stamp);
                 __syncwarp();
-                const uint32_t c2 = claim[slot];
-                const uint32_t c1 = head >= 0 ? claim[v & M] : 0xffffffffu;
-                const bool stale = c1 < (uint32_t)lane || c2 < (uint32_t)lane;
-                __syncwarp();
-                if (u) claim[slot] = 0xffffffffu;
+                const uint32_t c2 = claim[slot], c1 = claim[vslot];
+                const bool stale = (c2 > stamp) | (c1 > stamp);
                 const uint32_t stop = __ballot_sync(FULLM, stale || !valid);
                 const int f = stop ? __ffs(stop) - 1 : 32;        // records committed this round (>= 1)
                 if (lane < f && u) {
                     ring[slot] = make_int4(cand, dv + 1, (int32_t)v, rootv);
-                    ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;  // used-as-source (same value from every lane of a source)
+                    ring[vslot].y = dv | (int32_t)ICL_USED_FLAG;  // used-as-source (same value from every lane of a source)
                 }
                 // the source that is open after the last committed record
                 const int32_t gap_a = u ? (dc < gap_b ? dc : gap_b) : gap_b, dr_a = u ? dr : dr_b;
@@ -1012,18 +976,15 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 cdr = (int32_t)((st >> 8) & 255u);
                 cbroken = (st >> 16) != 0;
                 cur_v = __shfl_sync(FULLM, v, f - 1);
-                cSv = __shfl_sync(FULLM, Sv, f - 1);
-                cdv = __shfl_sync(FULLM, dv, f - 1);
-                croot = __shfl_sync(FULLM, rootv, f - 1);
                 e += (uint32_t)f;
-                if ((++rounds & 7u) == 0) {                       // let the helper retire finished points
+                if ((rounds & 7u) == 0) {                         // let the helper retire finished points
                     __threadfence_block();
                     if (lane == 0) ctl_retired = cur_v;
                 }
             }
             __syncwarp();
             __threadfence_block();
-            if (lane == 0 && A.dbg) {
+            if (DBG && lane == 0) {
                 A.dbg[4 * blockIdx.x] = rounds; A.dbg[4 * blockIdx.x + 1] = clock64() - t_begin;
                 A.dbg[4 * blockIdx.x + 2] = t_wait; A.dbg[4 * blockIdx.x + 3] = e1 - e0;
             }
@@ -1057,10 +1018,10 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
             for (; e < cend; e++) {
                 const uint2 rec = nxt;
                 nxt = ering[(e + 1) & EM];                        // next record early (unused at a chunk end)
-                const uint32_t adv = rec.y >> 8;
-                if (adv) {                                        // next source that has candidates
+                const uint32_t nv = a + (rec.y >> 8);
+                if (nv != v) {                                    // next source that has candidates
                     ring[v & M].y = (dv1 - 1) | (int32_t)uv;      // used-as-source flag of the finished source
-                    v += adv;
+                    v = nv;
                     if (loaded < b && loaded <= v + span) {       // the new source's window is not staged yet:
                         __threadfence_block();                    // retire everything before v so the helper can move on
                         ctl_retired = v;
@@ -1147,270 +1108,6 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         if (!progress) __nanosleep(100);
     }
 }
-// ------------------------------------------------------------------------------------------------
-// k_chain_wave: the same order-exact sweep with 32 rows of the item in flight (one lane per row, lock-step).
-//
-// Which sources may run concurrently?  Two sources interact only if one is a candidate of the other or they
-// share a candidate, i.e. only if their rows are less than mg1 apart and their columns less than mg2 apart.
-// A source at (row r, column c) may therefore run as soon as every earlier row still in flight has finished
-// all of its sources with column < c + mg2, and its own row everything left of c (validated
-// there against the reference with a randomised asynchronous pipeline).  Sources that run in the same step
-// have disjoint windows, and every conflicting pair of sources runs in the reference's order, so the result is
-// the reference's bit for bit.
-//
-// Lane l owns the dense rows l, l+32, l+64, ... in increasing order.  With the progress key
-//     K_l = row_l * B + column of the lane's next source that has candidates        (B > any column + mg2)
-// the condition for lane l is   min over d = 1..31 of ( K_{(l-d) mod 32} + d * B )  >=  K_l + mg2 :
-// lane l-d holds row r-d (compare columns), a later row r-d+32 (always true) or an earlier row r-d-32
-// (always false: row r-d has not started).  The min-plus is a 5-step cyclic scan with warp shuffles.
-// The lane with the smallest key always passes, so the wave never stalls.
-//
-// Shared memory: ring[RS] window slots (as k_chain_ring), colring[RS] source columns, rowring[256] row table
-// {first record, first source with records, first point}, ering edge records (TMA chunks).  The helper warp
-// stages all four ahead of the wave and writes finished points back behind it.
-// ------------------------------------------------------------------------------------------------
-#define ICL_WAVE_ROWS 256            // staged row-table entries (power of two)
-#define ICL_WAVE_REC 6               // lock-step record iterations per round
-
-struct WaveArgs {
-    ChainArgs c;
-    const int32_t *X2, *rowptr, *nrows;
-    const int2 *rowtab;
-    const int64_t *rb;
-    int64_t R;
-};
-
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-__global__ void __launch_bounds__(64) k_chain_wave(WaveArgs W) {
-    const ChainArgs &A = W.c;
-    extern __shared__ __align__(128) unsigned char dyn[];
-    uint2 *ering = (uint2 *)dyn;
-    int4 *ring = (int4 *)(dyn + ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2));
-    int4 *rowring = ring + A.RS;
-    int32_t *colring = (int32_t *)(rowring + ICL_WAVE_ROWS);
-    __shared__ volatile uint32_t ctl_loaded, ctl_retired, ctl_eloaded, ctl_emin, ctl_rowloaded, ctl_xmin;
-    __shared__ __align__(8) uint64_t ebar[ICL_EDGE_NCH];
-    const int32_t it = A.order[blockIdx.x];
-    const int32_t p = it >= A.P ? it - A.P : it;
-    const uint32_t a = (uint32_t)(A.off[p] + (it >= A.P ? A.n : 0)), b = (uint32_t)(A.off[p + 1] + (it >= A.P ? A.n : 0));
-    if (a == b) return;
-    const int64_t rbase = W.rb[p] + (it >= A.P ? W.R : 0);
-    const uint32_t nrows = (uint32_t)W.nrows[p];
-    const uint32_t e0 = A.eoff[a], e1 = A.eoff[b];
-    const uint32_t c0 = e0 / ICL_EDGE_CHUNK;
-    const uint32_t M = (uint32_t)A.RS - 1, EM = ICL_EDGE_NCH * ICL_EDGE_CHUNK - 1, RM = ICL_WAVE_ROWS - 1;
-    if (threadIdx.x == 0) {
-        ctl_loaded = a; ctl_retired = a; ctl_eloaded = e0; ctl_emin = e0; ctl_rowloaded = 0; ctl_xmin = 0;
-        for (int i = 0; i < ICL_EDGE_NCH; i++) mbar_init(&ebar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t FULL = 0xffffffffu;
-    if (threadIdx.x < 32) {
-        // ---------------------------------------------------------------- the wave: one lane per row in flight
-        // 32-bit progress keys: (row - xbase) << 20 | column, xbase = last published minimum row of the wave.
-        // A lane only enters rows less than 3000 above xbase, so entered lanes have exact keys; lanes further
-        // ahead are clamped to row 4000, which is later than every entered row, exactly what they are.
-        const uint32_t B = 1u << 20, KINF = 0xFC000000u;
-        const int32_t mg2 = A.mg2;
-        uint32_t x = (uint32_t)lane;                      // dense row owned right now
-        uint32_t e = e0, e_end = e0, v = a, rs = a;       // next record, end of the row's records, source, row start
-        bool need_row = true, done = false, in_src = false, fresh = false;
-        int32_t Sv = 0, dv = 0, rootv = 0, gap = 0, dr_old = 0;
-        bool uv = false, broken = false;
-        uint32_t round = 0;
-        const long long t_start = clock64();
-        uint32_t loaded = a, rowloaded = 0, eloaded = e0, xbase = 0;
-        uint32_t col = 0;                                 // column of source v (valid when staged)
-        bool staged = false;
-        while (true) {
-            __syncwarp();                                 // ring stores of the previous round are visible to every lane
-            // 0. control words of the helper, every 4th round (stale values only delay a lane)
-            if ((round & 3u) == 0) {
-                loaded = ctl_loaded; rowloaded = ctl_rowloaded; eloaded = ctl_eloaded; xbase = ctl_xmin;
-                __threadfence_block();
-                if (__all_sync(FULL, done)) break;
-            }
-            // 1. a lane between rows tries to enter its next row (one attempt per round)
-            if (need_row && !done) {
-                if (x >= nrows) done = true;
-                else if (x + 1 < rowloaded && x - xbase < 3000u) {   // row table staged, not too far ahead of the wave
-                    const int4 ent = rowring[x & RM];
-                    if (ent.y < 0) x += 32;                          // no source of this row has candidates
-                    else {
-                        e = (uint32_t)ent.x; v = (uint32_t)ent.y; rs = (uint32_t)ent.z;
-                        e_end = (uint32_t)rowring[(x + 1) & RM].x;
-                        need_row = false; fresh = true; staged = false;   // the first record's adv is replaced by v
-                    }
-                }
-            }
-            // 2. progress key of the lane's next (or current) source
-            const uint32_t elim = e_end < eloaded ? e_end : eloaded;  // records of the row that are in the edge ring
-            if (!staged && !done && !need_row && (v + (uint32_t)A.span < loaded || loaded >= b)) {
-                staged = true;
-                col = (uint32_t)colring[v & M];
-            }
-            const uint32_t xr = x - xbase < 4000u ? x - xbase : 4000u;
-            const uint32_t K = done ? KINF : (xr << 20) | (staged ? col : 0u);
-            // speculative operand loads (always valid addresses) so that they overlap the scan
-            const int4 sl = ring[v & M];
-            uint2 rec = ering[e & EM];
-            // 3. cyclic min-plus scan over the other 31 lanes: val = min_d (K[(l-d) mod 32] + d * B)
-            uint32_t val = __shfl_sync(FULL, K, (lane - 1) & 31) + B;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t other = __shfl_sync(FULL, val, (lane - d) & 31) + (uint32_t)d * B;
-                val = other < val ? other : val;
-            }
-            // 4. start the source when allowed, replay up to two of its records
-            if (!in_src && staged && e < elim && val >= K + (uint32_t)mg2) {
-                Sv = sl.x; dv = sl.y; rootv = sl.w;
-                gap = mg2; dr_old = 0; uv = false; broken = false;
-                in_src = true;
-            }
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                if (!(in_src && e < elim)) break;
-                if (r) rec = ering[e & EM];
-                bool close = false;
-                uint32_t adv = rec.y >> 8;
-                if (!fresh && adv) {
-                    close = true;                                     // this record opens the next source of the row
-                } else {
-                    const int32_t dc = rec.x >> 24, dr = (rec.x >> 16) & 255, sc = rec.y & 255;
-                    broken = broken || (dc > gap && dr > dr_old);     // collinearity.py:83-84
-                    const uint32_t slot = (v + (rec.x & 0xffffu)) & M;
-                    const int32_t cand = Sv + sc;
-                    if (!broken && sc > 0 && ring[slot].x < cand) {   // :87 strict <
-                        ring[slot] = make_int4(cand, dv + 1, (int32_t)v, rootv);
-                        uv = true;
-                        gap = dc < gap ? dc : gap;                    // :92
-                        dr_old = dr;                                  // :93
-                    }
-                    e++;
-                    fresh = false;
-                    adv = 0;
-                    if (e >= e_end) close = true;                     // end of the row
-                    else if (e < eloaded) { adv = ering[e & EM].y >> 8; close = adv != 0; }
-                }
-                if (close) {
-                    if (uv) ring[v & M].y = dv | (int32_t)ICL_USED_FLAG;
-                    in_src = false;
-                    staged = false;
-                    if (e >= e_end) { need_row = true; x += 32; }
-                    else { v += adv; fresh = true; }
-                }
-            }
-            // 5. publish the trailing edge of the wave so the helper can retire / refill
-            if ((++round & 7u) == 0) {
-                const uint32_t rmin = __reduce_min_sync(FULL, done ? b : rs);
-                const uint32_t emin = __reduce_min_sync(FULL, done ? e1 : e);
-                const uint32_t xmin = __reduce_min_sync(FULL, done ? nrows : x);
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) { ctl_retired = rmin; ctl_emin = emin; ctl_xmin = xmin; }
-                __syncwarp();                                         // every lane reads the same xbase next time
-            }
-        }
-        __syncwarp();
-        __threadfence_block();
-        if (lane == 0 && A.dbg) { A.dbg[4 * blockIdx.x] = round; A.dbg[4 * blockIdx.x + 1] = clock64() - t_start; }
-        if (lane == 0) { ctl_retired = b; ctl_emin = e1; ctl_xmin = nrows; }
-        return;
-    }
-    // -------------------------------------------------------------------- helper warp
-    uint32_t wb = a, ld = a, rld = 0;
-    uint32_t issued = c0, confirmed = c0;
-    const uint32_t last_chunk = e1 > e0 ? (e1 - 1) / ICL_EDGE_CHUNK : c0;
-    const bool has_edges = e1 > e0;
-    while (wb < b) {
-        uint32_t r = 0, emin = 0, xmin = 0;
-        if (lane == 0) { r = ctl_retired; emin = ctl_emin; xmin = ctl_xmin; }
-        r = __shfl_sync(FULL, r, 0);
-        emin = __shfl_sync(FULL, emin, 0);
-        xmin = __shfl_sync(FULL, xmin, 0);
-        __threadfence_block();
-        bool progress = false;
-        // 1. edge chunks by TMA: issue while a ring slot is free, confirm completed ones in order
-        if (has_edges && lane == 0) {
-            const uint32_t ech = emin / ICL_EDGE_CHUNK;
-            while (issued <= last_chunk && issued < ech + ICL_EDGE_NCH) {
-                uint64_t *bar = &ebar[issued % ICL_EDGE_NCH];
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(bar, ICL_EDGE_CHUNK * (uint32_t)sizeof(uint2));
-                tma_load_1d(ering + (issued % ICL_EDGE_NCH) * ICL_EDGE_CHUNK, A.edges + (size_t)issued * ICL_EDGE_CHUNK,
-                            ICL_EDGE_CHUNK * (uint32_t)sizeof(uint2), bar);
-                issued++;
-            }
-            bool any = false;
-            while (confirmed < issued && mbar_test(&ebar[confirmed % ICL_EDGE_NCH], ((confirmed - c0) / ICL_EDGE_NCH) & 1u)) {
-                confirmed++;
-                any = true;
-            }
-            if (any) {
-                __threadfence_block();
-                ctl_eloaded = confirmed * ICL_EDGE_CHUNK;
-            }
-        }
-        // 2. row table entries {first record, first source with records, first point}
-        {
-            uint32_t rlim = xmin + ICL_WAVE_ROWS;
-            rlim = rlim < nrows + 1 ? rlim : nrows + 1;
-            if (rld < rlim) {
-                for (uint32_t xr = rld + lane; xr < rlim; xr += 32) {
-                    const int2 t = W.rowtab[rbase + xr];
-                    rowring[xr & RM] = make_int4(t.x, t.y, W.rowptr[rbase + xr], 0);
-                }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) ctl_rowloaded = rlim;
-                rld = rlim;
-                progress = true;
-            }
-        }
-        // 3. results of retired points -> HBM (coalesced): score, pred/length, root, used
-        if (r > ld) r = ld;
-        if (r > wb) {
-            for (uint32_t v = wb + lane; v < r; v += 32) {
-                const int4 sl = ring[v & M];
-                const int32_t g = A.G[v];
-                A.S[v] = sl.x;
-                A.pd[v] = (sl.x != g) ? make_int2(sl.z, sl.y & 0x7fffffff) : make_int2(-1, 1);
-                A.root[v] = sl.w;
-                A.used[v] = (sl.x != g) || (sl.y < 0);
-            }
-            wb = r;
-            progress = true;
-        }
-        // 4. stage the next points of the window: score = grading, path length 1 (get_matrix :35-37), columns
-        uint32_t lim = wb + (uint32_t)A.RS;
-        lim = lim < b ? lim : b;
-        if (ld < lim) {
-            __syncwarp();
-            for (uint32_t v = ld + lane; v < lim; v += 32) {
-                ring[v & M] = make_int4(A.G[v], 1, -1, (int32_t)v);
-                colring[v & M] = W.X2[v];
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) ctl_loaded = lim;
-            ld = lim;
-            progress = true;
-        }
-        if (!progress) __nanosleep(40);
-    }
-}
 #endif
 
 
@@ -1433,22 +1130,6 @@ static int phase_chain(icl_ctx *c) {
     if (P == 0 || n == 0) return 0;
 #ifndef ICL_EMU
     if (c->chain_mode != 0) {
-        // ---- wave kernel: needs the row table and a window over (64 + mg1) rows
-        if (c->chain_mode == 2 && c->wave_span + 256 <= 8192 && c->bits2 <= 19) {   // 32-bit progress keys: columns < 2^19
-            int64_t RS = 512;
-            while (RS < (int64_t)c->wave_span + 256) RS <<= 1;
-            A.RS = (int32_t)RS;
-            WaveArgs W;
-            W.c = A; W.X2 = c->X2.p; W.rowptr = c->rowptr.p; W.nrows = c->d_nrows.p; W.rowtab = c->rowtab.p;
-            W.rb = c->d_rb.p; W.R = c->R;
-            size_t smem = (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2) + (size_t)RS * sizeof(int4) +
-                          (size_t)ICL_WAVE_ROWS * sizeof(int4) + (size_t)RS * sizeof(int32_t);
-            ICL_CUDA(st, cudaFuncSetAttribute(k_chain_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            k_chain_wave<<<(unsigned)(2 * P), 64, smem, s>>>(W);
-            ICL_CUDA(st, cudaGetLastError());
-            c->chain_kernel = 2;
-            return 0;
-        }
         // ---- ring kernels: window span + what a round / the executor may run ahead of the last retire point
         int64_t want = (int64_t)c->max_span + 256;
         int64_t RS = 512;
@@ -1458,13 +1139,12 @@ static int phase_chain(icl_ctx *c) {
             const bool batch = c->chain_mode == 1;
             size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2) +
                           (batch ? (size_t)RS * sizeof(uint32_t) : 0);
-            if (batch) {
-                ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                k_chain_ring<true><<<(unsigned)(2 * P), 64, smem, s>>>(A);
-            } else {
-                ICL_CUDA(st, cudaFuncSetAttribute(k_chain_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                k_chain_ring<false><<<(unsigned)(2 * P), 64, smem, s>>>(A);
-            }
+            auto launch = [&](void (*kern)(ChainArgs)) {
+                ICL_CUDA(st, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                kern<<<(unsigned)(2 * P), 64, smem, s>>>(A);
+                return 0;
+            };
+            if (launch(batch ? (A.dbg ? k_chain_ring<true, true> : k_chain_ring<true, false>) : k_chain_ring<false, false>)) return st.code;
             ICL_CUDA(st, cudaGetLastError());
             c->chain_kernel = batch ? 1 : 3;
             return 0;

@@ -292,7 +292,7 @@ class IclEngine:
         c = np.zeros(6, np.int64)
         self.lib.icl_counters(self.ctx, c.ctypes.data, 6)
         return dict(edges=int(c[0]), launches_dp=int(c[1]), launches_extract=int(c[2]), rows=int(c[3]),
-                    max_span=int(c[4]), chain_kernel={0: "generic", 1: "ring", 2: "wave", 3: "single"}[int(c[5])])
+                    max_span=int(c[4]), chain_kernel={0: "generic", 1: "ring", 3: "single"}[int(c[5])])
 
     # ---- whole hot path ------------------------------------------------------------------------
     def run_resident(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
