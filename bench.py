@@ -33,7 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DP_BYTES_PER_POINT = 42          # 2 directions x [12 B read + 9 B written]
+EXPORT_BYTES_PER_POINT = 12      # streamed export epilogue of the DP kernel: HBM reads of 2 x score (4 B) + mirror map (4 B);
+                                 # its 8 B/point of writes go to page-locked host memory over PCIe and are not counted
 METRIC = "blast_hits_chained_per_sec"
+NCU_TRAFFIC_C2 = 87.1e6          # bytes per launch of the DP kernel (with its export epilogue) on C2: ncu capture, profiles/r01_chain_ring_ncu_summary.md
 
 
 def peaks():
@@ -284,33 +287,51 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t_res = 0.0
-    blocks = None
-    for _ in range(args.steps):
-        flush_l2()
-        barrier()
-        t0 = time.perf_counter()
-        blocks = step_resident()
-        torch.cuda.synchronize()
-        t_res += time.perf_counter() - t0
+    # device-side clock: CUDA events on the stream the library launches on (host work between the two device phases
+    # leaves that stream idle, so event time and wall time must agree; both are reported)
+    if hasattr(eng, "ctx"):
+        estream = torch.cuda.ExternalStream(int(eng.lib.icl_stream(eng.ctx)), device=torch.device("cuda", local))
+    else:                                    # pipelined lanes: several contexts, no single stream
+        estream = torch.cuda.current_stream()
+
+    def timed(step):
+        wall, evms, out = 0.0, 0.0, None
+        for _ in range(args.steps):
+            flush_l2()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(estream)
+            t0 = time.perf_counter()
+            out = step()
+            e1.record(estream)
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
+            evms += e0.elapsed_time(e1)
+        return wall, evms * 1e-3, out
+
+    t_res, ev_res, blocks = timed(step_resident)
     # ---- e2e: host buffers in, blocks on the host out ----------------------------------------------------------
     for _ in range(2):
         step_e2e()
-    t_e2e = 0.0
-    for _ in range(args.steps):
-        flush_l2()
-        barrier()
-        t0 = time.perf_counter()
-        blocks = step_e2e()
-        torch.cuda.synchronize()
-        t_e2e += time.perf_counter() - t0
+    res_ms = {k: float(np.mean(v)) for k, v in dev_ms.items()}
+    t_e2e, ev_e2e, blocks = timed(step_e2e)
+    # ---- the DP kernel alone (export epilogue off), for the roofline note: untimed extra passes -------------------
+    dp_only_ms = None
+    if getattr(eng, "stream_rank", False):
+        eng.stream_rank = False
+        step_resident()
+        dev_ms.clear()
+        for _ in range(3):
+            step_resident()
+        dp_only_ms = float(np.mean(dev_ms["chain"]))
+        eng.stream_rank = True
     clocks = sampler.stop() if rank == 0 else None
     counters = eng.counters()
 
     if world > 1:
-        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([t_res, t_e2e, ev_res, ev_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_res, t_e2e = t.tolist()
+        t_res, t_e2e, ev_res, ev_e2e = t.tolist()
         nb = torch.tensor([len(blocks)], dtype=torch.int64, device="cuda")
         dist.all_reduce(nb)
         n_blocks = int(nb.item())
@@ -319,12 +340,15 @@ def main():
 
     if rank == 0:
         peak, peak_kind = peaks()
-        chain_ms = float(np.mean(dev_ms["chain"]))
-        achieved = DP_BYTES_PER_POINT * n_local / (chain_ms * 1e-3) / 1e9
+        chain_ms = res_ms["chain"]
+        streamed = bool(getattr(eng, "stream_rank", False)) and counters["chain_kernel"] == "ring"
+        bytes_pp = DP_BYTES_PER_POINT + (EXPORT_BYTES_PER_POINT if streamed else 0)
+        achieved = bytes_pp * n_local / (chain_ms * 1e-3) / 1e9
         d2h = 16 * n_local + int(len(blocks) * 64 + len(blocks.loc1) * 12)
         line = {
             "metric": METRIC, "value": total_points * args.steps / t_res, "unit": "hits/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
+            "ms_per_step_cuda_events": 1e3 * ev_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: BASELINE.json config 2 (Vitis-sized self comparison), one comparison per GPU",
                        "graded_hits": total_points, "chromosome_pairs": total_pairs, "blocks": n_blocks,
@@ -334,17 +358,25 @@ def main():
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
                        "tie_order": "numpy argsort on host between the two device phases (reference-exact)"},
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "ms_per_step_cuda_events": 1e3 * ev_e2e / args.steps,
                     "h2d_bytes_per_step": 16 * n_local + 8 * n_local, "d2h_bytes_per_step": d2h},
             "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
-            "roofline": {"kernel": "chain DP (both directions)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "k_chain_ring: chain DP, both directions" + (" + streamed score export" if streamed else ""),
+                         "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 70.6e6 if (args.workload == "C2" and world == 1) else None,
+                         "traffic": NCU_TRAFFIC_C2 if (args.workload == "C2" and world == 1) else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_chain_ring on this "
-                                           "workload (profiles/r01_chain_batch_ncu_summary.md)",
+                                           "workload (profiles/r01_chain_ring_ncu_summary.md)",
                          "peak_source": peak_kind,
-                         "kernel_ms": chain_ms, "algorithmic_bytes": DP_BYTES_PER_POINT * n_local,
+                         "kernel_ms": chain_ms, "algorithmic_bytes": bytes_pp * n_local,
+                         "bytes_per_point": bytes_pp,
+                         "dp_only": None if dp_only_ms is None else {
+                             "kernel_ms": dp_only_ms, "algorithmic_bytes": DP_BYTES_PER_POINT * n_local,
+                             "achieved": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9,
+                             "frac": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9 / peak,
+                             "what": "same kernel with the export epilogue off (ICL_B200_STREAM=0), 3 extra untimed passes"},
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
-            "phase_ms": {k: float(np.mean(v)) for k, v in dev_ms.items()},
+            "phase_ms": res_ms,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }

@@ -129,6 +129,23 @@ int icl_upload_from(icl_ctx *dst, icl_ctx *src, int32_t pair_lo, int32_t pair_hi
  */
 int icl_dp(icl_ctx *ctx, const icl_params *params, int32_t *key_fwd, int32_t *key_rev);
 
+/*
+ * Streaming form of icl_dp: same work, but the call returns as soon as the DP kernel is launched and the scores
+ * arrive item by item.  An item is one (pair, direction): id = dir * n_pairs + pair.  When an item is finished the
+ * kernel writes its segment of key_fwd / key_rev (same layout and meaning as in icl_dp) straight into the caller's
+ * buffers and then raises done_flags[id], so the host can run numpy's argsort on finished segments while heavier
+ * chromosome pairs are still being chained (the reference does the same sort after each pair's DP,
+ * wgdi/collinearity.py:49,60; here it overlaps the DP of the other pairs).
+ *   key_fwd, key_rev, done_flags: page-locked memory from icl_host_alloc (the device writes to it directly);
+ *   done_flags has 2 * n_pairs slots, all 0 when the call returns except those of empty pairs; a reader that
+ *   sees done_flags[id] != 0 may read that item's segment (forward items: key_fwd, ids >= n_pairs: key_rev).
+ * When the shared-memory DP kernel cannot be used (oversized window) the call degrades to icl_dp and raises all
+ * flags before returning.  icl_dp_end waits for the device and must precede icl_extract; icl_layout may be called
+ * in between (the layout is final once icl_dp_begin returns).
+ */
+int icl_dp_begin(icl_ctx *ctx, const icl_params *params, int32_t *key_fwd, int32_t *key_rev, int32_t *done_flags);
+int icl_dp_end(icl_ctx *ctx);
+
 /* Layout produced by icl_dp: pair_off[n_pairs + 1] (points of pair p are sorted positions
  * pair_off[p] .. pair_off[p+1]) and perm[n_points] (upload index of each sorted position).
  * Either pointer may be NULL. */
@@ -174,6 +191,10 @@ int icl_timings(icl_ctx *ctx, double *ms, int32_t n_slots);
  * [2] kernels launched by icl_extract, [3] total dense rows, [4] largest window span (positions),
  * [5] DP kernel used (1 = shared-memory ring, 0 = generic). */
 int icl_counters(icl_ctx *ctx, int64_t *out, int32_t n_slots);
+
+/* The CUDA stream (cudaStream_t) every kernel and copy of `ctx` is issued on, for callers that bracket calls with
+ * their own CUDA events (bench.py).  NULL in the emulation. */
+void *icl_stream(icl_ctx *ctx);
 
 /* "cuda" for the real library.  (A CPU emulation of the kernel bodies exists for the test-suite
  * only and reports "emu"; wgdi_b200 refuses to load it.) */

@@ -52,6 +52,8 @@ def _declare(lib):
     lib.icl_pair_counts.argtypes = [vp, vp]
     lib.icl_upload_from.argtypes = [vp, vp, i32, i32]
     lib.icl_dp.argtypes = [vp, C.POINTER(icl_params), vp, vp]
+    lib.icl_dp_begin.argtypes = [vp, C.POINTER(icl_params), vp, vp, vp]
+    lib.icl_dp_end.argtypes = [vp]
     lib.icl_layout.argtypes = [vp, vp, vp]
     lib.icl_extract.argtypes = [vp, vp, vp, i32, C.POINTER(icl_blocks)]
     lib.icl_free_blocks.argtypes = [C.POINTER(icl_blocks)]
@@ -59,12 +61,14 @@ def _declare(lib):
     lib.icl_debug_dp.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.icl_timings.argtypes = [vp, vp, i32]
     lib.icl_counters.argtypes = [vp, vp, i32]
+    lib.icl_stream.argtypes = [vp]
+    lib.icl_stream.restype = vp
     return lib
 
 
 EXPORTS = ("icl_backend", "icl_create", "icl_destroy", "icl_last_error", "icl_host_alloc", "icl_host_free",
-           "icl_upload", "icl_pair_counts", "icl_upload_from", "icl_dp", "icl_layout", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
-           "icl_counters")
+           "icl_upload", "icl_pair_counts", "icl_upload_from", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
+           "icl_counters", "icl_stream")
 
 
 def load():

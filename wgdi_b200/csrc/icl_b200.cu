@@ -68,6 +68,8 @@ struct icl_ctx {
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
     int32_t chain_mode = 1;          // 1 = batch ring kernel (default), 3 = single-executor ring kernel, 0 = generic (env ICL_B200_CHAIN)
     Buf<long long> chain_dbg;
+    int32_t *sq_fwd = nullptr, *sq_rev = nullptr, *sq_queue = nullptr;   // streaming targets of the current icl_dp_begin (host, device-visible)
+    bool streamed = false, dp_begun = false;
     int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
@@ -174,6 +176,8 @@ static int input_stats(icl_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // ABI: lifetime
 // ------------------------------------------------------------------------------------------------
+extern "C" void *icl_stream(icl_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
 extern "C" const char *icl_backend(void) {
 #ifndef ICL_EMU
     return "cuda";
@@ -277,7 +281,7 @@ extern "C" int icl_host_free(icl_ctx *c, void *ptr) {
 extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_id, const int32_t *loc1,
                           const int32_t *loc2, const int32_t *grading) {
     if (!c) return ICL_ERR_ARG;
-    c->uploaded = c->dp_done = false;
+    c->uploaded = c->dp_done = c->dp_begun = false;
     if (n < 0 || P < 0 || (n > 0 && (!pair_id || !loc1 || !loc2 || !grading)) || (n > 0 && P == 0))
         return fail(c, ICL_ERR_ARG, "icl_upload: bad argument");
     if (n >= (1ll << 30)) return fail(c, ICL_ERR_LIMIT, "icl_upload: n_points must be < 2^30");
@@ -341,7 +345,7 @@ extern "C" int icl_pair_counts(icl_ctx *c, int64_t *counts) {
 
 extern "C" int icl_upload_from(icl_ctx *dst, icl_ctx *src, int32_t pair_lo, int32_t pair_hi) {
     if (!dst || !src || dst == src) return ICL_ERR_ARG;
-    dst->uploaded = dst->dp_done = false;
+    dst->uploaded = dst->dp_done = dst->dp_begun = false;
     if (!src->uploaded) return fail(dst, ICL_ERR_STATE, "icl_upload_from: the source context has no upload");
     if (dst->device != src->device) return fail(dst, ICL_ERR_ARG, "icl_upload_from: contexts live on different devices");
     if (pair_lo < 0 || pair_hi < pair_lo || pair_hi > src->P) return fail(dst, ICL_ERR_ARG, "icl_upload_from: bad pair range");
@@ -754,6 +758,11 @@ struct ChainArgs {
     int2 *pd;
     uint8_t *used;
     long long *dbg;                  // optional per-item {rounds, cycles} (diagnostics), may be NULL
+    // streaming export (icl_dp_begin): a finished item writes its reversed scores straight into the caller's
+    // page-locked buffers and posts its id, so the host can sort it while heavier items are still running
+    int32_t *hkey_fwd, *hkey_rev;    // device-visible host memory, NULL = no streaming
+    volatile int32_t *hqueue;        // [items] completion flags in host memory
+    const int32_t *mmap;             // forward position -> mirrored position
 };
 
 // the reference sweep over the flat edge stream of one item, on global memory (oversized windows, emulation)
@@ -819,6 +828,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// Epilogue of a finished item (all 64 threads of the CTA): the item's final scores in REVERSED (loc1, loc2) order
+// — the array pandas' nargsort(ascending=False) hands to numpy.argsort — go to the caller's page-locked buffer
+// with coalesced stores over PCIe, then the item's completion flag is raised.
+__device__ __forceinline__ void stream_out(const ChainArgs &A, int32_t it, int32_t p, int tid, int nthreads) {
+    __syncthreads();                                              // the helper has written every S of the item
+    const uint32_t f0 = (uint32_t)A.off[p], f1 = (uint32_t)A.off[p + 1], len = f1 - f0;
+    if (it < A.P) {
+        int32_t *dst = A.hkey_fwd + f0;
+        for (uint32_t i = tid; i < len; i += nthreads) dst[i] = __ldcg(A.S + (f1 - 1 - i));
+    } else {
+        int32_t *dst = A.hkey_rev + f0;
+#pragma unroll 4
+        for (uint32_t i = tid; i < len; i += nthreads) dst[i] = __ldcg(A.S + __ldg(A.mmap + (f1 - 1 - i)));
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        A.hqueue[it] = 1;
+        __threadfence_system();
+    }
 }
 
 // One CTA per (pair, direction) item: warp 0 lane 0 is the executor, warp 1 the helper.
@@ -989,6 +1020,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 A.dbg[4 * blockIdx.x + 2] = t_wait; A.dbg[4 * blockIdx.x + 3] = e1 - e0;
             }
             if (lane == 0) ctl_retired = b;
+            if (A.hqueue) stream_out(A, it, p, threadIdx.x, 64);     // joins the helper warp in the epilogue
             return;
         }
         // ---------------------------------------------------------------- executor (one thread)
@@ -1107,6 +1139,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         }
         if (!progress) __nanosleep(100);
     }
+    if (BATCH && A.hqueue) stream_out(A, it, p, threadIdx.x, 64);
 }
 #endif
 
@@ -1122,6 +1155,8 @@ static int phase_chain(icl_ctx *c) {
     A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
     A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p; A.root = c->root.p;
     A.dbg = nullptr;
+    A.hkey_fwd = A.hkey_rev = nullptr; A.hqueue = nullptr; A.mmap = c->mmap.p;
+    c->streamed = false;
     if (getenv("ICL_B200_CHAIN_DEBUG")) {
         if (c->chain_dbg.reserve(st, 8 * (size_t)P + 8)) return st.code;
         ICL_CUDA(st, dev_memset(c->chain_dbg.p, 0, (8 * (size_t)P + 8) * sizeof(long long), s));
@@ -1137,6 +1172,10 @@ static int phase_chain(icl_ctx *c) {
         if (RS <= 8192) {
             A.RS = (int32_t)RS;
             const bool batch = c->chain_mode == 1;
+            if (batch && c->sq_queue) {                            // icl_dp_begin: items export themselves as they finish
+                A.hkey_fwd = c->sq_fwd; A.hkey_rev = c->sq_rev; A.hqueue = c->sq_queue;
+                c->streamed = true;
+            }
             size_t smem = (size_t)RS * sizeof(int4) + (size_t)ICL_EDGE_NCH * ICL_EDGE_CHUNK * sizeof(uint2) +
                           (batch ? (size_t)RS * sizeof(uint32_t) : 0);
             auto launch = [&](void (*kern)(ChainArgs)) {
@@ -1167,7 +1206,10 @@ static int phase_chain(icl_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // ABI: icl_dp
 // ------------------------------------------------------------------------------------------------
-extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t *score_rev) {
+// Everything icl_dp does.  With `queue` (icl_dp_begin) and the shared-memory ring kernel, finished items write
+// their scores to the caller's buffers themselves and the call returns right after the launch; otherwise the
+// scores are exported and copied after the DP and all completion flags (if any) are raised at the end.
+static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t *score_rev, int32_t *queue) {
     if (!c) return ICL_ERR_ARG;
     if (!c->uploaded) return fail(c, ICL_ERR_STATE, "icl_dp: icl_upload has not succeeded");
     if (!prm || (c->n > 0 && (!score_fwd || !score_rev))) return fail(c, ICL_ERR_ARG, "icl_dp: null argument");
@@ -1179,8 +1221,10 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaSetDevice(c->device));
 #endif
-    c->dp_done = false;
+    c->dp_done = c->dp_begun = false;
     c->prm = *prm;
+    c->sq_fwd = score_fwd; c->sq_rev = score_rev; c->sq_queue = queue;
+    if (queue) for (int64_t i = 0; i < 2 * (int64_t)c->P; i++) queue[i] = 0;
     cudaStream_t s = c->stream;
     const int64_t n = c->n;
     c->timers[ICL_T_SORT].start(s);
@@ -1195,6 +1239,21 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
     c->timers[ICL_T_CHAIN].start(s);
     if (phase_chain(c)) return st.code;
     c->timers[ICL_T_CHAIN].stop(s);
+    c->counters[0] = c->n_edges;
+    c->counters[1] = 11;   // kernels launched by icl_dp (stats excluded): key, decode, pair_off, pair_meta, rowptr x2,
+                           // mirror, rowptr_rev, edge count, edge fill, chain (+ export when not streamed) + CUB passes
+    c->counters[3] = c->R;
+    c->counters_ext[0] = c->max_span;
+    c->counters_ext[1] = c->chain_kernel;
+    if (c->streamed) {                                         // the kernel exports; icl_dp_end waits for it
+        for (int32_t p = 0; p < c->P; p++)                     // empty items never run: nothing to wait for
+            if (c->h_pair_off[p + 1] == c->h_pair_off[p]) queue[p] = queue[c->P + p] = 1;
+        c->timers[ICL_T_EXPORT].start(s); c->timers[ICL_T_EXPORT].stop(s);
+        c->timers[ICL_T_D2H].start(s); c->timers[ICL_T_D2H].stop(s);
+        c->dp_begun = true;
+        return ICL_OK;
+    }
+    c->counters[1] = 12;
     c->timers[ICL_T_EXPORT].start(s);
     if (c->score32.reserve(st, 2 * n)) return st.code;
     {
@@ -1234,19 +1293,37 @@ extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int
             fclose(f);
         }
     }
-    c->counters[0] = c->n_edges;
-    c->counters[1] = 13;   // kernels launched by icl_dp (stats excluded): key, decode, pair_off, pair_meta, rowptr x2,
-                           // mirror, rowptr_rev, edge count, edge fill, chain, export + CUB passes
-    c->counters[3] = c->R;
-    c->counters_ext[0] = c->max_span;
-    c->counters_ext[1] = c->chain_kernel;
+    if (queue) for (int64_t i = 0; i < 2 * (int64_t)c->P; i++) queue[i] = 1;     // not streamed: everything is complete now
+    c->dp_begun = true;
+    c->dp_done = true;
+    return ICL_OK;
+}
+
+extern "C" int icl_dp(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t *score_rev) {
+    return dp_run(c, prm, score_fwd, score_rev, nullptr);
+}
+
+extern "C" int icl_dp_begin(icl_ctx *c, const icl_params *prm, int32_t *key_fwd, int32_t *key_rev, int32_t *done_flags) {
+    if (c && c->P > 0 && !done_flags) return fail(c, ICL_ERR_ARG, "icl_dp_begin: null done_flags");
+    return dp_run(c, prm, key_fwd, key_rev, done_flags);
+}
+
+extern "C" int icl_dp_end(icl_ctx *c) {
+    if (!c) return ICL_ERR_ARG;
+    if (!c->dp_begun) return fail(c, ICL_ERR_STATE, "icl_dp_end: icl_dp_begin has not succeeded");
+    Status &st = c->st;
+    st.code = 0;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaSetDevice(c->device));
+#endif
+    ICL_CUDA(st, dev_sync(c->stream));
     c->dp_done = true;
     return ICL_OK;
 }
 
 extern "C" int icl_layout(icl_ctx *c, int64_t *pair_off, int32_t *perm) {
     if (!c) return ICL_ERR_ARG;
-    if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_layout: icl_dp has not succeeded");
+    if (!c->dp_begun) return fail(c, ICL_ERR_STATE, "icl_layout: icl_dp has not succeeded");
     Status &st = c->st;
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaSetDevice(c->device));

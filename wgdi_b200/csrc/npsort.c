@@ -12,8 +12,10 @@
  * segment from a pthread pool.  The Python side verifies on start-up that the result is identical to
  * numpy.argsort and otherwise falls back to one numpy call per segment (wgdi_b200/engine.py).
  *
- * Python API:  seg_argsort(keys:int32[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads:int) -> 0
+ * Python API:  seg_argsort(keys:int32[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads:int[, flush, flags, timeout]) -> 0
  *   out[off[s] + j] = argsort(keys[off[s]:off[s+1]].astype(int64), kind='quicksort')[j]   (narrowed to int32)
+ * With `flags` (int32[S], page-locked memory the GPU writes: include/icl_b200.h, icl_dp_begin) a segment is sorted
+ * as soon as its flag is raised, i.e. while the DP kernel is still working on other chromosome pairs.
  * The keys cross PCIe as int32 and are widened per segment here: the reference's score column is int64 and
  * numpy's sort kernels (hence the tie permutation) are dtype specific.
  */
@@ -26,28 +28,58 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <time.h>
+
 typedef struct {
     PyArray_ArgSortFunc *fn;
     const int32_t *keys;
     const int64_t *off;
     const int32_t *seg_order;
+    const volatile int32_t *flags;   /* optional: segment s may be read once flags[s] != 0 (written by the GPU) */
     int32_t *out;
     int64_t n_seg;
-    volatile int64_t next;
+    volatile uint8_t *claimed;       /* per position of seg_order */
+    volatile int64_t lo;             /* every position below is claimed */
     volatile int err;
     int flush;
+    double deadline;
 } job_t;
 
-static void *worker(void *vp)
+static double now_s(void)
 {
-    job_t *j = (job_t *)vp;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* One participant of a job: repeatedly claims the first segment of seg_order (longest first) that is unclaimed and
+   — when completion flags are given — already complete, and argsorts it.  With flags the segments become
+   available while the DP kernel is still running; the scan prefers the longest available one so that the pool
+   drains evenly once everything has arrived. */
+static void run_job(job_t *j)
+{
     npy_intp *idx = NULL;
     int64_t *wide = NULL;
     int64_t cap = 0;
+    unsigned idle = 0;
     for (;;) {
-        int64_t s = __sync_fetch_and_add(&j->next, 1);
-        if (s >= j->n_seg) break;
-        int64_t seg = j->seg_order ? j->seg_order[s] : s;
+        int64_t pick = -1, lo = j->lo;
+        int open = 0;
+        for (int64_t i = lo; i < j->n_seg; i++) {
+            if (j->claimed[i]) continue;
+            open = 1;
+            if (j->flags && !j->flags[j->seg_order[i]]) continue;
+            if (__sync_bool_compare_and_swap(&j->claimed[i], 0, 1)) { pick = i; break; }
+        }
+        if (pick < 0) {
+            if (!open || j->err) break;
+            for (int k = 0; k < 32; k++) _mm_pause();
+            if ((++idle & 1023u) == 0 && now_s() > j->deadline) { j->err = 3; break; }
+            continue;
+        }
+        while (lo < j->n_seg && j->claimed[lo]) lo++;
+        if (lo > j->lo) j->lo = lo;                 /* racy but harmless: a stale value only lengthens a scan */
+        int64_t seg = j->seg_order[pick];
         int64_t a = j->off[seg], n = j->off[seg + 1] - a;
         if (n <= 0) continue;
         if (n > cap) {
@@ -63,8 +95,8 @@ static void *worker(void *vp)
             for (int64_t i = 0; i < n; i += 16) _mm_prefetch((const char *)(k32 + i), _MM_HINT_NTA);
         }
         for (int64_t i = 0; i < n; i++) { idx[i] = i; wide[i] = k32[i]; }   /* index fill as _new_argsortlike does */
-        /* The key buffer is the target of the next device-to-host DMA: drop its lines from the CPU caches now so
-           that the DMA writes do not have to snoop them out (measured: 15 MB in 0.70 ms with cached lines vs
+        /* The key buffer is the target of the next device-to-host transfer: drop its lines from the CPU caches now
+           so that those writes do not have to snoop them out (measured: 15 MB in 0.70 ms with cached lines vs
            0.28 ms for untouched pinned memory). */
         if (j->flush == 1)
             for (const char *q = (const char *)((uintptr_t)k32 & ~(uintptr_t)63); q < (const char *)(k32 + n); q += 64) _mm_clflush(q);
@@ -77,25 +109,112 @@ static void *worker(void *vp)
         /* streaming stores: the argsort goes to the device next, keep it out of the caches */
         for (int64_t i = 0; i < n; i++) _mm_stream_si32((int *)&o[i], (int)idx[i]);
     }
+    _mm_sfence();
     free(idx);
     free(wide);
+}
+
+/* ---- persistent helper threads: created once, parked on a condition variable between jobs ------------------ */
+#define POOL_MAX 127
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t cv_job, cv_done;
+    pthread_t th[POOL_MAX];
+    int n_threads;          /* helper threads alive */
+    uint64_t gen;           /* job generation */
+    job_t *job;
+    int want;               /* helpers that should join the current job */
+    int running;            /* helpers still inside the current job */
+    pid_t owner;
+} pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, NULL, 0, 0, 0};
+
+static void *pool_main(void *vp)
+{
+    const int me = (int)(intptr_t)vp;
+    uint64_t seen = 0;
+    pthread_mutex_lock(&pool.mu);
+    for (;;) {
+        while (pool.gen == seen) pthread_cond_wait(&pool.cv_job, &pool.mu);
+        seen = pool.gen;
+        if (me >= pool.want) continue;
+        job_t *j = pool.job;
+        pthread_mutex_unlock(&pool.mu);
+        run_job(j);
+        pthread_mutex_lock(&pool.mu);
+        if (--pool.running == 0) pthread_cond_signal(&pool.cv_done);
+    }
     return NULL;
+}
+
+static pthread_mutex_t job_mu = PTHREAD_MUTEX_INITIALIZER;   /* one job at a time */
+
+static void pool_child(void)         /* after fork() the helper threads are gone */
+{
+    pthread_mutex_init(&pool.mu, NULL);
+    pthread_cond_init(&pool.cv_job, NULL);
+    pthread_cond_init(&pool.cv_done, NULL);
+    pthread_mutex_init(&job_mu, NULL);
+    pool.n_threads = 0;
+    pool.running = 0;
+}
+
+static void pool_run(job_t *j, int threads)
+{
+    pthread_mutex_lock(&job_mu);
+    int helpers = threads - 1;
+    if (helpers > POOL_MAX) helpers = POOL_MAX;
+    pthread_mutex_lock(&pool.mu);
+    if (pool.owner == 0) { pool.owner = 1; pthread_atfork(NULL, NULL, pool_child); }
+    while (pool.n_threads < helpers) {
+        pthread_attr_t at;
+        pthread_attr_init(&at);
+        pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+        int rc = pthread_create(&pool.th[pool.n_threads], &at, pool_main, (void *)(intptr_t)pool.n_threads);
+        pthread_attr_destroy(&at);
+        if (rc != 0) break;
+        pool.n_threads++;
+    }
+    if (helpers > pool.n_threads) helpers = pool.n_threads;
+    pool.job = j;
+    pool.want = helpers;
+    pool.running = helpers;
+    pool.gen++;
+    pthread_cond_broadcast(&pool.cv_job);
+    pthread_mutex_unlock(&pool.mu);
+    run_job(j);
+    pthread_mutex_lock(&pool.mu);
+    while (pool.running > 0) pthread_cond_wait(&pool.cv_done, &pool.mu);
+    pool.job = NULL;
+    pthread_mutex_unlock(&pool.mu);
+    pthread_mutex_unlock(&job_mu);
 }
 
 static PyObject *seg_argsort(PyObject *self, PyObject *args)
 {
     PyArrayObject *keys, *off, *order, *out;
+    PyObject *flags_obj = Py_None;
     int threads, flush = 0;
-    if (!PyArg_ParseTuple(args, "O!O!O!O!i|i", &PyArray_Type, &keys, &PyArray_Type, &off, &PyArray_Type, &order,
-                          &PyArray_Type, &out, &threads, &flush))
+    double timeout = 60.0;
+    if (!PyArg_ParseTuple(args, "O!O!O!O!i|iOd", &PyArray_Type, &keys, &PyArray_Type, &off, &PyArray_Type, &order,
+                          &PyArray_Type, &out, &threads, &flush, &flags_obj, &timeout))
         return NULL;
     if (PyArray_TYPE(keys) != NPY_INT32 || PyArray_TYPE(off) != NPY_INT64 || PyArray_TYPE(order) != NPY_INT32 ||
         PyArray_TYPE(out) != NPY_INT32 || !PyArray_IS_C_CONTIGUOUS(keys) || !PyArray_IS_C_CONTIGUOUS(off) ||
         !PyArray_IS_C_CONTIGUOUS(order) || !PyArray_IS_C_CONTIGUOUS(out) || !PyArray_ISALIGNED(keys) ||
         PyArray_NDIM(keys) != 1 || PyArray_NDIM(out) != 1 || PyArray_SIZE(out) < PyArray_SIZE(keys) ||
         PyArray_SIZE(off) < 1 || PyArray_SIZE(order) != PyArray_SIZE(off) - 1) {
-        PyErr_SetString(PyExc_TypeError, "seg_argsort(keys:int32[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads)");
+        PyErr_SetString(PyExc_TypeError, "seg_argsort(keys:int32[n], off:int64[S+1], seg_order:int32[S], out:int32[n], threads[, flush, flags:int32[S], timeout])");
         return NULL;
+    }
+    const volatile int32_t *flags = NULL;
+    if (flags_obj != Py_None) {
+        PyArrayObject *f = (PyArrayObject *)flags_obj;
+        if (!PyArray_Check(flags_obj) || PyArray_TYPE(f) != NPY_INT32 || !PyArray_IS_C_CONTIGUOUS(f) ||
+            PyArray_SIZE(f) < PyArray_SIZE(off) - 1) {
+            PyErr_SetString(PyExc_TypeError, "seg_argsort: flags must be a contiguous int32 array with one slot per segment");
+            return NULL;
+        }
+        flags = (const volatile int32_t *)PyArray_DATA(f);
     }
     PyArray_Descr *d64 = PyArray_DescrFromType(NPY_INT64);
     PyArray_ArgSortFunc *fn = PyDataType_GetArrFuncs(d64)->argsort[NPY_QUICKSORT];
@@ -109,25 +228,25 @@ static PyObject *seg_argsort(PyObject *self, PyObject *args)
     j.keys = (const int32_t *)PyArray_DATA(keys);
     j.off = (const int64_t *)PyArray_DATA(off);
     j.seg_order = (const int32_t *)PyArray_DATA(order);
+    j.flags = flags;
     j.out = (int32_t *)PyArray_DATA(out);
     j.n_seg = PyArray_SIZE(off) - 1;
-    j.next = 0;
+    j.lo = 0;
     j.err = 0;
     j.flush = flush;
+    j.claimed = (volatile uint8_t *)calloc((size_t)(j.n_seg > 0 ? j.n_seg : 1), 1);
+    if (!j.claimed) return PyErr_NoMemory();
     if (threads < 1) threads = 1;
     if (threads > 128) threads = 128;
     if (threads > j.n_seg) threads = (int)(j.n_seg > 0 ? j.n_seg : 1);
     Py_BEGIN_ALLOW_THREADS
-    pthread_t th[128];
-    int started = 0;
-    for (int t = 1; t < threads; t++)
-        if (pthread_create(&th[started], NULL, worker, &j) == 0) started++;
-    worker(&j);
-    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
-    _mm_sfence();
+    j.deadline = now_s() + timeout;
+    if (threads > 1) pool_run(&j, threads); else run_job(&j);
     Py_END_ALLOW_THREADS
+    free((void *)j.claimed);
     if (j.err) {
-        PyErr_SetString(PyExc_RuntimeError, j.err == 1 ? "seg_argsort: out of memory" : "seg_argsort: numpy argsort failed");
+        PyErr_SetString(PyExc_RuntimeError, j.err == 1 ? "seg_argsort: out of memory" :
+                        j.err == 3 ? "seg_argsort: timed out waiting for the device to complete a segment" : "seg_argsort: numpy argsort failed");
         return NULL;
     }
     return PyLong_FromLong(0);

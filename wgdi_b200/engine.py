@@ -142,6 +142,8 @@ class IclEngine:
         default_flush = "3" if (_npsort is not None and hasattr(_npsort, "has_clflushopt") and _npsort.has_clflushopt()) else "0"
         self.flush_keys = int(os.environ.get("ICL_B200_FLUSH_KEYS", default_flush))
         self._pool = ThreadPoolExecutor(self.sort_threads) if self.sort_threads > 1 else None
+        # overlap the host rank with the DP kernel (icl_dp_begin); ICL_B200_STREAM=0 runs the two one after the other
+        self.stream_rank = os.environ.get("ICL_B200_STREAM", "1") != "0"
         self.host_ms = {}
 
     # ---- plumbing ------------------------------------------------------------------------------
@@ -295,8 +297,42 @@ class IclEngine:
                     max_span=int(c[4]), chain_kernel={0: "generic", 1: "ring", 3: "single"}[int(c[5])])
 
     # ---- whole hot path ------------------------------------------------------------------------
+    def dp_rank_streamed(self, params: ChainParams):
+        """`dp` + `rank` overlapped: the DP kernel hands every finished (pair, direction) item to the host through
+        page-locked memory (icl_dp_begin) and the sort pool argsorts the segments while heavier pairs are still being
+        chained.  Same arrays and same numpy routine as `dp` followed by `rank`."""
+        prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
+                         float(params.coverage_ratio))
+        n, P = self.n, self.n_pairs
+        keys = self._buf("keys", 2 * n, np.int32)
+        both = self._buf("argsort", 2 * n, np.int32)
+        flags = self._buf("done", 2 * P, np.int32)
+        t0 = time.perf_counter()
+        self._check(self.lib.icl_dp_begin(self.ctx, C.byref(prm), keys.ctypes.data, keys.ctypes.data + 4 * n,
+                                          flags.ctypes.data))
+        self.pair_off = np.zeros(P + 1, np.int64)
+        self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
+        off = self.pair_off
+        sizes = np.diff(off)
+        off2 = np.concatenate([off, off[1:] + n])
+        order = np.argsort(-np.concatenate([sizes, sizes]), kind="stable").astype(np.int32)
+        t1 = time.perf_counter()
+        try:
+            _npsort.seg_argsort(keys, off2, order, both, self.sort_threads, self.flush_keys, flags, 120.0)
+        finally:
+            self._check(self.lib.icl_dp_end(self.ctx))
+        t2 = time.perf_counter()
+        self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3)
+        return both[:n], both[n:]
+
     def run_resident(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
         """Hot path on points already uploaded: sort + DP -> host rank -> extraction + p values."""
+        if self.stream_rank and _npsort_ok():
+            af, ar = self.dp_rank_streamed(params)
+            t2 = time.perf_counter()
+            blocks = self.extract(af, ar, min_members, copy)
+            self.host_ms["extract"] = (time.perf_counter() - t2) * 1e3
+            return blocks
         t0 = time.perf_counter()
         kf, kr = self.dp(params)
         t1 = time.perf_counter()
