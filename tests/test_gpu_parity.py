@@ -307,6 +307,28 @@ def test_other_baseline_configs_match_oracle(gpu_engine, name, scale, mg):
     assert gpu_engine.counters()["chain_kernel"] == "ring"
 
 
+def test_streamed_rank_equals_two_step_rank(gpu_engine):
+    """icl_dp_begin (items export their scores and raise a flag as they finish, the sort pool follows) gives the
+    same score arrays and the same numpy argsort as icl_dp followed by the rank, including empty chromosome pairs."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    pair = pts["pair_id"].astype(np.int32) * 2                      # every second pair id is empty
+    gpu_engine.upload(pair, pts["loc1"], pts["loc2"], pts["grading"], 2 * pts["n_pairs"])
+    kf, kr = gpu_engine.dp(prm)
+    kf, kr = kf.copy(), kr.copy()
+    af, ar = [x.copy() for x in gpu_engine.rank(kf, kr)]
+    for _ in range(3):
+        sf, sr = gpu_engine.dp_rank_streamed(prm)
+        keys = gpu_engine._buf("keys", 2 * gpu_engine.n, np.int32)
+        assert (keys[:gpu_engine.n] == kf).all() and (keys[gpu_engine.n:] == kr).all()
+        assert (sf == af).all() and (sr == ar).all()
+    assert gpu_engine.counters()["chain_kernel"] == "ring"
+    b1 = gpu_engine.extract(sf, sr)
+    _compare_with_oracle(b1, [(2 * p, d, l1, l2, a, sc) for p, d, l1, l2, a, sc in oracle_blocks(pts, prm)])
+
+
 def test_alternative_dp_kernels_agree(clouds):
     """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth

@@ -236,3 +236,77 @@ def test_cli_prints_example_and_missing_conf(capsys):
     assert "[collinearity]" in capsys.readouterr().out
     assert main(["-icl", "/nonexistent.conf"]) == 0
     assert "not exists" in capsys.readouterr().out
+
+
+# ---- streamed rank: completion flags and the sort pool -----------------------------------------------
+
+def test_sort_pool_with_completion_flags_equals_numpy():
+    """The sort helper argsorts a segment only after its flag is raised (the GPU raises them in the product,
+    a thread does here) and the result is numpy's own argsort of the widened segment."""
+    import threading
+    import time
+    from wgdi_b200 import _npsort
+    rng = np.random.default_rng(7)
+    sizes = rng.integers(0, 3000, 120).astype(np.int64)
+    sizes[[3, 77]] = 0
+    off = np.r_[0, np.cumsum(sizes)].astype(np.int64)
+    keys = rng.integers(25, 400, int(off[-1])).astype(np.int32)
+    order = np.argsort(-sizes, kind="stable").astype(np.int32)
+    flags = np.zeros(len(sizes), np.int32)
+    out = np.full(len(keys), -1, np.int32)
+
+    def raiser():
+        for s in np.argsort(sizes):                 # small segments finish first, like DP items do
+            flags[s] = 1
+            if s % 16 == 0:
+                time.sleep(0.0005)
+    th = threading.Thread(target=raiser)
+    th.start()
+    _npsort.seg_argsort(keys, off, order, out, 4, 0, flags, 30.0)
+    th.join()
+    for a, b in zip(off[:-1], off[1:]):
+        assert (out[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all()
+    # a flag that never comes up is an error, not a hang
+    flags[:] = 0
+    with pytest.raises(RuntimeError, match="timed out"):
+        _npsort.seg_argsort(keys, off, order, out, 2, 0, flags, 0.2)
+    # the pool survives the failed job
+    _npsort.seg_argsort(keys, off, order, out, 4)
+    a, b = off[5], off[6]
+    assert (out[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all()
+
+
+def test_dp_begin_end_contract_emu(emu_backend):
+    """icl_dp_begin / icl_dp_end: same keys as icl_dp, every completion flag raised when the device is done (the
+    emulation has no streaming kernel, so this is the documented degraded form), state errors reported."""
+    from wgdi_b200 import synth
+    from wgdi_b200._lib import IclError, icl_params
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("tiny"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        with pytest.raises(IclError):
+            eng._check(eng.lib.icl_dp_end(eng.ctx))                     # nothing begun
+        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+        kf, kr = eng.dp(prm)
+        kf, kr = kf.copy(), kr.copy()
+        af, ar = eng.rank(kf, kr)
+        af, ar = af.copy(), ar.copy()
+        n, P = eng.n, eng.n_pairs
+        keys = np.zeros(2 * n, np.int32)
+        flags = np.full(2 * P, -7, np.int32)
+        p = icl_params(25, 25, 50, 3, 0.8)
+        eng._check(eng.lib.icl_dp_begin(eng.ctx, ctypes.byref(p), keys.ctypes.data, keys.ctypes.data + 4 * n, flags.ctypes.data))
+        with pytest.raises(IclError):                                    # extraction needs icl_dp_end first
+            eng.extract(af, ar)
+        eng._check(eng.lib.icl_dp_end(eng.ctx))
+        assert (flags == 1).all()
+        assert (keys[:n] == kf).all() and (keys[n:] == kr).all()
+        sf, sr = eng.dp_rank_streamed(prm)
+        assert (sf == af).all() and (sr == ar).all()
+        b1 = eng.extract(sf, sr)
+        b2 = eng.extract(af, ar)
+        assert len(b1) == len(b2) and (b1.p_raw == b2.p_raw).all() and (b1.loc1 == b2.loc1).all()
+    finally:
+        eng.close()

@@ -1295,7 +1295,7 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
     }
     if (queue) for (int64_t i = 0; i < 2 * (int64_t)c->P; i++) queue[i] = 1;     // not streamed: everything is complete now
     c->dp_begun = true;
-    c->dp_done = true;
+    c->dp_done = queue == nullptr;                             // icl_dp_begin: only icl_dp_end completes the phase
     return ICL_OK;
 }
 
