@@ -286,6 +286,42 @@ def grade_hits(q_codes, bitscore, multiple, repeat_number, grading):
     return out
 
 
+def grade_hits_chromosomes(id1, subj, pair, bitscore, multiple, repeat_number, grading):
+    """`deal_blast_for_chromosomes` (wgdi/run_colliearity.py:42-57) as pandas < 3 ran it (under pandas 3 the
+    reference raises KeyError 'chr1' at :118; the golden fixture was generated with the pandas-2 behaviour of
+    groupby.apply restored, tests/make_golden.py).
+
+    id1: query id STRINGS per surviving hit (file order); subj / pair: integer codes of the subject gene and of the
+    chromosome pair.  Returns (grading per hit, 0 = dropped; the row order of the frame the function returns up to
+    the irrelevant concatenation order of the chromosome pairs).
+      :44  stable multi-key sort by (id1 ascending, bitscore descending)
+      :46  cumcount per subject gene inside each chromosome pair, in that order
+      :47  keep cumcount <= repeat_number
+      :48-53  pd.cut(cumcount, bins=[-1, 0, multiple, repeat_number], labels=grading, right=True)
+    """
+    bitscore = np.asarray(bitscore)
+    n = len(bitscore)
+    rn, blue = int(repeat_number), int(multiple)          # bluenum = rednum (:43)
+    if not (0 < blue < rn):
+        raise ValueError("bins must increase monotonically.")                  # what pd.cut raises
+    if len(set(grading)) != len(grading):
+        raise ValueError("labels must be unique if ordered=True; pass ordered=False for duplicate labels")
+    _, id_rank = np.unique(np.asarray(id1).astype(str), return_inverse=True)
+    order = np.lexsort((-bitscore, id_rank))               # stable: ties keep file order
+    cum = np.zeros(n, np.int64)
+    seen = {}
+    for r in order.tolist():
+        key = (int(pair[r]), int(subj[r]))
+        c = seen.get(key, 0)
+        cum[r] = c
+        seen[key] = c + 1
+    grade = np.zeros(n, np.int64)
+    grade[cum == 0] = grading[0]
+    grade[(cum > 0) & (cum <= blue)] = grading[1]
+    grade[(cum > blue) & (cum <= rn)] = grading[2]
+    return grade, order
+
+
 def icl_text(conf_path):
     """The outer seam: everything `mycollinearity(options).run()` writes to `savefile`
     (wgdi/run_colliearity.py:88-200), returned as a string instead of written."""
@@ -332,7 +368,16 @@ def icl_text(conf_path):
     g1, g2, bits = g1[rows], g2[rows], bits[rows]
     # groupby([0]) iterates query ids in sorted order but gradings are set by label, so the
     # iteration order is irrelevant; only the per-group file order matters.
-    grade = grade_hits(g1, bits, multiple, repeat_number, grading)
+    comparison = str(opts.get("comparison", "genomes")).lower()         # :22, :108-111
+    if comparison == "chromosomes":
+        c1u, c1c = np.unique(gff1["chr"][g1], return_inverse=True)
+        c2u, c2c = np.unique(gff2["chr"][g2], return_inverse=True)
+        grade, order = grade_hits_chromosomes(id1[rows], g2, c1c * len(c2u) + c2c, bits, multiple, repeat_number, grading)
+        g1, g2, grade = g1[order], g2[order], grade[order]             # the rows now follow the sort of :44
+    elif comparison == "genomes":
+        grade = grade_hits(g1, bits, multiple, repeat_number, grading)
+    else:
+        return None                                                     # neither branch runs; the reference then fails at :118
     ok = grade > 0                                                      # run_colliearity.py:86
     g1, g2, grade = g1[ok], g2[ok], grade[ok]
     if len(g1) < 1:

@@ -178,7 +178,25 @@ E2E_CASES = {
     "tiny": dict(cfg="tiny"),
     "cross": dict(cfg="cross"),
     "tiny_rev": dict(cfg="cross", blast_reverse=True, chr_names1=["10", "B2", "1", "2"]),
+    # `comparison = chromosomes` (wgdi/run_colliearity.py:42-57).  The reference's code predates pandas 3: its
+    # groupby(...).apply(f) at :55 relies on f receiving the grouping columns, which pandas 3 removed (KeyError
+    # 'chr1' at :118).  The reference is still run UNMODIFIED; the generating process restores that
+    # one pandas behaviour (`pandas2_groupby_apply_shim`) so that the mode can be pinned at all.
+    "cross_chrom": dict(cfg="cross", comparison="chromosomes", pandas2_shim=True),
 }
+
+
+def pandas2_groupby_apply_shim():
+    """pandas < 3 semantics of DataFrameGroupBy.apply for the one call the reference makes
+    (wgdi/run_colliearity.py:55): the function receives every group WITH its grouping columns, groups come in
+    sorted key order, results are concatenated (the caller resets the index right away)."""
+    import pandas as pd
+    from pandas.core.groupby.generic import DataFrameGroupBy
+
+    def apply_with_groups(self, func, *a, **k):
+        pieces = [func(g, *a, **k) for _, g in self]
+        return pd.concat(pieces) if pieces else self.obj.iloc[:0]
+    DataFrameGroupBy.apply = apply_with_groups
 
 
 def gen_e2e_child(case):
@@ -209,6 +227,11 @@ def gen_e2e_child(case):
                     f.write("\t".join(c) + "\n")
             txt = open(conf).read().replace("blast_reverse = false", "blast_reverse = true")
             open(conf, "w").write(txt)
+        if spec.get("comparison"):
+            txt = open(conf).read().replace("comparison = genomes", f"comparison = {spec['comparison']}")
+            open(conf, "w").write(txt)
+        if spec.get("pandas2_shim"):
+            pandas2_groupby_apply_shim()
         try:
             mycollinearity(base.load_conf(conf, "collinearity")).run()
         except SystemExit:
@@ -217,15 +240,18 @@ def gen_e2e_child(case):
             g.write(f.read())
         os.remove("blast.m8")
         json.dump({"argsort_fingerprint": argsort_fingerprint(), "numpy": np.__version__,
-                   "NPY_DISABLE_CPU_FEATURES": PORTABLE_ENV}, open("meta.json", "w"), indent=1)
+                   "NPY_DISABLE_CPU_FEATURES": PORTABLE_ENV, "pandas2_groupby_apply_shim": bool(spec.get("pandas2_shim"))},
+                  open("meta.json", "w"), indent=1)
     finally:
         os.chdir(cwd)
     print(case, "blocks:", sum(1 for l in open(os.path.join(d, "expected.collinearity.txt")) if l.startswith("#")))
 
 
-def gen_e2e():
+def gen_e2e(only=None):
     env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
     for case in E2E_CASES:
+        if only and case != only:
+            continue
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "--e2e-child", case], env=env)
 
 
@@ -239,3 +265,5 @@ if __name__ == "__main__":
             gen_clouds()
         if what in ("all", "e2e"):
             gen_e2e()
+        if what in E2E_CASES:
+            gen_e2e(only=what)

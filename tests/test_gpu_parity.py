@@ -106,7 +106,7 @@ print("OK" if open("got.txt").read() == open("expected.collinearity.txt").read()
 """
 
 
-@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev"])
+@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev", "cross_chrom"])
 def test_drop_in_driver_writes_reference_file(case):
     """Outer seam, conf in -> file out, byte-identical to what the unmodified reference wrote."""
     with tempfile.TemporaryDirectory() as d:

@@ -222,7 +222,7 @@ def run_e2e_child(case, emu_path):
         assert r.stdout.strip() == "OK", r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev"])
+@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev", "cross_chrom"])
 def test_drop_in_driver_writes_reference_file_emu(case):
     """`mycollinearity(options).run()` (host parsing, grading, grouping, formatting) on the fake backend
     reproduces the file the unmodified reference wrote."""
@@ -310,3 +310,28 @@ def test_dp_begin_end_contract_emu(emu_backend):
         assert len(b1) == len(b2) and (b1.p_raw == b2.p_raw).all() and (b1.loc1 == b2.loc1).all()
     finally:
         eng.close()
+
+
+def test_grade_hits_chromosomes_matches_oracle():
+    """`comparison = chromosomes` grading (run_colliearity.py:42-57): vectorised host code vs the oracle's loop, with
+    tied bit scores, several chromosome pairs and gene names whose string order differs from their numeric order."""
+    from wgdi_b200.ingest import grade_hits_chromosomes
+    rng = np.random.default_rng(3)
+    n_genes, n = 300, 6000
+    names = np.array([f"g{i}" for i in rng.permutation(n_genes)])          # "g10" < "g9": string order
+    g1 = rng.integers(0, n_genes, n)
+    g2 = rng.integers(0, 150, n)
+    pair = rng.integers(0, 7, n)
+    bits = rng.integers(100, 130, n).astype(np.int64)
+    name_rank = np.empty(n_genes, np.int64)
+    name_rank[np.argsort(names, kind="stable")] = np.arange(n_genes)
+    for multiple, rn, grading in ((1, 10, (50, 30, 25)), (2, 5, (60, 35, 20)), (3, 4, (9, 5, 1))):
+        ga, oa = grade_hits_chromosomes(name_rank, g1, g2, pair, bits, multiple, rn, grading)
+        gb, ob = icl_oracle.grade_hits_chromosomes(names[g1], g2, pair, bits, multiple, rn, grading)
+        assert (ga == gb).all() and (oa == ob).all()
+        assert set(np.unique(ga)) <= {0, *grading} and (ga > 0).any() and (ga == 0).any()
+    for bad in ((0, 10), (10, 10), (12, 10)):                              # pd.cut: bins must increase
+        with pytest.raises(ValueError):
+            grade_hits_chromosomes(name_rank, g1, g2, pair, bits, bad[0], bad[1], (50, 30, 25))
+        with pytest.raises(ValueError):
+            icl_oracle.grade_hits_chromosomes(names[g1], g2, pair, bits, bad[0], bad[1], (50, 30, 25))

@@ -95,7 +95,7 @@ def test_native_grading_matches_oracle_with_ties(host):
         assert (got == icl_oracle.grade_hits(q, bits, mult, rn, [50, 30, 25])).all()
 
 
-@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev"])
+@pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev", "cross_chrom"])
 def test_native_and_pandas_paths_write_the_same_file(host, emu_backend, case, tmp_path):
     """conf in -> file out through the native parser / writer and through the pandas readers (fake device backend)."""
     from wgdi_b200 import base

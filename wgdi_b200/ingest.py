@@ -67,6 +67,35 @@ def grade_hits_native(q, bits, n_query, multiple, repeat_number, grading):
     return out
 
 
+def grade_hits_chromosomes(name_rank, g1, g2, pair_code, bits, multiple, repeat_number, grading):
+    """`deal_blast_for_chromosomes` (wgdi/run_colliearity.py:42-57): stable sort by (query id string ascending,
+    bit score descending) (:44); cumcount per subject gene inside each chromosome pair in that order (:46); keep
+    cumcount <= repeat_number (:47); grading by pd.cut over bins [-1, 0, multiple, repeat_number] (:48-53).
+    Every sort in it is stable, so there is no tie hazard here.  name_rank[g] = rank of gene g's id among the query
+    ids in string order.  Returns (grading per hit, 0 = dropped; row order of the frame the reference continues
+    with — equal (loc1, loc2) keep THIS order in the later stable sort of :164-166, hazard H22)."""
+    rn, blue = int(repeat_number), int(multiple)
+    if not (0 < blue < rn):
+        raise ValueError("bins must increase monotonically.")                  # pd.cut, as in the reference
+    if len(set(grading)) != len(grading):
+        raise ValueError("labels must be unique if ordered=True; pass ordered=False for duplicate labels")
+    bits = np.asarray(bits)
+    n = len(bits)
+    order = np.lexsort((-bits, np.asarray(name_rank)[g1]))
+    key = (np.asarray(pair_code, np.int64) * (int(np.max(g2, initial=0)) + 1) + g2)[order]
+    o2 = np.argsort(key, kind="stable")
+    ks = key[o2]
+    start = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]]) if n else np.zeros(0, np.int64)
+    gid = np.cumsum(np.r_[True, ks[1:] != ks[:-1]]) - 1 if n else np.zeros(0, np.int64)
+    cum = np.empty(n, np.int64)
+    cum[order[o2]] = np.arange(n) - start[gid] if n else 0
+    grade = np.zeros(n, np.int64)
+    grade[cum == 0] = grading[0]
+    grade[(cum > 0) & (cum <= blue)] = grading[1]
+    grade[(cum > blue) & (cum <= rn)] = grading[2]
+    return grade, order
+
+
 def pair_ids(chr1_names, chr2_names, c1, c2):
     """Chromosome-pair id per hit, numbered in the sorted (chr1, chr2) STRING order pandas' groupby
     iterates (wgdi/run_colliearity.py:118).  Returns (pair_id, [(chr1, chr2) per pair])."""

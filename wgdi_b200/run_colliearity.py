@@ -5,8 +5,9 @@ output file; the per-chromosome-pair Python/pandas work of the reference's worke
 
 Differences a user can observe: `process` is accepted and ignored (there is no worker pool:
 chromosome pairs are work items of one CUDA launch, or shards over several GPUs, see
-wgdi_b200/shard.py), and `comparison = chromosomes` is not offered (the reference itself
-raises KeyError there under pandas >= 3, SURVEY.md hazard H19).
+wgdi_b200/shard.py), and `comparison = chromosomes` works (the reference itself raises
+KeyError there under pandas >= 3, SURVEY.md hazard H19; the semantics are those of its code
+under pandas < 3, pinned by tests/golden/e2e_cross_chrom).
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ import numpy as np
 
 from . import _host, base
 from .engine import ChainParams, IclEngine
-from .ingest import grade_hits, grade_hits_native, pair_ids
+from .ingest import grade_hits, grade_hits_chromosomes, grade_hits_native, pair_ids
 
 
 class mycollinearity():
@@ -57,27 +58,36 @@ class mycollinearity():
         gff2 = base.newgff(self.gff2)
         gff1 = gff1[gff1['chr'].isin(lens1.index)]        # :96-97
         gff2 = gff2[gff2['chr'].isin(lens2.index)]
-        if self.comparison.lower() != 'genomes':
-            raise NotImplementedError("comparison = chromosomes is not offered (the reference raises KeyError "
-                                      "there under pandas >= 3; SURVEY.md H19)")
+        mode = self.comparison.lower()                    # :108-111
+        if mode not in ('genomes', 'chromosomes'):
+            raise ValueError(f"comparison = {self.comparison}: expected 'genomes' or 'chromosomes'")
         if self.native:
             ids1 = _host.pack_strings(gff1.index)
             ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
             hits = _host.read_m8(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2)
             g1, g2 = hits['g1'], hits['g2']
-            grade = grade_hits_native(g1, hits['bits'], len(gff1), int(self.multiple), int(self.repeat_number), self.grading)
+            bits = hits['bits']
         else:
             blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
-            g1, g2 = blast['g1'].to_numpy(), blast['g2'].to_numpy()
-            grade = grade_hits(g1, blast[11].to_numpy(), int(self.multiple), int(self.repeat_number), self.grading)
-        ok = grade > 0                                    # :86
+            g1, g2, bits = blast['g1'].to_numpy(), blast['g2'].to_numpy(), blast[11].to_numpy()
+        t1 = _gene_table(gff1)
+        t2 = _gene_table(gff2)
+        if mode == 'chromosomes':                         # :42-57, every sort stable
+            name_rank = np.empty(len(gff1), np.int64)
+            name_rank[np.argsort(t1['name'], kind='stable')] = np.arange(len(gff1))
+            grade, order = grade_hits_chromosomes(name_rank, g1, g2, t1['chr_code'][g1] * len(t2['chr_names']) + t2['chr_code'][g2],
+                                                  bits, int(self.multiple), int(self.repeat_number), self.grading)
+            g1, g2, grade = g1[order], g2[order], grade[order]
+        elif self.native:
+            grade = grade_hits_native(g1, bits, len(gff1), int(self.multiple), int(self.repeat_number), self.grading)
+        else:
+            grade = grade_hits(g1, bits, int(self.multiple), int(self.repeat_number), self.grading)
+        ok = grade > 0                                    # :86 / :57
         g1, g2, grade = g1[ok], g2[ok], grade[ok]
         print(f"The filtered homologous gene pairs are {len(g1)}.\n")      # :112
         if len(g1) < 1:
             print("Stopped!\n\nIt may be that the id1 and id2 in the BLAST file do not match with (gff1, lens1) and (gff2, lens2).")
             sys.exit(1)                                   # :113-115
-        t1 = _gene_table(gff1)
-        t2 = _gene_table(gff2)
         pid, names = pair_ids(t1['chr_names'], t2['chr_names'], t1['chr_code'][g1], t2['chr_code'][g2])
         return dict(pair_id=pid, loc1=t1['order'][g1].astype(np.int32), loc2=t2['order'][g2].astype(np.int32),
                     grading=grade.astype(np.int32), pair_names=names, genes1=t1, genes2=t2)
