@@ -247,6 +247,63 @@ def gen_e2e_child(case):
     print(case, "blocks:", sum(1 for l in open(os.path.join(d, "expected.collinearity.txt")) if l.startswith("#")))
 
 
+# ----------------------------------------------------------------------------------------
+# `-bi` (block information) on the collinearity files the reference wrote above
+# ----------------------------------------------------------------------------------------
+
+BI_CASES = {"cross": dict(ks=False, repeat_number=20), "tiny": dict(ks=True, repeat_number=12)}
+
+
+def gen_bi_child(case):
+    """wgdi.block_info.block_info(options).run() (wgdi/block_info.py:136-165), unmodified, on e2e_<case>."""
+    import numpy as np
+    base, _, _ = import_reference()
+    from wgdi.block_info import block_info
+    spec = BI_CASES[case]
+    d = os.path.join(GOLD, f"e2e_{case}")
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        with gzip.open("blast.m8.gz", "rb") as g, open("blast.m8", "wb") as f:
+            f.write(g.read())
+        icl = dict(base.load_conf("icl.conf", "collinearity"))
+        ks = "none"
+        if spec["ks"]:
+            # synthetic Ks table over the block pairs: some given reversed, some missing, negative values (dropped
+            # by read_ks), duplicated keys (first wins)
+            rng = np.random.default_rng(42)
+            pairs = [ln.split()[0:3:2] for ln in open("expected.collinearity.txt") if not ln.startswith("#")]
+            with open("ks.tsv", "w") as f:
+                f.write("id1\tid2\tka_NG86\tks_NG86\tka_YN00\tks_YN00\n")
+                for a, b in pairs:
+                    u = rng.random()
+                    if u < 0.15:
+                        continue
+                    if u < 0.35:
+                        a, b = b, a
+                    v = -1.0 if u > 0.93 else round(float(rng.gamma(2.0, 0.4)), 4)
+                    f.write(f"{a}\t{b}\t{round(v / 3, 4)}\t{v}\t0.1\t{round(abs(v) * 1.1, 4)}\n")
+                    if u > 0.6 and u < 0.65:
+                        f.write(f"{a}\t{b}\t0.5\t9.9999\t0.1\t9.9\n")
+            ks = "ks.tsv"
+        with open("bi.conf", "w") as f:
+            f.write("[blockinfo]\n"
+                    f"blast = blast.m8\ngff1 = {icl['gff1']}\ngff2 = {icl['gff2']}\nlens1 = {icl['lens1']}\nlens2 = {icl['lens2']}\n"
+                    f"collinearity = expected.collinearity.txt\nscore = 100\nevalue = 1e-5\nrepeat_number = {spec['repeat_number']}\n"
+                    f"position = order\nks = {ks}\nks_col = ks_NG86\nsavefile = expected.blockinfo.csv\n")
+        block_info(base.load_conf("bi.conf", "blockinfo")).run()
+        os.remove("blast.m8")
+    finally:
+        os.chdir(cwd)
+    print(case, "blockinfo rows:", sum(1 for _ in open(os.path.join(d, "expected.blockinfo.csv"))) - 1)
+
+
+def gen_bi():
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+    for case in BI_CASES:
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--bi-child", case], env=env)
+
+
 def gen_e2e(only=None):
     env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
     for case in E2E_CASES:
@@ -259,6 +316,8 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if len(sys.argv) > 2 and sys.argv[1] == "--e2e-child":
         gen_e2e_child(sys.argv[2])
+    elif len(sys.argv) > 2 and sys.argv[1] == "--bi-child":
+        gen_bi_child(sys.argv[2])
     else:
         what = sys.argv[1] if len(sys.argv) > 1 else "all"
         if what in ("all", "clouds"):
@@ -267,3 +326,5 @@ if __name__ == "__main__":
             gen_e2e()
         if what in E2E_CASES:
             gen_e2e(only=what)
+        if what in ("all", "bi"):
+            gen_bi()

@@ -1,0 +1,206 @@
+"""`-bi` (block information): oracle vs files the reference wrote, host logic through a fake
+backend (no GPU), and the CUDA path through the C ABI (`-m gpu`)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import PORTABLE_ENV, ROOT, stage_e2e
+
+BI_CASES = ["cross", "tiny"]
+
+_ORACLE_CHILD = r"""
+import sys
+sys.path.insert(0, %r)
+from oracle import bi_oracle
+got = bi_oracle.block_info_csv("bi.conf")
+exp = open("expected.blockinfo.csv").read()
+assert got == exp, "oracle CSV differs from the reference's"
+print("OK", got.count("\n") - 1)
+"""
+
+# the product driver; FAKE=1 injects a numpy stand-in for the CUDA library (host-logic test without a GPU)
+_PRODUCT_CHILD = r"""
+import contextlib, io, os, sys
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+import numpy as np
+from wgdi_b200 import _bi, base
+from wgdi_b200.block_info import block_info
+if os.environ.get("FAKE") == "1":
+    from test_block_info import fake_block_stats
+    _bi.block_stats = fake_block_stats
+opts = [(k, v) for k, v in base.load_conf("bi.conf", "blockinfo") if k != "savefile"] + [("savefile", "got.csv")]
+if os.environ.get("INGEST"):
+    opts.append(("ingest", os.environ["INGEST"]))
+with contextlib.redirect_stdout(io.StringIO()):
+    b = block_info(opts)
+    b.run()
+got, exp = open("got.csv").read(), open("expected.blockinfo.csv").read()
+assert got == exp, "product CSV differs from the reference's"
+print("OK", got.count("\n") - 1, b.timing)
+"""
+
+
+def fake_block_stats(device, hit_off, hit_g2, hit_rank, hit_order2, blk_off, mem_g1, mem_g2, mem_order2, repeat_number):
+    """numpy/Python stand-in for icl_bi_block_stats with the semantics include/icl_blockinfo.h documents."""
+    B = len(blk_off) - 1
+    homo_sum = np.zeros((B, 5), np.int32)
+    homo_cnt = np.zeros(B, np.int32)
+    rows = np.zeros(B, np.int64)
+    uniq = np.zeros(B, np.int32)
+    for b in range(B):
+        a0, a1 = int(blk_off[b]), int(blk_off[b + 1])
+        subj = set(int(x) for x in mem_g2[a0:a1])
+        seen = set()
+        for j in range(a0, a1):
+            g1, g2 = int(mem_g1[j]), int(mem_g2[j])
+            if g1 < 0:
+                continue
+            for h in range(int(hit_off[g1]), int(hit_off[g1 + 1])):
+                t, r = int(hit_g2[h]), int(hit_rank[h])
+                if t == g2:
+                    homo_sum[b] += [1 if r < i else 0 if r < i + 5 else -1 for i in range(1, 6)]
+                    homo_cnt[b] += 1
+                if g2 >= 0 and t in subj and 0 < abs(int(hit_order2[h]) - int(mem_order2[j])) <= repeat_number:
+                    rows[b] += 1
+                    seen.add(g1)
+        uniq[b] = len(seen)
+    return homo_sum, homo_cnt, rows, uniq
+
+
+def _run_child(code, case, env_extra=None):
+    with tempfile.TemporaryDirectory() as d:
+        stage_e2e(case, d)
+        env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV, **(env_extra or {}))
+        r = subprocess.run([sys.executable, "-c", code], cwd=d, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "OK" in r.stdout
+        return r.stdout
+
+
+@pytest.mark.parametrize("case", BI_CASES)
+def test_bi_oracle_reproduces_reference_csv(case):
+    _run_child(_ORACLE_CHILD % ROOT, case)
+
+
+@pytest.mark.parametrize("case", BI_CASES)
+@pytest.mark.parametrize("ingest", ["native", "pandas"])
+def test_bi_host_logic_with_fake_backend(case, ingest):
+    """Parsing, ranking with the reference's tie order, frame assembly and CSV text — device statistics from a
+    numpy stand-in injected by the test."""
+    _run_child(_PRODUCT_CHILD % (ROOT, ROOT), case, {"FAKE": "1", "INGEST": ingest})
+
+
+def test_bi_library_exports_declared_symbols():
+    from wgdi_b200 import _bi, build
+    so = build.build_bi()
+    lib = ctypes.CDLL(so)
+    header = open(os.path.join(ROOT, "include", "icl_blockinfo.h")).read()
+    declared = set(re.findall(r"\b(icl_bi_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_bi.EXPORTS), declared ^ set(_bi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_rank_hits_is_the_reference_sort():
+    """rank_hits == per-query pandas-style nargsort (numpy's unstable sort) trimmed to repeat_number, with heavy ties."""
+    from wgdi_b200.engine import nargsort_desc
+    from wgdi_b200.ingest import rank_hits
+    rng = np.random.default_rng(11)
+    q = rng.integers(0, 400, 20000)
+    for bits in (rng.integers(100, 112, len(q)).astype(np.int64), rng.integers(100, 112, len(q)).astype(np.float64) / 2):
+        for rn in (3, 12, 20, 40):
+            got = rank_hits(q, bits, rn)
+            exp = np.full(len(q), -1, np.int64)
+            for g in np.unique(q):
+                rows = np.flatnonzero(q == g)
+                ranked = rows[nargsort_desc(bits[rows])][:rn]
+                exp[ranked] = np.arange(len(ranked))
+            assert (got == exp).all()
+
+
+def test_bi_without_gpu_fails_loudly():
+    from conftest import have_gpu
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    from wgdi_b200 import _bi
+    z = np.zeros(2, np.int64)
+    with pytest.raises(_bi.BiError):
+        _bi.block_stats(0, z, [], [], [], np.array([0, 1], np.int64), [0], [0], [0], 5)
+
+
+# ---- CUDA path ---------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", BI_CASES)
+def test_bi_cuda_writes_reference_csv(case):
+    _run_child(_PRODUCT_CHILD % (ROOT, ROOT), case)
+
+
+@pytest.mark.gpu
+def test_bi_cuda_kernel_equals_stand_in_on_random_blocks():
+    """icl_bi_block_stats vs the numpy stand-in on random blocks: unknown genes (-1), repeated id1 / id2 inside a
+    block, empty blocks, queries without hits."""
+    from wgdi_b200 import _bi
+    rng = np.random.default_rng(5)
+    n1, n2, rn = 500, 400, 7
+    per = rng.integers(0, rn + 1, n1)
+    hit_off = np.r_[0, np.cumsum(per)].astype(np.int64)
+    hit_g2 = np.concatenate([rng.choice(n2, k, replace=False) for k in per]).astype(np.int32)
+    hit_rank = np.concatenate([rng.permutation(k) for k in per]).astype(np.int32)
+    order_of2 = rng.integers(1, 120, n2).astype(np.int32)
+    sizes = rng.integers(0, 90, 300)
+    sizes[[0, 17]] = 0
+    blk_off = np.r_[0, np.cumsum(sizes)].astype(np.int64)
+    M = int(blk_off[-1])
+    mem_g1 = rng.integers(-1, 60, M).astype(np.int32)          # small range: repeated id1 inside a block
+    mem_g2 = rng.integers(-1, 80, M).astype(np.int32)
+    # make a fair share of members real hits
+    for j in range(0, M, 3):
+        g = int(rng.integers(0, n1))
+        if per[g]:
+            mem_g1[j] = g
+            mem_g2[j] = hit_g2[hit_off[g] + int(rng.integers(0, per[g]))]
+    mem_o2 = np.where(mem_g2 >= 0, order_of2[np.maximum(mem_g2, 0)], 0).astype(np.int32)
+    args = (0, hit_off, hit_g2, hit_rank, order_of2[hit_g2], blk_off, mem_g1, mem_g2, mem_o2, rn)
+    got = _bi.block_stats(*args)
+    exp = fake_block_stats(*args)
+    for a, b in zip(got, exp):
+        assert (a == b).all()
+    assert exp[1].sum() > 100 and exp[2].sum() > 100 and (exp[3] > 1).any()
+
+
+@pytest.mark.gpu
+def test_bi_cuda_on_icl_output_matches_oracle(tmp_path):
+    """-icl then -bi on a larger synthetic comparison, both through the CUDA libraries; CSV identical to the oracle's."""
+    import contextlib
+    import io
+    from oracle import bi_oracle
+    from wgdi_b200 import base, synth
+    from wgdi_b200.block_info import block_info
+    from wgdi_b200.run_colliearity import mycollinearity
+    d = str(tmp_path)
+    ds = synth.make_dataset("small")
+    conf = synth.write_dataset(ds, d)
+    opts = dict(base.load_conf(conf, "collinearity"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        try:
+            mycollinearity(list(opts.items())).run()
+        except SystemExit:
+            pass
+    bi = os.path.join(d, "bi.conf")
+    with open(bi, "w") as f:
+        f.write("[blockinfo]\n" + "".join(f"{k} = {opts[k]}\n" for k in ("blast", "gff1", "gff2", "lens1", "lens2")) +
+                f"collinearity = {opts['savefile']}\nscore = 100\nevalue = 1e-5\nrepeat_number = 20\nposition = order\n"
+                f"ks = none\nks_col = ks_NG86\nsavefile = {os.path.join(d, 'bi.csv')}\n")
+    with contextlib.redirect_stdout(io.StringIO()):
+        block_info(base.load_conf(bi, "blockinfo")).run()
+    got = open(os.path.join(d, "bi.csv")).read()
+    assert got.count("\n") > 50
+    assert got == bi_oracle.block_info_csv(bi)

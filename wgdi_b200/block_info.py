@@ -1,0 +1,181 @@
+"""Drop-in for the reference's `-bi` tool: `block_info(options).run()` (wgdi/block_info.py:6-165) for collinearity
+files in WGDI's own format (what `-icl` writes).  Same `[blockinfo]` options, same printed lines, same CSV.
+
+Where the reference loops over blocks and gene pairs in Python — one pandas lookup per gene pair and two `isin`
+scans of the whole BLAST table per block — the per-block integer statistics come from one CUDA launch over all
+blocks (include/icl_blockinfo.h); file parsing, the per-query hit rank (numpy's own sort where ties matter) and
+the CSV are host work.  Extra optional key: `device = <cuda index>`.
+"""
+from __future__ import annotations
+
+import re
+import time
+
+import numpy as np
+import pandas as pd
+
+from . import _bi, _host, base
+from .ingest import rank_hits
+
+
+def str_to_bool(s):
+    """wgdi/base.py:276-279."""
+    if isinstance(s, bool):
+        return s
+    return str(s).strip().lower() == 'true'
+
+
+def get_median(data):
+    """wgdi/base.py:154-160."""
+    if not data:
+        return 0
+    data_sorted = sorted(data)
+    half = len(data_sorted) // 2
+    return (data_sorted[half] + data_sorted[-(half + 1)]) / 2
+
+
+def read_ks(file, col):
+    """wgdi/base.py:144-151 — Series 'id1,id2' -> Ks (first occurrence of a pair, values >= 0)."""
+    ks = pd.read_csv(file, sep='\t')
+    ks = ks.drop_duplicates(subset=['id1', 'id2'], keep='first')
+    ks[col] = ks[col].astype(float)
+    ks = ks[ks[col] >= 0]
+    ks.index = ks['id1'] + ',' + ks['id2']
+    return ks[col]
+
+
+def read_collinearity_flat(fn):
+    """wgdi/base.py:120-141 with the blocks flattened: (ids, pvalues, offsets, name1, loc1, name2, loc2) where
+    ids / pvalues are the header strings `arr[0]` / `arr[2]` and block b owns members offsets[b]..offsets[b+1]."""
+    ids, pvs, off = [], [], [0]
+    n1, l1, n2, l2 = [], [], [], []
+    flag, arr, count = 0, [], 0
+    with open(fn) as f:
+        for line in f:
+            line = line.strip()
+            if line.startswith('# Alignment'):                     # re.match(r"# Alignment", line)
+                flag = 1
+                if count:
+                    ids.append(arr[0]); pvs.append(arr[2]); off.append(off[-1] + count)
+                    count = 0
+                arr = re.findall(r'[\.\d+]+', line)
+                continue
+            if flag == 0:
+                continue
+            k = re.split(r"\s", line)
+            n1.append(k[0]); l1.append(k[1]); n2.append(k[2]); l2.append(k[3])
+            count += 1
+        if count:
+            ids.append(arr[0]); pvs.append(arr[2]); off.append(off[-1] + count)
+    return ids, pvs, np.asarray(off, np.int64), n1, l1, n2, l2
+
+
+class block_info():
+    def __init__(self, options):
+        self.repeat_number = 20
+        self.ks_col = 'ks_NG86'
+        self.blast_reverse = False
+        for k, v in options:
+            setattr(self, str(k), v)
+            print(f"{k} = {v}")
+        self.repeat_number = int(self.repeat_number)
+        self.blast_reverse = str_to_bool(self.blast_reverse)
+        self.device = int(getattr(self, 'device', 0))
+        self.native = getattr(self, 'ingest', 'native').lower() != 'pandas' and _host.available()
+        self.timing = {}
+
+    def auto_file(self):
+        """wgdi/block_info.py:167-180: only WGDI's own format is offered here."""
+        with open(self.collinearity) as f:
+            p = ' '.join(f.readlines()[0:30])
+        if 'path length' in p or 'MAXIMUM GAP' in p or 'MATCH_SIZE' in p or '## Alignment' in p:
+            raise NotImplementedError("only WGDI-format collinearity files (as written by -icl) are supported")
+        if '# Alignment' in p:
+            return read_collinearity_flat(self.collinearity)
+        raise NotImplementedError("only WGDI-format collinearity files (as written by -icl) are supported")
+
+    def load_hits(self, gff1, gff2):
+        """base.newblast + blast_homo's trimming (block_info.py:149-150, :104-105): kept hits with their rank."""
+        if self.native:
+            ids1 = _host.pack_strings(gff1.index)
+            ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
+            hits = _host.read_m8(self.blast, self.blast_reverse, int(self.score), float(self.evalue), ids1, ids2)
+            g1, g2, bits = hits['g1'], hits['g2'], hits['bits']
+        else:
+            blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2,
+                                  'true' if self.blast_reverse else 'false')
+            g1, g2, bits = blast['g1'].to_numpy(), blast['g2'].to_numpy(), blast[11].to_numpy()
+        rank = rank_hits(g1, bits, self.repeat_number)
+        keep = rank >= 0
+        return g1[keep], g2[keep], rank[keep]
+
+    def run(self):
+        t0 = time.perf_counter()
+        lens1 = base.newlens(self.lens1, self.position)
+        lens2 = base.newlens(self.lens2, self.position)
+        gff1 = base.newgff(self.gff1)
+        gff2 = base.newgff(self.gff2)
+        gff1 = gff1[gff1['chr'].isin(lens1.index)]
+        gff2 = gff2[gff2['chr'].isin(lens2.index)]
+        g1, g2, rank = self.load_hits(gff1, gff2)
+        order2 = gff2['order'].to_numpy()
+        o = np.lexsort((rank, g1))
+        hit_off = np.zeros(len(gff1) + 1, np.int64)
+        np.cumsum(np.bincount(g1, minlength=len(gff1)), out=hit_off[1:])
+        ids, pvs, off, n1, l1, n2, l2 = self.auto_file()
+        ks = pd.Series([], dtype=float) if (not hasattr(self, 'ks') or self.ks == 'none' or self.ks == '') \
+            else read_ks(self.ks, self.ks_col)
+        m1 = gff1.index.get_indexer(pd.Index(n1, dtype=object)) if n1 else np.zeros(0, np.int64)
+        m2 = gff2.index.get_indexer(pd.Index(n2, dtype=object)) if n2 else np.zeros(0, np.int64)
+        mo2 = np.where(m2 >= 0, order2[np.maximum(m2, 0)], 0) if len(m2) else np.zeros(0, np.int64)
+        t1 = time.perf_counter()
+        homo_sum, homo_cnt, t_rows, t_uniq = _bi.block_stats(self.device, hit_off, g2[o], rank[o], order2[g2[o]] if len(o) else [],
+                                                             off, m1, m2, mo2, self.repeat_number)
+        t2 = time.perf_counter()
+        data = self.assemble(ids, pvs, off, n1, l1, n2, l2, m1, m2, gff1, gff2, ks, homo_sum, homo_cnt, t_rows, t_uniq)
+        data['class1'] = 0
+        data['class2'] = 0
+        data.to_csv(self.savefile, index=None)
+        t3 = time.perf_counter()
+        self.timing.update(ingest_s=t1 - t0, device_s=t2 - t1, write_s=t3 - t2, blocks=len(ids))
+
+    def assemble(self, ids, pvs, off, n1, l1, n2, l2, m1, m2, gff1, gff2, ks, homo_sum, homo_cnt, t_rows, t_uniq):
+        """The frame of block_position (block_info.py:18-75), built from the same Python values in the same order so
+        that pandas infers the same column types and `to_csv` prints the same text."""
+        chr1_of, chr2_of = gff1['chr'].to_numpy(), gff2['chr'].to_numpy()
+        have_ks = len(ks) > 0
+        ksd = dict(zip(ks.index.tolist(), ks.to_numpy())) if have_ks else {}
+        data = []
+        for b in range(len(ids)):
+            a0, a1 = int(off[b]), int(off[b + 1])
+            if m1[a0] < 0 or m2[a0] < 0:                             # :24-25
+                continue
+            L = a1 - a0
+            b1 = [int(float(v)) for v in l1[a0:a1]]
+            b2 = [int(float(v)) for v in l2[a0:a1]]
+            if have_ks:                                              # :40-41, :77-86
+                blk_ks = []
+                for x, y in zip(n1[a0:a1], n2[a0:a1]):
+                    v = ksd.get(f"{x},{y}")
+                    if v is None:
+                        v = ksd.get(f"{y},{x}", -1)
+                    blk_ks.append(v)
+                ks_arr = [k for k in blk_ks if k >= 0]               # :88-96
+                ks_median, ks_average = (get_median(ks_arr), sum(ks_arr) / len(ks_arr)) if ks_arr else (-1, -1)
+                blkks = '_'.join([str(k) for k in blk_ks])
+            else:
+                ks_median, ks_average, blkks = -1, -1, '_'.join(['-1'] * L)
+            cnt = int(homo_cnt[b])                                   # :98-100: mean over the pairs that are kept hits
+            homo = [np.float64(int(s)) / cnt for s in homo_sum[b]] if cnt > 0 else [-1, -1, -1, -1, -1]
+            R, U = int(t_rows[b]), int(t_uniq[b])
+            tandem_ratio = U / L * R / (L + R)                       # :134
+            data.append([ids[b], chr1_of[m1[a0]], chr2_of[m2[a0]], float(l1[a0]), float(l1[a1 - 1]), float(l2[a0]),
+                         float(l2[a1 - 1]), pvs[b], L, ks_median, ks_average, *homo,
+                         '_'.join([str(k) for k in b1]), '_'.join([str(k) for k in b2]), blkks, tandem_ratio])
+        data_df = pd.DataFrame(data, columns=[
+            'id', 'chr1', 'chr2', 'start1', 'end1', 'start2', 'end2', 'pvalue', 'length',
+            'ks_median', 'ks_average', 'homo1', 'homo2', 'homo3', 'homo4', 'homo5',
+            'block1', 'block2', 'ks', 'tandem_ratio'])
+        data_df['density1'] = data_df['length'] / ((data_df['end1'] - data_df['start1']).abs() + 1)     # :71-72
+        data_df['density2'] = data_df['length'] / ((data_df['end2'] - data_df['start2']).abs() + 1)
+        return data_df

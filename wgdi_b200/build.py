@@ -40,6 +40,22 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_bi(force=False, verbose=False):
+    """Device part of `-bi` (csrc/icl_blockinfo.cu -> libicl_bi_b200.so, include/icl_blockinfo.h)."""
+    src = os.path.join(HERE, "csrc", "icl_blockinfo.cu")
+    out = os.path.join(HERE, "libicl_bi_b200.so")
+    if not force and not _stale(out, [src, os.path.join(os.path.dirname(HERE), "include", "icl_blockinfo.h")]):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++", "-o", out, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return out
+
+
 def build_npsort(force=False):
     """CPython helper that calls numpy's own argsort routine from a thread pool (csrc/npsort.c)."""
     import sysconfig
@@ -79,5 +95,6 @@ if __name__ == "__main__":
         print(build_emu(sys.argv[2], force=True))
     else:
         print(build(force=True, verbose=True))
+        print(build_bi(force=True, verbose=True))
         print(build_npsort(force=True))
         print(build_host(force=True))

@@ -55,6 +55,40 @@ def grade_hits(q, bits, multiple, repeat_number, grading):
     return out
 
 
+def rank_hits(q, bits, repeat_number, class_bound=10):
+    """0-based per-query rank of every hit by bit score descending, -1 for hits beyond the first `repeat_number`
+    (`group.sort_values(by=11, ascending=False)[:repeat_number]`, wgdi/block_info.py:104 — the same unstable
+    single-key sort as the grading of -icl, hazard H2).  One stable lexsort; a query is re-ranked with the
+    reference's own numpy call when a run of tied scores could change what depends on the rank: the kept set
+    (a tie across rank repeat_number) or a class boundary (`class_bound`: -bi's homo classes switch at ranks 1..10)."""
+    q = np.asarray(q)
+    bits = np.asarray(bits)
+    n = len(q)
+    rn = int(repeat_number)
+    out = np.full(n, -1, np.int64)
+    if n == 0:
+        return out
+    o = np.lexsort((-bits, q))
+    qs, bs = q[o], bits[o]
+    new = np.r_[True, qs[1:] != qs[:-1]]
+    start = np.flatnonzero(new)
+    gid = np.cumsum(new) - 1
+    rank = np.arange(n) - start[gid]
+    out[o] = np.where(rank < rn, rank, -1)
+    same_next = np.r_[(qs[1:] == qs[:-1]) & (bs[1:] == bs[:-1]), False]      # element i ties with i+1 in its group
+    hit = same_next & ((rank < min(int(class_bound), rn)) | (rank == rn - 1))
+    amb = np.zeros(len(start), bool)
+    amb[gid[hit]] = True
+    if amb.any():
+        end = np.r_[start[1:], n]
+        for gi in np.flatnonzero(amb):
+            rows = np.sort(o[start[gi]:end[gi]])       # the query's hits in file order (groupby keeps row order)
+            ranked = rows[nargsort_desc(bits[rows])][:rn]
+            out[rows] = -1
+            out[ranked] = np.arange(len(ranked))
+    return out
+
+
 def grade_hits_native(q, bits, n_query, multiple, repeat_number, grading):
     """`grade_hits` with the per-query ranking done by libicl_host.so (stable order); queries whose class
     assignment depends on numpy's tie permutation are re-graded by `grade_hits` on exactly their hits."""

@@ -1,5 +1,5 @@
-"""Console entry point mirroring the `-icl` flag of the reference's dispatcher
-(wgdi/run.py:47 flag, :73-76 run_subprogram, :98 section name, :136/:150-152 `-icl ?`)."""
+"""Console entry point mirroring the `-icl` and `-bi` flags of the reference's dispatcher
+(wgdi/run.py:47 / :50 flags, :73-76 run_subprogram, :98 / :90 section names, :127 / :136 / :150-152 `-x ?`)."""
 from __future__ import annotations
 
 import argparse
@@ -18,23 +18,31 @@ def run_subprogram(program, conf, name):
 
 
 def main(argv=None):
-    parser = argparse.ArgumentParser(prog="wgdi_b200", description="B200-native `wgdi -icl` (improved collinearity)")
+    parser = argparse.ArgumentParser(prog="wgdi_b200", description="B200-native `wgdi -icl` (improved collinearity) and `-bi` (block information)")
     parser.add_argument("-icl", dest="improvedcollinearity", metavar="CONF",
                         help="improved collinearity; `?` prints an example conf")
+    parser.add_argument("-bi", dest="blockinfo", metavar="CONF",
+                        help="block information of a collinearity file; `?` prints an example conf")
     args = parser.parse_args(argv)
-    conf = args.improvedcollinearity
-    if conf is None:
+    tools = (("improvedcollinearity", "collinearity", "collinearity.conf"), ("blockinfo", "blockinfo", "blockinfo.conf"))
+    chosen = [(getattr(args, dest), section, example) for dest, section, example in tools if getattr(args, dest) is not None]
+    if not chosen:
         parser.print_help()
         return 0
-    if conf in ("?", "help", "example"):
-        with open(os.path.join(HERE, "example", "collinearity.conf")) as f:
-            print(f.read())
-        return 0
-    if not os.path.exists(conf):
-        print(f"{conf} not exists")                       # wgdi/run.py:156-158
-        return 0
-    from .run_colliearity import mycollinearity
-    run_subprogram(mycollinearity, conf, "collinearity")
+    for conf, section, example in chosen:
+        if conf in ("?", "help", "example"):
+            with open(os.path.join(HERE, "example", example)) as f:
+                print(f.read())
+            continue
+        if not os.path.exists(conf):
+            print(f"{conf} not exists")                   # wgdi/run.py:156-158
+            continue
+        if section == "collinearity":
+            from .run_colliearity import mycollinearity
+            run_subprogram(mycollinearity, conf, section)
+        else:
+            from .block_info import block_info
+            run_subprogram(block_info, conf, section)
     return 0
 
 
