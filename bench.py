@@ -147,10 +147,28 @@ def icl_wall_time(workload, device):
             if best is None or dt < best:
                 best, timing, native = dt, m.timing, m.native
         out_mb = os.path.getsize(dict(opts)["savefile"]) / 1e6
-        return {"value": best, "unit": "s", "what": "conf in -> collinearity file out, best of 2, files in tmpfs",
-                "blast_rows": int(len(ds.q)), "blast_mb": round(blast_mb, 1), "out_mb": round(out_mb, 1),
-                "ingest_s": timing.get("ingest_s"), "chain_s": timing.get("chain_s"), "write_s": timing.get("write_s"),
-                "host_path": "native (libicl_host.so)" if native else "pandas"}
+        res = {"value": best, "unit": "s", "what": "conf in -> collinearity file out, best of 2, files in tmpfs",
+               "blast_rows": int(len(ds.q)), "blast_mb": round(blast_mb, 1), "out_mb": round(out_mb, 1),
+               "ingest_s": timing.get("ingest_s"), "chain_s": timing.get("chain_s"), "write_s": timing.get("write_s"),
+               "host_path": "native (libicl_host.so)" if native else "pandas"}
+        # the tool every user runs next: `-bi` on the file just written, conf in -> CSV out
+        try:
+            from wgdi_b200.block_info import block_info
+            o = dict(opts)
+            bi = [(k, o[k]) for k in ("blast", "gff1", "gff2", "lens1", "lens2")] + [
+                ("collinearity", o["savefile"]), ("score", "100"), ("evalue", "1e-5"), ("repeat_number", "20"),
+                ("position", "order"), ("ks", "none"), ("ks_col", "ks_NG86"), ("savefile", os.path.join(d, "blockinfo.csv")),
+                ("device", str(device))]
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                b = block_info(bi)
+                b.run()
+            res["bi_wall"] = {"value": time.perf_counter() - t0, "unit": "s", "what": "-bi conf in -> block-information CSV out",
+                              "blocks": b.timing.get("blocks"), "ingest_s": b.timing.get("ingest_s"),
+                              "device_s": b.timing.get("device_s"), "write_s": b.timing.get("write_s")}
+        except Exception as e:                         # the -icl numbers above stand on their own
+            res["bi_wall"] = {"error": f"{type(e).__name__}: {e}"}
+        return res
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

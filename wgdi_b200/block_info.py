@@ -44,29 +44,40 @@ def read_ks(file, col):
     return ks[col]
 
 
+_ODD_SPACE = re.compile(r"[^\S \n]")      # whitespace other than ' ' and the line ends
+_HEADER_NUM = re.compile(r'[\.\d+]+')
+
+
 def read_collinearity_flat(fn):
-    """wgdi/base.py:120-141 with the blocks flattened: (ids, pvalues, offsets, name1, loc1, name2, loc2) where
-    ids / pvalues are the header strings `arr[0]` / `arr[2]` and block b owns members offsets[b]..offsets[b+1]."""
+    r"""wgdi/base.py:120-141 with the blocks flattened: (ids, pvalues, offsets, name1, loc1, name2, loc2) where
+    ids / pvalues are the header strings `arr[0]` / `arr[2]` and block b owns members offsets[b]..offsets[b+1].
+    The reference splits member lines with re.split(r"\s", line): one split per whitespace character.  When the
+    file holds no whitespace besides ' ' and newlines that is str.split(' '), which is what the fast path uses."""
+    with open(fn) as f:
+        text = f.read()
+    plain = _ODD_SPACE.search(text) is None
     ids, pvs, off = [], [], [0]
     n1, l1, n2, l2 = [], [], [], []
     flag, arr, count = 0, [], 0
-    with open(fn) as f:
-        for line in f:
-            line = line.strip()
-            if line.startswith('# Alignment'):                     # re.match(r"# Alignment", line)
-                flag = 1
-                if count:
-                    ids.append(arr[0]); pvs.append(arr[2]); off.append(off[-1] + count)
-                    count = 0
-                arr = re.findall(r'[\.\d+]+', line)
-                continue
-            if flag == 0:
-                continue
-            k = re.split(r"\s", line)
-            n1.append(k[0]); l1.append(k[1]); n2.append(k[2]); l2.append(k[3])
-            count += 1
-        if count:
-            ids.append(arr[0]); pvs.append(arr[2]); off.append(off[-1] + count)
+    lines = text.split('\n')
+    if lines and lines[-1] == '':                                  # file iteration yields no line after the last newline
+        lines.pop()
+    for line in lines:
+        line = line.strip()
+        if line.startswith('# Alignment'):                         # re.match(r"# Alignment", line)
+            flag = 1
+            if count:
+                ids.append(arr[0]); pvs.append(arr[2]); off.append(off[-1] + count)
+                count = 0
+            arr = _HEADER_NUM.findall(line)
+            continue
+        if flag == 0:
+            continue
+        k = line.split(' ') if plain else re.split(r"\s", line)
+        n1.append(k[0]); l1.append(k[1]); n2.append(k[2]); l2.append(k[3])
+        count += 1
+    if count:
+        ids.append(arr[0]); pvs.append(arr[2]); off.append(off[-1] + count)
     return ids, pvs, np.asarray(off, np.int64), n1, l1, n2, l2
 
 
@@ -145,14 +156,25 @@ class block_info():
         chr1_of, chr2_of = gff1['chr'].to_numpy(), gff2['chr'].to_numpy()
         have_ks = len(ks) > 0
         ksd = dict(zip(ks.index.tolist(), ks.to_numpy())) if have_ks else {}
+        # float(k[1]) / int(float(k[1])) / str(...) of :31, :37-38, :51-52 for all members at once
+        f1 = np.asarray(l1, dtype=np.float64) if l1 else np.zeros(0)
+        f2 = np.asarray(l2, dtype=np.float64) if l2 else np.zeros(0)
+        s1 = f1.astype(np.int64).astype(str).tolist()
+        s2 = f2.astype(np.int64).astype(str).tolist()
+        f1, f2 = f1.tolist(), f2.tolist()
+        # :98-100 mean over the pairs that are kept hits; :134 tandem ratio — same IEEE operations as the Python floats
+        Ls = np.diff(off).astype(np.int64)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            hmean = (homo_sum.astype(np.float64) / homo_cnt[:, None]).tolist()
+            tandem = (t_uniq / Ls * t_rows / (Ls + t_rows)).tolist()
+        cnts = homo_cnt.tolist()
+        none5 = [-1, -1, -1, -1, -1]
         data = []
         for b in range(len(ids)):
             a0, a1 = int(off[b]), int(off[b + 1])
             if m1[a0] < 0 or m2[a0] < 0:                             # :24-25
                 continue
             L = a1 - a0
-            b1 = [int(float(v)) for v in l1[a0:a1]]
-            b2 = [int(float(v)) for v in l2[a0:a1]]
             if have_ks:                                              # :40-41, :77-86
                 blk_ks = []
                 for x, y in zip(n1[a0:a1], n2[a0:a1]):
@@ -165,13 +187,9 @@ class block_info():
                 blkks = '_'.join([str(k) for k in blk_ks])
             else:
                 ks_median, ks_average, blkks = -1, -1, '_'.join(['-1'] * L)
-            cnt = int(homo_cnt[b])                                   # :98-100: mean over the pairs that are kept hits
-            homo = [np.float64(int(s)) / cnt for s in homo_sum[b]] if cnt > 0 else [-1, -1, -1, -1, -1]
-            R, U = int(t_rows[b]), int(t_uniq[b])
-            tandem_ratio = U / L * R / (L + R)                       # :134
-            data.append([ids[b], chr1_of[m1[a0]], chr2_of[m2[a0]], float(l1[a0]), float(l1[a1 - 1]), float(l2[a0]),
-                         float(l2[a1 - 1]), pvs[b], L, ks_median, ks_average, *homo,
-                         '_'.join([str(k) for k in b1]), '_'.join([str(k) for k in b2]), blkks, tandem_ratio])
+            homo = hmean[b] if cnts[b] > 0 else none5
+            data.append([ids[b], chr1_of[m1[a0]], chr2_of[m2[a0]], f1[a0], f1[a1 - 1], f2[a0], f2[a1 - 1], pvs[b], L,
+                         ks_median, ks_average, *homo, '_'.join(s1[a0:a1]), '_'.join(s2[a0:a1]), blkks, tandem[b]])
         data_df = pd.DataFrame(data, columns=[
             'id', 'chr1', 'chr2', 'start1', 'end1', 'start2', 'end2', 'pvalue', 'length',
             'ks_median', 'ks_average', 'homo1', 'homo2', 'homo3', 'homo4', 'homo5',
