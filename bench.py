@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wall", action="store_true")
+    ap.add_argument("--batch", type=int, default=8, help="comparisons in the pipelined-batch leg (0 = skip)")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("ICL_BENCH_LANES", "1")),
                     help="pipelined lanes per GPU (wgdi_b200/pipeline.py); 1 = plain engine")
     args = ap.parse_args()
@@ -343,6 +344,30 @@ def main():
             step_resident()
         dp_only_ms = float(np.mean(dev_ms["chain"]))
         eng.stream_rank = True
+    # ---- batch throughput (BASELINE config 5 shape): independent comparisons through two engines on this GPU, one
+    # job's host rank overlapping the next job's upload + device phases (wgdi_b200/batch.py); every job uploads
+    batch = None
+    if args.batch > 0 and args.lanes <= 1:
+        from wgdi_b200.batch import BatchRunner
+        runner = BatchRunner(local, depth=2, sort_threads=sort_threads)
+        try:
+            jobs = [(dict(pts), prm) for _ in range(args.batch)]
+            runner.run(jobs[:2], min_members=5, consume=lambda i, b: len(b))   # warm-up: buffers, sort pool
+            barrier()
+            t0 = time.perf_counter()
+            outs = runner.run(jobs, min_members=5, consume=lambda i, b: len(b))     # blocks handed over as views, like the file writer takes them
+            torch.cuda.synchronize()
+            t_batch = time.perf_counter() - t0
+            assert all(o == outs[0] for o in outs)
+        finally:
+            runner.close()
+        if world > 1:
+            tb = torch.tensor([t_batch], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            t_batch = float(tb.item())
+        batch = {"value": total_points * args.batch / t_batch, "unit": "hits/s", "comparisons": args.batch * world,
+                 "ms_per_comparison": 1e3 * t_batch / args.batch, "engines_per_gpu": 2,
+                 "what": "independent comparisons pipelined through two engines per GPU, each job uploads its points"}
     clocks = sampler.stop() if rank == 0 else None
     counters = eng.counters()
 
@@ -394,7 +419,7 @@ def main():
                              "frac": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9 / peak,
                              "what": "same kernel with the export epilogue off (ICL_B200_STREAM=0), 3 extra untimed passes"},
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
-            "phase_ms": res_ms,
+            "phase_ms": res_ms, "batch": batch,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }

@@ -329,6 +329,33 @@ def test_streamed_rank_equals_two_step_rank(gpu_engine):
     _compare_with_oracle(b1, [(2 * p, d, l1, l2, a, sc) for p, d, l1, l2, a, sc in oracle_blocks(pts, prm)])
 
 
+def test_batch_runner_equals_one_engine(gpu_engine):
+    """Config 5 shape: several comparisons x an mg sweep through two engines on one GPU (one job's host rank overlaps
+    the next job's device phases); every job's blocks equal those of a lone engine."""
+    from dataclasses import replace
+    from wgdi_b200 import synth
+    from wgdi_b200.batch import BatchRunner, sweep_jobs
+    from wgdi_b200.engine import ChainParams
+    comps = [synth.graded_points(synth.make_dataset(name)) for name in ("tiny", "cross", "small")]
+    jobs = []
+    for pts in comps:
+        j, keys = sweep_jobs(pts, [(50, 30, 25), (50, 40, 25)], [(25, 25), (40, 40), (50, 50)], [0.05, 0.2, 1])
+        assert len(j) == 6 and len(keys[0][2]) == 3
+        jobs += j
+    runner = BatchRunner(0, depth=2, sort_threads=4)
+    try:
+        got = runner.run(jobs, min_members=1)
+    finally:
+        runner.close()
+    assert len(got) == len(jobs) == 18
+    for (pts, prm), b in zip(jobs, got):
+        exp = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+        assert len(b) == len(exp)
+        for name in ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
+            assert (getattr(b, name) == getattr(exp, name)).all(), name
+    _compare_with_oracle(got[0], oracle_blocks(comps[0], jobs[0][1]))
+
+
 def test_alternative_dp_kernels_agree(clouds):
     """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth

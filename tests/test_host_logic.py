@@ -335,3 +335,29 @@ def test_grade_hits_chromosomes_matches_oracle():
             grade_hits_chromosomes(name_rank, g1, g2, pair, bits, bad[0], bad[1], (50, 30, 25))
         with pytest.raises(ValueError):
             icl_oracle.grade_hits_chromosomes(names[g1], g2, pair, bits, bad[0], bad[1], (50, 30, 25))
+
+
+def test_batch_runner_emu(emu_backend):
+    """BatchRunner (two engines, two host threads, shared sort pool) returns every job's blocks in job order,
+    identical to a lone engine; a failing job raises in the caller."""
+    from wgdi_b200 import synth
+    from wgdi_b200.batch import BatchRunner, sweep_jobs
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("tiny"))
+    jobs, _ = sweep_jobs(pts, [(50, 30, 25)], [(25, 25), (40, 40), (10, 15)], [1])
+    runner = BatchRunner(0, depth=2, sort_threads=2)
+    try:
+        got = runner.run(jobs)
+        bad = dict(pts, loc1=pts["loc1"][:-1])
+        with pytest.raises(ValueError):
+            runner.run(jobs[:1] + [(bad, jobs[0][1])])
+    finally:
+        runner.close()
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        for (p_, prm), b in zip(jobs, got):
+            exp = eng.chain(p_["pair_id"], p_["loc1"], p_["loc2"], p_["grading"], p_["n_pairs"], prm)
+            assert len(b) == len(exp) > 0 and (b.p_raw == exp.p_raw).all() and (b.loc1 == exp.loc1).all()
+    finally:
+        eng.close()
+    assert len({len(b) for b in got}) > 1                  # the mg sweep really changes the result

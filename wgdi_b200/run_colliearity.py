@@ -102,20 +102,22 @@ class mycollinearity():
         try:
             for c1, c2 in pts['pair_names']:
                 print(f'Running {c1} vs {c2}')            # :162
+            # blocks are views of the engine's page-locked staging: written out before the engine is closed
             blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params,
-                               min_members=self.over_gap, copy=True)
+                               min_members=self.over_gap, copy=False)
             self.timing['device_ms'] = eng.timings()
             self.timing['host_ms'] = dict(eng.host_ms)
+            t2 = time.perf_counter()
+            if self.native:
+                write_blocks_native(self.savefile, blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue,
+                                    self.over_gap)
+            else:
+                text = format_blocks(blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue, self.over_gap)
+                with open(self.savefile, 'w') as fout:
+                    fout.write(text)
+            del blocks
         finally:
             eng.close()
-        t2 = time.perf_counter()
-        if self.native:
-            write_blocks_native(self.savefile, blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue,
-                                self.over_gap)
-        else:
-            text = format_blocks(blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue, self.over_gap)
-            with open(self.savefile, 'w') as fout:
-                fout.write(text)
         t3 = time.perf_counter()
         self.timing.update(ingest_s=t1 - t0, chain_s=t2 - t1, write_s=t3 - t2)
         sys.exit(0)                                       # :156
