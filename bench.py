@@ -33,8 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DP_BYTES_PER_POINT = 42          # 2 directions x [12 B read + 9 B written]
-EXPORT_BYTES_PER_POINT = 12      # streamed export epilogue of the DP kernel: HBM reads of 2 x score (4 B) + mirror map (4 B);
-                                 # its 8 B/point of writes go to page-locked host memory over PCIe and are not counted
+EXPORT_BYTES_PER_POINT = 4       # streamed export of the DP kernel: the mirrored direction reads its position map (4 B);
+                                 # the 8 B/point of score writes go to page-locked host memory over PCIe and are not counted
 METRIC = "blast_hits_chained_per_sec"
 NCU_TRAFFIC_C2 = 87.1e6          # bytes per launch of the DP kernel (with its export epilogue) on C2: ncu capture, profiles/r01_chain_ring_ncu_summary.md
 

@@ -762,7 +762,7 @@ struct ChainArgs {
     // page-locked buffers and posts its id, so the host can sort it while heavier items are still running
     int32_t *hkey_fwd, *hkey_rev;    // device-visible host memory, NULL = no streaming
     volatile int32_t *hqueue;        // [items] completion flags in host memory
-    const int32_t *mmap;             // forward position -> mirrored position
+    const int32_t *imap;             // mirrored position - n -> forward position
 };
 
 // the reference sweep over the flat edge stream of one item, on global memory (oversized windows, emulation)
@@ -828,28 +828,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
-// Epilogue of a finished item (all 64 threads of the CTA): the item's final scores in REVERSED (loc1, loc2) order
-// — the array pandas' nargsort(ascending=False) hands to numpy.argsort — go to the caller's page-locked buffer
-// with coalesced stores over PCIe, then the item's completion flag is raised.
-__device__ __forceinline__ void stream_out(const ChainArgs &A, int32_t it, int32_t p, int tid, int nthreads) {
-    __syncthreads();                                              // the helper has written every S of the item
-    const uint32_t f0 = (uint32_t)A.off[p], f1 = (uint32_t)A.off[p + 1], len = f1 - f0;
-    if (it < A.P) {
-        int32_t *dst = A.hkey_fwd + f0;
-        for (uint32_t i = tid; i < len; i += nthreads) dst[i] = __ldcg(A.S + (f1 - 1 - i));
-    } else {
-        int32_t *dst = A.hkey_rev + f0;
-#pragma unroll 4
-        for (uint32_t i = tid; i < len; i += nthreads) dst[i] = __ldcg(A.S + __ldg(A.mmap + (f1 - 1 - i)));
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-        A.hqueue[it] = 1;
-        __threadfence_system();
-    }
 }
 
 // One CTA per (pair, direction) item: warp 0 lane 0 is the executor, warp 1 the helper.
@@ -1020,7 +998,6 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 A.dbg[4 * blockIdx.x + 2] = t_wait; A.dbg[4 * blockIdx.x + 3] = e1 - e0;
             }
             if (lane == 0) ctl_retired = b;
-            if (A.hqueue) stream_out(A, it, p, threadIdx.x, 64);     // joins the helper warp in the epilogue
             return;
         }
         // ---------------------------------------------------------------- executor (one thread)
@@ -1088,6 +1065,14 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         return;
     }
     // -------------------------------------------------------------------- helper warp
+    // streamed export (icl_dp_begin): the score of every retired point also goes straight to the caller's page-locked
+    // buffer, at its place in the REVERSED (loc1, loc2) order of the pair — the array pandas' nargsort(ascending=False)
+    // hands to numpy.argsort.  Forward items: 32 consecutive points are 128 contiguous bytes; mirrored items visit the
+    // rows in the same order as the reversed forward order and only run the other way inside a row, so a warp's 32
+    // stores still cover one contiguous range (up to the rows cut at its ends).
+    const bool mirrored = it >= A.P;
+    int32_t *hk = (BATCH && A.hqueue) ? (mirrored ? A.hkey_rev : A.hkey_fwd) : nullptr;
+    const uint32_t hbase = (uint32_t)A.off[p] + (uint32_t)A.off[p + 1] - 1u;
     uint32_t wb = a, ld = a;
     uint32_t next_chunk = c0;
     const uint32_t last_chunk = e1 > e0 ? (e1 - 1) / ICL_EDGE_CHUNK : c0;
@@ -1121,6 +1106,7 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 A.pd[v] = (sl.x != g) ? make_int2(sl.z, sl.y & 0x7fffffff) : make_int2(-1, 1);
                 A.root[v] = sl.w;
                 A.used[v] = (sl.x != g) || (sl.y < 0);
+                if (hk) hk[hbase - (mirrored ? (uint32_t)__ldg(A.imap + (v - (uint32_t)A.n)) : v)] = sl.x;
             }
             wb = r;
             progress = true;
@@ -1139,7 +1125,14 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
         }
         if (!progress) __nanosleep(100);
     }
-    if (BATCH && A.hqueue) stream_out(A, it, p, threadIdx.x, 64);
+    if (hk) {                                         // every score of the item is on its way: raise the completion flag
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            A.hqueue[it] = 1;
+            __threadfence_system();
+        }
+    }
 }
 #endif
 
@@ -1155,7 +1148,7 @@ static int phase_chain(icl_ctx *c) {
     A.order = c->d_item_order.p; A.G = c->G.p; A.off = c->d_pair_off.p; A.eoff = c->eoff.p; A.edges = c->edges.p;
     A.S = c->S.p; A.pd = c->pd.p; A.used = c->used.p; A.root = c->root.p;
     A.dbg = nullptr;
-    A.hkey_fwd = A.hkey_rev = nullptr; A.hqueue = nullptr; A.mmap = c->mmap.p;
+    A.hkey_fwd = A.hkey_rev = nullptr; A.hqueue = nullptr; A.imap = c->imap.p;
     c->streamed = false;
     if (getenv("ICL_B200_CHAIN_DEBUG")) {
         if (c->chain_dbg.reserve(st, 8 * (size_t)P + 8)) return st.code;
