@@ -1439,52 +1439,90 @@ static int phase_extract(icl_ctx *c) {
             if (t0 > 0 && key[t0 - 1] == rt) return;                            // not the head of its tree
             int32_t ver = 0;                                                    // accepted blocks of this tree so far
             uint32_t cursor = (uint32_t)t0;                                     // member scratch: the tree's own slice
-            for (int64_t u = t0; u < V && key[u] == rt; u++) {                  // the tree's points in rank order
-                const uint32_t t = tpos[u];
-                const int32_t top = rank2v[t];
-                if (!present[top]) continue;
-                const int2 nd = ICL_LDG(pd + top);
-                const int32_t L = nd.y;
-                int32_t m, q;
-                if (ver == 0) {
-                    m = L;                                                      // nothing of this tree removed yet
-                } else {
-                    const int2 h = hint[top];
-                    if (h.y == ver) m = L - h.x;                                // boundary known from a rejected child
-                    else {
+            // end of the tree's run of equal keys: gallop, then bisect
+            int64_t lo = t0 + 1, step = 1, uend;
+            while (lo < V && key[lo] == rt) { lo += step; step <<= 1; }
+            {
+                int64_t a0 = lo - (step >> 1), b0 = lo < V ? lo : V;             // key[a0 - 1] == rt (or a0 == t0 + 1), key[b0] != rt
+                if (a0 < t0 + 1) a0 = t0 + 1;
+                while (a0 < b0) {
+                    const int64_t mid = a0 + ((b0 - a0) >> 1);
+                    if (key[mid] == rt) a0 = mid + 1; else b0 = mid;
+                }
+                uend = a0;
+            }
+            // The tops of a tree are examined strictly in rank order, but everything a top needs except `present` and
+            // the memo is read-only here, and those two only change for OTHER tops when a block is accepted (ver++).
+            // So the loads run three tops ahead of the decisions (rank position at distance 3, point at 2, node record
+            // + present + memo at 1) and a prefetched present / memo is re-read only if a block was accepted since.
+            // A memo fetched before a rejected child wrote it is merely older: it is used only when its version
+            // matches, otherwise the path is walked — both are exact.
+            uint32_t tA = tpos[t0];
+            uint32_t tB = t0 + 1 < uend ? tpos[t0 + 1] : 0u, tC = t0 + 2 < uend ? tpos[t0 + 2] : 0u, tD = t0 + 3 < uend ? tpos[t0 + 3] : 0u;
+            int32_t topA = rank2v[tA], topB = t0 + 1 < uend ? rank2v[tB] : 0, topC = t0 + 2 < uend ? rank2v[tC] : 0;
+            int2 ndA = ICL_LDG(pd + topA), hA = hint[topA];
+            uint8_t prA = present[topA];
+            int32_t verA = 0, verB = 0;
+            int2 ndB = make_int2(0, 0), hB = make_int2(0, 0);
+            uint8_t prB = 0;
+            if (t0 + 1 < uend) { ndB = ICL_LDG(pd + topB); hB = hint[topB]; prB = present[topB]; }
+            for (int64_t u = t0; u < uend; u++) {                               // the tree's points in rank order
+                const uint32_t tE = u + 4 < uend ? tpos[u + 4] : 0u;
+                const int32_t topD = u + 3 < uend ? rank2v[tD] : 0;
+                int2 ndC = make_int2(0, 0), hC = make_int2(0, 0);
+                uint8_t prC = 0;
+                const int32_t verC = ver;
+                if (u + 2 < uend) { ndC = ICL_LDG(pd + topC); hC = hint[topC]; prC = present[topC]; }
+                const uint32_t t = tA;
+                const int32_t top = topA;
+                const int2 nd = ndA;
+                uint8_t pr = prA;
+                int2 h = hA;
+                if (verA != ver) { pr = present[top]; h = hint[top]; }
+                if (pr) {
+                    const int32_t L = nd.y;
+                    int32_t m, q;
+                    if (ver == 0) {
+                        m = L;                                                  // nothing of this tree removed yet
+                    } else if (h.y == ver) {
+                        m = L - h.x;                                            // boundary known from a rejected child
+                    } else {
                         m = 1; q = nd.x;
                         while (q >= 0 && present[q]) { m++; q = ICL_LDG(pd + q).x; }     // present part of the path
                     }
-                }
-                if (L >= over_gap && (double)m / (double)L > cov) {             // :129
-                    // remove the members (:130), list them, bounding box (:131)
-                    const bool rev = top >= n;
-                    int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
-                    q = top;
-                    for (int32_t k = 0; k < m; k++) {
-                        present[q] = 0;
-                        const int32_t i = rev ? imap[q - n] : q;                // forward sorted position
-                        mscr[cursor + k] = i;
-                        const int32_t yv = l2[i];
-                        l2min = yv < l2min ? yv : l2min;
-                        l2max = yv > l2max ? yv : l2max;
-                        if (k == 0) ifirst = i;
-                        ilast = i;
-                        q = ICL_LDG(pd + q).x;
+                    if (L >= over_gap && (double)m / (double)L > cov) {         // :129
+                        // remove the members (:130), list them, bounding box (:131)
+                        const bool rev = top >= n;
+                        int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
+                        q = top;
+                        for (int32_t k = 0; k < m; k++) {
+                            present[q] = 0;
+                            const int32_t i = rev ? imap[q - n] : q;            // forward sorted position
+                            mscr[cursor + k] = i;
+                            const int32_t yv = l2[i];
+                            l2min = yv < l2min ? yv : l2min;
+                            l2max = yv > l2max ? yv : l2max;
+                            if (k == 0) ifirst = i;
+                            ilast = i;
+                            q = ICL_LDG(pd + q).x;
+                        }
+                        ver++;                                                  // removed ancestors changed: memos expire
+                        const int32_t la = l1[ifirst], lb = l1[ilast];
+                        acc_m[t] = (uint32_t)m;
+                        acc_L[t] = L;
+                        acc_ms[t] = cursor;
+                        acc_box[t] = make_int4(la < lb ? la : lb, la < lb ? lb : la, l2min, l2max);
+                        cursor += (uint32_t)m;
+                    } else {
+                        present[top] = 0;                                       // :143
+                        // the parent sees the same removed ancestor until the next accepted block of this tree;
+                        // without the memo a long path whose root side was taken by another block costs O(L^2) hops
+                        if (m > 1) hint[nd.x] = make_int2(L - m, ver);
                     }
-                    ver++;                                                      // removed ancestors changed: memos expire
-                    const int32_t la = l1[ifirst], lb = l1[ilast];
-                    acc_m[t] = (uint32_t)m;
-                    acc_L[t] = L;
-                    acc_ms[t] = cursor;
-                    acc_box[t] = make_int4(la < lb ? la : lb, la < lb ? lb : la, l2min, l2max);
-                    cursor += (uint32_t)m;
-                } else {
-                    present[top] = 0;                                           // :143
-                    // the parent sees the same removed ancestor until the next accepted block of this tree;
-                    // without the memo a long path whose root side was taken by another block costs O(L^2) hops
-                    if (m > 1) hint[nd.x] = make_int2(L - m, ver);
                 }
+                tA = tB; topA = topB; ndA = ndB; hA = hB; prA = prB; verA = verB;
+                tB = tC; topB = topC; ndB = ndC; hB = hC; prB = prC; verB = verC;
+                tC = tD; topC = topD; tD = tE;
             }
         }));
     }
