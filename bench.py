@@ -36,7 +36,7 @@ DP_BYTES_PER_POINT = 42          # 2 directions x [12 B read + 9
 EXPORT_BYTES_PER_POINT = 4       # streamed export of the DP kernel: the mirrored direction reads its position map (4 B);
                                  # the 8 B/point of score writes go to page-locked host memory over PCIe and are not counted
 METRIC = "blast_hits_chained_per_sec"
-NCU_TRAFFIC_C2 = 87.1e6          # bytes per launch of the DP kernel (with its export epilogue) on C2: ncu capture, profiles/r01_chain_ring_ncu_summary.md
+NCU_TRAFFIC_C2 = 81.3e6          # bytes per launch of the DP kernel (with its export epilogue) on C2: ncu capture, profiles/r01_chain_ring_ncu_summary.md
 
 
 def peaks():
@@ -351,7 +351,7 @@ def main():
         from wgdi_b200.batch import BatchRunner
         runner = BatchRunner(local, depth=2, sort_threads=sort_threads)
         try:
-            jobs = [(dict(pts), prm) for _ in range(args.batch)]
+            jobs = [(dict(host_in, n_pairs=pts["n_pairs"]), prm) for _ in range(args.batch)]   # page-locked inputs, as in the e2e leg
             runner.run(jobs[:2], min_members=5, consume=lambda i, b: len(b))   # warm-up: buffers, sort pool
             barrier()
             t0 = time.perf_counter()
@@ -417,7 +417,7 @@ def main():
                              "kernel_ms": dp_only_ms, "algorithmic_bytes": DP_BYTES_PER_POINT * n_local,
                              "achieved": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9,
                              "frac": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9 / peak,
-                             "what": "same kernel with the export epilogue off (ICL_B200_STREAM=0), 3 extra untimed passes"},
+                             "what": "same kernel with the streamed export off (ICL_B200_STREAM=0), 3 extra untimed passes"},
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
             "phase_ms": res_ms, "batch": batch,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
