@@ -268,7 +268,7 @@ def main():
     n_local = len(pts["loc1"])
 
     # the host rank (numpy's argsort) is per-rank host work: split the box's cores between the ranks
-    sort_threads = max(1, (os.cpu_count() or 1) // world)
+    sort_threads = int(os.environ.get("ICL_BENCH_SORT_THREADS", 0)) or max(1, (os.cpu_count() or 1) // world)
     if args.lanes > 1:
         from wgdi_b200.pipeline import PipelinedEngine
         eng = PipelinedEngine(local, lanes=args.lanes, sort_threads=sort_threads)
