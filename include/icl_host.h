@@ -38,6 +38,10 @@ typedef struct icl_hits {
  * both ids present in the gene tables (:179), first occurrence of every (id1, id2) in file order (:180).
  * reverse != 0 swaps the two id columns first (base.py:176-177; the caller passes 1 only for the exact string
  * 'true').  Gene tables: concatenated id bytes + offsets[n+1].
+ * Numbers: exact (correctly rounded) conversion; identical to pandas' parser for tokens of up to 15 significant
+ * digits, which covers everything BLAST prints (pandas' default converter is itself an ulp off for some longer ones
+ * and for very large exponents, e.g. it reads "1.00e-300" as 9.999999999999999e-301 — relevant only if the e-value
+ * limit itself were such a number).
  */
 int icl_host_read_m8(const char *path, int32_t reverse, double min_score, double max_evalue,
                      const char *ids1, const int64_t *off1, int64_t n1,

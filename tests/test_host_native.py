@@ -83,6 +83,37 @@ def test_read_m8_filters_like_newblast(host, tmp_path):
     assert len(host.read_m8(str(tmp_path / "empty.m8"), False, 100, 1e-5, ids, ids)["g1"]) == 0
 
 
+def test_read_m8_number_forms_near_the_thresholds(host, tmp_path):
+    """The reader decides `evalue < limit` from an extended-precision estimate unless the token is within a hair of
+    the limit, and converts bit scores on a fast exact path: both must agree with pandas' parser for every spelling."""
+    import pandas as pd
+    from wgdi_b200 import base
+    # tokens of at most 15 significant digits: beyond that pandas' default parser is itself off by an ulp now and then
+    # ("9.999999999999999e-06" reads as 1e-05) and BLAST never prints such numbers
+    evs = ["1e-5", "1E-05", "0.00001", "1.00000000000001e-05", "9.99999999999999e-06", "0.999999999999999e-5",
+           "99999999999999e-19", "100000000000001e-19", "1e-400", "0", "0.0", "0e0", "-1e-3", "+2e-7",
+           "1e-05", "9.9e-6", "1.1e-5", "1e+2", "123456789012345e-27", ".5e-5", "5.e-6", "7e-006", "1.00e-300", "4.2e-161"]
+    scs = ["100", "99.9999999999999", "100.000000000001", "1e2", "100.0", "0100", "+250", "99", "1234.5", "59.3",
+           "100.5e0", "123456789012345e-12", "1e1", "1000000", "2.5E+2", "99.5"]
+    n = len(evs) * len(scs)
+    genes = [f"g{i}" for i in range(n + 1)]
+    gff = pd.DataFrame({"chr": ["1"] * len(genes)}, index=pd.Index(genes))
+    lines, k = [], 0
+    for ev in evs:
+        for sc in scs:
+            k += 1
+            lines.append("\t".join(["g0", f"g{k}", "90.1", "100", "1", "0", "1", "100", "1", "100", ev, sc]))
+    p = tmp_path / "forms.m8"
+    _write(p, "\n".join(lines) + "\n")
+    ids = host.pack_strings(genes)
+    for limit, score in ((1e-5, 100), (1e-05, 99.9999999999999), (9.99999999999999e-06, 100), (4.2e-7, 59.3)):
+        got = host.read_m8(str(p), False, score, limit, ids, ids, threads=2)
+        exp = base.newblast(str(p), score, limit, gff, gff, "false")
+        assert (got["row"] == exp.index.to_numpy()).all(), (limit, score)
+        assert (got["bits"] == exp[11].to_numpy()).all()
+        assert 0 < len(got["row"]) < n
+
+
 def test_native_grading_matches_oracle_with_ties(host):
     from wgdi_b200.ingest import grade_hits_native
     rng = np.random.default_rng(21)

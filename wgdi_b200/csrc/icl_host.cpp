@@ -95,7 +95,7 @@ inline bool is_int_literal(const char *p, const char *q) {
     return true;
 }
 
-inline double parse_double(const char *p, const char *q, bool *ok) {
+inline double parse_double_slow(const char *p, const char *q, bool *ok) {
     char buf[64];
     size_t n = (size_t)(q - p);
     if (n == 0 || n >= sizeof(buf)) { *ok = false; return NAN; }
@@ -106,6 +106,82 @@ inline double parse_double(const char *p, const char *q, bool *ok) {
     *ok = end == buf + n;
     return v;
 }
+
+// [sign] digits [. digits] [e|E [sign] digits], nothing else, at most 19 significant digits:
+// value = (neg ? -1 : 1) * w * 10^e10 with w exact.
+inline bool parse_simple(const char *p, const char *q, uint64_t &w, int &e10, bool &neg) {
+    neg = false;
+    if (p < q && (*p == '+' || *p == '-')) { neg = *p == '-'; p++; }
+    w = 0; e10 = 0;
+    int digits = 0, sig = 0;
+    for (; p < q && *p >= '0' && *p <= '9'; p++) {
+        digits++;
+        if (sig > 0 || *p != '0') { if (++sig > 19) return false; }
+        w = w * 10 + (uint64_t)(*p - '0');
+    }
+    if (p < q && *p == '.') {
+        p++;
+        for (; p < q && *p >= '0' && *p <= '9'; p++) {
+            digits++;
+            if (sig > 0 || *p != '0') { if (++sig > 19) return false; }
+            w = w * 10 + (uint64_t)(*p - '0');
+            e10--;
+        }
+    }
+    if (digits == 0) return false;
+    if (p < q && (*p == 'e' || *p == 'E')) {
+        p++;
+        bool eneg = false;
+        if (p < q && (*p == '+' || *p == '-')) { eneg = *p == '-'; p++; }
+        int e = 0, ed = 0;
+        for (; p < q && *p >= '0' && *p <= '9'; p++) { if (++ed > 4) return false; e = e * 10 + (*p - '0'); }
+        if (ed == 0) return false;
+        e10 += eneg ? -e : e;
+    }
+    return p == q;
+}
+
+static const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                  1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// Exact double of a decimal token: the classic fast path (mantissa < 2^53, |exponent| <= 22: one correctly rounded
+// multiplication or division of two exact doubles), strtod otherwise.
+inline double parse_double(const char *p, const char *q, bool *ok) {
+    uint64_t w; int e10; bool neg;
+    if (parse_simple(p, q, w, e10, neg) && w < (1ull << 53) && e10 >= -22 && e10 <= 22) {
+        double v = (double)w;
+        v = e10 < 0 ? v / kPow10[-e10] : v * kPow10[e10];
+        *ok = true;
+        return neg ? -v : v;
+    }
+    return parse_double_slow(p, q, ok);
+}
+
+// Only the outcome of `value < limit` is needed for the e-value column (base.py:178): decide it from an extended
+// precision estimate when the value is not within a hair of the limit, otherwise from the exact conversion.
+struct LessThan {
+    long double limit, lo, hi;
+    long double p10[801];
+    explicit LessThan(double lim) : limit(lim) {
+        long double band = fabsl(limit) * 1e-15L;
+        lo = limit - band; hi = limit + band;
+        for (int k = -400; k <= 400; k++) p10[k + 400] = powl(10.0L, (long double)k);
+    }
+    // returns 1 / 0, or -1 when the token does not parse (NaN in pandas: comparison false)
+    int test(const char *p, const char *q) const {
+        uint64_t w; int e10; bool neg;
+        if (parse_simple(p, q, w, e10, neg) && e10 >= -400 && e10 <= 400) {
+            long double v = (long double)w * p10[e10 + 400];
+            if (neg) v = -v;
+            if (v < lo) return 1;
+            if (v > hi) return 0;
+        }
+        bool ok = true;
+        double v = parse_double_slow(p, q, &ok);
+        if (!ok) return -1;
+        return v < (double)limit ? 1 : 0;
+    }
+};
 
 struct ChunkOut {
     std::vector<int64_t> row;
@@ -158,6 +234,7 @@ extern "C" int icl_host_read_m8(const char *path, int32_t reverse, double min_sc
     }
     for (int64_t c = 1; c <= n_chunks; c++) start[c] = std::max(start[c], start[c - 1]);
     std::vector<ChunkOut> outs(n_chunks);
+    const LessThan evalue_below(max_evalue);
     parallel_for(n_chunks, threads, [&](int64_t c) {
         ChunkOut &o = outs[c];
         const char *p = data + start[c], *end = data + start[c + 1];
@@ -179,13 +256,13 @@ extern "C" int icl_host_read_m8(const char *path, int32_t reverse, double min_sc
             const int64_t row = o.n_rows++;
             const char *a0 = f[0], *a1 = f[1] - 1, *b0 = f[1], *b1 = f[2] - 1;
             if (reverse) { std::swap(a0, b0); std::swap(a1, b1); }
-            bool ok1 = true, ok2 = true;
+            bool ok2 = true;
             if (o.all_int && !is_int_literal(f[11], e11)) o.all_int = false;
-            double ev = parse_double(f[10], f[11] - 1, &ok1);
+            const int ev_ok = evalue_below.test(f[10], f[11] - 1);
             double bs = parse_double(f[11], e11, &ok2);
             p = next;
-            if (!ok1 || !ok2) continue;                  // unparsable -> NaN in pandas -> fails both comparisons
-            if (!(bs >= min_score) || !(ev < max_evalue)) continue;                       // base.py:178
+            if (ev_ok < 0 || !ok2) continue;             // unparsable -> NaN in pandas -> fails both comparisons
+            if (!(bs >= min_score) || ev_ok == 0) continue;                               // base.py:178
             size_t la = (size_t)(a1 - a0), lb = (size_t)(b1 - b0);
             if (la == lb && !memcmp(a0, b0, la)) continue;                                // id1 != id2
             int32_t g1 = map1.find(a0, la);
@@ -204,33 +281,61 @@ extern "C" int icl_host_read_m8(const char *path, int32_t reverse, double min_sc
         total += (int64_t)o.row.size();
         all_int = all_int && o.all_int;
     }
-    // keep='first' on (id1, id2) in file order (base.py:180)
-    uint64_t cap = 16;
-    while (cap < (uint64_t)total * 2 + 8) cap <<= 1;
-    std::vector<uint64_t> seen(cap, ~0ull);
-    const uint64_t mask = cap - 1;
-    out->row = (int64_t *)malloc((size_t)std::max<int64_t>(total, 1) * sizeof(int64_t));
-    out->g1 = (int32_t *)malloc((size_t)std::max<int64_t>(total, 1) * sizeof(int32_t));
-    out->g2 = (int32_t *)malloc((size_t)std::max<int64_t>(total, 1) * sizeof(int32_t));
-    out->bits = (double *)malloc((size_t)std::max<int64_t>(total, 1) * sizeof(double));
-    if (!out->row || !out->g1 || !out->g2 || !out->bits) { icl_host_free_hits(out); set_err(err, errlen, "out of memory"); return -5; }
-    int64_t k = 0;
-    for (auto &o : outs) {
-        for (size_t i = 0; i < o.row.size(); i++) {
-            uint64_t key = ((uint64_t)(uint32_t)o.g1[i] << 32) | (uint32_t)o.g2[i];
-            uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> 17 & mask;
-            bool dup = false;
-            for (;;) {
-                if (seen[h] == ~0ull) { seen[h] = key; break; }
-                if (seen[h] == key) { dup = true; break; }
-                h = (h + 1) & mask;
+    // keep='first' on (id1, id2) in file order (base.py:180).  The keys are split by hash over `parts` private tables;
+    // every thread walks all rows in file order (cheap: two ints per row) and inserts only the keys of its part, so
+    // the first occurrence in file order wins inside every part and the random probes stay inside one small table.
+    std::vector<int64_t> cbase((size_t)n_chunks + 1, 0), rbase((size_t)n_chunks + 1, 0);
+    for (int64_t c = 0; c < n_chunks; c++) {
+        cbase[c + 1] = cbase[c] + (int64_t)outs[c].row.size();
+        rbase[c + 1] = rbase[c] + outs[c].n_rows;
+    }
+    std::vector<uint8_t> dup((size_t)std::max<int64_t>(total, 1), 0);
+    int parts = 1;
+    while (parts < threads && parts < 64) parts <<= 1;
+    auto key_of = [](int32_t a, int32_t b) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; };
+    auto mix = [](uint64_t key) { return key * 0x9E3779B97F4A7C15ull; };
+    parallel_for(parts, threads, [&](int64_t part) {
+        uint64_t cap = 16;
+        while (cap < (uint64_t)total * 2 / (uint64_t)parts + 64) cap <<= 1;
+        std::vector<uint64_t> seen(cap, ~0ull);
+        const uint64_t mask = cap - 1;
+        for (int64_t c = 0; c < n_chunks; c++) {
+            const ChunkOut &o = outs[c];
+            for (size_t i = 0; i < o.row.size(); i++) {
+                const uint64_t key = key_of(o.g1[i], o.g2[i]), hm = mix(key);
+                if ((int64_t)(hm >> 58) % parts != part) continue;
+                uint64_t h = (hm >> 20) & mask;
+                for (;;) {
+                    if (seen[h] == ~0ull) { seen[h] = key; break; }
+                    if (seen[h] == key) { dup[(size_t)cbase[c] + i] = 1; break; }
+                    h = (h + 1) & mask;
+                }
             }
-            if (dup) continue;
-            out->row[k] = rows + o.row[i]; out->g1[k] = o.g1[i]; out->g2[k] = o.g2[i]; out->bits[k] = o.bits[i];
+        }
+    });
+    std::vector<int64_t> obase((size_t)n_chunks + 1, 0);
+    for (int64_t c = 0; c < n_chunks; c++) {
+        int64_t kept = 0;
+        for (size_t i = 0; i < outs[c].row.size(); i++) kept += !dup[(size_t)cbase[c] + i];
+        obase[c + 1] = obase[c] + kept;
+    }
+    const int64_t kept_total = obase[n_chunks];
+    out->row = (int64_t *)malloc((size_t)std::max<int64_t>(kept_total, 1) * sizeof(int64_t));
+    out->g1 = (int32_t *)malloc((size_t)std::max<int64_t>(kept_total, 1) * sizeof(int32_t));
+    out->g2 = (int32_t *)malloc((size_t)std::max<int64_t>(kept_total, 1) * sizeof(int32_t));
+    out->bits = (double *)malloc((size_t)std::max<int64_t>(kept_total, 1) * sizeof(double));
+    if (!out->row || !out->g1 || !out->g2 || !out->bits) { icl_host_free_hits(out); set_err(err, errlen, "out of memory"); return -5; }
+    parallel_for(n_chunks, threads, [&](int64_t c) {
+        const ChunkOut &o = outs[c];
+        int64_t k = obase[c];
+        for (size_t i = 0; i < o.row.size(); i++) {
+            if (dup[(size_t)cbase[c] + i]) continue;
+            out->row[k] = rbase[c] + o.row[i]; out->g1[k] = o.g1[i]; out->g2[k] = o.g2[i]; out->bits[k] = o.bits[i];
             k++;
         }
-        rows += o.n_rows;
-    }
+    });
+    const int64_t k = kept_total;
+    rows = rbase[n_chunks];
     out->n = k;
     out->n_rows_file = rows;
     out->bits_is_int = all_int ? 1 : 0;

@@ -135,7 +135,12 @@ def pair_ids(chr1_names, chr2_names, c1, c2):
     iterates (wgdi/run_colliearity.py:118).  Returns (pair_id, [(chr1, chr2) per pair])."""
     nc2 = max(len(chr2_names), 1)
     code = c1.astype(np.int64) * nc2 + c2
-    uniq, inv = np.unique(code, return_inverse=True)
+    # the codes are dense (chromosomes x chromosomes): a table lookup instead of a sort of all hits
+    table = np.zeros(max(len(chr1_names), 1) * nc2, np.int64)
+    table[code] = 1
+    uniq = np.flatnonzero(table)
+    table[uniq] = np.arange(len(uniq))
+    inv = table[code]
     names = [(str(chr1_names[u // nc2]), str(chr2_names[u % nc2])) for u in uniq]
     order = sorted(range(len(uniq)), key=lambda i: names[i])
     rank = np.empty(len(uniq), np.int32)

@@ -54,16 +54,18 @@ class mycollinearity():
         (pair_id, loc1, loc2, grading), the pair names in output order and the gene tables."""
         lens1 = base.newlens(self.lens1, 'order')
         lens2 = base.newlens(self.lens2, 'order')
+        same = self.gff2 == self.gff1 and self.lens2 == self.lens1       # self comparison: parse the tables once
         gff1 = base.newgff(self.gff1)
-        gff2 = base.newgff(self.gff2)
         gff1 = gff1[gff1['chr'].isin(lens1.index)]        # :96-97
-        gff2 = gff2[gff2['chr'].isin(lens2.index)]
+        gff2 = gff1 if same else base.newgff(self.gff2)
+        if not same:
+            gff2 = gff2[gff2['chr'].isin(lens2.index)]
         mode = self.comparison.lower()                    # :108-111
         if mode not in ('genomes', 'chromosomes'):
             raise ValueError(f"comparison = {self.comparison}: expected 'genomes' or 'chromosomes'")
         if self.native:
             ids1 = _host.pack_strings(gff1.index)
-            ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
+            ids2 = ids1 if same else _host.pack_strings(gff2.index)
             hits = _host.read_m8(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2)
             g1, g2 = hits['g1'], hits['g2']
             bits = hits['bits']
@@ -71,7 +73,7 @@ class mycollinearity():
             blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
             g1, g2, bits = blast['g1'].to_numpy(), blast['g2'].to_numpy(), blast[11].to_numpy()
         t1 = _gene_table(gff1)
-        t2 = _gene_table(gff2)
+        t2 = t1 if same else _gene_table(gff2)
         if mode == 'chromosomes':                         # :42-57, every sort stable
             name_rank = np.empty(len(gff1), np.int64)
             name_rank[np.argsort(t1['name'], kind='stable')] = np.arange(len(gff1))
