@@ -2002,7 +2002,8 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     ICL_CUDA(st, dev_sync(s));
     out->n_blocks = NBo;
     out->n_members = NMo;
-    c->counters[2] = 11;   // rank2v, rankpos, root keys, tree walk, flags, emit, pvalue, select, gather + CUB sort/scans
+    c->counters[2] = 12;   // our kernels per icl_extract (profiles/r01_launches_final.csv): rank2v, tree keys + check, tree walk,
+                           // flags, emit, k_pvalue, p values, select x3, gather — CUB sort / scan kernels not counted
     return ICL_OK;
 }
 
