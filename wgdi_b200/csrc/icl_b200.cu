@@ -1199,6 +1199,26 @@ static int phase_chain(icl_ctx *c) {
 // ------------------------------------------------------------------------------------------------
 // ABI: icl_dp
 // ------------------------------------------------------------------------------------------------
+// diagnostics: per-item {rounds, cycles, wait cycles, records} of the DP kernel (env ICL_B200_CHAIN_DEBUG = file)
+static int dump_chain_debug(icl_ctx *c) {
+    Status &st = c->st;
+    cudaStream_t s = c->stream;
+    if (getenv("ICL_B200_CHAIN_DEBUG") && c->chain_dbg.p && c->P > 0) {
+        std::vector<long long> h(8 * (size_t)c->P);
+        ICL_CUDA(st, d2h(h.data(), c->chain_dbg.p, h.size() * sizeof(long long), s));
+        ICL_CUDA(st, dev_sync(s));
+        FILE *f = fopen(getenv("ICL_B200_CHAIN_DEBUG"), "w");
+        if (f) {
+            for (int32_t j = 0; j < 2 * c->P; j++) {
+                int32_t it = c->h_item_order[j], p = it >= c->P ? it - c->P : it;
+                fprintf(f, "%d %d %lld %d %lld %lld %lld %lld\n", j, it, (long long)(c->h_pair_off[p + 1] - c->h_pair_off[p]), c->h_nrows[p], h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            }
+            fclose(f);
+        }
+    }
+    return 0;
+}
+
 // Everything icl_dp does.  With `queue` (icl_dp_begin) and the shared-memory ring kernel, finished items write
 // their scores to the caller's buffers themselves and the call returns right after the launch; otherwise the
 // scores are exported and copied after the DP and all completion flags (if any) are raised at the end.
@@ -1273,19 +1293,7 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
     }
     c->timers[ICL_T_D2H].stop(s);
     ICL_CUDA(st, dev_sync(s));
-    if (getenv("ICL_B200_CHAIN_DEBUG") && c->chain_dbg.p && c->P > 0) {
-        std::vector<long long> h(8 * (size_t)c->P);
-        ICL_CUDA(st, d2h(h.data(), c->chain_dbg.p, h.size() * sizeof(long long), s));
-        ICL_CUDA(st, dev_sync(s));
-        FILE *f = fopen(getenv("ICL_B200_CHAIN_DEBUG"), "w");
-        if (f) {
-            for (int32_t j = 0; j < 2 * c->P; j++) {
-                int32_t it = c->h_item_order[j], p = it >= c->P ? it - c->P : it;
-                fprintf(f, "%d %d %lld %d %lld %lld %lld %lld\n", j, it, (long long)(c->h_pair_off[p + 1] - c->h_pair_off[p]), c->h_nrows[p], h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-            }
-            fclose(f);
-        }
-    }
+    if (dump_chain_debug(c)) return st.code;
     if (queue) for (int64_t i = 0; i < 2 * (int64_t)c->P; i++) queue[i] = 1;     // not streamed: everything is complete now
     c->dp_begun = true;
     c->dp_done = queue == nullptr;                             // icl_dp_begin: only icl_dp_end completes the phase
@@ -1310,6 +1318,7 @@ extern "C" int icl_dp_end(icl_ctx *c) {
     ICL_CUDA(st, cudaSetDevice(c->device));
 #endif
     ICL_CUDA(st, dev_sync(c->stream));
+    if (c->streamed && dump_chain_debug(c)) return st.code;
     c->dp_done = true;
     return ICL_OK;
 }
