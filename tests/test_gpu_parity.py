@@ -356,6 +356,70 @@ def test_batch_runner_equals_one_engine(gpu_engine):
     _compare_with_oracle(got[0], oracle_blocks(comps[0], jobs[0][1]))
 
 
+def _random_comparison(rng, n_pairs, n_rows, n_cols, per_row, diag_frac, dup_frac):
+    """Random chromosome pairs with a mix of diagonal runs (both orientations, with gaps and side hits) and noise;
+    several hits per row and duplicate coordinates allowed."""
+    pid, l1, l2 = [], [], []
+    for p in range(n_pairs):
+        n = int(n_rows * per_row)
+        rows = rng.integers(1, n_rows + 1, n)
+        cols = rng.integers(1, n_cols + 1, n)
+        nd = int(n * diag_frac)
+        k = 0
+        while k < nd:
+            r, c = int(rng.integers(1, n_rows)), int(rng.integers(1, n_cols))
+            sign = 1 if rng.random() < 0.5 else -1
+            for _ in range(int(rng.integers(3, 60))):
+                if k >= nd or not (1 <= r <= n_rows and 1 <= c <= n_cols):
+                    break
+                rows[k], cols[k] = r, c
+                k += 1
+                r += int(rng.integers(1, 4))
+                c += sign * int(rng.integers(1, 4))
+        nd2 = int(n * dup_frac)
+        if nd2:
+            src = rng.integers(0, n, nd2)
+            rows, cols = np.r_[rows, rows[src]], np.r_[cols, cols[src]]
+        pid.append(np.full(len(rows), p)); l1.append(rows); l2.append(cols)
+    pid, l1, l2 = (np.concatenate(x).astype(np.int32) for x in (pid, l1, l2))
+    g = rng.choice(np.array([50, 30, 25], np.int32), len(pid), p=[0.25, 0.35, 0.4])
+    o = rng.permutation(len(pid))
+    return dict(pair_id=pid[o], loc1=l1[o], loc2=l2[o], grading=g[o], n_pairs=n_pairs)
+
+
+@pytest.mark.parametrize("seed", range(9))
+def test_random_comparisons_match_oracle(gpu_engine, seed):
+    """Randomised parity: dense and sparse rows, mg from 2 to 255 (window spans from a few points to beyond the
+    shared-memory ring, i.e. every ring size and the global-memory fallback), odd coverage ratios, duplicates."""
+    from wgdi_b200.engine import ChainParams
+    rng = np.random.default_rng(1000 + seed)
+    shapes = [  # (pairs, rows, cols, hits per row, diagonal share, duplicate share, mg1, mg2)
+        (3, 400, 400, 6.0, 0.5, 0.02, 25, 25), (2, 150, 900, 40.0, 0.3, 0.0, 60, 120), (4, 2000, 2000, 1.5, 0.7, 0.01, 2, 2),
+        (1, 120, 120, 40.0, 0.2, 0.0, 255, 255), (2, 1200, 300, 3.0, 0.6, 0.05, 5, 200), (3, 800, 800, 8.0, 0.4, 0.0, 120, 9),
+        (1, 60, 60, 30.0, 0.5, 0.1, 40, 40), (5, 500, 700, 2.5, 0.8, 0.0, 33, 64), (1, 140, 140, 70.0, 0.1, 0.0, 255, 255)]
+    npairs, nr, nc, per, diag, dup, mg1, mg2 = shapes[seed]
+    pts = _random_comparison(rng, npairs, nr, nc, per, diag, dup)
+    prm = ChainParams(mg1=mg1, mg2=mg2, grading=(50, 30, 25), coverage_ratio=float(rng.choice([0.8, 0.5, 0.95])))
+    blocks = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    exp = oracle_blocks(pts, prm)
+    assert len(exp) > 0
+    _compare_with_oracle(blocks, exp)
+    assert gpu_engine.counters()["chain_kernel"] == ("generic" if seed == 8 else "ring")     # seed 8: window beyond the ring
+    # the DP state itself, point by point (score, predecessor, path length, used) against the C oracle
+    from oracle import c_oracle
+    off, perm = gpu_engine.layout()
+    for d in (0, 1):
+        s, pr, dp, us = gpu_engine.debug_dp(d)
+        for p in range(pts["n_pairs"]):
+            a, b = off[p], off[p + 1]
+            if a == b:
+                continue
+            i = perm[a:b]
+            es, ep, eu, ed = c_oracle.chain(pts["loc1"][i], pts["loc2"][i], pts["grading"][i], mg1, mg2, 1 if d == 0 else -1)
+            assert (s[a:b] == es).all() and (us[a:b].astype(bool) == eu).all() and (dp[a:b] == ed).all(), (seed, d, p)
+            assert (np.where(pr[a:b] >= 0, pr[a:b] - a, -1) == ep).all(), (seed, d, p)
+
+
 def test_alternative_dp_kernels_agree(clouds):
     """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth
