@@ -152,6 +152,17 @@ int icl_dp_end(icl_ctx *ctx);
 int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
 
 /*
+ * NON-REFERENCE option: rank every (pair, direction) item on the device with a STABLE sort instead of numpy's
+ * unstable argsort, then call icl_extract with both argsort pointers NULL.  This is the result pandas'
+ * nargsort(ascending=False) would give if numpy's argsort were stable (reverse, stable ascending argsort, reverse):
+ * identical to the reference wherever scores are distinct, but tied scores come in reversed (loc1, loc2) order and
+ * not in numpy's CPU-specific permutation, so blocks with tied top scores can come out in a different order (and, where
+ * they share points, differently).  It removes the host from the step: for throughput runs that do not need the
+ * reference's tie order.  icl_dp may then be called with both key pointers NULL (no score export).
+ */
+int icl_rank_device(icl_ctx *ctx);
+
+/*
  * Block extraction + p values (wgdi/collinearity.py:42-70, 117-153).
  * argsort_fwd / argsort_rev: for every pair segment the UNMODIFIED result of
  *     numpy.argsort(key[pair_off[p]:pair_off[p+1]].astype(int64), kind='quicksort')
@@ -163,6 +174,7 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
  * blocks still take part in the `times` accounting of the p value (collinearity.py:150).
  * The arrays of `out` live in page-locked staging owned by `ctx`: valid until the next icl_extract or
  * icl_destroy on that context; icl_free_blocks only clears the view.
+ * Both argsort pointers NULL: use the order icl_rank_device left on the device (non-reference tie order).
  */
 int icl_extract(icl_ctx *ctx, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
                 icl_blocks *out);

@@ -125,6 +125,30 @@ def oracle_batch(pts, prm, threads=None):
     return bt, (off, l1, l2, g, o)
 
 
+def oracle_blocks_stable(pts, prm):
+    """`oracle_blocks` with the extraction order of a STABLE sort (what pandas' nargsort(ascending=False) would give if
+    numpy's argsort were stable): the rule of the engine's non-reference device-rank mode."""
+    from oracle import c_oracle, icl_oracle
+    off, l1, l2, g, o = sorted_layout(pts)
+    op = icl_oracle.IclParams([("grading", ",".join(map(str, prm.grading))), ("mg", f"{prm.mg1},{prm.mg2}"),
+                               ("pvalue", str(prm.pvalue)), ("coverage_ratio", str(prm.coverage_ratio))])
+    bt = c_oracle.Batch(off, l1, l2, g, op)
+    bt.chain()
+    bt.order = [np.empty(bt.n, np.int32) for _ in range(2)]
+    for d in range(2):
+        for p in range(bt.n_pairs):
+            a, b = off[p], off[p + 1]
+            sc = bt.dp[d]["score"][a:b].astype(np.int64)
+            m = b - a
+            bt.order[d][a:b] = (m - 1 - np.argsort(sc[::-1], kind="stable"))[::-1]
+    bt.extract()
+    out = []
+    for p in range(pts["n_pairs"]):
+        for mm, a, sc, d in bt.blocks(p):
+            out.append((p, 0 if d > 0 else 1, l1[mm], l2[mm], a, sc))
+    return out
+
+
 def oracle_blocks(pts, prm):
     """[(pair, dir, loc1[], loc2[], a, score)] of every accepted block, in emission order."""
     bt, (off, l1, l2, g, o) = oracle_batch(pts, prm)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import (PORTABLE_ENV, ROOT, check_blocks_against_golden, check_dp_against_golden, oracle_batch,
-                      oracle_blocks, sorted_layout, stage_e2e)
+                      oracle_blocks, oracle_blocks_stable, sorted_layout, stage_e2e)
 
 pytestmark = pytest.mark.gpu
 
@@ -418,6 +418,19 @@ def test_random_comparisons_match_oracle(gpu_engine, seed):
             es, ep, eu, ed = c_oracle.chain(pts["loc1"][i], pts["loc2"][i], pts["grading"][i], mg1, mg2, 1 if d == 0 else -1)
             assert (s[a:b] == es).all() and (us[a:b].astype(bool) == eu).all() and (dp[a:b] == ed).all(), (seed, d, p)
             assert (np.where(pr[a:b] >= 0, pr[a:b] - a, -1) == ep).all(), (seed, d, p)
+
+
+@pytest.mark.parametrize("name,scale", [("small", 1.0), ("C2", 0.1)])
+def test_device_rank_mode_matches_stable_oracle(gpu_engine, name, scale):
+    """Non-reference option (icl_rank_device): extraction order from a stable device sort; bit-exact against the oracle
+    run with the same stable order."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    pts = synth.graded_points(synth.make_dataset(name, scale=scale))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    gpu_engine.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+    got = gpu_engine.run_resident_device_rank(prm)
+    _compare_with_oracle(got, oracle_blocks_stable(pts, prm))
 
 
 def test_alternative_dp_kernels_agree(clouds):

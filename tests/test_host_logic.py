@@ -361,3 +361,30 @@ def test_batch_runner_emu(emu_backend):
     finally:
         eng.close()
     assert len({len(b) for b in got}) > 1                  # the mg sweep really changes the result
+
+
+def test_device_rank_mode_emu(emu_backend):
+    """icl_rank_device (non-reference option): blocks equal the oracle's under a stable descending sort; same block
+    set as the reference order wherever no top scores tie; state errors reported."""
+    from conftest import oracle_blocks_stable
+    from wgdi_b200 import synth
+    from wgdi_b200._lib import IclError
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("tiny"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+        with pytest.raises(IclError):
+            eng._check(eng.lib.icl_rank_device(eng.ctx))                 # before icl_dp
+        got = eng.run_resident_device_rank(prm)
+        ref = eng.run_resident(prm)
+    finally:
+        eng.close()
+    exp = oracle_blocks_stable(pts, prm)
+    assert len(got) == len(exp) > 20
+    for b, (pair, d, l1, l2, a, sc) in enumerate(exp):
+        a0, a1 = got.member_off[b], got.member_off[b + 1]
+        assert got.pair[b] == pair and got.dir[b] == d and got.score[b] == sc and got.p_raw[b] == a
+        assert (got.loc1[a0:a1] == l1).all() and (got.loc2[a0:a1] == l2).all()
+    assert sorted(got.score.tolist()) == sorted(ref.score.tolist()) or len(got) != len(ref)   # tie order may differ, nothing else

@@ -70,6 +70,7 @@ struct icl_ctx {
     Buf<long long> chain_dbg;
     int32_t *sq_fwd = nullptr, *sq_rev = nullptr, *sq_queue = nullptr;   // streaming targets of the current icl_dp_begin (host, device-visible)
     bool streamed = false, dp_begun = false;
+    bool order_on_device = false;    // icl_rank_device filled order_in (non-reference tie order)
     int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
@@ -1225,7 +1226,9 @@ static int dump_chain_debug(icl_ctx *c) {
 static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t *score_rev, int32_t *queue) {
     if (!c) return ICL_ERR_ARG;
     if (!c->uploaded) return fail(c, ICL_ERR_STATE, "icl_dp: icl_upload has not succeeded");
-    if (!prm || (c->n > 0 && (!score_fwd || !score_rev))) return fail(c, ICL_ERR_ARG, "icl_dp: null argument");
+    if (!prm || (c->n > 0 && (!score_fwd != !score_rev)) || (queue && c->n > 0 && !score_fwd))
+        return fail(c, ICL_ERR_ARG, "icl_dp: null argument");
+    const bool want_keys = score_fwd != nullptr;               // NULL, NULL: the caller ranks on the device (icl_rank_device)
     if (prm->mg1 < 2 || prm->mg1 > 255 || prm->mg2 < 2 || prm->mg2 > 255)
         return fail(c, ICL_ERR_LIMIT, "icl_dp: mg values must be in 2..255");
     if (prm->g0 <= 0 || prm->over_gap < 1) return fail(c, ICL_ERR_ARG, "icl_dp: grading[0] and over_gap must be positive");
@@ -1235,6 +1238,7 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
     ICL_CUDA(st, cudaSetDevice(c->device));
 #endif
     c->dp_done = c->dp_begun = false;
+    c->order_on_device = false;
     c->prm = *prm;
     c->sq_fwd = score_fwd; c->sq_rev = score_rev; c->sq_queue = queue;
     if (queue) for (int64_t i = 0; i < 2 * (int64_t)c->P; i++) queue[i] = 0;
@@ -1266,10 +1270,10 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
         c->dp_begun = true;
         return ICL_OK;
     }
-    c->counters[1] = 12;
+    c->counters[1] = want_keys ? 12 : 11;
     c->timers[ICL_T_EXPORT].start(s);
-    if (c->score32.reserve(st, 2 * n)) return st.code;
-    {
+    if (want_keys && c->score32.reserve(st, 2 * n)) return st.code;
+    if (want_keys) {
         // per pair segment in REVERSED point order: the array pandas' nargsort(ascending=False) hands to numpy
         const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
         const int64_t *off = c->d_pair_off.p;
@@ -1283,7 +1287,7 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
     }
     c->timers[ICL_T_EXPORT].stop(s);
     c->timers[ICL_T_D2H].start(s);
-    if (n > 0) {
+    if (n > 0 && want_keys) {
         if (score_rev == score_fwd + n) {                      // one buffer of 2n: a single transfer
             ICL_CUDA(st, d2h(score_fwd, c->score32.p, (size_t)2 * n * sizeof(int32_t), s));
         } else {
@@ -1855,11 +1859,57 @@ struct Stage {                               // bump allocator over the context'
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// ABI: icl_rank_device — NON-REFERENCE tie order.  The extraction order of every (pair, direction) item from a
+// STABLE device sort: what pandas' nargsort(ascending=False) would return if numpy's argsort were stable (reverse,
+// stable ascending argsort, reverse).  Identical to the reference wherever scores are distinct; tied scores come
+// in reversed (loc1, loc2) order instead of numpy's CPU-specific permutation.
+// ------------------------------------------------------------------------------------------------
+extern "C" int icl_rank_device(icl_ctx *c) {
+    if (!c) return ICL_ERR_ARG;
+    if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_rank_device: icl_dp has not succeeded");
+    Status &st = c->st;
+    st.code = 0;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaSetDevice(c->device));
+#endif
+    cudaStream_t s = c->stream;
+    const int64_t n = c->n, V = 2 * n;
+    const int32_t P = c->P;
+    c->timers[ICL_T_D2H].start(s);
+    if (c->order_in.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
+        c->tree_v.reserve(st, V))
+        return st.code;
+    if (n > 0) {
+        // element i of the first half = position j of pair p's REVERSED segment (as in the score export of icl_dp);
+        // key = item | score, value = j; a stable sort leaves every item's ascending argsort in place
+        const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
+        const int64_t *off = c->d_pair_off.p;
+        uint64_t *key = c->key_a.p;
+        uint32_t *val = c->idx_a.p;
+        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
+            const int32_t p = ps[i];
+            const int64_t src = off[p] + (off[p + 1] - 1 - i);
+            const uint32_t j = (uint32_t)(i - off[p]);
+            key[i] = ((uint64_t)(uint32_t)p << 32) | (uint32_t)S[src];
+            key[n + i] = ((uint64_t)(uint32_t)(P + p) << 32) | (uint32_t)S[mmap[src]];
+            val[i] = j;
+            val[n + i] = j;
+        }));
+        if (radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, 32 + bits_for(2 * (int64_t)P), s)) return st.code;
+        ICL_CUDA(st, d2d(c->order_in.p, c->tree_v.p, (size_t)V * sizeof(int32_t), s));
+    }
+    c->timers[ICL_T_D2H].stop(s);
+    c->order_on_device = true;
+    return ICL_OK;
+}
+
 extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
                            icl_blocks *out) {
     if (!c) return ICL_ERR_ARG;
     if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_extract: icl_dp has not succeeded");
-    if (!out || (c->n > 0 && (!argsort_fwd || !argsort_rev))) return fail(c, ICL_ERR_ARG, "icl_extract: null argument");
+    const bool dev_order = !argsort_fwd && !argsort_rev && c->order_on_device;       // icl_rank_device ran
+    if (!out || (c->n > 0 && !dev_order && (!argsort_fwd || !argsort_rev))) return fail(c, ICL_ERR_ARG, "icl_extract: null argument");
     memset(out, 0, sizeof(*out));
     Status &st = c->st;
     st.code = 0;
@@ -1872,7 +1922,9 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     c->timers[ICL_T_EXTRACT].start(s);
     if (c->order_in.reserve(st, 2 * n) || c->rank2v.reserve(st, V)) return st.code;
     if (n > 0) {
-        if (argsort_rev == argsort_fwd + n) {
+        if (dev_order) {
+            // order_in already holds the device argsort
+        } else if (argsort_rev == argsort_fwd + n) {
             ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)2 * n * sizeof(int32_t), s));
         } else {
             ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)n * sizeof(int32_t), s));

@@ -262,6 +262,9 @@ class IclEngine:
         af = np.ascontiguousarray(argsort_fwd, np.int32)
         ar = np.ascontiguousarray(argsort_rev, np.int32)
         self._check(self.lib.icl_extract(self.ctx, af.ctypes.data, ar.ctypes.data, int(min_members), C.byref(out)))
+        return self._blocks_from(out, copy)
+
+    def _blocks_from(self, out, copy):
         nb, nm = out.n_blocks, out.n_members
 
         def arr(ptr, n, dt):          # the staging is reused by the next call
@@ -324,6 +327,22 @@ class IclEngine:
         t2 = time.perf_counter()
         self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3)
         return both[:n], both[n:]
+
+    def run_resident_device_rank(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
+        """NON-REFERENCE tie order: like `run_resident`, but the extraction order comes from a stable sort on the device
+        (icl_rank_device) instead of numpy's unstable argsort on the host.  Same blocks wherever scores are distinct."""
+        prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
+                         float(params.coverage_ratio))
+        t0 = time.perf_counter()
+        self._check(self.lib.icl_dp(self.ctx, C.byref(prm), None, None))
+        self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
+        self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
+        self._check(self.lib.icl_rank_device(self.ctx))
+        out = icl_blocks()
+        self._check(self.lib.icl_extract(self.ctx, None, None, int(min_members), C.byref(out)))
+        res = self._blocks_from(out, copy)
+        self.host_ms = dict(total=(time.perf_counter() - t0) * 1e3, rank=0.0)
+        return res
 
     def run_resident(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
         """Hot path on points already uploaded: sort + DP -> host rank -> extraction + p values."""
