@@ -94,7 +94,10 @@ if fp != json.load(open("meta.json"))["argsort_fingerprint"]:
     print("SKIP fingerprint", fp); sys.exit(0)
 from wgdi_b200 import _lib, base
 from wgdi_b200.run_colliearity import mycollinearity
+import os
 conf = open("icl.conf").read().replace("expected.collinearity.txt", "got.txt")
+if os.environ.get("ICL_TEST_DEVICES"):
+    conf += "devices = " + os.environ["ICL_TEST_DEVICES"] + "\n"      # chromosome pairs sharded over several engines
 open("icl.conf", "w").write(conf)
 with contextlib.redirect_stdout(io.StringIO()):
     try:
@@ -112,6 +115,29 @@ def test_drop_in_driver_writes_reference_file(case):
     with tempfile.TemporaryDirectory() as d:
         stage_e2e(case, d)
         env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+        r = subprocess.run([sys.executable, "-c", _E2E_CHILD % ROOT], cwd=d, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        if r.stdout.startswith("SKIP"):
+            pytest.skip("numpy scalar-sort fingerprint differs on this machine: " + r.stdout)
+        assert r.stdout.strip() == "OK", r.stdout + r.stderr
+
+
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+def test_drop_in_driver_sharded_over_devices():
+    """`devices = ...` in the conf: chromosome pairs LPT-sharded over several engines from one process (every visible
+    GPU, at least two engines), blocks merged on the host — the file the reference wrote."""
+    n = max(2, min(_gpu_count(), 8))
+    devices = ",".join(str(i % max(_gpu_count(), 1)) for i in range(n))
+    with tempfile.TemporaryDirectory() as d:
+        stage_e2e("cross", d)
+        env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV, ICL_TEST_DEVICES=devices)
         r = subprocess.run([sys.executable, "-c", _E2E_CHILD % ROOT], cwd=d, env=env, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         if r.stdout.startswith("SKIP"):

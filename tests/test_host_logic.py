@@ -199,7 +199,10 @@ emu = %r
 if emu:
     _lib._LIB = _lib._declare(ctypes.CDLL(emu))     # fake backend injected by the test
 from wgdi_b200.run_colliearity import mycollinearity
+import os
 conf = open("icl.conf").read().replace("expected.collinearity.txt", "got.txt")
+if os.environ.get("ICL_TEST_DEVICES"):
+    conf += "devices = " + os.environ["ICL_TEST_DEVICES"] + "\n"      # chromosome pairs sharded over several engines
 open("icl.conf", "w").write(conf)
 with contextlib.redirect_stdout(io.StringIO()):
     try:
@@ -210,10 +213,12 @@ print("OK" if open("got.txt").read() == open("expected.collinearity.txt").read()
 """
 
 
-def run_e2e_child(case, emu_path):
+def run_e2e_child(case, emu_path, devices=None):
     with tempfile.TemporaryDirectory() as d:
         stage_e2e(case, d)
         env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+        if devices:
+            env["ICL_TEST_DEVICES"] = devices
         r = subprocess.run([sys.executable, "-c", _E2E_CHILD % (ROOT, emu_path)], cwd=d, env=env,
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
@@ -228,6 +233,13 @@ def test_drop_in_driver_writes_reference_file_emu(case):
     reproduces the file the unmodified reference wrote."""
     from wgdi_b200 import build
     run_e2e_child(case, build.build_emu(os.path.join(ROOT, "tests", "_emu")))
+
+
+def test_drop_in_driver_sharded_over_devices_emu():
+    """`devices = a,b,c`: chromosome pairs LPT-sharded over three engines from one process, blocks merged on the host —
+    the same file as one engine writes (the emulation ignores the device index)."""
+    from wgdi_b200 import build
+    run_e2e_child("cross", build.build_emu(os.path.join(ROOT, "tests", "_emu")), devices="0,0,0")
 
 
 def test_cli_prints_example_and_missing_conf(capsys):

@@ -43,6 +43,8 @@ class mycollinearity():
         self.process = int(self.process) if hasattr(self, 'process') else 4
         self.over_gap = int(self.over_gap)
         self.device = int(getattr(self, 'device', 0))     # extra, optional key: CUDA device index
+        # extra, optional key: `devices = 0,1,2,3` shards the chromosome pairs over several GPUs (LPT by point count)
+        self.devices = [int(k) for k in str(getattr(self, 'devices', self.device)).split(',') if k.strip() != '']
         # extra, optional key: `ingest = pandas` forces the reference-like pandas readers of wgdi_b200.base;
         # the default uses the native parser / writer (libicl_host.so) when it is built.  Same results.
         self.native = getattr(self, 'ingest', 'native').lower() != 'pandas' and _host.available()
@@ -100,15 +102,20 @@ class mycollinearity():
         pts = self.load_points()
         t1 = time.perf_counter()
         params = ChainParams.from_options(self.options)
-        eng = IclEngine(self.device)
+        for c1, c2 in pts['pair_names']:
+            print(f'Running {c1} vs {c2}')                # :162
+        eng = None
         try:
-            for c1, c2 in pts['pair_names']:
-                print(f'Running {c1} vs {c2}')            # :162
-            # blocks are views of the engine's page-locked staging: written out before the engine is closed
-            blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params,
-                               min_members=self.over_gap, copy=False)
-            self.timing['device_ms'] = eng.timings()
-            self.timing['host_ms'] = dict(eng.host_ms)
+            if len(self.devices) > 1:
+                from .shard import chain_on_devices
+                blocks = chain_on_devices(pts, len(pts['pair_names']), params, self.devices, min_members=self.over_gap)
+            else:
+                eng = IclEngine(self.devices[0])
+                # blocks are views of the engine's page-locked staging: written out before the engine is closed
+                blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params,
+                                   min_members=self.over_gap, copy=False)
+                self.timing['device_ms'] = eng.timings()
+                self.timing['host_ms'] = dict(eng.host_ms)
             t2 = time.perf_counter()
             if self.native:
                 write_blocks_native(self.savefile, blocks, pts['pair_names'], pts['genes1'], pts['genes2'], params.pvalue,
@@ -119,7 +126,8 @@ class mycollinearity():
                     fout.write(text)
             del blocks
         finally:
-            eng.close()
+            if eng is not None:
+                eng.close()
         t3 = time.perf_counter()
         self.timing.update(ingest_s=t1 - t0, chain_s=t2 - t1, write_s=t3 - t2)
         sys.exit(0)                                       # :156

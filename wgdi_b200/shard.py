@@ -59,3 +59,40 @@ def merge_blocks(parts):
         return np.concatenate([getattr(p, name) for p in parts])[order]
     return Blocks(pair[order], cat("dir"), cat("score"), m[order], cat("L"), cat("N"), cat("N1"), cat("L1"), cat("L2"),
                   cat("p_raw"), new_off, loc1[gather], loc2[gather], midx[gather])
+
+
+def chain_on_devices(points: dict, n_pairs: int, params, devices, min_members: int = 1):
+    """One comparison over several GPUs of this host from ONE process: chromosome pairs LPT-sharded over `devices`
+    (`shard_points`), one engine and one host thread per GPU (the C calls release the GIL; the sort pool serves one
+    shard at a time, so a shard's device phases overlap the other shards' host rank), blocks merged in pair order.
+    Same result as a single engine (tests).  No collective: results meet on the host."""
+    import threading
+
+    from .engine import IclEngine
+    pts = dict(points, n_pairs=n_pairs)
+    world = len(devices)
+    parts, errors = [None] * world, []
+
+    def work(r):
+        try:
+            sp = shard_points(pts, r, world)
+            eng = IclEngine(int(devices[r]))
+            try:
+                b = eng.chain(sp["pair_id"], sp["loc1"], sp["loc2"], sp["grading"], sp["n_pairs"], params,
+                              min_members=min_members, copy=True)
+            finally:
+                eng.close()
+            b.pair = sp["global_pair"][b.pair]
+            b.member_idx = sp["rows"][b.member_idx].astype(np.int32)
+            parts[r] = b
+        except Exception as e:                             # noqa: BLE001 — re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return merge_blocks(parts)
