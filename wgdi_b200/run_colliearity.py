@@ -48,6 +48,11 @@ class mycollinearity():
         # extra, optional key: `ingest = pandas` forces the reference-like pandas readers of wgdi_b200.base;
         # the default uses the native parser / writer (libicl_host.so) when it is built.  Same results.
         self.native = getattr(self, 'ingest', 'native').lower() != 'pandas' and _host.available()
+        # extra, optional key: `rank = device` takes the extraction order from a stable sort on the GPU instead of numpy's
+        # unstable argsort on the host — NOT the reference's tie order (include/icl_b200.h, icl_rank_device); default numpy
+        self.rank = str(getattr(self, 'rank', 'numpy')).strip().lower()
+        if self.rank not in ('numpy', 'device'):
+            raise ValueError(f"rank = {self.rank}: expected 'numpy' (reference tie order) or 'device'")
         self.timing = {}
 
     # ---- ingest: wgdi/run_colliearity.py:88-121 -------------------------------------------------
@@ -107,13 +112,19 @@ class mycollinearity():
         eng = None
         try:
             if len(self.devices) > 1:
+                if self.rank == 'device':
+                    raise ValueError("rank = device is offered for a single device only")
                 from .shard import chain_on_devices
                 blocks = chain_on_devices(pts, len(pts['pair_names']), params, self.devices, min_members=self.over_gap)
             else:
                 eng = IclEngine(self.devices[0])
                 # blocks are views of the engine's page-locked staging: written out before the engine is closed
-                blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params,
-                                   min_members=self.over_gap, copy=False)
+                if self.rank == 'device':
+                    eng.upload(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']))
+                    blocks = eng.run_resident_device_rank(params, min_members=self.over_gap, copy=False)
+                else:
+                    blocks = eng.chain(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], len(pts['pair_names']), params,
+                                       min_members=self.over_gap, copy=False)
                 self.timing['device_ms'] = eng.timings()
                 self.timing['host_ms'] = dict(eng.host_ms)
             t2 = time.perf_counter()
