@@ -245,7 +245,11 @@ def test_drop_in_driver_sharded_over_devices_emu():
 def test_cli_prints_example_and_missing_conf(capsys):
     from wgdi_b200.run import main
     assert main(["-icl", "?"]) == 0
-    assert "[collinearity]" in capsys.readouterr().out
+    out = capsys.readouterr().out
+    assert out.startswith("[collinearity]\ngff1 = gff1 file\n") and "positon = order" in out and "mg = 25,25" in out
+    assert main(["-bi", "?"]) == 0
+    out = capsys.readouterr().out
+    assert out.startswith("[blockinfo]\nblast = blast file\n") and "ks_col = ks_NG86" in out
     assert main(["-icl", "/nonexistent.conf"]) == 0
     assert "not exists" in capsys.readouterr().out
 

@@ -24,15 +24,15 @@ def main(argv=None):
     parser.add_argument("-bi", dest="blockinfo", metavar="CONF",
                         help="block information of a collinearity file; `?` prints an example conf")
     args = parser.parse_args(argv)
-    tools = (("improvedcollinearity", "collinearity", "collinearity.conf"), ("blockinfo", "blockinfo", "blockinfo.conf"))
-    chosen = [(getattr(args, dest), section, example) for dest, section, example in tools if getattr(args, dest) is not None]
+    tools = (("improvedcollinearity", "collinearity"), ("blockinfo", "blockinfo"))
+    chosen = [(getattr(args, dest), section) for dest, section in tools if getattr(args, dest) is not None]
     if not chosen:
         parser.print_help()
         return 0
-    for conf, section, example in chosen:
+    for conf, section in chosen:
         if conf in ("?", "help", "example"):
-            with open(os.path.join(HERE, "example", example)) as f:
-                print(f.read())
+            from .example import render
+            print(render(section))
             continue
         if not os.path.exists(conf):
             print(f"{conf} not exists")                   # wgdi/run.py:156-158
