@@ -204,6 +204,71 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+PORTABLE_NUMPY = ("AVX2 FMA3 AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX512_KNL AVX512_KNM")
+
+
+def portable_child(args):
+    """Runs in a child process whose numpy has its SIMD sorts disabled (NPY_DISABLE_CPU_FEATURES, set by the parent before
+    numpy is imported): numpy.argsort is then its scalar introsort, which the device reproduces exactly, so the engine
+    ranks on the GPU and the host is out of the step — still the reference's tie order for THAT numpy.  Prints one JSON
+    object: step time with inputs resident, and whether the blocks equal the C oracle's ranked by this process's numpy."""
+    import torch
+    from wgdi_b200.engine import IclEngine
+    dev = args.portable_child
+    torch.cuda.set_device(dev)
+    pts = make_points(args.workload, seed_shift=args.seed_shift)
+    from wgdi_b200 import synth
+    prm = params_for(synth.CONFIGS[args.workload])
+    eng = IclEngine(dev)
+    scalar = eng.numpy_sort_is_scalar()
+    eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+    for _ in range(max(args.warmup, 3)):
+        blocks = eng.run_resident(prm, min_members=5, copy=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    t = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        blocks = eng.run_resident(prm, min_members=5, copy=False)
+        torch.cuda.synchronize()
+        t += time.perf_counter() - t0
+    out = {"ms_per_step": 1e3 * t / args.steps, "hits": len(pts["loc1"]), "numpy_sort_is_scalar": bool(scalar),
+           "rank_on_device": bool(scalar) and eng.rank_mode == "auto", "blocks": len(blocks), "device_ms": eng.timings()}
+    if args.portable_check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import oracle_blocks
+        got = eng.run_resident(prm, min_members=1)
+        exp = oracle_blocks(pts, prm)
+        same = len(got) == len(exp)
+        for b, (pair, d, l1, l2, a, sc) in enumerate(exp if same else []):
+            a0, a1 = got.member_off[b], got.member_off[b + 1]
+            if not (got.pair[b] == pair and got.dir[b] == d and got.score[b] == sc and got.p_raw[b] == a and
+                    (got.loc1[a0:a1] == l1).all() and (got.loc2[a0:a1] == l2).all()):
+                same = False
+                break
+        out["identical_to_oracle_with_this_numpy"] = bool(same)
+    eng.close()
+    print("PORTABLE " + json.dumps(out), flush=True)
+
+
+def run_portable_leg(args, local, rank, world):
+    """Parent side: the same workload in a child with numpy's SIMD sorts disabled (see portable_child)."""
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_NUMPY)
+    cmd = [sys.executable, os.path.abspath(__file__), "--portable-child", str(local), "--workload", args.workload,
+           "--steps", str(args.steps), "--warmup", str(args.warmup), "--seed-shift", str(rank)]
+    if rank == 0 and world == 1:
+        cmd.append("--portable-check")
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("PORTABLE ")]
+        if not line:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        return json.loads(line[-1][len("PORTABLE "):])
+    except Exception as e:                                  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +279,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wall", action="store_true")
     ap.add_argument("--batch", type=int, default=8, help="comparisons in the pipelined-batch leg (0 = skip)")
+    ap.add_argument("--portable-child", type=int, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--portable-check", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--seed-shift", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--no-portable", action="store_true")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("ICL_BENCH_LANES", "1")),
                     help="pipelined lanes per GPU (wgdi_b200/pipeline.py); 1 = plain engine")
     args = ap.parse_args()
@@ -223,6 +292,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
 
+    if args.portable_child is not None:
+        portable_child(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
@@ -360,6 +432,22 @@ def main():
                        "blocks_this_rank": len(out_dev),
                        "what": "NOT bit-exact with the reference: stable device sort instead of numpy's unstable host argsort "
                                "for the extraction order (tied scores in reversed (loc1, loc2) order); inputs resident"}
+    # ---- the reference's tie order WITHOUT the host: in a process whose numpy runs its scalar introsort (SIMD sorts
+    # disabled — also how the fixtures under tests/golden were generated) the device reproduces numpy's argsort exactly and
+    # ranks itself.  One comparison per GPU, every rank's child at the same time.
+    portable = None
+    if not args.no_portable:
+        barrier()
+        portable = run_portable_leg(args, local, rank, world)
+        if "ms_per_step" in portable:
+            tp = torch.tensor([portable["ms_per_step"]], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            portable["ms_per_step_max_over_ranks"] = float(tp.item())
+            portable["value"] = total_points / (float(tp.item()) * 1e-3)
+            portable["unit"] = "hits/s"
+            portable["what"] = ("same path in a child process with NPY_DISABLE_CPU_FEATURES (numpy's scalar argsort): the device "
+                                "reproduces that argsort exactly and ranks itself; reference-exact for that numpy, inputs resident")
     # ---- batch throughput (BASELINE config 5 shape): independent comparisons through two engines on this GPU, one
     # job's host rank overlapping the next job's upload + device phases (wgdi_b200/batch.py); every job uploads
     batch = None
@@ -435,7 +523,7 @@ def main():
                              "frac": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9 / peak,
                              "what": "same kernel with the streamed export off (ICL_B200_STREAM=0), 3 extra untimed passes"},
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
-            "phase_ms": res_ms, "batch": batch, "device_rank_option": device_rank,
+            "phase_ms": res_ms, "batch": batch, "device_rank_option": device_rank, "portable_numpy": portable,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }

@@ -152,15 +152,23 @@ int icl_dp_end(icl_ctx *ctx);
 int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
 
 /*
- * NON-REFERENCE option: rank every (pair, direction) item on the device with a STABLE sort instead of numpy's
- * unstable argsort, then call icl_extract with both argsort pointers NULL.  This is the result pandas'
- * nargsort(ascending=False) would give if numpy's argsort were stable (reverse, stable ascending argsort, reverse):
- * identical to the reference wherever scores are distinct, but tied scores come in reversed (loc1, loc2) order and
- * not in numpy's CPU-specific permutation, so blocks with tied top scores can come out in a different order (and, where
- * they share points, differently).  It removes the host from the step: for throughput runs that do not need the
- * reference's tie order.  icl_dp may then be called with both key pointers NULL (no score export).
+ * Rank every (pair, direction) item on the device instead of on the host, then call icl_extract with both argsort
+ * pointers NULL.  icl_dp may then be called with both key pointers NULL (no score export).  Two modes:
+ *
+ * ICL_RANK_NUMPY_SCALAR — the reference's tie order on every numpy that sorts int64 with its scalar introsort
+ *   (npysort/quicksort.cpp `aquicksort_`: CPUs without AVX2 / AVX-512 sort dispatch, or NPY_DISABLE_CPU_FEATURES —
+ *   which is how the end-to-end fixtures of this repository were generated).  The kernel reproduces that algorithm
+ *   exactly: median of three, Hoare partition, insertion sort up to 16 elements, heap sort at the depth limit.
+ *   A caller may use it whenever numpy.argsort in its own process behaves that way (wgdi_b200/engine.py checks this
+ *   against the running numpy before choosing it); the result is then bit-identical to the host rank.
+ * ICL_RANK_STABLE — NON-REFERENCE: a stable sort, i.e. what pandas' nargsort(ascending=False) would return if numpy's
+ *   argsort were stable (reverse, stable ascending argsort, reverse): identical to the reference wherever scores are
+ *   distinct, but tied scores come in reversed (loc1, loc2) order, so blocks with tied top scores can come out in a
+ *   different order (and, where they share points, differently).  For throughput runs that do not need a tie order.
  */
-int icl_rank_device(icl_ctx *ctx);
+#define ICL_RANK_STABLE 0
+#define ICL_RANK_NUMPY_SCALAR 1
+int icl_rank_device(icl_ctx *ctx, int32_t mode);
 
 /*
  * Block extraction + p values (wgdi/collinearity.py:42-70, 117-153).
@@ -174,7 +182,7 @@ int icl_rank_device(icl_ctx *ctx);
  * blocks still take part in the `times` accounting of the p value (collinearity.py:150).
  * The arrays of `out` live in page-locked staging owned by `ctx`: valid until the next icl_extract or
  * icl_destroy on that context; icl_free_blocks only clears the view.
- * Both argsort pointers NULL: use the order icl_rank_device left on the device (non-reference tie order).
+ * Both argsort pointers NULL: use the order icl_rank_device left on the device.
  */
 int icl_extract(icl_ctx *ctx, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
                 icl_blocks *out);
@@ -184,6 +192,10 @@ void icl_free_blocks(icl_blocks *blocks);
  * pred = sorted position of the last updating source (-1 for path roots), depth = path length,
  * used = (usedtimes > 0).  Any pointer may be NULL. */
 int icl_debug_dp(icl_ctx *ctx, int32_t dir, int32_t *score, int32_t *pred, int32_t *depth, uint8_t *used);
+
+/* Test / diagnostics: the argsort icl_rank_device left on the device, forward segments then anti-diagonal ones (2 n
+ * values, segment-local indices into the REVERSED score arrays — the format icl_extract takes from the host). */
+int icl_debug_order(icl_ctx *ctx, int32_t *argsort);
 
 /* Device time (ms, CUDA events on the context's stream) of the phases of the most recent
  * icl_dp / icl_extract calls; see ICL_T_* for the slots.  Returns the number of slots written. */

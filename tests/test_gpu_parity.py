@@ -459,6 +459,57 @@ def test_device_rank_mode_matches_stable_oracle(gpu_engine, name, scale):
     _compare_with_oracle(got, oracle_blocks_stable(pts, prm))
 
 
+_NPSCALAR_CHILD = r"""
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, %r)
+from wgdi_b200 import synth
+from wgdi_b200._lib import icl_params
+from wgdi_b200.engine import ChainParams, IclEngine
+def check(pts, prm):
+    eng = IclEngine(0)
+    try:
+        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+        kf, kr = eng.dp(prm)                                  # the arrays the host would sort
+        n = eng.n
+        keys = np.concatenate([kf, kr])
+        off = np.concatenate([eng.pair_off, eng.pair_off[1:] + n])
+        eng._check(eng.lib.icl_rank_device(eng.ctx, 1))       # numpy's scalar argsort, on the device
+        got = np.zeros(2 * n, np.int32)
+        eng._check(eng.lib.icl_debug_order(eng.ctx, got.ctypes.data))
+        bad = 0
+        for a, b in zip(off[:-1], off[1:]):
+            exp = keys[a:b].astype(np.int64).argsort(kind="quicksort")      # numpy in THIS process: SIMD sorts disabled
+            bad += not (got[a:b] == exp).all()
+        b1 = eng.run_resident_device_rank(prm, mode="numpy_scalar")
+        b2 = eng.run_resident(prm)                            # host rank with the same numpy
+        same = len(b1) == len(b2) and all((getattr(b1, f) == getattr(b2, f)).all() for f in
+                                          ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx"))
+        return len(off) - 1, bad, same, eng.numpy_sort_is_scalar()
+    finally:
+        eng.close()
+rng = np.random.default_rng(3)
+out = []
+out.append(check(synth.graded_points(synth.make_dataset("small")), ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))))
+out.append(check(synth.graded_points(synth.make_dataset("C2", scale=0.15)), ChainParams(mg1=40, mg2=40, grading=(50, 40, 25))))
+# adversarial segments: all ties, sorted, reversed, organ pipe, few distinct values, one huge pair
+n = 40000
+l1 = np.repeat(np.arange(1, n // 4 + 1), 4).astype(np.int32); l2 = rng.integers(1, 3000, n).astype(np.int32)
+out.append(check(dict(pair_id=np.zeros(n, np.int32), loc1=l1, loc2=l2, grading=rng.choice(np.array([50, 30, 25], np.int32), n), n_pairs=1),
+                 ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))))
+print("RESULT", out)
+assert all(bad == 0 and same and scalar for _, bad, same, scalar in out), out
+print("OK")
+"""
+
+
+def test_device_numpy_scalar_argsort_is_numpys():
+    """icl_rank_device(ICL_RANK_NUMPY_SCALAR) against numpy itself in a process whose numpy runs its scalar introsort
+    (NPY_DISABLE_CPU_FEATURES): every segment's argsort identical, and the blocks identical to the host-ranked path."""
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+    r = subprocess.run([sys.executable, "-c", _NPSCALAR_CHILD % ROOT], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_alternative_dp_kernels_agree(clouds):
     """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth

@@ -392,7 +392,7 @@ def test_device_rank_mode_emu(emu_backend):
     try:
         eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
         with pytest.raises(IclError):
-            eng._check(eng.lib.icl_rank_device(eng.ctx))                 # before icl_dp
+            eng._check(eng.lib.icl_rank_device(eng.ctx, 0))              # before icl_dp
         got = eng.run_resident_device_rank(prm)
         ref = eng.run_resident(prm)
     finally:

@@ -78,7 +78,7 @@ struct icl_ctx {
     Buf<int32_t> S, root;            // root = first point of the path (root of the predecessor tree)
     Buf<int2> pd;                    // per point: {pred (-1 for path roots), path length}
     Buf<uint8_t> used;
-    Buf<int32_t> score32;
+    Buf<int32_t> score32, npscr;     // npscr: stop lists of the numpy-scalar argsort kernel
     // extraction
     Buf<int32_t> order_in, rank2v, acc_L, members, times, mscr;
     Buf<uint32_t> tree_v, acc_m, acc_ms, acc_flag, blkidx, moff;
@@ -1860,14 +1860,240 @@ struct Stage {                               // bump allocator over the context'
 };
 
 // ------------------------------------------------------------------------------------------------
+// numpy's SCALAR argsort, reproduced exactly on the device.
+//
+// numpy.argsort(kind='quicksort') on int64 runs npysort/quicksort.cpp `aquicksort_` wherever no SIMD sort is dispatched
+// (CPUs without AVX2 / AVX-512, or NPY_DISABLE_CPU_FEATURES as used for the fixtures under tests/golden/):
+//   depth limit cdepth = 2 * floor(log2(n)); ranges longer than 16 are partitioned — median of three on
+//   (first, middle, last) with index swaps, pivot parked at last - 1, Hoare scans `do ++pi while v[pi] < vp`,
+//   `do --pj while vp < v[pj]`, swap until they cross, pivot to pi, larger side pushed, smaller side continued, both at
+//   cdepth - 1; a range popped with cdepth < 0 is heap sorted; ranges of at most 16 elements are insertion sorted.
+// (Restated from the numpy source and checked against numpy 2.3.5 with its SIMD sorts disabled on 2 330 arrays.)
+// Its tie permutation is a function of the keys alone, and every step can be done in parallel WITHOUT changing it:
+//  * Hoare partition: the k-th element from the left that is not below the pivot is swapped with the k-th element from
+//    the right that is not above it, for as long as the former lies left of the latter — the stops are found on the
+//    untouched array because a swap never moves anything the scans have yet to pass.  One warp lists both kinds of
+//    stops with ballots, counts the crossing point and performs the swaps at once;
+//  * sub-ranges are independent (only their depth travels with them), so the order in which they are taken is free;
+//  * insertion sort is a stable sort of at most 16 elements: 32 small ranges are sorted at a time, one per lane.
+// One warp per (pair, direction) segment; keys int32 (read only), indices in global memory (L2 resident).
+// ------------------------------------------------------------------------------------------------
+#ifndef ICL_EMU
+struct NpSortArgs {
+    const int32_t *key;        // [2n] segments back to back: the REVERSED score arrays (what pandas hands to numpy)
+    int32_t *idx;              // [2n] out: argsort of every segment (segment-local indices)
+    int32_t *scr;              // [4n] scratch: per segment 2 x len stop lists
+    const int64_t *off;        // [P + 1]
+    const int32_t *order;      // item order (longest first)
+    int64_t n;
+    int32_t P, smem_cap;       // segments of at most smem_cap elements keep keys and indices in shared memory
+};
+
+#define ICL_NPS_SMALL 15         // SMALL_QUICKSORT of this numpy build: ranges with pr - pl <= 15 are insertion sorted
+#define ICL_NPS_STACK 48
+
+__device__ __forceinline__ void nps_heapsort(const int32_t *v, int32_t *tosort, int32_t n) {   // aheapsort_, one lane
+    int32_t *a = tosort - 1, i, j, l, tmp;
+    for (l = n >> 1; l > 0; --l) {
+        tmp = a[l];
+        for (i = l, j = l << 1; j <= n;) {
+            if (j < n && v[a[j]] < v[a[j + 1]]) j += 1;
+            if (v[tmp] < v[a[j]]) { a[i] = a[j]; i = j; j += j; } else break;
+        }
+        a[i] = tmp;
+    }
+    for (; n > 1;) {
+        tmp = a[n]; a[n] = a[1]; n -= 1;
+        for (i = 1, j = 2; j <= n;) {
+            if (j < n && v[a[j]] < v[a[j + 1]]) j++;
+            if (v[tmp] < v[a[j]]) { a[i] = a[j]; i = j; j += j; } else break;
+        }
+        a[i] = tmp;
+    }
+}
+
+// aquicksort_ on x[pl..pr] with depth budget cdepth, by ONE lane (sub-ranges of at most ICL_NPS_LANE elements: below
+// that size a warp-wide partition costs more in fixed overhead than a lane needs for the whole sub-range)
+#define ICL_NPS_LANE 96
+// `popped`: the range comes off the stack (numpy checks the depth budget only then, not for the side it continues with)
+__device__ void nps_seq(const int32_t *v, int32_t *x, int32_t pl, int32_t pr, int cdepth, bool popped) {
+    int32_t slo[10], shi[10];
+    int sd[10], sp = 0;
+    for (;;) {
+        if (popped && cdepth < 0) {
+            nps_heapsort(v, x + pl, pr - pl + 1);
+        } else {
+            while (pr - pl > ICL_NPS_SMALL) {
+                const int32_t pm = pl + ((pr - pl) >> 1);
+                int32_t t;
+                if (v[x[pm]] < v[x[pl]]) { t = x[pm]; x[pm] = x[pl]; x[pl] = t; }
+                if (v[x[pr]] < v[x[pm]]) { t = x[pr]; x[pr] = x[pm]; x[pm] = t; }
+                if (v[x[pm]] < v[x[pl]]) { t = x[pm]; x[pm] = x[pl]; x[pl] = t; }
+                const int32_t vp = v[x[pm]];
+                int32_t pi = pl, pj = pr - 1;
+                t = x[pm]; x[pm] = x[pj]; x[pj] = t;
+                for (;;) {
+                    do { ++pi; } while (v[x[pi]] < vp);
+                    do { --pj; } while (vp < v[x[pj]]);
+                    if (pi >= pj) break;
+                    t = x[pi]; x[pi] = x[pj]; x[pj] = t;
+                }
+                t = x[pi]; x[pi] = x[pr - 1]; x[pr - 1] = t;
+                if (pi - pl < pr - pi) { slo[sp] = pi + 1; shi[sp] = pr; pr = pi - 1; }
+                else { slo[sp] = pl; shi[sp] = pi - 1; pl = pi + 1; }
+                sd[sp++] = --cdepth;
+            }
+            for (int32_t pi = pl + 1; pi <= pr; ++pi) {                  // insertion sort
+                const int32_t vi = x[pi], vp = v[vi];
+                int32_t pj = pi;
+                while (pj > pl && vp < v[x[pj - 1]]) { x[pj] = x[pj - 1]; pj--; }
+                x[pj] = vi;
+            }
+        }
+        if (sp == 0) break;
+        sp--;
+        pl = slo[sp]; pr = shi[sp]; cdepth = sd[sp];
+        popped = true;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_np_argsort(NpSortArgs A) {
+    __shared__ int32_t st_lo[ICL_NPS_STACK], st_hi[ICL_NPS_STACK], st_d[ICL_NPS_STACK];
+    __shared__ int32_t sm_lo[32], sm_hi[32], sm_d[32], sm_p[32];
+    const int lane = threadIdx.x;
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t it = A.order[blockIdx.x];
+    const int32_t p = it >= A.P ? it - A.P : it;
+    const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
+    const int32_t len = (int32_t)(A.off[p + 1] - A.off[p]);
+    if (len <= 0) return;
+    extern __shared__ int32_t nps_sm[];
+    const bool fits = len <= A.smem_cap;
+    const int32_t *v = A.key + base;
+    int32_t *x = A.idx + base;
+    if (fits) {                                              // the whole segment on chip: every gather is a shared-memory load
+        int32_t *vs = nps_sm, *xs = nps_sm + A.smem_cap;
+        for (int32_t i = lane; i < len; i += 32) { vs[i] = v[i]; xs[i] = i; }
+        v = vs;
+        x = xs;
+    } else {
+        for (int32_t i = lane; i < len; i += 32) x[i] = i;
+    }
+    int32_t *Ls = A.scr + 2 * base, *Rs = Ls + len;
+    __syncwarp();
+    int sp = 0, nsmall = 0;
+    {
+        int msb = 31 - __clz((unsigned)len);
+        if (lane == 0) { st_lo[0] = 0; st_hi[0] = len - 1; st_d[0] = 2 * msb; }
+        sp = 1;
+    }
+    __syncwarp();
+    // sub-ranges of at most ICL_NPS_LANE elements are collected and sorted 32 at a time, one per lane
+    auto flush_small = [&]() {
+        __syncwarp();
+        if (lane < nsmall) nps_seq(v, x, sm_lo[lane], sm_hi[lane], sm_d[lane], sm_p[lane] != 0);
+        nsmall = 0;
+        __syncwarp();
+    };
+    while (sp > 0) {
+        sp--;
+        int32_t pl = st_lo[sp], pr = st_hi[sp], cdepth = st_d[sp];
+        bool popped = true;
+        __syncwarp();
+        if (cdepth < 0 && pr - pl + 1 > ICL_NPS_LANE) {
+            if (lane == 0) nps_heapsort(v, x + pl, pr - pl + 1);
+            __syncwarp();
+            continue;
+        }
+        while (pr - pl + 1 > ICL_NPS_LANE) {
+            // median of three with index swaps, pivot parked at pr - 1 (lane 0; a handful of dependent loads)
+            int32_t vp = 0;
+            if (lane == 0) {
+                const int32_t pm = pl + ((pr - pl) >> 1);
+                int32_t a = x[pl], b = x[pm], c = x[pr];
+                if (v[b] < v[a]) { int32_t t = a; a = b; b = t; }
+                if (v[c] < v[b]) { int32_t t = b; b = c; c = t; }
+                if (v[b] < v[a]) { int32_t t = a; a = b; b = t; }
+                vp = v[b];
+                x[pl] = a; x[pr] = c;
+                x[pm] = x[pr - 1];                  // INTP_SWAP(*pm, *pj) with pj = pr - 1 (pm < pr - 1 here)
+                x[pr - 1] = b;
+            }
+            vp = __shfl_sync(FULL, vp, 0);
+            __syncwarp();
+            // stop lists: L = positions in [pl + 1, pr - 1] with key >= pivot, ascending;
+            //             R = positions in [pl, pr - 2] with key <= pivot, descending
+            // one ascending pass lists both kinds of stops; the right-hand stops are read back to front below
+            int32_t nL = 0, nR = 0;
+            for (int32_t b0 = pl; b0 <= pr - 1; b0 += 32) {
+                const int32_t q = b0 + lane;
+                const int32_t kq = q <= pr - 1 ? v[x[q]] : 0;
+                const bool fl = q >= pl + 1 && q <= pr - 1 && !(kq < vp);
+                const bool fr = q <= pr - 2 && !(vp < kq);
+                const uint32_t ml = __ballot_sync(FULL, fl), mr = __ballot_sync(FULL, fr);
+                const uint32_t below = (1u << lane) - 1u;
+                if (fl) Ls[nL + __popc(ml & below)] = q;
+                if (fr) Rs[nR + __popc(mr & below)] = q;
+                nL += __popc(ml);
+                nR += __popc(mr);
+            }
+            __syncwarp();
+            // K = number of k with L[k] < R[k] (a prefix: L ascends, R descends); then swap those pairs
+            const int32_t kmax = nL < nR ? nL : nR;
+            int32_t K = 0;
+            for (int32_t b0 = 0; b0 < kmax; b0 += 32) {
+                const int32_t k = b0 + lane;
+                const bool f = k < kmax && Ls[k] < Rs[nR - 1 - k];
+                const uint32_t m = __ballot_sync(FULL, f);
+                K += __popc(m);
+                if (m != FULL) break;
+            }
+            for (int32_t k = lane; k < K; k += 32) {
+                const int32_t a = Ls[k], b = Rs[nR - 1 - k];
+                const int32_t t = x[a]; x[a] = x[b]; x[b] = t;
+            }
+            __syncwarp();
+            // where the left scan stops for good: the next stop of the untouched array, or the slot the last swap filled
+            // from the left side, whichever comes first
+            int32_t pi = Ls[K];
+            if (K >= 1 && Rs[nR - K] < pi) pi = Rs[nR - K];
+            if (lane == 0) { const int32_t t = x[pi]; x[pi] = x[pr - 1]; x[pr - 1] = t; }
+            __syncwarp();
+            --cdepth;
+            // push the larger side, continue with the smaller one (both at the decremented depth)
+            int32_t ql, qr;
+            if (pi - pl < pr - pi) { ql = pi + 1; qr = pr; pr = pi - 1; }
+            else { ql = pl; qr = pi - 1; pl = pi + 1; }
+            if (lane == 0) { st_lo[sp] = ql; st_hi[sp] = qr; st_d[sp] = cdepth; }
+            sp++;
+            popped = false;
+            __syncwarp();
+        }
+        if (pr > pl) {                                       // the rest of this sub-range goes to one lane, with its depth
+            if (lane == 0) { sm_lo[nsmall] = pl; sm_hi[nsmall] = pr; sm_d[nsmall] = cdepth; sm_p[nsmall] = popped ? 1 : 0; }
+            nsmall++;
+            if (nsmall == 32) flush_small();
+        }
+    }
+    if (nsmall) flush_small();
+    if (fits) {
+        __syncwarp();
+        int32_t *out = A.idx + base;
+        for (int32_t i = lane; i < len; i += 32) out[i] = x[i];
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // ABI: icl_rank_device — NON-REFERENCE tie order.  The extraction order of every (pair, direction) item from a
 // STABLE device sort: what pandas' nargsort(ascending=False) would return if numpy's argsort were stable (reverse,
 // stable ascending argsort, reverse).  Identical to the reference wherever scores are distinct; tied scores come
 // in reversed (loc1, loc2) order instead of numpy's CPU-specific permutation.
 // ------------------------------------------------------------------------------------------------
-extern "C" int icl_rank_device(icl_ctx *c) {
+extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     if (!c) return ICL_ERR_ARG;
     if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_rank_device: icl_dp has not succeeded");
+    if (mode != ICL_RANK_STABLE && mode != ICL_RANK_NUMPY_SCALAR) return fail(c, ICL_ERR_ARG, "icl_rank_device: unknown mode");
     Status &st = c->st;
     st.code = 0;
 #ifndef ICL_EMU
@@ -1880,7 +2106,30 @@ extern "C" int icl_rank_device(icl_ctx *c) {
     if (c->order_in.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V))
         return st.code;
-    if (n > 0) {
+    if (n > 0 && mode == ICL_RANK_NUMPY_SCALAR) {
+        // the REVERSED score array of every (pair, direction) item, as in the score export of icl_dp
+        if (c->score32.reserve(st, V) || c->npscr.reserve(st, 2 * V)) return st.code;
+        const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
+        const int64_t *off = c->d_pair_off.p;
+        int32_t *o = c->score32.p;
+        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
+            int32_t p = ps[i];
+            int64_t src = off[p] + (off[p + 1] - 1 - i);
+            o[i] = S[src];
+            o[n + i] = S[mmap[src]];
+        }));
+#ifndef ICL_EMU
+        int64_t longest = 0;
+        for (int32_t q = 0; q < P; q++) longest = std::max<int64_t>(longest, c->h_pair_off[q + 1] - c->h_pair_off[q]);
+        const int32_t cap = (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);          // 96 KB at most
+        NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
+        ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        k_np_argsort<<<(unsigned)(2 * P), 32, (size_t)cap * 8, s>>>(A);
+        ICL_CUDA(st, cudaGetLastError());
+#else
+        return fail(c, ICL_ERR_STATE, "icl_rank_device: the numpy-scalar mode exists in the CUDA build only");
+#endif
+    } else if (n > 0) {
         // element i of the first half = position j of pair p's REVERSED segment (as in the score export of icl_dp);
         // key = item | score, value = j; a stable sort leaves every item's ascending argsort in place
         const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
@@ -1901,6 +2150,20 @@ extern "C" int icl_rank_device(icl_ctx *c) {
     }
     c->timers[ICL_T_D2H].stop(s);
     c->order_on_device = true;
+    return ICL_OK;
+}
+
+extern "C" int icl_debug_order(icl_ctx *c, int32_t *argsort) {
+    if (!c || !argsort) return ICL_ERR_ARG;
+    if (!c->order_on_device) return fail(c, ICL_ERR_STATE, "icl_debug_order: icl_rank_device has not succeeded");
+    Status &st = c->st;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaSetDevice(c->device));
+#endif
+    if (c->n > 0) {
+        ICL_CUDA(st, d2h(argsort, c->order_in.p, (size_t)2 * c->n * sizeof(int32_t), c->stream));
+        ICL_CUDA(st, dev_sync(c->stream));
+    }
     return ICL_OK;
 }
 

@@ -26,6 +26,7 @@ try:                                    # numpy's own argsort routine, GIL-free 
 except ImportError:                     # not built: one numpy call per segment instead (same results)
     _npsort = None
 _NPSORT_OK = None
+_NP_SCALAR = {}          # device -> numpy's argsort in this process is the scalar introsort (IclEngine.numpy_sort_is_scalar)
 
 
 def _npsort_ok():
@@ -144,6 +145,10 @@ class IclEngine:
         self._pool = ThreadPoolExecutor(self.sort_threads) if self.sort_threads > 1 else None
         # overlap the host rank with the DP kernel (icl_dp_begin); ICL_B200_STREAM=0 runs the two one after the other
         self.stream_rank = os.environ.get("ICL_B200_STREAM", "1") != "0"
+        # who ranks: "auto" = the device when it provably gives numpy's own permutation in this process (numpy running its
+        # scalar introsort), else the host; "host" = always numpy on the host; "device" = the device's numpy-scalar sort
+        # regardless (the reference's tie order on machines without SIMD-sort numpy)
+        self.rank_mode = os.environ.get("ICL_B200_RANK", "auto")
         self.host_ms = {}
 
     # ---- plumbing ------------------------------------------------------------------------------
@@ -328,16 +333,48 @@ class IclEngine:
         self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3)
         return both[:n], both[n:]
 
-    def run_resident_device_rank(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
-        """NON-REFERENCE tie order: like `run_resident`, but the extraction order comes from a stable sort on the device
-        (icl_rank_device) instead of numpy's unstable argsort on the host.  Same blocks wherever scores are distinct."""
+    def numpy_sort_is_scalar(self):
+        """True when numpy.argsort(kind='quicksort') on int64 in THIS process is numpy's scalar introsort (no SIMD sort
+        dispatched: older CPUs, or NPY_DISABLE_CPU_FEATURES), checked by sorting tie-heavy arrays both with numpy and
+        with the device's exact reproduction of that algorithm (icl_rank_device, ICL_RANK_NUMPY_SCALAR).  Only then may
+        the device rank replace the host rank without changing a single tie."""
+        if _NP_SCALAR.get(self.device) is None:
+            rng = np.random.default_rng(20260)
+            sizes = [1, 2, 16, 17, 18, 33, 100, 257, 1000, 4099, 9001]
+            n = sum(sizes)
+            pair = np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)
+            loc1 = np.concatenate([np.arange(1, m + 1) for m in sizes]).astype(np.int32)
+            loc2 = rng.integers(1, 40, n).astype(np.int32)            # dense columns: long chains, many tied scores
+            grad = rng.choice(np.array([50, 30, 25], np.int32), n)
+            probe = IclEngine(self.device, sort_threads=1)
+            try:
+                probe.upload(pair, loc1, loc2, grad, len(sizes))
+                kf, kr = probe.dp(ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))
+                keys = np.concatenate([kf, kr])
+                off = np.concatenate([probe.pair_off, probe.pair_off[1:] + n])
+                probe._check(probe.lib.icl_rank_device(probe.ctx, 1))
+                got = np.zeros(2 * n, np.int32)
+                probe._check(probe.lib.icl_debug_order(probe.ctx, got.ctypes.data))
+                _NP_SCALAR[self.device] = all((got[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all()
+                                              for a, b in zip(off[:-1], off[1:]))
+            except IclError:
+                _NP_SCALAR[self.device] = False            # e.g. a backend without the kernel: the host ranks
+            finally:
+                probe.close()
+        return _NP_SCALAR[self.device]
+
+    def run_resident_device_rank(self, params: ChainParams, min_members: int = 1, copy: bool = True,
+                                 mode: str = "stable") -> Blocks:
+        """Like `run_resident`, but the extraction order comes from the device (icl_rank_device) instead of numpy on the
+        host.  mode "stable": NON-REFERENCE tie order (same blocks wherever scores are distinct); mode "numpy_scalar":
+        numpy's scalar introsort reproduced exactly — the reference's tie order wherever numpy has no SIMD sort."""
         prm = icl_params(int(params.mg1), int(params.mg2), int(params.grading[0]), int(params.over_gap),
                          float(params.coverage_ratio))
         t0 = time.perf_counter()
         self._check(self.lib.icl_dp(self.ctx, C.byref(prm), None, None))
         self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
         self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
-        self._check(self.lib.icl_rank_device(self.ctx))
+        self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1}[mode]))
         out = icl_blocks()
         self._check(self.lib.icl_extract(self.ctx, None, None, int(min_members), C.byref(out)))
         res = self._blocks_from(out, copy)
@@ -345,7 +382,11 @@ class IclEngine:
         return res
 
     def run_resident(self, params: ChainParams, min_members: int = 1, copy: bool = True) -> Blocks:
-        """Hot path on points already uploaded: sort + DP -> host rank -> extraction + p values."""
+        """Hot path on points already uploaded: sort + DP -> rank -> extraction + p values.  The rank is numpy's own
+        argsort on the host, except when numpy in this process runs its scalar introsort (no SIMD sort dispatched): the
+        device reproduces that algorithm exactly, so it ranks there and the host is out of the step (`rank_mode`)."""
+        if self.rank_mode == "device" or (self.rank_mode == "auto" and self.numpy_sort_is_scalar()):
+            return self.run_resident_device_rank(params, min_members, copy, mode="numpy_scalar")
         if self.stream_rank and _npsort_ok():
             af, ar = self.dp_rank_streamed(params)
             t2 = time.perf_counter()
