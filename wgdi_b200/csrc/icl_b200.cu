@@ -1890,7 +1890,7 @@ struct NpSortArgs {
 };
 
 #define ICL_NPS_SMALL 15         // SMALL_QUICKSORT of this numpy build: ranges with pr - pl <= 15 are insertion sorted
-#define ICL_NPS_STACK 48
+#define ICL_NPS_STACK 160
 
 __device__ __forceinline__ void nps_heapsort(const int32_t *v, int32_t *tosort, int32_t n) {   // aheapsort_, one lane
     int32_t *a = tosort - 1, i, j, l, tmp;
@@ -1957,10 +1957,15 @@ __device__ void nps_seq(const int32_t *v, int32_t *x, int32_t pl, int32_t pr, in
     }
 }
 
-__global__ void __launch_bounds__(32) k_np_argsort(NpSortArgs A) {
+#define ICL_NPS_WARPS 8
+// One CTA of ICL_NPS_WARPS warps per segment.  The warps share a stack of sub-ranges (any order is fine: sub-ranges are
+// disjoint and carry their own depth budget): a warp pops a range, partitions it, pushes the larger side and goes on
+// with the smaller one until what is left fits a lane; those leftovers are sorted 32 at a time, one per lane.
+__global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A) {
     __shared__ int32_t st_lo[ICL_NPS_STACK], st_hi[ICL_NPS_STACK], st_d[ICL_NPS_STACK];
-    __shared__ int32_t sm_lo[32], sm_hi[32], sm_d[32], sm_p[32];
-    const int lane = threadIdx.x;
+    __shared__ int32_t sm_lo[ICL_NPS_WARPS][32], sm_hi[ICL_NPS_WARPS][32], sm_d[ICL_NPS_WARPS][32], sm_p[ICL_NPS_WARPS][32];
+    __shared__ int32_t s_sp, s_pending, s_lock;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t FULL = 0xffffffffu;
     const int32_t it = A.order[blockIdx.x];
     const int32_t p = it >= A.P ? it - A.P : it;
@@ -1973,39 +1978,61 @@ __global__ void __launch_bounds__(32) k_np_argsort(NpSortArgs A) {
     int32_t *x = A.idx + base;
     if (fits) {                                              // the whole segment on chip: every gather is a shared-memory load
         int32_t *vs = nps_sm, *xs = nps_sm + A.smem_cap;
-        for (int32_t i = lane; i < len; i += 32) { vs[i] = v[i]; xs[i] = i; }
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) { vs[i] = v[i]; xs[i] = i; }
         v = vs;
         x = xs;
     } else {
-        for (int32_t i = lane; i < len; i += 32) x[i] = i;
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) x[i] = i;
     }
-    int32_t *Ls = A.scr + 2 * base, *Rs = Ls + len;
-    __syncwarp();
-    int sp = 0, nsmall = 0;
-    {
-        int msb = 31 - __clz((unsigned)len);
-        if (lane == 0) { st_lo[0] = 0; st_hi[0] = len - 1; st_d[0] = 2 * msb; }
-        sp = 1;
+    int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;        // a range [pl, pr] uses the slice [pl, pr] of both lists
+    if (threadIdx.x == 0) {
+        st_lo[0] = 0; st_hi[0] = len - 1; st_d[0] = 2 * (31 - __clz((unsigned)len));
+        s_sp = 1; s_pending = 1; s_lock = 0;
     }
-    __syncwarp();
-    // sub-ranges of at most ICL_NPS_LANE elements are collected and sorted 32 at a time, one per lane
+    __syncthreads();
+    volatile int32_t *vsp = &s_sp, *vpend = &s_pending;
+    auto lock = [&]() { while (atomicCAS(&s_lock, 0, 1) != 0) __nanosleep(20); __threadfence_block(); };
+    auto unlock = [&]() { __threadfence_block(); atomicExch(&s_lock, 0); };
+    int nsmall = 0;
+    // sub-ranges of at most ICL_NPS_LANE elements are collected per warp and sorted 32 at a time, one per lane
     auto flush_small = [&]() {
         __syncwarp();
-        if (lane < nsmall) nps_seq(v, x, sm_lo[lane], sm_hi[lane], sm_d[lane], sm_p[lane] != 0);
+        if (lane < nsmall) nps_seq(v, x, sm_lo[w][lane], sm_hi[w][lane], sm_d[w][lane], sm_p[w][lane] != 0);
         nsmall = 0;
         __syncwarp();
     };
-    while (sp > 0) {
-        sp--;
-        int32_t pl = st_lo[sp], pr = st_hi[sp], cdepth = st_d[sp];
+    for (;;) {
+        // ---- pop a range (lane 0), or leave when the stack is empty and nobody is still producing
+        int32_t pl = 0, pr = 0, cdepth = 0, got = 0;
+        if (lane == 0) {
+            for (;;) {
+                lock();
+                if (*vsp > 0) {
+                    const int32_t t = *vsp - 1;
+                    pl = st_lo[t]; pr = st_hi[t]; cdepth = st_d[t];
+                    *vsp = t;
+                    got = 1;
+                    unlock();
+                    break;
+                }
+                const int32_t pend = *vpend;
+                unlock();
+                if (pend == 0) break;
+                __nanosleep(200);
+            }
+        }
+        got = __shfl_sync(FULL, got, 0);
+        if (!got) break;
+        pl = __shfl_sync(FULL, pl, 0); pr = __shfl_sync(FULL, pr, 0); cdepth = __shfl_sync(FULL, cdepth, 0);
         bool popped = true;
-        __syncwarp();
         if (cdepth < 0 && pr - pl + 1 > ICL_NPS_LANE) {
             if (lane == 0) nps_heapsort(v, x + pl, pr - pl + 1);
             __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicSub(&s_pending, 1); }
             continue;
         }
         while (pr - pl + 1 > ICL_NPS_LANE) {
+            int32_t *Ls = Lbase + pl, *Rs = Rbase + pl;
             // median of three with index swaps, pivot parked at pr - 1 (lane 0; a handful of dependent loads)
             int32_t vp = 0;
             if (lane == 0) {
@@ -2022,8 +2049,8 @@ __global__ void __launch_bounds__(32) k_np_argsort(NpSortArgs A) {
             vp = __shfl_sync(FULL, vp, 0);
             __syncwarp();
             // stop lists: L = positions in [pl + 1, pr - 1] with key >= pivot, ascending;
-            //             R = positions in [pl, pr - 2] with key <= pivot, descending
-            // one ascending pass lists both kinds of stops; the right-hand stops are read back to front below
+            //             R = positions in [pl, pr - 2] with key <= pivot — listed ascending in the same pass and read
+            //             back to front below
             int32_t nL = 0, nR = 0;
             for (int32_t b0 = pl; b0 <= pr - 1; b0 += 32) {
                 const int32_t q = b0 + lane;
@@ -2060,26 +2087,33 @@ __global__ void __launch_bounds__(32) k_np_argsort(NpSortArgs A) {
             if (lane == 0) { const int32_t t = x[pi]; x[pi] = x[pr - 1]; x[pr - 1] = t; }
             __syncwarp();
             --cdepth;
-            // push the larger side, continue with the smaller one (both at the decremented depth)
+            // push the larger side for any warp to take, continue with the smaller one (both at the decremented depth)
             int32_t ql, qr;
             if (pi - pl < pr - pi) { ql = pi + 1; qr = pr; pr = pi - 1; }
             else { ql = pl; qr = pi - 1; pl = pi + 1; }
-            if (lane == 0) { st_lo[sp] = ql; st_hi[sp] = qr; st_d[sp] = cdepth; }
-            sp++;
+            if (lane == 0) {
+                lock();
+                const int32_t t = *vsp;
+                st_lo[t] = ql; st_hi[t] = qr; st_d[t] = cdepth;
+                *vsp = t + 1;
+                atomicAdd(&s_pending, 1);             // (the decrements are atomics outside the lock)
+                unlock();
+            }
             popped = false;
             __syncwarp();
         }
         if (pr > pl) {                                       // the rest of this sub-range goes to one lane, with its depth
-            if (lane == 0) { sm_lo[nsmall] = pl; sm_hi[nsmall] = pr; sm_d[nsmall] = cdepth; sm_p[nsmall] = popped ? 1 : 0; }
+            if (lane == 0) { sm_lo[w][nsmall] = pl; sm_hi[w][nsmall] = pr; sm_d[w][nsmall] = cdepth; sm_p[w][nsmall] = popped ? 1 : 0; }
             nsmall++;
             if (nsmall == 32) flush_small();
         }
+        if (lane == 0) { __threadfence_block(); atomicSub(&s_pending, 1); }
     }
     if (nsmall) flush_small();
+    __syncthreads();
     if (fits) {
-        __syncwarp();
         int32_t *out = A.idx + base;
-        for (int32_t i = lane; i < len; i += 32) out[i] = x[i];
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) out[i] = x[i];
     }
 }
 #endif
@@ -2124,7 +2158,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
         const int32_t cap = (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);          // 96 KB at most
         NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
         ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        k_np_argsort<<<(unsigned)(2 * P), 32, (size_t)cap * 8, s>>>(A);
+        k_np_argsort<<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, (size_t)cap * 8, s>>>(A);
         ICL_CUDA(st, cudaGetLastError());
 #else
         return fail(c, ICL_ERR_STATE, "icl_rank_device: the numpy-scalar mode exists in the CUDA build only");
