@@ -300,6 +300,9 @@ def main():
     ap.add_argument("--portable-check", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--seed-shift", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-portable", action="store_true")
+    ap.add_argument("--portable", action="store_true",
+                    help="run the WHOLE benchmark (either arm) with numpy's SIMD sorts disabled (NPY_DISABLE_CPU_FEATURES): "
+                         "numpy's scalar argsort, the tie order that is the same on every machine; the engine then ranks on the device")
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("ICL_BENCH_LANES", "1")),
                     help="pipelined lanes per GPU (wgdi_b200/pipeline.py); 1 = plain engine")
     args = ap.parse_args()
@@ -309,6 +312,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
 
+    if args.portable and os.environ.get("NPY_DISABLE_CPU_FEATURES") != PORTABLE_NUMPY:
+        # numpy reads the variable when it is imported, which has happened already: start over with it set
+        os.environ["NPY_DISABLE_CPU_FEATURES"] = PORTABLE_NUMPY
+        os.execve(sys.executable, [sys.executable] + sys.argv, os.environ)
     if args.portable_child is not None:
         portable_child(args)
         return
@@ -510,7 +517,8 @@ def main():
     if rank == 0:
         peak, peak_kind = peaks()
         chain_ms = res_ms["chain"]
-        streamed = bool(getattr(eng, "stream_rank", False)) and counters["chain_kernel"] == "ring"
+        on_device = getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_is_scalar") and eng.numpy_sort_is_scalar()
+        streamed = bool(getattr(eng, "stream_rank", False)) and counters["chain_kernel"] == "ring" and not on_device
         bytes_pp = DP_BYTES_PER_POINT + (EXPORT_BYTES_PER_POINT if streamed else 0)
         achieved = bytes_pp * n_local / (chain_ms * 1e-3) / 1e9
         d2h = 16 * n_local + int(len(blocks) * 64 + len(blocks.loc1) * 12)
@@ -525,7 +533,9 @@ def main():
                        "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
                        "lanes_per_gpu": args.lanes,
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
-                       "tie_order": "numpy argsort on host between the two device phases (reference-exact)"},
+                       "tie_order": ("numpy's scalar argsort (NPY_DISABLE_CPU_FEATURES), reproduced exactly on the device: reference-exact for this numpy"
+                                     if getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_is_scalar") and eng.numpy_sort_is_scalar()
+                                     else "numpy argsort on host between the two device phases (reference-exact)")},
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "ms_per_step_cuda_events": 1e3 * ev_e2e / args.steps,
                     "h2d_bytes_per_step": 16 * n_local + 8 * n_local, "d2h_bytes_per_step": d2h},
