@@ -1892,8 +1892,10 @@ struct NpSortArgs {
 #define ICL_NPS_SMALL 15         // SMALL_QUICKSORT of this numpy build: ranges with pr - pl <= 15 are insertion sorted
 #define ICL_NPS_STACK 160
 
-__device__ __forceinline__ void nps_heapsort(const int32_t *v, int32_t *tosort, int32_t n) {   // aheapsort_, one lane
-    int32_t *a = tosort - 1, i, j, l, tmp;
+template <class IdxT>
+__device__ __forceinline__ void nps_heapsort(const int32_t *v, IdxT *tosort, int32_t n) {   // aheapsort_, one lane
+    IdxT *a = tosort - 1;
+    int32_t i, j, l, tmp;
     for (l = n >> 1; l > 0; --l) {
         tmp = a[l];
         for (i = l, j = l << 1; j <= n;) {
@@ -1916,7 +1918,8 @@ __device__ __forceinline__ void nps_heapsort(const int32_t *v, int32_t *tosort, 
 // that size a warp-wide partition costs more in fixed overhead than a lane needs for the whole sub-range)
 #define ICL_NPS_LANE 96
 // `popped`: the range comes off the stack (numpy checks the depth budget only then, not for the side it continues with)
-__device__ void nps_seq(const int32_t *v, int32_t *x, int32_t pl, int32_t pr, int cdepth, bool popped) {
+template <class IdxT>
+__device__ void nps_seq(const int32_t *v, IdxT *x, int32_t pl, int32_t pr, int cdepth, bool popped) {
     int32_t slo[10], shi[10];
     int sd[10], sp = 0;
     for (;;) {
@@ -1961,6 +1964,7 @@ __device__ void nps_seq(const int32_t *v, int32_t *x, int32_t pl, int32_t pr, in
 // One CTA of ICL_NPS_WARPS warps per segment.  The warps share a stack of sub-ranges (any order is fine: sub-ranges are
 // disjoint and carry their own depth budget): a warp pops a range, partitions it, pushes the larger side and goes on
 // with the smaller one until what is left fits a lane; those leftovers are sorted 32 at a time, one per lane.
+template <class IdxT>
 __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A) {
     __shared__ int32_t st_lo[ICL_NPS_STACK], st_hi[ICL_NPS_STACK], st_d[ICL_NPS_STACK];
     __shared__ int32_t sm_lo[ICL_NPS_WARPS][32], sm_hi[ICL_NPS_WARPS][32], sm_d[ICL_NPS_WARPS][32], sm_p[ICL_NPS_WARPS][32];
@@ -1973,16 +1977,20 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
     const int32_t len = (int32_t)(A.off[p + 1] - A.off[p]);
     if (len <= 0) return;
     extern __shared__ int32_t nps_sm[];
-    const bool fits = len <= A.smem_cap;
+    // IdxT = uint16_t: every segment fits shared memory with 16-bit indices (6 B per element, more CTAs per SM);
+    // IdxT = int32_t: segments beyond smem_cap work on global memory
+    const bool fits = sizeof(IdxT) == 2 || len <= A.smem_cap;
     const int32_t *v = A.key + base;
-    int32_t *x = A.idx + base;
+    IdxT *x;
     if (fits) {                                              // the whole segment on chip: every gather is a shared-memory load
-        int32_t *vs = nps_sm, *xs = nps_sm + A.smem_cap;
-        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) { vs[i] = v[i]; xs[i] = i; }
+        int32_t *vs = nps_sm;
+        IdxT *xs = (IdxT *)(nps_sm + A.smem_cap);
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) { vs[i] = v[i]; xs[i] = (IdxT)i; }
         v = vs;
         x = xs;
     } else {
-        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) x[i] = i;
+        x = (IdxT *)(A.idx + base);                          // only reached with IdxT = int32_t
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) x[i] = (IdxT)i;
     }
     int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;        // a range [pl, pr] uses the slice [pl, pr] of both lists
     if (threadIdx.x == 0) {
@@ -2042,9 +2050,9 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
                 if (v[c] < v[b]) { int32_t t = b; b = c; c = t; }
                 if (v[b] < v[a]) { int32_t t = a; a = b; b = t; }
                 vp = v[b];
-                x[pl] = a; x[pr] = c;
+                x[pl] = (IdxT)a; x[pr] = (IdxT)c;
                 x[pm] = x[pr - 1];                  // INTP_SWAP(*pm, *pj) with pj = pr - 1 (pm < pr - 1 here)
-                x[pr - 1] = b;
+                x[pr - 1] = (IdxT)b;
             }
             vp = __shfl_sync(FULL, vp, 0);
             __syncwarp();
@@ -2077,14 +2085,14 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
             }
             for (int32_t k = lane; k < K; k += 32) {
                 const int32_t a = Ls[k], b = Rs[nR - 1 - k];
-                const int32_t t = x[a]; x[a] = x[b]; x[b] = t;
+                const IdxT t = x[a]; x[a] = x[b]; x[b] = t;
             }
             __syncwarp();
             // where the left scan stops for good: the next stop of the untouched array, or the slot the last swap filled
             // from the left side, whichever comes first
             int32_t pi = Ls[K];
             if (K >= 1 && Rs[nR - K] < pi) pi = Rs[nR - K];
-            if (lane == 0) { const int32_t t = x[pi]; x[pi] = x[pr - 1]; x[pr - 1] = t; }
+            if (lane == 0) { const IdxT t = x[pi]; x[pi] = x[pr - 1]; x[pr - 1] = t; }
             __syncwarp();
             --cdepth;
             // push the larger side for any warp to take, continue with the smaller one (both at the decremented depth)
@@ -2155,10 +2163,17 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
 #ifndef ICL_EMU
         int64_t longest = 0;
         for (int32_t q = 0; q < P; q++) longest = std::max<int64_t>(longest, c->h_pair_off[q + 1] - c->h_pair_off[q]);
-        const int32_t cap = (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);          // 96 KB at most
-        NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
-        ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        k_np_argsort<<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, (size_t)cap * 8, s>>>(A);
+        if (longest <= 16000) {                                  // 16-bit indices: 6 B per element, everything on chip
+            const int32_t cap = (int32_t)((longest + 31) & ~31ll);
+            NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
+            ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            k_np_argsort<uint16_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, (size_t)cap * 6, s>>>(A);
+        } else {
+            const int32_t cap = (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);      // 96 KB at most
+            NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
+            ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            k_np_argsort<int32_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, (size_t)cap * 8, s>>>(A);
+        }
         ICL_CUDA(st, cudaGetLastError());
 #else
         return fail(c, ICL_ERR_STATE, "icl_rank_device: the numpy-scalar mode exists in the CUDA build only");
