@@ -23,7 +23,6 @@ numpy float64 rounding (`round(np.float64, 4)`).
 from __future__ import annotations
 
 import configparser
-import os
 
 import numpy as np
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import (PORTABLE_ENV, ROOT, check_blocks_against_golden, check_dp_against_golden, oracle_batch,
-                      oracle_blocks, oracle_blocks_stable, sorted_layout, stage_e2e)
+                      oracle_blocks, oracle_blocks_stable, stage_e2e)
 
 pytestmark = pytest.mark.gpu
 

@@ -1,8 +1,6 @@
 """Host-side logic and the ABI surface, without a GPU.  Device work is served by the `emu_backend`
 fixture (a g++ build of the same kernel bodies, injected by the test as a fake backend)."""
 import ctypes
-import io
-import contextlib
 import os
 import re
 import subprocess
@@ -12,8 +10,8 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import GOLD, PORTABLE_ENV, ROOT, check_blocks_against_golden, check_dp_against_golden, stage_e2e
-from oracle import c_oracle, icl_oracle
+from conftest import PORTABLE_ENV, ROOT, check_blocks_against_golden, check_dp_against_golden, stage_e2e
+from oracle import icl_oracle
 
 
 def test_library_exports_every_declared_symbol():

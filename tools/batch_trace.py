@@ -1,7 +1,6 @@
 """Timeline of the pipelined batch (wgdi_b200/batch.py): per job and engine, when each phase started and ended."""
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -47,7 +46,6 @@ def patch_lib(eng):
         return r
     return timed
 runner = BatchRunner(0, depth=int(os.environ.get("DEPTH", "2")), sort_threads=int(os.environ["SORT_THREADS"]) if os.environ.get("SORT_THREADS") else None)
-import wgdi_b200.engine as _e
 _real = runner.engines[0].lib.icl_extract
 class _Lib:
     def __init__(self, lib): self._lib = lib

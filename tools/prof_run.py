@@ -4,7 +4,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 
 from bench import make_points, params_for
 from wgdi_b200.engine import IclEngine

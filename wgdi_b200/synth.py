@@ -16,7 +16,7 @@ gff / lens / m8 / conf files that the unmodified reference can read.
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass, field, replace
+from dataclasses import dataclass, replace
 
 import numpy as np
 
