@@ -250,8 +250,8 @@ def portable_child(args):
         if i >= 2:
             te += time.perf_counter() - t0
     out = {"ms_per_step": 1e3 * t / args.steps, "e2e_ms_per_step": 1e3 * te / args.steps,
-           "hits": len(pts["loc1"]), "numpy_sort_is_scalar": bool(scalar),
-           "rank_on_device": bool(scalar) and eng.rank_mode == "auto", "blocks": len(blocks), "device_ms": eng.timings()}
+           "hits": len(pts["loc1"]), "numpy_sort_is_scalar": bool(scalar), "numpy_sort_kind": eng.numpy_sort_kind(),
+           "rank_on_device": bool(eng.numpy_sort_kind()) and eng.rank_mode == "auto", "blocks": len(blocks), "device_ms": eng.timings()}
     if args.portable_check:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from conftest import oracle_blocks
@@ -517,7 +517,7 @@ def main():
     if rank == 0:
         peak, peak_kind = peaks()
         chain_ms = res_ms["chain"]
-        on_device = getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_is_scalar") and eng.numpy_sort_is_scalar()
+        on_device = getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_kind") and bool(eng.numpy_sort_kind())
         streamed = bool(getattr(eng, "stream_rank", False)) and counters["chain_kernel"] == "ring" and not on_device
         bytes_pp = DP_BYTES_PER_POINT + (EXPORT_BYTES_PER_POINT if streamed else 0)
         achieved = bytes_pp * n_local / (chain_ms * 1e-3) / 1e9
@@ -533,8 +533,8 @@ def main():
                        "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
                        "lanes_per_gpu": args.lanes,
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
-                       "tie_order": ("numpy's scalar argsort (NPY_DISABLE_CPU_FEATURES), reproduced exactly on the device: reference-exact for this numpy"
-                                     if getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_is_scalar") and eng.numpy_sort_is_scalar()
+                       "tie_order": (f"this process's numpy argsort ({eng.numpy_sort_kind()}) reproduced exactly on the device, checked against numpy at start-up: reference-exact"
+                                     if getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_kind") and eng.numpy_sort_kind()
                                      else "numpy argsort on host between the two device phases (reference-exact)")},
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "ms_per_step_cuda_events": 1e3 * ev_e2e / args.steps,

@@ -161,6 +161,11 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
  *   exactly: median of three, Hoare partition, insertion sort up to 16 elements, heap sort at the depth limit.
  *   A caller may use it whenever numpy.argsort in its own process behaves that way (wgdi_b200/engine.py checks this
  *   against the running numpy before choosing it); the result is then bit-identical to the host rank.
+ * ICL_RANK_NUMPY_AVX512 — the same for numpy builds that dispatch int64 argsort to x86-simd-sort's AVX-512 kernels (hosts
+ *   with AVX-512, e.g. this pool's): bitonic key-index networks up to 256 elements, 8-sample pivot, 4 x 8-lane unrolled
+ *   compress-store partition, libstdc++ std::sort when the iteration budget runs out — all reproduced exactly.  The one
+ *   branch that is not (std::sort's heap sort at its depth limit) makes the call fail with ICL_ERR_STATE: rank that
+ *   comparison on the host instead.
  * ICL_RANK_STABLE — NON-REFERENCE: a stable sort, i.e. what pandas' nargsort(ascending=False) would return if numpy's
  *   argsort were stable (reverse, stable ascending argsort, reverse): identical to the reference wherever scores are
  *   distinct, but tied scores come in reversed (loc1, loc2) order, so blocks with tied top scores can come out in a
@@ -168,6 +173,7 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
  */
 #define ICL_RANK_STABLE 0
 #define ICL_RANK_NUMPY_SCALAR 1
+#define ICL_RANK_NUMPY_AVX512 2
 int icl_rank_device(icl_ctx *ctx, int32_t mode);
 
 /*

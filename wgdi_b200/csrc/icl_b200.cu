@@ -79,6 +79,7 @@ struct icl_ctx {
     Buf<int2> pd;                    // per point: {pred (-1 for path roots), path length}
     Buf<uint8_t> used;
     Buf<int32_t> score32, npscr;     // npscr: stop lists of the numpy-scalar argsort kernel
+    Buf<int32_t> host_flag;          // AVX-512 argsort kernel: segments that must be ranked on the host
     // extraction
     Buf<int32_t> order_in, rank2v, acc_L, members, times, mscr;
     Buf<uint32_t> tree_v, acc_m, acc_ms, acc_flag, blkidx, moff;
@@ -2127,6 +2128,352 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// numpy's AVX-512 argsort, reproduced exactly on the device.
+//
+// On CPUs with AVX-512 numpy.argsort(kind='quicksort') on int64 is x86-simd-sort's `avx512_argsort` (this pool's hosts).
+// The algorithm (restated from the library's source as I know it and checked step by step against numpy 2.3.5 on such a
+// host — tools/xss_emulation.py: 8-lane network, 16, 32..256 elements, pivot + partition, std::sort fallback, real DP
+// score arrays — before any CUDA was written):
+//   argsort_(left, right, iters = 2 * floor(log2 n)):
+//     iters <= 0            -> std::sort of the index range with the comparator arr[a] < arr[b] (libstdc++ introsort)
+//     at most 256 elements  -> key-index bitonic network over 8-lane registers (padding key = max, padding index = 0):
+//                              every stage pairs a position with a partner, keeps min or max, and the index follows the
+//                              rule  new_index = own if new_key == own_key else partner's
+//     else pivot = 5th smallest of the 8 keys at left + k * ((right - left) / 8), k = 1..8; partition (below);
+//          recurse left if pivot != smallest key seen, right if pivot != largest key seen, both with iters - 1.
+//   partition (4 x 8 lanes unrolled; `right` exclusive): the first (right - left) % 32 elements one by one
+//   (key >= pivot: swap with --right, else ++left); the first and the last 32 elements are set aside; then groups of
+//   32 are taken from the right if fewer elements have been stored on the right than on the left, else from the left;
+//   of every 8-lane vector the keys < pivot are compress-stored at l_store, the keys >= pivot below r_store + 8; the two
+//   groups set aside go last (left one first).
+// Every step is a function of the keys alone, so a warp can do the 32 lanes of a group, or the positions of a network
+// stage, at once without changing the result.  The std::sort fallback — DP score arrays always have one: the mass of
+// never-updated points holds two or three distinct keys and a pivot equal to the smallest makes no progress — is
+// replayed by one lane (median of three to the front, unguarded Hoare partition, right part first, 16-element
+// threshold, final insertion sort); its heap-sort branch (depth limit) has never been observed and hands the segment
+// back to the host (flag), as does anything else this kernel does not cover.
+// ------------------------------------------------------------------------------------------------
+#ifndef ICL_EMU
+struct XsArgs {
+    const int32_t *key;        // [2n] segments back to back: the REVERSED score arrays
+    int32_t *idx;              // [2n] out: argsort of every segment (segment-local indices)
+    const int64_t *off;        // [P + 1]
+    const int32_t *order;      // item order (longest first)
+    int32_t *host_flag;        // [2P] set to 1 when a segment must be re-sorted by numpy on the host
+    int32_t *scr;              // [4n] scratch: stop lists of the std::sort partitions
+    int64_t n;
+    int32_t P, smem_cap;
+};
+
+// The key-index network is a bitonic sort with flip merges over P = 8 * numVecs slots: for S = 2, 4, .., P: compare
+// slot i with S - 1 - i inside every group of S (min to the lower slot), then for m = S/4, S/8, .., 1 compare i with
+// i + m (bit m of i clear).  One thread per pair; the index follows its key, and on equal keys nothing moves.
+__device__ __forceinline__ void xs_pair(int32_t *nk, int32_t *na, int i, int j) {
+    const int32_t ki = nk[i], kj = nk[j];
+    if (kj < ki) {                                           // strictly out of order: swap key and index
+        const int32_t ai = na[i], aj = na[j];
+        nk[i] = kj; nk[j] = ki;
+        na[i] = aj; na[j] = ai;
+    }
+}
+
+template <class IdxT>
+__device__ void xs_network(const int32_t *v, IdxT *x, int32_t left, int32_t n, int32_t *nk, int32_t *na, int lane) {
+    int P = 256;
+    while (P > 8 && n * 2 <= P) P >>= 1;
+    for (int i = lane; i < P; i += 32) {
+        if (i < n) { const int32_t a = (int32_t)x[left + i]; na[i] = a; nk[i] = v[a]; }
+        else { na[i] = 0; nk[i] = 0x7fffffff; }
+    }
+    __syncwarp();
+    const int half = P >> 1;
+    for (int S = 2; S <= P; S <<= 1) {
+        for (int t = lane; t < half; t += 32) {              // flip stage: (G*S + k, G*S + S-1-k), k < S/2
+            const int hs = S >> 1, G = t / hs, k = t - G * hs;
+            xs_pair(nk, na, G * S + k, G * S + S - 1 - k);
+        }
+        __syncwarp();
+        for (int m = S >> 2; m >= 1; m >>= 1) {
+            for (int t = lane; t < half; t += 32) {          // xor stage: insert a zero bit at log2(m)
+                const int i = ((t & ~(m - 1)) << 1) | (t & (m - 1));
+                xs_pair(nk, na, i, i | m);
+            }
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < n; i += 32) x[left + i] = (IdxT)na[i];
+    __syncwarp();
+}
+
+// ---- libstdc++ std::sort(x + first, x + last, [v](a, b) { return v[a] < v[b]; }), the fallback of argsort_ ----
+// __introsort_loop on [f, l) with the given depth budget by ONE lane (sub-ranges of at most ICL_XS_LANE elements),
+// followed by the part of __final_insertion_sort that concerns this sub-range: the loop leaves pieces of at most 16
+// elements that are ordered among each other, and the final insertion sort never moves an element across a piece
+// boundary (it stops at the first element that is not greater), so it is an insertion sort of every piece — here of
+// the whole sub-range, which is the same.  Returns false at the depth limit (heap sort: not reproduced).
+#define ICL_XS_LANE 96
+template <class IdxT>
+__device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int depth) {
+    const int32_t first = f, last = l;
+    int32_t sf[12], sl[12];
+    int sd[12], sp = 0;
+    for (;;) {
+        while (l - f > 16) {
+            if (depth == 0) return false;
+            --depth;
+            const int32_t mid = f + ((l - f) >> 1), a = f + 1, b = mid, c = l - 1;
+            const int32_t ka = v[x[a]], kb = v[x[b]], kc = v[x[c]];
+            int32_t r;
+            if (ka < kb) { if (kb < kc) r = b; else if (ka < kc) r = c; else r = a; }
+            else if (ka < kc) r = a;
+            else if (kb < kc) r = c;
+            else r = b;
+            IdxT t = x[f]; x[f] = x[r]; x[r] = t;
+            const int32_t pv = v[x[f]];
+            int32_t i = f + 1, j = l;
+            for (;;) {
+                while (v[x[i]] < pv) ++i;
+                --j;
+                while (pv < v[x[j]]) --j;
+                if (!(i < j)) break;
+                t = x[i]; x[i] = x[j]; x[j] = t;
+                ++i;
+            }
+            sf[sp] = f; sl[sp] = i; sd[sp] = depth; sp++;     // left part later, right part now (order is free)
+            f = i;
+        }
+        if (sp == 0) break;
+        sp--;
+        f = sf[sp]; l = sl[sp]; depth = sd[sp];
+    }
+    for (int32_t i = first + 1; i < last; ++i) {              // insertion sort (stable) of the sub-range
+        const IdxT val = x[i];
+        const int32_t kv = v[val];
+        int32_t q = i;
+        while (q > first && kv < v[x[q - 1]]) { x[q] = x[q - 1]; --q; }
+        x[q] = val;
+    }
+    return true;
+}
+
+template <class IdxT>
+__global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
+    __shared__ int32_t nk[256], na[256];
+    __shared__ int32_t st_lo[96], st_hi[96], st_it[96];      // st_it >= 0: argsort_ range with that budget; < 0: std::sort
+                                                              // range [lo, hi) with depth budget -st_it - 1
+    __shared__ int32_t sm_lo[32], sm_hi[32], sm_d[32];
+    const int lane = threadIdx.x;
+    const uint32_t FULL = 0xffffffffu;
+    const int32_t it = A.order[blockIdx.x];
+    const int32_t p = it >= A.P ? it - A.P : it;
+    const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
+    const int32_t len = (int32_t)(A.off[p + 1] - A.off[p]);
+    if (len <= 0) return;
+    extern __shared__ int32_t xs_sm[];
+    const bool fits = sizeof(IdxT) == 2 || len <= A.smem_cap;
+    const int32_t *v = A.key + base;
+    IdxT *x;
+    if (fits) {
+        int32_t *vs = xs_sm;
+        IdxT *xs = (IdxT *)(xs_sm + A.smem_cap);
+        for (int32_t i = lane; i < len; i += 32) { vs[i] = v[i]; xs[i] = (IdxT)i; }
+        v = vs;
+        x = xs;
+    } else {
+        x = (IdxT *)(A.idx + base);
+        for (int32_t i = lane; i < len; i += 32) x[i] = (IdxT)i;
+    }
+    int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;  // stop lists of the std::sort partitions
+    __syncwarp();
+    int sp = 0, nsmall = 0;
+    bool give_up = false;
+    if (len > 1) {
+        if (lane == 0) { st_lo[0] = 0; st_hi[0] = len - 1; st_it[0] = 2 * (31 - __clz((unsigned)len)); }
+        sp = 1;
+    }
+    __syncwarp();
+    auto flush_small = [&]() {                                // std::sort sub-ranges, one per lane
+        __syncwarp();
+        int ok = 1;
+        if (lane < nsmall) ok = xs_std_seq(v, x, sm_lo[lane], sm_hi[lane], sm_d[lane]) ? 1 : 0;
+        if (__any_sync(FULL, !ok)) give_up = true;
+        nsmall = 0;
+        __syncwarp();
+    };
+    while (sp > 0 && !give_up) {
+        sp--;
+        int32_t left = st_lo[sp], right = st_hi[sp];
+        const int32_t iters = st_it[sp];
+        __syncwarp();
+        if (iters < 0) {
+            // ------------------------------------------------ std::sort range [f, l), depth budget -iters - 1
+            int32_t f = left, l = right;
+            int depth = -iters - 1;
+            while (l - f > ICL_XS_LANE) {
+                if (depth == 0) { give_up = true; break; }
+                --depth;
+                int32_t pv = 0;
+                if (lane == 0) {                             // __move_median_to_first(f, f + 1, mid, l - 1)
+                    const int32_t mid = f + ((l - f) >> 1), a = f + 1, b = mid, c = l - 1;
+                    const int32_t ka = v[x[a]], kb = v[x[b]], kc = v[x[c]];
+                    int32_t r;
+                    if (ka < kb) { if (kb < kc) r = b; else if (ka < kc) r = c; else r = a; }
+                    else if (ka < kc) r = a;
+                    else if (kb < kc) r = c;
+                    else r = b;
+                    const IdxT t = x[f]; x[f] = x[r]; x[r] = t;
+                    pv = v[x[f]];
+                }
+                pv = __shfl_sync(FULL, pv, 0);
+                __syncwarp();
+                // __unguarded_partition(f + 1, l, pivot at f): left stops = positions in [f + 1, l) with key >= pivot
+                // (ascending), right stops = positions in [f + 1, l) with key <= pivot (taken back to front); pairs are
+                // swapped while the left stop lies left of the right stop; the scan ends at the next left stop or at the
+                // slot the last swap filled, whichever comes first
+                int32_t *Ls = Lbase + f, *Rs = Rbase + f;
+                int32_t nL = 0, nR = 0;
+                for (int32_t b0 = f + 1; b0 < l; b0 += 32) {
+                    const int32_t q = b0 + lane;
+                    const int32_t kq = q < l ? v[x[q]] : 0;
+                    const bool fl = q < l && !(kq < pv), fr = q < l && !(pv < kq);
+                    const uint32_t ml = __ballot_sync(FULL, fl), mr = __ballot_sync(FULL, fr);
+                    const uint32_t below = (1u << lane) - 1u;
+                    if (fl) Ls[nL + __popc(ml & below)] = q;
+                    if (fr) Rs[nR + __popc(mr & below)] = q;
+                    nL += __popc(ml);
+                    nR += __popc(mr);
+                }
+                __syncwarp();
+                const int32_t kmax2 = nL < nR ? nL : nR;
+                int32_t K = 0;
+                for (int32_t b0 = 0; b0 < kmax2; b0 += 32) {
+                    const int32_t k = b0 + lane;
+                    const bool g = k < kmax2 && Ls[k] < Rs[nR - 1 - k];
+                    const uint32_t m = __ballot_sync(FULL, g);
+                    K += __popc(m);
+                    if (m != FULL) break;
+                }
+                for (int32_t k = lane; k < K; k += 32) {
+                    const int32_t a = Ls[k], b = Rs[nR - 1 - k];
+                    const IdxT t = x[a]; x[a] = x[b]; x[b] = t;
+                }
+                __syncwarp();
+                // the final left scan: next untouched left stop, or the slot the last swap filled; without either, l
+                int32_t cut = K < nL ? Ls[K] : l;
+                if (K >= 1 && Rs[nR - K] < cut) cut = Rs[nR - K];
+                // right part [cut, l) onto the stack, go on with [f, cut)
+                if (lane == 0) { st_lo[sp] = cut; st_hi[sp] = l; st_it[sp] = -depth - 1; }
+                sp++;
+                l = cut;
+                __syncwarp();
+            }
+            if (!give_up && l - f > 1) {
+                if (lane == 0) { sm_lo[nsmall] = f; sm_hi[nsmall] = l; sm_d[nsmall] = depth; }
+                nsmall++;
+                if (nsmall == 32) flush_small();
+            }
+            continue;
+        }
+        if (iters == 0) {                                     // argsort_ out of budget: std::sort of the range
+            const int32_t cnt = right + 1 - left;
+            if (lane == 0) { st_lo[sp] = left; st_hi[sp] = right + 1; st_it[sp] = -(2 * (31 - __clz((unsigned)cnt))) - 1; }
+            sp++;
+            __syncwarp();
+            continue;
+        }
+        if (right + 1 - left <= 256) {
+            xs_network(v, x, left, right + 1 - left, nk, na, lane);
+            continue;
+        }
+        // ---- pivot: 5th smallest of 8 samples
+        int32_t pivot;
+        {
+            const int32_t size = (right - left) >> 3;
+            const int32_t mine = lane < 8 ? v[x[left + (lane + 1) * size]] : 0;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int32_t o = __shfl_sync(FULL, mine, j);
+                rank += (o < mine) || (o == mine && j < lane);
+            }
+            const uint32_t who = __ballot_sync(FULL, lane < 8 && rank == 4);
+            pivot = __shfl_sync(FULL, mine, __ffs(who) - 1);
+        }
+        // ---- partition [left, rend)
+        const int32_t range_left = left, range_right = right;
+        int32_t rend = right + 1;
+        int32_t kmin = 0x7fffffff, kmax = (int32_t)0x80000000;
+        {
+            int32_t pre = (rend - left) & 31;
+            if (lane == 0) {
+                for (; pre > 0; --pre) {
+                    const int32_t kv = v[x[left]];
+                    kmin = kv < kmin ? kv : kmin;
+                    kmax = kv > kmax ? kv : kmax;
+                    if (!(kv < pivot)) { --rend; const IdxT t = x[left]; x[left] = x[rend]; x[rend] = t; }
+                    else ++left;
+                }
+            }
+            left = __shfl_sync(FULL, left, 0);
+            rend = __shfl_sync(FULL, rend, 0);
+            __syncwarp();
+        }
+        int32_t l_store = left;
+        if (left != rend) {
+            const int32_t aL = (int32_t)x[left + lane], kL = v[aL];
+            const int32_t aR = (int32_t)x[rend - 32 + lane], kR = v[aR];
+            int32_t r_store = rend - 8;
+            int32_t lo = left + 32, hi = rend - 32;
+            const int vec = lane >> 3, l8 = lane & 7;
+            const uint32_t below8 = (1u << l8) - 1u;
+            auto put = [&](int32_t a, int32_t kv) {          // one group of 4 vectors, vector by vector
+                const uint32_t m = __ballot_sync(FULL, kv >= pivot);
+                int32_t ls = l_store, rs = r_store;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    if (j < vec) { const int ge = __popc((m >> (8 * j)) & 0xffu); ls += 8 - ge; rs -= ge; }
+                }
+                const uint32_t m8 = (m >> (8 * vec)) & 0xffu;
+                const int ge = __popc(m8);
+                const int32_t dst = (kv >= pivot) ? rs + 8 - ge + __popc(m8 & below8) : ls + __popc(~m8 & below8);
+                __syncwarp();
+                x[dst] = (IdxT)a;
+                const int tot = __popc(m);
+                l_store += 32 - tot;
+                r_store -= tot;
+                kmin = kv < kmin ? kv : kmin;
+                kmax = kv > kmax ? kv : kmax;
+                __syncwarp();
+            };
+            while (hi != lo) {
+                int32_t b0;
+                if ((r_store + 8) - hi < lo - l_store) { hi -= 32; b0 = hi; }
+                else { b0 = lo; lo += 32; }
+                const int32_t a = (int32_t)x[b0 + lane];
+                put(a, v[a]);
+            }
+            put(aL, kL);
+            put(aR, kR);
+        }
+        kmin = __reduce_min_sync(FULL, kmin);
+        kmax = __reduce_max_sync(FULL, kmax);
+        const int32_t pi = l_store;
+        // both sides with iters - 1 (order is free)
+        if (pivot != kmax) { if (lane == 0) { st_lo[sp] = pi; st_hi[sp] = range_right; st_it[sp] = iters - 1; } sp++; }
+        if (pivot != kmin) { if (lane == 0) { st_lo[sp] = range_left; st_hi[sp] = pi - 1; st_it[sp] = iters - 1; } sp++; }
+        __syncwarp();
+    }
+    if (nsmall && !give_up) flush_small();
+    if (give_up) { if (lane == 0) A.host_flag[it] = 1; }
+    if (fits) {
+        __syncwarp();
+        int32_t *out = A.idx + base;
+        for (int32_t i = lane; i < len; i += 32) out[i] = (int32_t)x[i];
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // ABI: icl_rank_device — NON-REFERENCE tie order.  The extraction order of every (pair, direction) item from a
 // STABLE device sort: what pandas' nargsort(ascending=False) would return if numpy's argsort were stable (reverse,
 // stable ascending argsort, reverse).  Identical to the reference wherever scores are distinct; tied scores come
@@ -2135,7 +2482,8 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
 extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     if (!c) return ICL_ERR_ARG;
     if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_rank_device: icl_dp has not succeeded");
-    if (mode != ICL_RANK_STABLE && mode != ICL_RANK_NUMPY_SCALAR) return fail(c, ICL_ERR_ARG, "icl_rank_device: unknown mode");
+    if (mode != ICL_RANK_STABLE && mode != ICL_RANK_NUMPY_SCALAR && mode != ICL_RANK_NUMPY_AVX512)
+        return fail(c, ICL_ERR_ARG, "icl_rank_device: unknown mode");
     Status &st = c->st;
     st.code = 0;
 #ifndef ICL_EMU
@@ -2148,7 +2496,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     if (c->order_in.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V))
         return st.code;
-    if (n > 0 && mode == ICL_RANK_NUMPY_SCALAR) {
+    if (n > 0 && mode != ICL_RANK_STABLE) {
         // the REVERSED score array of every (pair, direction) item, as in the score export of icl_dp
         if (c->score32.reserve(st, V) || c->npscr.reserve(st, 2 * V)) return st.code;
         const int32_t *S = c->S.p, *mmap = c->mmap.p, *ps = c->pair_s.p;
@@ -2163,16 +2511,36 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
 #ifndef ICL_EMU
         int64_t longest = 0;
         for (int32_t q = 0; q < P; q++) longest = std::max<int64_t>(longest, c->h_pair_off[q + 1] - c->h_pair_off[q]);
-        if (longest <= 16000) {                                  // 16-bit indices: 6 B per element, everything on chip
-            const int32_t cap = (int32_t)((longest + 31) & ~31ll);
+        const bool narrow = longest <= 16000;                    // 16-bit indices: 6 B per element, everything on chip
+        const int32_t cap = narrow ? (int32_t)((longest + 31) & ~31ll) : (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);
+        const size_t smem = (size_t)cap * (narrow ? 6 : 8);
+        if (mode == ICL_RANK_NUMPY_SCALAR) {
             NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
-            ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            k_np_argsort<uint16_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, (size_t)cap * 6, s>>>(A);
+            if (narrow) {
+                ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                k_np_argsort<uint16_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, smem, s>>>(A);
+            } else {
+                ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                k_np_argsort<int32_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, smem, s>>>(A);
+            }
         } else {
-            const int32_t cap = (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);      // 96 KB at most
-            NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
-            ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            k_np_argsort<int32_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, (size_t)cap * 8, s>>>(A);
+            if (c->host_flag.reserve(st, 2 * (size_t)P + 1)) return st.code;
+            ICL_CUDA(st, dev_memset(c->host_flag.p, 0, (2 * (size_t)P + 1) * sizeof(int32_t), s));
+            XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, cap};
+            if (narrow) {
+                ICL_CUDA(st, cudaFuncSetAttribute(k_xss_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                k_xss_argsort<uint16_t><<<(unsigned)(2 * P), 32, smem, s>>>(A);
+            } else {
+                ICL_CUDA(st, cudaFuncSetAttribute(k_xss_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                k_xss_argsort<int32_t><<<(unsigned)(2 * P), 32, smem, s>>>(A);
+            }
+            ICL_CUDA(st, cudaGetLastError());
+            // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
+            std::vector<int32_t> hf(2 * (size_t)P);
+            ICL_CUDA(st, d2h(hf.data(), c->host_flag.p, hf.size() * sizeof(int32_t), s));
+            ICL_CUDA(st, dev_sync(s));
+            for (int32_t f : hf)
+                if (f) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
         }
         ICL_CUDA(st, cudaGetLastError());
 #else

@@ -26,7 +26,7 @@ try:                                    # numpy's own argsort routine, GIL-free 
 except ImportError:                     # not built: one numpy call per segment instead (same results)
     _npsort = None
 _NPSORT_OK = None
-_NP_SCALAR = {}          # device -> numpy's argsort in this process is the scalar introsort (IclEngine.numpy_sort_is_scalar)
+_NP_KIND = {}            # device -> which device reproduction of numpy's argsort matches this process (IclEngine.numpy_sort_kind)
 
 
 def _npsort_ok():
@@ -145,9 +145,9 @@ class IclEngine:
         self._pool = ThreadPoolExecutor(self.sort_threads) if self.sort_threads > 1 else None
         # overlap the host rank with the DP kernel (icl_dp_begin); ICL_B200_STREAM=0 runs the two one after the other
         self.stream_rank = os.environ.get("ICL_B200_STREAM", "1") != "0"
-        # who ranks: "auto" = the device when it provably gives numpy's own permutation in this process (numpy running its
-        # scalar introsort), else the host; "host" = always numpy on the host; "device" = the device's numpy-scalar sort
-        # regardless (the reference's tie order on machines without SIMD-sort numpy)
+        # who ranks: "auto" = the device when it provably gives numpy's own permutation in this process (numpy's AVX-512
+        # or scalar argsort, checked against the running numpy), else the host; "host" = always numpy on the host;
+        # "numpy_scalar" / "numpy_avx512" = that device reproduction regardless of what numpy does here
         self.rank_mode = os.environ.get("ICL_B200_RANK", "auto")
         self.host_ms = {}
 
@@ -333,14 +333,16 @@ class IclEngine:
         self.host_ms = dict(dp=(t1 - t0) * 1e3, rank=(t2 - t1) * 1e3)
         return both[:n], both[n:]
 
-    def numpy_sort_is_scalar(self):
-        """True when numpy.argsort(kind='quicksort') on int64 in THIS process is numpy's scalar introsort (no SIMD sort
-        dispatched: older CPUs, or NPY_DISABLE_CPU_FEATURES), checked by sorting tie-heavy arrays both with numpy and
-        with the device's exact reproduction of that algorithm (icl_rank_device, ICL_RANK_NUMPY_SCALAR).  Only then may
-        the device rank replace the host rank without changing a single tie."""
-        if _NP_SCALAR.get(self.device) is None:
+    def numpy_sort_kind(self):
+        """Which of the device's exact reproductions of numpy.argsort(kind='quicksort') on int64 matches numpy in THIS
+        process: "numpy_avx512" (x86-simd-sort's AVX-512 kernels, hosts with AVX-512), "numpy_scalar" (numpy's scalar
+        introsort: no SIMD sort dispatched — other CPUs, or NPY_DISABLE_CPU_FEATURES) or None (e.g. the AVX2 kernels:
+        the host ranks).  Checked once per process and device by sorting tie-heavy score arrays both ways; only on a
+        match may the device rank replace the host rank without changing a single tie."""
+        if self.device not in _NP_KIND:
+            kind = None
             rng = np.random.default_rng(20260)
-            sizes = [1, 2, 16, 17, 18, 33, 100, 257, 1000, 4099, 9001]
+            sizes = [1, 2, 16, 17, 18, 33, 100, 257, 300, 1000, 4099, 9001]
             n = sum(sizes)
             pair = np.repeat(np.arange(len(sizes), dtype=np.int32), sizes)
             loc1 = np.concatenate([np.arange(1, m + 1) for m in sizes]).astype(np.int32)
@@ -352,16 +354,26 @@ class IclEngine:
                 kf, kr = probe.dp(ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))
                 keys = np.concatenate([kf, kr])
                 off = np.concatenate([probe.pair_off, probe.pair_off[1:] + n])
-                probe._check(probe.lib.icl_rank_device(probe.ctx, 1))
+                exp = [keys[a:b].astype(np.int64).argsort(kind="quicksort") for a, b in zip(off[:-1], off[1:])]
                 got = np.zeros(2 * n, np.int32)
-                probe._check(probe.lib.icl_debug_order(probe.ctx, got.ctypes.data))
-                _NP_SCALAR[self.device] = all((got[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all()
-                                              for a, b in zip(off[:-1], off[1:]))
+                for name, mode in (("numpy_avx512", 2), ("numpy_scalar", 1)):
+                    try:
+                        probe._check(probe.lib.icl_rank_device(probe.ctx, mode))
+                        probe._check(probe.lib.icl_debug_order(probe.ctx, got.ctypes.data))
+                    except IclError:
+                        continue
+                    if all((got[a:b] == e).all() for a, b, e in zip(off[:-1], off[1:], exp)):
+                        kind = name
+                        break
             except IclError:
-                _NP_SCALAR[self.device] = False            # e.g. a backend without the kernel: the host ranks
+                kind = None                                    # e.g. a backend without the kernels: the host ranks
             finally:
                 probe.close()
-        return _NP_SCALAR[self.device]
+            _NP_KIND[self.device] = kind
+        return _NP_KIND[self.device]
+
+    def numpy_sort_is_scalar(self):
+        return self.numpy_sort_kind() == "numpy_scalar"
 
     def run_resident_device_rank(self, params: ChainParams, min_members: int = 1, copy: bool = True,
                                  mode: str = "stable") -> Blocks:
@@ -374,7 +386,15 @@ class IclEngine:
         self._check(self.lib.icl_dp(self.ctx, C.byref(prm), None, None))
         self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
         self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
-        self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1}[mode]))
+        try:
+            self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1, "numpy_avx512": 2}[mode]))
+        except IclError as e:
+            if e.code != -3 or mode == "stable":
+                raise
+            # a segment the device does not cover (std::sort's heap-sort branch): numpy itself ranks this comparison
+            kf, kr = self.dp(params)
+            af, ar = self.rank(kf, kr)
+            return self.extract(af, ar, min_members, copy)
         out = icl_blocks()
         self._check(self.lib.icl_extract(self.ctx, None, None, int(min_members), C.byref(out)))
         res = self._blocks_from(out, copy)
@@ -385,8 +405,12 @@ class IclEngine:
         """Hot path on points already uploaded: sort + DP -> rank -> extraction + p values.  The rank is numpy's own
         argsort on the host, except when numpy in this process runs its scalar introsort (no SIMD sort dispatched): the
         device reproduces that algorithm exactly, so it ranks there and the host is out of the step (`rank_mode`)."""
-        if self.rank_mode == "device" or (self.rank_mode == "auto" and self.numpy_sort_is_scalar()):
-            return self.run_resident_device_rank(params, min_members, copy, mode="numpy_scalar")
+        if self.rank_mode == "auto":
+            kind = self.numpy_sort_kind()
+            if kind:
+                return self.run_resident_device_rank(params, min_members, copy, mode=kind)
+        elif self.rank_mode in ("numpy_scalar", "numpy_avx512"):
+            return self.run_resident_device_rank(params, min_members, copy, mode=self.rank_mode)
         if self.stream_rank and _npsort_ok():
             af, ar = self.dp_rank_streamed(params)
             t2 = time.perf_counter()
