@@ -510,6 +510,50 @@ def test_device_numpy_scalar_argsort_is_numpys():
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+def test_device_numpy_avx512_argsort_is_numpys(gpu_engine):
+    """icl_rank_device(ICL_RANK_NUMPY_AVX512) against numpy in this process, where numpy sorts int64 with its AVX-512
+    kernels: every segment's argsort identical (all sizes 1..600, real score arrays, one 40 000-element segment on the
+    global-memory path), and the blocks identical to the host-ranked path."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    if gpu_engine.numpy_sort_kind() != "numpy_avx512":
+        pytest.skip("numpy in this process does not use its AVX-512 argsort")
+    rng = np.random.default_rng(8)
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    sizes = list(range(1, 601, 5))
+    cases = [dict(pair_id=np.repeat(np.arange(len(sizes), dtype=np.int32), sizes),
+                  loc1=np.concatenate([np.arange(1, m + 1) for m in sizes]).astype(np.int32),
+                  loc2=rng.integers(1, 40, sum(sizes)).astype(np.int32),
+                  grading=rng.choice(np.array([50, 30, 25], np.int32), sum(sizes)), n_pairs=len(sizes)),
+             synth.graded_points(synth.make_dataset("small")),
+             synth.graded_points(synth.make_dataset("C2", scale=0.15))]
+    n = 40000
+    cases.append(dict(pair_id=np.zeros(n, np.int32), loc1=np.repeat(np.arange(1, n // 4 + 1), 4).astype(np.int32),
+                      loc2=rng.integers(1, 3000, n).astype(np.int32), grading=rng.choice(np.array([50, 30, 25], np.int32), n), n_pairs=1))
+    eng = IclEngine(0)
+    try:
+        for pts in cases:
+            eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+            kf, kr = eng.dp(prm)
+            m = eng.n
+            keys = np.concatenate([kf, kr])
+            off = np.concatenate([eng.pair_off, eng.pair_off[1:] + m])
+            eng._check(eng.lib.icl_rank_device(eng.ctx, 2))
+            got = np.zeros(2 * m, np.int32)
+            eng._check(eng.lib.icl_debug_order(eng.ctx, got.ctypes.data))
+            for a, b in zip(off[:-1], off[1:]):
+                assert (got[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all(), (a, b)
+            b1 = eng.run_resident_device_rank(prm, mode="numpy_avx512")
+            eng.rank_mode = "host"
+            b2 = eng.run_resident(prm)
+            eng.rank_mode = "auto"
+            assert len(b1) == len(b2)
+            for f in ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
+                assert (getattr(b1, f) == getattr(b2, f)).all(), f
+    finally:
+        eng.close()
+
+
 def test_alternative_dp_kernels_agree(clouds):
     """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth

@@ -402,3 +402,13 @@ def test_device_rank_mode_emu(emu_backend):
         assert got.pair[b] == pair and got.dir[b] == d and got.score[b] == sc and got.p_raw[b] == a
         assert (got.loc1[a0:a1] == l1).all() and (got.loc2[a0:a1] == l2).all()
     assert sorted(got.score.tolist()) == sorted(ref.score.tolist()) or len(got) != len(ref)   # tie order may differ, nothing else
+
+
+def test_avx512_argsort_specification_matches_numpy():
+    """tools/xss_emulation.py — the plain-Python statement of numpy's AVX-512 argsort that the CUDA kernel follows —
+    against numpy itself, where numpy sorts that way (AVX-512 hosts); elsewhere there is nothing to compare with."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import xss_emulation
+    if not xss_emulation.is_avx512_numpy():
+        pytest.skip("numpy on this machine does not dispatch int64 argsort to its AVX-512 kernels")
+    assert xss_emulation.self_check(cases=120, seed=7, verbose=False) == 0
