@@ -440,6 +440,32 @@ def main():
             step_resident()
         dp_only_ms = float(np.mean(dev_ms["chain"]))
         eng.stream_rank = True
+    # ---- the same steps with numpy itself ranking on the host (what every step did before the device reproduced numpy's
+    # argsort, and what still happens where numpy sorts in a way the device does not know): for comparison
+    host_ranked = None
+    if getattr(eng, "rank_mode", None) == "auto" and hasattr(eng, "numpy_sort_kind") and eng.numpy_sort_kind():
+        keep = {k: list(v) for k, v in dev_ms.items()}
+        try:
+            eng.rank_mode = "host"
+            for _ in range(2):
+                step_resident()
+            t_h, ev_h, _ = timed(step_resident)
+            host_rank_ms = float(np.mean(dev_ms["host_rank"][-args.steps:]))
+            if world > 1:
+                th = torch.tensor([t_h], dtype=torch.float64, device="cuda")
+                dist.all_reduce(th, op=dist.ReduceOp.MAX)
+                t_h = float(th.item())
+            host_ranked = {"value": total_points * args.steps / t_h, "unit": "hits/s", "ms_per_step": 1e3 * t_h / args.steps,
+                           "host_rank_ms": host_rank_ms, "sort_threads": sort_threads,
+                           "what": "rank by numpy on the host between the two device phases (streamed), same result"}
+        except Exception as e:                              # noqa: BLE001 — a comparison leg must not take the run down
+            if world > 1:
+                raise
+            host_ranked = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            eng.rank_mode = "auto"
+            dev_ms.clear()
+            dev_ms.update(keep)
     # ---- NON-REFERENCE option, reported next to the headline and never instead of it: extraction order from a stable
     # device sort (icl_rank_device) instead of numpy's unstable argsort on the host.  Same algorithm, same blocks wherever
     # top scores are distinct, but not the reference's tie order; it shows the device-bound rate of the path.
@@ -555,7 +581,7 @@ def main():
                              "frac": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9 / peak,
                              "what": "same kernel with the streamed export off (ICL_B200_STREAM=0), 3 extra untimed passes"},
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
-            "phase_ms": res_ms, "batch": batch, "device_rank_option": device_rank, "portable_numpy": portable,
+            "phase_ms": res_ms, "batch": batch, "host_ranked": host_ranked, "device_rank_option": device_rank, "portable_numpy": portable,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }
