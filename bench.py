@@ -566,6 +566,7 @@ def main():
                     "ms_per_step_cuda_events": 1e3 * ev_e2e / args.steps,
                     "h2d_bytes_per_step": 16 * n_local + 8 * n_local, "d2h_bytes_per_step": d2h},
             "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
+            "host_rank_fallbacks": int(getattr(eng, "host_rank_fallbacks", 0)),
             "roofline": {"kernel": "k_chain_ring: chain DP, both directions" + (" + streamed score export" if streamed else ""),
                          "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,

@@ -153,7 +153,7 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
 
 /*
  * Rank every (pair, direction) item on the device instead of on the host, then call icl_extract with both argsort
- * pointers NULL.  icl_dp may then be called with both key pointers NULL (no score export).  Two modes:
+ * pointers NULL.  icl_dp may then be called with both key pointers NULL (no score export).  Modes:
  *
  * ICL_RANK_NUMPY_SCALAR — the reference's tie order on every numpy that sorts int64 with its scalar introsort
  *   (npysort/quicksort.cpp `aquicksort_`: CPUs without AVX2 / AVX-512 sort dispatch, or NPY_DISABLE_CPU_FEATURES —
@@ -166,6 +166,10 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
  *   compress-store partition, libstdc++ std::sort when the iteration budget runs out — all reproduced exactly.  The one
  *   branch that is not (std::sort's heap sort at its depth limit) makes the call fail with ICL_ERR_STATE: rank that
  *   comparison on the host instead.
+ * ICL_RANK_NUMPY_AVX2 — the same for numpy builds / hosts where int64 argsort goes to x86-simd-sort's AVX2 kernels (x86 CPUs
+ *   without AVX-512): the same algorithm on 4-lane vectors — groups of 16 in the partition, pivot = 3rd smallest of 4
+ *   samples — and, because AVX2 has no compress-store (a permute and a full-width store take its place), the keys >=
+ *   pivot of every vector stored in reversed lane order.
  * ICL_RANK_STABLE — NON-REFERENCE: a stable sort, i.e. what pandas' nargsort(ascending=False) would return if numpy's
  *   argsort were stable (reverse, stable ascending argsort, reverse): identical to the reference wherever scores are
  *   distinct, but tied scores come in reversed (loc1, loc2) order, so blocks with tied top scores can come out in a
@@ -174,6 +178,7 @@ int icl_layout(icl_ctx *ctx, int64_t *pair_off, int32_t *perm);
 #define ICL_RANK_STABLE 0
 #define ICL_RANK_NUMPY_SCALAR 1
 #define ICL_RANK_NUMPY_AVX512 2
+#define ICL_RANK_NUMPY_AVX2 3
 int icl_rank_device(icl_ctx *ctx, int32_t mode);
 
 /*

@@ -465,6 +465,8 @@ sys.path.insert(0, %r)
 from wgdi_b200 import synth
 from wgdi_b200._lib import icl_params
 from wgdi_b200.engine import ChainParams, IclEngine
+KIND = sys.argv[1]
+MODE = {"numpy_scalar": 1, "numpy_avx512": 2, "numpy_avx2": 3}[KIND]
 def check(pts, prm):
     eng = IclEngine(0)
     try:
@@ -473,18 +475,20 @@ def check(pts, prm):
         n = eng.n
         keys = np.concatenate([kf, kr])
         off = np.concatenate([eng.pair_off, eng.pair_off[1:] + n])
-        eng._check(eng.lib.icl_rank_device(eng.ctx, 1))       # numpy's scalar argsort, on the device
+        eng._check(eng.lib.icl_rank_device(eng.ctx, MODE))    # numpy's argsort of this flavour, on the device
         got = np.zeros(2 * n, np.int32)
         eng._check(eng.lib.icl_debug_order(eng.ctx, got.ctypes.data))
         bad = 0
         for a, b in zip(off[:-1], off[1:]):
             exp = keys[a:b].astype(np.int64).argsort(kind="quicksort")      # numpy in THIS process: SIMD sorts disabled
             bad += not (got[a:b] == exp).all()
-        b1 = eng.run_resident_device_rank(prm, mode="numpy_scalar")
+        b1 = eng.run_resident_device_rank(prm, mode=KIND)
+        assert eng.host_rank_fallbacks == 0
+        eng.rank_mode = "host"
         b2 = eng.run_resident(prm)                            # host rank with the same numpy
         same = len(b1) == len(b2) and all((getattr(b1, f) == getattr(b2, f)).all() for f in
                                           ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx"))
-        return len(off) - 1, bad, same, eng.numpy_sort_is_scalar()
+        return len(off) - 1, bad, same, eng.numpy_sort_kind() == KIND
     finally:
         eng.close()
 rng = np.random.default_rng(3)
@@ -496,6 +500,11 @@ n = 40000
 l1 = np.repeat(np.arange(1, n // 4 + 1), 4).astype(np.int32); l2 = rng.integers(1, 3000, n).astype(np.int32)
 out.append(check(dict(pair_id=np.zeros(n, np.int32), loc1=l1, loc2=l2, grading=rng.choice(np.array([50, 30, 25], np.int32), n), n_pairs=1),
                  ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))))
+iso = np.arange(1, 901, dtype=np.int32) * 1000                  # isolated points: constant / sorted / reversed key segments
+out.append(check(dict(pair_id=np.repeat(np.arange(3, dtype=np.int32), 300), loc1=iso, loc2=rng.permutation(iso).astype(np.int32),
+                      grading=np.concatenate([np.full(300, 50), np.sort(rng.choice([25, 30, 50], 300)),
+                                              np.sort(rng.choice([25, 30, 50], 300))[::-1]]).astype(np.int32), n_pairs=3),
+                 ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))))
 print("RESULT", out)
 assert all(bad == 0 and same and scalar for _, bad, same, scalar in out), out
 print("OK")
@@ -506,7 +515,24 @@ def test_device_numpy_scalar_argsort_is_numpys():
     """icl_rank_device(ICL_RANK_NUMPY_SCALAR) against numpy itself in a process whose numpy runs its scalar introsort
     (NPY_DISABLE_CPU_FEATURES): every segment's argsort identical, and the blocks identical to the host-ranked path."""
     env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
-    r = subprocess.run([sys.executable, "-c", _NPSCALAR_CHILD % ROOT], env=env, capture_output=True, text=True)
+    r = subprocess.run([sys.executable, "-c", _NPSCALAR_CHILD % ROOT, "numpy_scalar"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+AVX2_ENV = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX512_KNL AVX512_KNM"
+
+
+def test_device_numpy_avx2_argsort_is_numpys():
+    """icl_rank_device(ICL_RANK_NUMPY_AVX2) against numpy itself in a process whose numpy dispatches int64 argsort to its
+    AVX2 kernels (every AVX512* feature disabled): every segment's argsort identical, the engine's start-up probe picks
+    that flavour, and the blocks are identical to the host-ranked path."""
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=AVX2_ENV)
+    probe = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import xss_emulation as x; "
+                            "print('AVX2' if x.is_avx2_numpy() else 'OTHER')" % os.path.join(ROOT, "tools")],
+                           env=env, capture_output=True, text=True)
+    if "AVX2" not in probe.stdout:
+        pytest.skip("numpy on this machine has no AVX2 argsort to compare with")
+    r = subprocess.run([sys.executable, "-c", _NPSCALAR_CHILD % ROOT, "numpy_avx2"], env=env, capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
@@ -530,6 +556,12 @@ def test_device_numpy_avx512_argsort_is_numpys(gpu_engine):
     n = 40000
     cases.append(dict(pair_id=np.zeros(n, np.int32), loc1=np.repeat(np.arange(1, n // 4 + 1), 4).astype(np.int32),
                       loc2=rng.integers(1, 3000, n).astype(np.int32), grading=rng.choice(np.array([50, 30, 25], np.int32), n), n_pairs=1))
+    # isolated points: every score equals the grading -> constant and sorted key segments (numpy's SIMD argsort leaves
+    # an already sorted array untouched; a partition pass whose pivot is the smallest key moves everything)
+    iso = np.arange(1, 901, dtype=np.int32) * 1000
+    cases.append(dict(pair_id=np.repeat(np.arange(3, dtype=np.int32), 300), loc1=iso, loc2=rng.permutation(iso).astype(np.int32),
+                      grading=np.concatenate([np.full(300, 50), np.sort(rng.choice([25, 30, 50], 300)),
+                                              np.sort(rng.choice([25, 30, 50], 300))[::-1]]).astype(np.int32), n_pairs=3))
     eng = IclEngine(0)
     try:
         for pts in cases:
@@ -544,6 +576,7 @@ def test_device_numpy_avx512_argsort_is_numpys(gpu_engine):
             for a, b in zip(off[:-1], off[1:]):
                 assert (got[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all(), (a, b)
             b1 = eng.run_resident_device_rank(prm, mode="numpy_avx512")
+            assert eng.host_rank_fallbacks == 0
             eng.rank_mode = "host"
             b2 = eng.run_resident(prm)
             eng.rank_mode = "auto"

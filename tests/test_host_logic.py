@@ -412,3 +412,26 @@ def test_avx512_argsort_specification_matches_numpy():
     if not xss_emulation.is_avx512_numpy():
         pytest.skip("numpy on this machine does not dispatch int64 argsort to its AVX-512 kernels")
     assert xss_emulation.self_check(cases=120, seed=7, verbose=False) == 0
+
+
+def test_no_progress_passes_in_closed_form():
+    """The closed-form permutation of a partition pass that moves everything to one side (and runs of such passes) —
+    what the CUDA kernel applies instead of replaying them — against the sequential specification."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import xss_emulation
+    assert xss_emulation.check_fast_forward(cases=24)
+
+
+def test_avx2_argsort_specification_matches_numpy():
+    """The 4-lane flavour of the same specification against numpy in a child process with every AVX512* feature
+    disabled (numpy then dispatches int64 argsort to its AVX2 kernels, where the CPU has AVX2)."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import xss_emulation as x\n"
+            "if not x.is_avx2_numpy(): print('SKIP'); raise SystemExit(0)\n"
+            "print('BAD', x.self_check(cases=120, seed=7, verbose=False, fn=x.avx2_argsort))" % os.path.join(ROOT, "tools"))
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES="AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX512_KNL AVX512_KNM")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if "SKIP" in r.stdout:
+        pytest.skip("numpy on this machine has no AVX2 argsort to compare with")
+    assert "BAD 0" in r.stdout, r.stdout

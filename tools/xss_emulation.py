@@ -1,12 +1,17 @@
-"""numpy's AVX-512 argsort (x86-simd-sort `avx512_argsort` + libstdc++ std::sort fallback), restated in plain Python.
+"""numpy's AVX-512 and AVX2 argsort (x86-simd-sort `avx512_argsort` / `avx2_argsort` + libstdc++ std::sort fallback),
+restated in plain Python.
 
 This is the specification the CUDA kernel `k_xss_argsort` (wgdi_b200/csrc/icl_b200.cu) follows; it was written from
 the library's algorithm and checked step by step against numpy 2.3.5 on an AVX-512 host:
 
     python tools/xss_emulation.py          # compares with numpy.argsort(kind='quicksort') on this machine
 
-The comparison only means something where numpy dispatches int64 argsort to its AVX-512 kernels (`is_avx512_numpy`).
+The comparison only means something where numpy dispatches int64 argsort to its AVX-512 kernels (`is_avx512_numpy`) or,
+for the 4-lane flavour, to its AVX2 kernels (`is_avx2_numpy`; on an AVX-512 host: NPY_DISABLE_CPU_FEATURES with every
+AVX512* feature).
 
+  keys already in non-decreasing order: the identity (found by experiment: numpy returns arange(n) for every such array,
+  and only at the top level — a sorted sub-range is still permuted by its partitions)
   argsort_(left, right, iters = 2 * floor(log2 n))
     iters <= 0          std::sort(arg + left, arg + right + 1, arr[a] < arr[b])          (libstdc++ introsort)
     <= 256 elements     key-index bitonic network over 8-lane registers: padding key = max, padding index = 0;
@@ -14,6 +19,11 @@ The comparison only means something where numpy dispatches int64 argsort to its 
     else                pivot = 5th smallest of arr[arg[left + k * ((right - left) // 8)]], k = 1..8
                         partition_unrolled (4 vectors of 8 lanes), then left part if pivot != smallest key seen,
                         right part if pivot != largest key seen, both with iters - 1
+
+AVX2 (`lanes=4`): the same on 4-lane vectors — 4 samples at left + k * ((right - left) // 4), pivot = the 3rd smallest;
+groups of 4 x 4 = 16 elements in the partition — with one difference that shows in the tie order: AVX2 has no
+compress-store, the library permutes the vector (keys < pivot first, keys >= pivot last) and stores it whole at both
+ends, and its permutation table puts the keys >= pivot in REVERSED lane order.
 """
 import math
 import sys
@@ -45,9 +55,9 @@ def network(keys, idx):
         S *= 2
 
 
-def argsort_n(arr, arg, left, n):
+def argsort_n(arr, arg, left, n, lanes=8):
     N = 256
-    while N > 8 and n * 2 <= N:
+    while N > lanes and n * 2 <= N:
         N //= 2
     keys = [arr[arg[left + i]] if i < n else MAX for i in range(N)]
     idx = [arg[left + i] if i < n else 0 for i in range(N)]
@@ -55,15 +65,16 @@ def argsort_n(arr, arg, left, n):
     arg[left:left + n] = idx[:n]
 
 
-def get_pivot(arr, arg, left, right):
-    size = (right - left) // 8
-    return sorted(arr[arg[left + (j + 1) * size]] for j in range(8))[4]
+def get_pivot(arr, arg, left, right, lanes=8):
+    size = (right - left) // lanes
+    return sorted(arr[arg[left + (j + 1) * size]] for j in range(lanes))[lanes // 2]
 
 
-def partition_unrolled(arr, arg, left, right, pivot, unroll=4):
+def partition_unrolled(arr, arg, left, right, pivot, unroll=4, lanes=8):
     """`right` exclusive; returns (pivot index, smallest key, largest key)."""
+    W = lanes
     smallest, biggest = MAX, -MAX - 1
-    for _ in range((right - left) % (unroll * 8)):
+    for _ in range((right - left) % (unroll * W)):
         v = arr[arg[left]]
         smallest, biggest = min(smallest, v), max(biggest, v)
         if not v < pivot:
@@ -73,28 +84,28 @@ def partition_unrolled(arr, arg, left, right, pivot, unroll=4):
             left += 1
     if left == right:
         return left, smallest, biggest
-    state = [left, right - 8, smallest, biggest]          # l_store, r_store, min, max
+    state = [left, right - W, smallest, biggest]          # l_store, r_store, min, max
 
     def store(vec):
         keys = [arr[a] for a in vec]
         ge = [a for a, k in zip(vec, keys) if k >= pivot]
         lt = [a for a, k in zip(vec, keys) if not k >= pivot]
         arg[state[0]:state[0] + len(lt)] = lt
-        arg[state[1] + 8 - len(ge):state[1] + 8] = ge
+        arg[state[1] + W - len(ge):state[1] + W] = ge[::-1] if W == 4 else ge
         state[0] += len(lt)
         state[1] -= len(ge)
         state[2], state[3] = min(state[2], min(keys)), max(state[3], max(keys))
-    vec_left = [list(arg[left + 8 * i:left + 8 * i + 8]) for i in range(unroll)]
-    vec_right = [list(arg[right - 8 * (unroll - i):right - 8 * (unroll - i) + 8]) for i in range(unroll)]
-    left += unroll * 8
-    right -= unroll * 8
+    vec_left = [list(arg[left + W * i:left + W * i + W]) for i in range(unroll)]
+    vec_right = [list(arg[right - W * (unroll - i):right - W * (unroll - i) + W]) for i in range(unroll)]
+    left += unroll * W
+    right -= unroll * W
     while right != left:
-        if (state[1] + 8) - right < left - state[0]:
-            right -= unroll * 8
-            cur = [list(arg[right + 8 * i:right + 8 * i + 8]) for i in range(unroll)]
+        if (state[1] + W) - right < left - state[0]:
+            right -= unroll * W
+            cur = [list(arg[right + W * i:right + W * i + W]) for i in range(unroll)]
         else:
-            cur = [list(arg[left + 8 * i:left + 8 * i + 8]) for i in range(unroll)]
-            left += unroll * 8
+            cur = [list(arg[left + W * i:left + W * i + W]) for i in range(unroll)]
+            left += unroll * W
         for vec in cur:
             store(vec)
     for vec in vec_left + vec_right:
@@ -162,58 +173,199 @@ def std_sort(arr, arg, first, last):
         insertion_sort(first, last)
 
 
-def argsort_(arr, arg, left, right, iters):
+def argsort_(arr, arg, left, right, iters, lanes=8):
     if iters <= 0:
         std_sort(arr, arg, left, right + 1)
         return
     if right + 1 - left <= 256:
-        argsort_n(arr, arg, left, right + 1 - left)
+        argsort_n(arr, arg, left, right + 1 - left, lanes)
         return
-    pivot = get_pivot(arr, arg, left, right)
-    pi, smallest, biggest = partition_unrolled(arr, arg, left, right + 1, pivot)
+    pivot = get_pivot(arr, arg, left, right, lanes)
+    pi, smallest, biggest = partition_unrolled(arr, arg, left, right + 1, pivot, lanes=lanes)
     if pivot != smallest:
-        argsort_(arr, arg, left, pi - 1, iters - 1)
+        argsort_(arr, arg, left, pi - 1, iters - 1, lanes)
     if pivot != biggest:
-        argsort_(arr, arg, pi, right, iters - 1)
+        argsort_(arr, arg, pi, right, iters - 1, lanes)
 
 
-def avx512_argsort(x):
+def avx512_argsort(x, lanes=8):
     arr = [int(k) for k in x]
     arg = list(range(len(arr)))
-    if len(arr) > 1:
-        argsort_(arr, arg, 0, len(arr) - 1, 2 * int(math.log2(len(arr))))
+    if len(arr) > 1 and not all(a <= b for a, b in zip(arr, arr[1:])):   # already sorted (ties included): untouched
+        argsort_(arr, arg, 0, len(arr) - 1, 2 * int(math.log2(len(arr))), lanes)
     return arg
 
 
-def is_avx512_numpy():
-    """numpy.argsort on this machine behaves like the emulation on a few tie-heavy arrays."""
+def avx2_argsort(x):
+    return avx512_argsort(x, lanes=4)
+
+
+# ---- passes without progress, in closed form (what the CUDA kernel does instead of replaying them) -------------------
+# pivot == smallest key of the range: every element goes to the "right" side, the pass is a fixed permutation of the
+# positions [left, R) and argsort_ comes back to the same range with iters - 1.
+
+def pass_forward(q, left, R, W):
+    """Position after one such pass of the element at position q."""
+    G = 4 * W
+    pre = (R - left) % G
+    rend = R - pre
+    if pre:
+        if q == left:
+            q = R - 1
+        elif q >= rend:
+            q = left if q == rend else q - 1
+    if q >= rend:
+        return q
+    M = (rend - left) // G
+    g, r = divmod(q - left, G)
+    j, t = divmod(r, W)
+    k = g if M == 2 else 0 if g == 1 else M - 2 if g == 0 else M - 1 if g == M - 1 else M - 1 - g
+    return rend - k * G - (j + 1) * W + (t if W == 8 else W - 1 - t)
+
+
+def pass_inverse(d, left, R, W):
+    """Position before the pass of the element now at d."""
+    G = 4 * W
+    pre = (R - left) % G
+    rend = R - pre
+    if d >= rend:
+        return left if d == R - 1 else d + 1
+    M = (rend - left) // G
+    k, r = divmod(rend - 1 - d, G)
+    j, s = r // W, W - 1 - r % W
+    t = s if W == 8 else W - 1 - s
+    g = k if M == 2 else 1 if k == 0 else 0 if k == M - 2 else M - 1 if k == M - 1 else M - 1 - k
+    q = left + g * G + j * W + t
+    return rend if pre and q == left else q
+
+
+def argsort_ff(arr, arg, left, right, iters, lanes=8):
+    """argsort_ with runs of no-progress passes applied at once: the sample positions are followed backwards through
+    the permutation to get each pass's pivot, the run ends when the pivot moves, the budget runs out or all keys are equal."""
+    if iters <= 0:
+        std_sort(arr, arg, left, right + 1)
+        return
+    if right + 1 - left <= 256:
+        argsort_n(arr, arg, left, right + 1 - left, lanes)
+        return
+    W, R = lanes, right + 1
+    size = (right - left) // W
+    q = [left + (j + 1) * size for j in range(W)]
+    keys = sorted(arr[arg[p]] for p in q)
+    pivot = keys[W // 2]
+    if keys[0] == pivot:
+        lo_k = min(arr[arg[i]] for i in range(left, R))
+        hi_k = max(arr[arg[i]] for i in range(left, R))
+        if pivot == lo_k:
+            t = 0
+            while True:
+                t += 1
+                if pivot == hi_k:
+                    state = "all equal"
+                    break
+                if iters - t == 0:
+                    state = "out of budget"
+                    break
+                q = [pass_inverse(p, left, R, W) for p in q]
+                pivot = sorted(arr[arg[p]] for p in q)[W // 2]
+                if pivot != lo_k:
+                    state = "progress"
+                    break
+            old = arg[left:R]
+            for i in range(left, R):
+                d = i
+                for _ in range(t):
+                    d = pass_forward(d, left, R, W)
+                arg[d] = old[i - left]
+            iters -= t
+            if state == "all equal":
+                return
+            if state == "out of budget":
+                std_sort(arr, arg, left, R)
+                return
+    pi, smallest, biggest = partition_unrolled(arr, arg, left, R, pivot, lanes=W)
+    if pivot != smallest:
+        argsort_ff(arr, arg, left, pi - 1, iters - 1, lanes)
+    if pivot != biggest:
+        argsort_ff(arr, arg, pi, right, iters - 1, lanes)
+
+
+def check_fast_forward(cases=60, seed=3):
+    """The closed forms against the sequential partition, and argsort_ff against argsort_ (no numpy involved)."""
+    rng = np.random.default_rng(seed)
+    for W in (8, 4):
+        for n in list(range(8 * W, 8 * W + 70)) + [257, 300, 1000, 1023, 1024, 1025, 3333]:
+            left = int(rng.integers(0, 50))
+            R = left + n
+            arr = [5] * (R + 2000)
+            arg = list(range(1000, 1000 + R))
+            old = arg[:]
+            assert partition_unrolled(arr, arg, left, R, 5, lanes=W)[0] == left
+            for p in range(left, R):
+                d = pass_forward(p, left, R, W)
+                assert arg[d] == old[p] and pass_inverse(d, left, R, W) == p, (W, n, p)
+        for c in range(cases):
+            n = int(rng.integers(257, 4000))
+            x = rng.choice([25, 30, 50], n, p=[.8, .15, .05] if c % 2 else [.5, .3, .2])
+            m = rng.random(n) < (0.1 if c % 2 else 0.3)
+            x[m] += rng.integers(20, 2000, int(m.sum()))
+            if c % 5 == 0:
+                x = rng.integers(0, int(rng.choice([1, 2, 3])) + 1, n)
+            arr = [int(k) for k in x]
+            a, b = list(range(n)), list(range(n))
+            it = 2 * int(math.log2(n))
+            argsort_(arr, a, 0, n - 1, it, W)
+            argsort_ff(arr, b, 0, n - 1, it, W)
+            assert a == b, (W, c, n)
+    return True
+
+
+def _numpy_is(fn):
     rng = np.random.default_rng(99)
-    for n in (5, 16, 100, 300, 700):
+    for n in (5, 16, 100, 300, 700, 1500):
         x = rng.integers(0, 4, n).astype(np.int64)
-        if np.argsort(x, kind="quicksort").tolist() != avx512_argsort(x):
+        if np.argsort(x, kind="quicksort").tolist() != fn(x):
             return False
     return True
 
 
-def self_check(cases=400, seed=0, verbose=True):
+def is_avx2_numpy():
+    """numpy.argsort on this machine (in this environment) behaves like the 4-lane emulation on a few tie-heavy arrays."""
+    return _numpy_is(avx2_argsort)
+
+
+def is_avx512_numpy():
+    """numpy.argsort on this machine behaves like the emulation on a few tie-heavy arrays."""
+    return _numpy_is(avx512_argsort)
+
+
+def self_check(cases=400, seed=0, verbose=True, fn=None):
+    fn = fn or avx512_argsort
     rng = np.random.default_rng(seed)
     bad = 0
     for t in range(cases):
         n = int(rng.integers(1, 3000)) if t % 3 else int(rng.integers(1, 300))
         nv = int(rng.choice([2, 3, 5, 40, 3000]))
         x = rng.integers(0, nv, n).astype(np.int64)
+        if t % 7 == 3:                                   # constant / sorted with ties / sorted but for one element
+            x = np.sort(x) if t % 2 else np.full(n, 7, np.int64)
+            if t % 4 == 1 and n > 2:
+                x[n // 2] = x[0] - 1
         if t % 5 == 0:                                   # like DP scores: a mass of 25 / 30 / 50 plus a tail
             x = rng.choice([25, 30, 50], n, p=[.5, .3, .2]).astype(np.int64)
             m = rng.random(n) < 0.3
             x[m] += rng.integers(20, 2000, int(m.sum()))
-        bad += np.argsort(x, kind="quicksort").tolist() != avx512_argsort(x)
+        bad += np.argsort(x, kind="quicksort").tolist() != fn(x)
     if verbose:
         print(f"{cases} arrays, {bad} differ from numpy.argsort(kind='quicksort')")
     return bad
 
 
 if __name__ == "__main__":
-    if not is_avx512_numpy():
-        print("numpy on this machine does not sort int64 with its AVX-512 kernels: nothing to compare")
-        sys.exit(0)
-    sys.exit(1 if self_check() else 0)
+    if is_avx512_numpy():
+        sys.exit(1 if self_check() else 0)
+    if is_avx2_numpy():
+        print("numpy sorts int64 with its AVX2 kernels here")
+        sys.exit(1 if self_check(fn=avx2_argsort) else 0)
+    print("numpy on this machine sorts int64 with neither its AVX-512 nor its AVX2 kernels: nothing to compare")
+    sys.exit(0)

@@ -2163,6 +2163,7 @@ struct XsArgs {
     int32_t *scr;              // [4n] scratch: stop lists of the std::sort partitions
     int64_t n;
     int32_t P, smem_cap;
+    int32_t W;                 // lanes of the emulated vector: 8 = AVX-512, 4 = AVX2
 };
 
 // The key-index network is a bitonic sort with flip merges over P = 8 * numVecs slots: for S = 2, 4, .., P: compare
@@ -2256,14 +2257,73 @@ __device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int 
     return true;
 }
 
-template <class IdxT>
-__global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
-    __shared__ int32_t nk[256], na[256];
-    __shared__ int32_t st_lo[96], st_hi[96], st_it[96];      // st_it >= 0: argsort_ range with that budget; < 0: std::sort
-                                                              // range [lo, hi) with depth budget -st_it - 1
-    __shared__ int32_t sm_lo[32], sm_hi[32], sm_d[32];
-    const int lane = threadIdx.x;
+#define ICL_XS_WARPS_DEFAULT 8
+#define ICL_XS_STACK 256
+
+// A partition pass whose pivot equals the smallest key of its range moves every element to the "right" side: nothing
+// is decided by the keys, the pass is a fixed permutation of the positions [left, R) and the recursion comes back to the
+// same range with one iteration less.  DP score arrays spend most of their budget this way (the never-updated points
+// are a mass of equal smallest keys), so the permutation is written in closed form and a run of t such passes is applied
+// at once.  One pass: the first pre = (R - left) mod G elements rotate through position `left` to the end of the
+// range; of the M groups of G that remain, group 1 is stored first, then M-2, M-3, .., 2, then the two groups set aside
+// (0 and M-1); the k-th stored group fills [rend - (k+1)G, rend - kG) from the top, vector by vector (AVX2: lanes
+// reversed).  Checked against the sequential partition in tools/xss_emulation.py (`check_fast_forward`).
+struct XsPerm {
+    int32_t left, R, rend, M, pre;
+    int W, wsh;
+};
+__device__ __forceinline__ int32_t xs_fwd(const XsPerm &P, int32_t q) {          // where the element at q goes
+    if (P.pre) {
+        if (q == P.left) q = P.R - 1;
+        else if (q >= P.rend) q = (q == P.rend) ? P.left : q - 1;
+    }
+    if (q >= P.rend) return q;
+    const int32_t e = q - P.left;
+    const int32_t g = e >> (P.wsh + 2), r = e & (4 * P.W - 1);
+    const int32_t j = r >> P.wsh, t = r & (P.W - 1);
+    int32_t k;
+    if (P.M == 2) k = g;
+    else if (g == 1) k = 0;
+    else if (g == 0) k = P.M - 2;
+    else if (g == P.M - 1) k = P.M - 1;
+    else k = P.M - 1 - g;
+    const int32_t sl = P.W == 8 ? t : P.W - 1 - t;
+    return P.rend - k * 4 * P.W - (j + 1) * P.W + sl;
+}
+__device__ __forceinline__ int32_t xs_inv(const XsPerm &P, int32_t d) {          // where the element at d came from
+    if (d >= P.rend) return d == P.R - 1 ? P.left : d + 1;
+    const int32_t u = P.rend - 1 - d;
+    const int32_t k = u >> (P.wsh + 2), r = u & (4 * P.W - 1);
+    const int32_t j = r >> P.wsh, sl = P.W - 1 - (r & (P.W - 1));
+    const int32_t t = P.W == 8 ? sl : P.W - 1 - sl;
+    int32_t g;
+    if (P.M == 2) g = k;
+    else if (k == 0) g = 1;
+    else if (k == P.M - 2) g = 0;
+    else if (k == P.M - 1) g = P.M - 1;
+    else g = P.M - 1 - k;
+    int32_t q = P.left + g * 4 * P.W + j * P.W + t;
+    if (P.pre && q == P.left) q = P.rend;
+    return q;
+}
+// One CTA of NW warps per segment; the warps take ranges from a shared stack (sub-ranges are disjoint and carry their
+// own budgets, so the order is free), each with its own network scratch and its own list of small std::sort
+// sub-ranges.  A.W = lanes of the emulated vector: 8 (AVX-512) or 4 (AVX2: same algorithm on 4-lane vectors, groups of 16,
+// pivot = 3rd smallest of 4 samples, and — its compress-store is a permute + full-width store — the keys >= pivot of a
+// vector land in REVERSED lane order).
+template <class IdxT, int NW>
+__global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
+    __shared__ int32_t nk_all[NW][256], na_all[NW][256];
+    __shared__ int32_t st_lo[ICL_XS_STACK], st_hi[ICL_XS_STACK], st_it[ICL_XS_STACK];   // st_it >= 0: argsort_ range with that
+                                                              // budget; < 0: std::sort range [lo, hi), depth budget -st_it - 1
+    __shared__ int32_t sm_lo_all[NW][32], sm_hi_all[NW][32], sm_d_all[NW][32];
+    __shared__ int32_t s_sp, s_pending, s_lock, s_giveup;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t *nk = nk_all[wid], *na = na_all[wid];
+    int32_t *sm_lo = sm_lo_all[wid], *sm_hi = sm_hi_all[wid], *sm_d = sm_d_all[wid];
     const uint32_t FULL = 0xffffffffu;
+    const int W = A.W, G = 4 * W;                             // lanes per vector, elements per unrolled group
+    const int wsh = W == 8 ? 3 : 2;
     const int32_t it = A.order[blockIdx.x];
     const int32_t p = it >= A.P ? it - A.P : it;
     const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
@@ -2276,41 +2336,94 @@ __global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
     if (fits) {
         int32_t *vs = xs_sm;
         IdxT *xs = (IdxT *)(xs_sm + A.smem_cap);
-        for (int32_t i = lane; i < len; i += 32) { vs[i] = v[i]; xs[i] = (IdxT)i; }
-        v = vs;
-        x = xs;
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) { vs[i] = v[i]; xs[i] = (IdxT)i; }
     } else {
         x = (IdxT *)(A.idx + base);
-        for (int32_t i = lane; i < len; i += 32) x[i] = (IdxT)i;
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) x[i] = (IdxT)i;
     }
-    int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;  // stop lists of the std::sort partitions
-    __syncwarp();
-    int sp = 0, nsmall = 0;
+    // keys already in non-decreasing order: the library leaves the identity (top level only)
+    int uns = 0;
+    for (int32_t i = threadIdx.x; i + 1 < len; i += blockDim.x) uns |= v[i] > v[i + 1];
+    const int unsorted = __syncthreads_or(uns);
+    if (fits) {
+        v = xs_sm;
+        x = (IdxT *)(xs_sm + A.smem_cap);
+    }
+    int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;  // stop lists of the std::sort partitions (slice [f, l) per range)
+    if (threadIdx.x == 0) {
+        st_lo[0] = 0; st_hi[0] = len - 1; st_it[0] = 2 * (31 - __clz((unsigned)len));
+        s_sp = unsorted ? 1 : 0; s_pending = unsorted ? 1 : 0; s_lock = 0; s_giveup = 0;
+    }
+    __syncthreads();
+    volatile int32_t *vsp = &s_sp, *vpend = &s_pending, *vgive = &s_giveup;
+    // lane 0 of a warp only; a lock that cannot be had (never seen) gives the segment up instead of hanging the GPU
+    auto lock = [&]() {
+        if (NW == 1) return;
+        int spins = 0;
+        while (atomicCAS(&s_lock, 0, 1) != 0) {
+            __nanosleep(20);
+            if (++spins > (1 << 24)) { *vgive = 1; break; }
+        }
+        __threadfence_block();
+    };
+    auto unlock = [&]() { if (NW == 1) return; __threadfence_block(); atomicExch(&s_lock, 0); };
+    auto push = [&](int32_t lo_, int32_t hi_, int32_t it_) {   // lane 0 only, after a __syncwarp() behind the warp's last
+        lock();                                                // write to x: the range's elements travel with the entry
+        const int32_t t = *vsp;
+        if (t < ICL_XS_STACK) {
+            st_lo[t] = lo_; st_hi[t] = hi_; st_it[t] = it_;
+            __threadfence_block();
+            *vsp = t + 1;
+            atomicAdd(&s_pending, 1);
+        } else *vgive = 1;                                     // stack full (never seen): the host ranks this segment
+        unlock();
+    };
+    int nsmall = 0;
     bool give_up = false;
-    if (len > 1) {
-        if (lane == 0) { st_lo[0] = 0; st_hi[0] = len - 1; st_it[0] = 2 * (31 - __clz((unsigned)len)); }
-        sp = 1;
-    }
-    __syncwarp();
     auto flush_small = [&]() {                                // std::sort sub-ranges, one per lane
         __syncwarp();
         int ok = 1;
         if (lane < nsmall) ok = xs_std_seq(v, x, sm_lo[lane], sm_hi[lane], sm_d[lane]) ? 1 : 0;
-        if (__any_sync(FULL, !ok)) give_up = true;
+        if (__any_sync(FULL, !ok)) { give_up = true; if (lane == 0) *vgive = 1; }
         nsmall = 0;
         __syncwarp();
     };
-    while (sp > 0 && !give_up) {
-        sp--;
-        int32_t left = st_lo[sp], right = st_hi[sp];
-        const int32_t iters = st_it[sp];
-        __syncwarp();
+    for (;;) {
+        // ---- pop a range (lane 0), or leave when the stack is empty and no warp is still producing; idle warps look at
+        // the stack pointer without taking the lock
+        int32_t left = 0, right = 0, iters = 0, got = 0;
+        if (lane == 0) {
+            for (int spins = 0;; ++spins) {
+                if (*vgive) break;
+                if (spins > (1 << 21)) { *vgive = 1; break; }  // ~1 s without work while work is pending: give up
+                if (*vsp > 0) {
+                    lock();
+                    const int32_t t = *vsp - 1;
+                    if (t >= 0) {
+                        left = st_lo[t]; right = st_hi[t]; iters = st_it[t];
+                        *vsp = t;
+                        got = 1;
+                    }
+                    unlock();
+                    if (got) break;
+                    continue;
+                }
+                if (*vpend == 0) break;
+                __nanosleep(400);
+            }
+        }
+        got = __shfl_sync(FULL, got, 0);
+        if (!got) break;
+        left = __shfl_sync(FULL, left, 0); right = __shfl_sync(FULL, right, 0); iters = __shfl_sync(FULL, iters, 0);
+        __syncwarp();                                         // the other lanes read x behind lane 0's acquire
+        // `done`: this popped range has been dealt with (its pieces are on the stack or in this warp's small list)
+        auto done = [&]() { if (lane == 0) { __threadfence_block(); atomicSub(&s_pending, 1); } };
         if (iters < 0) {
             // ------------------------------------------------ std::sort range [f, l), depth budget -iters - 1
             int32_t f = left, l = right;
             int depth = -iters - 1;
             while (l - f > ICL_XS_LANE) {
-                if (depth == 0) { give_up = true; break; }
+                if (depth == 0) { give_up = true; if (lane == 0) *vgive = 1; break; }
                 --depth;
                 int32_t pv = 0;
                 if (lane == 0) {                             // __move_median_to_first(f, f + 1, mid, l - 1)
@@ -2361,9 +2474,8 @@ __global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
                 // the final left scan: next untouched left stop, or the slot the last swap filled; without either, l
                 int32_t cut = K < nL ? Ls[K] : l;
                 if (K >= 1 && Rs[nR - K] < cut) cut = Rs[nR - K];
-                // right part [cut, l) onto the stack, go on with [f, cut)
-                if (lane == 0) { st_lo[sp] = cut; st_hi[sp] = l; st_it[sp] = -depth - 1; }
-                sp++;
+                // right part [cut, l) onto the stack for any warp, go on with [f, cut)
+                if (lane == 0) push(cut, l, -depth - 1);
                 l = cut;
                 __syncwarp();
             }
@@ -2372,39 +2484,88 @@ __global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
                 nsmall++;
                 if (nsmall == 32) flush_small();
             }
+            done();
+            if (give_up) break;
             continue;
         }
         if (iters == 0) {                                     // argsort_ out of budget: std::sort of the range
             const int32_t cnt = right + 1 - left;
-            if (lane == 0) { st_lo[sp] = left; st_hi[sp] = right + 1; st_it[sp] = -(2 * (31 - __clz((unsigned)cnt))) - 1; }
-            sp++;
+            if (lane == 0) push(left, right + 1, -(2 * (31 - __clz((unsigned)cnt))) - 1);
             __syncwarp();
+            done();
             continue;
         }
         if (right + 1 - left <= 256) {
             xs_network(v, x, left, right + 1 - left, nk, na, lane);
+            done();
             continue;
         }
-        // ---- pivot: 5th smallest of 8 samples
-        int32_t pivot;
-        {
-            const int32_t size = (right - left) >> 3;
-            const int32_t mine = lane < 8 ? v[x[left + (lane + 1) * size]] : 0;
+        // ---- pivot: 5th smallest of 8 samples (AVX-512), 3rd smallest of 4 (AVX2)
+        auto median = [&](int32_t mine) {
             int rank = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int32_t o = __shfl_sync(FULL, mine, j);
-                rank += (o < mine) || (o == mine && j < lane);
+                rank += j < W && ((o < mine) || (o == mine && j < lane));
             }
-            const uint32_t who = __ballot_sync(FULL, lane < 8 && rank == 4);
-            pivot = __shfl_sync(FULL, mine, __ffs(who) - 1);
+            const uint32_t who = __ballot_sync(FULL, lane < W && rank == (W >> 1));
+            return __shfl_sync(FULL, mine, __ffs(who) - 1);
+        };
+        const int32_t ssize = (right - left) >> wsh;
+        const int32_t mine0 = lane < W ? v[x[left + (lane + 1) * ssize]] : 0x7fffffff;
+        int32_t pivot = median(mine0);
+        // ---- passes that cannot make progress (pivot == smallest key of the range), applied at once
+        if (__reduce_min_sync(FULL, mine0) == pivot) {
+            int32_t rmin = 0x7fffffff, rmax = (int32_t)0x80000000;
+            for (int32_t i = left + lane; i <= right; i += 32) {
+                const int32_t kv = v[x[i]];
+                rmin = kv < rmin ? kv : rmin;
+                rmax = kv > rmax ? kv : rmax;
+            }
+            rmin = __reduce_min_sync(FULL, rmin);
+            rmax = __reduce_max_sync(FULL, rmax);
+            if (pivot == rmin) {
+                XsPerm P;
+                P.left = left; P.R = right + 1; P.W = W; P.wsh = wsh;
+                P.pre = (P.R - left) & (G - 1);
+                P.rend = P.R - P.pre;
+                P.M = (P.rend - left) >> (wsh + 2);
+                int32_t q = lane < W ? left + (lane + 1) * ssize : left;
+                int t = 0, state;
+                for (;;) {
+                    ++t;
+                    if (pivot == rmax) { state = 0; break; }              // all keys equal: neither side is visited
+                    if (iters - t == 0) { state = 1; break; }             // out of budget: std::sort of the range
+                    q = xs_inv(P, q);                                     // what sits at the sample positions now
+                    pivot = median(lane < W ? v[x[q]] : 0x7fffffff);
+                    if (pivot != rmin) { state = 2; break; }
+                }
+                int32_t *tmp = Lbase + left;                              // out of place through the scratch slice
+                for (int32_t i = left + lane; i < P.R; i += 32) {
+                    int32_t d = i;
+                    for (int k = 0; k < t; k++) d = xs_fwd(P, d);
+                    tmp[d - left] = (int32_t)x[i];
+                }
+                __syncwarp();
+                for (int32_t i = left + lane; i < P.R; i += 32) x[i] = (IdxT)tmp[i - left];
+                __syncwarp();
+                iters -= t;
+                if (state == 0) { done(); continue; }
+                if (state == 1) {
+                    const int32_t cnt = right + 1 - left;
+                    if (lane == 0) push(left, right + 1, -(2 * (31 - __clz((unsigned)cnt))) - 1);
+                    __syncwarp();
+                    done();
+                    continue;
+                }
+            }
         }
         // ---- partition [left, rend)
         const int32_t range_left = left, range_right = right;
         int32_t rend = right + 1;
         int32_t kmin = 0x7fffffff, kmax = (int32_t)0x80000000;
         {
-            int32_t pre = (rend - left) & 31;
+            int32_t pre = (rend - left) & (G - 1);
             if (lane == 0) {
                 for (; pre > 0; --pre) {
                     const int32_t kv = v[x[left]];
@@ -2420,37 +2581,40 @@ __global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
         }
         int32_t l_store = left;
         if (left != rend) {
-            const int32_t aL = (int32_t)x[left + lane], kL = v[aL];
-            const int32_t aR = (int32_t)x[rend - 32 + lane], kR = v[aR];
-            int32_t r_store = rend - 8;
-            int32_t lo = left + 32, hi = rend - 32;
-            const int vec = lane >> 3, l8 = lane & 7;
-            const uint32_t below8 = (1u << l8) - 1u;
+            const bool act = lane < G;                        // AVX2: 16 lanes carry a group
+            const int32_t aL = act ? (int32_t)x[left + lane] : 0, kL = act ? v[aL] : 0;
+            const int32_t aR = act ? (int32_t)x[rend - G + lane] : 0, kR = act ? v[aR] : 0;
+            int32_t r_store = rend - W;
+            int32_t lo = left + G, hi = rend - G;
+            const int vec = lane >> wsh, lW = lane & (W - 1);
+            const uint32_t maskW = (1u << W) - 1u, belowW = (1u << lW) - 1u;
+            const bool rev = W == 4;
             auto put = [&](int32_t a, int32_t kv) {          // one group of 4 vectors, vector by vector
-                const uint32_t m = __ballot_sync(FULL, kv >= pivot);
-                int32_t ls = l_store, rs = r_store;
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    if (j < vec) { const int ge = __popc((m >> (8 * j)) & 0xffu); ls += 8 - ge; rs -= ge; }
-                }
-                const uint32_t m8 = (m >> (8 * vec)) & 0xffu;
-                const int ge = __popc(m8);
-                const int32_t dst = (kv >= pivot) ? rs + 8 - ge + __popc(m8 & below8) : ls + __popc(~m8 & below8);
+                const bool isge = act && kv >= pivot;
+                const uint32_t m = __ballot_sync(FULL, isge);
+                const int geb = __popc(m & ((1u << (W * vec)) - 1u));   // keys >= pivot in the vectors before mine
+                const int32_t ls = l_store + W * vec - geb, rs = r_store - geb;
+                const uint32_t mv = (m >> (W * vec)) & maskW;
+                const int ge = __popc(mv);
+                const int rk = __popc(mv & belowW);
+                const int32_t dst = isge ? (rev ? rs + W - 1 - rk : rs + W - ge + rk) : ls + __popc(~mv & belowW);
                 __syncwarp();
-                x[dst] = (IdxT)a;
+                if (act) {
+                    x[dst] = (IdxT)a;
+                    kmin = kv < kmin ? kv : kmin;
+                    kmax = kv > kmax ? kv : kmax;
+                }
                 const int tot = __popc(m);
-                l_store += 32 - tot;
+                l_store += G - tot;
                 r_store -= tot;
-                kmin = kv < kmin ? kv : kmin;
-                kmax = kv > kmax ? kv : kmax;
                 __syncwarp();
             };
             while (hi != lo) {
                 int32_t b0;
-                if ((r_store + 8) - hi < lo - l_store) { hi -= 32; b0 = hi; }
-                else { b0 = lo; lo += 32; }
-                const int32_t a = (int32_t)x[b0 + lane];
-                put(a, v[a]);
+                if ((r_store + W) - hi < lo - l_store) { hi -= G; b0 = hi; }
+                else { b0 = lo; lo += G; }
+                const int32_t a = act ? (int32_t)x[b0 + lane] : 0;
+                put(a, act ? v[a] : 0);
             }
             put(aL, kL);
             put(aR, kR);
@@ -2459,16 +2623,39 @@ __global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
         kmax = __reduce_max_sync(FULL, kmax);
         const int32_t pi = l_store;
         // both sides with iters - 1 (order is free)
-        if (pivot != kmax) { if (lane == 0) { st_lo[sp] = pi; st_hi[sp] = range_right; st_it[sp] = iters - 1; } sp++; }
-        if (pivot != kmin) { if (lane == 0) { st_lo[sp] = range_left; st_hi[sp] = pi - 1; st_it[sp] = iters - 1; } sp++; }
+        if (lane == 0) {
+            if (pivot != kmax) push(pi, range_right, iters - 1);
+            if (pivot != kmin) push(range_left, pi - 1, iters - 1);
+        }
         __syncwarp();
+        done();
     }
-    if (nsmall && !give_up) flush_small();
-    if (give_up) { if (lane == 0) A.host_flag[it] = 1; }
+    {
+        const int gv = __shfl_sync(FULL, lane == 0 ? *vgive : 0, 0);
+        if (nsmall && !gv) flush_small();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && *vgive) A.host_flag[it] = 1;
     if (fits) {
-        __syncwarp();
         int32_t *out = A.idx + base;
-        for (int32_t i = lane; i < len; i += 32) out[i] = (int32_t)x[i];
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) out[i] = (int32_t)x[i];
+    }
+}
+
+template <class IdxT, int NW>
+static cudaError_t xss_launch(const XsArgs &A, unsigned grid, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_xss_argsort<IdxT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    k_xss_argsort<IdxT, NW><<<grid, 32 * NW, smem, s>>>(A);
+    return cudaGetLastError();
+}
+template <class IdxT>
+static cudaError_t xss_launch_w(int warps, const XsArgs &A, unsigned grid, size_t smem, cudaStream_t s) {
+    switch (warps) {
+    case 1: return xss_launch<IdxT, 1>(A, grid, smem, s);
+    case 2: return xss_launch<IdxT, 2>(A, grid, smem, s);
+    case 4: return xss_launch<IdxT, 4>(A, grid, smem, s);
+    default: return xss_launch<IdxT, 8>(A, grid, smem, s);
     }
 }
 #endif
@@ -2482,7 +2669,7 @@ __global__ void __launch_bounds__(32) k_xss_argsort(XsArgs A) {
 extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     if (!c) return ICL_ERR_ARG;
     if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_rank_device: icl_dp has not succeeded");
-    if (mode != ICL_RANK_STABLE && mode != ICL_RANK_NUMPY_SCALAR && mode != ICL_RANK_NUMPY_AVX512)
+    if (mode != ICL_RANK_STABLE && mode != ICL_RANK_NUMPY_SCALAR && mode != ICL_RANK_NUMPY_AVX512 && mode != ICL_RANK_NUMPY_AVX2)
         return fail(c, ICL_ERR_ARG, "icl_rank_device: unknown mode");
     Status &st = c->st;
     st.code = 0;
@@ -2526,14 +2713,11 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
         } else {
             if (c->host_flag.reserve(st, 2 * (size_t)P + 1)) return st.code;
             ICL_CUDA(st, dev_memset(c->host_flag.p, 0, (2 * (size_t)P + 1) * sizeof(int32_t), s));
-            XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, cap};
-            if (narrow) {
-                ICL_CUDA(st, cudaFuncSetAttribute(k_xss_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                k_xss_argsort<uint16_t><<<(unsigned)(2 * P), 32, smem, s>>>(A);
-            } else {
-                ICL_CUDA(st, cudaFuncSetAttribute(k_xss_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                k_xss_argsort<int32_t><<<(unsigned)(2 * P), 32, smem, s>>>(A);
-            }
+            XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, cap,
+                     mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8};
+            static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
+            if (narrow) ICL_CUDA(st, xss_launch_w<uint16_t>(xs_warps, A, (unsigned)(2 * P), smem, s));
+            else ICL_CUDA(st, xss_launch_w<int32_t>(xs_warps, A, (unsigned)(2 * P), smem, s));
             ICL_CUDA(st, cudaGetLastError());
             // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
             std::vector<int32_t> hf(2 * (size_t)P);

@@ -5,8 +5,11 @@ two device phases of include/icl_b200.h and, between them, obtains the extractio
 from numpy exactly the way the reference does through pandas
 (`sort_values(by=['score1'], ascending=False)`, wgdi/collinearity.py:49,60 ->
 pandas.core.sorting.nargsort -> numpy.argsort(kind='quicksort')).  That sort is unstable
-and CPU dependent for tied scores (SURVEY.md hazard H1), so it is not re-implemented: the
-very same numpy call is made on the int64 score arrays the device returns.
+and CPU dependent for tied scores (SURVEY.md hazard H1).  The device holds exact
+reproductions of the three algorithms numpy dispatches to on x86 (AVX-512, AVX2, scalar);
+the engine checks them against the running numpy once per process and lets the one that
+matches rank on the device (`numpy_sort_kind`).  When none matches, the very same numpy
+call is made on the host on the int64 score arrays the device returns.
 """
 from __future__ import annotations
 
@@ -145,10 +148,11 @@ class IclEngine:
         self._pool = ThreadPoolExecutor(self.sort_threads) if self.sort_threads > 1 else None
         # overlap the host rank with the DP kernel (icl_dp_begin); ICL_B200_STREAM=0 runs the two one after the other
         self.stream_rank = os.environ.get("ICL_B200_STREAM", "1") != "0"
-        # who ranks: "auto" = the device when it provably gives numpy's own permutation in this process (numpy's AVX-512
-        # or scalar argsort, checked against the running numpy), else the host; "host" = always numpy on the host;
-        # "numpy_scalar" / "numpy_avx512" = that device reproduction regardless of what numpy does here
+        # who ranks: "auto" = the device when it provably gives numpy's own permutation in this process (numpy's AVX-512,
+        # AVX2 or scalar argsort, checked against the running numpy), else the host; "host" = always numpy on the host;
+        # "numpy_scalar" / "numpy_avx512" / "numpy_avx2" = that device reproduction regardless of what numpy does here
         self.rank_mode = os.environ.get("ICL_B200_RANK", "auto")
+        self.host_rank_fallbacks = 0        # comparisons the device rank handed back to numpy (std::sort's heap-sort branch)
         self.host_ms = {}
 
     # ---- plumbing ------------------------------------------------------------------------------
@@ -335,9 +339,9 @@ class IclEngine:
 
     def numpy_sort_kind(self):
         """Which of the device's exact reproductions of numpy.argsort(kind='quicksort') on int64 matches numpy in THIS
-        process: "numpy_avx512" (x86-simd-sort's AVX-512 kernels, hosts with AVX-512), "numpy_scalar" (numpy's scalar
-        introsort: no SIMD sort dispatched — other CPUs, or NPY_DISABLE_CPU_FEATURES) or None (e.g. the AVX2 kernels:
-        the host ranks).  Checked once per process and device by sorting tie-heavy score arrays both ways; only on a
+        process: "numpy_avx512" (x86-simd-sort's AVX-512 kernels, hosts with AVX-512), "numpy_avx2" (its AVX2 kernels: x86
+        hosts without AVX-512), "numpy_scalar" (numpy's scalar introsort: no SIMD sort dispatched — other CPUs, or
+        NPY_DISABLE_CPU_FEATURES) or None (something else, e.g. a future numpy: the host ranks).  Checked once per process and device by sorting tie-heavy score arrays both ways; only on a
         match may the device rank replace the host rank without changing a single tie."""
         if self.device not in _NP_KIND:
             kind = None
@@ -356,7 +360,7 @@ class IclEngine:
                 off = np.concatenate([probe.pair_off, probe.pair_off[1:] + n])
                 exp = [keys[a:b].astype(np.int64).argsort(kind="quicksort") for a, b in zip(off[:-1], off[1:])]
                 got = np.zeros(2 * n, np.int32)
-                for name, mode in (("numpy_avx512", 2), ("numpy_scalar", 1)):
+                for name, mode in (("numpy_avx512", 2), ("numpy_avx2", 3), ("numpy_scalar", 1)):
                     try:
                         probe._check(probe.lib.icl_rank_device(probe.ctx, mode))
                         probe._check(probe.lib.icl_debug_order(probe.ctx, got.ctypes.data))
@@ -387,11 +391,12 @@ class IclEngine:
         self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
         self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
         try:
-            self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1, "numpy_avx512": 2}[mode]))
+            self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1, "numpy_avx512": 2, "numpy_avx2": 3}[mode]))
         except IclError as e:
             if e.code != -3 or mode == "stable":
                 raise
             # a segment the device does not cover (std::sort's heap-sort branch): numpy itself ranks this comparison
+            self.host_rank_fallbacks += 1
             kf, kr = self.dp(params)
             af, ar = self.rank(kf, kr)
             return self.extract(af, ar, min_members, copy)
@@ -409,7 +414,7 @@ class IclEngine:
             kind = self.numpy_sort_kind()
             if kind:
                 return self.run_resident_device_rank(params, min_members, copy, mode=kind)
-        elif self.rank_mode in ("numpy_scalar", "numpy_avx512"):
+        elif self.rank_mode in ("numpy_scalar", "numpy_avx512", "numpy_avx2"):
             return self.run_resident_device_rank(params, min_members, copy, mode=self.rank_mode)
         if self.stream_rank and _npsort_ok():
             af, ar = self.dp_rank_streamed(params)
