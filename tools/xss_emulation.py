@@ -223,6 +223,23 @@ def pass_forward(q, left, R, W):
     return rend - k * G - (j + 1) * W + (t if W == 8 else W - 1 - t)
 
 
+def pass_forward_t(q, t, left, R, W):
+    """Position after t passes: groups 2 .. M-2 stay where they are and only reverse their vectors (AVX2: and lanes), an
+    involution; groups 0, 1, M-1 and the rotated elements move among themselves and are followed pass by pass."""
+    G = 4 * W
+    rend = R - (R - left) % G
+    M = (rend - left) // G
+    g, r = divmod(q - left, G)
+    if q < rend and 2 <= g <= M - 2:
+        if t % 2 == 0:
+            return q
+        j, l = divmod(r, W)
+        return left + g * G + (3 - j) * W + (l if W == 8 else W - 1 - l)
+    for _ in range(t):
+        q = pass_forward(q, left, R, W)
+    return q
+
+
 def pass_inverse(d, left, R, W):
     """Position before the pass of the element now at d."""
     G = 4 * W
@@ -273,10 +290,7 @@ def argsort_ff(arr, arg, left, right, iters, lanes=8):
                     break
             old = arg[left:R]
             for i in range(left, R):
-                d = i
-                for _ in range(t):
-                    d = pass_forward(d, left, R, W)
-                arg[d] = old[i - left]
+                arg[pass_forward_t(i, t, left, R, W)] = old[i - left]
             iters -= t
             if state == "all equal":
                 return
@@ -304,6 +318,11 @@ def check_fast_forward(cases=60, seed=3):
             for p in range(left, R):
                 d = pass_forward(p, left, R, W)
                 assert arg[d] == old[p] and pass_inverse(d, left, R, W) == p, (W, n, p)
+                for t in (2, 3, 7):
+                    e = p
+                    for _ in range(t):
+                        e = pass_forward(e, left, R, W)
+                    assert pass_forward_t(p, t, left, R, W) == e, (W, n, p, t)
         for c in range(cases):
             n = int(rng.integers(257, 4000))
             x = rng.choice([25, 30, 50], n, p=[.8, .15, .05] if c % 2 else [.5, .3, .2])

@@ -2268,10 +2268,12 @@ __device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int 
 // range; of the M groups of G that remain, group 1 is stored first, then M-2, M-3, .., 2, then the two groups set aside
 // (0 and M-1); the k-th stored group fills [rend - (k+1)G, rend - kG) from the top, vector by vector (AVX2: lanes
 // reversed).  Checked against the sequential partition in tools/xss_emulation.py (`check_fast_forward`).
+// Groups 2 .. M-2 keep their place and only reverse their vectors (and lanes, AVX2): on them the pass is an involution;
+// groups 0, 1, M-1 and the rotated elements move among themselves.
 struct XsPerm {
     int32_t left, R, rend, M, pre;
-    int W, wsh;
 };
+template <int W>
 __device__ __forceinline__ int32_t xs_fwd(const XsPerm &P, int32_t q) {          // where the element at q goes
     if (P.pre) {
         if (q == P.left) q = P.R - 1;
@@ -2279,30 +2281,47 @@ __device__ __forceinline__ int32_t xs_fwd(const XsPerm &P, int32_t q) {         
     }
     if (q >= P.rend) return q;
     const int32_t e = q - P.left;
-    const int32_t g = e >> (P.wsh + 2), r = e & (4 * P.W - 1);
-    const int32_t j = r >> P.wsh, t = r & (P.W - 1);
+    constexpr int wsh = W == 8 ? 3 : 2;
+    const int32_t g = e >> (wsh + 2), r = e & (4 * W - 1);
+    const int32_t j = r >> wsh, t = r & (W - 1);
     int32_t k;
     if (P.M == 2) k = g;
     else if (g == 1) k = 0;
     else if (g == 0) k = P.M - 2;
     else if (g == P.M - 1) k = P.M - 1;
     else k = P.M - 1 - g;
-    const int32_t sl = P.W == 8 ? t : P.W - 1 - t;
-    return P.rend - k * 4 * P.W - (j + 1) * P.W + sl;
+    const int32_t sl = W == 8 ? t : W - 1 - t;
+    return P.rend - k * 4 * W - (j + 1) * W + sl;
 }
+template <int W>
+__device__ __forceinline__ int32_t xs_fwd_t(const XsPerm &P, int32_t q, int t) {  // after t passes
+    constexpr int wsh = W == 8 ? 3 : 2;
+    const int32_t e = q - P.left;
+    const int32_t g = e >> (wsh + 2);
+    if (q < P.rend && g >= 2 && g <= P.M - 2) {
+        if (!(t & 1)) return q;
+        const int32_t r = e & (4 * W - 1);
+        const int32_t j = r >> wsh, l = r & (W - 1);
+        return P.left + g * 4 * W + (3 - j) * W + (W == 8 ? l : W - 1 - l);
+    }
+    for (int k = 0; k < t; k++) q = xs_fwd<W>(P, q);
+    return q;
+}
+template <int W>
 __device__ __forceinline__ int32_t xs_inv(const XsPerm &P, int32_t d) {          // where the element at d came from
+    constexpr int wsh = W == 8 ? 3 : 2;
     if (d >= P.rend) return d == P.R - 1 ? P.left : d + 1;
     const int32_t u = P.rend - 1 - d;
-    const int32_t k = u >> (P.wsh + 2), r = u & (4 * P.W - 1);
-    const int32_t j = r >> P.wsh, sl = P.W - 1 - (r & (P.W - 1));
-    const int32_t t = P.W == 8 ? sl : P.W - 1 - sl;
+    const int32_t k = u >> (wsh + 2), r = u & (4 * W - 1);
+    const int32_t j = r >> wsh, sl = W - 1 - (r & (W - 1));
+    const int32_t t = W == 8 ? sl : W - 1 - sl;
     int32_t g;
     if (P.M == 2) g = k;
     else if (k == 0) g = 1;
     else if (k == P.M - 2) g = 0;
     else if (k == P.M - 1) g = P.M - 1;
     else g = P.M - 1 - k;
-    int32_t q = P.left + g * 4 * P.W + j * P.W + t;
+    int32_t q = P.left + g * 4 * W + j * W + t;
     if (P.pre && q == P.left) q = P.rend;
     return q;
 }
@@ -2311,7 +2330,7 @@ __device__ __forceinline__ int32_t xs_inv(const XsPerm &P, int32_t d) {         
 // sub-ranges.  A.W = lanes of the emulated vector: 8 (AVX-512) or 4 (AVX2: same algorithm on 4-lane vectors, groups of 16,
 // pivot = 3rd smallest of 4 samples, and — its compress-store is a permute + full-width store — the keys >= pivot of a
 // vector land in REVERSED lane order).
-template <class IdxT, int NW>
+template <class IdxT, int NW, int W>
 __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     __shared__ int32_t nk_all[NW][256], na_all[NW][256];
     __shared__ int32_t st_lo[ICL_XS_STACK], st_hi[ICL_XS_STACK], st_it[ICL_XS_STACK];   // st_it >= 0: argsort_ range with that
@@ -2322,8 +2341,8 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     int32_t *nk = nk_all[wid], *na = na_all[wid];
     int32_t *sm_lo = sm_lo_all[wid], *sm_hi = sm_hi_all[wid], *sm_d = sm_d_all[wid];
     const uint32_t FULL = 0xffffffffu;
-    const int W = A.W, G = 4 * W;                             // lanes per vector, elements per unrolled group
-    const int wsh = W == 8 ? 3 : 2;
+    constexpr int G = 4 * W;                                  // W lanes per vector, G elements per unrolled group
+    constexpr int wsh = W == 8 ? 3 : 2;
     const int32_t it = A.order[blockIdx.x];
     const int32_t p = it >= A.P ? it - A.P : it;
     const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
@@ -2526,7 +2545,7 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
             rmax = __reduce_max_sync(FULL, rmax);
             if (pivot == rmin) {
                 XsPerm P;
-                P.left = left; P.R = right + 1; P.W = W; P.wsh = wsh;
+                P.left = left; P.R = right + 1;
                 P.pre = (P.R - left) & (G - 1);
                 P.rend = P.R - P.pre;
                 P.M = (P.rend - left) >> (wsh + 2);
@@ -2536,16 +2555,12 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
                     ++t;
                     if (pivot == rmax) { state = 0; break; }              // all keys equal: neither side is visited
                     if (iters - t == 0) { state = 1; break; }             // out of budget: std::sort of the range
-                    q = xs_inv(P, q);                                     // what sits at the sample positions now
+                    q = xs_inv<W>(P, q);                                  // what sits at the sample positions now
                     pivot = median(lane < W ? v[x[q]] : 0x7fffffff);
                     if (pivot != rmin) { state = 2; break; }
                 }
                 int32_t *tmp = Lbase + left;                              // out of place through the scratch slice
-                for (int32_t i = left + lane; i < P.R; i += 32) {
-                    int32_t d = i;
-                    for (int k = 0; k < t; k++) d = xs_fwd(P, d);
-                    tmp[d - left] = (int32_t)x[i];
-                }
+                for (int32_t i = left + lane; i < P.R; i += 32) tmp[xs_fwd_t<W>(P, i, t) - left] = (int32_t)x[i];
                 __syncwarp();
                 for (int32_t i = left + lane; i < P.R; i += 32) x[i] = (IdxT)tmp[i - left];
                 __syncwarp();
@@ -2588,7 +2603,7 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
             int32_t lo = left + G, hi = rend - G;
             const int vec = lane >> wsh, lW = lane & (W - 1);
             const uint32_t maskW = (1u << W) - 1u, belowW = (1u << lW) - 1u;
-            const bool rev = W == 4;
+            constexpr bool rev = W == 4;
             auto put = [&](int32_t a, int32_t kv) {          // one group of 4 vectors, vector by vector
                 const bool isge = act && kv >= pivot;
                 const uint32_t m = __ballot_sync(FULL, isge);
@@ -2642,21 +2657,25 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     }
 }
 
-template <class IdxT, int NW>
+template <class IdxT, int NW, int W>
 static cudaError_t xss_launch(const XsArgs &A, unsigned grid, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_xss_argsort<IdxT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_xss_argsort<IdxT, NW, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    k_xss_argsort<IdxT, NW><<<grid, 32 * NW, smem, s>>>(A);
+    k_xss_argsort<IdxT, NW, W><<<grid, 32 * NW, smem, s>>>(A);
     return cudaGetLastError();
 }
-template <class IdxT>
+template <class IdxT, int W>
 static cudaError_t xss_launch_w(int warps, const XsArgs &A, unsigned grid, size_t smem, cudaStream_t s) {
     switch (warps) {
-    case 1: return xss_launch<IdxT, 1>(A, grid, smem, s);
-    case 2: return xss_launch<IdxT, 2>(A, grid, smem, s);
-    case 4: return xss_launch<IdxT, 4>(A, grid, smem, s);
-    default: return xss_launch<IdxT, 8>(A, grid, smem, s);
+    case 1: return xss_launch<IdxT, 1, W>(A, grid, smem, s);
+    case 2: return xss_launch<IdxT, 2, W>(A, grid, smem, s);
+    case 4: return xss_launch<IdxT, 4, W>(A, grid, smem, s);
+    default: return xss_launch<IdxT, 8, W>(A, grid, smem, s);
     }
+}
+template <class IdxT>
+static cudaError_t xss_launch_v(int lanes, int warps, const XsArgs &A, unsigned grid, size_t smem, cudaStream_t s) {
+    return lanes == 4 ? xss_launch_w<IdxT, 4>(warps, A, grid, smem, s) : xss_launch_w<IdxT, 8>(warps, A, grid, smem, s);
 }
 #endif
 
@@ -2716,8 +2735,8 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
             XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, cap,
                      mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8};
             static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
-            if (narrow) ICL_CUDA(st, xss_launch_w<uint16_t>(xs_warps, A, (unsigned)(2 * P), smem, s));
-            else ICL_CUDA(st, xss_launch_w<int32_t>(xs_warps, A, (unsigned)(2 * P), smem, s));
+            if (narrow) ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, (unsigned)(2 * P), smem, s));
+            else ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, (unsigned)(2 * P), smem, s));
             ICL_CUDA(st, cudaGetLastError());
             // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
             std::vector<int32_t> hf(2 * (size_t)P);
