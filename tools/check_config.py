@@ -32,6 +32,7 @@ for _ in range(4):
     best = dt if best is None or dt < best else best
 blocks = eng.run_resident(prm, min_members=1)                        # detached copy for the comparison below
 print(f"GPU pass {best * 1e3:.2f} ms = {n / best / 1e6:.1f} M hits/s; phases {eng.timings()}; host {eng.host_ms}; {eng.counters()}", flush=True)
+print(f"ranked by: {eng.numpy_sort_kind() if eng.rank_mode == 'auto' else eng.rank_mode} (None = numpy on the host); handed back to the host: {eng.host_rank_fallbacks}", flush=True)
 t = time.perf_counter()
 exp = oracle_blocks(pts, prm)
 print(f"oracle (C port, {os.cpu_count()} threads incl. Python glue) {time.perf_counter() - t:.2f} s, {len(exp)} blocks", flush=True)
