@@ -2164,6 +2164,8 @@ struct XsArgs {
     int64_t n;
     int32_t P, smem_cap;
     int32_t W;                 // lanes of the emulated vector: 8 = AVX-512, 4 = AVX2
+    int32_t first;             // this launch covers order[first .. first + gridDim.x)
+    int32_t keys_in_smem;      // keys next to the indices in shared memory (else only the indices; keys through L1)
 };
 
 // The key-index network is a bitonic sort with flip merges over P = 8 * numVecs slots: for S = 2, 4, .., P: compare
@@ -2240,7 +2242,9 @@ __device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int 
                 t = x[i]; x[i] = x[j]; x[j] = t;
                 ++i;
             }
-            sf[sp] = f; sl[sp] = i; sd[sp] = depth; sp++;     // left part later, right part now (order is free)
+            // left part later, right part now (order is free); a part of at most 16 elements is finished (the
+            // insertion sort below covers it), so at most 96 / 17 parts wait here at any time
+            if (i - f > 16) { sf[sp] = f; sl[sp] = i; sd[sp] = depth; sp++; }
             f = i;
         }
         if (sp == 0) break;
@@ -2258,6 +2262,7 @@ __device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int 
 }
 
 #define ICL_XS_WARPS_DEFAULT 8
+#define ICL_XS_SMEM_MAX 208768     // dynamic shared memory a CTA may ask for: 227 KB minus the static arrays of 8 warps
 #define ICL_XS_STACK 256
 
 // A partition pass whose pivot equals the smallest key of its range moves every element to the "right" side: nothing
@@ -2343,19 +2348,22 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     const uint32_t FULL = 0xffffffffu;
     constexpr int G = 4 * W;                                  // W lanes per vector, G elements per unrolled group
     constexpr int wsh = W == 8 ? 3 : 2;
-    const int32_t it = A.order[blockIdx.x];
+    const int32_t it = A.order[A.first + blockIdx.x];
     const int32_t p = it >= A.P ? it - A.P : it;
     const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
     const int32_t len = (int32_t)(A.off[p + 1] - A.off[p]);
     if (len <= 0) return;
     extern __shared__ int32_t xs_sm[];
-    const bool fits = sizeof(IdxT) == 2 || len <= A.smem_cap;
+    const bool fits = sizeof(IdxT) == 2 || len <= A.smem_cap;   // indices in shared memory
+    const bool kin = fits && A.keys_in_smem;                     // keys too
     const int32_t *v = A.key + base;
     IdxT *x;
+    IdxT *xsh = (IdxT *)(xs_sm + (A.keys_in_smem ? A.smem_cap : 0));
     if (fits) {
-        int32_t *vs = xs_sm;
-        IdxT *xs = (IdxT *)(xs_sm + A.smem_cap);
-        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) { vs[i] = v[i]; xs[i] = (IdxT)i; }
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) {
+            if (kin) xs_sm[i] = v[i];
+            xsh[i] = (IdxT)i;
+        }
     } else {
         x = (IdxT *)(A.idx + base);
         for (int32_t i = threadIdx.x; i < len; i += blockDim.x) x[i] = (IdxT)i;
@@ -2365,8 +2373,8 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     for (int32_t i = threadIdx.x; i + 1 < len; i += blockDim.x) uns |= v[i] > v[i + 1];
     const int unsorted = __syncthreads_or(uns);
     if (fits) {
-        v = xs_sm;
-        x = (IdxT *)(xs_sm + A.smem_cap);
+        if (kin) v = xs_sm;
+        x = xsh;
     }
     int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;  // stop lists of the std::sort partitions (slice [f, l) per range)
     if (threadIdx.x == 0) {
@@ -2659,7 +2667,7 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
 
 template <class IdxT, int NW, int W>
 static cudaError_t xss_launch(const XsArgs &A, unsigned grid, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_xss_argsort<IdxT, NW, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_xss_argsort<IdxT, NW, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICL_XS_SMEM_MAX);
     if (e != cudaSuccess) return e;
     k_xss_argsort<IdxT, NW, W><<<grid, 32 * NW, smem, s>>>(A);
     return cudaGetLastError();
@@ -2732,11 +2740,29 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
         } else {
             if (c->host_flag.reserve(st, 2 * (size_t)P + 1)) return st.code;
             ICL_CUDA(st, dev_memset(c->host_flag.p, 0, (2 * (size_t)P + 1) * sizeof(int32_t), s));
-            XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, cap,
-                     mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8};
             static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
-            if (narrow) ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, (unsigned)(2 * P), smem, s));
-            else ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, (unsigned)(2 * P), smem, s));
+            // Pairs come longest first (h_pair_order), so the size classes are runs of the item order; one launch each:
+            //   <= 16 000 keys   keys + 16-bit indices in shared memory (96 KB: several CTAs per SM)
+            //   <= 34 000        the same with up to 204 KB (one CTA per SM)
+            //   <= 65 535        16-bit indices in shared memory, keys through L1
+            //   longer           32-bit indices; both in shared memory up to 12 288 keys, else in global memory
+            auto plen = [&](int32_t j) { const int32_t q = c->h_pair_order[j]; return (int64_t)(c->h_pair_off[q + 1] - c->h_pair_off[q]); };
+            auto cls_of = [](int64_t L) { return L > 65535 ? 0 : L > 34000 ? 1 : L > 16000 ? 2 : 3; };
+            for (int32_t j0 = 0; j0 < P;) {
+                const int64_t L = plen(j0);
+                const int cls = cls_of(L);
+                int32_t j1 = j0;
+                while (j1 < P && cls_of(plen(j1)) == cls) j1++;
+                const int64_t Lr = (L + 31) & ~31ll;
+                const int32_t ccap = cls == 0 ? (int32_t)std::min<int64_t>(Lr, 12288) : (int32_t)Lr;
+                const size_t csmem = (size_t)ccap * (cls == 0 ? 8 : cls == 1 ? 2 : 6);
+                XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, ccap,
+                         mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, 2 * j0, cls == 1 ? 0 : 1};
+                const unsigned grid = (unsigned)(2 * (j1 - j0));
+                if (cls == 0) ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, grid, csmem, s));
+                else ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, grid, csmem, s));
+                j0 = j1;
+            }
             ICL_CUDA(st, cudaGetLastError());
             // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
             std::vector<int32_t> hf(2 * (size_t)P);
