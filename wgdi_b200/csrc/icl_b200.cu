@@ -2166,45 +2166,45 @@ struct XsArgs {
     int32_t W;                 // lanes of the emulated vector: 8 = AVX-512, 4 = AVX2
     int32_t first;             // this launch covers order[first .. first + gridDim.x)
     int32_t keys_in_smem;      // keys next to the indices in shared memory (else only the indices; keys through L1)
+    int32_t lane_max;          // std::sort pieces of at most this many elements are sorted by one lane each
 };
 
 // The key-index network is a bitonic sort with flip merges over P = 8 * numVecs slots: for S = 2, 4, .., P: compare
 // slot i with S - 1 - i inside every group of S (min to the lower slot), then for m = S/4, S/8, .., 1 compare i with
 // i + m (bit m of i clear).  One thread per pair; the index follows its key, and on equal keys nothing moves.
-__device__ __forceinline__ void xs_pair(int32_t *nk, int32_t *na, int i, int j) {
-    const int32_t ki = nk[i], kj = nk[j];
-    if (kj < ki) {                                           // strictly out of order: swap key and index
-        const int32_t ai = na[i], aj = na[j];
-        nk[i] = kj; nk[j] = ki;
-        na[i] = aj; na[j] = ai;
+__device__ __forceinline__ void xs_pair(int2 *nkv, int i, int j) {      // .x = key, .y = index
+    const int2 a = nkv[i], b = nkv[j];
+    if (b.x < a.x) {                                         // strictly out of order: swap key and index
+        nkv[i] = b;
+        nkv[j] = a;
     }
 }
 
 template <class IdxT>
-__device__ void xs_network(const int32_t *v, IdxT *x, int32_t left, int32_t n, int32_t *nk, int32_t *na, int lane) {
+__device__ void xs_network(const int32_t *v, IdxT *x, int32_t left, int32_t n, int2 *nkv, int lane) {
     int P = 256;
     while (P > 8 && n * 2 <= P) P >>= 1;
     for (int i = lane; i < P; i += 32) {
-        if (i < n) { const int32_t a = (int32_t)x[left + i]; na[i] = a; nk[i] = v[a]; }
-        else { na[i] = 0; nk[i] = 0x7fffffff; }
+        if (i < n) { const int32_t a = (int32_t)x[left + i]; nkv[i] = make_int2(v[a], a); }
+        else nkv[i] = make_int2(0x7fffffff, 0);
     }
     __syncwarp();
     const int half = P >> 1;
     for (int S = 2; S <= P; S <<= 1) {
         for (int t = lane; t < half; t += 32) {              // flip stage: (G*S + k, G*S + S-1-k), k < S/2
             const int hs = S >> 1, G = t / hs, k = t - G * hs;
-            xs_pair(nk, na, G * S + k, G * S + S - 1 - k);
+            xs_pair(nkv, G * S + k, G * S + S - 1 - k);
         }
         __syncwarp();
         for (int m = S >> 2; m >= 1; m >>= 1) {
             for (int t = lane; t < half; t += 32) {          // xor stage: insert a zero bit at log2(m)
                 const int i = ((t & ~(m - 1)) << 1) | (t & (m - 1));
-                xs_pair(nk, na, i, i | m);
+                xs_pair(nkv, i, i | m);
             }
             __syncwarp();
         }
     }
-    for (int i = lane; i < n; i += 32) x[left + i] = (IdxT)na[i];
+    for (int i = lane; i < n; i += 32) x[left + i] = (IdxT)nkv[i].y;
     __syncwarp();
 }
 
@@ -2337,13 +2337,13 @@ __device__ __forceinline__ int32_t xs_inv(const XsPerm &P, int32_t d) {         
 // vector land in REVERSED lane order).
 template <class IdxT, int NW, int W>
 __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
-    __shared__ int32_t nk_all[NW][256], na_all[NW][256];
+    __shared__ int2 nkv_all[NW][256];
     __shared__ int32_t st_lo[ICL_XS_STACK], st_hi[ICL_XS_STACK], st_it[ICL_XS_STACK];   // st_it >= 0: argsort_ range with that
                                                               // budget; < 0: std::sort range [lo, hi), depth budget -st_it - 1
     __shared__ int32_t sm_lo_all[NW][32], sm_hi_all[NW][32], sm_d_all[NW][32];
     __shared__ int32_t s_sp, s_pending, s_lock, s_giveup;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int32_t *nk = nk_all[wid], *na = na_all[wid];
+    int2 *nkv = nkv_all[wid];
     int32_t *sm_lo = sm_lo_all[wid], *sm_hi = sm_hi_all[wid], *sm_d = sm_d_all[wid];
     const uint32_t FULL = 0xffffffffu;
     constexpr int G = 4 * W;                                  // W lanes per vector, G elements per unrolled group
@@ -2449,7 +2449,7 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
             // ------------------------------------------------ std::sort range [f, l), depth budget -iters - 1
             int32_t f = left, l = right;
             int depth = -iters - 1;
-            while (l - f > ICL_XS_LANE) {
+            while (l - f > A.lane_max) {
                 if (depth == 0) { give_up = true; if (lane == 0) *vgive = 1; break; }
                 --depth;
                 int32_t pv = 0;
@@ -2523,7 +2523,7 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
             continue;
         }
         if (right + 1 - left <= 256) {
-            xs_network(v, x, left, right + 1 - left, nk, na, lane);
+            xs_network(v, x, left, right + 1 - left, nkv, lane);
             done();
             continue;
         }
@@ -2632,12 +2632,16 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
                 r_store -= tot;
                 __syncwarp();
             };
+            // the next group of either side is fetched before the rule picks one: a pass only writes positions it has
+            // already read, so reading early returns the same values and takes two shared-memory round trips off the chain
+            int32_t nLa = 0, nLk = 0, nRa = 0, nRk = 0;
+            auto fetch = [&](int32_t b0, int32_t &a, int32_t &k) { a = act ? (int32_t)x[b0 + lane] : 0; k = act ? v[a] : 0; };
+            if (lo < hi) { fetch(lo, nLa, nLk); fetch(hi - G, nRa, nRk); }
             while (hi != lo) {
-                int32_t b0;
-                if ((r_store + W) - hi < lo - l_store) { hi -= G; b0 = hi; }
-                else { b0 = lo; lo += G; }
-                const int32_t a = act ? (int32_t)x[b0 + lane] : 0;
-                put(a, act ? v[a] : 0);
+                int32_t a, k;
+                if ((r_store + W) - hi < lo - l_store) { hi -= G; a = nRa; k = nRk; if (lo < hi) fetch(hi - G, nRa, nRk); }
+                else { a = nLa; k = nLk; lo += G; if (lo < hi) fetch(lo, nLa, nLk); }
+                put(a, k);
             }
             put(aL, kL);
             put(aR, kR);
@@ -2741,6 +2745,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
             if (c->host_flag.reserve(st, 2 * (size_t)P + 1)) return st.code;
             ICL_CUDA(st, dev_memset(c->host_flag.p, 0, (2 * (size_t)P + 1) * sizeof(int32_t), s));
             static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
+            static const int xs_lane = [] { const char *e = getenv("ICL_B200_XS_LANE"); const int q = e ? atoi(e) : ICL_XS_LANE; return q < 16 ? 16 : q > 160 ? 160 : q; }();
             // Pairs come longest first (h_pair_order), so the size classes are runs of the item order; one launch each:
             //   <= 16 000 keys   keys + 16-bit indices in shared memory (96 KB: several CTAs per SM)
             //   <= 34 000        the same with up to 204 KB (one CTA per SM)
@@ -2757,7 +2762,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
                 const int32_t ccap = cls == 0 ? (int32_t)std::min<int64_t>(Lr, 12288) : (int32_t)Lr;
                 const size_t csmem = (size_t)ccap * (cls == 0 ? 8 : cls == 1 ? 2 : 6);
                 XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, ccap,
-                         mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, 2 * j0, cls == 1 ? 0 : 1};
+                         mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, 2 * j0, cls == 1 ? 0 : 1, xs_lane};
                 const unsigned grid = (unsigned)(2 * (j1 - j0));
                 if (cls == 0) ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, grid, csmem, s));
                 else ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, grid, csmem, s));
