@@ -538,8 +538,8 @@ def test_device_numpy_avx2_argsort_is_numpys():
 
 def test_device_numpy_avx512_argsort_is_numpys(gpu_engine):
     """icl_rank_device(ICL_RANK_NUMPY_AVX512) against numpy in this process, where numpy sorts int64 with its AVX-512
-    kernels: every segment's argsort identical (all sizes 1..600, real score arrays, one 40 000-element segment on the
-    global-memory path), and the blocks identical to the host-ranked path."""
+    kernels: every segment's argsort identical (all sizes 1..600, real score arrays, constant / sorted segments, segments
+    of every size class of the kernel's launches), and the blocks identical to the host-ranked path."""
     from wgdi_b200 import synth
     from wgdi_b200.engine import ChainParams, IclEngine
     if gpu_engine.numpy_sort_kind() != "numpy_avx512":
@@ -553,9 +553,17 @@ def test_device_numpy_avx512_argsort_is_numpys(gpu_engine):
                   grading=rng.choice(np.array([50, 30, 25], np.int32), sum(sizes)), n_pairs=len(sizes)),
              synth.graded_points(synth.make_dataset("small")),
              synth.graded_points(synth.make_dataset("C2", scale=0.15))]
-    n = 40000
-    cases.append(dict(pair_id=np.zeros(n, np.int32), loc1=np.repeat(np.arange(1, n // 4 + 1), 4).astype(np.int32),
-                      loc2=rng.integers(1, 3000, n).astype(np.int32), grading=rng.choice(np.array([50, 30, 25], np.int32), n), n_pairs=1))
+    # one launch per size class of the rank kernel: <= 16 000 keys (above), <= 34 000 (keys + 16-bit indices in up to 204 KB
+    # of shared memory), <= 65 535 (indices in shared memory, keys through L1), longer (32-bit indices in global memory);
+    # the last case mixes three classes in one comparison
+    for n in (40000, 20000, 70000):
+        cases.append(dict(pair_id=np.zeros(n, np.int32), loc1=np.repeat(np.arange(1, n // 4 + 1), 4).astype(np.int32),
+                          loc2=rng.integers(1, 3000, n).astype(np.int32), grading=rng.choice(np.array([50, 30, 25], np.int32), n), n_pairs=1))
+    sizes3 = [70000, 36000, 17000, 900, 300]
+    cases.append(dict(pair_id=np.repeat(np.arange(5, dtype=np.int32), sizes3),
+                      loc1=np.concatenate([np.repeat(np.arange(1, m // 4 + 1), 4) for m in sizes3]).astype(np.int32),
+                      loc2=rng.integers(1, 3000, sum(sizes3)).astype(np.int32),
+                      grading=rng.choice(np.array([50, 30, 25], np.int32), sum(sizes3)), n_pairs=5))
     # isolated points: every score equals the grading -> constant and sorted key segments (numpy's SIMD argsort leaves
     # an already sorted array untouched; a partition pass whose pivot is the smallest key moves everything)
     iso = np.arange(1, 901, dtype=np.int32) * 1000
