@@ -5,13 +5,19 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: all chromosome pairs of
 BASELINE.json config 2 (Vitis-sized self comparison, 19 chromosomes -> 361 chromosome pairs, ~2M graded
-BLAST hits) are sorted, chained in both directions, ranked with numpy (the reference's own unstable
-argsort, required for bit-exact tie order) and extracted into blocks with p values.
+BLAST hits) are sorted, chained in both directions, ranked in the order numpy's own unstable argsort would give
+(required for the reference's tie order) and extracted into blocks with p values.  The rank runs on the device when one
+of its exact reproductions of numpy's argsort (AVX-512 / AVX2 / scalar) matches numpy in this process — checked at
+start-up, `config.tie_order` reports it — and with numpy on the host otherwise.
 
-  value   hits/s with the graded hits already resident in HBM (icl_dp + host rank + icl_extract)
+  value   hits/s with the graded hits already resident in HBM (icl_dp + rank + icl_extract)
   e2e     hits/s through the engine's public call with HOST buffers: pinned inputs -> H2D -> ... -> blocks on host
   roofline  the chaining-DP kernel against the measured HBM bandwidth (it is latency-bound: DESIGN.md)
   cpu_baseline  the oracle's C restatement of the reference algorithm on all host cores (kind "port")
+  host_ranked / portable_numpy / avx2_numpy / device_rank_option / batch / icl_wall   comparison legs: the same step
+          ranked by numpy on the host; the same in child processes whose numpy runs its scalar resp. AVX2 argsort (device-
+          ranked with that flavour, blocks checked against the oracle in the child); the stable-rank option (NOT the
+          reference's tie order); pipelined comparisons; conf-in -> file-out wall time
 
 With N > 1 (torchrun, one rank per GPU) the workload is N such comparisons (seeds differ); their 361*N chromosome
 pairs are pooled and assigned to ranks by longest-processing-time on point count; every rank uploads only its
@@ -269,9 +275,13 @@ def portable_child(args):
     print("PORTABLE " + json.dumps(out), flush=True)
 
 
-def run_portable_leg(args, local, rank, world):
-    """Parent side: the same workload in a child with numpy's SIMD sorts disabled (see portable_child)."""
-    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_NUMPY)
+AVX2_NUMPY = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX512_KNL AVX512_KNM"
+
+
+def run_portable_leg(args, local, rank, world, features=PORTABLE_NUMPY):
+    """Parent side: the same workload in a child with numpy's SIMD sorts disabled (see portable_child); with
+    `features=AVX2_NUMPY` only the AVX-512 ones, which leaves numpy with its AVX2 argsort."""
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=features)
     cmd = [sys.executable, os.path.abspath(__file__), "--portable-child", str(local), "--workload", args.workload,
            "--steps", str(args.steps), "--warmup", str(args.warmup), "--seed-shift", str(rank)]
     if rank == 0 and world == 1:
@@ -485,6 +495,16 @@ def main():
     # ---- the reference's tie order WITHOUT the host: in a process whose numpy runs its scalar introsort (SIMD sorts
     # disabled — also how the fixtures under tests/golden were generated) the device reproduces numpy's argsort exactly and
     # ranks itself.  One comparison per GPU, every rank's child at the same time.
+    avx2_leg = None
+    if not args.no_portable and world == 1:
+        # third flavour: numpy with its AVX2 argsort (what x86 hosts without AVX-512 run), device-ranked, checked against
+        # the oracle ranked by that numpy inside the child
+        avx2_leg = run_portable_leg(args, local, rank, world, features=AVX2_NUMPY)
+        if "ms_per_step" in avx2_leg:
+            avx2_leg["value"] = total_points / (avx2_leg["ms_per_step"] * 1e-3)
+            avx2_leg["unit"] = "hits/s"
+            avx2_leg["what"] = ("same path in a child process whose numpy has its AVX-512 kernels disabled (AVX2 argsort): "
+                                "device-ranked with that flavour, inputs resident")
     portable = None
     if not args.no_portable:
         barrier()
@@ -583,6 +603,7 @@ def main():
                              "what": "same kernel with the streamed export off (ICL_B200_STREAM=0), 3 extra untimed passes"},
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
             "phase_ms": res_ms, "batch": batch, "host_ranked": host_ranked, "device_rank_option": device_rank, "portable_numpy": portable,
+            "avx2_numpy": avx2_leg,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }
