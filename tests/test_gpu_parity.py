@@ -595,6 +595,49 @@ def test_device_numpy_avx512_argsort_is_numpys(gpu_engine):
         eng.close()
 
 
+def test_device_rank_is_deterministic(gpu_engine):
+    """The rank kernel's warps hand sub-ranges to each other through a shared stack; whatever order they take them in,
+    the permutation is a function of the keys alone: 25 repetitions (and 1, 2, 4 warps per segment in child processes)
+    give the same order as numpy every time."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    kind = gpu_engine.numpy_sort_kind()
+    if kind is None:
+        pytest.skip("numpy in this process is none of the reproduced flavours")
+    mode = {"numpy_scalar": 1, "numpy_avx512": 2, "numpy_avx2": 3}[kind]
+    pts = synth.graded_points(synth.make_dataset("C2", scale=0.15))
+    prm = ChainParams(mg1=40, mg2=40, grading=(50, 40, 25))
+    eng = IclEngine(0)
+    try:
+        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+        kf, kr = eng.dp(prm)
+        n = eng.n
+        keys = np.concatenate([kf, kr])
+        off = np.concatenate([eng.pair_off, eng.pair_off[1:] + n])
+        exp = np.concatenate([keys[a:b].astype(np.int64).argsort(kind="quicksort") for a, b in zip(off[:-1], off[1:])])
+        got = np.zeros(2 * n, np.int32)
+        for rep in range(25):
+            eng._check(eng.lib.icl_rank_device(eng.ctx, mode))
+            eng._check(eng.lib.icl_debug_order(eng.ctx, got.ctypes.data))
+            assert (got == exp).all(), rep
+    finally:
+        eng.close()
+    if kind != "numpy_scalar":
+        child = ("import sys; sys.path.insert(0, %r)\n"
+                 "import numpy as np\nfrom wgdi_b200 import synth\nfrom wgdi_b200.engine import ChainParams, IclEngine\n"
+                 "pts = synth.graded_points(synth.make_dataset('C2', scale=0.15))\n"
+                 "prm = ChainParams(mg1=40, mg2=40, grading=(50, 40, 25))\n"
+                 "eng = IclEngine(0); eng.upload(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], pts['n_pairs'])\n"
+                 "b1 = eng.run_resident(prm); assert eng.numpy_sort_kind() == %r and eng.host_rank_fallbacks == 0\n"
+                 "eng.rank_mode = 'host'; b2 = eng.run_resident(prm)\n"
+                 "assert len(b1) == len(b2) and all((getattr(b1, f) == getattr(b2, f)).all() for f in ('pair', 'dir', 'score', 'p_raw', 'loc1', 'loc2'))\n"
+                 "print('OK')\n" % (ROOT, kind))
+        for warps in (1, 2, 4):
+            r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, ICL_B200_XS_WARPS=str(warps)),
+                               capture_output=True, text=True)
+            assert r.returncode == 0 and "OK" in r.stdout, (warps, r.stdout[-1000:] + r.stderr[-2000:])
+
+
 def test_alternative_dp_kernels_agree(clouds):
     """The alternative DP kernels (ICL_B200_CHAIN=generic / single) give the same blocks as the default ring kernel."""
     from wgdi_b200 import synth
