@@ -567,7 +567,11 @@ def main():
         streamed = bool(getattr(eng, "stream_rank", False)) and counters["chain_kernel"] == "ring" and not on_device
         bytes_pp = DP_BYTES_PER_POINT + (EXPORT_BYTES_PER_POINT if streamed else 0)
         achieved = bytes_pp * n_local / (chain_ms * 1e-3) / 1e9
-        d2h = 16 * n_local + int(len(blocks) * 64 + len(blocks.loc1) * 12)
+        # bytes that cross PCIe per e2e step: points in (4 int32 arrays); blocks out (64 B per block + 12 B per member) plus
+        # one flag per segment; with the host ranking also the score keys out (2 x 4 B per point: streamed by the DP kernel)
+        # and the argsort back in (2 x 4 B per point)
+        d2h = int(len(blocks) * 64 + len(blocks.loc1) * 12) + (8 * int(mine["n_pairs"]) if on_device else 8 * n_local)
+        h2d = 16 * n_local + (0 if on_device else 8 * n_local)
         line = {
             "metric": METRIC, "value": total_points * args.steps / t_res, "unit": "hits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
@@ -584,7 +588,7 @@ def main():
                                      else "numpy argsort on host between the two device phases (reference-exact)")},
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "ms_per_step_cuda_events": 1e3 * ev_e2e / args.steps,
-                    "h2d_bytes_per_step": 16 * n_local + 8 * n_local, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
             "host_rank_fallbacks": int(getattr(eng, "host_rank_fallbacks", 0)),
             "roofline": {"kernel": "k_chain_ring: chain DP, both directions" + (" + streamed score export" if streamed else ""),
