@@ -2128,12 +2128,14 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// numpy's AVX-512 argsort, reproduced exactly on the device.
+// numpy's AVX-512 and AVX2 argsort, reproduced exactly on the device.
 //
-// On CPUs with AVX-512 numpy.argsort(kind='quicksort') on int64 is x86-simd-sort's `avx512_argsort` (this pool's hosts).
-// The algorithm (restated from the library's source as I know it and checked step by step against numpy 2.3.5 on such a
-// host — tools/xss_emulation.py: 8-lane network, 16, 32..256 elements, pivot + partition, std::sort fallback, real DP
-// score arrays — before any CUDA was written):
+// On CPUs with AVX-512 numpy.argsort(kind='quicksort') on int64 is x86-simd-sort's `avx512_argsort` (this pool's hosts),
+// on other x86 CPUs its AVX2 counterpart.  The algorithm (restated from the library's source as I know it and checked
+// step by step against numpy 2.3.5 — tools/xss_emulation.py: 8-lane network, 16, 32..256 elements, pivot + partition,
+// std::sort fallback, sorted / constant arrays, real DP score arrays — before any CUDA was written; described for 8
+// lanes, the AVX2 differences are at the kernel):
+//   keys already in non-decreasing order: the identity (top level only).
 //   argsort_(left, right, iters = 2 * floor(log2 n)):
 //     iters <= 0            -> std::sort of the index range with the comparator arr[a] < arr[b] (libstdc++ introsort)
 //     at most 256 elements  -> key-index bitonic network over 8-lane registers (padding key = max, padding index = 0):
@@ -2147,10 +2149,12 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
 //   of every 8-lane vector the keys < pivot are compress-stored at l_store, the keys >= pivot below r_store + 8; the two
 //   groups set aside go last (left one first).
 // Every step is a function of the keys alone, so a warp can do the 32 lanes of a group, or the positions of a network
-// stage, at once without changing the result.  The std::sort fallback — DP score arrays always have one: the mass of
-// never-updated points holds two or three distinct keys and a pivot equal to the smallest makes no progress — is
-// replayed by one lane (median of three to the front, unguarded Hoare partition, right part first, 16-element
-// threshold, final insertion sort); its heap-sort branch (depth limit) has never been observed and hands the segment
+// stage, at once, and disjoint sub-ranges can be taken by different warps in any order, without changing the result.
+// DP score arrays always reach the std::sort fallback: the mass of never-updated points holds two or three distinct
+// keys, a pivot equal to the smallest key moves everything and makes no progress, and the budget runs out.  Those
+// passes are applied in closed form (XsPerm below); std::sort itself (median of three to the front, unguarded Hoare
+// partition, 16-element threshold, final insertion sort) is done by a warp with stop lists down to ICL_XS_LANE elements
+// and by single lanes below that; its heap-sort branch (depth limit) has never been observed and hands the segment
 // back to the host (flag), as does anything else this kernel does not cover.
 // ------------------------------------------------------------------------------------------------
 #ifndef ICL_EMU
