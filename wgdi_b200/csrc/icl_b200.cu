@@ -2696,10 +2696,12 @@ static cudaError_t xss_launch_v(int lanes, int warps, const XsArgs &A, unsigned 
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// ABI: icl_rank_device — NON-REFERENCE tie order.  The extraction order of every (pair, direction) item from a
-// STABLE device sort: what pandas' nargsort(ascending=False) would return if numpy's argsort were stable (reverse,
-// stable ascending argsort, reverse).  Identical to the reference wherever scores are distinct; tied scores come
-// in reversed (loc1, loc2) order instead of numpy's CPU-specific permutation.
+// ABI: icl_rank_device — the extraction order of every (pair, direction) item computed on the device.
+// ICL_RANK_NUMPY_AVX512 / _AVX2 / _SCALAR: numpy's own argsort of that flavour, reproduced exactly (the reference's tie
+// order wherever numpy runs that flavour).  ICL_RANK_STABLE: NON-REFERENCE tie order from a STABLE device sort — what
+// pandas' nargsort(ascending=False) would return if numpy's argsort were stable (reverse, stable ascending argsort,
+// reverse): identical to the reference wherever scores are distinct; tied scores come in reversed (loc1, loc2) order
+// instead of numpy's CPU-specific permutation.
 // ------------------------------------------------------------------------------------------------
 extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     if (!c) return ICL_ERR_ARG;
