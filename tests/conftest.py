@@ -58,7 +58,10 @@ def emu_backend(monkeypatch):
     lib = _lib._declare(ctypes.CDLL(so))
     assert lib.icl_backend() == b"emu"
     monkeypatch.setattr(_lib, "_LIB", lib)
+    from wgdi_b200 import engine
+    engine._NP_KIND.clear()                  # which numpy flavour the "device" reproduces is probed per backend
     yield lib
+    engine._NP_KIND.clear()
 
 
 def have_gpu():
@@ -72,8 +75,10 @@ def have_gpu():
 @pytest.fixture(scope="session")
 def gpu_engine():
     from wgdi_b200 import _lib
+    from wgdi_b200 import engine
     from wgdi_b200.engine import IclEngine
     _lib._LIB = None
+    engine._NP_KIND.clear()
     eng = IclEngine(0)
     assert eng.lib.icl_backend() == b"cuda"
     yield eng

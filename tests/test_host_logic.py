@@ -404,6 +404,33 @@ def test_device_rank_mode_emu(emu_backend):
     assert sorted(got.score.tolist()) == sorted(ref.score.tolist()) or len(got) != len(ref)   # tie order may differ, nothing else
 
 
+def test_device_rank_hands_back_to_the_host_emu(emu_backend):
+    """When the device cannot rank a comparison with the requested numpy flavour (ICL_ERR_STATE: on a GPU the std::sort
+    heap-sort branch, here the emulated backend, which has no such kernels), the engine ranks that comparison with numpy
+    on the host: same blocks as the host-ranked path, the hand-back counted; the start-up probe finds no flavour."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("tiny"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+        eng.rank_mode = "host"
+        ref = eng.run_resident(prm)
+        for k, mode in enumerate(("numpy_avx512", "numpy_avx2", "numpy_scalar")):
+            got = eng.run_resident_device_rank(prm, mode=mode)
+            assert eng.host_rank_fallbacks == k + 1
+            assert len(got) == len(ref) > 20
+            for f in ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
+                assert (getattr(got, f) == getattr(ref, f)).all(), (mode, f)
+        assert eng.numpy_sort_kind() is None
+        eng.rank_mode = "auto"
+        auto = eng.run_resident(prm)                                     # auto with no matching flavour = the host path
+        assert (auto.score == ref.score).all() and (auto.loc1 == ref.loc1).all()
+    finally:
+        eng.close()
+
+
 def test_avx512_argsort_specification_matches_numpy():
     """tools/xss_emulation.py — the plain-Python statement of numpy's AVX-512 argsort that the CUDA kernel follows —
     against numpy itself, where numpy sorts that way (AVX-512 hosts); elsewhere there is nothing to compare with."""
