@@ -313,8 +313,6 @@ def main():
     ap.add_argument("--portable", action="store_true",
                     help="run the WHOLE benchmark (either arm) with numpy's SIMD sorts disabled (NPY_DISABLE_CPU_FEATURES): "
                          "numpy's scalar argsort, the tie order that is the same on every machine; the engine then ranks on the device")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("ICL_BENCH_LANES", "1")),
-                    help="pipelined lanes per GPU (wgdi_b200/pipeline.py); 1 = plain engine")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -375,11 +373,7 @@ def main():
 
     # the host rank (numpy's argsort) is per-rank host work: split the box's cores between the ranks
     sort_threads = int(os.environ.get("ICL_BENCH_SORT_THREADS", 0)) or max(1, (os.cpu_count() or 1) // world)
-    if args.lanes > 1:
-        from wgdi_b200.pipeline import PipelinedEngine
-        eng = PipelinedEngine(local, lanes=args.lanes, sort_threads=sort_threads)
-    else:
-        eng = IclEngine(local, sort_threads=sort_threads)
+    eng = IclEngine(local, sort_threads=sort_threads)
     # inputs in page-locked host memory (the e2e leg copies them every step)
     host_in = {}
     for k in ("pair_id", "loc1", "loc2", "grading"):
@@ -414,10 +408,7 @@ def main():
         sampler.start()
     # device-side clock: CUDA events on the stream the library launches on (host work between the two device phases
     # leaves that stream idle, so event time and wall time must agree; both are reported)
-    if hasattr(eng, "ctx"):
-        estream = torch.cuda.ExternalStream(int(eng.lib.icl_stream(eng.ctx)), device=torch.device("cuda", local))
-    else:                                    # pipelined lanes: several contexts, no single stream
-        estream = torch.cuda.current_stream()
+    estream = torch.cuda.ExternalStream(int(eng.lib.icl_stream(eng.ctx)), device=torch.device("cuda", local))
 
     def timed(step):
         wall, evms, out = 0.0, 0.0, None
@@ -526,7 +517,7 @@ def main():
     # ---- batch throughput (BASELINE config 5 shape): independent comparisons through two engines on this GPU, one
     # job's host rank overlapping the next job's upload + device phases (wgdi_b200/batch.py); every job uploads
     batch = None
-    if args.batch > 0 and args.lanes <= 1:
+    if args.batch > 0:
         from wgdi_b200.batch import BatchRunner
         runner = BatchRunner(local, depth=2, sort_threads=sort_threads)
         try:
@@ -581,7 +572,6 @@ def main():
                        "graded_hits": total_points, "chromosome_pairs": total_pairs, "blocks": n_blocks,
                        "mg": list(mine["cfg"].mg), "grading": list(mine["cfg"].grading),
                        "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
-                       "lanes_per_gpu": args.lanes,
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
                        "tie_order": (f"this process's numpy argsort ({eng.numpy_sort_kind()}) reproduced exactly on the device, checked against numpy at start-up: reference-exact"
                                      if getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_kind") and eng.numpy_sort_kind()

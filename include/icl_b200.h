@@ -106,16 +106,17 @@ int icl_host_free(icl_ctx *ctx, void *ptr);
 int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
                const int32_t *pair_id, const int32_t *loc1, const int32_t *loc2, const int32_t *grading);
 
-/* Points per chromosome pair of the current upload (host array of n_pairs elements). */
-int icl_pair_counts(icl_ctx *ctx, int64_t *counts);
-
 /*
- * Fill `dst` with the points of `src`'s current upload whose pair id lies in [pair_lo, pair_hi), in upload order,
- * pair ids renumbered from 0 (device to device; both contexts on the same GPU).  Chromosome pairs are independent,
- * so a comparison can be cut into lanes that run icl_dp / icl_extract on their own streams while the host sorts
- * another lane (wgdi_b200/pipeline.py).  `member_idx` of blocks extracted from `dst` refers to `src`'s upload.
+ * Grading classes for parameter sweeps over `grading` (BASELINE config 5).  The reference assigns a hit's grading
+ * from the class of its per-query rank (wgdi/run_colliearity.py:30-33,64-86: rank < multiple -> grading[0], the next
+ * four -> grading[1], the rest up to repeat_number -> grading[2]), so two confs that differ only in `grading` grade
+ * the same hits into the same classes.  With a table set (n_classes > 0) the `grading` array given to icl_upload is
+ * read as class ids in [0, n_classes) and every later icl_dp / icl_dp_begin chains with values[class]; the table may
+ * be changed between icl_dp calls on the same upload.  n_classes = 0 (the default) restores plain grading values.
+ * values must lie in 0..255.
  */
-int icl_upload_from(icl_ctx *dst, icl_ctx *src, int32_t pair_lo, int32_t pair_hi);
+#define ICL_MAX_GRADE_CLASSES 8
+int icl_set_grading_table(icl_ctx *ctx, int32_t n_classes, const int32_t *values);
 
 /*
  * Sort + chaining DP in both directions (wgdi/collinearity.py:72-115: forward :74-93, anti-diagonal

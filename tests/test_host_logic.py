@@ -163,29 +163,6 @@ def test_forked_chains_emu(emu_backend):
         eng.close()
 
 
-def test_pipelined_lanes_equal_single_engine_emu(emu_backend):
-    """K lanes of consecutive pair ranges (device-side split of one upload) reproduce the single-engine result,
-    including lanes without pairs."""
-    from wgdi_b200 import synth
-    from wgdi_b200.engine import ChainParams, IclEngine
-    from wgdi_b200.pipeline import PipelinedEngine
-    pts = synth.graded_points(synth.make_dataset("tiny"))
-    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
-    e1 = IclEngine(0, sort_threads=2)
-    whole = e1.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
-    e1.close()
-    for lanes in (1, 2, 3, 12):
-        pe = PipelinedEngine(0, lanes=lanes, sort_threads=2)
-        try:
-            got = pe.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
-            again = pe.run_resident(prm)
-        finally:
-            pe.close()
-        for f in ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx"):
-            assert (getattr(got, f) == getattr(whole, f)).all(), (lanes, f)
-            assert (getattr(again, f) == getattr(whole, f)).all(), (lanes, f)
-
-
 _E2E_CHILD = r"""
 import sys, hashlib, json, ctypes, io, contextlib, numpy as np
 sys.path.insert(0, %r)
@@ -353,27 +330,47 @@ def test_grade_hits_chromosomes_matches_oracle():
 
 def test_batch_runner_emu(emu_backend):
     """BatchRunner (two engines, two host threads, shared sort pool) returns every job's blocks in job order,
-    identical to a lone engine; a failing job raises in the caller."""
+    identical to a lone engine fed the points RE-GRADED for that job's `grading` (run_colliearity.py:64-86: a grading
+    sweep changes every point's value); a failing job raises in the caller."""
+    from conftest import oracle_blocks
     from wgdi_b200 import synth
-    from wgdi_b200.batch import BatchRunner, sweep_jobs
+    from wgdi_b200.batch import BatchRunner, regrade, sweep_jobs
     from wgdi_b200.engine import ChainParams, IclEngine
-    pts = synth.graded_points(synth.make_dataset("tiny"))
-    jobs, _ = sweep_jobs(pts, [(50, 30, 25)], [(25, 25), (40, 40), (10, 15)], [1])
+    ds = synth.make_dataset("tiny")
+    pts = synth.graded_points(ds)
+    gradings = [(50, 30, 25), (50, 40, 25), (40, 40, 10)]
+    jobs, keys = sweep_jobs(pts, gradings, [(25, 25), (40, 40), (10, 15)], [1])
+    assert all("grading" not in p_ for p_, _ in jobs)       # class ids travel, values come from the job
     runner = BatchRunner(0, depth=2, sort_threads=2)
     try:
         got = runner.run(jobs)
-        bad = dict(pts, loc1=pts["loc1"][:-1])
+        bad = dict(jobs[0][0], loc1=pts["loc1"][:-1])
         with pytest.raises(ValueError):
             runner.run(jobs[:1] + [(bad, jobs[0][1])])
     finally:
         runner.close()
+    with pytest.raises(ValueError):
+        sweep_jobs({k: v for k, v in pts.items() if k != "grade_class"}, gradings, [(25, 25)], [1])
     eng = IclEngine(0, sort_threads=2)
     try:
-        for (p_, prm), b in zip(jobs, got):
-            exp = eng.chain(p_["pair_id"], p_["loc1"], p_["loc2"], p_["grading"], p_["n_pairs"], prm)
+        for (p_, prm), (g, mg, _), b in zip(jobs, keys, got):
+            own = synth.graded_points(ds, grading=g)         # graded from scratch with this job's values
+            assert (own["grading"] == regrade(pts, g)["grading"]).all()
+            exp = eng.chain(own["pair_id"], own["loc1"], own["loc2"], own["grading"], own["n_pairs"], prm)
             assert len(b) == len(exp) > 0 and (b.p_raw == exp.p_raw).all() and (b.loc1 == exp.loc1).all()
+            assert (b.score == exp.score).all()
+        # the oracle on independently re-graded input, one job per grading
+        for j in (0, 3, 6):
+            own = synth.graded_points(ds, grading=keys[j][0])
+            exp = oracle_blocks(own, jobs[j][1])
+            assert len(exp) == len(got[j])
+            for bi, (pair, d, l1, l2, a, sc) in enumerate(exp):
+                a0, a1 = got[j].member_off[bi], got[j].member_off[bi + 1]
+                assert got[j].score[bi] == sc and got[j].p_raw[bi] == a and (got[j].loc1[a0:a1] == l1).all()
     finally:
         eng.close()
+    # the grading sweep really changes the result (same mg, gradings 50,30,25 vs 50,40,25)
+    assert len(got[0]) != len(got[3]) or (got[0].score[:50] != got[3].score[:50]).any()
     assert len({len(b) for b in got}) > 1                  # the mg sweep really changes the result
 
 

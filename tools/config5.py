@@ -32,6 +32,13 @@ PVALUES = [0.05, 0.2, 1.0]
 SPECIES = [(25_000, 7), (28_000, 9), (30_000, 10), (33_000, 12), (36_000, 13), (39_000, 16), (42_000, 17), (45_000, 19)]
 
 
+def comparison_config(ci, a, b):
+    (ga, ca), (gb, cb) = SPECIES[a], SPECIES[b]
+    genes = (ga + gb) // 2
+    return synth.SynthConfig(f"c5_{a}_{b}", 20260500 + ci, n_anc=int(genes / 2 / 0.6), k=2, n_chr1=ca, n_chr2=cb,
+                             self_cmp=False, target_points=int(genes * 60))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=0.25)
@@ -40,12 +47,10 @@ def main():
     args = ap.parse_args()
     gpus = [int(g) for g in args.gpus.split(",")]
     t0 = time.perf_counter()
-    comps = []
+    comps, cfgs = [], []
     for ci, (a, b) in enumerate(itertools.combinations(range(len(SPECIES)), 2)):
-        (ga, ca), (gb, cb) = SPECIES[a], SPECIES[b]
-        genes = (ga + gb) // 2
-        cfg = synth.SynthConfig(f"c5_{a}_{b}", 20260500 + ci, n_anc=int(genes / 2 / 0.6), k=2, n_chr1=ca, n_chr2=cb,
-                                self_cmp=False, target_points=int(genes * 60))
+        cfg = comparison_config(ci, a, b)
+        cfgs.append(cfg)
         comps.append(synth.graded_points(synth.make_dataset(cfg, scale=args.scale)))
     n_hits = [len(c["loc1"]) for c in comps]
     print(f"{len(comps)} comparisons, {sum(n_hits)} graded hits in total ({min(n_hits)}..{max(n_hits)}), "
@@ -98,7 +103,10 @@ def main():
         for key in sorted(check_keys):
             c, g, mg = key
             prm = ChainParams(mg1=mg[0], mg2=mg[1], grading=g)
-            exp = oracle_blocks(comps[c], prm)
+            # the oracle's input is graded from scratch with THIS job's grading (run_colliearity.py:64-86), not looked up
+            # from the classes the device path uses
+            own = synth.graded_points(synth.make_dataset(cfgs[c], scale=args.scale), grading=g)
+            exp = oracle_blocks(own, prm)
             pair, d, score, p_raw, moff, l1, l2 = results[key][1]
             assert len(exp) == len(pair), (key, len(exp), len(pair))
             for b, (ep, ed, el1, el2, ea, esc) in enumerate(exp):

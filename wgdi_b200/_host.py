@@ -40,6 +40,24 @@ def load():
     return _LIB
 
 
+_COMPRESSED_EXT = (".gz", ".bz2", ".zip", ".xz", ".zst", ".tar", ".tar.gz", ".tar.xz", ".tar.bz2")
+_COMPRESSED_MAGIC = (b"\x1f\x8b", b"BZh", b"\xfd7zXZ\x00", b"PK\x03\x04", b"\x28\xb5\x2f\xfd")
+
+
+def is_compressed(path):
+    """True when pandas.read_csv would (have to) decompress `path`: the reference reads the BLAST table with pandas
+    (wgdi/base.py:174), which infers gzip / bz2 / zip / xz / zstd from the extension.  The native parser maps raw bytes, so
+    such files go through the pandas reader (also when only the magic bytes say so: then pandas fails as the reference does)."""
+    if str(path).lower().endswith(_COMPRESSED_EXT):
+        return True
+    try:
+        with open(path, "rb") as f:
+            head = f.read(6)
+    except OSError:
+        return False
+    return head.startswith(_COMPRESSED_MAGIC)
+
+
 class HostError(RuntimeError):
     pass
 

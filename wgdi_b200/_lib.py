@@ -49,8 +49,7 @@ def _declare(lib):
     lib.icl_host_alloc.argtypes = [vp, i64, C.POINTER(vp)]
     lib.icl_host_free.argtypes = [vp, vp]
     lib.icl_upload.argtypes = [vp, i64, i32, vp, vp, vp, vp]
-    lib.icl_pair_counts.argtypes = [vp, vp]
-    lib.icl_upload_from.argtypes = [vp, vp, i32, i32]
+    lib.icl_set_grading_table.argtypes = [vp, i32, vp]
     lib.icl_dp.argtypes = [vp, C.POINTER(icl_params), vp, vp]
     lib.icl_dp_begin.argtypes = [vp, C.POINTER(icl_params), vp, vp, vp]
     lib.icl_dp_end.argtypes = [vp]
@@ -69,7 +68,7 @@ def _declare(lib):
 
 
 EXPORTS = ("icl_backend", "icl_create", "icl_destroy", "icl_last_error", "icl_host_alloc", "icl_host_free",
-           "icl_upload", "icl_pair_counts", "icl_upload_from", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
+           "icl_upload", "icl_set_grading_table", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
            "icl_counters", "icl_stream")
 
 

@@ -20,6 +20,8 @@ import queue
 import threading
 from dataclasses import replace
 
+import numpy as np
+
 from .engine import ChainParams, IclEngine
 
 
@@ -34,6 +36,8 @@ class BatchRunner:
     def run(self, jobs, min_members: int = 1, consume=None):
         """jobs: sequence of (points, params) with points = dict(pair_id, loc1, loc2, grading, n_pairs) (host arrays;
         consecutive jobs that pass the SAME dict object reuse the upload) -> list of Blocks in job order.
+        A points dict with `grade_class` instead of `grading` (what `sweep_jobs` builds) is uploaded once as rank
+        classes and every job chains with ITS params.grading through the device's grading table.
         With `consume(job_index, blocks)` the blocks are handed over as zero-copy views of the engine's page-locked
         staging (valid only during the call — e.g. the file writer) and the list holds what `consume` returned."""
         jobs = list(jobs)
@@ -52,9 +56,12 @@ class BatchRunner:
                     return
                 pts, prm = jobs[i]
                 try:
+                    by_class = "grading" not in pts
                     if uploaded is not pts:
-                        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+                        eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grade_class" if by_class else "grading"],
+                                   pts["n_pairs"])
                         uploaded = pts
+                    eng.set_grading_table(prm.grading if by_class else None)
                     if consume is None:
                         results[i] = eng.run_resident(prm, min_members, copy=True)
                     else:
@@ -75,11 +82,28 @@ class BatchRunner:
 
 def sweep_jobs(points, gradings, mgs, pvalues, base: ChainParams | None = None):
     """The parameter sweep of config 5 over one comparison: one job per (grading, mg); the pvalue variants of a job
-    share its blocks (apply `Blocks.p_value() > pvalue` per variant).  Returns (jobs, [(grading, mg, pvalues)])."""
+    share its blocks (apply `Blocks.p_value() > pvalue` per variant).  Returns (jobs, [(grading, mg, pvalues)]).
+
+    `grading` enters the reference when the hits are graded (wgdi/run_colliearity.py:30-33,64-86): every point's value
+    changes with it, not only the divisor of the p value.  The rank CLASS of a hit does not depend on the values, so
+    `points` must carry `grade_class` (0 red / 1 blue / 2 rest, as synth.graded_points and mycollinearity.load_points
+    return it); the jobs share one upload of the classes and each chains with its own table."""
+    if "grade_class" not in points:
+        raise ValueError("sweep_jobs needs points['grade_class']: a grading sweep re-grades every hit")
     base = base or ChainParams()
+    by_class = {k: points[k] for k in ("pair_id", "loc1", "loc2", "grade_class", "n_pairs")}
     jobs, keys = [], []
     for g in gradings:
+        if len(g) <= int(np.max(points["grade_class"], initial=0)):
+            raise ValueError("grading has fewer values than there are rank classes")
         for mg in mgs:
-            jobs.append((points, replace(base, grading=tuple(g), mg1=int(mg[0]), mg2=int(mg[1]), pvalue=1.0)))
+            jobs.append((by_class, replace(base, grading=tuple(int(x) for x in g), mg1=int(mg[0]), mg2=int(mg[1]), pvalue=1.0)))
             keys.append((tuple(g), tuple(mg), tuple(pvalues)))
     return jobs, keys
+
+
+def regrade(points, grading):
+    """The points of a comparison as `-icl` with this `grading` would grade them (host copy; tests and checks)."""
+    out = dict(points)
+    out["grading"] = np.asarray(grading, np.int32)[points["grade_class"]]
+    return out

@@ -106,15 +106,17 @@ class block_info():
         raise NotImplementedError("only WGDI-format collinearity files (as written by -icl) are supported")
 
     def load_hits(self, gff1, gff2):
-        """base.newblast + blast_homo's trimming (block_info.py:149-150, :104-105): kept hits with their rank."""
-        if self.native:
+        """base.newblast + blast_homo's trimming (block_info.py:149-150, :104-105): kept hits with their rank.
+        The id columns are NEVER swapped here, whatever `blast_reverse` says: the reference turns the option into a bool
+        (wgdi/block_info.py:16) and hands that bool to base.newblast, whose test is `reverse == 'true'` (base.py:176) —
+        False for either bool.  Reproduced as is (drop-in; pinned by test_block_info_ignores_blast_reverse)."""
+        if self.native and not _host.is_compressed(self.blast):
             ids1 = _host.pack_strings(gff1.index)
             ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
-            hits = _host.read_m8(self.blast, self.blast_reverse, int(self.score), float(self.evalue), ids1, ids2)
+            hits = _host.read_m8(self.blast, False, int(self.score), float(self.evalue), ids1, ids2)
             g1, g2, bits = hits['g1'], hits['g2'], hits['bits']
         else:
-            blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2,
-                                  'true' if self.blast_reverse else 'false')
+            blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
             g1, g2, bits = blast['g1'].to_numpy(), blast['g2'].to_numpy(), blast[11].to_numpy()
         rank = rank_hits(g1, bits, self.repeat_number)
         keep = rank >= 0

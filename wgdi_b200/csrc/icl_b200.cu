@@ -36,6 +36,12 @@ using namespace icl;
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// grading classes -> grading values of the current parameter set (icl_set_grading_table)
+struct GradeTable {
+    int32_t n = 0;                   // 0 = the uploaded values are the gradings themselves
+    int32_t v[ICL_MAX_GRADE_CLASSES] = {};
+};
+
 struct icl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -45,10 +51,11 @@ struct icl_ctx {
     bool uploaded = false, dp_done = false;
     icl_params prm{};
     int bits1 = 1, bits2 = 1, bitsp = 1;
+    int32_t max_grad = 0;            // largest value of the uploaded grading array
+    GradeTable gtab{};               // icl_set_grading_table: uploaded values are class ids, G = table[class]
 
     // inputs in upload order
-    Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats, src_index;
-    bool has_src_index = false;      // upload came from icl_upload_from: src_index maps to the source context's upload
+    Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats;
     // sort
     Buf<uint64_t> key_a, key_b;
     Buf<uint32_t> idx_a, perm;
@@ -224,7 +231,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
 #endif
-    c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release(); c->src_index.release();
+    c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release();
     c->key_a.release(); c->key_b.release(); c->idx_a.release(); c->perm.release(); c->tmp.release();
     c->d_pair_off.release(); c->d_rb.release(); c->d_rmin.release(); c->d_nrows.release();
     c->d_item_order.release(); c->d_pair_order.release();
@@ -293,7 +300,6 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
 #endif
     c->n = n;
     c->P = P;
-    c->has_src_index = false;
     if (c->in_pair.reserve(st, n) || c->in_loc1.reserve(st, n) || c->in_loc2.reserve(st, n) || c->in_grad.reserve(st, n))
         return st.code;
     size_t b = (size_t)n * sizeof(int32_t);
@@ -308,6 +314,7 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
     if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_upload: negative coordinate or pair id outside [0, n_pairs)");
     if (hs[0] >= (1 << 26) || hs[1] >= (1 << 26)) return fail(c, ICL_ERR_LIMIT, "icl_upload: coordinates must be < 2^26");
     if (hs[3] > 255) return fail(c, ICL_ERR_LIMIT, "icl_upload: grading values must be <= 255");
+    c->max_grad = hs[3];
     c->bits1 = bits_for(hs[0]);
     c->bits2 = bits_for(hs[1]);
     c->bitsp = bits_for(P > 0 ? P - 1 : 0);
@@ -318,77 +325,18 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
 }
 
 // ------------------------------------------------------------------------------------------------
-// ABI: split one upload over several contexts of the same device (pipelined lanes, see wgdi_b200/pipeline.py)
+// ABI: grading classes.  The grading of a hit is a function of its per-query rank class only
+// (wgdi/run_colliearity.py:64-86: red / blue / rest), so a parameter sweep over `grading` re-maps the classes of the
+// SAME upload instead of uploading again.
 // ------------------------------------------------------------------------------------------------
-extern "C" int icl_pair_counts(icl_ctx *c, int64_t *counts) {
-    if (!c || !counts) return ICL_ERR_ARG;
-    if (!c->uploaded) return fail(c, ICL_ERR_STATE, "icl_pair_counts: icl_upload has not succeeded");
-    Status &st = c->st;
-#ifndef ICL_EMU
-    ICL_CUDA(st, cudaSetDevice(c->device));
-#endif
-    const int32_t P = c->P;
-    if (P == 0) return ICL_OK;
-    Buf<int32_t> cnt;
-    if (cnt.reserve(st, P)) return st.code;
-    ICL_CUDA(st, dev_memset(cnt.p, 0, (size_t)P * sizeof(int32_t), c->stream));
-    {
-        const int32_t *ip = c->in_pair.p;
-        int32_t *d = cnt.p;
-        ICL_CUDA(st, foreach(c->stream, c->n, ICL_LAMBDA(int64_t i) { atomic_add_i32(&d[ip[i]], 1); }));
-    }
-    std::vector<int32_t> h((size_t)P);
-    ICL_CUDA(st, d2h(h.data(), cnt.p, (size_t)P * sizeof(int32_t), c->stream));
-    ICL_CUDA(st, dev_sync(c->stream));
-    cnt.release();
-    for (int32_t p = 0; p < P; p++) counts[p] = h[p];
-    return ICL_OK;
-}
-
-extern "C" int icl_upload_from(icl_ctx *dst, icl_ctx *src, int32_t pair_lo, int32_t pair_hi) {
-    if (!dst || !src || dst == src) return ICL_ERR_ARG;
-    dst->uploaded = dst->dp_done = dst->dp_begun = false;
-    if (!src->uploaded) return fail(dst, ICL_ERR_STATE, "icl_upload_from: the source context has no upload");
-    if (dst->device != src->device) return fail(dst, ICL_ERR_ARG, "icl_upload_from: contexts live on different devices");
-    if (pair_lo < 0 || pair_hi < pair_lo || pair_hi > src->P) return fail(dst, ICL_ERR_ARG, "icl_upload_from: bad pair range");
-    Status &st = dst->st;
-#ifndef ICL_EMU
-    ICL_CUDA(st, cudaSetDevice(dst->device));
-#endif
-    cudaStream_t s = dst->stream;
-    const int64_t n = src->n;
-    if (dst->acc_flag.reserve(st, n + 2) || dst->blkidx.reserve(st, n + 2)) return st.code;
-    {
-        const int32_t *ip = src->in_pair.p;
-        uint32_t *flag = dst->acc_flag.p;
-        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) { flag[i] = (ip[i] >= pair_lo && ip[i] < pair_hi) ? 1u : 0u; }));
-    }
-    if (exclusive_sum_u32(st, dst->tmp, dst->acc_flag.p, dst->blkidx.p, n, s)) return st.code;
-    uint32_t m = 0;
-    ICL_CUDA(st, d2h(&m, dst->blkidx.p + n, sizeof(uint32_t), s));
-    ICL_CUDA(st, dev_sync(s));
-    dst->n = m;
-    dst->P = pair_hi - pair_lo;
-    if (dst->in_pair.reserve(st, m) || dst->in_loc1.reserve(st, m) || dst->in_loc2.reserve(st, m) || dst->in_grad.reserve(st, m) ||
-        dst->src_index.reserve(st, m))
-        return st.code;
-    {
-        // order-preserving compaction: equal coordinates keep the source's upload order (stable sort later, H22)
-        const int32_t *ip = src->in_pair.p, *i1 = src->in_loc1.p, *i2 = src->in_loc2.p, *ig = src->in_grad.p;
-        const uint32_t *pos = dst->blkidx.p;
-        int32_t *op = dst->in_pair.p, *o1 = dst->in_loc1.p, *o2 = dst->in_loc2.p, *og = dst->in_grad.p, *oi = dst->src_index.p;
-        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
-            if (ip[i] < pair_lo || ip[i] >= pair_hi) return;
-            const uint32_t k = pos[i];
-            op[k] = ip[i] - pair_lo; o1[k] = i1[i]; o2[k] = i2[i]; og[k] = ig[i]; oi[k] = (int32_t)i;
-        }));
-    }
-    dst->bits1 = src->bits1;
-    dst->bits2 = src->bits2;
-    dst->bitsp = bits_for(dst->P > 0 ? dst->P - 1 : 0);
-    dst->has_src_index = true;
-    dst->uploaded = true;
-    st.code = 0;
+extern "C" int icl_set_grading_table(icl_ctx *c, int32_t n_classes, const int32_t *values) {
+    if (!c) return ICL_ERR_ARG;
+    if (n_classes < 0 || n_classes > ICL_MAX_GRADE_CLASSES || (n_classes > 0 && !values))
+        return fail(c, ICL_ERR_ARG, "icl_set_grading_table: bad argument");
+    for (int32_t k = 0; k < n_classes; k++)
+        if (values[k] < 0 || values[k] > 255) return fail(c, ICL_ERR_LIMIT, "icl_set_grading_table: grading values must be in 0..255");
+    c->gtab.n = n_classes;
+    for (int32_t k = 0; k < ICL_MAX_GRADE_CLASSES; k++) c->gtab.v[k] = k < n_classes ? values[k] : 0;
     return ICL_OK;
 }
 
@@ -422,12 +370,14 @@ static int phase_sort(icl_ctx *c) {
         const int32_t *ig = c->in_grad.p;
         int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p, *ps = c->pair_s.p, *G = c->G.p;
         const uint64_t m1 = (1ull << c->bits1) - 1, m2 = (1ull << c->bits2) - 1;
+        const GradeTable gt = c->gtab;
         ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
             uint64_t k = key[i];
             l2[i] = (int32_t)(k & m2);
             l1[i] = (int32_t)((k >> sh2) & m1);
             ps[i] = (int32_t)(k >> shp);
-            G[i] = ig[perm[i]];
+            const int32_t g = ig[perm[i]];
+            G[i] = gt.n ? gt.v[g] : g;                        // class id -> grading of this parameter set
         }));
         int64_t *off = c->d_pair_off.p;
         ICL_CUDA(st, foreach(s, (int64_t)P + 1, ICL_LAMBDA(int64_t p) {
@@ -1233,6 +1183,8 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
     if (prm->mg1 < 2 || prm->mg1 > 255 || prm->mg2 < 2 || prm->mg2 > 255)
         return fail(c, ICL_ERR_LIMIT, "icl_dp: mg values must be in 2..255");
     if (prm->g0 <= 0 || prm->over_gap < 1) return fail(c, ICL_ERR_ARG, "icl_dp: grading[0] and over_gap must be positive");
+    if (c->gtab.n > 0 && c->n > 0 && c->max_grad >= c->gtab.n)
+        return fail(c, ICL_ERR_ARG, "icl_dp: a grading table is set but the upload holds a class id outside it");
     Status &st = c->st;
     st.code = 0;
 #ifndef ICL_EMU
@@ -2944,7 +2896,6 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
         const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;
         const int32_t *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_item = c->b_item.p, *members = c->members.p;
         const int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p;
-        const int32_t *srcidx = c->has_src_index ? c->src_index.p : nullptr;
         const int64_t *b_N1 = c->b_N1.p;
         const double *b_a = c->b_a.p;
         icl_blocks o = dv;
@@ -2974,7 +2925,7 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
             const int32_t i = members[b_moff[o_src[lo]] + (uint32_t)(t - omoff[lo])];
             o.loc1[t] = l1[i];
             o.loc2[t] = l2[i];
-            o.member_idx[t] = srcidx ? srcidx[perm[i]] : (int32_t)perm[i];
+            o.member_idx[t] = (int32_t)perm[i];
         }));
         if (NBo == 0) ICL_CUDA(st, dev_memset(dv.member_off, 0, sizeof(int64_t), s));
     }

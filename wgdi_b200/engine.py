@@ -195,6 +195,16 @@ class IclEngine:
         self._check(self.lib.icl_upload(self.ctx, n, int(n_pairs), *[x.ctypes.data for x in a]))
         self.n, self.n_pairs = n, int(n_pairs)
 
+    def set_grading_table(self, values=None):
+        """Sweeps over `grading`: with a table the `grading` array of `upload` holds rank-class ids (0 red, 1 blue, 2 rest,
+        wgdi/run_colliearity.py:64-86) and every later DP chains with values[class] — same upload, new gradings.
+        None restores plain grading values."""
+        if values is None:
+            self._check(self.lib.icl_set_grading_table(self.ctx, 0, None))
+        else:
+            v = np.ascontiguousarray(values, np.int32)
+            self._check(self.lib.icl_set_grading_table(self.ctx, len(v), v.ctypes.data))
+
     def dp(self, params: ChainParams):
         """Both DP directions; returns (key_fwd, key_rev): int32 scores, every pair segment in REVERSED point
         order (widened to int64: the array pandas' nargsort(ascending=False) hands to numpy.argsort)."""

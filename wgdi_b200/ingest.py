@@ -101,13 +101,14 @@ def grade_hits_native(q, bits, n_query, multiple, repeat_number, grading):
     return out
 
 
-def grade_hits_chromosomes(name_rank, g1, g2, pair_code, bits, multiple, repeat_number, grading):
+def grade_hits_chromosomes(name_rank, g1, g2, pair_code, bits, multiple, repeat_number, grading, classes=False):
     """`deal_blast_for_chromosomes` (wgdi/run_colliearity.py:42-57): stable sort by (query id string ascending,
     bit score descending) (:44); cumcount per subject gene inside each chromosome pair in that order (:46); keep
     cumcount <= repeat_number (:47); grading by pd.cut over bins [-1, 0, multiple, repeat_number] (:48-53).
     Every sort in it is stable, so there is no tie hazard here.  name_rank[g] = rank of gene g's id among the query
     ids in string order.  Returns (grading per hit, 0 = dropped; row order of the frame the reference continues
-    with — equal (loc1, loc2) keep THIS order in the later stable sort of :164-166, hazard H22)."""
+    with — equal (loc1, loc2) keep THIS order in the later stable sort of :164-166, hazard H22).
+    classes=True: 1 / 2 / 3 for the three bins instead of the grading values (the caller looks the values up)."""
     rn, blue = int(repeat_number), int(multiple)
     if not (0 < blue < rn):
         raise ValueError("bins must increase monotonically.")                  # pd.cut, as in the reference
@@ -123,10 +124,11 @@ def grade_hits_chromosomes(name_rank, g1, g2, pair_code, bits, multiple, repeat_
     gid = np.cumsum(np.r_[True, ks[1:] != ks[:-1]]) - 1 if n else np.zeros(0, np.int64)
     cum = np.empty(n, np.int64)
     cum[order[o2]] = np.arange(n) - start[gid] if n else 0
+    val = [1, 2, 3] if classes else grading
     grade = np.zeros(n, np.int64)
-    grade[cum == 0] = grading[0]
-    grade[(cum > 0) & (cum <= blue)] = grading[1]
-    grade[(cum > blue) & (cum <= rn)] = grading[2]
+    grade[cum == 0] = val[0]
+    grade[(cum > 0) & (cum <= blue)] = val[1]
+    grade[(cum > blue) & (cum <= rn)] = val[2]
     return grade, order
 
 

@@ -58,7 +58,9 @@ class mycollinearity():
     # ---- ingest: wgdi/run_colliearity.py:88-121 -------------------------------------------------
     def load_points(self):
         """Read lens/gff/blast, filter, grade and group: returns a dict with the graded points
-        (pair_id, loc1, loc2, grading), the pair names in output order and the gene tables."""
+        (pair_id, loc1, loc2, grading, grade_class), the pair names in output order and the gene tables.
+        `grade_class` is the rank class behind every grading (0 red / 1 blue / 2 rest, :64-86 resp. the bins of :48-53):
+        a sweep over `grading` keeps the classes and swaps the values (batch.sweep_jobs)."""
         lens1 = base.newlens(self.lens1, 'order')
         lens2 = base.newlens(self.lens2, 'order')
         same = self.gff2 == self.gff1 and self.lens2 == self.lens1       # self comparison: parse the tables once
@@ -70,7 +72,7 @@ class mycollinearity():
         mode = self.comparison.lower()                    # :108-111
         if mode not in ('genomes', 'chromosomes'):
             raise ValueError(f"comparison = {self.comparison}: expected 'genomes' or 'chromosomes'")
-        if self.native:
+        if self.native and not _host.is_compressed(self.blast):    # compressed tables: pandas decompresses (base.py:174)
             ids1 = _host.pack_strings(gff1.index)
             ids2 = ids1 if same else _host.pack_strings(gff2.index)
             hits = _host.read_m8(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2)
@@ -85,21 +87,22 @@ class mycollinearity():
             name_rank = np.empty(len(gff1), np.int64)
             name_rank[np.argsort(t1['name'], kind='stable')] = np.arange(len(gff1))
             grade, order = grade_hits_chromosomes(name_rank, g1, g2, t1['chr_code'][g1] * len(t2['chr_names']) + t2['chr_code'][g2],
-                                                  bits, int(self.multiple), int(self.repeat_number), self.grading)
+                                                  bits, int(self.multiple), int(self.repeat_number), self.grading, classes=True)
             g1, g2, grade = g1[order], g2[order], grade[order]
         elif self.native:
-            grade = grade_hits_native(g1, bits, len(gff1), int(self.multiple), int(self.repeat_number), self.grading)
+            grade = grade_hits_native(g1, bits, len(gff1), int(self.multiple), int(self.repeat_number), [1, 2, 3])
         else:
-            grade = grade_hits(g1, bits, int(self.multiple), int(self.repeat_number), self.grading)
+            grade = grade_hits(g1, bits, int(self.multiple), int(self.repeat_number), [1, 2, 3])
         ok = grade > 0                                    # :86 / :57
-        g1, g2, grade = g1[ok], g2[ok], grade[ok]
+        g1, g2, cls = g1[ok], g2[ok], grade[ok] - 1
+        grade = np.asarray(self.grading, np.int64)[cls]
         print(f"The filtered homologous gene pairs are {len(g1)}.\n")      # :112
         if len(g1) < 1:
             print("Stopped!\n\nIt may be that the id1 and id2 in the BLAST file do not match with (gff1, lens1) and (gff2, lens2).")
             sys.exit(1)                                   # :113-115
         pid, names = pair_ids(t1['chr_names'], t2['chr_names'], t1['chr_code'][g1], t2['chr_code'][g2])
         return dict(pair_id=pid, loc1=t1['order'][g1].astype(np.int32), loc2=t2['order'][g2].astype(np.int32),
-                    grading=grade.astype(np.int32), pair_names=names, genes1=t1, genes2=t2)
+                    grading=grade.astype(np.int32), grade_class=cls.astype(np.int32), pair_names=names, genes1=t1, genes2=t2)
 
     # ---- wgdi/run_colliearity.py:88-156 ----------------------------------------------------------
     def run(self):

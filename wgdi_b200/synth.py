@@ -233,10 +233,12 @@ def write_dataset(ds: Dataset, outdir: str, savefile: str | None = None, process
     return conf
 
 
-def graded_points(ds: Dataset) -> dict:
+def graded_points(ds: Dataset, grading=None) -> dict:
     """Host ingest of the integer-coded BLAST table: the filters of wgdi/base.py:178-180, the grading of
     wgdi/run_colliearity.py:59-86 and the (chr1, chr2) grouping of :117-121, vectorised — the same code
-    path `mycollinearity.load_points` takes after parsing the files."""
+    path `mycollinearity.load_points` takes after parsing the files.
+    `grading`: grade with these values instead of the config's, straight through `grade_hits` (what `-icl` with that
+    conf value does; the independent check of the class-table path of a grading sweep)."""
     import pandas as pd
     from .ingest import grade_hits, pair_ids
     c = ds.cfg
@@ -247,13 +249,19 @@ def graded_points(ds: Dataset) -> dict:
     q, t = ds.q[rows], ds.t[rows]
     first = ~pd.Series(q.astype(np.int64) * ds.g2.n + t).duplicated(keep="first").to_numpy()
     rows, q, t = rows[first], q[first], t[first]
-    grade = grade_hits(q, ds.bits[rows], c.multiple, ds.repeat_number, list(c.grading))
-    ok = grade > 0
-    q, t, grade = q[ok], t[ok], grade[ok]
+    # rank class of every hit (0 red, 1 blue, 2 rest; run_colliearity.py:64-86) — the grading is a table lookup on it, so a
+    # sweep over `grading` keeps the classes and swaps the table (icl_set_grading_table)
+    cls = grade_hits(q, ds.bits[rows], c.multiple, ds.repeat_number, [1, 2, 3])
+    ok = cls > 0
+    q, t, cls = q[ok], t[ok], cls[ok] - 1
+    grade = np.asarray(c.grading, np.int64)[cls]
+    if grading is not None:
+        direct = grade_hits(ds.q[rows], ds.bits[rows], c.multiple, ds.repeat_number, list(grading))
+        grade = direct[ok]
     names1 = sorted(ds.g1.chr_names)
     names2 = sorted(ds.g2.chr_names)
     code1 = np.array([names1.index(x) for x in ds.g1.chr_names])[ds.g1.chr_idx[q]]
     code2 = np.array([names2.index(x) for x in ds.g2.chr_names])[ds.g2.chr_idx[t]]
     pid, names = pair_ids(names1, names2, code1, code2)
     return dict(pair_id=pid, loc1=ds.g1.order[q].astype(np.int32), loc2=ds.g2.order[t].astype(np.int32),
-                grading=grade.astype(np.int32), n_pairs=len(names), pair_names=names)
+                grading=grade.astype(np.int32), grade_class=cls.astype(np.int32), n_pairs=len(names), pair_names=names)
