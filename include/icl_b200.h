@@ -209,6 +209,17 @@ int icl_debug_dp(icl_ctx *ctx, int32_t dir, int32_t *score, int32_t *pred, int32
  * values, segment-local indices into the REVERSED score arrays — the format icl_extract takes from the host). */
 int icl_debug_order(icl_ctx *ctx, int32_t *argsort);
 
+/* Probe / test: numpy's argsort of flavour `mode` (one of ICL_RANK_NUMPY_*) of arbitrary int32 key segments, computed by
+ * the same kernels and launch classes as icl_rank_device: keys[seg_off[j] .. seg_off[j+1]) -> argsort_out (segment-local
+ * indices).  Host arrays; independent of the upload.  wgdi_b200/engine.py probes every launch size class with it against
+ * the running numpy before it lets the device rank. */
+int icl_debug_rank_keys(icl_ctx *ctx, int32_t mode, int32_t n_segments, const int64_t *seg_off, const int32_t *keys,
+                        int32_t *argsort_out);
+
+/* Test / verification: the key arrays the last icl_rank_device (numpy flavours) sorted — the scores of every item in
+ * REVERSED point order, forward items then anti-diagonal ones (2 n values: what icl_dp exports when given buffers). */
+int icl_debug_keys(icl_ctx *ctx, int32_t *keys);
+
 /* Device time (ms, CUDA events on the context's stream) of the phases of the most recent
  * icl_dp / icl_extract calls; see ICL_T_* for the slots.  Returns the number of slots written. */
 #define ICL_T_SORT 0      /* key build + radix sort + layout */
@@ -223,9 +234,10 @@ int icl_debug_order(icl_ctx *ctx, int32_t *argsort);
 #define ICL_T_COUNT 9
 int icl_timings(icl_ctx *ctx, double *ms, int32_t n_slots);
 
-/* Counters of the most recent icl_dp: [0] edges enumerated, [1] kernels launched by icl_dp,
- * [2] kernels launched by icl_extract, [3] total dense rows, [4] largest window span (positions),
- * [5] DP kernel used (1 = shared-memory ring, 0 = generic). */
+/* Counters of the most recent calls: [0] edges enumerated, [1] kernels of this library launched by icl_dp (counted at
+ * every launch, CUB excluded), [2] the same for icl_extract, [3] total dense rows, [4] largest window span (positions),
+ * [5] DP kernel used (1 = shared-memory ring, 0 = generic), [6] kernels launched by icl_rank_device, [7] CUB device-wide
+ * calls (radix sorts, scans) of the three together.  Returns the number of slots written (at most 8). */
 int icl_counters(icl_ctx *ctx, int64_t *out, int32_t n_slots);
 
 /* The CUDA stream (cudaStream_t) every kernel and copy of `ctx` is issued on, for callers that bracket calls with

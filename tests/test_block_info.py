@@ -38,6 +38,8 @@ if os.environ.get("FAKE") == "1":
 opts = [(k, v) for k, v in base.load_conf("bi.conf", "blockinfo") if k != "savefile"] + [("savefile", "got.csv")]
 if os.environ.get("INGEST"):
     opts.append(("ingest", os.environ["INGEST"]))
+if os.environ.get("BI_REVERSE"):
+    opts.append(("blast_reverse", os.environ["BI_REVERSE"]))
 with contextlib.redirect_stdout(io.StringIO()):
     b = block_info(opts)
     b.run()
@@ -95,6 +97,15 @@ def test_bi_host_logic_with_fake_backend(case, ingest):
     """Parsing, ranking with the reference's tie order, frame assembly and CSV text — device statistics from a
     numpy stand-in injected by the test."""
     _run_child(_PRODUCT_CHILD % (ROOT, ROOT), case, {"FAKE": "1", "INGEST": ingest})
+
+
+@pytest.mark.parametrize("ingest", ["native", "pandas"])
+def test_block_info_ignores_blast_reverse(ingest):
+    """`blast_reverse = true` changes nothing in the reference's -bi: the option becomes a bool (wgdi/block_info.py:16) and
+    base.newblast compares it with the string 'true' (base.py:176), so the id columns are never swapped.  Checked by
+    running the unmodified reference on this fixture with the key set: it writes expected.blockinfo.csv byte for byte.
+    The drop-in does the same on both ingest paths."""
+    _run_child(_PRODUCT_CHILD % (ROOT, ROOT), "tiny", {"FAKE": "1", "INGEST": ingest, "BI_REVERSE": "true"})
 
 
 def test_bi_library_exports_declared_symbols():

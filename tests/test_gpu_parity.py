@@ -282,10 +282,12 @@ def test_sharded_equals_unsharded(gpu_engine):
             assert (getattr(merged, f) == getattr(whole, f)).all(), f
 
 
-@pytest.mark.parametrize("name,scale,mg", [("C1", 1.0, (25, 25)), ("C3", 0.3, (40, 40)), ("C4", 0.25, (50, 50))])
+@pytest.mark.parametrize("name,scale,mg", [("C1", 1.0, (25, 25)), ("C3", 1.0, (25, 25)), ("C4", 1.0, (25, 25)),
+                                           ("C3", 0.3, (40, 40)), ("C4", 0.25, (50, 50))])
 def test_other_baseline_configs_match_oracle(gpu_engine, name, scale, mg):
-    """BASELINE.json configs 1 (full size: 25 pairs of ~40k points), 3 (cross-species) and 4 (wheat-like) at a
-    bounded scale, with the three `mg` settings of config 5's sweep: block lists identical to the C oracle."""
+    """BASELINE.json configs 1 (25 pairs of ~40k points), 3 (cross-species, ~4.7 M hits, 144 pairs) and 4 (wheat-like,
+    ~9.9 M hits, 441 pairs) at FULL size with their own parameters, plus 3 and 4 at a bounded scale with the other two
+    `mg` settings of config 5's sweep: block lists identical to the C oracle, block by block."""
     from wgdi_b200 import synth
     from wgdi_b200.engine import ChainParams
     ds = synth.make_dataset(name, scale=scale)
@@ -350,6 +352,35 @@ def test_batch_runner_equals_one_engine(gpu_engine):
         _compare_with_oracle(got[j], oracle_blocks(synth.graded_points(dss[ci], grading=g), jobs[j][1]))
     # 50,40,25 against 50,30,25 at the same mg: different blue values, different result
     assert len(got[0]) != len(got[3]) or (got[0].score != got[3].score).any()
+
+
+def test_config5_comparison_full_sweep_matches_oracle(gpu_engine):
+    """BASELINE.json config 5: one of the 28 cross-species comparisons at full size through the batch runner with all
+    six (grading, mg) device jobs of the sweep — the three pvalue variants of a job share its blocks — every job
+    identical to the oracle run on points graded FROM SCRATCH with that job's grading (run_colliearity.py:64-86), and the
+    two gradings give different results at every mg."""
+    from wgdi_b200 import synth
+    from wgdi_b200.batch import BatchRunner, sweep_jobs
+    ds = synth.make_dataset(synth.config5_comparison(9))
+    pts = synth.graded_points(ds)
+    assert len(pts["loc1"]) > 1_000_000
+    jobs, keys = sweep_jobs(pts, synth.C5_GRADINGS, synth.C5_MGS, synth.C5_PVALUES)
+    assert len(jobs) == 6
+    runner = BatchRunner(0, depth=2)
+    try:
+        got = runner.run(jobs, min_members=1)
+    finally:
+        runner.close()
+    own = {g: synth.graded_points(ds, grading=g) for g in synth.C5_GRADINGS}
+    assert (own[(50, 40, 25)]["grading"] != own[(50, 30, 25)]["grading"]).any()
+    for (_, prm), (g, mg, pvs), b in zip(jobs, keys, got):
+        exp = oracle_blocks(own[g], prm)
+        _compare_with_oracle(b, exp)
+        p = b.p_value()
+        kept = [int((~(p > pv) & (b.m >= 5)).sum()) for pv in pvs]            # what the writer keeps per pvalue variant
+        assert kept[0] <= kept[1] <= kept[2] == int((b.m >= 5).sum())
+    for j in range(3):                                                          # same mg, the two gradings
+        assert len(got[j]) != len(got[3 + j]) or (got[j].score != got[3 + j].score).any()
 
 
 def _random_comparison(rng, n_pairs, n_rows, n_cols, per_row, diag_frac, dup_frac):
@@ -669,3 +700,79 @@ def test_full_size_C2_matches_oracle_and_properties(gpu_engine):
     assert (blocks.m <= blocks.L).all() and (blocks.N >= blocks.m).all() and (blocks.m >= 3).all()
     order_key = blocks.pair.astype(np.int64) * 2 + blocks.dir
     assert (np.diff(order_key) >= 0).all()
+
+
+def test_rank_probe_covers_every_launch_class(gpu_engine):
+    """The start-up probe that lets the device rank sorts one tie-heavy segment per launch size class of the rank kernels
+    (<= 16 000 keys, <= 34 000, <= 65 535, longer) with the device and with the running numpy — and it discriminates:
+    the other SIMD flavour fails it."""
+    from wgdi_b200.engine import IclEngine
+    kind = gpu_engine.numpy_sort_kind()
+    if kind is None:
+        pytest.skip("numpy in this process is none of the reproduced flavours")
+    mode = {"numpy_scalar": 1, "numpy_avx512": 2, "numpy_avx2": 3}[kind]
+    sizes = IclEngine.PROBE_CLASS_SIZES
+    assert max(sizes) > 65535 and any(34000 < m <= 65535 for m in sizes) and any(16000 < m <= 34000 for m in sizes)
+    assert gpu_engine._probe_size_classes(mode)
+    other = {1: 2, 2: 3, 3: 2}[mode]
+    assert not gpu_engine._probe_size_classes(other)
+    # the probe entry point on segments of every size 0..300 and on empty input
+    rng = np.random.default_rng(5)
+    segs = [IclEngine._score_like_keys(rng, m, m % 3) for m in range(0, 300)]
+    off = np.r_[0, np.cumsum([len(x) for x in segs])].astype(np.int64)
+    keys = np.concatenate(segs).astype(np.int32)
+    got = np.zeros(len(keys), np.int32)
+    gpu_engine._check(gpu_engine.lib.icl_debug_rank_keys(gpu_engine.ctx, mode, len(segs), off.ctypes.data, keys.ctypes.data, got.ctypes.data))
+    for a, b, x in zip(off[:-1], off[1:], segs):
+        assert (got[a:b] == x.astype(np.int64).argsort(kind="quicksort")).all(), b - a
+    assert gpu_engine.lib.icl_debug_rank_keys(gpu_engine.ctx, mode, 0, off.ctypes.data, None, None) == 0
+    assert gpu_engine.lib.icl_debug_rank_keys(gpu_engine.ctx, 0, 1, off.ctypes.data, keys.ctypes.data, got.ctypes.data) == -1
+
+
+def test_rank_verify_switch_and_forced_hand_back(gpu_engine, monkeypatch):
+    """ICL_B200_RANK_VERIFY re-sorts a sample of the device-ranked segments with numpy every step; a rank that is not
+    numpy's (forced here: the other SIMD flavour) is caught, the comparison goes to the host rank and the blocks are the
+    host-ranked ones.  ICL_B200_XS_FORCE_GIVEUP drives the rank kernel's give-up path (s_giveup -> host_flag ->
+    ICL_ERR_STATE) and the engine's hand-back to numpy."""
+    from wgdi_b200 import engine, synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    kind = gpu_engine.numpy_sort_kind()
+    if kind is None:
+        pytest.skip("numpy in this process is none of the reproduced flavours")
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    gpu_engine.rank_mode = "host"
+    try:
+        ref = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    finally:
+        gpu_engine.rank_mode = "auto"
+    fields = ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx")
+    monkeypatch.setenv("ICL_B200_RANK_VERIFY", "1")
+    eng = IclEngine(0)
+    try:
+        assert eng.rank_verify == 32
+        got = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+        assert eng.rank_verified_segments >= 8 and eng.rank_verify_failures == 0 and eng.host_rank_fallbacks == 0
+        assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)
+        if kind != "numpy_scalar":
+            eng.rank_mode = "numpy_avx2" if kind == "numpy_avx512" else "numpy_avx512"      # not this numpy's order
+            got = eng.run_resident(prm)
+            assert eng.rank_verify_failures == 1 and engine._NP_KIND[0] is None
+            assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)          # ranked by numpy after all
+            eng.rank_mode = "auto"
+            got = eng.run_resident(prm)                                                     # the process stays on the host rank
+            assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)
+    finally:
+        eng.close()
+        engine._NP_KIND.clear()
+    monkeypatch.delenv("ICL_B200_RANK_VERIFY")
+    if kind != "numpy_scalar":
+        monkeypatch.setenv("ICL_B200_XS_FORCE_GIVEUP", "1")
+        eng = IclEngine(0)
+        try:
+            eng.upload(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"])
+            got = eng.run_resident_device_rank(prm, mode=kind)
+            assert eng.host_rank_fallbacks == 1
+            assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)
+        finally:
+            eng.close()

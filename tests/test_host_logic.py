@@ -176,6 +176,9 @@ if emu:
 from wgdi_b200.run_colliearity import mycollinearity
 import os
 conf = open("icl.conf").read().replace("expected.collinearity.txt", "got.txt")
+if os.environ.get("ICL_TEST_GZ"):                                     # the compressed table, as pandas would read it
+    os.remove("blast.m8")
+    conf = conf.replace("./blast.m8", "./blast.m8.gz")
 if os.environ.get("ICL_TEST_DEVICES"):
     conf += "devices = " + os.environ["ICL_TEST_DEVICES"] + "\n"      # chromosome pairs sharded over several engines
 open("icl.conf", "w").write(conf)
@@ -188,12 +191,14 @@ print("OK" if open("got.txt").read() == open("expected.collinearity.txt").read()
 """
 
 
-def run_e2e_child(case, emu_path, devices=None):
+def run_e2e_child(case, emu_path, devices=None, gz=False):
     with tempfile.TemporaryDirectory() as d:
         stage_e2e(case, d)
         env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
         if devices:
             env["ICL_TEST_DEVICES"] = devices
+        if gz:
+            env["ICL_TEST_GZ"] = "1"
         r = subprocess.run([sys.executable, "-c", _E2E_CHILD % (ROOT, emu_path)], cwd=d, env=env,
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
@@ -208,6 +213,15 @@ def test_drop_in_driver_writes_reference_file_emu(case):
     reproduces the file the unmodified reference wrote."""
     from wgdi_b200 import build
     run_e2e_child(case, build.build_emu(os.path.join(ROOT, "tests", "_emu")))
+
+
+def test_drop_in_driver_reads_compressed_blast_emu():
+    """`blast = table.m8.gz`: the reference reads the table with pandas, which decompresses by extension (base.py:174);
+    the native parser maps raw bytes, so the driver routes compressed tables through the pandas reader — same file."""
+    from wgdi_b200 import _host, build
+    assert _host.is_compressed(os.path.join(ROOT, "tests", "golden", "e2e_tiny", "blast.m8.gz"))
+    assert not _host.is_compressed(os.path.join(ROOT, "tests", "golden", "e2e_tiny", "genome1.gff"))
+    run_e2e_child("tiny", build.build_emu(os.path.join(ROOT, "tests", "_emu")), gz=True)
 
 
 def test_drop_in_driver_sharded_over_devices_emu():

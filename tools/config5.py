@@ -26,17 +26,7 @@ from wgdi_b200.batch import BatchRunner, sweep_jobs
 from wgdi_b200.engine import ChainParams
 from wgdi_b200.shard import lpt_assign
 
-GRADINGS = [(50, 40, 25), (50, 30, 25)]
-MGS = [(25, 25), (40, 40), (50, 50)]
-PVALUES = [0.05, 0.2, 1.0]
-SPECIES = [(25_000, 7), (28_000, 9), (30_000, 10), (33_000, 12), (36_000, 13), (39_000, 16), (42_000, 17), (45_000, 19)]
-
-
-def comparison_config(ci, a, b):
-    (ga, ca), (gb, cb) = SPECIES[a], SPECIES[b]
-    genes = (ga + gb) // 2
-    return synth.SynthConfig(f"c5_{a}_{b}", 20260500 + ci, n_anc=int(genes / 2 / 0.6), k=2, n_chr1=ca, n_chr2=cb,
-                             self_cmp=False, target_points=int(genes * 60))
+GRADINGS, MGS, PVALUES, SPECIES = synth.C5_GRADINGS, synth.C5_MGS, synth.C5_PVALUES, synth.C5_SPECIES
 
 
 def main():
@@ -49,7 +39,7 @@ def main():
     t0 = time.perf_counter()
     comps, cfgs = [], []
     for ci, (a, b) in enumerate(itertools.combinations(range(len(SPECIES)), 2)):
-        cfg = comparison_config(ci, a, b)
+        cfg = synth.config5_comparison(ci)
         cfgs.append(cfg)
         comps.append(synth.graded_points(synth.make_dataset(cfg, scale=args.scale)))
     n_hits = [len(c["loc1"]) for c in comps]

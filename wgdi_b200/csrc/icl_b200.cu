@@ -61,9 +61,9 @@ struct icl_ctx {
     Buf<uint32_t> idx_a, perm;
     Buf<uint8_t> tmp;
     // layout
-    Buf<int64_t> d_pair_off, d_rb;
+    Buf<int64_t> d_pair_off, d_rb, d_seg_off;      // d_seg_off[2P + 1]: V-space start of every (pair, direction) item
     Buf<int32_t> d_rmin, d_nrows, d_item_order, d_pair_order;
-    std::vector<int64_t> h_pair_off, h_rb;
+    std::vector<int64_t> h_pair_off, h_rb, h_seg_off;
     std::vector<int32_t> h_rmin, h_nrows, h_item_order, h_pair_order;
     int64_t R = 0;      // dense rows incl. one sentinel per pair (forward); the mirrored index follows at +R
     Buf<int32_t> loc1s, loc2s, pair_s, rowptr, X1, X2, G, itemof, mmap, imap;
@@ -77,7 +77,8 @@ struct icl_ctx {
     Buf<long long> chain_dbg;
     int32_t *sq_fwd = nullptr, *sq_rev = nullptr, *sq_queue = nullptr;   // streaming targets of the current icl_dp_begin (host, device-visible)
     bool streamed = false, dp_begun = false;
-    bool order_on_device = false;    // icl_rank_device filled order_in (non-reference tie order)
+    bool order_on_device = false;    // icl_rank_device filled order_in
+    bool keys_on_device = false;     // ... from score32 (numpy flavours)
     int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
@@ -108,6 +109,16 @@ struct icl_ctx {
     Timer timers[ICL_T_COUNT];
     int64_t counters[4] = {0, 0, 0, 0};
     int64_t counters_ext[2] = {0, 0};
+    int64_t n_own[3] = {0, 0, 0}, n_cub[3] = {0, 0, 0};   // kernels / CUB calls of the last icl_dp, icl_rank_device, icl_extract
+};
+
+// counts the launches an ABI call makes (slot 0 icl_dp, 1 icl_rank_device, 2 icl_extract)
+struct LaunchScope {
+    icl_ctx *c;
+    int slot;
+    LaunchCount at;
+    LaunchScope(icl_ctx *c_, int slot_) : c(c_), slot(slot_), at(launch_count()) { c->n_own[slot] = c->n_cub[slot] = 0; }
+    ~LaunchScope() { c->n_own[slot] = launch_count().own - at.own; c->n_cub[slot] = launch_count().cub - at.cub; }
 };
 
 static std::string g_create_error;
@@ -168,6 +179,7 @@ static int input_stats(icl_ctx *c) {
     if (c->n > 0) {
         int64_t blocks = std::min<int64_t>((c->n + 255) / 256, 148 * 8);
         k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, c->P, c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p, c->stats.p);
+        ICL_COUNT_KERNEL();
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
@@ -233,7 +245,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
 #endif
     c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release();
     c->key_a.release(); c->key_b.release(); c->idx_a.release(); c->perm.release(); c->tmp.release();
-    c->d_pair_off.release(); c->d_rb.release(); c->d_rmin.release(); c->d_nrows.release();
+    c->d_pair_off.release(); c->d_rb.release(); c->d_seg_off.release(); c->d_rmin.release(); c->d_nrows.release();
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
@@ -423,7 +435,12 @@ static int phase_sort(icl_ctx *c) {
         c->h_item_order[2 * j] = c->h_pair_order[j];
         c->h_item_order[2 * j + 1] = P + c->h_pair_order[j];
     }
-    if (c->d_rb.reserve(st, P + 1) || c->d_item_order.reserve(st, 2 * P + 1) || c->d_pair_order.reserve(st, P + 1)) return st.code;
+    c->h_seg_off.resize(2 * (size_t)P + 1);
+    for (int32_t p = 0; p <= P; p++) { c->h_seg_off[p] = po[p]; c->h_seg_off[P + p] = n + po[p]; }
+    if (c->d_rb.reserve(st, P + 1) || c->d_item_order.reserve(st, 2 * P + 1) || c->d_pair_order.reserve(st, P + 1) ||
+        c->d_seg_off.reserve(st, 2 * P + 1))
+        return st.code;
+    ICL_CUDA(st, h2d(c->d_seg_off.p, c->h_seg_off.data(), (2 * (size_t)P + 1) * sizeof(int64_t), s));
     ICL_CUDA(st, h2d(c->d_rb.p, c->h_rb.data(), (size_t)(P + 1) * sizeof(int64_t), s));
     if (P > 0) {
         ICL_CUDA(st, h2d(c->d_item_order.p, c->h_item_order.data(), (size_t)2 * P * sizeof(int32_t), s));
@@ -633,6 +650,7 @@ static int phase_edges(icl_ctx *c) {
     const unsigned eblocks = (unsigned)((V + 255) / 256);
     if (V > 0) {
         k_edges_tile<false><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, nullptr, nullptr, c->d_pair_off.p, stats);
+        ICL_COUNT_KERNEL();
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
@@ -659,6 +677,7 @@ static int phase_edges(icl_ctx *c) {
 #ifndef ICL_EMU
     if (V > 0) {
         k_edges_tile<true><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, eoff, edges, c->d_pair_off.p, stats);
+        ICL_COUNT_KERNEL();
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
@@ -1126,6 +1145,7 @@ static int phase_chain(icl_ctx *c) {
             auto launch = [&](void (*kern)(ChainArgs)) {
                 ICL_CUDA(st, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 kern<<<(unsigned)(2 * P), 64, smem, s>>>(A);
+                ICL_COUNT_KERNEL();
                 return 0;
             };
             if (launch(batch ? (A.dbg ? k_chain_ring<true, true> : k_chain_ring<true, false>) : k_chain_ring<false, false>)) return st.code;
@@ -1190,6 +1210,7 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaSetDevice(c->device));
 #endif
+    LaunchScope scope(c, 0);
     c->dp_done = c->dp_begun = false;
     c->order_on_device = false;
     c->prm = *prm;
@@ -1210,8 +1231,6 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
     if (phase_chain(c)) return st.code;
     c->timers[ICL_T_CHAIN].stop(s);
     c->counters[0] = c->n_edges;
-    c->counters[1] = 11;   // kernels launched by icl_dp (stats excluded): key, decode, pair_off, pair_meta, rowptr x2,
-                           // mirror, rowptr_rev, edge count, edge fill, chain (+ export when not streamed) + CUB passes
     c->counters[3] = c->R;
     c->counters_ext[0] = c->max_span;
     c->counters_ext[1] = c->chain_kernel;
@@ -1223,7 +1242,6 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
         c->dp_begun = true;
         return ICL_OK;
     }
-    c->counters[1] = want_keys ? 12 : 11;
     c->timers[ICL_T_EXPORT].start(s);
     if (want_keys && c->score32.reserve(st, 2 * n)) return st.code;
     if (want_keys) {
@@ -1692,11 +1710,21 @@ static int phase_pvalue_incidence(icl_ctx *c, bool *handled) {
         }));
     }
     if (exclusive_sum_u32(st, c->tmp, c->inc_cnt.p, c->inc_off.p, NB, s)) return st.code;
+    // the 32-bit scan wraps when the boxes of all blocks hold 2^32 incidences or more; a box holds fewer than 2^24 points
+    // (pair size limit), so a wrap always shows as a DEcrease between neighbours — checked before the total is trusted
+    ICL_CUDA(st, dev_memset(c->stats.p + 1, 0, sizeof(int32_t), s));
+    {
+        const uint32_t *ioff = c->inc_off.p;
+        int32_t *stats = c->stats.p;
+        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) { if (ioff[b + 1] < ioff[b]) atomic_or_i32(&stats[1], 1); }));
+    }
     uint32_t total = 0;
+    int32_t wrapped = 0;
     ICL_CUDA(st, d2h(&total, c->inc_off.p + NB, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(&wrapped, c->stats.p + 1, sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
     const int64_t I = total;
-    if (I > (1ll << 28)) return 0;                                          // pathological nesting: sequential kernel instead
+    if (wrapped || I > (1ll << 28)) return 0;                               // pathological nesting: sequential kernel instead
     *handled = true;
     if (I == 0) return 0;
     if (c->key_a.reserve(st, I) || c->key_b.reserve(st, I) || c->inc_start.reserve(st, I + 2)) return st.code;
@@ -1759,6 +1787,7 @@ static int phase_pvalue(icl_ctx *c) {
     size_t smem = (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15) + (size_t)l2_cap * 4;
     ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     k_pvalue<<<(unsigned)P, 32, smem, s>>>(A, l2_cap);
+    ICL_COUNT_KERNEL();
     ICL_CUDA(st, cudaGetLastError());
 #else
     A.smem_cap = 0;
@@ -1836,10 +1865,9 @@ struct NpSortArgs {
     const int32_t *key;        // [2n] segments back to back: the REVERSED score arrays (what pandas hands to numpy)
     int32_t *idx;              // [2n] out: argsort of every segment (segment-local indices)
     int32_t *scr;              // [4n] scratch: per segment 2 x len stop lists
-    const int64_t *off;        // [P + 1]
-    const int32_t *order;      // item order (longest first)
-    int64_t n;
-    int32_t P, smem_cap;       // segments of at most smem_cap elements keep keys and indices in shared memory
+    const int64_t *off;        // [segments + 1] start of every segment in key / idx
+    const int32_t *order;      // segment order (longest first)
+    int32_t smem_cap;          // segments of at most smem_cap elements keep keys and indices in shared memory
 };
 
 #define ICL_NPS_SMALL 15         // SMALL_QUICKSORT of this numpy build: ranges with pr - pl <= 15 are insertion sorted
@@ -1925,9 +1953,8 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t FULL = 0xffffffffu;
     const int32_t it = A.order[blockIdx.x];
-    const int32_t p = it >= A.P ? it - A.P : it;
-    const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
-    const int32_t len = (int32_t)(A.off[p + 1] - A.off[p]);
+    const int64_t base = A.off[it];
+    const int32_t len = (int32_t)(A.off[it + 1] - base);
     if (len <= 0) return;
     extern __shared__ int32_t nps_sm[];
     // IdxT = uint16_t: every segment fits shared memory with 16-bit indices (6 B per element, more CTAs per SM);
@@ -2113,16 +2140,16 @@ __global__ void __launch_bounds__(32 * ICL_NPS_WARPS) k_np_argsort(NpSortArgs A)
 struct XsArgs {
     const int32_t *key;        // [2n] segments back to back: the REVERSED score arrays
     int32_t *idx;              // [2n] out: argsort of every segment (segment-local indices)
-    const int64_t *off;        // [P + 1]
-    const int32_t *order;      // item order (longest first)
-    int32_t *host_flag;        // [2P] set to 1 when a segment must be re-sorted by numpy on the host
+    const int64_t *off;        // [segments + 1] start of every segment in key / idx
+    const int32_t *order;      // segment order (longest first)
+    int32_t *host_flag;        // [segments] set to 1 when a segment must be re-sorted by numpy on the host
     int32_t *scr;              // [4n] scratch: stop lists of the std::sort partitions
-    int64_t n;
-    int32_t P, smem_cap;
+    int32_t smem_cap;
     int32_t W;                 // lanes of the emulated vector: 8 = AVX-512, 4 = AVX2
     int32_t first;             // this launch covers order[first .. first + gridDim.x)
     int32_t keys_in_smem;      // keys next to the indices in shared memory (else only the indices; keys through L1)
     int32_t lane_max;          // std::sort pieces of at most this many elements are sorted by one lane each
+    int32_t force_giveup;      // test hook (env ICL_B200_XS_FORCE_GIVEUP): the first segment of the launch gives up at once
 };
 
 // The key-index network is a bitonic sort with flip merges over P = 8 * numVecs slots: for S = 2, 4, .., P: compare
@@ -2305,9 +2332,8 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     constexpr int G = 4 * W;                                  // W lanes per vector, G elements per unrolled group
     constexpr int wsh = W == 8 ? 3 : 2;
     const int32_t it = A.order[A.first + blockIdx.x];
-    const int32_t p = it >= A.P ? it - A.P : it;
-    const int64_t base = A.off[p] + (it >= A.P ? A.n : 0);
-    const int32_t len = (int32_t)(A.off[p + 1] - A.off[p]);
+    const int64_t base = A.off[it];
+    const int32_t len = (int32_t)(A.off[it + 1] - base);
     if (len <= 0) return;
     extern __shared__ int32_t xs_sm[];
     const bool fits = sizeof(IdxT) == 2 || len <= A.smem_cap;   // indices in shared memory
@@ -2335,7 +2361,8 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     int32_t *Lbase = A.scr + 2 * base, *Rbase = Lbase + len;  // stop lists of the std::sort partitions (slice [f, l) per range)
     if (threadIdx.x == 0) {
         st_lo[0] = 0; st_hi[0] = len - 1; st_it[0] = 2 * (31 - __clz((unsigned)len));
-        s_sp = unsorted ? 1 : 0; s_pending = unsorted ? 1 : 0; s_lock = 0; s_giveup = 0;
+        s_sp = unsorted ? 1 : 0; s_pending = unsorted ? 1 : 0; s_lock = 0;
+        s_giveup = (A.force_giveup && blockIdx.x == 0) ? 1 : 0;
     }
     __syncthreads();
     volatile int32_t *vsp = &s_sp, *vpend = &s_pending, *vgive = &s_giveup;
@@ -2647,6 +2674,73 @@ static cudaError_t xss_launch_v(int lanes, int warps, const XsArgs &A, unsigned 
 }
 #endif
 
+#ifndef ICL_EMU
+// numpy's argsort (flavour `mode`) of segments of `key` into `idx`.  off / order: device arrays (segment starts, segments
+// longest first); lens[j] = length of segment order[j] (host copy, non-increasing).  Fails with ICL_ERR_STATE when a
+// segment needs the host rank (std::sort's heap-sort branch).
+static int rank_segments(icl_ctx *c, int32_t mode, const int32_t *key, int32_t *idx, const int64_t *off, const int32_t *order,
+                         const std::vector<int64_t> &lens) {
+    Status &st = c->st;
+    cudaStream_t s = c->stream;
+    const int32_t nseg = (int32_t)lens.size();
+    if (nseg == 0) return 0;
+    int64_t total = 0;
+    for (int64_t L : lens) total += L;
+    if (c->npscr.reserve(st, 2 * (size_t)total + 64)) return st.code;
+    const int64_t longest = lens[0];
+    if (mode == ICL_RANK_NUMPY_SCALAR) {
+        const bool narrow = longest <= 16000;                    // 16-bit indices: 6 B per element, everything on chip
+        const int32_t cap = narrow ? (int32_t)((longest + 31) & ~31ll) : (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);
+        const size_t smem = (size_t)cap * (narrow ? 6 : 8);
+        NpSortArgs A{key, idx, c->npscr.p, off, order, cap};
+        if (narrow) {
+            ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            k_np_argsort<uint16_t><<<(unsigned)nseg, 32 * ICL_NPS_WARPS, smem, s>>>(A);
+        } else {
+            ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            k_np_argsort<int32_t><<<(unsigned)nseg, 32 * ICL_NPS_WARPS, smem, s>>>(A);
+        }
+        ICL_COUNT_KERNEL();
+        ICL_CUDA(st, cudaGetLastError());
+        return 0;
+    }
+    if (c->host_flag.reserve(st, (size_t)nseg + 1)) return st.code;
+    ICL_CUDA(st, dev_memset(c->host_flag.p, 0, ((size_t)nseg + 1) * sizeof(int32_t), s));
+    static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
+    static const int xs_lane = [] { const char *e = getenv("ICL_B200_XS_LANE"); const int q = e ? atoi(e) : ICL_XS_LANE; return q < 16 ? 16 : q > 160 ? 160 : q; }();
+    // Segments come longest first, so the size classes are runs of the order; one launch each:
+    //   <= 16 000 keys   keys + 16-bit indices in shared memory (96 KB: several CTAs per SM)
+    //   <= 34 000        the same with up to 204 KB (one CTA per SM)
+    //   <= 65 535        16-bit indices in shared memory, keys through L1
+    //   longer           32-bit indices; both in shared memory up to 12 288 keys, else in global memory
+    auto cls_of = [](int64_t L) { return L > 65535 ? 0 : L > 34000 ? 1 : L > 16000 ? 2 : 3; };
+    for (int32_t j0 = 0; j0 < nseg;) {
+        const int64_t L = lens[j0];
+        const int cls = cls_of(L);
+        int32_t j1 = j0;
+        while (j1 < nseg && cls_of(lens[j1]) == cls) j1++;
+        const int64_t Lr = (L + 31) & ~31ll;
+        const int32_t ccap = cls == 0 ? (int32_t)std::min<int64_t>(Lr, 12288) : (int32_t)Lr;
+        const size_t csmem = (size_t)ccap * (cls == 0 ? 8 : cls == 1 ? 2 : 6);
+        XsArgs A{key, idx, off, order, c->host_flag.p, c->npscr.p, ccap,
+                 mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, j0, cls == 1 ? 0 : 1, xs_lane, getenv("ICL_B200_XS_FORCE_GIVEUP") ? 1 : 0};
+        const unsigned grid = (unsigned)(j1 - j0);
+        if (cls == 0) ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, grid, csmem, s));
+        else ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, grid, csmem, s));
+        ICL_COUNT_KERNEL();
+        j0 = j1;
+    }
+    ICL_CUDA(st, cudaGetLastError());
+    // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
+    std::vector<int32_t> hf((size_t)nseg);
+    ICL_CUDA(st, d2h(hf.data(), c->host_flag.p, hf.size() * sizeof(int32_t), s));
+    ICL_CUDA(st, dev_sync(s));
+    for (int32_t f : hf)
+        if (f) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
+    return 0;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // ABI: icl_rank_device — the extraction order of every (pair, direction) item computed on the device.
 // ICL_RANK_NUMPY_AVX512 / _AVX2 / _SCALAR: numpy's own argsort of that flavour, reproduced exactly (the reference's tie
@@ -2668,6 +2762,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     cudaStream_t s = c->stream;
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
+    LaunchScope scope(c, 1);
     c->timers[ICL_T_D2H].start(s);
     if (c->order_in.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V))
@@ -2685,56 +2780,9 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
             o[n + i] = S[mmap[src]];
         }));
 #ifndef ICL_EMU
-        int64_t longest = 0;
-        for (int32_t q = 0; q < P; q++) longest = std::max<int64_t>(longest, c->h_pair_off[q + 1] - c->h_pair_off[q]);
-        const bool narrow = longest <= 16000;                    // 16-bit indices: 6 B per element, everything on chip
-        const int32_t cap = narrow ? (int32_t)((longest + 31) & ~31ll) : (int32_t)std::min<int64_t>((longest + 31) & ~31ll, 12288);
-        const size_t smem = (size_t)cap * (narrow ? 6 : 8);
-        if (mode == ICL_RANK_NUMPY_SCALAR) {
-            NpSortArgs A{c->score32.p, c->order_in.p, c->npscr.p, c->d_pair_off.p, c->d_item_order.p, n, P, cap};
-            if (narrow) {
-                ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                k_np_argsort<uint16_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, smem, s>>>(A);
-            } else {
-                ICL_CUDA(st, cudaFuncSetAttribute(k_np_argsort<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                k_np_argsort<int32_t><<<(unsigned)(2 * P), 32 * ICL_NPS_WARPS, smem, s>>>(A);
-            }
-        } else {
-            if (c->host_flag.reserve(st, 2 * (size_t)P + 1)) return st.code;
-            ICL_CUDA(st, dev_memset(c->host_flag.p, 0, (2 * (size_t)P + 1) * sizeof(int32_t), s));
-            static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
-            static const int xs_lane = [] { const char *e = getenv("ICL_B200_XS_LANE"); const int q = e ? atoi(e) : ICL_XS_LANE; return q < 16 ? 16 : q > 160 ? 160 : q; }();
-            // Pairs come longest first (h_pair_order), so the size classes are runs of the item order; one launch each:
-            //   <= 16 000 keys   keys + 16-bit indices in shared memory (96 KB: several CTAs per SM)
-            //   <= 34 000        the same with up to 204 KB (one CTA per SM)
-            //   <= 65 535        16-bit indices in shared memory, keys through L1
-            //   longer           32-bit indices; both in shared memory up to 12 288 keys, else in global memory
-            auto plen = [&](int32_t j) { const int32_t q = c->h_pair_order[j]; return (int64_t)(c->h_pair_off[q + 1] - c->h_pair_off[q]); };
-            auto cls_of = [](int64_t L) { return L > 65535 ? 0 : L > 34000 ? 1 : L > 16000 ? 2 : 3; };
-            for (int32_t j0 = 0; j0 < P;) {
-                const int64_t L = plen(j0);
-                const int cls = cls_of(L);
-                int32_t j1 = j0;
-                while (j1 < P && cls_of(plen(j1)) == cls) j1++;
-                const int64_t Lr = (L + 31) & ~31ll;
-                const int32_t ccap = cls == 0 ? (int32_t)std::min<int64_t>(Lr, 12288) : (int32_t)Lr;
-                const size_t csmem = (size_t)ccap * (cls == 0 ? 8 : cls == 1 ? 2 : 6);
-                XsArgs A{c->score32.p, c->order_in.p, c->d_pair_off.p, c->d_item_order.p, c->host_flag.p, c->npscr.p, n, P, ccap,
-                         mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, 2 * j0, cls == 1 ? 0 : 1, xs_lane};
-                const unsigned grid = (unsigned)(2 * (j1 - j0));
-                if (cls == 0) ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, grid, csmem, s));
-                else ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, grid, csmem, s));
-                j0 = j1;
-            }
-            ICL_CUDA(st, cudaGetLastError());
-            // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
-            std::vector<int32_t> hf(2 * (size_t)P);
-            ICL_CUDA(st, d2h(hf.data(), c->host_flag.p, hf.size() * sizeof(int32_t), s));
-            ICL_CUDA(st, dev_sync(s));
-            for (int32_t f : hf)
-                if (f) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
-        }
-        ICL_CUDA(st, cudaGetLastError());
+        std::vector<int64_t> lens(2 * (size_t)P);
+        for (int32_t j = 0; j < 2 * P; j++) { const int32_t it = c->h_item_order[j]; lens[j] = c->h_seg_off[it + 1] - c->h_seg_off[it]; }
+        if (rank_segments(c, mode, c->score32.p, c->order_in.p, c->d_seg_off.p, c->d_item_order.p, lens)) return st.code;
 #else
         return fail(c, ICL_ERR_STATE, "icl_rank_device: the numpy-scalar mode exists in the CUDA build only");
 #endif
@@ -2759,6 +2807,71 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     }
     c->timers[ICL_T_D2H].stop(s);
     c->order_on_device = true;
+    c->keys_on_device = mode != ICL_RANK_STABLE;
+    return ICL_OK;
+}
+
+// Probe / test: the rank kernels on caller-supplied key segments (nothing of the upload is touched).
+extern "C" int icl_debug_rank_keys(icl_ctx *c, int32_t mode, int32_t n_segments, const int64_t *seg_off, const int32_t *keys,
+                                   int32_t *argsort_out) {
+    if (!c) return ICL_ERR_ARG;
+    if (n_segments < 0 || !seg_off || (n_segments > 0 && seg_off[n_segments] > 0 && (!keys || !argsort_out)))
+        return fail(c, ICL_ERR_ARG, "icl_debug_rank_keys: bad argument");
+    if (mode != ICL_RANK_NUMPY_SCALAR && mode != ICL_RANK_NUMPY_AVX512 && mode != ICL_RANK_NUMPY_AVX2)
+        return fail(c, ICL_ERR_ARG, "icl_debug_rank_keys: mode must be one of the numpy flavours");
+#ifndef ICL_EMU
+    Status &st = c->st;
+    st.code = 0;
+    ICL_CUDA(st, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (seg_off[0] != 0) return fail(c, ICL_ERR_ARG, "icl_debug_rank_keys: seg_off[0] must be 0");
+    for (int32_t j = 0; j < n_segments; j++)
+        if (seg_off[j + 1] < seg_off[j] || seg_off[j + 1] - seg_off[j] >= (1 << 24))
+            return fail(c, ICL_ERR_ARG, "icl_debug_rank_keys: segment offsets must ascend, segments < 2^24 keys");
+    const int64_t total = n_segments ? seg_off[n_segments] : 0;
+    if (total == 0) return ICL_OK;
+    std::vector<int32_t> order((size_t)n_segments);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return seg_off[a + 1] - seg_off[a] > seg_off[b + 1] - seg_off[b]; });
+    std::vector<int64_t> lens((size_t)n_segments);
+    for (int32_t j = 0; j < n_segments; j++) lens[j] = seg_off[order[j] + 1] - seg_off[order[j]];
+    Buf<int32_t> dk, di, dord;
+    Buf<int64_t> doff;
+    int rc = 0;
+    if (dk.reserve(st, total) || di.reserve(st, total) || dord.reserve(st, n_segments) || doff.reserve(st, (size_t)n_segments + 1)) rc = st.code;
+    if (!rc) {
+        cudaError_t e = h2d(dk.p, keys, (size_t)total * 4, s);
+        if (e == cudaSuccess) e = h2d(dord.p, order.data(), (size_t)n_segments * 4, s);
+        if (e == cudaSuccess) e = h2d(doff.p, seg_off, ((size_t)n_segments + 1) * 8, s);
+        if (e != cudaSuccess) rc = fail(c, ICL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (!rc) rc = rank_segments(c, mode, dk.p, di.p, doff.p, dord.p, lens);
+    if (!rc) {
+        cudaError_t e = d2h(argsort_out, di.p, (size_t)total * 4, s);
+        if (e == cudaSuccess) e = dev_sync(s);
+        if (e != cudaSuccess) rc = fail(c, ICL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(s);
+    dk.release(); di.release(); dord.release(); doff.release();
+    return rc;
+#else
+    return fail(c, ICL_ERR_STATE, "icl_debug_rank_keys: the numpy rank kernels exist in the CUDA build only");
+#endif
+}
+
+// Test / verification: the key arrays the last icl_rank_device (numpy flavours) sorted — every (pair, direction) item's
+// scores in REVERSED point order, forward items then anti-diagonal ones (2 n values; what icl_dp would have exported).
+extern "C" int icl_debug_keys(icl_ctx *c, int32_t *keys) {
+    if (!c || !keys) return ICL_ERR_ARG;
+    if (!c->order_on_device || !c->keys_on_device) return fail(c, ICL_ERR_STATE, "icl_debug_keys: icl_rank_device (numpy flavour) has not succeeded");
+    Status &st = c->st;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaSetDevice(c->device));
+#endif
+    if (c->n > 0) {
+        ICL_CUDA(st, d2h(keys, c->score32.p, (size_t)2 * c->n * sizeof(int32_t), c->stream));
+        ICL_CUDA(st, dev_sync(c->stream));
+    }
     return ICL_OK;
 }
 
@@ -2791,6 +2904,7 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     cudaStream_t s = c->stream;
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
+    LaunchScope scope(c, 2);
     c->timers[ICL_T_EXTRACT].start(s);
     if (c->order_in.reserve(st, 2 * n) || c->rank2v.reserve(st, V)) return st.code;
     if (n > 0) {
@@ -2934,8 +3048,6 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     ICL_CUDA(st, dev_sync(s));
     out->n_blocks = NBo;
     out->n_members = NMo;
-    c->counters[2] = 12;   // our kernels per icl_extract (profiles/r01_launches_final.csv): rank2v, tree keys + check, tree walk,
-                           // flags, emit, k_pvalue, p values, select x3, gather — CUB sort / scan kernels not counted
     return ICL_OK;
 }
 
@@ -2948,7 +3060,9 @@ extern "C" int icl_timings(icl_ctx *c, double *ms, int32_t n_slots) {
 
 extern "C" int icl_counters(icl_ctx *c, int64_t *out, int32_t n_slots) {
     if (!c || !out) return ICL_ERR_ARG;
-    int32_t k = n_slots < 6 ? n_slots : 6;
-    for (int32_t i = 0; i < k; i++) out[i] = i < 4 ? c->counters[i] : c->counters_ext[i - 4];
+    int32_t k = n_slots < 8 ? n_slots : 8;
+    for (int32_t i = 0; i < k; i++)
+        out[i] = i == 1 ? c->n_own[0] : i == 2 ? c->n_own[2] : i < 4 ? c->counters[i] : i < 6 ? c->counters_ext[i - 4]
+                 : i == 6 ? c->n_own[1] : c->n_cub[0] + c->n_cub[1] + c->n_cub[2];
     return k;
 }

@@ -104,6 +104,14 @@ struct Buf {
 };
 
 // ------------------------------------------------------------------------------------------------
+// launch accounting: every kernel launch of the library and every CUB device-wide call on the calling thread
+// (an ABI call runs on one host thread from start to finish: it reads the counters on entry and on exit)
+// ------------------------------------------------------------------------------------------------
+struct LaunchCount { int64_t own = 0, cub = 0; };
+inline LaunchCount &launch_count() { static thread_local LaunchCount lc; return lc; }
+#define ICL_COUNT_KERNEL() (++icl::launch_count().own)
+
+// ------------------------------------------------------------------------------------------------
 // kernel launch: grid-stride foreach over [0, n)
 // ------------------------------------------------------------------------------------------------
 #ifndef ICL_EMU
@@ -125,17 +133,19 @@ inline cudaError_t foreach(cudaStream_t s, int64_t n, F f) {
     const int64_t maxb = 148 * 16;
     if (blocks > maxb) blocks = maxb;
     k_foreach<<<(unsigned)blocks, 256, 0, s>>>(n, f);
+    ICL_COUNT_KERNEL();
     return cudaGetLastError();
 }
 template <class F>
 inline cudaError_t foreach_warp(cudaStream_t s, int64_t n, F f) {
     if (n <= 0) return cudaSuccess;
     k_foreach_warp<<<(unsigned)n, 32, 0, s>>>(n, f);
+    ICL_COUNT_KERNEL();
     return cudaGetLastError();
 }
 #else
-template <class F> inline int foreach(cudaStream_t, int64_t n, F f) { for (int64_t i = 0; i < n; i++) f(i); return 0; }
-template <class F> inline int foreach_warp(cudaStream_t, int64_t n, F f) { for (int64_t i = 0; i < n; i++) f(i); return 0; }
+template <class F> inline int foreach(cudaStream_t, int64_t n, F f) { if (n > 0) ICL_COUNT_KERNEL(); for (int64_t i = 0; i < n; i++) f(i); return 0; }
+template <class F> inline int foreach_warp(cudaStream_t, int64_t n, F f) { if (n > 0) ICL_COUNT_KERNEL(); for (int64_t i = 0; i < n; i++) f(i); return 0; }
 #endif
 
 ICL_HD void atomic_max_i32(int32_t *p, int32_t v) {
@@ -177,6 +187,7 @@ inline int radix_sort_pairs(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, 
     ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
     if (tmp.reserve(st, bytes)) return st.code;
     ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+    ++launch_count().cub;
     return 0;
 }
 inline int radix_sort_keys(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, uint64_t *kout, int64_t n, int end_bit,
@@ -186,6 +197,7 @@ inline int radix_sort_keys(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, u
     ICL_CUDA(st, cub::DeviceRadixSort::SortKeys(nullptr, bytes, kin, kout, (int)n, 0, end_bit, s));
     if (tmp.reserve(st, bytes)) return st.code;
     ICL_CUDA(st, cub::DeviceRadixSort::SortKeys(tmp.p, bytes, kin, kout, (int)n, 0, end_bit, s));
+    ++launch_count().cub;
     return 0;
 }
 // out[0..n] = exclusive prefix sum of in[0..n) with the total in out[n]; `in` must have n+1 slots
@@ -196,6 +208,7 @@ inline int exclusive_sum_u32(Status &st, Buf<uint8_t> &tmp, uint32_t *in, uint32
     ICL_CUDA(st, cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)(n + 1), s));
     if (tmp.reserve(st, bytes)) return st.code;
     ICL_CUDA(st, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)(n + 1), s));
+    ++launch_count().cub;
     return 0;
 }
 struct MaxI32 {
@@ -208,6 +221,7 @@ inline int inclusive_max_i32(Status &st, Buf<uint8_t> &tmp, int32_t *a, int64_t 
     ICL_CUDA(st, cub::DeviceScan::InclusiveScan(nullptr, bytes, a, a, MaxI32(), (int)n, s));
     if (tmp.reserve(st, bytes)) return st.code;
     ICL_CUDA(st, cub::DeviceScan::InclusiveScan(tmp.p, bytes, a, a, MaxI32(), (int)n, s));
+    ++launch_count().cub;
     return 0;
 }
 struct Timer {

@@ -153,6 +153,14 @@ class IclEngine:
         # "numpy_scalar" / "numpy_avx512" / "numpy_avx2" = that device reproduction regardless of what numpy does here
         self.rank_mode = os.environ.get("ICL_B200_RANK", "auto")
         self.host_rank_fallbacks = 0        # comparisons the device rank handed back to numpy (std::sort's heap-sort branch)
+        # ICL_B200_RANK_VERIFY=K (1 = 32): after every device rank, K segments (the longest four, the rest at random) are
+        # re-sorted with the running numpy and compared; a difference sends this comparison — and from then on the process —
+        # to the host rank and is counted here
+        v = os.environ.get("ICL_B200_RANK_VERIFY", "0")
+        self.rank_verify = (32 if v == "1" else max(0, int(v))) if v.isdigit() else 0
+        self.rank_verify_failures = 0
+        self.rank_verified_segments = 0
+        self._verify_rng = np.random.default_rng(977)
         self.host_ms = {}
 
     # ---- plumbing ------------------------------------------------------------------------------
@@ -313,10 +321,11 @@ class IclEngine:
         return dict(zip(_lib.ICL_T_NAMES, ms.tolist()))
 
     def counters(self):
-        c = np.zeros(6, np.int64)
-        self.lib.icl_counters(self.ctx, c.ctypes.data, 6)
+        c = np.zeros(8, np.int64)
+        self.lib.icl_counters(self.ctx, c.ctypes.data, 8)
         return dict(edges=int(c[0]), launches_dp=int(c[1]), launches_extract=int(c[2]), rows=int(c[3]),
-                    max_span=int(c[4]), chain_kernel={0: "generic", 1: "ring", 3: "single"}[int(c[5])])
+                    max_span=int(c[4]), chain_kernel={0: "generic", 1: "ring", 3: "single"}[int(c[5])],
+                    launches_rank=int(c[6]), cub_calls=int(c[7]))
 
     # ---- whole hot path ------------------------------------------------------------------------
     def dp_rank_streamed(self, params: ChainParams):
@@ -376,7 +385,7 @@ class IclEngine:
                         probe._check(probe.lib.icl_debug_order(probe.ctx, got.ctypes.data))
                     except IclError:
                         continue
-                    if all((got[a:b] == e).all() for a, b, e in zip(off[:-1], off[1:], exp)):
+                    if all((got[a:b] == e).all() for a, b, e in zip(off[:-1], off[1:], exp)) and probe._probe_size_classes(mode):
                         kind = name
                         break
             except IclError:
@@ -385,6 +394,58 @@ class IclEngine:
                 probe.close()
             _NP_KIND[self.device] = kind
         return _NP_KIND[self.device]
+
+    # one tie-heavy segment per launch class of the rank kernels (include/icl_b200.h, icl_rank_device: <= 16 000 keys,
+    # <= 34 000, <= 65 535, longer) plus the network / small-partition sizes, straight on key arrays (no DP needed)
+    PROBE_CLASS_SIZES = (70001, 36007, 17003, 9001, 4099, 257, 256, 33)
+
+    @staticmethod
+    def _score_like_keys(rng, m, flavour):
+        """Key arrays shaped like DP score segments: a mass of never-updated points holding the three grading values,
+        chains of growing scores on top; `flavour` 1 = only the three values (every pass of the SIMD sort stalls and the
+        std::sort fallback does the work), 2 = many distinct values."""
+        k = rng.choice(np.array([25, 30, 50], np.int32), m, p=[0.5, 0.3, 0.2])
+        if flavour == 0:
+            chain = rng.random(m) < 0.4
+            k[chain] += rng.integers(1, 40, int(chain.sum())).astype(np.int32) * rng.integers(1, 60, int(chain.sum())).astype(np.int32)
+        elif flavour == 2:
+            k = rng.integers(25, 1 << 20, m).astype(np.int32)
+        return k
+
+    def _probe_size_classes(self, mode):
+        """True when the device argsort of flavour `mode` equals the running numpy's on every probe segment."""
+        rng = np.random.default_rng(4242)
+        segs = [self._score_like_keys(rng, m, f) for f in (0, 1, 2) for m in self.PROBE_CLASS_SIZES]
+        off = np.r_[0, np.cumsum([len(x) for x in segs])].astype(np.int64)
+        keys = np.ascontiguousarray(np.concatenate(segs), np.int32)
+        got = np.zeros(len(keys), np.int32)
+        try:
+            self._check(self.lib.icl_debug_rank_keys(self.ctx, int(mode), len(segs), off.ctypes.data, keys.ctypes.data, got.ctypes.data))
+        except IclError:
+            return False
+        return all((got[a:b] == x.astype(np.int64).argsort(kind="quicksort")).all() for a, b, x in zip(off[:-1], off[1:], segs))
+
+    def _verify_device_rank(self):
+        """ICL_B200_RANK_VERIFY: a sample of the segments the device just ranked, re-sorted with numpy in this process."""
+        n, P = self.n, self.n_pairs
+        if n == 0:
+            return True
+        keys, order = self._buf("vkeys", 2 * n, np.int32), self._buf("vorder", 2 * n, np.int32)
+        self._check(self.lib.icl_debug_keys(self.ctx, keys.ctypes.data))
+        self._check(self.lib.icl_debug_order(self.ctx, order.ctypes.data))
+        off = np.concatenate([self.pair_off, self.pair_off[1:] + n])
+        sizes = np.diff(off)
+        cand = np.flatnonzero(sizes > 1)
+        if len(cand) == 0:
+            return True
+        longest = cand[np.argsort(-sizes[cand], kind="stable")[:4]]
+        rest = self._verify_rng.choice(cand, min(len(cand), max(0, self.rank_verify - len(longest))), replace=False)
+        for sgm in np.unique(np.r_[longest, rest]):
+            a, b = off[sgm], off[sgm + 1]
+            self.rank_verified_segments += 1
+            if not (order[a:b] == keys[a:b].astype(np.int64).argsort(kind="quicksort")).all():
+                return False
+        return True
 
     def numpy_sort_is_scalar(self):
         return self.numpy_sort_kind() == "numpy_scalar"
@@ -407,6 +468,13 @@ class IclEngine:
                 raise
             # a segment the device does not cover (std::sort's heap-sort branch): numpy itself ranks this comparison
             self.host_rank_fallbacks += 1
+            kf, kr = self.dp(params)
+            af, ar = self.rank(kf, kr)
+            return self.extract(af, ar, min_members, copy)
+        if self.rank_verify and mode != "stable" and not self._verify_device_rank():
+            # the device's permutation is not this numpy's: numpy ranks this comparison and every later one of the process
+            self.rank_verify_failures += 1
+            _NP_KIND[self.device] = None
             kf, kr = self.dp(params)
             af, ar = self.rank(kf, kr)
             return self.extract(af, ar, min_members, copy)

@@ -54,6 +54,24 @@ CONFIGS = {
 }
 
 
+# BASELINE.json config 5: 8 species (genes, chromosomes) -> 28 pairwise comparisons, each swept over
+# grading x mg x pvalue
+C5_SPECIES = [(25_000, 7), (28_000, 9), (30_000, 10), (33_000, 12), (36_000, 13), (39_000, 16), (42_000, 17), (45_000, 19)]
+C5_GRADINGS = [(50, 40, 25), (50, 30, 25)]
+C5_MGS = [(25, 25), (40, 40), (50, 50)]
+C5_PVALUES = [0.05, 0.2, 1.0]
+
+
+def config5_comparison(ci: int) -> SynthConfig:
+    """The ci-th (0..27) cross-species comparison of config 5, in itertools.combinations order of the species."""
+    import itertools
+    a, b = list(itertools.combinations(range(len(C5_SPECIES)), 2))[ci]
+    (ga, ca), (gb, cb) = C5_SPECIES[a], C5_SPECIES[b]
+    genes = (ga + gb) // 2
+    return SynthConfig(f"c5_{a}_{b}", 20260500 + ci, n_anc=int(genes / 2 / 0.6), k=2, n_chr1=ca, n_chr2=cb,
+                       self_cmp=False, target_points=int(genes * 60))
+
+
 @dataclass
 class Genome:
     prefix: str
