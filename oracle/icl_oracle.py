@@ -285,6 +285,28 @@ def grade_hits(q_codes, bitscore, multiple, repeat_number, grading):
     return out
 
 
+def color_hits(q_codes, bitscore, rednum, repeat_number):
+    """`dotplot.pair_positon` (wgdi/dotplot.py:31-56): colour per hit, 1 red / 2 blue / 3 gray / 0 not drawn.
+
+    :36-37  per query (groupby column 0) `sort_values(by=[11], ascending=[False])[:repeat_number]` — a one-key sort, i.e.
+            nargsort_desc of the group's scores in file order;
+    :35,38-40  red = first rednum, blue = [rednum : 5 + rednum], gray = [5 + rednum : repeat_number];
+    :53-56  rows without a colour are dropped (`str.contains` of a word character)."""
+    q_codes = np.asarray(q_codes)
+    out = np.zeros(len(q_codes), np.int8)
+    rednum = int(rednum)
+    bluenum = 5 + rednum
+    order = np.argsort(q_codes, kind="stable")
+    bounds = np.flatnonzero(np.r_[True, q_codes[order][1:] != q_codes[order][:-1], True])
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        rows = order[a:b]
+        ranked = rows[nargsort_desc(bitscore[rows])][:repeat_number]
+        out[ranked[:rednum]] = 1
+        out[ranked[rednum:bluenum]] = 2
+        out[ranked[bluenum:repeat_number]] = 3
+    return out
+
+
 def grade_hits_chromosomes(id1, subj, pair, bitscore, multiple, repeat_number, grading):
     """`deal_blast_for_chromosomes` (wgdi/run_colliearity.py:42-57) as pandas < 3 ran it (under pandas 3 the
     reference raises KeyError 'chr1' at :118; the golden fixture was generated with the pandas-2 behaviour of

@@ -298,6 +298,50 @@ def gen_bi_child(case):
     print(case, "blockinfo rows:", sum(1 for _ in open(os.path.join(d, "expected.blockinfo.csv"))) - 1)
 
 
+COLOR_PARAMS = [(1, 20), (2, 12), (3, 5), (1, 3), (0, 8), (4, 40)]      # (multiple, repeat_number)
+
+
+def gen_colors_child(case):
+    """dotplot.pair_positon (wgdi/dotplot.py:31-56), unmodified, on the BLAST table of e2e_<case>: for several (multiple,
+    repeat_number) the rows it keeps and their colours -> e2e_<case>/expected.colors.npz."""
+    import numpy as np
+    base, _, _ = import_reference()
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    from wgdi.dotplot import dotplot
+    d = os.path.join(GOLD, f"e2e_{case}")
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        icl = dict(base.load_conf("icl.conf", "collinearity"))
+        lens1, lens2 = base.newlens(icl["lens1"], "order"), base.newlens(icl["lens2"], "order")
+        gff1, gff2 = base.newgff(icl["gff1"]), base.newgff(icl["gff2"])
+        # dotplot.py:97-98 calls base.gene_location, which raises under pandas >= 3 (it assigns floats into a column created
+        # as '' — TypeError: Invalid value for dtype 'str'); pair_positon only maps the column, so the fixture gives it the
+        # lens filter of base.py:222 and a plain numeric 'loc'
+        gff1 = gff1[gff1["chr"].isin(lens1.index)].copy()
+        gff2 = gff2[gff2["chr"].isin(lens2.index)].copy()
+        gff1["loc"] = gff1["order"].astype(float)
+        gff2["loc"] = gff2["order"].astype(float)
+        out = {}
+        for reverse in ("false", "true"):
+            for mult, rn in COLOR_PARAMS:
+                blast = base.newblast("blast.m8.gz", 100, 1e-5, gff1, gff2, reverse)  # :108-109
+                df = dotplot.pair_positon(None, blast, gff1, gff2, mult, rn)
+                code = df["color"].map({"red": 1, "blue": 2, "gray": 3}).to_numpy().astype(np.int8)
+                out[f"{reverse}_{mult}_{rn}_row"] = df.index.to_numpy().astype(np.int64)
+                out[f"{reverse}_{mult}_{rn}_color"] = code
+        np.savez_compressed("expected.colors.npz", **out)
+    finally:
+        os.chdir(cwd)
+    print(case, "colour sets:", len(out) // 2)
+
+
+def gen_colors():
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
+    for case in ("tiny", "cross"):
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--colors-child", case], env=env)
+
+
 def gen_bi():
     env = dict(os.environ, NPY_DISABLE_CPU_FEATURES=PORTABLE_ENV)
     for case in BI_CASES:
@@ -318,6 +362,8 @@ if __name__ == "__main__":
         gen_e2e_child(sys.argv[2])
     elif len(sys.argv) > 2 and sys.argv[1] == "--bi-child":
         gen_bi_child(sys.argv[2])
+    elif len(sys.argv) > 2 and sys.argv[1] == "--colors-child":
+        gen_colors_child(sys.argv[2])
     else:
         what = sys.argv[1] if len(sys.argv) > 1 else "all"
         if what in ("all", "clouds"):
@@ -328,3 +374,5 @@ if __name__ == "__main__":
             gen_e2e(only=what)
         if what in ("all", "bi"):
             gen_bi()
+        if what in ("all", "colors"):
+            gen_colors()

@@ -378,7 +378,7 @@ def test_config5_comparison_full_sweep_matches_oracle(gpu_engine):
         _compare_with_oracle(b, exp)
         p = b.p_value()
         kept = [int((~(p > pv) & (b.m >= 5)).sum()) for pv in pvs]            # what the writer keeps per pvalue variant
-        assert kept[0] <= kept[1] <= kept[2] == int((b.m >= 5).sum())
+        assert 0 < kept[0] <= kept[1] <= kept[2] <= int((b.m >= 5).sum())     # (the unrounded `a` may exceed 1)
     for j in range(3):                                                          # same mg, the two gradings
         assert len(got[j]) != len(got[3 + j]) or (got[j].score != got[3 + j].score).any()
 

@@ -15,8 +15,10 @@ import numpy as np
 from .engine import nargsort_desc
 
 
-def grade_hits(q, bits, multiple, repeat_number, grading):
-    """Grading per hit (0 = dropped).  q: query gene code per hit in file order; bits: column 11."""
+def grade_hits(q, bits, multiple, repeat_number, grading, blue_extra=4):
+    """Grading per hit (0 = dropped).  q: query gene code per hit in file order; bits: column 11.
+    blue_extra: size of the second class — 4 in `-icl` (bluenum = 4 + rednum, run_colliearity.py:64), 5 in the dotplot
+    colouring (bluenum = 5 + rednum, dotplot.py:35; `color_hits`)."""
     q = np.asarray(q)
     bits = np.asarray(bits)
     n = len(q)
@@ -25,7 +27,7 @@ def grade_hits(q, bits, multiple, repeat_number, grading):
         return out
     rn = int(repeat_number)
     red = min(int(multiple), rn)                      # [:repeat_number] is applied first (:67)
-    blue = min(4 + int(multiple), rn)                 # bluenum = 4 + rednum (:64)
+    blue = min(int(blue_extra) + int(multiple), rn)   # bluenum = 4 + rednum (:64)
     o = np.lexsort((-bits, q))                        # stable: ties keep file order
     qs, bs = q[o], bits[o]
     start = np.flatnonzero(np.r_[True, qs[1:] != qs[:-1]])
@@ -53,6 +55,17 @@ def grade_hits(q, bits, multiple, repeat_number, grading):
             out[ranked[red:blue]] = grading[1]
             out[ranked[blue:rn]] = grading[2]
     return out
+
+
+COLOR_NAMES = ("", "red", "blue", "gray")
+
+
+def color_hits(q, bits, multiple, repeat_number):
+    """Colour class per hit of the `-d` dotplot (wgdi/dotplot.py:31-56, `pair_positon`): per query gene the hits by bit
+    score descending (the same unstable single-key sort as the grading, hazard H2), the first `repeat_number` kept; rank <
+    multiple -> 1 (red), the next five -> 2 (blue, bluenum = 5 + rednum, :35), the rest -> 3 (gray); 0 = not drawn (:56).
+    The same rank machinery as `grade_hits` with the other blue width."""
+    return grade_hits(q, bits, multiple, repeat_number, [1, 2, 3], blue_extra=5).astype(np.int8)
 
 
 def rank_hits(q, bits, repeat_number, class_bound=10):
