@@ -45,6 +45,18 @@ METRIC = "blast_hits_chained_per_sec"
 NCU_TRAFFIC_C2 = 81.3e6          # bytes per launch of the DP kernel (with its export epilogue) on C2: ncu capture, profiles/r01_chain_ring_ncu_summary.md
 
 
+WORKLOADS = {   # BASELINE.json `configs`, as built by wgdi_b200/synth.py
+    "C1": "BASELINE.json config 1 (5-chromosome self comparison, ~1M graded hits, 25 chromosome pairs)",
+    "C2": "BASELINE.json config 2 (Vitis-sized self comparison, 19 chromosomes, ~2M graded hits, 361 chromosome pairs)",
+    "C3": "BASELINE.json config 3 (cross-species, two 12-chromosome genomes, ~5M graded hits, 144 chromosome pairs)",
+    "C4": "BASELINE.json config 4 (hexaploid-wheat-sized all-vs-all, 21x21 chromosome pairs, ~10M graded hits)",
+}
+
+
+def workload_label(name):
+    return f"{name}: {WORKLOADS.get(name, 'synthetic workload ' + name)}"
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -100,7 +112,7 @@ def make_points(workload, seed_shift=0, scale=1.0):
 
 
 def params_for(cfg):
-    from wgdi_b200.engine import ChainParams
+    from wgdi_b200.params import ChainParams            # plain dataclass: the CPU arm loads nothing of the CUDA product
     return ChainParams(mg1=cfg.mg[0], mg2=cfg.mg[1], grading=tuple(cfg.grading), pvalue=cfg.pvalue)
 
 
@@ -124,7 +136,7 @@ def cpu_port_pass(pts, prm, threads):
     return dt, int(bt.n_blk[0].sum() + bt.n_blk[1].sum())
 
 
-def icl_wall_time(workload, device):
+def icl_wall_time(workload, device, bi=True, repeats=3):
     """`-icl` wall time per genome pair: conf in -> collinearity file out through the drop-in driver
     (`mycollinearity(options).run()`: parse gff/lens/m8, filter, grade, GPU chaining, write the file)."""
     import contextlib
@@ -140,7 +152,7 @@ def icl_wall_time(workload, device):
         conf = synth.write_dataset(ds, d)
         blast_mb = os.path.getsize(os.path.join(d, "blast.m8")) / 1e6
         best, timing, native = None, None, None
-        for _ in range(3):
+        for _ in range(repeats):
             opts = list(base.load_conf(conf, "collinearity")) + [("device", str(device))]
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(io.StringIO()):
@@ -153,10 +165,12 @@ def icl_wall_time(workload, device):
             if best is None or dt < best:
                 best, timing, native = dt, m.timing, m.native
         out_mb = os.path.getsize(dict(opts)["savefile"]) / 1e6
-        res = {"value": best, "unit": "s", "what": "conf in -> collinearity file out, best of 3, files in tmpfs",
+        res = {"value": best, "unit": "s", "what": f"{workload}: conf in -> collinearity file out, best of {repeats}, files in tmpfs",
                "blast_rows": int(len(ds.q)), "blast_mb": round(blast_mb, 1), "out_mb": round(out_mb, 1),
                "ingest_s": timing.get("ingest_s"), "chain_s": timing.get("chain_s"), "write_s": timing.get("write_s"),
                "host_path": "native (libicl_host.so)" if native else "pandas"}
+        if not bi:
+            return res
         # the tool every user runs next: `-bi` on the file just written, conf in -> CSV out
         try:
             from wgdi_b200.block_info import block_info
@@ -179,10 +193,49 @@ def icl_wall_time(workload, device):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def reference_sample(pts, prm, k, max_points, gpu_blocks=None):
+    """The REAL reference (unmodified wgdi/collinearity.py from oracle/_ref, see oracle/make_ref.py) on a stratified sample
+    of chromosome pairs at the inner seam `collinearity(options, points).run()`, one pair per host core; the whole-workload
+    figure is an extrapolation with the per-pair model fitted on the sample.  With `gpu_blocks` (all blocks
+    of >= 5 gene pairs of the same comparison from the CUDA path) the sampled pairs are compared block by block."""
+    from oracle import ref_leg
+    if not ref_leg.available():
+        return {"unavailable": "oracle/_ref/wgdi/collinearity.py not present (run `make -C oracle ref` where /root/reference exists)"}
+    options = [("grading", ",".join(map(str, prm.grading))), ("mg", f"{prm.mg1},{prm.mg2}"), ("pvalue", str(prm.pvalue))]
+    r = ref_leg.time_sample(pts, options, k=k, max_points=max_points)
+    blocks = r.pop("blocks")
+    out = {"kind": "reference", "what": "unmodified wgdi/collinearity.py: collinearity(options, points).run() per chromosome pair, "
+           "one pair per process; whole-workload numbers are EXTRAPOLATED with t = a*n + b*n^2 fitted on the sample and the "
+           "reference's static chunking of pairs over `cores` processes (run_colliearity.py:123-132)",
+           "sample": f"{len(r['pairs'])} chromosome pairs of the workload (largest" + (f" <= {max_points} points" if max_points else "") +
+                     ", median, smallest, random), " + f"{sum(r['points'])} points, measured",
+           **r}
+    if gpu_blocks is not None:
+        same, checked = True, 0
+        for p, ref_blocks in blocks.items():
+            keep = [b for b in ref_blocks if len(b[0]) >= 5]                       # run_colliearity.py:178
+            idx = np.flatnonzero(gpu_blocks.pair == p)
+            pv = np.round(gpu_blocks.p_raw[idx], 4)                                 # collinearity.py:153
+            idx = idx[~(pv > prm.pvalue)]
+            if len(idx) != len(keep):
+                same = False
+                continue
+            for b, (l1, l2, pval, sc) in zip(idx, keep):
+                a0, a1 = gpu_blocks.member_off[b], gpu_blocks.member_off[b + 1]
+                same &= bool((gpu_blocks.loc1[a0:a1] == l1).all() and (gpu_blocks.loc2[a0:a1] == l2).all() and
+                             gpu_blocks.score[b] == sc and np.round(gpu_blocks.p_raw[b], 4) == pval)
+                checked += 1
+        out["blocks_compared_with_gpu"] = checked
+        out["identical_to_gpu"] = bool(same)
+    return out
+
+
 def run_reference_arm(args, rank, world):
     """The reference's algorithm on the host cores.  The reference is pure Python (6-8 ms per point per core,
-    BASELINE.md) and does not exist on the GPU box, so this arm times the oracle's C port of it (kind "port"),
-    multi-threaded over chromosome pairs like the reference's worker pool."""
+    BASELINE.md): the timed steps run the oracle's C port of it (kind "port"), multi-threaded over chromosome pairs like the
+    reference's worker pool, on the whole workload; next to it `cpu_baseline.reference_sample` times the unmodified
+    reference itself on a stratified sample of chromosome pairs (oracle/_ref) and extrapolates.  Nothing of the CUDA
+    product is imported here."""
     if rank != 0:
         return
     from oracle import c_oracle
@@ -196,14 +249,22 @@ def run_reference_arm(args, rank, world):
     times = [cpu_port_pass(pts, prm, threads)[0] for _ in range(args.steps)]
     T = float(np.sum(times))
     value = n * args.steps / T
+    sample = None
+    if not args.no_reference_sample:
+        try:
+            sample = reference_sample(pts, prm, k=min(8, threads), max_points=None)
+        except Exception as e:                              # noqa: BLE001 — the timed port steps stand on their own
+            sample = {"error": f"{type(e).__name__}: {e}"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "hits/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: BASELINE.json config 2 (Vitis-sized self comparison)", "graded_hits": n,
-                   "chromosome_pairs": pts["n_pairs"]},
+        "config": {"workload": workload_label(args.workload), "graded_hits": n, "chromosome_pairs": pts["n_pairs"],
+                   "note": "one comparison on the host cores whatever --gpus says: at N > 1 the GPU arm runs N such comparisons, "
+                           "so the driver's ratio compares RATES (hits/s), not equal amounts of work"},
         "cpu_baseline": {"value": value, "unit": "hits/s", "cores": threads, "kind": "port",
-                         "sample": f"full {args.workload} workload per step ({n} hits), C port of the reference algorithm"},
+                         "sample": f"full {args.workload} workload per step ({n} hits), C port of the reference algorithm",
+                         "reference_sample": sample},
         "e2e": {"value": value, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -296,6 +357,101 @@ def run_portable_leg(args, local, rank, world, features=PORTABLE_NUMPY):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+def strong_leg(args, rank, world, local, barrier, sort_threads):
+    """BASELINE configs 3 / 4 and the north_star's target: ONE comparison whose chromosome pairs are LPT-sharded over the N
+    ranks (wgdi_b200/shard.py; the reference's analogue is run_colliearity.py:117-141).  Every step is end to end: each
+    rank uploads its shard from page-locked host memory, chains, ranks and extracts it, hands its blocks to rank 0 through
+    /dev/shm, and rank 0 merges them into the reference's emission order (shard.merge_blocks) — all inside the timed
+    region, no collective on the data path.  Returns rank 0's record (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    from wgdi_b200 import shard
+    from wgdi_b200.engine import Blocks, IclEngine
+    FIELDS = ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx")
+    full = make_points(args.strong_workload)                 # same seed on every rank: the same comparison
+    prm = params_for(full["cfg"])
+    total = len(full["loc1"])
+    sizes = np.bincount(full["pair_id"], minlength=full["n_pairs"])
+    owner = shard.lpt_assign(shard.pair_cost(sizes), world)
+    pts = shard.shard_points(full, rank, world, owner=owner)
+    n_local = len(pts["loc1"])
+    shm = f"/dev/shm/icl_strong_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+    os.makedirs(shm, exist_ok=True)
+    eng = IclEngine(local, sort_threads=sort_threads)
+    host_in = {}
+    for k in ("pair_id", "loc1", "loc2", "grading"):
+        buf = eng._buf("in_" + k, n_local, np.int32)
+        buf[:] = pts[k]
+        host_in[k] = buf
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    phase = {}
+    merged = None
+
+    def step(timed):
+        nonlocal merged
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        b = eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm,
+                      min_members=5, copy=False)
+        t1 = time.perf_counter()
+        if world > 1:
+            # host gather: every rank's blocks (pair ids and row indices mapped back to the whole comparison) -> rank 0
+            part = {f: getattr(b, f) for f in FIELDS}
+            part["pair"] = pts["global_pair"][b.pair]
+            part["member_idx"] = pts["rows"][b.member_idx].astype(np.int32)
+            np.savez(os.path.join(shm, f"part{rank}.npz"), **part)
+            barrier()
+            if rank == 0:
+                parts = []
+                for r in range(world):
+                    with np.load(os.path.join(shm, f"part{r}.npz")) as z:
+                        parts.append(Blocks(*[z[f] for f in FIELDS]))
+                merged = shard.merge_blocks(parts)
+            barrier()
+        else:
+            merged = b
+        t2 = time.perf_counter()
+        if timed:
+            for k, v in eng.timings().items():
+                phase.setdefault(k, []).append(v)
+            phase.setdefault("chain_call_ms", []).append((t1 - t0) * 1e3)
+            phase.setdefault("gather_merge_ms", []).append((t2 - t1) * 1e3)
+        return t2 - t0
+
+    try:
+        for _ in range(2):
+            step(False)
+        T = sum(step(True) for _ in range(args.steps))
+    finally:
+        eng.close()
+    mean = {k: float(np.mean(v)) for k, v in phase.items()}
+    keys = sorted(mean)
+    vec = torch.tensor([T] + [mean[k] for k in keys] + [float(n_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mn = vec.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    else:
+        mx = mn = vec
+    if rank != 0:
+        return None
+    mx, mn = mx.tolist(), mn.tolist()
+    T = mx[0]
+    ph_max = dict(zip(keys, mx[1:-1]))
+    dev = {k: v for k, v in ph_max.items() if k not in ("chain_call_ms", "gather_merge_ms")}
+    limiting = max(dev, key=dev.get) if dev else None
+    return {"workload": workload_label(args.strong_workload) + f", ONE comparison, chromosome pairs LPT-sharded over {world} GPU(s)",
+            "scaling": "strong", "value": total * args.steps / T, "unit": "hits/s", "ms_per_step": 1e3 * T / args.steps,
+            "graded_hits": total, "chromosome_pairs": int(full["n_pairs"]), "blocks": int(len(merged)),
+            "what": "end to end per step: H2D of every rank's shard from pinned host memory, sort, DP, rank, extraction, "
+                    "blocks to the host, host gather to rank 0 (/dev/shm) and merge into emission order; max over ranks",
+            "hits_per_rank": {"max": int(mx[-1]), "min": int(mn[-1])},
+            "phase_ms_max_over_ranks": ph_max, "limiting_device_phase": limiting,
+            "lpt_cost": "points + points^2 / 65536 per chromosome pair (shard.pair_cost)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,6 +461,9 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wall", action="store_true")
+    ap.add_argument("--no-reference-sample", action="store_true", help="skip the timed sample of the real reference (oracle/_ref)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg")
+    ap.add_argument("--strong-workload", default="C4", help="ONE comparison sharded over all ranks (strong scaling leg)")
     ap.add_argument("--batch", type=int, default=8, help="comparisons in the pipelined-batch leg (0 = skip)")
     ap.add_argument("--portable-child", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--portable-check", action="store_true", help=argparse.SUPPRESS)
@@ -538,6 +697,9 @@ def main():
         batch = {"value": total_points * args.batch / t_batch, "unit": "hits/s", "comparisons": args.batch * world,
                  "ms_per_comparison": 1e3 * t_batch / args.batch, "engines_per_gpu": 2,
                  "what": "independent comparisons pipelined through two engines per GPU, each job uploads its points"}
+    strong = None
+    if not args.no_strong:
+        strong = strong_leg(args, rank, world, local, barrier, sort_threads)
     clocks = sampler.stop() if rank == 0 else None
     counters = eng.counters()
 
@@ -568,7 +730,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
             "ms_per_step_cuda_events": 1e3 * ev_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: BASELINE.json config 2 (Vitis-sized self comparison), one comparison per GPU",
+            "config": {"workload": workload_label(args.workload) + ", one comparison per GPU",
                        "graded_hits": total_points, "chromosome_pairs": total_pairs, "blocks": n_blocks,
                        "mg": list(mine["cfg"].mg), "grading": list(mine["cfg"].grading),
                        "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
@@ -601,9 +763,19 @@ def main():
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
         }
+        blocks_copy = None
+        if world == 1 and not args.no_cpu_baseline and not args.no_reference_sample:
+            blocks_copy = eng.run_resident(prm, min_members=5, copy=True)           # detached: the engine is closed below
+        if strong is not None:
+            line["strong"] = strong
         if not args.no_wall and world == 1:
             eng.close()
             line["icl_wall"] = icl_wall_time(args.workload, local)
+            if not args.no_strong and args.strong_workload != args.workload:
+                try:
+                    line["icl_wall_strong_workload"] = icl_wall_time(args.strong_workload, local, bi=False, repeats=1)
+                except Exception as e:                      # noqa: BLE001
+                    line["icl_wall_strong_workload"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline and world == 1:
             from oracle import c_oracle
             c_oracle.build()
@@ -613,6 +785,14 @@ def main():
             line["cpu_baseline"] = {"value": len(mine["loc1"]) / dt, "unit": "hits/s", "cores": threads, "kind": "port",
                                     "sample": f"full {args.workload} workload, 1 pass ({len(mine['loc1'])} hits, {nb_cpu} blocks), "
                                               "oracle C port of the reference algorithm, pthread pool over chromosome pairs"}
+            if not args.no_reference_sample:
+                # the real reference on a bounded stratified sample of this workload's chromosome pairs (about 25 s on all
+                # cores), compared block by block with what the CUDA path returned for the same pairs
+                try:
+                    line["cpu_baseline"]["reference_sample"] = reference_sample(mine, prm, k=min(8, threads), max_points=3000,
+                                                                                 gpu_blocks=blocks_copy)
+                except Exception as e:                      # noqa: BLE001
+                    line["cpu_baseline"]["reference_sample"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -23,6 +23,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import IclError, icl_blocks, icl_params
+from .params import ChainParams, nargsort_desc  # noqa: F401  (re-exported: the reference-facing names live in params.py)
 
 try:                                    # numpy's own argsort routine, GIL-free (wgdi_b200/csrc/npsort.c)
     from . import _npsort
@@ -52,37 +53,6 @@ def _npsort_ok():
                 ok = False
         _NPSORT_OK = ok
     return _NPSORT_OK
-
-
-@dataclass
-class ChainParams:
-    """Typed `[collinearity]` options of the DP engine (wgdi/collinearity.py:6-28)."""
-    mg1: int = 40
-    mg2: int = 40
-    grading: tuple = (50, 40, 25)
-    pvalue: float = 1.0
-    coverage_ratio: float = 0.8
-    over_gap: int = 3            # inner over_gap (collinearity.py:13); not a usable conf key (string bug)
-
-    @classmethod
-    def from_options(cls, options):
-        o = {str(k): v for k, v in options}
-        p = cls()
-        if "grading" in o:
-            p.grading = tuple(int(k) for k in str(o["grading"]).split(","))
-        if "mg" in o:
-            p.mg1, p.mg2 = [int(k) for k in str(o["mg"]).split(",")]
-        p.pvalue = float(o.get("pvalue", 1))
-        p.coverage_ratio = float(o.get("coverage_ratio", 0.8))
-        return p
-
-
-def nargsort_desc(a: np.ndarray) -> np.ndarray:
-    """pandas.core.sorting.nargsort(a, kind='quicksort', ascending=False) for NaN-free `a`:
-    reverse, numpy's unstable argsort, map back, reverse (collinearity.py:49,60; run_colliearity.py:67)."""
-    n = len(a)
-    r = a[::-1].argsort(kind="quicksort")
-    return (n - 1 - r)[::-1]
 
 
 @dataclass

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .engine import nargsort_desc
+from .params import nargsort_desc
 
 
 def grade_hits(q, bits, multiple, repeat_number, grading, blue_extra=4):

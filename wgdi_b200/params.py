@@ -1,0 +1,38 @@
+"""Typed options and the pandas sort rule of the `-icl` path — pure numpy, no native library behind it, so that the host
+ingest, the synthetic-data generator and the benchmark's CPU arm can use them without loading anything CUDA."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class ChainParams:
+    """Typed `[collinearity]` options of the DP engine (wgdi/collinearity.py:6-28)."""
+    mg1: int = 40
+    mg2: int = 40
+    grading: tuple = (50, 40, 25)
+    pvalue: float = 1.0
+    coverage_ratio: float = 0.8
+    over_gap: int = 3            # inner over_gap (collinearity.py:13); not a usable conf key (string bug)
+
+    @classmethod
+    def from_options(cls, options):
+        o = {str(k): v for k, v in options}
+        p = cls()
+        if "grading" in o:
+            p.grading = tuple(int(k) for k in str(o["grading"]).split(","))
+        if "mg" in o:
+            p.mg1, p.mg2 = [int(k) for k in str(o["mg"]).split(",")]
+        p.pvalue = float(o.get("pvalue", 1))
+        p.coverage_ratio = float(o.get("coverage_ratio", 0.8))
+        return p
+
+
+def nargsort_desc(a: np.ndarray) -> np.ndarray:
+    """pandas.core.sorting.nargsort(a, kind='quicksort', ascending=False) for NaN-free `a`:
+    reverse, numpy's unstable argsort, map back, reverse (collinearity.py:49,60; run_colliearity.py:67)."""
+    n = len(a)
+    r = a[::-1].argsort(kind="quicksort")
+    return (n - 1 - r)[::-1]

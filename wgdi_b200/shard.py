@@ -26,10 +26,20 @@ def lpt_assign(sizes, n_bins: int) -> np.ndarray:
     return owner
 
 
-def shard_points(points: dict, rank: int, world: int):
+def pair_cost(sizes) -> np.ndarray:
+    """Cost of a chromosome pair for the assignment.  Most device phases are linear in the pair's points, but a long pair
+    also holds the longest dependent work of the step (the DP sweep of its heaviest window, the top-level partitions of
+    its rank segment, its largest predecessor tree), which grows faster than the point count: a quadratic term that equals
+    the linear one at 65 536 points keeps two very long pairs off the same GPU when a few pairs dominate."""
+    n = np.asarray(sizes, np.float64)
+    return np.round(n + n * n / 65536.0).astype(np.int64)
+
+
+def shard_points(points: dict, rank: int, world: int, owner=None):
     """The sub-problem of `rank`: its pairs renumbered densely, plus the map back to global pair ids."""
-    sizes = np.bincount(points["pair_id"], minlength=points["n_pairs"])
-    owner = lpt_assign(sizes, world)
+    if owner is None:
+        sizes = np.bincount(points["pair_id"], minlength=points["n_pairs"])
+        owner = lpt_assign(pair_cost(sizes), world)
     mine = np.flatnonzero(owner == rank).astype(np.int32)
     local_of = np.full(points["n_pairs"], -1, np.int32)
     local_of[mine] = np.arange(len(mine), dtype=np.int32)
@@ -53,7 +63,9 @@ def merge_blocks(parts):
     midx = np.concatenate([p.member_idx for p in parts])
     mo = m[order].astype(np.int64)
     new_off = np.r_[0, np.cumsum(mo)]
-    gather = np.concatenate([np.arange(starts[b], starts[b] + m[b]) for b in order]) if len(order) else np.zeros(0, np.int64)
+    # member positions of the blocks in their new order: start of the block's run + offset inside it
+    gather = (np.repeat(starts[order], mo) + (np.arange(int(new_off[-1]), dtype=np.int64) - np.repeat(new_off[:-1], mo))
+              if len(order) else np.zeros(0, np.int64))
 
     def cat(name):
         return np.concatenate([getattr(p, name) for p in parts])[order]
