@@ -70,6 +70,10 @@ struct icl_ctx {
     // edges
     Buf<uint32_t> ecnt, eoff;
     Buf<uint2> edges;
+    Buf<unsigned long long> tile_state;   // edge kernel: per-tile counts and staging places, pool cursor, per-item first records
+    Buf<uint32_t> tile_dst;               // first record of every tile in the source-ordered stream
+    Buf<uint2> edge_stage;                // staging pool: tiles in the order they reserved room
+    uint64_t edge_cap = 0;                // records the edge pool holds
     int64_t n_edges = 0;
     int32_t max_span = 0;            // largest (target position - source position) over all edges
     int32_t chain_kernel = 0;        // 1 = shared-memory ring kernel, 0 = generic global-memory kernel
@@ -79,6 +83,7 @@ struct icl_ctx {
     bool streamed = false, dp_begun = false;
     bool order_on_device = false;    // icl_rank_device filled order_in
     bool keys_on_device = false;     // ... from score32 (numpy flavours)
+    bool order_on_device_used = false;   // the current icl_extract takes the device's order
     int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
@@ -249,7 +254,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_item_order.release(); c->d_pair_order.release();
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
-    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
+    c->ecnt.release(); c->eoff.release(); c->edges.release(); c->tile_state.release(); c->tile_dst.release(); c->edge_stage.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
     c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
@@ -586,52 +591,157 @@ struct EdgeEnum {
 #define ICL_EDGE_CHUNK 512           // records per TMA chunk (4 KB)
 
 #ifndef ICL_EMU
-// Edge enumeration, one thread per source, 256 consecutive sources per CTA.  Consecutive sources have heavily
-// overlapping bands (the points are sorted), so the CTA stages the union of its bands — a contiguous slice of
-// X1 / X2 / G — in shared memory once and every thread scans its own band from there.
-#define ICL_EDGE_TILE 1536
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_edges_tile(EdgeEnum ee, int64_t V, int64_t n, uint32_t *ecnt,
-                                                    const uint32_t *eoff, uint2 *edges, const int64_t *off, int32_t *stats) {
-    __shared__ int32_t sX1[ICL_EDGE_TILE], sX2[ICL_EDGE_TILE], sG[ICL_EDGE_TILE];
-    __shared__ int32_t s_kmin, s_kmax;
-    const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (threadIdx.x == 0) { s_kmin = 0x7fffffff; s_kmax = 0; }
+// Edge enumeration: 256 consecutive sources per CTA (one thread each); every record is built ONCE.
+//  * Consecutive sources have heavily overlapping bands (the points are sorted), so the CTA stages the union of its
+//    bands — a contiguous slice of X1 / X2 / G — in shared memory.
+//  * stage 1: every thread scans ITS band for the column window with 16-byte shared-memory loads and does nothing on a
+//    hit but append the position to its own short list (2-byte stores): the scan stays convergent.  (ncu on the
+//    two-pass predecessor: issue-bound, 431 M warp instructions, 10-16 of 32 threads active around every hit.)
+//  * stage 2: the thread walks its hit list (a few entries) and keeps the candidates the sweep can see (s > 0 or
+//    row-last, see above); a block scan numbers them inside the tile.
+//  * stage 3: the tile reserves room in a staging pool with one atomic and its threads store their records there,
+//    contiguous and in source order INSIDE the tile.  Tiles land in the pool in any order; k_edges_place then moves every
+//    tile's run to its place in the source-ordered stream (a coalesced copy of 8 E bytes; the tile offsets are one small
+//    scan).  A chained scan with look-back inside this kernel was tried first: correct, but every tile waited for the
+//    slowest tile before it (barrier stall 12.8 warps per issue, 48 % of the samples in the look-back: profiles/).
+// Only the record index at the first point of every (pair, direction) item is kept (eoff[item start], eoff[V] = total):
+// records name their source, the DP kernel needs nothing else.
+#define ICL_EDGE_TILE 2048
+#define ICL_EDGE_HITS 24             // hit slots per thread; a source with more hits re-scans its band in stages 2 and 3
+struct EdgeScan {
+    uint32_t *tile_cnt;              // [tiles + 1] records of the tile
+    uint32_t *tile_at;               // [tiles] where the tile's run starts in the staging pool
+    uint32_t *first_local;           // [2P] tile-local record index of the first source of every item
+    unsigned long long *cursor;      // staging pool fill (may exceed cap: then the caller grows the pool and repeats)
+    uint2 *staging;
+    uint64_t cap;                    // records the pool holds
+    const int64_t *seg_off;          // [2P + 1] first V position of every item
+};
+
+__global__ void __launch_bounds__(256, 4) k_edges_enum(EdgeEnum ee, int64_t V, EdgeScan es, int32_t *stats) {
+    __shared__ __align__(16) int32_t sX2[ICL_EDGE_TILE + 8];
+    __shared__ int32_t sX1[ICL_EDGE_TILE + 8], sG[ICL_EDGE_TILE + 8];
+    __shared__ uint16_t hl[ICL_EDGE_HITS * 256];
+    __shared__ int32_t s_kmin, s_kmax, s_span;
+    __shared__ unsigned long long s_base;
+    typedef cub::BlockScan<uint32_t, 256> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_kmin = 0x7fffffff; s_kmax = 0; s_span = 0; }
     __syncthreads();
+    const uint32_t tile = blockIdx.x;
+    const int64_t v = (int64_t)tile * 256 + tid;
     int32_t k0 = 0, k1 = 0, x1 = 0, x2 = 0, nr = 0;
     int64_t base = 0;
     bool has = false;
     if (v < V) has = ee.band(v, k0, k1, x1, x2, base, nr);
     const bool small = has && (k1 - k0 <= 384);
-    if (small) { atomicMin(&s_kmin, k0); atomicMax(&s_kmax, k1); }
-    __syncthreads();
-    const int32_t kmin = s_kmin, kmax = s_kmax;
-    const bool tiled = kmax > kmin && kmax - kmin <= ICL_EDGE_TILE;
-    if (tiled) {
-        for (int32_t k = kmin + threadIdx.x; k < kmax; k += 256) { sX1[k - kmin] = ee.X1[k]; sX2[k - kmin] = ee.X2[k]; sG[k - kmin] = ee.G[k]; }
+    {
+        int32_t lo = small ? k0 : 0x7fffffff, hi = small ? k1 : 0;
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((tid & 31) == 0 && hi > lo) { atomicMin(&s_kmin, lo); atomicMax(&s_kmax, hi); }
     }
     __syncthreads();
+    const int32_t kbase = s_kmin & ~3, kmax = s_kmax;          // 16-byte alignment of the staged slice follows the global one
+    const bool tiled = kmax > kbase && kmax - kbase <= ICL_EDGE_TILE;
+    if (tiled) {
+        for (int32_t k = kbase + tid; k < kmax; k += 256) { sX1[k - kbase] = ee.X1[k]; sX2[k - kbase] = ee.X2[k]; sG[k - kbase] = ee.G[k]; }
+    }
+    __syncthreads();
+    const int32_t mg2 = ee.mg2;
+    const bool fast = tiled && small;
+    const int32_t a = k0 - kbase, b = k1 - kbase;              // the band inside the staged slice (fast only)
+    uint32_t cnt = 0, nh = 0;                                  // records of this source; hits of stage 1
+    int32_t span = 0;
+    // what the sweep can see of candidate q (staged position): s > 0, or the last candidate of its row
+    auto keep = [&](int32_t q) {
+        const int32_t r = sX1[q];
+        const int32_t sc = sG[q] - (r - x1 + sX2[q] - x2);
+        return sc > 0 || (q + 1 == b) || sX1[q + 1] != r || (sX2[q + 1] - x2 >= mg2);
+    };
+    if (fast) {
+        // ---- stage 1: positions of the band whose column lies in (x2, x2 + mg2)
+        const uint32_t w = (uint32_t)(mg2 - 1);
+        const int32_t xs = x2 + 1;
+        auto hit = [&](int32_t j) {
+            hl[(nh < ICL_EDGE_HITS ? nh : ICL_EDGE_HITS - 1) * 256 + tid] = (uint16_t)j;
+            nh++;
+        };
+        int32_t j = a;
+        for (; j < b && (j & 3); j++)
+            if ((uint32_t)(sX2[j] - xs) < w) hit(j);
+        for (; j + 4 <= b; j += 4) {
+            const int4 q = *(const int4 *)(sX2 + j);
+            if ((uint32_t)(q.x - xs) < w) hit(j);
+            if ((uint32_t)(q.y - xs) < w) hit(j + 1);
+            if ((uint32_t)(q.z - xs) < w) hit(j + 2);
+            if ((uint32_t)(q.w - xs) < w) hit(j + 3);
+        }
+        for (; j < b; j++)
+            if ((uint32_t)(sX2[j] - xs) < w) hit(j);
+        // ---- stage 2: keep what the sweep can see, in visiting order
+        if (nh <= ICL_EDGE_HITS) {
+            for (uint32_t h = 0; h < nh; h++) {
+                const int32_t q = hl[h * 256 + tid];
+                if (keep(q)) { hl[cnt * 256 + tid] = (uint16_t)q; cnt++; span = kbase + q - (int32_t)v; }
+            }
+        } else {                                               // more hits than slots: straight from the staged band
+            for (int32_t q = a; q < b; q++)
+                if ((uint32_t)(sX2[q] - xs) < w && keep(q)) { cnt++; span = kbase + q - (int32_t)v; }
+        }
+    } else if (has) {                                          // oversized band or tile: the generic scan on global memory
+        ee.scan(k0, k1, x1, x2, base, nr, ee.X1, ee.X2, ee.G, [&](int32_t k, int32_t, int32_t, int32_t) { cnt++; span = k - (int32_t)v; });
+    }
+    uint32_t off_in_tile, tile_total;
+    Scan(scan_tmp).ExclusiveSum(cnt, off_in_tile, tile_total);
+    if (span > 0) atomicMax(&s_span, span);
+    if (tid == 0) {
+        const unsigned long long at = tile_total ? atomicAdd(es.cursor, (unsigned long long)tile_total) : 0ull;
+        s_base = at;
+        es.tile_cnt[tile] = tile_total;
+        es.tile_at[tile] = (uint32_t)at;
+    }
+    __syncthreads();
+    if (tid == 0 && s_span > stats[3]) atomicMax(&stats[3], s_span);
     if (v >= V) return;
-    const int32_t *pX1 = (tiled && small) ? sX1 - kmin : ee.X1, *pX2 = (tiled && small) ? sX2 - kmin : ee.X2,
-                  *pG = (tiled && small) ? sG - kmin : ee.G;
-    if (!FILL) {
-        uint32_t cnt = 0;
-        int32_t span = 0;
-        if (has) ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t k, int32_t, int32_t, int32_t) { cnt++; span = k - (int32_t)v; });
-        ecnt[v] = cnt;
-        // largest distance a source reaches ahead (candidates are visited in increasing position): sizes the
-        // shared-memory window of the DP kernel.  Monotonic max: the plain read filters almost every atomic away.
-        if (span > stats[3]) atomicMax(&stats[3], span);
+    const int32_t it = ee.itemof[v];
+    const int64_t istart = es.seg_off[it];
+    if (v == istart) es.first_local[it] = off_in_tile;
+    if (cnt == 0) return;
+    const unsigned long long e0 = s_base + off_in_tile;
+    if (e0 + cnt > es.cap) return;                             // pool too small: the caller sees the cursor and repeats
+    const uint32_t srel = (uint32_t)(v - istart) << 8;
+    uint2 *out = es.staging + e0;
+    // ---- stage 3: the records
+    auto record = [&](int32_t q) {
+        const int32_t dr = sX1[q] - x1, dc = sX2[q] - x2;
+        const int32_t sc = sG[q] - (dr + dc);
+        return make_uint2(((uint32_t)(kbase + q - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                          ((uint32_t)(sc > 0 ? sc : 0) & 0xffu) | srel);
+    };
+    if (fast && nh <= ICL_EDGE_HITS) {
+        for (uint32_t h = 0; h < cnt; h++) out[h] = record(hl[h * 256 + tid]);
+    } else if (fast) {
+        const uint32_t w = (uint32_t)(mg2 - 1);
+        for (int32_t q = a; q < b; q++)
+            if ((uint32_t)(sX2[q] - x2 - 1) < w && keep(q)) *out++ = record(q);
     } else {
-        uint32_t e = eoff[v];
-        if (eoff[v + 1] == e) return;
-        const int32_t it = ee.itemof[v];
-        const int64_t a = off[it >= ee.P ? it - ee.P : it] + (it >= ee.P ? n : 0);
-        const uint32_t srel = (uint32_t)(v - a) << 8;
-        ee.scan(k0, k1, x1, x2, base, nr, pX1, pX2, pG, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
-            edges[e++] = make_uint2(((uint32_t)(k - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
-                                    ((uint32_t)sc & 0xffu) | srel);
+        ee.scan(k0, k1, x1, x2, base, nr, ee.X1, ee.X2, ee.G, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
+            *out++ = make_uint2(((uint32_t)(k - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                                ((uint32_t)sc & 0xffu) | srel);
         });
+    }
+}
+
+// every tile's run of records from where it landed in the staging pool to its place in the source-ordered stream
+__global__ void __launch_bounds__(256) k_edges_place(uint32_t tiles, const uint32_t *tile_cnt, const uint32_t *tile_at,
+                                                     const uint32_t *tile_dst, const uint2 *staging, uint2 *edges) {
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint32_t n = tile_cnt[t];
+        const uint2 *src = staging + tile_at[t];
+        uint2 *dst = edges + tile_dst[t];
+        for (uint32_t i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
     }
 }
 #endif
@@ -641,19 +751,60 @@ static int phase_edges(icl_ctx *c) {
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->ecnt.reserve(st, V + 2) || c->eoff.reserve(st, V + 2)) return st.code;
+    if (c->eoff.reserve(st, V + 2)) return st.code;
     EdgeEnum ee{c->X1.p, c->X2.p, c->G.p, c->itemof.p, c->rowptr.p, c->d_nrows.p, c->d_rb.p, c->R, c->P, c->prm.mg1, c->prm.mg2};
-    uint32_t *ecnt = c->ecnt.p;
     int32_t *stats = c->stats.p;
     ICL_CUDA(st, dev_memset(c->stats.p + 3, 0, sizeof(int32_t), s));
 #ifndef ICL_EMU
-    const unsigned eblocks = (unsigned)((V + 255) / 256);
+    const unsigned tiles = (unsigned)((V + 255) / 256);
+    uint64_t total = 0;
+    int32_t span = 0;
     if (V > 0) {
-        k_edges_tile<false><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, nullptr, nullptr, c->d_pair_off.p, stats);
+        // per tile: count, place in the staging pool, place in the stream; then cursor (8 B, aligned) and per-item first records
+        if (c->tile_state.reserve(st, 2 * (size_t)tiles + (size_t)P + 8) || c->tile_dst.reserve(st, (size_t)tiles + 2)) return st.code;
+        uint32_t *tile_cnt = (uint32_t *)c->tile_state.p, *tile_at = tile_cnt + tiles + 2;
+        unsigned long long *cursor = c->tile_state.p + tiles + 2;
+        uint32_t *first_local = (uint32_t *)(cursor + 1);
+        // the pools are sized from experience (records per source: C2 1.3, wide windows a few times that) and grown when
+        // a comparison needs more: the kernel reports the real total and stores nothing that does not fit
+        uint64_t want = std::max<uint64_t>(c->edge_cap, 3 * (uint64_t)V + 4096);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if (c->edges.reserve(st, (size_t)want + 2 * ICL_EDGE_CHUNK + 16) || c->edge_stage.reserve(st, (size_t)want + 16)) return st.code;
+            c->edge_cap = want;
+            ICL_CUDA(st, dev_memset(cursor, 0, sizeof(unsigned long long), s));
+            EdgeScan es{tile_cnt, tile_at, first_local, cursor, c->edge_stage.p, want, c->d_seg_off.p};
+            k_edges_enum<<<tiles, 256, 0, s>>>(ee, V, es, stats);
+            ICL_COUNT_KERNEL();
+            ICL_CUDA(st, cudaGetLastError());
+            ICL_CUDA(st, d2h(&total, cursor, sizeof(uint64_t), s));
+            ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
+            ICL_CUDA(st, dev_sync(s));
+            if (total <= want) break;
+            want = total + total / 8 + 4096;                   // enumerate again into pools that hold everything
+        }
+        if (total >= (1ull << 32)) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 2^32 candidate records");
+        if (exclusive_sum_u32(st, c->tmp, tile_cnt, c->tile_dst.p, tiles, s)) return st.code;
+        const uint32_t *tile_dst = c->tile_dst.p;
+        k_edges_place<<<std::min<unsigned>(tiles, 148 * 8), 256, 0, s>>>(tiles, tile_cnt, tile_at, tile_dst, c->edge_stage.p, c->edges.p);
         ICL_COUNT_KERNEL();
         ICL_CUDA(st, cudaGetLastError());
+        {
+            // record index at the first point of every item (the DP kernel reads eoff[item start] and eoff[next start])
+            uint32_t *eoff = c->eoff.p;
+            const int64_t *seg_off = c->d_seg_off.p;
+            ICL_CUDA(st, foreach(s, 2 * (int64_t)P + 1, ICL_LAMBDA(int64_t it) {
+                if (it == 2 * (int64_t)P) { eoff[V] = tile_dst[tiles]; return; }
+                const int64_t a = seg_off[it];
+                if (seg_off[it + 1] > a) eoff[a] = tile_dst[a >> 8] + first_local[it];
+            }));
+        }
     }
+    c->n_edges = (int64_t)total;
+    c->max_span = span;
+    if (span >= 65536) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 65535 points inside one mg1-row window of a chromosome pair");
 #else
+    if (c->ecnt.reserve(st, V + 2)) return st.code;
+    uint32_t *ecnt = c->ecnt.p;
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
         uint32_t cnt = 0;
         int32_t span = 0;
@@ -661,7 +812,6 @@ static int phase_edges(icl_ctx *c) {
         ecnt[v] = cnt;
         if (span > stats[3]) atomic_max_i32(&stats[3], span);
     }));
-#endif
     if (exclusive_sum_u32(st, c->tmp, c->ecnt.p, c->eoff.p, V, s)) return st.code;
     uint32_t total = 0;
     int32_t span = 0;
@@ -674,13 +824,6 @@ static int phase_edges(icl_ctx *c) {
     if (c->edges.reserve(st, (size_t)total + 2 * ICL_EDGE_CHUNK + 16)) return st.code;
     const uint32_t *eoff = c->eoff.p;
     uint2 *edges = c->edges.p;
-#ifndef ICL_EMU
-    if (V > 0) {
-        k_edges_tile<true><<<eblocks, 256, 0, s>>>(ee, V, n, ecnt, eoff, edges, c->d_pair_off.p, stats);
-        ICL_COUNT_KERNEL();
-        ICL_CUDA(st, cudaGetLastError());
-    }
-#else
     const int32_t *itemof = c->itemof.p;
     const int64_t *off = c->d_pair_off.p;
     ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) {
@@ -695,7 +838,6 @@ static int phase_edges(icl_ctx *c) {
         });
     }));
 #endif
-    (void)P;
     return 0;
 }
 
@@ -1381,7 +1523,6 @@ static int phase_extract(icl_ctx *c) {
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
-    ICL_CUDA(st, dev_memset(c->seen.p, 0, (size_t)V, s));
     ICL_CUDA(st, dev_memset(c->hint.p, 0xFF, (size_t)V * sizeof(int2), s));
     ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));      // drop usedtimes < 1 (:50 / :61)
     const int2 *pd = c->pd.p;
@@ -1395,15 +1536,25 @@ static int phase_extract(icl_ctx *c) {
         uint64_t *key = c->key_a.p;
         uint32_t *idx = c->idx_a.p;
         uint8_t *seen = c->seen.p;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
-            idx[t] = (uint32_t)t;
-            const int32_t v = rank2v[t];
-            if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = (uint64_t)V; return; }   // not a permutation
-            seen[v] = 1;
-            key[t] = used[v] ? (uint64_t)(uint32_t)root[v] : (uint64_t)V;
-        }));
-        // a duplicate may slip through the unsynchronised test above, but then some point is never seen
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (!seen[v]) atomic_or_i32(&stats[2], 1); }));
+        if (c->order_on_device_used) {
+            // the order comes from the device's own sort: a permutation by construction, nothing to validate
+            ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+                idx[t] = (uint32_t)t;
+                const int32_t v = rank2v[t];
+                key[t] = used[v] ? (uint64_t)(uint32_t)root[v] : (uint64_t)V;
+            }));
+        } else {
+            ICL_CUDA(st, dev_memset(c->seen.p, 0, (size_t)V, s));
+            ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+                idx[t] = (uint32_t)t;
+                const int32_t v = rank2v[t];
+                if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = (uint64_t)V; return; }   // not a permutation
+                seen[v] = 1;
+                key[t] = used[v] ? (uint64_t)(uint32_t)root[v] : (uint64_t)V;
+            }));
+            // a duplicate may slip through the unsynchronised test above, but then some point is never seen
+            ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (!seen[v]) atomic_or_i32(&stats[2], 1); }));
+        }
     }
     if (V > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, vb, s)) return st.code;
     {
@@ -2907,6 +3058,7 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     LaunchScope scope(c, 2);
     c->timers[ICL_T_EXTRACT].start(s);
     if (c->order_in.reserve(st, 2 * n) || c->rank2v.reserve(st, V)) return st.code;
+    c->order_on_device_used = dev_order;
     if (n > 0) {
         if (dev_order) {
             // order_in already holds the device argsort
