@@ -595,9 +595,10 @@ struct EdgeEnum {
 //  * Consecutive sources have heavily overlapping bands (the points are sorted), so the CTA stages the union of its
 //    bands — a contiguous slice of X1 / X2 / G — in shared memory.
 //  * stage 1: every thread scans ITS band for the column window with 16-byte shared-memory loads and does nothing on a
-//    hit but append the position to its own short list (2-byte stores): the scan stays convergent.  (ncu on the
-//    two-pass predecessor: issue-bound, 431 M warp instructions, 10-16 of 32 threads active around every hit.)
-//  * stage 2: the thread walks its hit list (a few entries) and keeps the candidates the sweep can see (s > 0 or
+//    hit but set a bit (a predicated OR): the scan stays convergent.  (ncu on the two-pass predecessor: issue-bound,
+//    431 M warp instructions, 10-16 of 32 threads active around every hit; a hit LIST appended under a branch still spent
+//    28 % of its instructions in the append at 11.6 threads.)
+//  * stage 2: the thread walks the set bits of a word (a few) and keeps the candidates the sweep can see (s > 0 or
 //    row-last, see above); a block scan numbers them inside the tile.
 //  * stage 3: the tile reserves room in a staging pool with one atomic and its threads store their records there,
 //    contiguous and in source order INSIDE the tile.  Tiles land in the pool in any order; k_edges_place then moves every
@@ -607,7 +608,8 @@ struct EdgeEnum {
 // Only the record index at the first point of every (pair, direction) item is kept (eoff[item start], eoff[V] = total):
 // records name their source, the DP kernel needs nothing else.
 #define ICL_EDGE_TILE 2048
-#define ICL_EDGE_HITS 24             // hit slots per thread; a source with more hits re-scans its band in stages 2 and 3
+#define ICL_EDGE_BAND 384            // bands up to this many points are scanned from the staged slice
+#define ICL_EDGE_WORDS ((ICL_EDGE_BAND + 3 + 31) / 32 + 1)   // candidate-bit words per thread
 struct EdgeScan {
     uint32_t *tile_cnt;              // [tiles + 1] records of the tile
     uint32_t *tile_at;               // [tiles] where the tile's run starts in the staging pool
@@ -619,9 +621,9 @@ struct EdgeScan {
 };
 
 __global__ void __launch_bounds__(256, 4) k_edges_enum(EdgeEnum ee, int64_t V, EdgeScan es, int32_t *stats) {
-    __shared__ __align__(16) int32_t sX2[ICL_EDGE_TILE + 8];
+    __shared__ __align__(16) int32_t sX2[ICL_EDGE_TILE + 40];
     __shared__ int32_t sX1[ICL_EDGE_TILE + 8], sG[ICL_EDGE_TILE + 8];
-    __shared__ uint16_t hl[ICL_EDGE_HITS * 256];
+    __shared__ uint32_t hm[ICL_EDGE_WORDS * 256];             // per thread: bit e of word w = band position a4 + 32 w + e is a candidate
     __shared__ int32_t s_kmin, s_kmax, s_span;
     __shared__ unsigned long long s_base;
     typedef cub::BlockScan<uint32_t, 256> Scan;
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(256, 4) k_edges_enum(EdgeEnum ee, int64_t V, E
     int64_t base = 0;
     bool has = false;
     if (v < V) has = ee.band(v, k0, k1, x1, x2, base, nr);
-    const bool small = has && (k1 - k0 <= 384);
+    const bool small = has && (k1 - k0 <= ICL_EDGE_BAND);
     {
         int32_t lo = small ? k0 : 0x7fffffff, hi = small ? k1 : 0;
         lo = __reduce_min_sync(0xffffffffu, lo);
@@ -652,43 +654,41 @@ __global__ void __launch_bounds__(256, 4) k_edges_enum(EdgeEnum ee, int64_t V, E
     const int32_t mg2 = ee.mg2;
     const bool fast = tiled && small;
     const int32_t a = k0 - kbase, b = k1 - kbase;              // the band inside the staged slice (fast only)
-    uint32_t cnt = 0, nh = 0;                                  // records of this source; hits of stage 1
+    const int32_t a4 = a & ~3;
+    const int32_t nwords = fast ? (b - a4 + 31) >> 5 : 0;
+    uint32_t cnt = 0;                                          // records of this source
     int32_t span = 0;
-    // what the sweep can see of candidate q (staged position): s > 0, or the last candidate of its row
-    auto keep = [&](int32_t q) {
-        const int32_t r = sX1[q];
-        const int32_t sc = sG[q] - (r - x1 + sX2[q] - x2);
-        return sc > 0 || (q + 1 == b) || sX1[q + 1] != r || (sX2[q + 1] - x2 >= mg2);
-    };
     if (fast) {
-        // ---- stage 1: positions of the band whose column lies in (x2, x2 + mg2)
+        // ---- stage 1: which positions of the band have their column in (x2, x2 + mg2): one bit each, no branch on a hit
         const uint32_t w = (uint32_t)(mg2 - 1);
         const int32_t xs = x2 + 1;
-        auto hit = [&](int32_t j) {
-            hl[(nh < ICL_EDGE_HITS ? nh : ICL_EDGE_HITS - 1) * 256 + tid] = (uint16_t)j;
-            nh++;
-        };
-        int32_t j = a;
-        for (; j < b && (j & 3); j++)
-            if ((uint32_t)(sX2[j] - xs) < w) hit(j);
-        for (; j + 4 <= b; j += 4) {
-            const int4 q = *(const int4 *)(sX2 + j);
-            if ((uint32_t)(q.x - xs) < w) hit(j);
-            if ((uint32_t)(q.y - xs) < w) hit(j + 1);
-            if ((uint32_t)(q.z - xs) < w) hit(j + 2);
-            if ((uint32_t)(q.w - xs) < w) hit(j + 3);
-        }
-        for (; j < b; j++)
-            if ((uint32_t)(sX2[j] - xs) < w) hit(j);
-        // ---- stage 2: keep what the sweep can see, in visiting order
-        if (nh <= ICL_EDGE_HITS) {
-            for (uint32_t h = 0; h < nh; h++) {
-                const int32_t q = hl[h * 256 + tid];
-                if (keep(q)) { hl[cnt * 256 + tid] = (uint16_t)q; cnt++; span = kbase + q - (int32_t)v; }
+        for (int32_t wd = 0; wd < nwords; wd++) {
+            const int32_t j0 = a4 + (wd << 5);
+            uint32_t m = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (j0 + 4 * u >= b) break;
+                const int4 q = *(const int4 *)(sX2 + j0 + 4 * u);
+                if ((uint32_t)(q.x - xs) < w) m |= 1u << (4 * u);
+                if ((uint32_t)(q.y - xs) < w) m |= 2u << (4 * u);
+                if ((uint32_t)(q.z - xs) < w) m |= 4u << (4 * u);
+                if ((uint32_t)(q.w - xs) < w) m |= 8u << (4 * u);
             }
-        } else {                                               // more hits than slots: straight from the staged band
-            for (int32_t q = a; q < b; q++)
-                if ((uint32_t)(sX2[q] - xs) < w && keep(q)) { cnt++; span = kbase + q - (int32_t)v; }
+            if (wd == 0) m &= ~0u << (a - a4);                 // positions before the band
+            const int32_t rem = b - j0;
+            if (rem < 32) m &= (1u << rem) - 1u;               // positions behind it
+            // ---- stage 2: keep what the sweep can see — s > 0, or the last candidate of its row — in visiting order
+            uint32_t t = m;
+            while (t) {
+                const int e = __ffs(t) - 1;
+                t &= t - 1;
+                const int32_t q = j0 + e, r = sX1[q];
+                const int32_t sc = sG[q] - (r - x1 + sX2[q] - x2);
+                if (sc > 0 || (q + 1 == b) || sX1[q + 1] != r || (sX2[q + 1] - x2 >= mg2)) span = kbase + q - (int32_t)v;
+                else m &= ~(1u << e);
+            }
+            hm[wd * 256 + tid] = m;
+            cnt += __popc(m);
         }
     } else if (has) {                                          // oversized band or tile: the generic scan on global memory
         ee.scan(k0, k1, x1, x2, base, nr, ee.X1, ee.X2, ee.G, [&](int32_t k, int32_t, int32_t, int32_t) { cnt++; span = k - (int32_t)v; });
@@ -713,19 +713,19 @@ __global__ void __launch_bounds__(256, 4) k_edges_enum(EdgeEnum ee, int64_t V, E
     if (e0 + cnt > es.cap) return;                             // pool too small: the caller sees the cursor and repeats
     const uint32_t srel = (uint32_t)(v - istart) << 8;
     uint2 *out = es.staging + e0;
-    // ---- stage 3: the records
-    auto record = [&](int32_t q) {
-        const int32_t dr = sX1[q] - x1, dc = sX2[q] - x2;
-        const int32_t sc = sG[q] - (dr + dc);
-        return make_uint2(((uint32_t)(kbase + q - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
-                          ((uint32_t)(sc > 0 ? sc : 0) & 0xffu) | srel);
-    };
-    if (fast && nh <= ICL_EDGE_HITS) {
-        for (uint32_t h = 0; h < cnt; h++) out[h] = record(hl[h * 256 + tid]);
-    } else if (fast) {
-        const uint32_t w = (uint32_t)(mg2 - 1);
-        for (int32_t q = a; q < b; q++)
-            if ((uint32_t)(sX2[q] - x2 - 1) < w && keep(q)) *out++ = record(q);
+    // ---- stage 3: the records of the kept candidates
+    if (fast) {
+        for (int32_t wd = 0; wd < nwords; wd++) {
+            uint32_t t = hm[wd * 256 + tid];
+            while (t) {
+                const int32_t q = a4 + (wd << 5) + __ffs(t) - 1;
+                t &= t - 1;
+                const int32_t dr = sX1[q] - x1, dc = sX2[q] - x2;
+                const int32_t sc = sG[q] - (dr + dc);
+                *out++ = make_uint2(((uint32_t)(kbase + q - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
+                                    ((uint32_t)(sc > 0 ? sc : 0) & 0xffu) | srel);
+            }
+        }
     } else {
         ee.scan(k0, k1, x1, x2, base, nr, ee.X1, ee.X2, ee.G, [&](int32_t k, int32_t dr, int32_t dc, int32_t sc) {
             *out++ = make_uint2(((uint32_t)(k - (int32_t)v) & 0xffffu) | ((uint32_t)dr << 16) | ((uint32_t)dc << 24),
