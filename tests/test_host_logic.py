@@ -460,6 +460,14 @@ def test_no_progress_passes_in_closed_form():
     assert xss_emulation.check_fast_forward(cases=24)
 
 
+def test_partition_in_merge_order_equals_the_sequential_partition():
+    """The closed form behind the rank kernel's CTA-cooperative phase: the groups of a partition pass are taken in the
+    order of a merge of two prefix-sum sequences, so every group's store pointers can be computed independently."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import xss_emulation as x
+    assert x.check_merge_path(trials=200) == 0
+
+
 def test_avx2_argsort_specification_matches_numpy():
     """The 4-lane flavour of the same specification against numpy in a child process with every AVX512* feature
     disabled (numpy then dispatches int64 argsort to its AVX2 kernels, where the CPU has AVX2)."""

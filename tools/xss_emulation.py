@@ -113,6 +113,89 @@ def partition_unrolled(arr, arg, left, right, pivot, unroll=4, lanes=8):
     return state[0], state[2], state[3]
 
 
+def partition_merge_path(arr, arg, left, right, pivot, unroll=4, lanes=8):
+    """`partition_unrolled` without the sequential dependence between groups — what the CTA-cooperative phase of
+    `k_xss_argsort` computes.  With lt(g) = keys < pivot in group g, the rule "take the next group from the right iff
+    (r_store + W) - right < left - l_store" reads: sum of lt over the groups taken from the right so far < sum of (G - lt)
+    over the groups taken from the left so far.  A[i] / B[j] = those sums after i groups from the left / j from the right;
+    both only grow, so the groups are taken in the order of the MERGE of A and B (A first on ties), and the two store
+    pointers at a group's turn follow from its place in the merge.  Same result as `partition_unrolled`
+    (`check_merge_path`)."""
+    import bisect
+    W = lanes
+    G = unroll * W
+    smallest, biggest = MAX, -MAX - 1
+    for _ in range((right - left) % G):
+        v = arr[arg[left]]
+        smallest, biggest = min(smallest, v), max(biggest, v)
+        if not v < pivot:
+            right -= 1
+            arg[left], arg[right] = arg[right], arg[left]
+        else:
+            left += 1
+    if left == right:
+        return left, smallest, biggest
+    L0, R0 = left, right
+    M = (R0 - L0) // G
+    src = list(arg[L0:R0])
+    keys = [arr[a] for a in src]
+    smallest, biggest = min(smallest, min(keys)), max(biggest, max(keys))
+    lt = [sum(1 for k in keys[g * G:(g + 1) * G] if k < pivot) for g in range(M)]
+    out = [None] * (R0 - L0)
+
+    def put(g, l_store, r_store):                       # store pointers relative to L0
+        for vv in range(unroll):
+            vec = src[g * G + vv * W:g * G + (vv + 1) * W]
+            ks = keys[g * G + vv * W:g * G + (vv + 1) * W]
+            ge = [a for a, k in zip(vec, ks) if k >= pivot]
+            lo = [a for a, k in zip(vec, ks) if not k >= pivot]
+            out[l_store:l_store + len(lo)] = lo
+            out[r_store + W - len(ge):r_store + W] = ge[::-1] if W == 4 else ge
+            l_store += len(lo)
+            r_store -= len(ge)
+    m = M - 2                                           # the first and the last group are set aside and stored last
+    A, B = [0] * (m + 1), [0] * (m + 1)
+    for i in range(m):
+        A[i + 1] = A[i] + (G - lt[1 + i])               # left candidate i is group 1 + i
+    for j in range(m):
+        B[j + 1] = B[j] + lt[M - 2 - j]                 # right candidate j is group M - 2 - j
+    for g in range(1, M - 1):
+        i = g - 1
+        j = bisect.bisect_left(B, A[i], 0, m + 1)       # right groups taken before left candidate i: B[j'] < A[i]
+        if i + j >= m:                                  # the merge ends before it gets here from the left
+            j = M - 2 - g
+            i = bisect.bisect_right(A, B[j], 0, m + 1)  # left groups taken before right candidate j: A[i'] <= B[j]
+        LT = (i * G - A[i]) + B[j]
+        GE = A[i] + (j * G - B[j])
+        put(g, LT, (R0 - L0) - W - GE)
+    LTm = sum(lt[1:M - 1])
+    GEm = m * G - LTm
+    put(0, LTm, (R0 - L0) - W - GEm)
+    put(M - 1, LTm + lt[0], (R0 - L0) - W - GEm - (G - lt[0]))
+    arg[L0:R0] = out
+    return L0 + sum(lt), smallest, biggest
+
+
+def check_merge_path(trials=300, seed=1):
+    """`partition_merge_path` against the sequential `partition_unrolled`, both vector widths; returns the mismatches."""
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for trial in range(trials):
+        n = int(rng.integers(64, 3000))
+        kind = trial % 4
+        x = (rng.integers(0, 5, n) if kind == 0 else rng.integers(0, 1000, n) if kind == 1 else
+             np.sort(rng.integers(0, 50, n)) if kind == 2 else rng.choice([25, 30, 50], n))
+        arr = [int(k) for k in x]
+        for lanes in (8, 4):
+            pivot = int(rng.choice(x))
+            a1 = [int(k) for k in rng.permutation(n)]
+            a2 = list(a1)
+            r1 = partition_unrolled(arr, a1, 0, n, pivot, lanes=lanes)
+            r2 = partition_merge_path(arr, a2, 0, n, pivot, lanes=lanes)
+            bad += r1 != r2 or a1 != a2
+    return bad
+
+
 def std_sort(arr, arg, first, last):
     """libstdc++ std::sort(arg + first, arg + last, [arr](a, b) { return arr[a] < arr[b]; })."""
     def less(i, j):

@@ -93,6 +93,7 @@ struct icl_ctx {
     Buf<uint8_t> used;
     Buf<int32_t> score32, npscr;     // npscr: stop lists of the numpy-scalar argsort kernel
     Buf<int32_t> host_flag;          // AVX-512 argsort kernel: segments that must be ranked on the host
+    Buf<uint32_t> xs_chunk;          // ... per-chunk stop counts of very long std::sort ranges
     // extraction
     Buf<int32_t> order_in, rank2v, acc_L, members, times, mscr;
     Buf<uint32_t> tree_v, acc_m, acc_ms, acc_flag, blkidx, moff;
@@ -263,6 +264,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->b_N.release(); c->b_moff.release(); c->b_N1.release(); c->b_a.release();
     c->o_flag.release(); c->o_bidx.release(); c->o_mcnt.release(); c->o_moff.release(); c->d_stage.release();
     c->o_src.release(); c->o_mout.release(); c->o_moff2.release();
+    c->host_flag.release(); c->xs_chunk.release(); c->npscr.release();
 #ifndef ICL_EMU
     if (c->h_stage) cudaFreeHost(c->h_stage);
 #else
@@ -2301,6 +2303,8 @@ struct XsArgs {
     int32_t keys_in_smem;      // keys next to the indices in shared memory (else only the indices; keys through L1)
     int32_t lane_max;          // std::sort pieces of at most this many elements are sorted by one lane each
     int32_t force_giveup;      // test hook (env ICL_B200_XS_FORCE_GIVEUP): the first segment of the launch gives up at once
+    int32_t coop_min;          // ranges longer than this are processed by the whole CTA (phase 1)
+    uint32_t *chunk;           // [2 (total / 32 + 3 segments)] per-chunk stop counts of very long std::sort ranges
 };
 
 // The key-index network is a bitonic sort with flip merges over P = 8 * numVecs slots: for S = 2, 4, .., P: compare
@@ -2398,6 +2402,7 @@ __device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int 
 #define ICL_XS_WARPS_DEFAULT 8
 #define ICL_XS_SMEM_MAX 208768     // dynamic shared memory a CTA may ask for: 227 KB minus the static arrays of 8 warps
 #define ICL_XS_STACK 256
+#define ICL_XS_BIG 64              // ranges waiting for the cooperative phase (depth of the recursion, at most)
 
 // A partition pass whose pivot equals the smallest key of its range moves every element to the "right" side: nothing
 // is decided by the keys, the pass is a fixed permutation of the positions [left, R) and the recursion comes back to the
@@ -2516,6 +2521,338 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
         s_giveup = (A.force_giveup && blockIdx.x == 0) ? 1 : 0;
     }
     __syncthreads();
+    // ------------------------------------------------------------------------------------------------------------
+    // phase 1: ranges longer than A.coop_min, the whole CTA on one range at a time.
+    // A long segment used to spend its top levels on ONE warp (a partition step per 32 keys, each a dependent chain);
+    // everything that warp does is a function of per-group counts only, so it can be laid out in advance:
+    //  * partition: with lt(g) = keys < pivot in group g, the side rule "take the next group from the right iff fewer
+    //    elements have been stored on the right than on the left" reads  sum of lt over the groups taken from the right <
+    //    sum of (G - lt) over the groups taken from the left.  Both sums only grow, so the order in which groups are taken is
+    //    the MERGE of the two prefix-sum sequences A (from the left) and B (from the right), A first on ties: a group's turn
+    //    and the two store pointers at its turn follow from A, B and one binary search per group
+    //    (checked against the sequential partition: tools/xss_emulation.py `partition_merge_path`).  All warps count, two
+    //    scan, all scatter out of place;
+    //  * passes without progress: a fixed permutation of positions, applied by all threads;
+    //  * std::sort's unguarded partition: stop lists by all warps (counts per 32 positions, scan, fill), crossing point by
+    //    counting, swaps in parallel.
+    // Sub-ranges of at most coop_min elements go to the shared stack for phase 2 (one warp per range, as before).
+    // ------------------------------------------------------------------------------------------------------------
+    __shared__ int32_t bg_lo[ICL_XS_BIG], bg_hi[ICL_XS_BIG], bg_it[ICL_XS_BIG];
+    __shared__ int32_t s_nbig, c_a, c_b, c_c, c_d, c_min, c_max, c_cnt0, c_cnt1;
+    {
+        const int32_t coop_min = A.coop_min > 512 ? A.coop_min : 512;
+        const int nthr = 32 * NW;
+        if (threadIdx.x == 0) {
+            s_nbig = 0;
+            if (unsorted && len > coop_min) {                  // the whole segment starts here
+                bg_lo[0] = st_lo[0]; bg_hi[0] = st_hi[0]; bg_it[0] = st_it[0];
+                s_nbig = 1; s_sp = 0; s_pending = 0;
+            }
+        }
+        __syncthreads();
+        // thread 0 only, between barriers
+        auto place = [&](int32_t lo_, int32_t hi_, int32_t it_) {
+            const int32_t cnt = it_ < 0 ? hi_ - lo_ : hi_ + 1 - lo_;
+            if (cnt > coop_min && s_nbig < ICL_XS_BIG) { bg_lo[s_nbig] = lo_; bg_hi[s_nbig] = hi_; bg_it[s_nbig] = it_; s_nbig++; }
+            else if (s_sp < ICL_XS_STACK) { st_lo[s_sp] = lo_; st_hi[s_sp] = hi_; st_it[s_sp] = it_; s_sp++; s_pending++; }
+            else s_giveup = 1;
+        };
+        uint32_t *const smA = (uint32_t *)&nkv_all[0][0];     // prefix sums of the partition: free while no network runs
+        constexpr int smcap = NW * 256;                        // uint32 entries per array in nkv_all (two arrays)
+        for (;;) {
+            __syncthreads();
+            if (s_nbig == 0 || s_giveup) break;
+            int32_t left = bg_lo[s_nbig - 1], right = bg_hi[s_nbig - 1], iters = bg_it[s_nbig - 1];
+            __syncthreads();
+            if (threadIdx.x == 0) s_nbig--;
+            if (iters < 0) {
+                // ---------------------------------------------------------------- std::sort range [f, l), one partition step
+                const int32_t f = left, l = right;
+                int depth = -iters - 1;
+                if (depth == 0) { if (threadIdx.x == 0) s_giveup = 1; continue; }     // heap-sort branch: the host ranks
+                --depth;
+                if (threadIdx.x == 0) {                      // __move_median_to_first(f, f + 1, mid, l - 1)
+                    const int32_t mid = f + ((l - f) >> 1), a = f + 1, b = mid, c = l - 1;
+                    const int32_t ka = v[x[a]], kb = v[x[b]], kc = v[x[c]];
+                    int32_t r;
+                    if (ka < kb) { if (kb < kc) r = b; else if (ka < kc) r = c; else r = a; }
+                    else if (ka < kc) r = a;
+                    else if (kb < kc) r = c;
+                    else r = b;
+                    const IdxT t = x[f]; x[f] = x[r]; x[r] = t;
+                    c_a = v[x[f]];
+                    c_cnt0 = 0; c_cnt1 = 0;
+                }
+                __syncthreads();
+                const int32_t pv = c_a;
+                // stop lists of [f + 1, l): per chunk of 32 positions the counts, a scan over chunks, then the lists
+                int32_t *Ls = Lbase + f, *Rs = Rbase + f;
+                const int32_t nch = (l - (f + 1) + 31) >> 5;
+                uint32_t *chL, *chR;                          // exclusive chunk offsets
+                if (nch + 1 <= smcap) { chL = smA; chR = smA + smcap; }
+                else { chL = A.chunk + 2 * ((base >> 5) + 3 * (int64_t)it); chR = chL + nch + 1; }   // the segment's own region
+                for (int32_t ch = wid; ch < nch; ch += NW) {
+                    const int32_t q = f + 1 + (ch << 5) + lane;
+                    const int32_t kq = q < l ? v[x[q]] : 0;
+                    const uint32_t ml = __ballot_sync(FULL, q < l && !(kq < pv)), mr = __ballot_sync(FULL, q < l && !(pv < kq));
+                    if (lane == 0) { chL[ch] = __popc(ml); chR[ch] = __popc(mr); }
+                }
+                __syncthreads();
+                if (wid == 0 || (NW > 1 && wid == 1)) {       // exclusive scans over the chunks (warp 0: left, warp 1: right)
+                    for (int pass = 0; pass < (NW > 1 ? 1 : 2); pass++) {
+                        uint32_t *arr = (NW > 1 ? wid : pass) == 0 ? chL : chR;
+                        uint32_t carry = 0;
+                        for (int32_t b0 = 0; b0 <= nch; b0 += 32) {
+                            const int32_t i = b0 + lane;
+                            uint32_t val = i < nch ? arr[i] : 0u, inc = val;
+                            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+                            if (i <= nch) arr[i] = carry + inc - val;
+                            carry += __shfl_sync(FULL, inc, 31);
+                        }
+                    }
+                }
+                __syncthreads();
+                const int32_t nL = (int32_t)chL[nch], nR = (int32_t)chR[nch];
+                for (int32_t ch = wid; ch < nch; ch += NW) {
+                    const int32_t q = f + 1 + (ch << 5) + lane;
+                    const int32_t kq = q < l ? v[x[q]] : 0;
+                    const bool fl = q < l && !(kq < pv), fr = q < l && !(pv < kq);
+                    const uint32_t ml = __ballot_sync(FULL, fl), mr = __ballot_sync(FULL, fr);
+                    const uint32_t below = (1u << lane) - 1u;
+                    if (fl) Ls[chL[ch] + __popc(ml & below)] = q;
+                    if (fr) Rs[chR[ch] + __popc(mr & below)] = q;
+                }
+                __syncthreads();
+                // K = number of k with L[k] < R[nR - 1 - k] (a prefix); swap those pairs
+                const int32_t kmax2 = nL < nR ? nL : nR;
+                int32_t myK = 0;
+                for (int32_t k = threadIdx.x; k < kmax2; k += nthr) myK += Ls[k] < Rs[nR - 1 - k];
+                myK = __reduce_add_sync(FULL, myK);
+                if (lane == 0 && myK) atomicAdd(&c_cnt0, myK);
+                __syncthreads();
+                const int32_t K = c_cnt0;
+                for (int32_t k = threadIdx.x; k < K; k += nthr) {
+                    const int32_t a = Ls[k], b = Rs[nR - 1 - k];
+                    const IdxT t = x[a]; x[a] = x[b]; x[b] = t;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int32_t cut = K < nL ? Ls[K] : l;
+                    if (K >= 1 && Rs[nR - K] < cut) cut = Rs[nR - K];
+                    // right part [cut, l) and left part [f, cut), both with the decremented depth; parts of at most 16
+                    // elements are left to the final insertion sort of the piece they end up in: they ride with a neighbour
+                    if (l - cut > 1) place(cut, l, -depth - 1);
+                    if (cut - f > 1) place(f, cut, -depth - 1);
+                }
+                continue;
+            }
+            if (iters == 0) {                                 // argsort_ out of budget: std::sort of the range
+                if (threadIdx.x == 0) {
+                    const int32_t cnt = right + 1 - left;
+                    place(left, right + 1, -(2 * (31 - __clz((unsigned)cnt))) - 1);
+                }
+                continue;
+            }
+            // ---------------------------------------------------------------- argsort_ range [left, right], > 256 elements
+            const int32_t ssize = (right - left) >> wsh;
+            if (wid == 0) {
+                const int32_t mine0 = lane < W ? v[x[left + (lane + 1) * ssize]] : 0x7fffffff;
+                int rank = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int32_t o = __shfl_sync(FULL, mine0, j);
+                    rank += j < W && ((o < mine0) || (o == mine0 && j < lane));
+                }
+                const uint32_t who = __ballot_sync(FULL, lane < W && rank == (W >> 1));
+                const int32_t pv = __shfl_sync(FULL, mine0, __ffs(who) - 1);
+                const int32_t mn = __reduce_min_sync(FULL, mine0);
+                if (lane == 0) { c_a = pv; c_b = mn; c_min = 0x7fffffff; c_max = (int32_t)0x80000000; c_cnt0 = 0; }
+            }
+            __syncthreads();
+            int32_t pivot = c_a;
+            if (c_b == pivot) {
+                // the pivot is the smallest sample: if it is the smallest key of the range, the pass decides nothing
+                int32_t rmin = 0x7fffffff, rmax = (int32_t)0x80000000;
+                for (int32_t i = left + threadIdx.x; i <= right; i += nthr) {
+                    const int32_t kv = v[x[i]];
+                    rmin = kv < rmin ? kv : rmin;
+                    rmax = kv > rmax ? kv : rmax;
+                }
+                rmin = __reduce_min_sync(FULL, rmin);
+                rmax = __reduce_max_sync(FULL, rmax);
+                if (lane == 0) { atomicMin(&c_min, rmin); atomicMax(&c_max, rmax); }
+                __syncthreads();
+                rmin = c_min; rmax = c_max;
+                if (pivot == rmin) {
+                    XsPerm P;
+                    P.left = left; P.R = right + 1;
+                    P.pre = (P.R - left) & (G - 1);
+                    P.rend = P.R - P.pre;
+                    P.M = (P.rend - left) >> (wsh + 2);
+                    if (wid == 0) {                            // how many such passes follow each other, and what ends them
+                        int32_t q = lane < W ? left + (lane + 1) * ssize : left;
+                        int t = 0, state;
+                        int32_t pv = pivot;
+                        for (;;) {
+                            ++t;
+                            if (pv == rmax) { state = 0; break; }
+                            if (iters - t == 0) { state = 1; break; }
+                            q = xs_inv<W>(P, q);
+                            const int32_t mine = lane < W ? v[x[q]] : 0x7fffffff;
+                            int rank = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int32_t o = __shfl_sync(FULL, mine, j);
+                                rank += j < W && ((o < mine) || (o == mine && j < lane));
+                            }
+                            const uint32_t who = __ballot_sync(FULL, lane < W && rank == (W >> 1));
+                            pv = __shfl_sync(FULL, mine, __ffs(who) - 1);
+                            if (pv != rmin) { state = 2; break; }
+                        }
+                        if (lane == 0) { c_a = pv; c_c = t; c_d = state; }
+                    }
+                    __syncthreads();
+                    const int t = c_c, state = c_d;
+                    pivot = c_a;
+                    int32_t *tmp = Lbase + left;               // out of place through the scratch slice
+                    for (int32_t i = left + threadIdx.x; i < P.R; i += nthr) tmp[xs_fwd_t<W>(P, i, t) - left] = (int32_t)x[i];
+                    __syncthreads();
+                    for (int32_t i = left + threadIdx.x; i < P.R; i += nthr) x[i] = (IdxT)tmp[i - left];
+                    __syncthreads();
+                    iters -= t;
+                    if (state == 0) continue;
+                    if (state == 1) {
+                        if (threadIdx.x == 0) {
+                            const int32_t cnt = right + 1 - left;
+                            place(left, right + 1, -(2 * (31 - __clz((unsigned)cnt))) - 1);
+                        }
+                        continue;
+                    }
+                    if (threadIdx.x == 0) { c_min = 0x7fffffff; c_max = (int32_t)0x80000000; }
+                    __syncthreads();
+                }
+            }
+            // ---- partition [left, right + 1) around `pivot`
+            const int32_t range_left = left, range_right = right;
+            if (threadIdx.x == 0) {
+                int32_t lf = left, rend = right + 1, kmin = 0x7fffffff, kmax = (int32_t)0x80000000;
+                for (int32_t pre = (rend - lf) & (G - 1); pre > 0; --pre) {
+                    const int32_t kv = v[x[lf]];
+                    kmin = kv < kmin ? kv : kmin;
+                    kmax = kv > kmax ? kv : kmax;
+                    if (!(kv < pivot)) { --rend; const IdxT t = x[lf]; x[lf] = x[rend]; x[rend] = t; }
+                    else ++lf;
+                }
+                c_a = lf; c_b = rend; c_min = kmin; c_max = kmax;
+            }
+            __syncthreads();
+            const int32_t L0 = c_a, R0 = c_b;
+            const int32_t M = (R0 - L0) >> (wsh + 2), m = M - 2;          // groups; the first and the last are set aside
+            uint32_t *PA, *PB;                                // PA[i] = keys >= pivot in the first i middle groups from the left,
+            if (M <= smcap) { PA = smA; PB = smA + smcap; }   // PB[j] = keys < pivot in the first j from the right (i, j = 0..m)
+            else { PA = (uint32_t *)(Rbase + left); PB = PA + M; }
+            const bool act = lane < G;                        // AVX2: 16 lanes carry a group
+            {
+                int32_t kmin = 0x7fffffff, kmax = (int32_t)0x80000000;
+                for (int32_t gb = wid << 5; gb < M; gb += NW << 5) {
+                    int32_t myge = 0;
+                    const int32_t ge_n = M - gb < 32 ? M - gb : 32;
+                    for (int32_t k = 0; k < ge_n; k++) {
+                        const int32_t a = act ? (int32_t)x[L0 + ((gb + k) << (wsh + 2)) + lane] : 0;
+                        const int32_t kv = act ? v[a] : pivot;
+                        const uint32_t mm = __ballot_sync(FULL, act && kv >= pivot);
+                        kmin = kv < kmin ? kv : kmin;
+                        kmax = kv > kmax ? kv : kmax;
+                        if (lane == k) myge = __popc(mm);
+                    }
+                    const int32_t g = gb + lane;
+                    if (g < M) {
+                        if (g == 0) c_c = myge;
+                        else if (g == M - 1) c_d = myge;
+                        else { PA[g] = (uint32_t)myge; PB[M - 1 - g] = (uint32_t)(G - myge); }
+                    }
+                }
+                kmin = __reduce_min_sync(FULL, kmin);
+                kmax = __reduce_max_sync(FULL, kmax);
+                if (lane == 0) { atomicMin(&c_min, kmin); atomicMax(&c_max, kmax); }
+                if (threadIdx.x == 0) { PA[0] = 0; PB[0] = 0; }
+            }
+            __syncthreads();
+            if (wid == 0 || (NW > 1 && wid == 1)) {           // inclusive scans of PA[0..m] and PB[0..m]
+                for (int pass = 0; pass < (NW > 1 ? 1 : 2); pass++) {
+                    uint32_t *arr = (NW > 1 ? wid : pass) == 0 ? PA : PB;
+                    uint32_t carry = 0;
+                    for (int32_t b0 = 0; b0 <= m; b0 += 32) {
+                        const int32_t i = b0 + lane;
+                        uint32_t inc = i <= m ? arr[i] : 0u;
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+                        if (i <= m) arr[i] = carry + inc;
+                        carry += __shfl_sync(FULL, inc, 31);
+                    }
+                }
+            }
+            __syncthreads();
+            {
+                const int32_t GEm = (int32_t)PA[m], LTm = m * G - GEm;         // middle groups in total
+                const int32_t ge0 = c_c;
+                int32_t *tmp = Lbase + left;                  // scatter target, positions relative to L0
+                const int vec = lane >> wsh, lW = lane & (W - 1);
+                const uint32_t maskW = (1u << W) - 1u, belowW = (1u << lW) - 1u;
+                constexpr bool rev = W == 4;
+                for (int32_t gb = wid << 5; gb < M; gb += NW << 5) {
+                    // the turn of group gb + lane: what has been stored on either side before it
+                    const int32_t g = gb + lane;
+                    int32_t LT = 0, GE = 0;
+                    if (g < M) {
+                        if (g == 0) { LT = LTm; GE = GEm; }
+                        else if (g == M - 1) { LT = LTm + (G - ge0); GE = GEm + ge0; }
+                        else {
+                            int32_t i = g - 1;
+                            const uint32_t Ai = PA[i];
+                            int32_t lo = 0, hi = m + 1;       // j = number of j' in [0, m] with PB[j'] < Ai
+                            while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (PB[mid] < Ai) lo = mid + 1; else hi = mid; }
+                            int32_t j = lo;
+                            if (i + j >= m) {                 // not reached from the left: taken from the right
+                                j = M - 2 - g;
+                                const uint32_t Bj = PB[j];
+                                lo = 0; hi = m + 1;           // i = number of i' in [0, m] with PA[i'] <= Bj
+                                while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (PA[mid] <= Bj) lo = mid + 1; else hi = mid; }
+                                i = lo;
+                            }
+                            LT = i * G - (int32_t)PA[i] + (int32_t)PB[j];
+                            GE = (int32_t)PA[i] + j * G - (int32_t)PB[j];
+                        }
+                    }
+                    const int32_t ge_n = M - gb < 32 ? M - gb : 32;
+                    for (int32_t k = 0; k < ge_n; k++) {
+                        const int32_t l_store = __shfl_sync(FULL, LT, k), r_store = (R0 - L0) - W - __shfl_sync(FULL, GE, k);
+                        const int32_t a = act ? (int32_t)x[L0 + ((gb + k) << (wsh + 2)) + lane] : 0;
+                        const int32_t kv = act ? v[a] : pivot;
+                        const bool isge = act && kv >= pivot;
+                        const uint32_t mm = __ballot_sync(FULL, isge);
+                        const int geb = __popc(mm & ((1u << (W * vec)) - 1u));   // keys >= pivot in the vectors before mine
+                        const int32_t ls = l_store + W * vec - geb, rs = r_store - geb;
+                        const uint32_t mv = (mm >> (W * vec)) & maskW;
+                        const int ge = __popc(mv);
+                        const int rk = __popc(mv & belowW);
+                        const int32_t dst = isge ? (rev ? rs + W - 1 - rk : rs + W - ge + rk) : ls + __popc(~mv & belowW);
+                        if (act) tmp[dst] = a;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int32_t i = threadIdx.x; i < R0 - L0; i += nthr) x[L0 + i] = (IdxT)(Lbase + left)[i];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int32_t GEall = (int32_t)PA[m] + c_c + c_d;
+                const int32_t pi = R0 - GEall;                // first key >= pivot
+                const int32_t kmin = c_min, kmax = c_max;
+                if (pivot != kmax) place(pi, range_right, iters - 1);
+                if (pivot != kmin) place(range_left, pi - 1, iters - 1);
+            }
+        }
+        __syncthreads();
+    }
     volatile int32_t *vsp = &s_sp, *vpend = &s_pending, *vgive = &s_giveup;
     // lane 0 of a warp only; a lock that cannot be had (never seen) gives the segment up instead of hanging the GPU
     auto lock = [&]() {
@@ -2859,6 +3196,8 @@ static int rank_segments(icl_ctx *c, int32_t mode, const int32_t *key, int32_t *
     ICL_CUDA(st, dev_memset(c->host_flag.p, 0, ((size_t)nseg + 1) * sizeof(int32_t), s));
     static const int xs_warps = [] { const char *e = getenv("ICL_B200_XS_WARPS"); return e ? atoi(e) : ICL_XS_WARPS_DEFAULT; }();
     static const int xs_lane = [] { const char *e = getenv("ICL_B200_XS_LANE"); const int q = e ? atoi(e) : ICL_XS_LANE; return q < 16 ? 16 : q > 160 ? 160 : q; }();
+    static const int xs_coop = [] { const char *e = getenv("ICL_B200_XS_COOP"); return e ? atoi(e) : 1024; }();   // 0x7fffffff = off
+    if (c->xs_chunk.reserve(st, 2 * ((size_t)(total >> 5) + 3 * (size_t)nseg) + 64)) return st.code;
     // Segments come longest first, so the size classes are runs of the order; one launch each:
     //   <= 16 000 keys   keys + 16-bit indices in shared memory (96 KB: several CTAs per SM)
     //   <= 34 000        the same with up to 204 KB (one CTA per SM)
@@ -2874,7 +3213,8 @@ static int rank_segments(icl_ctx *c, int32_t mode, const int32_t *key, int32_t *
         const int32_t ccap = cls == 0 ? (int32_t)std::min<int64_t>(Lr, 12288) : (int32_t)Lr;
         const size_t csmem = (size_t)ccap * (cls == 0 ? 8 : cls == 1 ? 2 : 6);
         XsArgs A{key, idx, off, order, c->host_flag.p, c->npscr.p, ccap,
-                 mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, j0, cls == 1 ? 0 : 1, xs_lane, getenv("ICL_B200_XS_FORCE_GIVEUP") ? 1 : 0};
+                 mode == ICL_RANK_NUMPY_AVX2 ? 4 : 8, j0, cls == 1 ? 0 : 1, xs_lane, getenv("ICL_B200_XS_FORCE_GIVEUP") ? 1 : 0,
+                 xs_coop, c->xs_chunk.p};
         const unsigned grid = (unsigned)(j1 - j0);
         if (cls == 0) ICL_CUDA(st, xss_launch_v<int32_t>(A.W, xs_warps, A, grid, csmem, s));
         else ICL_CUDA(st, xss_launch_v<uint16_t>(A.W, xs_warps, A, grid, csmem, s));
