@@ -466,6 +466,7 @@ def test_partition_in_merge_order_equals_the_sequential_partition():
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import xss_emulation as x
     assert x.check_merge_path(trials=200) == 0
+    assert x.check_std_sort_equal() == 0          # std::sort on equal keys is a fixed permutation (xs_std_equal_pos)
 
 
 def test_avx2_argsort_specification_matches_numpy():

@@ -256,6 +256,38 @@ def std_sort(arr, arg, first, last):
         insertion_sort(first, last)
 
 
+def std_sort_equal_pos(f, l, q):
+    """Where std::sort(arg + f, arg + l, cmp) leaves the element found at position q when every key of the range is the
+    same: no comparison is true, so each level of __introsort_loop moves the middle element to the front, reverses
+    [f + 1, l) (the unguarded partition swaps (f + 1 + k, l - 1 - k) until the scans meet) and cuts at
+    f + 1 + (l - f - 1) // 2; the final insertion sort moves nothing.  The kernel applies this in one step per element
+    (`xs_std_equal_pos`) instead of partitioning level by level; `check_std_sort_equal` compares it with `std_sort`."""
+    while l - f > 16:
+        mid = f + ((l - f) >> 1)
+        q = f + l - mid if q == f else (f if q == mid else f + l - q)
+        cut = f + 1 + ((l - f - 1) >> 1)
+        if q < cut:
+            l = cut
+        else:
+            f = cut
+    return q
+
+
+def check_std_sort_equal(sizes=tuple(range(1, 300)) + (1000, 1023, 1024, 1025, 4097, 9999)):
+    rng = np.random.default_rng(3)
+    bad = 0
+    for n in sizes:
+        arr = [7] * n
+        arg = [int(k) for k in rng.permutation(n)]
+        a1 = list(arg)
+        std_sort(arr, a1, 0, n)
+        a2 = [None] * n
+        for q in range(n):
+            a2[std_sort_equal_pos(0, n, q)] = arg[q]
+        bad += a1 != a2
+    return bad
+
+
 def argsort_(arr, arg, left, right, iters, lanes=8):
     if iters <= 0:
         std_sort(arr, arg, left, right + 1)

@@ -2399,6 +2399,31 @@ __device__ bool xs_std_seq(const int32_t *v, IdxT *x, int32_t f, int32_t l, int 
     return true;
 }
 
+// std::sort on a range of EQUAL keys is a fixed permutation of positions: no comparison is ever true, so every level of
+// __introsort_loop moves the middle element to the front (__move_median_to_first picks `mid`), __unguarded_partition
+// swaps (f + 1 + k, l - 1 - k) for k < (l - f - 1) / 2 — the reversal of [f + 1, l) — and cuts at f + 1 + (l - f - 1) / 2;
+// the final insertion sort moves nothing.  Where the element at q ends up (tools/xss_emulation.py `std_sort_equal_pos`,
+// checked against the emulation of std::sort for all sizes 1..400 and some larger ones):
+__device__ __forceinline__ int32_t xs_std_equal_pos(int32_t f, int32_t l, int32_t q) {
+    while (l - f > 16) {
+        const int32_t mid = f + ((l - f) >> 1);
+        q = (q == f) ? f + l - mid : (q == mid) ? f : f + l - q;
+        const int32_t cut = f + 1 + ((l - f - 1) >> 1);
+        if (q < cut) l = cut; else f = cut;
+    }
+    return q;
+}
+// levels of __introsort_loop that a range of s equal keys goes through (its larger part decides)
+__device__ __forceinline__ int xs_std_equal_levels(int32_t s) {
+    int lv = 0;
+    while (s > 16) {
+        const int32_t a = 1 + ((s - 1) >> 1), b = s - a;
+        s = a > b ? a : b;
+        lv++;
+    }
+    return lv;
+}
+
 #define ICL_XS_WARPS_DEFAULT 8
 #define ICL_XS_SMEM_MAX 208768     // dynamic shared memory a CTA may ask for: 227 KB minus the static arrays of 8 warps
 #define ICL_XS_STACK 256
@@ -2498,17 +2523,31 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
     IdxT *x;
     IdxT *xsh = (IdxT *)(xs_sm + (A.keys_in_smem ? A.smem_cap : 0));
     if (fits) {
-        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) {
-            if (kin) xs_sm[i] = v[i];
-            xsh[i] = (IdxT)i;
+        for (int32_t i = threadIdx.x; i < len; i += blockDim.x) xsh[i] = (IdxT)i;
+        if (kin) {
+            // keys to shared memory with 16-byte global loads (one CTA per SM in the large classes: nothing else hides them)
+            const int32_t head = (int32_t)((4 - (base & 3)) & 3) < len ? (int32_t)((4 - (base & 3)) & 3) : len;
+            const int32_t nvec = (len - head) >> 2;
+            const int4 *src = (const int4 *)(v + head);
+            if ((int32_t)threadIdx.x < head) xs_sm[threadIdx.x] = v[threadIdx.x];
+            for (int32_t j = threadIdx.x; j < nvec; j += blockDim.x) {
+                const int4 q = __ldg(src + j);
+                int32_t *d = xs_sm + head + 4 * j;
+                d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+            }
+            for (int32_t i = head + 4 * nvec + threadIdx.x; i < len; i += blockDim.x) xs_sm[i] = v[i];
         }
     } else {
         x = (IdxT *)(A.idx + base);
         for (int32_t i = threadIdx.x; i < len; i += blockDim.x) x[i] = (IdxT)i;
     }
+    __syncthreads();
     // keys already in non-decreasing order: the library leaves the identity (top level only)
     int uns = 0;
-    for (int32_t i = threadIdx.x; i + 1 < len; i += blockDim.x) uns |= v[i] > v[i + 1];
+    {
+        const int32_t *vv = kin ? xs_sm : v;
+        for (int32_t i = threadIdx.x; i + 1 < len; i += blockDim.x) uns |= vv[i] > vv[i + 1];
+    }
     const int unsorted = __syncthreads_or(uns);
     if (fits) {
         if (kin) v = xs_sm;
@@ -2591,13 +2630,32 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
                 uint32_t *chL, *chR;                          // exclusive chunk offsets
                 if (nch + 1 <= smcap) { chL = smA; chR = smA + smcap; }
                 else { chL = A.chunk + 2 * ((base >> 5) + 3 * (int64_t)it); chR = chL + nch + 1; }   // the segment's own region
-                for (int32_t ch = wid; ch < nch; ch += NW) {
-                    const int32_t q = f + 1 + (ch << 5) + lane;
-                    const int32_t kq = q < l ? v[x[q]] : 0;
-                    const uint32_t ml = __ballot_sync(FULL, q < l && !(kq < pv)), mr = __ballot_sync(FULL, q < l && !(pv < kq));
-                    if (lane == 0) { chL[ch] = __popc(ml); chR[ch] = __popc(mr); }
+                {
+                    int32_t kmin = pv, kmax = pv;
+                    for (int32_t ch = wid; ch < nch; ch += NW) {
+                        const int32_t q = f + 1 + (ch << 5) + lane;
+                        const int32_t kq = q < l ? v[x[q]] : pv;
+                        const uint32_t ml = __ballot_sync(FULL, q < l && !(kq < pv)), mr = __ballot_sync(FULL, q < l && !(pv < kq));
+                        kmin = kq < kmin ? kq : kmin;
+                        kmax = kq > kmax ? kq : kmax;
+                        if (lane == 0) { chL[ch] = __popc(ml); chR[ch] = __popc(mr); }
+                    }
+                    const bool eq = kmin == kmax;
+                    if (!__all_sync(FULL, eq)) c_cnt1 = 1;    // (benign race: every writer stores 1)
                 }
                 __syncthreads();
+                if (c_cnt1 == 0 && depth + 1 >= xs_std_equal_levels(l - f)) {
+                    // every key of the range equals the pivot: std::sort is a fixed permutation here (xs_std_equal_pos), all
+                    // levels at once.  The median swap of this level is undone first: the permutation starts from the range
+                    // as std::sort found it.
+                    if (threadIdx.x == 0) { const int32_t mid = f + ((l - f) >> 1); const IdxT t = x[f]; x[f] = x[mid]; x[mid] = t; }
+                    __syncthreads();
+                    int32_t *tmp = Lbase + f;
+                    for (int32_t q = f + threadIdx.x; q < l; q += nthr) tmp[xs_std_equal_pos(f, l, q) - f] = (int32_t)x[q];
+                    __syncthreads();
+                    for (int32_t q = f + threadIdx.x; q < l; q += nthr) x[q] = (IdxT)tmp[q - f];
+                    continue;
+                }
                 if (wid == 0 || (NW > 1 && wid == 1)) {       // exclusive scans over the chunks (warp 0: left, warp 1: right)
                     for (int pass = 0; pass < (NW > 1 ? 1 : 2); pass++) {
                         uint32_t *arr = (NW > 1 ? wid : pass) == 0 ? chL : chR;
@@ -2943,18 +3001,32 @@ __global__ void __launch_bounds__(32 * NW) k_xss_argsort(XsArgs A) {
                 // slot the last swap filled, whichever comes first
                 int32_t *Ls = Lbase + f, *Rs = Rbase + f;
                 int32_t nL = 0, nR = 0;
+                bool alleq = true;
                 for (int32_t b0 = f + 1; b0 < l; b0 += 32) {
                     const int32_t q = b0 + lane;
-                    const int32_t kq = q < l ? v[x[q]] : 0;
+                    const int32_t kq = q < l ? v[x[q]] : pv;
                     const bool fl = q < l && !(kq < pv), fr = q < l && !(pv < kq);
                     const uint32_t ml = __ballot_sync(FULL, fl), mr = __ballot_sync(FULL, fr);
                     const uint32_t below = (1u << lane) - 1u;
+                    alleq = alleq && kq == pv;
                     if (fl) Ls[nL + __popc(ml & below)] = q;
                     if (fr) Rs[nR + __popc(mr & below)] = q;
                     nL += __popc(ml);
                     nR += __popc(mr);
                 }
                 __syncwarp();
+                if (__all_sync(FULL, alleq) && depth + 1 >= xs_std_equal_levels(l - f)) {
+                    // equal keys throughout: the rest of std::sort on this range is a fixed permutation (xs_std_equal_pos);
+                    // undo this level's median swap, apply all levels at once through the scratch slice
+                    if (lane == 0) { const int32_t mid = f + ((l - f) >> 1); const IdxT t = x[f]; x[f] = x[mid]; x[mid] = t; }
+                    __syncwarp();
+                    for (int32_t q = f + lane; q < l; q += 32) Ls[xs_std_equal_pos(f, l, q) - f] = (int32_t)x[q];
+                    __syncwarp();
+                    for (int32_t q = f + lane; q < l; q += 32) x[q] = (IdxT)Ls[q - f];
+                    __syncwarp();
+                    l = f;                                   // nothing left of this range
+                    break;
+                }
                 const int32_t kmax2 = nL < nR ? nL : nR;
                 int32_t K = 0;
                 for (int32_t b0 = 0; b0 < kmax2; b0 += 32) {
