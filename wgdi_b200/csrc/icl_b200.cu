@@ -101,6 +101,7 @@ struct icl_ctx {
     Buf<uint8_t> seen;
     Buf<uint8_t> present;
     Buf<int2> hint;                  // per point: {depth of the nearest removed ancestor, tree version} memo
+    Buf<int2> big_trees;             // [t0, uend) of the trees that go to the staged walk
     int64_t NB = 0, NM = 0;
     Buf<int32_t> b_top, b_m, b_L, b_j0, b_j1, b_l2min, b_l2max, b_L1, b_item, b_N;
     Buf<uint32_t> b_moff;
@@ -256,7 +257,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->tile_state.release(); c->tile_dst.release(); c->edge_stage.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
-    c->S.release(); c->root.release(); c->hint.release(); c->pd.release(); c->used.release(); c->score32.release();
+    c->S.release(); c->root.release(); c->hint.release(); c->big_trees.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
     c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
@@ -1513,6 +1514,124 @@ extern "C" int icl_debug_dp(icl_ctx *c, int32_t dir, int32_t *score, int32_t *pr
 // order, record accepted blocks at their rank position, and recover the reference's acceptance order with a
 // prefix sum over rank positions.
 // ------------------------------------------------------------------------------------------------
+#define ICL_TREE_SMALL 32           // trees of at most this many used points: one thread each, on global memory
+#define ICL_TREE_CAP 2048            // larger ones up to this size: one warp each, staged in shared memory
+#define ICL_TREE_SMEM (ICL_TREE_CAP * 37 + 64)
+#ifndef ICL_EMU
+struct TreeArgs {
+    int64_t n, V;
+    const uint32_t *key, *tpos;      // sorted tree keys; rank position of every sorted entry
+    const int32_t *rank2v;
+    const int2 *pd;
+    const int32_t *imap, *l1, *l2;
+    const int2 *big;                 // queue of [t0, uend)
+    int32_t *stats;                  // [0] queue head (this kernel), [1] queue length (written by the tree-head pass)
+    uint32_t *acc_m, *acc_ms;
+    int32_t *acc_L, *mscr;
+    int4 *acc_box;
+    int32_t over_gap;
+    double cov;
+};
+
+// The extraction of one predecessor tree (same decisions, same outputs as the thread-per-tree walk above) with the tree
+// in shared memory: the warp gathers its points once — rank position, forward position, loc2, path length, and the
+// predecessor as an index INTO the tree (through a hash of the tree's points) — and lane 0 then walks tops, paths and
+// members at shared-memory latency instead of one dependent DRAM round trip per hop.
+__global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    int32_t *s_t = (int32_t *)tsm;                             // rank position
+    int32_t *s_f = s_t + ICL_TREE_CAP;                         // forward sorted position of the point
+    int32_t *s_y = s_f + ICL_TREE_CAP;                         // loc2
+    int32_t *s_pl = s_y + ICL_TREE_CAP;                        // predecessor: index into the tree, -1 for the root
+    int32_t *s_L = s_pl + ICL_TREE_CAP;                        // path length
+    int2 *s_h = (int2 *)(s_L + ICL_TREE_CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
+    uint8_t *s_pres = (uint8_t *)(s_h + 2 * ICL_TREE_CAP);
+    const int lane = threadIdx.x;
+    const uint32_t FULL = 0xffffffffu;
+    for (;;) {
+        int32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(&T.stats[0], 1);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= T.stats[1]) break;
+        const int2 rg = T.big[qi];
+        const int32_t t0 = rg.x, N = rg.y - rg.x;
+        int32_t hsz = 64;
+        while (hsz < 2 * N) hsz <<= 1;
+        for (int32_t i = lane; i < hsz; i += 32) s_h[i] = make_int2(-1, -1);
+        __syncwarp();
+        bool rev = false;
+        for (int32_t j = lane; j < N; j += 32) {
+            const int32_t t = (int32_t)T.tpos[t0 + j], v = T.rank2v[t];
+            const int2 nd = T.pd[v];
+            const int32_t i = v >= T.n ? T.imap[v - T.n] : v;
+            s_t[j] = t; s_f[j] = i; s_y[j] = T.l2[i]; s_pl[j] = nd.x; s_L[j] = nd.y; s_pres[j] = 1;
+            if (j == 0) rev = v >= T.n;
+            uint32_t h = ((uint32_t)v * 2654435761u) & (uint32_t)(hsz - 1);
+            int32_t tries = 0;                                 // (bounded: a caller's broken order must not hang the GPU)
+            while (atomicCAS(&s_h[h].x, -1, v) != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
+            if (tries < hsz) s_h[h].y = j;
+        }
+        rev = __shfl_sync(FULL, rev, 0);
+        __syncwarp();
+        for (int32_t j = lane; j < N; j += 32) {
+            const int32_t p = s_pl[j];
+            int32_t loc = -1;
+            if (p >= 0) {                                      // the predecessor is a used point of the same tree
+                uint32_t h = ((uint32_t)p * 2654435761u) & (uint32_t)(hsz - 1);
+                int32_t tries = 0;
+                while (s_h[h].x != p && s_h[h].x != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
+                loc = s_h[h].x == p ? s_h[h].y : -1;
+            }
+            s_pl[j] = loc;
+        }
+        __syncwarp();
+        for (int32_t j = lane; j < N; j += 32) s_h[j] = make_int2(-1, -1);   // the memo takes the hash's place
+        __syncwarp();
+        if (lane == 0) {
+            int32_t ver = 0;                                   // accepted blocks of this tree so far
+            uint32_t cursor = (uint32_t)t0;                    // member scratch: the tree's own slice
+            for (int32_t u = 0; u < N; u++) {                  // the tree's points in rank order
+                if (!s_pres[u]) continue;
+                const int32_t L = s_L[u];
+                int32_t m, q;
+                if (ver == 0) m = L;
+                else if (s_h[u].y == ver) m = L - s_h[u].x;
+                else { m = 1; q = s_pl[u]; while (q >= 0 && s_pres[q]) { m++; q = s_pl[q]; } }
+                if (L >= T.over_gap && (double)m / (double)L > T.cov) {          // :129
+                    int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
+                    q = u;
+                    for (int32_t k = 0; k < m; k++) {
+                        if (q < 0) break;                      // (only with a caller's broken order, reported by the caller)
+                        s_pres[q] = 0;
+                        const int32_t i = s_f[q];
+                        T.mscr[cursor + k] = i;
+                        const int32_t yv = s_y[q];
+                        l2min = yv < l2min ? yv : l2min;
+                        l2max = yv > l2max ? yv : l2max;
+                        if (k == 0) ifirst = i;
+                        ilast = i;
+                        q = s_pl[q];
+                    }
+                    ver++;
+                    const int32_t la = T.l1[ifirst], lb = T.l1[ilast];
+                    const int32_t t = s_t[u];
+                    T.acc_m[t] = (uint32_t)m;
+                    T.acc_L[t] = L;
+                    T.acc_ms[t] = cursor;
+                    T.acc_box[t] = make_int4(la < lb ? la : lb, la < lb ? lb : la, l2min, l2max);
+                    cursor += (uint32_t)m;
+                } else {
+                    s_pres[u] = 0;                             // :143
+                    if (m > 1) s_h[s_pl[u]] = make_int2(L - m, ver);
+                }
+            }
+        }
+        __syncwarp();
+        (void)rev;
+    }
+}
+#endif
+
 static int phase_extract(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n, V = 2 * n;
@@ -1521,7 +1640,8 @@ static int phase_extract(icl_ctx *c) {
     if (c->present.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) || c->acc_ms.reserve(st, V) ||
         c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->acc_flag.reserve(st, V + 2) ||
-        c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4))
+        c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4) ||
+        c->big_trees.reserve(st, V / ICL_TREE_SMALL + 2))
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
@@ -1535,7 +1655,7 @@ static int phase_extract(icl_ctx *c) {
     // groups every predecessor tree with its points in rank order.  Unused points sort behind everything.
     const int vb = bits_for(V);
     {
-        uint64_t *key = c->key_a.p;
+        uint32_t *key = (uint32_t *)c->key_a.p;                  // tree root < V < 2^31: 32-bit keys
         uint32_t *idx = c->idx_a.p;
         uint8_t *seen = c->seen.p;
         if (c->order_on_device_used) {
@@ -1543,24 +1663,24 @@ static int phase_extract(icl_ctx *c) {
             ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
                 idx[t] = (uint32_t)t;
                 const int32_t v = rank2v[t];
-                key[t] = used[v] ? (uint64_t)(uint32_t)root[v] : (uint64_t)V;
+                key[t] = used[v] ? (uint32_t)root[v] : (uint32_t)V;
             }));
         } else {
             ICL_CUDA(st, dev_memset(c->seen.p, 0, (size_t)V, s));
             ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
                 idx[t] = (uint32_t)t;
                 const int32_t v = rank2v[t];
-                if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = (uint64_t)V; return; }   // not a permutation
+                if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = (uint32_t)V; return; }   // not a permutation
                 seen[v] = 1;
-                key[t] = used[v] ? (uint64_t)(uint32_t)root[v] : (uint64_t)V;
+                key[t] = used[v] ? (uint32_t)root[v] : (uint32_t)V;
             }));
             // a duplicate may slip through the unsynchronised test above, but then some point is never seen
             ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (!seen[v]) atomic_or_i32(&stats[2], 1); }));
         }
     }
-    if (V > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->tree_v.p, V, vb, s)) return st.code;
+    if (V > 0 && radix_sort_pairs32(st, c->tmp, (uint32_t *)c->key_a.p, (uint32_t *)c->key_b.p, c->idx_a.p, c->tree_v.p, V, vb, s)) return st.code;
     {
-        const uint64_t *key = c->key_b.p;
+        const uint32_t *key = (const uint32_t *)c->key_b.p;
         const uint32_t *tpos = c->tree_v.p;            // rank position of every sorted entry
         const int32_t *imap = c->imap.p, *l1 = c->loc1s.p, *l2 = c->loc2s.p;
         uint8_t *present = c->present.p;
@@ -1570,9 +1690,12 @@ static int phase_extract(icl_ctx *c) {
         int2 *hint = c->hint.p;
         const int32_t over_gap = c->prm.over_gap;
         const double cov = c->prm.coverage_ratio;
+#ifndef ICL_EMU
+        int2 *big = c->big_trees.p;
+#endif
         ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t0) {
-            const uint64_t rt = key[t0];
-            if (rt >= (uint64_t)V) return;                                      // unused tail
+            const uint32_t rt = key[t0];
+            if (rt >= (uint32_t)V) return;                                      // unused tail
             if (t0 > 0 && key[t0 - 1] == rt) return;                            // not the head of its tree
             int32_t ver = 0;                                                    // accepted blocks of this tree so far
             uint32_t cursor = (uint32_t)t0;                                     // member scratch: the tree's own slice
@@ -1588,6 +1711,14 @@ static int phase_extract(icl_ctx *c) {
                 }
                 uend = a0;
             }
+#ifndef ICL_EMU
+            // a long tree is a long chain of dependent loads for one thread (ncu: 5.4 of 32 threads active, the walk as
+            // long as its largest tree): it goes to k_tree_walk_staged, one warp with the tree in shared memory
+            if (uend - t0 > ICL_TREE_SMALL && uend - t0 <= ICL_TREE_CAP) {
+                big[atomic_fetch_add_i32(&stats[1], 1)] = make_int2((int32_t)t0, (int32_t)uend);
+                return;
+            }
+#endif
             // The tops of a tree are examined strictly in rank order, but everything a top needs except `present` and
             // the memo is read-only here, and those two only change for OTHER tops when a block is accepted (ver++).
             // So the loads run three tops ahead of the decisions (rank position at distance 3, point at 2, node record
@@ -1633,6 +1764,7 @@ static int phase_extract(icl_ctx *c) {
                         int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
                         q = top;
                         for (int32_t k = 0; k < m; k++) {
+                            if (q < 0) break;                                   // (only with a caller's broken order, reported below)
                             present[q] = 0;
                             const int32_t i = rev ? imap[q - n] : q;            // forward sorted position
                             mscr[cursor + k] = i;
@@ -1662,6 +1794,15 @@ static int phase_extract(icl_ctx *c) {
                 tC = tD; topC = topD; tD = tE;
             }
         }));
+#ifndef ICL_EMU
+        if (V > 0) {
+            TreeArgs T{n, V, key, tpos, rank2v, pd, imap, l1, l2, big, stats, acc_m, acc_ms, acc_L, mscr, acc_box, over_gap, cov};
+            ICL_CUDA(st, cudaFuncSetAttribute(k_tree_walk_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, ICL_TREE_SMEM));
+            k_tree_walk_staged<<<148 * 3, 32, ICL_TREE_SMEM, s>>>(T);
+            ICL_COUNT_KERNEL();
+            ICL_CUDA(st, cudaGetLastError());
+        }
+#endif
     }
     // acceptance order = rank order: block index and member offset by prefix sums over rank positions
     {

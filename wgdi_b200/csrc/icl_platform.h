@@ -162,6 +162,15 @@ ICL_HD void atomic_add_i32(int32_t *p, int32_t v) {
     *p += v;
 #endif
 }
+ICL_HD int32_t atomic_fetch_add_i32(int32_t *p, int32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    const int32_t old = *p;
+    *p += v;
+    return old;
+#endif
+}
 ICL_HD void atomic_add_i64(int64_t *p, int64_t v) {
 #if defined(__CUDA_ARCH__)
     atomicAdd((unsigned long long *)p, (unsigned long long)v);
@@ -184,6 +193,16 @@ ICL_HD void atomic_or_i32(int32_t *p, int32_t v) {
 inline int radix_sort_pairs(Status &st, Buf<uint8_t> &tmp, const uint64_t *kin, uint64_t *kout,
                             const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, cudaStream_t s) {
     size_t bytes = 0;
+    ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+    if (tmp.reserve(st, bytes)) return st.code;
+    ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
+    ++launch_count().cub;
+    return 0;
+}
+inline int radix_sort_pairs32(Status &st, Buf<uint8_t> &tmp, const uint32_t *kin, uint32_t *kout,
+                              const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, cudaStream_t s) {
+    size_t bytes = 0;
+    if (end_bit > 32) end_bit = 32;
     ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
     if (tmp.reserve(st, bytes)) return st.code;
     ICL_CUDA(st, cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, s));
@@ -248,6 +267,15 @@ inline int radix_sort_pairs(Status &, Buf<uint8_t> &, const uint64_t *kin, uint6
     std::vector<uint32_t> o((size_t)n);
     std::iota(o.begin(), o.end(), 0u);
     uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
+    std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
+    for (int64_t i = 0; i < n; i++) { kout[i] = kin[o[i]]; vout[i] = vin[o[i]]; }
+    return 0;
+}
+inline int radix_sort_pairs32(Status &, Buf<uint8_t> &, const uint32_t *kin, uint32_t *kout,
+                              const uint32_t *vin, uint32_t *vout, int64_t n, int end_bit, cudaStream_t) {
+    std::vector<uint32_t> o((size_t)n);
+    std::iota(o.begin(), o.end(), 0u);
+    uint32_t mask = end_bit >= 32 ? ~0u : ((1u << end_bit) - 1);
     std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
     for (int64_t i = 0; i < n; i++) { kout[i] = kin[o[i]]; vout[i] = vin[o[i]]; }
     return 0;
