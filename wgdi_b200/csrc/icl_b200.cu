@@ -102,6 +102,7 @@ struct icl_ctx {
     Buf<uint8_t> present;
     Buf<int2> hint;                  // per point: {depth of the nearest removed ancestor, tree version} memo
     Buf<int2> big_trees;             // [t0, uend) of the trees that go to the staged walk
+    Buf<int2> small_trees;           // ... and of the short ones (one thread each)
     int64_t NB = 0, NM = 0;
     Buf<int32_t> b_top, b_m, b_L, b_j0, b_j1, b_l2min, b_l2max, b_L1, b_item, b_N;
     Buf<uint32_t> b_moff;
@@ -238,7 +239,7 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
     const char *pvm = getenv("ICL_B200_PVALUE");
-    if (pvm) c->pvalue_mode = !strcmp(pvm, "seq") ? 1 : !strcmp(pvm, "inc") ? 2 : 0;
+    if (pvm) c->pvalue_mode = !strcmp(pvm, "seq") ? 1 : !strcmp(pvm, "inc") ? 2 : !strcmp(pvm, "warp") ? 3 : 0;
     if (mode) c->chain_mode = !strcmp(mode, "generic") ? 0 : !strcmp(mode, "single") ? 3 : 1;
     *out = c;
     return ICL_OK;
@@ -257,7 +258,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->loc1s.release(); c->loc2s.release(); c->pair_s.release(); c->rowptr.release();
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->tile_state.release(); c->tile_dst.release(); c->edge_stage.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
-    c->S.release(); c->root.release(); c->hint.release(); c->big_trees.release(); c->pd.release(); c->used.release(); c->score32.release();
+    c->S.release(); c->root.release(); c->hint.release(); c->big_trees.release(); c->small_trees.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
     c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
     c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
@@ -1516,7 +1517,152 @@ extern "C" int icl_debug_dp(icl_ctx *c, int32_t dir, int32_t *score, int32_t *pr
 // ------------------------------------------------------------------------------------------------
 #define ICL_TREE_SMALL 32           // trees of at most this many used points: one thread each, on global memory
 #define ICL_TREE_CAP 2048            // larger ones up to this size: one warp each, staged in shared memory
-#define ICL_TREE_SMEM (ICL_TREE_CAP * 37 + 64)
+#define ICL_TREE_SMEM (ICL_TREE_CAP * 41 + 64)
+// One predecessor tree on global memory: its points are the sorted entries [t0, uend), in rank order.
+struct TreeWalk {
+    int64_t n, V;
+    const uint32_t *key, *tpos;
+    const int32_t *rank2v;
+    const int2 *pd;
+    const int32_t *imap, *l1, *l2;
+    uint8_t *present;
+    int2 *hint;
+    uint32_t *acc_m, *acc_ms;
+    int32_t *acc_L, *mscr;
+    int4 *acc_box;
+    int32_t over_gap;
+    double cov;
+    // end of the run of equal keys that starts at t0: gallop, then bisect
+    ICL_HD int64_t run_end(int64_t t0) const {
+        const uint32_t rt = key[t0];
+        int64_t lo = t0 + 1, step = 1;
+        while (lo < V && key[lo] == rt) { lo += step; step <<= 1; }
+        int64_t a0 = lo - (step >> 1), b0 = lo < V ? lo : V;             // key[a0 - 1] == rt (or a0 == t0 + 1), key[b0] != rt
+        if (a0 < t0 + 1) a0 = t0 + 1;
+        while (a0 < b0) {
+            const int64_t mid = a0 + ((b0 - a0) >> 1);
+            if (key[mid] == rt) a0 = mid + 1; else b0 = mid;
+        }
+        return a0;
+    }
+    ICL_HD void walk(int64_t t0, int64_t uend) const {
+        int32_t ver = 0;                                                    // accepted blocks of this tree so far
+        uint32_t cursor = (uint32_t)t0;                                     // member scratch: the tree's own slice
+        // The tops of a tree are examined strictly in rank order, but everything a top needs except `present` and
+        // the memo is read-only here, and those two only change for OTHER tops when a block is accepted (ver++).
+        // So the loads run three tops ahead of the decisions (rank position at distance 3, point at 2, node record
+        // + present + memo at 1) and a prefetched present / memo is re-read only if a block was accepted since.
+        // A memo fetched before a rejected child wrote it is merely older: it is used only when its version
+        // matches, otherwise the path is walked — both are exact.
+        uint32_t tA = tpos[t0];
+        uint32_t tB = t0 + 1 < uend ? tpos[t0 + 1] : 0u, tC = t0 + 2 < uend ? tpos[t0 + 2] : 0u, tD = t0 + 3 < uend ? tpos[t0 + 3] : 0u;
+        int32_t topA = rank2v[tA], topB = t0 + 1 < uend ? rank2v[tB] : 0, topC = t0 + 2 < uend ? rank2v[tC] : 0;
+        int2 ndA = ICL_LDG(pd + topA), hA = hint[topA];
+        uint8_t prA = present[topA];
+        int32_t verA = 0, verB = 0;
+        int2 ndB = make_int2(0, 0), hB = make_int2(0, 0);
+        uint8_t prB = 0;
+        if (t0 + 1 < uend) { ndB = ICL_LDG(pd + topB); hB = hint[topB]; prB = present[topB]; }
+        for (int64_t u = t0; u < uend; u++) {                               // the tree's points in rank order
+            const uint32_t tE = u + 4 < uend ? tpos[u + 4] : 0u;
+            const int32_t topD = u + 3 < uend ? rank2v[tD] : 0;
+            int2 ndC = make_int2(0, 0), hC = make_int2(0, 0);
+            uint8_t prC = 0;
+            const int32_t verC = ver;
+            if (u + 2 < uend) { ndC = ICL_LDG(pd + topC); hC = hint[topC]; prC = present[topC]; }
+            const uint32_t t = tA;
+            const int32_t top = topA;
+            const int2 nd = ndA;
+            uint8_t pr = prA;
+            int2 h = hA;
+            if (verA != ver) { pr = present[top]; h = hint[top]; }
+            if (pr) {
+                const int32_t L = nd.y;
+                int32_t m, q;
+                if (ver == 0) {
+                    m = L;                                                  // nothing of this tree removed yet
+                } else if (h.y == ver) {
+                    m = L - h.x;                                            // boundary known from a rejected child
+                } else {
+                    m = 1; q = nd.x;
+                    while (q >= 0 && present[q]) { m++; q = ICL_LDG(pd + q).x; }     // present part of the path
+                }
+                if (L >= over_gap && (double)m / (double)L > cov) {         // :129
+                    // remove the members (:130), list them, bounding box (:131)
+                    const bool rev = top >= n;
+                    int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
+                    q = top;
+                    for (int32_t k = 0; k < m; k++) {
+                        if (q < 0) break;                                   // (only with a caller's broken order, reported below)
+                        present[q] = 0;
+                        const int32_t i = rev ? imap[q - n] : q;            // forward sorted position
+                        mscr[cursor + k] = i;
+                        const int32_t yv = l2[i];
+                        l2min = yv < l2min ? yv : l2min;
+                        l2max = yv > l2max ? yv : l2max;
+                        if (k == 0) ifirst = i;
+                        ilast = i;
+                        q = ICL_LDG(pd + q).x;
+                    }
+                    ver++;                                                  // removed ancestors changed: memos expire
+                    const int32_t la = l1[ifirst], lb = l1[ilast];
+                    acc_m[t] = (uint32_t)m;
+                    acc_L[t] = L;
+                    acc_ms[t] = cursor;
+                    acc_box[t] = make_int4(la < lb ? la : lb, la < lb ? lb : la, l2min, l2max);
+                    cursor += (uint32_t)m;
+                } else {
+                    present[top] = 0;                                       // :143
+                    // the parent sees the same removed ancestor until the next accepted block of this tree;
+                    // without the memo a long path whose root side was taken by another block costs O(L^2) hops
+                    if (m > 1) hint[nd.x] = make_int2(L - m, ver);
+                }
+            }
+            tA = tB; topA = topB; ndA = ndB; hA = hB; prA = prB; verA = verB;
+            tB = tC; topB = topC; ndB = ndC; hB = hC; prB = prC; verB = verC;
+            tC = tD; topC = topD; tD = tE;
+        }
+    }
+};
+
+#ifndef ICL_EMU
+// heads of the sorted runs (one predecessor tree each) -> the queue of short trees (warp-aggregated push) or of long ones
+__global__ void __launch_bounds__(256) k_tree_heads(TreeWalk W, int2 *smallq, int2 *bigq, int32_t *stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t b0 = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31); b0 < W.V; b0 += stride) {
+        const int64_t t0 = b0 + lane;
+        bool head = false;
+        if (t0 < W.V) {
+            const uint32_t rt = W.key[t0];
+            head = rt < (uint32_t)W.V && (t0 == 0 || W.key[t0 - 1] != rt);
+        }
+        int64_t uend = 0;
+        if (head) uend = W.run_end(t0);
+        const bool big = head && uend - t0 > ICL_TREE_SMALL && uend - t0 <= ICL_TREE_CAP;
+        const bool small = head && !big;
+        const uint32_t ms = __ballot_sync(0xffffffffu, small);
+        if (ms) {
+            const int leader = __ffs(ms) - 1;
+            int32_t at = 0;
+            if (lane == leader) at = atomicAdd(&stats[3], __popc(ms));
+            at = __shfl_sync(0xffffffffu, at, leader);
+            if (small) smallq[at + __popc(ms & ((1u << lane) - 1u))] = make_int2((int32_t)t0, (int32_t)uend);
+        }
+        if (big) bigq[atomicAdd(&stats[1], 1)] = make_int2((int32_t)t0, (int32_t)uend);
+    }
+}
+
+// one thread per short tree, on global memory
+__global__ void __launch_bounds__(128) k_tree_walk_small(TreeWalk W, const int2 *smallq, const int32_t *stats) {
+    const int32_t count = stats[3];
+    for (int32_t i = blockIdx.x * 128 + threadIdx.x; i < count; i += gridDim.x * 128) {
+        const int2 rg = smallq[i];
+        W.walk(rg.x, rg.y);
+    }
+}
+#endif
+
 #ifndef ICL_EMU
 struct TreeArgs {
     int64_t n, V;
@@ -1544,7 +1690,8 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
     int32_t *s_y = s_f + ICL_TREE_CAP;                         // loc2
     int32_t *s_pl = s_y + ICL_TREE_CAP;                        // predecessor: index into the tree, -1 for the root
     int32_t *s_L = s_pl + ICL_TREE_CAP;                        // path length
-    int2 *s_h = (int2 *)(s_L + ICL_TREE_CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
+    int32_t *s_x = s_L + ICL_TREE_CAP;                         // loc1
+    int2 *s_h = (int2 *)(s_x + ICL_TREE_CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
     uint8_t *s_pres = (uint8_t *)(s_h + 2 * ICL_TREE_CAP);
     const int lane = threadIdx.x;
     const uint32_t FULL = 0xffffffffu;
@@ -1560,16 +1707,24 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
         for (int32_t i = lane; i < hsz; i += 32) s_h[i] = make_int2(-1, -1);
         __syncwarp();
         bool rev = false;
-        for (int32_t j = lane; j < N; j += 32) {
-            const int32_t t = (int32_t)T.tpos[t0 + j], v = T.rank2v[t];
-            const int2 nd = T.pd[v];
-            const int32_t i = v >= T.n ? T.imap[v - T.n] : v;
-            s_t[j] = t; s_f[j] = i; s_y[j] = T.l2[i]; s_pl[j] = nd.x; s_L[j] = nd.y; s_pres[j] = 1;
-            if (j == 0) rev = v >= T.n;
-            uint32_t h = ((uint32_t)v * 2654435761u) & (uint32_t)(hsz - 1);
-            int32_t tries = 0;                                 // (bounded: a caller's broken order must not hang the GPU)
-            while (atomicCAS(&s_h[h].x, -1, v) != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
-            if (tries < hsz) s_h[h].y = j;
+        for (int32_t j0 = lane; j0 < N; j0 += 64) {             // two independent load chains per lane and round
+            const int32_t j1 = j0 + 32;
+            const bool two = j1 < N;
+            const int32_t ta = (int32_t)T.tpos[t0 + j0], tb = two ? (int32_t)T.tpos[t0 + j1] : ta;
+            const int32_t va = T.rank2v[ta], vb = T.rank2v[tb];
+            const int2 na = T.pd[va], nb = T.pd[vb];
+            const int32_t ia = va >= T.n ? T.imap[va - T.n] : va, ib = vb >= T.n ? T.imap[vb - T.n] : vb;
+            const int32_t ya = T.l2[ia], yb = T.l2[ib], xa = T.l1[ia], xb = T.l1[ib];
+            if (j0 == 0) rev = va >= T.n;
+            for (int r = 0; r < (two ? 2 : 1); r++) {
+                const int32_t j = r ? j1 : j0, t = r ? tb : ta, v = r ? vb : va, i = r ? ib : ia;
+                const int2 nd = r ? nb : na;
+                s_t[j] = t; s_f[j] = i; s_y[j] = r ? yb : ya; s_x[j] = r ? xb : xa; s_pl[j] = nd.x; s_L[j] = nd.y; s_pres[j] = 1;
+                uint32_t h = ((uint32_t)v * 2654435761u) & (uint32_t)(hsz - 1);
+                int32_t tries = 0;                             // (bounded: a caller's broken order must not hang the GPU)
+                while (atomicCAS(&s_h[h].x, -1, v) != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
+                if (tries < hsz) s_h[h].y = j;
+            }
         }
         rev = __shfl_sync(FULL, rev, 0);
         __syncwarp();
@@ -1598,22 +1753,20 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
                 else if (s_h[u].y == ver) m = L - s_h[u].x;
                 else { m = 1; q = s_pl[u]; while (q >= 0 && s_pres[q]) { m++; q = s_pl[q]; } }
                 if (L >= T.over_gap && (double)m / (double)L > T.cov) {          // :129
-                    int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
+                    int32_t l2min = 0x7fffffff, l2max = -1, la = 0, lb = 0;
                     q = u;
                     for (int32_t k = 0; k < m; k++) {
                         if (q < 0) break;                      // (only with a caller's broken order, reported by the caller)
                         s_pres[q] = 0;
-                        const int32_t i = s_f[q];
-                        T.mscr[cursor + k] = i;
+                        T.mscr[cursor + k] = s_f[q];
                         const int32_t yv = s_y[q];
                         l2min = yv < l2min ? yv : l2min;
                         l2max = yv > l2max ? yv : l2max;
-                        if (k == 0) ifirst = i;
-                        ilast = i;
+                        if (k == 0) la = s_x[q];
+                        lb = s_x[q];
                         q = s_pl[q];
                     }
                     ver++;
-                    const int32_t la = T.l1[ifirst], lb = T.l1[ilast];
                     const int32_t t = s_t[u];
                     T.acc_m[t] = (uint32_t)m;
                     T.acc_L[t] = L;
@@ -1641,7 +1794,7 @@ static int phase_extract(icl_ctx *c) {
         c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) || c->acc_ms.reserve(st, V) ||
         c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->acc_flag.reserve(st, V + 2) ||
         c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4) ||
-        c->big_trees.reserve(st, V / ICL_TREE_SMALL + 2))
+        c->big_trees.reserve(st, V / ICL_TREE_SMALL + 2) || c->small_trees.reserve(st, V + 2))
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
     ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
@@ -1693,109 +1846,23 @@ static int phase_extract(icl_ctx *c) {
 #ifndef ICL_EMU
         int2 *big = c->big_trees.p;
 #endif
+        TreeWalk W{n, V, key, tpos, rank2v, pd, imap, l1, l2, present, hint, acc_m, acc_ms, acc_L, mscr, acc_box, over_gap, cov};
+#ifdef ICL_EMU
         ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t0) {
             const uint32_t rt = key[t0];
             if (rt >= (uint32_t)V) return;                                      // unused tail
             if (t0 > 0 && key[t0 - 1] == rt) return;                            // not the head of its tree
-            int32_t ver = 0;                                                    // accepted blocks of this tree so far
-            uint32_t cursor = (uint32_t)t0;                                     // member scratch: the tree's own slice
-            // end of the tree's run of equal keys: gallop, then bisect
-            int64_t lo = t0 + 1, step = 1, uend;
-            while (lo < V && key[lo] == rt) { lo += step; step <<= 1; }
-            {
-                int64_t a0 = lo - (step >> 1), b0 = lo < V ? lo : V;             // key[a0 - 1] == rt (or a0 == t0 + 1), key[b0] != rt
-                if (a0 < t0 + 1) a0 = t0 + 1;
-                while (a0 < b0) {
-                    const int64_t mid = a0 + ((b0 - a0) >> 1);
-                    if (key[mid] == rt) a0 = mid + 1; else b0 = mid;
-                }
-                uend = a0;
-            }
-#ifndef ICL_EMU
-            // a long tree is a long chain of dependent loads for one thread (ncu: 5.4 of 32 threads active, the walk as
-            // long as its largest tree): it goes to k_tree_walk_staged, one warp with the tree in shared memory
-            if (uend - t0 > ICL_TREE_SMALL && uend - t0 <= ICL_TREE_CAP) {
-                big[atomic_fetch_add_i32(&stats[1], 1)] = make_int2((int32_t)t0, (int32_t)uend);
-                return;
-            }
-#endif
-            // The tops of a tree are examined strictly in rank order, but everything a top needs except `present` and
-            // the memo is read-only here, and those two only change for OTHER tops when a block is accepted (ver++).
-            // So the loads run three tops ahead of the decisions (rank position at distance 3, point at 2, node record
-            // + present + memo at 1) and a prefetched present / memo is re-read only if a block was accepted since.
-            // A memo fetched before a rejected child wrote it is merely older: it is used only when its version
-            // matches, otherwise the path is walked — both are exact.
-            uint32_t tA = tpos[t0];
-            uint32_t tB = t0 + 1 < uend ? tpos[t0 + 1] : 0u, tC = t0 + 2 < uend ? tpos[t0 + 2] : 0u, tD = t0 + 3 < uend ? tpos[t0 + 3] : 0u;
-            int32_t topA = rank2v[tA], topB = t0 + 1 < uend ? rank2v[tB] : 0, topC = t0 + 2 < uend ? rank2v[tC] : 0;
-            int2 ndA = ICL_LDG(pd + topA), hA = hint[topA];
-            uint8_t prA = present[topA];
-            int32_t verA = 0, verB = 0;
-            int2 ndB = make_int2(0, 0), hB = make_int2(0, 0);
-            uint8_t prB = 0;
-            if (t0 + 1 < uend) { ndB = ICL_LDG(pd + topB); hB = hint[topB]; prB = present[topB]; }
-            for (int64_t u = t0; u < uend; u++) {                               // the tree's points in rank order
-                const uint32_t tE = u + 4 < uend ? tpos[u + 4] : 0u;
-                const int32_t topD = u + 3 < uend ? rank2v[tD] : 0;
-                int2 ndC = make_int2(0, 0), hC = make_int2(0, 0);
-                uint8_t prC = 0;
-                const int32_t verC = ver;
-                if (u + 2 < uend) { ndC = ICL_LDG(pd + topC); hC = hint[topC]; prC = present[topC]; }
-                const uint32_t t = tA;
-                const int32_t top = topA;
-                const int2 nd = ndA;
-                uint8_t pr = prA;
-                int2 h = hA;
-                if (verA != ver) { pr = present[top]; h = hint[top]; }
-                if (pr) {
-                    const int32_t L = nd.y;
-                    int32_t m, q;
-                    if (ver == 0) {
-                        m = L;                                                  // nothing of this tree removed yet
-                    } else if (h.y == ver) {
-                        m = L - h.x;                                            // boundary known from a rejected child
-                    } else {
-                        m = 1; q = nd.x;
-                        while (q >= 0 && present[q]) { m++; q = ICL_LDG(pd + q).x; }     // present part of the path
-                    }
-                    if (L >= over_gap && (double)m / (double)L > cov) {         // :129
-                        // remove the members (:130), list them, bounding box (:131)
-                        const bool rev = top >= n;
-                        int32_t l2min = 0x7fffffff, l2max = -1, ifirst = 0, ilast = 0;
-                        q = top;
-                        for (int32_t k = 0; k < m; k++) {
-                            if (q < 0) break;                                   // (only with a caller's broken order, reported below)
-                            present[q] = 0;
-                            const int32_t i = rev ? imap[q - n] : q;            // forward sorted position
-                            mscr[cursor + k] = i;
-                            const int32_t yv = l2[i];
-                            l2min = yv < l2min ? yv : l2min;
-                            l2max = yv > l2max ? yv : l2max;
-                            if (k == 0) ifirst = i;
-                            ilast = i;
-                            q = ICL_LDG(pd + q).x;
-                        }
-                        ver++;                                                  // removed ancestors changed: memos expire
-                        const int32_t la = l1[ifirst], lb = l1[ilast];
-                        acc_m[t] = (uint32_t)m;
-                        acc_L[t] = L;
-                        acc_ms[t] = cursor;
-                        acc_box[t] = make_int4(la < lb ? la : lb, la < lb ? lb : la, l2min, l2max);
-                        cursor += (uint32_t)m;
-                    } else {
-                        present[top] = 0;                                       // :143
-                        // the parent sees the same removed ancestor until the next accepted block of this tree;
-                        // without the memo a long path whose root side was taken by another block costs O(L^2) hops
-                        if (m > 1) hint[nd.x] = make_int2(L - m, ver);
-                    }
-                }
-                tA = tB; topA = topB; ndA = ndB; hA = hB; prA = prB; verA = verB;
-                tB = tC; topB = topC; ndB = ndC; hB = hC; prB = prC; verB = verC;
-                tC = tD; topC = topD; tD = tE;
-            }
+            W.walk(t0, W.run_end(t0));
         }));
-#ifndef ICL_EMU
+#else
         if (V > 0) {
+            // tree heads -> two queues: trees of at most ICL_TREE_SMALL points (one thread each: compacted, so that every
+            // lane of a warp has a tree to walk) and longer ones (one warp each, staged in shared memory)
+            int2 *smallq = c->small_trees.p;
+            k_tree_heads<<<148 * 8, 256, 0, s>>>(W, smallq, big, stats);
+            ICL_COUNT_KERNEL();
+            k_tree_walk_small<<<148 * 8, 128, 0, s>>>(W, smallq, stats);
+            ICL_COUNT_KERNEL();
             TreeArgs T{n, V, key, tpos, rank2v, pd, imap, l1, l2, big, stats, acc_m, acc_ms, acc_L, mscr, acc_box, over_gap, cov};
             ICL_CUDA(st, cudaFuncSetAttribute(k_tree_walk_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, ICL_TREE_SMEM));
             k_tree_walk_staged<<<148 * 3, 32, ICL_TREE_SMEM, s>>>(T);
@@ -1973,6 +2040,72 @@ __global__ void __launch_bounds__(32) k_pvalue(PvalArgs A, int32_t l2_cap) {
 }
 #endif
 
+#ifndef ICL_EMU
+// times / N / N1 with several warps per chromosome pair.  `times` couples the blocks of a pair only through the points
+// they share, so the POINTS are divided instead of the blocks: every warp owns a contiguous share of the pair's points,
+// walks ALL blocks of the pair in acceptance order (forward, then anti-diagonal) and treats the part of each box's row
+// slice that falls into its share — the counters of a point are only ever touched by its owner, in block order, so the
+// warps never wait for each other; the per-block sums meet in b_N / b_N1 through atomic adds (zeroed before the launch).
+// Blocks that miss a warp's share cost it one ballot per 32 blocks.  (The one-warp-per-pair kernel was a chain of ~900
+// dependent block steps on the heaviest pair: 0.40 ms on C2 with 2.4 warps per SM.)
+// TS: counters and loc2 of the pair in shared memory (pairs up to l2_cap points); else counters in global memory.
+template <bool TS>
+__global__ void __launch_bounds__(1024) k_pvalue_owned(PvalArgs A) {
+    extern __shared__ __align__(16) unsigned char psm[];
+    const int32_t p = A.pair_order[blockIdx.x];
+    const int64_t a = A.off[p], np_ = A.off[p + 1] - a;
+    const uint32_t bf0 = A.blkidx[a], bf1 = A.blkidx[a + np_], br0 = A.blkidx[A.n + a], br1 = A.blkidx[A.n + a + np_];
+    if (bf1 - bf0 + br1 - br0 == 0) return;
+    uint32_t *tsm = (uint32_t *)psm;                           // TS: one counter per point of the pair
+    int32_t *l2sm = (int32_t *)(psm + (((size_t)np_ * 4 + 15) & ~(size_t)15));
+    if (TS) {
+        for (int64_t i = threadIdx.x; i < np_; i += blockDim.x) { tsm[i] = 1; l2sm[i] = A.l2[a + i]; }   // get_matrix :34
+    } else {
+        for (int64_t i = threadIdx.x; i < np_; i += blockDim.x) A.times[a + i] = 1;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int32_t own0 = (int32_t)(a + np_ * w / nw), own1 = (int32_t)(a + np_ * (w + 1) / nw);
+    const uint32_t FULL = 0xffffffffu;
+    for (int d = 0; d < 2; d++) {
+        const uint32_t b0 = d ? br0 : bf0, b1 = d ? br1 : bf1;
+        for (uint32_t base = b0; base < b1; base += 32) {
+            const uint32_t b = base + lane;
+            int32_t rj0 = 0, rj1 = 0, rlo = 0, rhi = 0;
+            if (b < b1) { rj0 = A.b_j0[b]; rj1 = A.b_j1[b]; rlo = A.b_l2min[b]; rhi = A.b_l2max[b]; }
+            rj0 = rj0 > own0 ? rj0 : own0;                     // the slice inside my share
+            rj1 = rj1 < own1 ? rj1 : own1;
+            uint32_t todo = __ballot_sync(FULL, b < b1 && rj0 < rj1);
+            while (todo) {
+                const int i = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int32_t j0 = __shfl_sync(FULL, rj0, i), j1 = __shfl_sync(FULL, rj1, i);
+                const int32_t lo = __shfl_sync(FULL, rlo, i), hi = __shfl_sync(FULL, rhi, i);
+                uint32_t N = 0;
+                unsigned long long N1 = 0;
+                for (int32_t q = j0 + lane; q < j1; q += 32) {                    // :134-137 inclusive box
+                    const int32_t y = TS ? l2sm[q - a] : __ldg(A.l2 + q);
+                    if (y >= lo && y <= hi) {
+                        uint32_t t;
+                        if (TS) { t = tsm[q - a]; tsm[q - a] = t + 1; }
+                        else { t = (uint32_t)A.times[q]; A.times[q] = (int32_t)t + 1; }
+                        N1 += t;                                                  // :148
+                        N++;                                                      // :149, times += 1 :150
+                    }
+                }
+                N = __reduce_add_sync(FULL, N);
+                for (int o = 16; o > 0; o >>= 1) N1 += __shfl_xor_sync(FULL, N1, o);
+                __syncwarp();                                  // my lanes' counters before the next block of my share
+                if (lane == 0 && N) {
+                    atomicAdd(&A.b_N[base + i], (int32_t)N);
+                    atomicAdd((unsigned long long *)&A.b_N1[base + i], N1);
+                }
+            }
+        }
+    }
+}
+#endif
+
 // Order-free form of the `times` accounting: times[q] before block b = 1 + number of blocks accepted earlier in
 // the same pair whose box contains q, so  N1(b) = N(b) + sum over the points q of box(b) of rank_q(b),  where
 // rank_q(b) counts the earlier blocks containing q.  Enumerate the (point, block) incidences of all boxes in
@@ -2068,19 +2201,34 @@ static int phase_pvalue(icl_ctx *c) {
     // sequential warp-per-pair kernel; large pairs serialise there and take the order-free incidence path.
     int64_t maxnp_all = 1;
     for (int32_t p = 0; p < P; p++) maxnp_all = std::max<int64_t>(maxnp_all, c->h_pair_off[p + 1] - c->h_pair_off[p]);
-    const bool prefer_seq = c->pvalue_mode == 1 || (c->pvalue_mode == 0 && maxnp_all <= 12 * 1024);
+    const bool prefer_seq = c->pvalue_mode != 2;               // the incidence form stays selectable (env ICL_B200_PVALUE=inc)
     bool handled = false;
     if (!prefer_seq && phase_pvalue_incidence(c, &handled)) return st.code;
     if (!handled) {
 #ifndef ICL_EMU
     int64_t maxnp = 1;
     for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
-    // shared memory per CTA: uint16 times for up to smem_cap points (+ int32 loc2 for up to l2_cap points)
-    A.smem_cap = (int32_t)std::min<int64_t>(maxnp, 100 * 1024);
-    int32_t l2_cap = (int32_t)std::min<int64_t>(maxnp, 12 * 1024);              // keeps >= 3 CTAs per SM
-    size_t smem = (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15) + (size_t)l2_cap * 4;
-    ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    k_pvalue<<<(unsigned)P, 32, smem, s>>>(A, l2_cap);
+    ICL_CUDA(st, dev_memset(c->b_N.p, 0, (size_t)NB * sizeof(int32_t), s));
+    ICL_CUDA(st, dev_memset(c->b_N1.p, 0, (size_t)NB * sizeof(int64_t), s));
+    if (c->pvalue_mode == 3) {                                 // the one-warp-per-pair kernel (A/B, env ICL_B200_PVALUE=warp)
+        // shared memory per CTA: uint16 times for up to smem_cap points (+ int32 loc2 for up to l2_cap points)
+        A.smem_cap = (int32_t)std::min<int64_t>(maxnp, 100 * 1024);
+        int32_t l2_cap = (int32_t)std::min<int64_t>(maxnp, 12 * 1024);              // keeps >= 3 CTAs per SM
+        size_t smem = (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15) + (size_t)l2_cap * 4;
+        ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        k_pvalue<<<(unsigned)P, 32, smem, s>>>(A, l2_cap);
+    } else {
+        // warps per pair: enough that a warp's share of the blocks is short, few enough that several pairs fit an SM
+        const bool ts = maxnp <= 27 * 1024;                    // counters + loc2 of the pair: 8 B per point in shared memory
+        const int threads = maxnp <= 4096 ? 128 : maxnp <= 12 * 1024 ? 256 : maxnp <= 40 * 1024 ? 512 : 1024;
+        if (ts) {
+            const size_t smem = (((size_t)maxnp * 4 + 15) & ~(size_t)15) + (size_t)maxnp * 4;
+            ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue_owned<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            k_pvalue_owned<true><<<(unsigned)P, threads, smem, s>>>(A);
+        } else {
+            k_pvalue_owned<false><<<(unsigned)P, threads, 0, s>>>(A);
+        }
+    }
     ICL_COUNT_KERNEL();
     ICL_CUDA(st, cudaGetLastError());
 #else
