@@ -45,6 +45,10 @@ struct GradeTable {
 struct icl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // side stream: kernels of a phase that do not depend on each other (fork / join by events)
+#ifndef ICL_EMU
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
     Status st;
     int64_t n = 0;      // points
     int32_t P = 0;      // chromosome pairs
@@ -84,6 +88,8 @@ struct icl_ctx {
     bool order_on_device = false;    // icl_rank_device filled order_in
     bool keys_on_device = false;     // ... from score32 (numpy flavours)
     bool order_on_device_used = false;   // the current icl_extract takes the device's order
+    bool rank_flag_pending = false;      // icl_rank_device left its hand-back flag (host_flag[rank_flag_slot]) unread
+    int32_t rank_flag_slot = 0;
     int32_t pvalue_mode = 0;         // 0 = by pair size, 1 = sequential warp-per-pair kernel, 2 = incidence sort (env ICL_B200_PVALUE=seq|inc)
     Buf<uint32_t> inc_cnt, inc_off;
     Buf<int32_t> inc_start;
@@ -235,6 +241,10 @@ extern "C" int icl_create(int device, icl_ctx **out) {
 #ifndef ICL_EMU
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
+    e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
 #endif
     if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
@@ -274,6 +284,10 @@ extern "C" void icl_destroy(icl_ctx *c) {
 #endif
     for (auto &t : c->timers) t.destroy();
 #ifndef ICL_EMU
+    cudaStreamSynchronize(c->stream2);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
 #endif
     delete c;
@@ -1413,7 +1427,9 @@ static int dp_run(icl_ctx *c, const icl_params *prm, int32_t *score_fwd, int32_t
         }
     }
     c->timers[ICL_T_D2H].stop(s);
-    ICL_CUDA(st, dev_sync(s));
+    // with scores for the host the call ends when they have arrived; without (device rank), the next phase is simply
+    // queued behind this one on the stream
+    if (want_keys || queue || getenv("ICL_B200_CHAIN_DEBUG")) ICL_CUDA(st, dev_sync(s));
     if (dump_chain_debug(c)) return st.code;
     if (queue) for (int64_t i = 0; i < 2 * (int64_t)c->P; i++) queue[i] = 1;     // not streamed: everything is complete now
     c->dp_begun = true;
@@ -1517,7 +1533,7 @@ extern "C" int icl_debug_dp(icl_ctx *c, int32_t dir, int32_t *score, int32_t *pr
 // ------------------------------------------------------------------------------------------------
 #define ICL_TREE_SMALL 32           // trees of at most this many used points: one thread each, on global memory
 #define ICL_TREE_CAP 2048            // larger ones up to this size: one warp each, staged in shared memory
-#define ICL_TREE_SMEM (ICL_TREE_CAP * 41 + 64)
+#define ICL_TREE_SMEM (ICL_TREE_CAP * 45 + 64)
 // One predecessor tree on global memory: its points are the sorted entries [t0, uend), in rank order.
 struct TreeWalk {
     int64_t n, V;
@@ -1639,6 +1655,9 @@ __global__ void __launch_bounds__(256) k_tree_heads(TreeWalk W, int2 *smallq, in
         }
         int64_t uend = 0;
         if (head) uend = W.run_end(t0);
+        // a path is made of points of its tree: a tree with fewer used points than over_gap cannot yield a block (:129), and
+        // nothing else looks at its `present` flags — most trees are such pairs of noise hits
+        head = head && uend - t0 >= W.over_gap;
         const bool big = head && uend - t0 > ICL_TREE_SMALL && uend - t0 <= ICL_TREE_CAP;
         const bool small = head && !big;
         const uint32_t ms = __ballot_sync(0xffffffffu, small);
@@ -1691,7 +1710,8 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
     int32_t *s_pl = s_y + ICL_TREE_CAP;                        // predecessor: index into the tree, -1 for the root
     int32_t *s_L = s_pl + ICL_TREE_CAP;                        // path length
     int32_t *s_x = s_L + ICL_TREE_CAP;                         // loc1
-    int2 *s_h = (int2 *)(s_x + ICL_TREE_CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
+    int32_t *s_mm = s_x + ICL_TREE_CAP;                        // per path length L <= N: the smallest m with (double) m / L > cov
+    int2 *s_h = (int2 *)(s_mm + ICL_TREE_CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
     uint8_t *s_pres = (uint8_t *)(s_h + 2 * ICL_TREE_CAP);
     const int lane = threadIdx.x;
     const uint32_t FULL = 0xffffffffu;
@@ -1741,6 +1761,16 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
         }
         __syncwarp();
         for (int32_t j = lane; j < N; j += 32) s_h[j] = make_int2(-1, -1);   // the memo takes the hash's place
+        // the coverage test `len(rem) / L > coverage_ratio` (:129) is a correctly rounded binary64 division in the reference;
+        // the quotient grows with m, so per L there is a smallest m that passes — found with that very division, once per
+        // length instead of once per examined top (a path of this tree is at most N long)
+        for (int32_t L = lane + 1; L <= N; L += 32) {
+            int32_t m = (int32_t)(T.cov * (double)L);
+            m = m < 0 ? 0 : m > L ? L : m;
+            while (m <= L && !((double)m / (double)L > T.cov)) m++;
+            while (m > 0 && (double)(m - 1) / (double)L > T.cov) m--;
+            s_mm[L - 1] = m;                                   // L + 1 when no m <= L passes (coverage_ratio >= 1)
+        }
         __syncwarp();
         if (lane == 0) {
             int32_t ver = 0;                                   // accepted blocks of this tree so far
@@ -1752,7 +1782,7 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
                 if (ver == 0) m = L;
                 else if (s_h[u].y == ver) m = L - s_h[u].x;
                 else { m = 1; q = s_pl[u]; while (q >= 0 && s_pres[q]) { m++; q = s_pl[q]; } }
-                if (L >= T.over_gap && (double)m / (double)L > T.cov) {          // :129
+                if (L >= T.over_gap && L <= N && m >= s_mm[L - 1]) {              // :129
                     int32_t l2min = 0x7fffffff, l2max = -1, la = 0, lb = 0;
                     q = u;
                     for (int32_t k = 0; k < m; k++) {
@@ -1861,12 +1891,18 @@ static int phase_extract(icl_ctx *c) {
             int2 *smallq = c->small_trees.p;
             k_tree_heads<<<148 * 8, 256, 0, s>>>(W, smallq, big, stats);
             ICL_COUNT_KERNEL();
-            k_tree_walk_small<<<148 * 8, 128, 0, s>>>(W, smallq, stats);
-            ICL_COUNT_KERNEL();
+            // the two walks touch different trees: the staged one (few long trees, one warp each) runs beside the short
+            // ones on the side stream
+            ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));
+            ICL_CUDA(st, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
             TreeArgs T{n, V, key, tpos, rank2v, pd, imap, l1, l2, big, stats, acc_m, acc_ms, acc_L, mscr, acc_box, over_gap, cov};
             ICL_CUDA(st, cudaFuncSetAttribute(k_tree_walk_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, ICL_TREE_SMEM));
-            k_tree_walk_staged<<<148 * 3, 32, ICL_TREE_SMEM, s>>>(T);
+            k_tree_walk_staged<<<148 * 2, 32, ICL_TREE_SMEM, c->stream2>>>(T);
             ICL_COUNT_KERNEL();
+            ICL_CUDA(st, cudaEventRecord(c->ev_join, c->stream2));
+            k_tree_walk_small<<<148 * 16, 128, 0, s>>>(W, smallq, stats);
+            ICL_COUNT_KERNEL();
+            ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join, 0));
             ICL_CUDA(st, cudaGetLastError());
         }
 #endif
@@ -1884,7 +1920,12 @@ static int phase_extract(icl_ctx *c) {
     ICL_CUDA(st, d2h(&tot[0], c->blkidx.p + V, sizeof(uint32_t), s));
     ICL_CUDA(st, d2h(&tot[1], c->moff.p + V, sizeof(uint32_t), s));
     ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), s));
+    int32_t rank_any = 0;                                      // hand-back flag icl_rank_device left unread (no sync there)
+    if (c->rank_flag_pending && c->order_on_device_used)
+        ICL_CUDA(st, d2h(&rank_any, c->host_flag.p + c->rank_flag_slot, sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
+    c->rank_flag_pending = false;
+    if (rank_any) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
     if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_extract: argsort array is not a permutation of its pair segment");
     c->NB = tot[0];
     c->NM = tot[1];
@@ -3528,7 +3569,7 @@ static cudaError_t xss_launch_v(int lanes, int warps, const XsArgs &A, unsigned 
 // longest first); lens[j] = length of segment order[j] (host copy, non-increasing).  Fails with ICL_ERR_STATE when a
 // segment needs the host rank (std::sort's heap-sort branch).
 static int rank_segments(icl_ctx *c, int32_t mode, const int32_t *key, int32_t *idx, const int64_t *off, const int32_t *order,
-                         const std::vector<int64_t> &lens) {
+                         const std::vector<int64_t> &lens, bool defer = false) {
     Status &st = c->st;
     cudaStream_t s = c->stream;
     const int32_t nseg = (int32_t)lens.size();
@@ -3583,12 +3624,17 @@ static int rank_segments(icl_ctx *c, int32_t mode, const int32_t *key, int32_t *
         j0 = j1;
     }
     ICL_CUDA(st, cudaGetLastError());
-    // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself
-    std::vector<int32_t> hf((size_t)nseg);
-    ICL_CUDA(st, d2h(hf.data(), c->host_flag.p, hf.size() * sizeof(int32_t), s));
+    // segments the kernel does not cover (std::sort's heap-sort branch) must be ranked by numpy itself: every such
+    // segment raises host_flag[nseg]; `defer` leaves the look at it to the caller's next synchronisation (icl_extract)
+    {
+        int32_t *hf = c->host_flag.p;
+        ICL_CUDA(st, foreach(s, (int64_t)nseg, ICL_LAMBDA(int64_t j) { if (hf[j]) atomic_or_i32(&hf[nseg], 1); }));
+    }
+    if (defer) { c->rank_flag_pending = true; c->rank_flag_slot = nseg; return 0; }
+    int32_t any = 0;
+    ICL_CUDA(st, d2h(&any, c->host_flag.p + nseg, sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
-    for (int32_t f : hf)
-        if (f) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
+    if (any) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
     return 0;
 }
 #endif
@@ -3615,6 +3661,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
     const int64_t n = c->n, V = 2 * n;
     const int32_t P = c->P;
     LaunchScope scope(c, 1);
+    c->rank_flag_pending = false;
     c->timers[ICL_T_D2H].start(s);
     if (c->order_in.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V))
@@ -3634,7 +3681,7 @@ extern "C" int icl_rank_device(icl_ctx *c, int32_t mode) {
 #ifndef ICL_EMU
         std::vector<int64_t> lens(2 * (size_t)P);
         for (int32_t j = 0; j < 2 * P; j++) { const int32_t it = c->h_item_order[j]; lens[j] = c->h_seg_off[it + 1] - c->h_seg_off[it]; }
-        if (rank_segments(c, mode, c->score32.p, c->order_in.p, c->d_seg_off.p, c->d_item_order.p, lens)) return st.code;
+        if (rank_segments(c, mode, c->score32.p, c->order_in.p, c->d_seg_off.p, c->d_item_order.p, lens, true)) return st.code;
 #else
         return fail(c, ICL_ERR_STATE, "icl_rank_device: the numpy-scalar mode exists in the CUDA build only");
 #endif

@@ -431,25 +431,26 @@ class IclEngine:
         self._check(self.lib.icl_dp(self.ctx, C.byref(prm), None, None))
         self.pair_off = np.zeros(self.n_pairs + 1, np.int64)
         self._check(self.lib.icl_layout(self.ctx, self.pair_off.ctypes.data, None))
-        try:
-            self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1, "numpy_avx512": 2, "numpy_avx2": 3}[mode]))
-        except IclError as e:
-            if e.code != -3 or mode == "stable":
-                raise
-            # a segment the device does not cover (std::sort's heap-sort branch): numpy itself ranks this comparison
-            self.host_rank_fallbacks += 1
-            kf, kr = self.dp(params)
-            af, ar = self.rank(kf, kr)
-            return self.extract(af, ar, min_members, copy)
-        if self.rank_verify and mode != "stable" and not self._verify_device_rank():
-            # the device's permutation is not this numpy's: numpy ranks this comparison and every later one of the process
-            self.rank_verify_failures += 1
-            _NP_KIND[self.device] = None
+        def by_numpy():
             kf, kr = self.dp(params)
             af, ar = self.rank(kf, kr)
             return self.extract(af, ar, min_members, copy)
         out = icl_blocks()
-        self._check(self.lib.icl_extract(self.ctx, None, None, int(min_members), C.byref(out)))
+        try:
+            self._check(self.lib.icl_rank_device(self.ctx, {"stable": 0, "numpy_scalar": 1, "numpy_avx512": 2, "numpy_avx2": 3}[mode]))
+            if self.rank_verify and mode != "stable" and not self._verify_device_rank():
+                # the device's permutation is not this numpy's: numpy ranks this comparison and every later one of the process
+                self.rank_verify_failures += 1
+                _NP_KIND[self.device] = None
+                return by_numpy()
+            # (the rank kernels report a segment they do not cover — std::sort's heap-sort branch — without stopping the
+            # stream: the flag is read at icl_extract's first synchronisation, which then fails with the same code)
+            self._check(self.lib.icl_extract(self.ctx, None, None, int(min_members), C.byref(out)))
+        except IclError as e:
+            if e.code != -3 or mode == "stable":
+                raise
+            self.host_rank_fallbacks += 1                  # numpy itself ranks this comparison
+            return by_numpy()
         res = self._blocks_from(out, copy)
         self.host_ms = dict(total=(time.perf_counter() - t0) * 1e3, rank=0.0)
         return res
