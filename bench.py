@@ -42,7 +42,10 @@ DP_BYTES_PER_POINT = 42          # 2 directions x [12 B read + 9
 EXPORT_BYTES_PER_POINT = 4       # streamed export of the DP kernel: the mirrored direction reads its position map (4 B);
                                  # the 8 B/point of score writes go to page-locked host memory over PCIe and are not counted
 METRIC = "blast_hits_chained_per_sec"
-NCU_TRAFFIC_C2 = 81.3e6          # bytes per launch of the DP kernel (with its export epilogue) on C2: ncu capture, profiles/r01_chain_ring_ncu_summary.md
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the DP kernel on C2 (ncu --set full captures): without the
+# export (device-ranked, the default: profiles/r02_chain_ring_ncu_summary.md) and with the streamed export to the host
+# (host-ranked: profiles/r01_chain_ring_ncu_summary.md)
+NCU_TRAFFIC_C2 = {"dp_only": 72.0e6, "streamed_export": 81.3e6}
 
 
 WORKLOADS = {   # BASELINE.json `configs`, as built by wgdi_b200/synth.py
@@ -367,7 +370,7 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     import torch.distributed as dist
     from wgdi_b200 import shard
     from wgdi_b200.engine import Blocks, IclEngine
-    FIELDS = ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx")
+    FIELDS = shard.BLOCK_FIELDS
     full = make_points(args.strong_workload)                 # same seed on every rank: the same comparison
     prm = params_for(full["cfg"])
     total = len(full["loc1"])
@@ -375,8 +378,31 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     owner = shard.lpt_assign(shard.pair_cost(sizes), world)
     pts = shard.shard_points(full, rank, world, owner=owner)
     n_local = len(pts["loc1"])
+    # host gather without a collective: ONE memory-mapped region in /dev/shm holds the merged block arrays (mapped by every
+    # rank once, outside the timed region).  Per step a rank publishes its per-pair block / member counts, all ranks meet at
+    # a barrier, every rank derives where each chromosome pair's run starts in the merged arrays and writes its own blocks
+    # there (shard.place_blocks: the merge is done by N ranks in parallel); after a second barrier rank 0 holds the whole
+    # comparison in the reference's emission order.
     shm = f"/dev/shm/icl_strong_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
     os.makedirs(shm, exist_ok=True)
+    DT = dict(pair=np.int32, dir=np.int32, score=np.int64, m=np.int32, L=np.int32, N=np.int32, N1=np.int64, L1=np.int32,
+              L2=np.int32, p_raw=np.float64, member_off=np.int64, loc1=np.int32, loc2=np.int32, member_idx=np.int32)
+    P_all = int(full["n_pairs"])
+    cap_b, cap_m = total // 5 + 64, 2 * total + 64                   # blocks of >= 5 gene pairs, both directions
+    size, offs = 0, {}
+    for f in ("counts",) + FIELDS:
+        cnt = 2 * world * P_all if f == "counts" else cap_m if f in shard.MEMBER_FIELDS else cap_b + 1
+        dt = np.int64 if f == "counts" else DT[f]
+        offs[f] = (size, cnt, dt)
+        size += (cnt * np.dtype(dt).itemsize + 63) & ~63
+    path = os.path.join(shm, "merged.bin")
+    if rank == 0:
+        np.memmap(path, dtype=np.uint8, mode="w+", shape=(size,)).flush()
+    barrier()
+    mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(size,))
+    arrs = {f: np.frombuffer(mm, dt, cnt, off) for f, (off, cnt, dt) in offs.items()}
+    counts = arrs["counts"].reshape(world, 2, P_all)
+    out = {f: arrs[f] for f in FIELDS}
     eng = IclEngine(local, sort_threads=sort_threads)
     host_in = {}
     for k in ("pair_id", "loc1", "loc2", "grading"):
@@ -395,20 +421,24 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
         b = eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm,
                       min_members=5, copy=False)
         t1 = time.perf_counter()
+        t_wait = 0.0
         if world > 1:
-            # host gather: every rank's blocks (pair ids and row indices mapped back to the whole comparison) -> rank 0
-            part = {f: getattr(b, f) for f in FIELDS}
-            part["pair"] = pts["global_pair"][b.pair]
-            part["member_idx"] = pts["rows"][b.member_idx].astype(np.int32)
-            np.savez(os.path.join(shm, f"part{rank}.npz"), **part)
-            barrier()
+            cb, cm = shard.pair_counts(b, pts["global_pair"], P_all)
+            counts[rank, 0], counts[rank, 1] = cb, cm
+            tw = time.perf_counter()
+            barrier()                                        # every rank's counts are in
+            t_wait = time.perf_counter() - tw
+            bb = np.r_[0, np.cumsum(counts[:, 0].sum(0))]
+            mb = np.r_[0, np.cumsum(counts[:, 1].sum(0))]
+            shard.place_blocks(b, pts["global_pair"], pts["rows"], bb, mb, out)
             if rank == 0:
-                parts = []
-                for r in range(world):
-                    with np.load(os.path.join(shm, f"part{r}.npz")) as z:
-                        parts.append(Blocks(*[z[f] for f in FIELDS]))
-                merged = shard.merge_blocks(parts)
-            barrier()
+                out["member_off"][int(bb[-1])] = int(mb[-1])
+            tw = time.perf_counter()
+            barrier()                                        # every rank's blocks are in place
+            t_wait += time.perf_counter() - tw
+            if rank == 0:
+                nb, nm = int(bb[-1]), int(mb[-1])
+                merged = Blocks(*[out[f][:(nm if f in shard.MEMBER_FIELDS else nb + 1 if f == "member_off" else nb)] for f in FIELDS])
         else:
             merged = b
         t2 = time.perf_counter()
@@ -416,7 +446,8 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
             for k, v in eng.timings().items():
                 phase.setdefault(k, []).append(v)
             phase.setdefault("chain_call_ms", []).append((t1 - t0) * 1e3)
-            phase.setdefault("gather_merge_ms", []).append((t2 - t1) * 1e3)
+            phase.setdefault("gather_merge_ms", []).append((t2 - t1 - t_wait) * 1e3)
+            phase.setdefault("wait_at_barriers_ms", []).append(t_wait * 1e3)
         return t2 - t0
 
     try:
@@ -440,13 +471,15 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     mx, mn = mx.tolist(), mn.tolist()
     T = mx[0]
     ph_max = dict(zip(keys, mx[1:-1]))
-    dev = {k: v for k, v in ph_max.items() if k not in ("chain_call_ms", "gather_merge_ms")}
+    dev = {k: v for k, v in ph_max.items() if k not in ("chain_call_ms", "gather_merge_ms", "wait_at_barriers_ms")}
     limiting = max(dev, key=dev.get) if dev else None
     return {"workload": workload_label(args.strong_workload) + f", ONE comparison, chromosome pairs LPT-sharded over {world} GPU(s)",
             "scaling": "strong", "value": total * args.steps / T, "unit": "hits/s", "ms_per_step": 1e3 * T / args.steps,
             "graded_hits": total, "chromosome_pairs": int(full["n_pairs"]), "blocks": int(len(merged)),
             "what": "end to end per step: H2D of every rank's shard from pinned host memory, sort, DP, rank, extraction, "
-                    "blocks to the host, host gather to rank 0 (/dev/shm) and merge into emission order; max over ranks",
+                    "blocks to the host, host gather: every rank writes its blocks to their place in the merged arrays "
+                    "(one memory-mapped /dev/shm region, shard.place_blocks; no collective on the data path); the step ends "
+                    "when rank 0 holds the whole comparison in emission order; max over ranks",
             "hits_per_rank": {"max": int(mx[-1]), "min": int(mn[-1])},
             "phase_ms_max_over_ranks": ph_max, "limiting_device_phase": limiting,
             "lpt_cost": "points + points^2 / 65536 per chromosome pair (shard.pair_cost)"}
@@ -741,14 +774,19 @@ def main():
             "e2e": {"value": total_points * args.steps / t_e2e, "unit": "hits/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                     "ms_per_step_cuda_events": 1e3 * ev_e2e / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": (counters["launches_dp"] + counters["launches_extract"]) * args.steps,
+            # kernels of this library launched inside the timed region, counted at every launch by the library itself
+            # (icl_counters; CUB's sort / scan kernels are library code and reported separately)
+            "gpu_launches": (counters["launches_dp"] + counters["launches_rank"] + counters["launches_extract"]) * args.steps,
+            "cub_calls": counters["cub_calls"] * args.steps,
             "host_rank_fallbacks": int(getattr(eng, "host_rank_fallbacks", 0)),
             "roofline": {"kernel": "k_chain_ring: chain DP, both directions" + (" + streamed score export" if streamed else ""),
                          "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_C2 if (args.workload == "C2" and world == 1) else None,
+                         "traffic": (NCU_TRAFFIC_C2["streamed_export" if streamed else "dp_only"]
+                                     if (args.workload == "C2" and world == 1) else None),
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_chain_ring on this "
-                                           "workload (profiles/r01_chain_ring_ncu_summary.md)",
+                                           "workload and variant (" + ("profiles/r01_chain_ring_ncu_summary.md" if streamed else
+                                                                       "profiles/r02_chain_ring_ncu_summary.md") + ")",
                          "peak_source": peak_kind,
                          "kernel_ms": chain_ms, "algorithmic_bytes": bytes_pp * n_local,
                          "bytes_per_point": bytes_pp,

@@ -47,6 +47,9 @@ def stratified_pairs(sizes, k=8, max_points=None, seed=7):
     """Largest, median, smallest and k - 3 random pairs among those with 3 <= points <= max_points."""
     sizes = np.asarray(sizes)
     ok = np.flatnonzero((sizes >= 3) & ((sizes <= max_points) if max_points else True))
+    if len(ok) < 3:                                         # nothing that small: the k smallest pairs instead
+        ok = np.flatnonzero(sizes >= 3)
+        ok = ok[np.argsort(sizes[ok], kind="stable")[:max(1, k)]]
     if len(ok) == 0:
         return []
     by = ok[np.argsort(sizes[ok], kind="stable")]
@@ -115,7 +118,7 @@ def time_sample(pts, options, k=8, max_points=None, workers=None):
     return {"pairs": [int(p) for p in pairs], "points": [int(x) for x in n], "seconds": [float(x) for x in t],
             "sample_wall_s": wall, "workers": workers, "cores": cores,
             "model": {"a_s_per_point": float(coef[0]), "b_s_per_point2": float(coef[1])},
-            "measured_points_per_s_per_core": float(n.sum() / t.sum()),
+            "measured_points_per_s_per_core": float(n.sum() / t.sum()) if t.sum() > 0 else None,
             "extrapolated_cpu_s": total_cpu, "extrapolated_wall_s_all_cores": est_wall,
             "extrapolated_points_per_s_all_cores": float(sizes.sum() / est_wall) if est_wall > 0 else None,
             "blocks": {int(p): r[1] for p, r in zip(pairs, res)}}

@@ -482,3 +482,46 @@ def test_avx2_argsort_specification_matches_numpy():
     if "SKIP" in r.stdout:
         pytest.skip("numpy on this machine has no AVX2 argsort to compare with")
     assert "BAD 0" in r.stdout, r.stdout
+
+
+def test_place_blocks_equals_merge_blocks():
+    """The parallel host gather of the strong-scaling path (every rank writes its blocks to their place in the merged arrays,
+    shard.place_blocks) gives exactly what the sequential merge (shard.merge_blocks) gives."""
+    from wgdi_b200 import shard
+    from wgdi_b200.engine import Blocks
+    rng = np.random.default_rng(4)
+    P, world = 23, 3
+    owner = rng.integers(0, world, P)
+    parts, gps, rowss = [], [], []
+    for r in range(world):
+        mine = np.flatnonzero(owner == r)
+        nbp = rng.integers(0, 6, len(mine))                       # blocks per local pair (some pairs without blocks)
+        pair = np.repeat(np.arange(len(mine)), nbp).astype(np.int32)
+        nb = len(pair)
+        m = rng.integers(3, 9, nb).astype(np.int32)
+        nm = int(m.sum())
+        rows = rng.permutation(5000)[:4000]
+        parts.append(Blocks(pair, rng.integers(0, 2, nb).astype(np.int32), rng.integers(0, 999, nb).astype(np.int64), m,
+                            m + 1, m + 2, (m + 3).astype(np.int64), m + 4, m + 5, rng.random(nb),
+                            np.r_[0, np.cumsum(m)].astype(np.int64), rng.integers(0, 99, nm).astype(np.int32),
+                            rng.integers(0, 99, nm).astype(np.int32), rng.integers(0, 4000, nm).astype(np.int32)))
+        gps.append(mine)
+        rowss.append(rows)
+    # sequential merge on globally renumbered copies
+    glob = []
+    for b, gp, rows in zip(parts, gps, rowss):
+        g = Blocks(*[getattr(b, f) for f in shard.BLOCK_FIELDS])
+        g.pair = gp[b.pair].astype(np.int32)
+        g.member_idx = rows[b.member_idx].astype(np.int32)
+        glob.append(g)
+    exp = shard.merge_blocks(glob)
+    cb = sum(shard.pair_counts(b, gp, P)[0] for b, gp in zip(parts, gps))
+    cm = sum(shard.pair_counts(b, gp, P)[1] for b, gp in zip(parts, gps))
+    bb, mb = np.r_[0, np.cumsum(cb)], np.r_[0, np.cumsum(cm)]
+    out = {f: np.zeros(int(mb[-1]) if f in shard.MEMBER_FIELDS else int(bb[-1]) + 1, getattr(exp, f).dtype) for f in shard.BLOCK_FIELDS}
+    for b, gp, rows in zip(parts, gps, rowss):
+        shard.place_blocks(b, gp, rows, bb, mb, out)
+    out["member_off"][int(bb[-1])] = int(mb[-1])
+    for f in shard.BLOCK_FIELDS:
+        n = len(getattr(exp, f))
+        assert (out[f][:n] == getattr(exp, f)).all(), f

@@ -73,6 +73,43 @@ def merge_blocks(parts):
                   cat("p_raw"), new_off, loc1[gather], loc2[gather], midx[gather])
 
 
+BLOCK_FIELDS = ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw", "member_off", "loc1", "loc2", "member_idx")
+MEMBER_FIELDS = ("loc1", "loc2", "member_idx")
+
+
+def pair_counts(blocks, global_pair, n_pairs: int):
+    """(blocks, members) per GLOBAL chromosome pair of one rank's block list."""
+    gp = np.asarray(global_pair)[blocks.pair]
+    return (np.bincount(gp, minlength=n_pairs).astype(np.int64),
+            np.bincount(gp, weights=blocks.m, minlength=n_pairs).astype(np.int64))
+
+
+def place_blocks(blocks, global_pair, rows, block_base, member_base, out: dict):
+    """Write one rank's blocks straight to their place in the merged (emission-order) arrays `out` — the parallel form of
+    `merge_blocks`: every chromosome pair is owned by one rank and a rank's blocks are pair-major already, so a pair's run
+    of blocks is contiguous on both sides; `block_base` / `member_base` = exclusive sums over the per-pair counts of ALL
+    ranks (`pair_counts`).  `rows` maps the rank's upload indices back to the whole comparison's."""
+    nb = len(blocks)
+    if nb == 0:
+        return
+    gp = np.asarray(global_pair)[blocks.pair]
+    new = np.r_[True, gp[1:] != gp[:-1]]
+    first = np.flatnonzero(new)[np.cumsum(new) - 1]            # first block of the pair's run, per block
+    dest = block_base[gp] + (np.arange(nb) - first)
+    mo = blocks.member_off
+    mdest0 = member_base[gp] + (mo[:-1] - mo[first])           # first member of every block in the merged arrays
+    for f in BLOCK_FIELDS:
+        if f in MEMBER_FIELDS or f == "member_off":
+            continue
+        out[f][dest] = gp if f == "pair" else getattr(blocks, f)
+    out["member_off"][dest] = mdest0
+    shift = np.repeat(mdest0 - mo[:-1], blocks.m)              # merged position - local position, per member
+    mdest = shift + np.arange(len(shift))
+    out["loc1"][mdest] = blocks.loc1
+    out["loc2"][mdest] = blocks.loc2
+    out["member_idx"][mdest] = np.asarray(rows)[blocks.member_idx]
+
+
 def chain_on_devices(points: dict, n_pairs: int, params, devices, min_members: int = 1):
     """One comparison over several GPUs of this host from ONE process: chromosome pairs LPT-sharded over `devices`
     (`shard_points`), one engine and one host thread per GPU (the C calls release the GIL; the sort pool serves one
