@@ -304,10 +304,11 @@ def portable_child(args):
         torch.cuda.synchronize()
         t += time.perf_counter() - t0
     # end to end: page-locked host inputs -> H2D -> ... -> blocks on the host
+    from wgdi_b200.params import compact_points
     host_in = {}
-    for k in ("pair_id", "loc1", "loc2", "grading"):
-        buf = eng._buf("in_" + k, len(pts[k]), np.int32)
-        buf[:] = pts[k]
+    for k, arr in zip(("pair_id", "loc1", "loc2", "grading"), compact_points(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"])):
+        buf = eng._buf("in_" + k, len(arr), arr.dtype)
+        buf[:] = arr
         host_in[k] = buf
     te = 0.0
     for i in range(args.steps + 2):
@@ -390,9 +391,9 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     P_all = int(full["n_pairs"])
     cap_b, cap_m = total // 5 + 64, 2 * total + 64                   # blocks of >= 5 gene pairs, both directions
     size, offs = 0, {}
-    for f in ("counts",) + FIELDS:
-        cnt = 2 * world * P_all if f == "counts" else cap_m if f in shard.MEMBER_FIELDS else cap_b + 1
-        dt = np.int64 if f == "counts" else DT[f]
+    for f in ("epoch", "counts") + FIELDS:
+        cnt = 8 * world if f == "epoch" else 2 * world * P_all if f == "counts" else cap_m if f in shard.MEMBER_FIELDS else cap_b + 1
+        dt = np.int64 if f in ("epoch", "counts") else DT[f]
         offs[f] = (size, cnt, dt)
         size += (cnt * np.dtype(dt).itemsize + 63) & ~63
     path = os.path.join(shm, "merged.bin")
@@ -403,11 +404,26 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     arrs = {f: np.frombuffer(mm, dt, cnt, off) for f, (off, cnt, dt) in offs.items()}
     counts = arrs["counts"].reshape(world, 2, P_all)
     out = {f: arrs[f] for f in FIELDS}
+    epoch = arrs["epoch"].reshape(world, 8)                       # one cache line per rank
+    my_epoch = 0
+
+    def host_barrier():
+        """The ranks of the host gather meet in shared memory (a counter per rank, one cache line each): the data path of
+        the gather has no NCCL call at all."""
+        nonlocal my_epoch
+        my_epoch += 1
+        epoch[rank, 0] = my_epoch
+        deadline = time.perf_counter() + 60.0
+        while int(epoch[:, 0].min()) < my_epoch:
+            if time.perf_counter() > deadline:
+                raise RuntimeError("strong leg: a rank did not reach the host barrier within 60 s")
+
     eng = IclEngine(local, sort_threads=sort_threads)
+    from wgdi_b200.params import compact_points
     host_in = {}
-    for k in ("pair_id", "loc1", "loc2", "grading"):
-        buf = eng._buf("in_" + k, n_local, np.int32)
-        buf[:] = pts[k]
+    for k, arr in zip(("pair_id", "loc1", "loc2", "grading"), compact_points(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"])):
+        buf = eng._buf("in_" + k, n_local, arr.dtype)
+        buf[:] = arr
         host_in[k] = buf
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     phase = {}
@@ -426,7 +442,7 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
             cb, cm = shard.pair_counts(b, pts["global_pair"], P_all)
             counts[rank, 0], counts[rank, 1] = cb, cm
             tw = time.perf_counter()
-            barrier()                                        # every rank's counts are in
+            host_barrier()                                   # every rank's counts are in
             t_wait = time.perf_counter() - tw
             bb = np.r_[0, np.cumsum(counts[:, 0].sum(0))]
             mb = np.r_[0, np.cumsum(counts[:, 1].sum(0))]
@@ -434,7 +450,7 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
             if rank == 0:
                 out["member_off"][int(bb[-1])] = int(mb[-1])
             tw = time.perf_counter()
-            barrier()                                        # every rank's blocks are in place
+            host_barrier()                                   # every rank's blocks are in place
             t_wait += time.perf_counter() - tw
             if rank == 0:
                 nb, nm = int(bb[-1]), int(mb[-1])
@@ -567,10 +583,12 @@ def main():
     sort_threads = int(os.environ.get("ICL_BENCH_SORT_THREADS", 0)) or max(1, (os.cpu_count() or 1) // world)
     eng = IclEngine(local, sort_threads=sort_threads)
     # inputs in page-locked host memory (the e2e leg copies them every step)
+    # (in the narrowest element types that hold them, as the drop-in driver hands them over: params.compact_points)
+    from wgdi_b200.params import compact_points
     host_in = {}
-    for k in ("pair_id", "loc1", "loc2", "grading"):
-        buf = eng._buf("in_" + k, n_local, np.int32)
-        buf[:] = pts[k]
+    for k, arr in zip(("pair_id", "loc1", "loc2", "grading"), compact_points(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"])):
+        buf = eng._buf("in_" + k, n_local, arr.dtype)
+        buf[:] = arr
         host_in[k] = buf
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -757,7 +775,7 @@ def main():
         # one flag per segment; with the host ranking also the score keys out (2 x 4 B per point: streamed by the DP kernel)
         # and the argsort back in (2 x 4 B per point)
         d2h = int(len(blocks) * 64 + len(blocks.loc1) * 12) + (8 * int(mine["n_pairs"]) if on_device else 8 * n_local)
-        h2d = 16 * n_local + (0 if on_device else 8 * n_local)
+        h2d = sum(int(v.nbytes) for v in host_in.values()) + (0 if on_device else 8 * n_local)
         line = {
             "metric": METRIC, "value": total_points * args.steps / t_res, "unit": "hits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,

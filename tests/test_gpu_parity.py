@@ -776,3 +776,31 @@ def test_rank_verify_switch_and_forced_hand_back(gpu_engine, monkeypatch):
             assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)
         finally:
             eng.close()
+
+
+def test_typed_upload_equals_int32_upload(gpu_engine):
+    """icl_upload_typed: the point arrays in uint8 / uint16 (what params.compact_points hands over: 7 bytes per point on
+    the wire instead of 16) give exactly the blocks of the int32 upload; mixed widths, and values that do not fit stay int32."""
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    from wgdi_b200.params import compact_points
+    pts = synth.graded_points(synth.make_dataset("small"))
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    ref = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    fields = ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off", "loc1", "loc2", "member_idx")
+    cp = compact_points(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"])
+    assert [a.dtype for a in cp] == [np.uint8, np.uint16, np.uint16, np.uint8]
+    got = gpu_engine.chain(*cp, pts["n_pairs"], prm)
+    assert gpu_engine.upload_bytes == 6 * len(pts["loc1"])
+    assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)
+    mixed = (pts["pair_id"].astype(np.uint16), pts["loc1"].astype(np.int32), pts["loc2"].astype(np.uint16), pts["grading"].astype(np.uint8))
+    got = gpu_engine.chain(*mixed, pts["n_pairs"], prm)
+    assert all((getattr(got, f) == getattr(ref, f)).all() for f in fields)
+    big = compact_points(np.array([0, 70000]), np.array([1, 2]), np.array([3, 4]), np.array([50, 300]))
+    assert [a.dtype for a in big] == [np.int32, np.uint8, np.uint8, np.uint16]
+    from wgdi_b200._lib import IclError
+    with pytest.raises(IclError) as e:
+        gpu_engine.upload(np.zeros(2, np.uint8), big[1], big[2], big[3], 1)          # grading 300 > 255
+    assert e.value.code == -4
+    assert gpu_engine.lib.icl_upload_typed(gpu_engine.ctx, 2, 1, big[1].ctypes.data, 3, big[1].ctypes.data, 1, big[2].ctypes.data, 1,
+                                           big[1].ctypes.data, 1) == -1              # element size 3

@@ -49,6 +49,7 @@ def _declare(lib):
     lib.icl_host_alloc.argtypes = [vp, i64, C.POINTER(vp)]
     lib.icl_host_free.argtypes = [vp, vp]
     lib.icl_upload.argtypes = [vp, i64, i32, vp, vp, vp, vp]
+    lib.icl_upload_typed.argtypes = [vp, i64, i32, vp, i32, vp, i32, vp, i32, vp, i32]
     lib.icl_set_grading_table.argtypes = [vp, i32, vp]
     lib.icl_dp.argtypes = [vp, C.POINTER(icl_params), vp, vp]
     lib.icl_dp_begin.argtypes = [vp, C.POINTER(icl_params), vp, vp, vp]
@@ -70,7 +71,7 @@ def _declare(lib):
 
 
 EXPORTS = ("icl_backend", "icl_create", "icl_destroy", "icl_last_error", "icl_host_alloc", "icl_host_free",
-           "icl_upload", "icl_set_grading_table", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_debug_rank_keys", "icl_debug_keys", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
+           "icl_upload", "icl_upload_typed", "icl_set_grading_table", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_debug_rank_keys", "icl_debug_keys", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
            "icl_counters", "icl_stream")
 
 

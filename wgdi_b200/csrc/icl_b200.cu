@@ -60,6 +60,7 @@ struct icl_ctx {
 
     // inputs in upload order
     Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats;
+    Buf<uint8_t> in_raw;             // icl_upload_typed: the narrow arrays as they crossed PCIe
     // sort
     Buf<uint64_t> key_a, key_b;
     Buf<uint32_t> idx_a, perm;
@@ -261,7 +262,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
 #endif
-    c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release();
+    c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release(); c->in_raw.release();
     c->key_a.release(); c->key_b.release(); c->idx_a.release(); c->perm.release(); c->tmp.release();
     c->d_pair_off.release(); c->d_rb.release(); c->d_seg_off.release(); c->d_rmin.release(); c->d_nrows.release();
     c->d_item_order.release(); c->d_pair_order.release();
@@ -322,13 +323,14 @@ extern "C" int icl_host_free(icl_ctx *c, void *ptr) {
 // ------------------------------------------------------------------------------------------------
 // ABI: upload
 // ------------------------------------------------------------------------------------------------
-extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_id, const int32_t *loc1,
-                          const int32_t *loc2, const int32_t *grading) {
-    if (!c) return ICL_ERR_ARG;
+// the four input arrays in 1-, 2- or 4-byte unsigned elements: copied as they are, widened to int32 on the device
+static int upload_typed(icl_ctx *c, int64_t n, int32_t P, const void *const src[4], const int32_t bytes[4], const char *who) {
     c->uploaded = c->dp_done = c->dp_begun = false;
-    if (n < 0 || P < 0 || (n > 0 && (!pair_id || !loc1 || !loc2 || !grading)) || (n > 0 && P == 0))
-        return fail(c, ICL_ERR_ARG, "icl_upload: bad argument");
-    if (n >= (1ll << 30)) return fail(c, ICL_ERR_LIMIT, "icl_upload: n_points must be < 2^30");
+    if (n < 0 || P < 0 || (n > 0 && (!src[0] || !src[1] || !src[2] || !src[3])) || (n > 0 && P == 0))
+        return fail(c, ICL_ERR_ARG, std::string(who) + ": bad argument");
+    for (int k = 0; k < 4; k++)
+        if (bytes[k] != 1 && bytes[k] != 2 && bytes[k] != 4) return fail(c, ICL_ERR_ARG, std::string(who) + ": element sizes must be 1, 2 or 4 bytes");
+    if (n >= (1ll << 30)) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": n_points must be < 2^30");
     Status &st = c->st;
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaSetDevice(c->device));
@@ -337,26 +339,50 @@ extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_
     c->P = P;
     if (c->in_pair.reserve(st, n) || c->in_loc1.reserve(st, n) || c->in_loc2.reserve(st, n) || c->in_grad.reserve(st, n))
         return st.code;
-    size_t b = (size_t)n * sizeof(int32_t);
-    ICL_CUDA(st, h2d(c->in_pair.p, pair_id, b, c->stream));
-    ICL_CUDA(st, h2d(c->in_loc1.p, loc1, b, c->stream));
-    ICL_CUDA(st, h2d(c->in_loc2.p, loc2, b, c->stream));
-    ICL_CUDA(st, h2d(c->in_grad.p, grading, b, c->stream));
+    int32_t *dst[4] = {c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p};
+    size_t narrow = 0;
+    for (int k = 0; k < 4; k++) if (bytes[k] != 4) narrow += ((size_t)n * bytes[k] + 15) & ~(size_t)15;
+    if (narrow && c->in_raw.reserve(st, narrow)) return st.code;
+    uint8_t *raw = c->in_raw.p;
+    for (int k = 0; k < 4; k++) {
+        if (bytes[k] == 4) { ICL_CUDA(st, h2d(dst[k], src[k], (size_t)n * 4, c->stream)); continue; }
+        ICL_CUDA(st, h2d(raw, src[k], (size_t)n * bytes[k], c->stream));
+        int32_t *o = dst[k];
+        if (bytes[k] == 1) { const uint8_t *r = raw; ICL_CUDA(st, foreach(c->stream, n, ICL_LAMBDA(int64_t i) { o[i] = r[i]; })); }
+        else { const uint16_t *r = (const uint16_t *)raw; ICL_CUDA(st, foreach(c->stream, n, ICL_LAMBDA(int64_t i) { o[i] = r[i]; })); }
+        raw += ((size_t)n * bytes[k] + 15) & ~(size_t)15;
+    }
     if (input_stats(c)) return st.code;
     int32_t hs[4] = {0, 0, 0, 0};
     ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), c->stream));
     ICL_CUDA(st, dev_sync(c->stream));
-    if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_upload: negative coordinate or pair id outside [0, n_pairs)");
-    if (hs[0] >= (1 << 26) || hs[1] >= (1 << 26)) return fail(c, ICL_ERR_LIMIT, "icl_upload: coordinates must be < 2^26");
-    if (hs[3] > 255) return fail(c, ICL_ERR_LIMIT, "icl_upload: grading values must be <= 255");
+    if (hs[2]) return fail(c, ICL_ERR_ARG, std::string(who) + ": negative coordinate or pair id outside [0, n_pairs)");
+    if (hs[0] >= (1 << 26) || hs[1] >= (1 << 26)) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": coordinates must be < 2^26");
+    if (hs[3] > 255) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": grading values must be <= 255");
     c->max_grad = hs[3];
     c->bits1 = bits_for(hs[0]);
     c->bits2 = bits_for(hs[1]);
     c->bitsp = bits_for(P > 0 ? P - 1 : 0);
-    if (c->bits1 + c->bits2 + c->bitsp > 64) return fail(c, ICL_ERR_LIMIT, "icl_upload: key does not fit 64 bits");
+    if (c->bits1 + c->bits2 + c->bitsp > 64) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": key does not fit 64 bits");
     c->uploaded = true;
     st.code = 0;
     return ICL_OK;
+}
+
+extern "C" int icl_upload(icl_ctx *c, int64_t n, int32_t P, const int32_t *pair_id, const int32_t *loc1,
+                          const int32_t *loc2, const int32_t *grading) {
+    if (!c) return ICL_ERR_ARG;
+    const void *src[4] = {pair_id, loc1, loc2, grading};
+    const int32_t bytes[4] = {4, 4, 4, 4};
+    return upload_typed(c, n, P, src, bytes, "icl_upload");
+}
+
+extern "C" int icl_upload_typed(icl_ctx *c, int64_t n, int32_t P, const void *pair_id, int32_t pair_bytes, const void *loc1,
+                                int32_t loc1_bytes, const void *loc2, int32_t loc2_bytes, const void *grading, int32_t grading_bytes) {
+    if (!c) return ICL_ERR_ARG;
+    const void *src[4] = {pair_id, loc1, loc2, grading};
+    const int32_t bytes[4] = {pair_bytes, loc1_bytes, loc2_bytes, grading_bytes};
+    return upload_typed(c, n, P, src, bytes, "icl_upload_typed");
 }
 
 // ------------------------------------------------------------------------------------------------

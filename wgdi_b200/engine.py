@@ -166,12 +166,22 @@ class IclEngine:
 
     # ---- device phases -------------------------------------------------------------------------
     def upload(self, pair_id, loc1, loc2, grading, n_pairs):
-        a = [np.ascontiguousarray(x, np.int32) for x in (pair_id, loc1, loc2, grading)]
+        """Arrays of uint8 / uint16 cross PCIe as they are (icl_upload_typed; see `compact_points`); anything else is
+        passed as int32."""
+        a = [np.ascontiguousarray(x) if np.asarray(x).dtype in (np.uint8, np.uint16) else np.ascontiguousarray(x, np.int32)
+             for x in (pair_id, loc1, loc2, grading)]
         n = len(a[0])
         if not all(len(x) == n for x in a):
             raise ValueError("pair_id, loc1, loc2, grading must have equal length")
-        self._check(self.lib.icl_upload(self.ctx, n, int(n_pairs), *[x.ctypes.data for x in a]))
+        if all(x.dtype == np.int32 for x in a):
+            self._check(self.lib.icl_upload(self.ctx, n, int(n_pairs), *[x.ctypes.data for x in a]))
+        else:
+            args = []
+            for x in a:
+                args += [x.ctypes.data, x.dtype.itemsize]
+            self._check(self.lib.icl_upload_typed(self.ctx, n, int(n_pairs), *args))
         self.n, self.n_pairs = n, int(n_pairs)
+        self.upload_bytes = sum(x.nbytes for x in a)
 
     def set_grading_table(self, values=None):
         """Sweeps over `grading`: with a table the `grading` array of `upload` holds rank-class ids (0 red, 1 blue, 2 rest,

@@ -36,3 +36,16 @@ def nargsort_desc(a: np.ndarray) -> np.ndarray:
     n = len(a)
     r = a[::-1].argsort(kind="quicksort")
     return (n - 1 - r)[::-1]
+
+
+def compact_points(pair_id, loc1, loc2, grading):
+    """The four point arrays in the narrowest unsigned dtype that holds them (uint8 / uint16, else int32): what the ingest
+    hands to `IclEngine.upload`, so that a point crosses PCIe in 7 bytes instead of 16 where gene orders and pair ids fit
+    16 bits and gradings 8 (include/icl_b200.h, icl_upload_typed).  Negative values stay int32 and are rejected by the upload."""
+    def narrow(x):
+        x = np.asarray(x)
+        if len(x) == 0 or x.min() < 0:
+            return np.ascontiguousarray(x, np.int32)
+        hi = int(x.max())
+        return np.ascontiguousarray(x, np.uint8 if hi < 256 else np.uint16 if hi < 65536 else np.int32)
+    return narrow(pair_id), narrow(loc1), narrow(loc2), narrow(grading)
