@@ -379,45 +379,18 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     owner = shard.lpt_assign(shard.pair_cost(sizes), world)
     pts = shard.shard_points(full, rank, world, owner=owner)
     n_local = len(pts["loc1"])
-    # host gather without a collective: ONE memory-mapped region in /dev/shm holds the merged block arrays (mapped by every
-    # rank once, outside the timed region).  Per step a rank publishes its per-pair block / member counts, all ranks meet at
-    # a barrier, every rank derives where each chromosome pair's run starts in the merged arrays and writes its own blocks
-    # there (shard.place_blocks: the merge is done by N ranks in parallel); after a second barrier rank 0 holds the whole
-    # comparison in the reference's emission order.
+    # host gather without a collective (shard.HostGather): one memory-mapped file in /dev/shm, mapped by every rank once,
+    # outside the timed region; per step every rank writes its blocks to their place in the merged arrays and rank 0 ends
+    # up holding the whole comparison in the reference's emission order
     shm = f"/dev/shm/icl_strong_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
     os.makedirs(shm, exist_ok=True)
-    DT = dict(pair=np.int32, dir=np.int32, score=np.int64, m=np.int32, L=np.int32, N=np.int32, N1=np.int64, L1=np.int32,
-              L2=np.int32, p_raw=np.float64, member_off=np.int64, loc1=np.int32, loc2=np.int32, member_idx=np.int32)
+    path = os.path.join(shm, "merged.bin")
     P_all = int(full["n_pairs"])
     cap_b, cap_m = total // 5 + 64, 2 * total + 64                   # blocks of >= 5 gene pairs, both directions
-    size, offs = 0, {}
-    for f in ("epoch", "counts") + FIELDS:
-        cnt = 8 * world if f == "epoch" else 2 * world * P_all if f == "counts" else cap_m if f in shard.MEMBER_FIELDS else cap_b + 1
-        dt = np.int64 if f in ("epoch", "counts") else DT[f]
-        offs[f] = (size, cnt, dt)
-        size += (cnt * np.dtype(dt).itemsize + 63) & ~63
-    path = os.path.join(shm, "merged.bin")
-    if rank == 0:
-        np.memmap(path, dtype=np.uint8, mode="w+", shape=(size,)).flush()
+    hg = shard.HostGather(path, 0, world, P_all, cap_b, cap_m, create=True) if rank == 0 else None
     barrier()
-    mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(size,))
-    arrs = {f: np.frombuffer(mm, dt, cnt, off) for f, (off, cnt, dt) in offs.items()}
-    counts = arrs["counts"].reshape(world, 2, P_all)
-    out = {f: arrs[f] for f in FIELDS}
-    epoch = arrs["epoch"].reshape(world, 8)                       # one cache line per rank
-    my_epoch = 0
-
-    def host_barrier():
-        """The ranks of the host gather meet in shared memory (a counter per rank, one cache line each): the data path of
-        the gather has no NCCL call at all."""
-        nonlocal my_epoch
-        my_epoch += 1
-        epoch[rank, 0] = my_epoch
-        deadline = time.perf_counter() + 60.0
-        while int(epoch[:, 0].min()) < my_epoch:
-            if time.perf_counter() > deadline:
-                raise RuntimeError("strong leg: a rank did not reach the host barrier within 60 s")
-
+    if rank != 0:
+        hg = shard.HostGather(path, rank, world, P_all, cap_b, cap_m, create=False)
     eng = IclEngine(local, sort_threads=sort_threads)
     from wgdi_b200.params import compact_points
     host_in = {}
@@ -437,24 +410,8 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
         b = eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm,
                       min_members=5, copy=False)
         t1 = time.perf_counter()
-        t_wait = 0.0
         if world > 1:
-            cb, cm = shard.pair_counts(b, pts["global_pair"], P_all)
-            counts[rank, 0], counts[rank, 1] = cb, cm
-            tw = time.perf_counter()
-            host_barrier()                                   # every rank's counts are in
-            t_wait = time.perf_counter() - tw
-            bb = np.r_[0, np.cumsum(counts[:, 0].sum(0))]
-            mb = np.r_[0, np.cumsum(counts[:, 1].sum(0))]
-            shard.place_blocks(b, pts["global_pair"], pts["rows"], bb, mb, out)
-            if rank == 0:
-                out["member_off"][int(bb[-1])] = int(mb[-1])
-            tw = time.perf_counter()
-            host_barrier()                                   # every rank's blocks are in place
-            t_wait += time.perf_counter() - tw
-            if rank == 0:
-                nb, nm = int(bb[-1]), int(mb[-1])
-                merged = Blocks(*[out[f][:(nm if f in shard.MEMBER_FIELDS else nb + 1 if f == "member_off" else nb)] for f in FIELDS])
+            merged = hg.gather(b, pts["global_pair"], pts["rows"])
         else:
             merged = b
         t2 = time.perf_counter()
@@ -462,8 +419,7 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
             for k, v in eng.timings().items():
                 phase.setdefault(k, []).append(v)
             phase.setdefault("chain_call_ms", []).append((t1 - t0) * 1e3)
-            phase.setdefault("gather_merge_ms", []).append((t2 - t1 - t_wait) * 1e3)
-            phase.setdefault("wait_at_barriers_ms", []).append(t_wait * 1e3)
+            phase.setdefault("gather_merge_ms", []).append((t2 - t1) * 1e3)      # incl. the wait for the slowest rank
         return t2 - t0
 
     try:
@@ -487,14 +443,14 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     mx, mn = mx.tolist(), mn.tolist()
     T = mx[0]
     ph_max = dict(zip(keys, mx[1:-1]))
-    dev = {k: v for k, v in ph_max.items() if k not in ("chain_call_ms", "gather_merge_ms", "wait_at_barriers_ms")}
+    dev = {k: v for k, v in ph_max.items() if k not in ("chain_call_ms", "gather_merge_ms")}
     limiting = max(dev, key=dev.get) if dev else None
     return {"workload": workload_label(args.strong_workload) + f", ONE comparison, chromosome pairs LPT-sharded over {world} GPU(s)",
             "scaling": "strong", "value": total * args.steps / T, "unit": "hits/s", "ms_per_step": 1e3 * T / args.steps,
             "graded_hits": total, "chromosome_pairs": int(full["n_pairs"]), "blocks": int(len(merged)),
             "what": "end to end per step: H2D of every rank's shard from pinned host memory, sort, DP, rank, extraction, "
                     "blocks to the host, host gather: every rank writes its blocks to their place in the merged arrays "
-                    "(one memory-mapped /dev/shm region, shard.place_blocks; no collective on the data path); the step ends "
+                    "(one memory-mapped /dev/shm file, shard.HostGather; no collective on the data path); the step ends "
                     "when rank 0 holds the whole comparison in emission order; max over ranks",
             "hits_per_rank": {"max": int(mx[-1]), "min": int(mn[-1])},
             "phase_ms_max_over_ranks": ph_max, "limiting_device_phase": limiting,

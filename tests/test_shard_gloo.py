@@ -15,7 +15,7 @@ def _worker(rank, world, port, emu_path, out_path):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     from wgdi_b200 import _lib, shard, synth
-    from wgdi_b200.engine import ChainParams, IclEngine
+    from wgdi_b200.engine import Blocks, ChainParams, IclEngine
     _lib._LIB = _lib._declare(ctypes.CDLL(emu_path))            # fake backend injected by the test
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pts = synth.graded_points(synth.make_dataset("tiny"))
@@ -24,12 +24,25 @@ def _worker(rank, world, port, emu_path, out_path):
     eng = IclEngine(0, sort_threads=1)
     b = eng.chain(sp["pair_id"], sp["loc1"], sp["loc2"], sp["grading"], sp["n_pairs"], prm)
     eng.close()
+    # the strong-scaling gather of bench.py: every rank places its blocks in the merged arrays of one memory-mapped file
+    # (shard.HostGather; its barriers are counters in that file, not collectives), twice to exercise the barrier epochs
+    P = pts["n_pairs"]
+    path = out_path + ".gather"
+    hg = shard.HostGather(path, 0, world, P, 4000, 40000, create=True, timeout_s=120) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        hg = shard.HostGather(path, rank, world, P, 4000, 40000, create=False, timeout_s=120)
+    local = Blocks(*[getattr(b, f).copy() for f in shard.BLOCK_FIELDS])
+    for _ in range(2):
+        placed = hg.gather(local, sp["global_pair"], sp["rows"])
     b.pair = sp["global_pair"][b.pair]
     b.member_idx = sp["rows"][b.member_idx].astype(np.int32)
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(b, gathered, dst=0)                       # host-side gather: no data-path collective on GPUs
     if rank == 0:
         merged = shard.merge_blocks(gathered)
+        for f in shard.BLOCK_FIELDS:
+            assert (getattr(placed, f) == getattr(merged, f)).all(), f     # parallel placement == sequential merge
         np.savez(out_path, pair=merged.pair, dir=merged.dir, score=merged.score, m=merged.m, p_raw=merged.p_raw,
                  member_off=merged.member_off, loc1=merged.loc1, loc2=merged.loc2, member_idx=merged.member_idx)
     dist.barrier()

@@ -110,6 +110,71 @@ def place_blocks(blocks, global_pair, rows, block_base, member_base, out: dict):
     out["member_idx"][mdest] = np.asarray(rows)[blocks.member_idx]
 
 
+class HostGather:
+    """Gather of the per-rank block lists of ONE comparison on the host, between processes of one node, without a
+    collective: one memory-mapped file (put it in /dev/shm) holds the merged block arrays, the per-rank per-pair counts and
+    a barrier word per rank.  Per gather: every rank publishes how many blocks / members each of its chromosome pairs has,
+    the ranks meet (`barrier`), every rank derives where each pair's run starts in the merged arrays and writes its own
+    blocks there (`place_blocks` — the merge is done by all ranks in parallel), the ranks meet again and rank 0 reads the
+    whole comparison in the reference's emission order as views of the file.  The reference's analogue is the parent
+    process concatenating the workers' texts in chunk order (wgdi/run_colliearity.py:133-141)."""
+
+    DT = dict(pair=np.int32, dir=np.int32, score=np.int64, m=np.int32, L=np.int32, N=np.int32, N1=np.int64, L1=np.int32,
+              L2=np.int32, p_raw=np.float64, member_off=np.int64, loc1=np.int32, loc2=np.int32, member_idx=np.int32)
+
+    def __init__(self, path: str, rank: int, world: int, n_pairs: int, cap_blocks: int, cap_members: int, create: bool,
+                 timeout_s: float = 60.0):
+        """`create`: this rank makes the (zero-filled) file — call it on one rank, then let the others map it (any
+        start-up barrier of the launcher in between)."""
+        self.rank, self.world, self.n_pairs, self.timeout_s = int(rank), int(world), int(n_pairs), float(timeout_s)
+        size, offs = 0, {}
+        for f in ("epoch", "counts") + BLOCK_FIELDS:
+            cnt = (8 * world if f == "epoch" else 2 * world * n_pairs if f == "counts" else
+                   cap_members if f in MEMBER_FIELDS else cap_blocks + 1)
+            dt = np.int64 if f in ("epoch", "counts") else self.DT[f]
+            offs[f] = (size, cnt, dt)
+            size += (cnt * np.dtype(dt).itemsize + 63) & ~63
+        self.cap_blocks, self.cap_members = int(cap_blocks), int(cap_members)
+        self.mm = np.memmap(path, dtype=np.uint8, mode="w+" if create else "r+", shape=(size,))
+        arrs = {f: np.frombuffer(self.mm, dt, cnt, off) for f, (off, cnt, dt) in offs.items()}
+        self.counts = arrs["counts"].reshape(world, 2, n_pairs)
+        self.epoch = arrs["epoch"].reshape(world, 8)             # one cache line per rank
+        self.out = {f: arrs[f] for f in BLOCK_FIELDS}
+        self._epoch = 0
+
+    def barrier(self):
+        """The ranks meet in shared memory: a counter per rank (x86: stores are seen in program order, so whatever a rank
+        wrote before raising its counter is visible to a rank that has seen the counter)."""
+        import time
+        self._epoch += 1
+        self.epoch[self.rank, 0] = self._epoch
+        deadline = time.perf_counter() + self.timeout_s
+        while int(self.epoch[:, 0].min()) < self._epoch:
+            if time.perf_counter() > deadline:
+                raise RuntimeError(f"HostGather: a rank did not reach the barrier within {self.timeout_s} s")
+
+    def gather(self, blocks, global_pair, rows):
+        """Collective over the ranks of the file.  blocks: this rank's `Blocks` (pair ids local to its shard);
+        global_pair / rows: the shard's maps back to the whole comparison (`shard_points`).  Returns the merged `Blocks`
+        (views of the file, valid until the next gather) on rank 0, None elsewhere."""
+        from .engine import Blocks
+        cb, cm = pair_counts(blocks, global_pair, self.n_pairs)
+        self.counts[self.rank, 0], self.counts[self.rank, 1] = cb, cm
+        self.barrier()                                           # every rank's counts are in
+        bb = np.r_[0, np.cumsum(self.counts[:, 0].sum(0))]
+        mb = np.r_[0, np.cumsum(self.counts[:, 1].sum(0))]
+        nb, nm = int(bb[-1]), int(mb[-1])
+        if nb > self.cap_blocks or nm > self.cap_members:
+            raise ValueError("HostGather: the merged block list does not fit the capacity the file was created with")
+        place_blocks(blocks, global_pair, rows, bb, mb, self.out)
+        if self.rank == 0:
+            self.out["member_off"][nb] = nm
+        self.barrier()                                           # every rank's blocks are in place
+        if self.rank != 0:
+            return None
+        return Blocks(*[self.out[f][:(nm if f in MEMBER_FIELDS else nb + 1 if f == "member_off" else nb)] for f in BLOCK_FIELDS])
+
+
 def chain_on_devices(points: dict, n_pairs: int, params, devices, min_members: int = 1):
     """One comparison over several GPUs of this host from ONE process: chromosome pairs LPT-sharded over `devices`
     (`shard_points`), one engine and one host thread per GPU (the C calls release the GIL; the sort pool serves one
