@@ -469,7 +469,7 @@ def main():
     ap.add_argument("--no-reference-sample", action="store_true", help="skip the timed sample of the real reference (oracle/_ref)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg")
     ap.add_argument("--strong-workload", default="C4", help="ONE comparison sharded over all ranks (strong scaling leg)")
-    ap.add_argument("--batch", type=int, default=8, help="comparisons in the pipelined-batch leg (0 = skip)")
+    ap.add_argument("--batch", type=int, default=12, help="comparisons in the pipelined-batch leg (0 = skip)")
     ap.add_argument("--portable-child", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--portable-check", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--seed-shift", type=int, default=0, help=argparse.SUPPRESS)
@@ -685,10 +685,11 @@ def main():
     batch = None
     if args.batch > 0:
         from wgdi_b200.batch import BatchRunner
-        runner = BatchRunner(local, depth=2, sort_threads=sort_threads)
+        depth = int(os.environ.get("ICL_BENCH_BATCH_DEPTH", "4"))
+        runner = BatchRunner(local, depth=depth, sort_threads=sort_threads)
         try:
             jobs = [(dict(host_in, n_pairs=pts["n_pairs"]), prm) for _ in range(args.batch)]   # page-locked inputs, as in the e2e leg
-            runner.run(jobs[:2], min_members=5, consume=lambda i, b: len(b))   # warm-up: buffers, sort pool
+            runner.run(jobs[:2 * depth], min_members=5, consume=lambda i, b: len(b))   # warm-up: buffers, sort pool
             barrier()
             t0 = time.perf_counter()
             outs = runner.run(jobs, min_members=5, consume=lambda i, b: len(b))     # blocks handed over as views, like the file writer takes them
@@ -702,8 +703,8 @@ def main():
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
             t_batch = float(tb.item())
         batch = {"value": total_points * args.batch / t_batch, "unit": "hits/s", "comparisons": args.batch * world,
-                 "ms_per_comparison": 1e3 * t_batch / args.batch, "engines_per_gpu": 2,
-                 "what": "independent comparisons pipelined through two engines per GPU, each job uploads its points"}
+                 "ms_per_comparison": 1e3 * t_batch / args.batch, "engines_per_gpu": depth,
+                 "what": f"independent comparisons pipelined through {depth} engines per GPU, each job uploads its points"}
     strong = None
     if not args.no_strong:
         strong = strong_leg(args, rank, world, local, barrier, sort_threads)

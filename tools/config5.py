@@ -50,7 +50,7 @@ def main():
     lock = threading.Lock()
 
     def on_gpu(gi):
-        runner = BatchRunner(gpus[gi], depth=2, sort_threads=max(1, (os.cpu_count() or 1) // len(gpus)))
+        runner = BatchRunner(gpus[gi], depth=4, sort_threads=max(1, (os.cpu_count() or 1) // len(gpus)))
         try:
             mine = [c for c in np.argsort(-np.asarray(n_hits)) if owner[c] == gi]
             jobs, keys = [], []

@@ -26,7 +26,7 @@ from .engine import ChainParams, IclEngine
 
 
 class BatchRunner:
-    def __init__(self, device: int = 0, depth: int = 2, sort_threads: int | None = None):
+    def __init__(self, device: int = 0, depth: int = 4, sort_threads: int | None = None):
         self.engines = [IclEngine(device, sort_threads) for _ in range(max(1, int(depth)))]
 
     def close(self):
