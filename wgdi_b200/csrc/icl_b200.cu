@@ -780,7 +780,9 @@ __global__ void __launch_bounds__(256, 4) k_edges_enum(EdgeEnum ee, int64_t V, E
 
 // every tile's run of records from where it landed in the staging pool to its place in the source-ordered stream
 __global__ void __launch_bounds__(256) k_edges_place(uint32_t tiles, const uint32_t *tile_cnt, const uint32_t *tile_at,
-                                                     const uint32_t *tile_dst, const uint2 *staging, uint2 *edges) {
+                                                     const uint32_t *tile_dst, const uint2 *staging, uint2 *edges,
+                                                     const unsigned long long *cursor, uint64_t cap) {
+    if (*cursor > cap) return;                                 // the staging pool overflowed: the caller repeats the enumeration
     for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const uint32_t n = tile_cnt[t];
         const uint2 *src = staging + tile_at[t];
@@ -820,6 +822,23 @@ static int phase_edges(icl_ctx *c) {
             k_edges_enum<<<tiles, 256, 0, s>>>(ee, V, es, stats);
             ICL_COUNT_KERNEL();
             ICL_CUDA(st, cudaGetLastError());
+            if (exclusive_sum_u32(st, c->tmp, tile_cnt, c->tile_dst.p, tiles, s)) return st.code;
+            const uint32_t *tile_dst = c->tile_dst.p;
+            // (a pool that turned out too small holds nothing beyond its end: the placement is skipped on the device and the
+            // whole enumeration repeated below; total and window span are read once, behind everything)
+            k_edges_place<<<std::min<unsigned>(tiles, 148 * 8), 256, 0, s>>>(tiles, tile_cnt, tile_at, tile_dst, c->edge_stage.p, c->edges.p, cursor, want);
+            ICL_COUNT_KERNEL();
+            ICL_CUDA(st, cudaGetLastError());
+            {
+                // record index at the first point of every item (the DP kernel reads eoff[item start] and eoff[next start])
+                uint32_t *eoff = c->eoff.p;
+                const int64_t *seg_off = c->d_seg_off.p;
+                ICL_CUDA(st, foreach(s, 2 * (int64_t)P + 1, ICL_LAMBDA(int64_t it) {
+                    if (it == 2 * (int64_t)P) { eoff[V] = tile_dst[tiles]; return; }
+                    const int64_t a = seg_off[it];
+                    if (seg_off[it + 1] > a) eoff[a] = tile_dst[a >> 8] + first_local[it];
+                }));
+            }
             ICL_CUDA(st, d2h(&total, cursor, sizeof(uint64_t), s));
             ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
             ICL_CUDA(st, dev_sync(s));
@@ -827,21 +846,6 @@ static int phase_edges(icl_ctx *c) {
             want = total + total / 8 + 4096;                   // enumerate again into pools that hold everything
         }
         if (total >= (1ull << 32)) return fail(c, ICL_ERR_LIMIT, "icl_dp: more than 2^32 candidate records");
-        if (exclusive_sum_u32(st, c->tmp, tile_cnt, c->tile_dst.p, tiles, s)) return st.code;
-        const uint32_t *tile_dst = c->tile_dst.p;
-        k_edges_place<<<std::min<unsigned>(tiles, 148 * 8), 256, 0, s>>>(tiles, tile_cnt, tile_at, tile_dst, c->edge_stage.p, c->edges.p);
-        ICL_COUNT_KERNEL();
-        ICL_CUDA(st, cudaGetLastError());
-        {
-            // record index at the first point of every item (the DP kernel reads eoff[item start] and eoff[next start])
-            uint32_t *eoff = c->eoff.p;
-            const int64_t *seg_off = c->d_seg_off.p;
-            ICL_CUDA(st, foreach(s, 2 * (int64_t)P + 1, ICL_LAMBDA(int64_t it) {
-                if (it == 2 * (int64_t)P) { eoff[V] = tile_dst[tiles]; return; }
-                const int64_t a = seg_off[it];
-                if (seg_off[it + 1] > a) eoff[a] = tile_dst[a >> 8] + first_local[it];
-            }));
-        }
     }
     c->n_edges = (int64_t)total;
     c->max_span = span;
