@@ -1857,9 +1857,11 @@ static int phase_extract(icl_ctx *c) {
         c->big_trees.reserve(st, V / ICL_TREE_SMALL + 2) || c->small_trees.reserve(st, V + 2))
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
-    ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
-    ICL_CUDA(st, dev_memset(c->hint.p, 0xFF, (size_t)V * sizeof(int2), s));
-    ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));      // drop usedtimes < 1 (:50 / :61)
+    if (!c->order_on_device_used) {                            // (a device order initialises these in its key pass below)
+        ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
+        ICL_CUDA(st, dev_memset(c->hint.p, 0xFF, (size_t)V * sizeof(int2), s));
+        ICL_CUDA(st, d2d(c->present.p, c->used.p, (size_t)V, s));  // drop usedtimes < 1 (:50 / :61)
+    }
     const int2 *pd = c->pd.p;
     const int32_t *root = c->root.p, *rank2v = c->rank2v.p;
     const uint8_t *used = c->used.p;
@@ -1872,11 +1874,29 @@ static int phase_extract(icl_ctx *c) {
         uint32_t *idx = c->idx_a.p;
         uint8_t *seen = c->seen.p;
         if (c->order_on_device_used) {
-            // the order comes from the device's own sort: a permutation by construction, nothing to validate
+            // the order comes from the device's own sort: a permutation by construction, nothing to validate.  One pass:
+            // the point examined at rank position t (undoing pandas' two reversals), its tree key, and the initial state
+            // of the walk (present = used: :50 / :61 drop usedtimes < 1)
+            const int32_t *itemof = c->itemof.p, *mmap = c->mmap.p, *ord = c->order_in.p;
+            const int64_t *off = c->d_pair_off.p;
+            int32_t *r2v = c->rank2v.p;
+            uint32_t *acc_m = c->acc_m.p;
+            int2 *hint = c->hint.p;
+            uint8_t *present = c->present.p;
             ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+                const int32_t it = itemof[t];
+                const bool rev = it >= P;
+                const int64_t a = off[rev ? it - P : it], np_ = off[(rev ? it - P : it) + 1] - a;
+                const int64_t r = t - (rev ? n : 0) - a;           // rank position inside the item
+                const int32_t rf = ord[(rev ? n : 0) + a + (np_ - 1 - r)];
+                const int64_t f = a + (np_ - 1 - rf);              // forward sorted position of the point
+                const int32_t v = rev ? mmap[f] : (int32_t)f;
+                r2v[t] = v;
                 idx[t] = (uint32_t)t;
-                const int32_t v = rank2v[t];
                 key[t] = used[v] ? (uint32_t)root[v] : (uint32_t)V;
+                acc_m[t] = 0u;
+                hint[t] = make_int2(-1, -1);
+                present[t] = used[t];
             }));
         } else {
             ICL_CUDA(st, dev_memset(c->seen.p, 0, (size_t)V, s));
@@ -1962,7 +1982,8 @@ static int phase_extract(icl_ctx *c) {
     const int64_t NB = c->NB;
     if (c->members.reserve(st, c->NM) || c->b_top.reserve(st, NB) || c->b_m.reserve(st, NB) || c->b_L.reserve(st, NB) ||
         c->b_moff.reserve(st, NB + 1) || c->b_j0.reserve(st, NB) || c->b_j1.reserve(st, NB) || c->b_l2min.reserve(st, NB) ||
-        c->b_l2max.reserve(st, NB) || c->b_L1.reserve(st, NB) || c->b_item.reserve(st, NB))
+        c->b_l2max.reserve(st, NB) || c->b_L1.reserve(st, NB) || c->b_item.reserve(st, NB) || c->b_N.reserve(st, NB) ||
+        c->b_N1.reserve(st, NB))
         return st.code;
     {
         // one thread per accepted block: members by loc1 ascending (:140), row slice of the bounding box
@@ -1972,7 +1993,8 @@ static int phase_extract(icl_ctx *c) {
         const int32_t *rmin = c->d_rmin.p;
         const int64_t *rb_ = c->d_rb.p;
         const int32_t *itemof_pos = c->itemof.p;       // item of a V position == item of the point stored there
-        int32_t *members = c->members.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_j0 = c->b_j0.p;
+        int32_t *members = c->members.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_j0 = c->b_j0.p, *b_N = c->b_N.p;
+        int64_t *b_N1 = c->b_N1.p;
         int32_t *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_L1 = c->b_L1.p, *b_item = c->b_item.p;
         uint32_t *b_moff = c->b_moff.p;
         ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
@@ -1986,6 +2008,8 @@ static int phase_extract(icl_ctx *c) {
             else for (uint32_t k = 0; k < m; k++) members[mo + k] = mscr[ms + m - 1 - k];
             const int4 box = acc_box[t];
             b_top[b] = rank2v[t];
+            b_N[b] = 0;                                                         // (the p-value pass adds into these)
+            b_N1[b] = 0;
             b_m[b] = (int32_t)m;
             b_L[b] = acc_L[t];
             b_moff[b] = mo;
@@ -2279,8 +2303,6 @@ static int phase_pvalue(icl_ctx *c) {
 #ifndef ICL_EMU
     int64_t maxnp = 1;
     for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
-    ICL_CUDA(st, dev_memset(c->b_N.p, 0, (size_t)NB * sizeof(int32_t), s));
-    ICL_CUDA(st, dev_memset(c->b_N1.p, 0, (size_t)NB * sizeof(int64_t), s));
     if (c->pvalue_mode == 3) {                                 // the one-warp-per-pair kernel (A/B, env ICL_B200_PVALUE=warp)
         // shared memory per CTA: uint16 times for up to smem_cap points (+ int32 loc2 for up to l2_cap points)
         A.smem_cap = (int32_t)std::min<int64_t>(maxnp, 100 * 1024);
@@ -3846,12 +3868,12 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
             ICL_CUDA(st, h2d(c->order_in.p, argsort_fwd, (size_t)n * sizeof(int32_t), s));
             ICL_CUDA(st, h2d(c->order_in.p + n, argsort_rev, (size_t)n * sizeof(int32_t), s));
         }
-        // rank2v[V position] = point examined at that rank position of its item
+        // rank2v[V position] = point examined at that rank position of its item (a device order: in phase_extract's key pass)
         const int32_t *ps = c->pair_s.p, *mmap = c->mmap.p, *ord = c->order_in.p;
         const int64_t *off = c->d_pair_off.p;
         int32_t *rank2v = c->rank2v.p;
-        ICL_CUDA(st, dev_memset(c->rank2v.p, 0xFF, (size_t)V * sizeof(int32_t), s));
-        ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
+        if (!dev_order) ICL_CUDA(st, dev_memset(c->rank2v.p, 0xFF, (size_t)V * sizeof(int32_t), s));
+        if (!dev_order) ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
             int32_t p = ps[i];
             int64_t a = off[p], np_ = off[p + 1] - a, j = i - a;
             int32_t rf = ord[i], rr = ord[n + i];
