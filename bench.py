@@ -499,6 +499,8 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    from wgdi_b200 import shard
+    bound_cpus = shard.bind_to_gpu_node(local) if world > 1 else None   # before any page-locked allocation
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -775,6 +777,7 @@ def main():
             "avx2_numpy": avx2_leg,
             "edges_per_step": counters["edges"], "max_span": counters["max_span"], "chain_kernel": counters["chain_kernel"],
             "clocks": clocks,
+            "cpu_binding": ("rank 0 bound to the CPUs next to its GPU: " + ",".join(map(str, bound_cpus))) if bound_cpus else "none",
         }
         blocks_copy = None
         if world == 1 and not args.no_cpu_baseline and not args.no_reference_sample:

@@ -14,14 +14,17 @@
  *
  * Call sequence (one icl_ctx per GPU; a ctx is not thread-safe):
  *
- *   icl_create -> icl_upload -> icl_dp -> [host: numpy.argsort of every pair segment] -> icl_extract
- *              -> icl_free_blocks ... -> icl_destroy
+ *   icl_create -> icl_upload -> icl_dp -> rank -> icl_extract -> icl_free_blocks ... -> icl_destroy
+ *
+ * where `rank` is either icl_rank_device (the order is computed on the device and never leaves it) or the host:
+ * numpy.argsort of every pair segment of the scores icl_dp returned, handed to icl_extract.
  *
  * The split into icl_dp / icl_extract exists because the reference orders block extraction with
  * pandas' sort_values(by=['score1'], ascending=False) (wgdi/collinearity.py:49,60), i.e. numpy's
  * UNSTABLE argsort(kind='quicksort') whose tie permutation depends on the numpy build and the CPU
- * (SURVEY.md hazard H1).  Bit-exact output therefore needs that very numpy call between the two
- * device phases; the library never sorts scores itself.
+ * (SURVEY.md hazard H1).  Bit-exact output therefore needs that very permutation between the two
+ * device phases: from numpy itself on the host, or from icl_rank_device, which reproduces numpy's three
+ * argsort flavours exactly (the caller checks which one its numpy runs; wgdi_b200/engine.py does).
  *
  * All functions return ICL_OK (0) or a negative error code; icl_last_error() gives the message.
  * No exceptions cross the boundary.  Host input arrays are caller-owned and only read during the
@@ -100,8 +103,10 @@ int icl_host_free(icl_ctx *ctx, void *ptr);
  * (loc1, loc2) with a stable radix sort, i.e. equal coordinates keep upload order like the stable
  * lexsort of wgdi/run_colliearity.py:164-166.
  * Limits: 0 <= loc < 2^26, grading <= 255, n_points < 2^30, fewer than 2^24 points per pair,
- * bits(n_pairs) + bits(max loc1) + bits(max loc2) <= 64; icl_dp additionally requires that no window of
- * mg1 consecutive rows of a pair holds more than 65535 points.
+ * bits(n_pairs) + bits(max loc1) + bits(max loc2) <= 64, sum over pairs of (loc1 range + 1) < 2^30 (all checked
+ * here: ICL_ERR_LIMIT); icl_dp additionally requires that no window of mg1 consecutive rows of a pair holds more
+ * than 65535 points.  The call also fixes the layout of the comparison (points and loc1 range of every pair, counted
+ * on the device while the arrays are validated), so icl_dp needs no host round trip for it.
  */
 int icl_upload(icl_ctx *ctx, int64_t n_points, int32_t n_pairs,
                const int32_t *pair_id, const int32_t *loc1, const int32_t *loc2, const int32_t *grading);

@@ -59,7 +59,7 @@ struct icl_ctx {
     GradeTable gtab{};               // icl_set_grading_table: uploaded values are class ids, G = table[class]
 
     // inputs in upload order
-    Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats;
+    Buf<int32_t> in_pair, in_loc1, in_loc2, in_grad, stats, pair_hist;
     Buf<uint8_t> in_raw;             // icl_upload_typed: the narrow arrays as they crossed PCIe
     // sort
     Buf<uint64_t> key_a, key_b;
@@ -102,21 +102,23 @@ struct icl_ctx {
     Buf<int32_t> host_flag;          // AVX-512 argsort kernel: segments that must be ranked on the host
     Buf<uint32_t> xs_chunk;          // ... per-chunk stop counts of very long std::sort ranges
     // extraction
-    Buf<int32_t> order_in, rank2v, acc_L, members, times, mscr;
-    Buf<uint32_t> tree_v, acc_m, acc_ms, acc_flag, blkidx, moff;
+    Buf<int32_t> order_in, rank2v, acc_L, times, mscr;
+    Buf<uint32_t> tree_v, acc_m, acc_ms;
+    Buf<Tri> tri_in, tri;            // per emission position: {accepted, wanted, members of wanted} and their exclusive sums
     Buf<int4> acc_box;               // per accepted rank position: {loc1 min, loc1 max, loc2 min, loc2 max}
     Buf<uint8_t> seen;
     Buf<uint8_t> present;
     Buf<int2> hint;                  // per point: {depth of the nearest removed ancestor, tree version} memo
     Buf<int2> big_trees;             // [t0, uend) of the trees that go to the staged walk
     Buf<int2> small_trees;           // ... and of the short ones (one thread each)
-    int64_t NB = 0, NM = 0;
-    Buf<int32_t> b_top, b_m, b_L, b_j0, b_j1, b_l2min, b_l2max, b_L1, b_item, b_N;
-    Buf<uint32_t> b_moff;
+    int64_t NB = 0, NBo = 0, NMo = 0;   // accepted blocks; blocks / gene pairs the caller gets (m >= min_members)
+    int32_t min_members = 1;
+    Buf<int32_t> b_j0, b_j1, b_l2min, b_l2max, b_N;    // per accepted block, emission order: what the times / p-value pass needs
     Buf<int64_t> b_N1;
-    Buf<double> b_a;
-    // output selection + staging
-    Buf<uint32_t> o_flag, o_bidx, o_mcnt, o_moff, o_src, o_mout, o_moff2;
+    // output staging (blocks the caller gets, emission order)
+    Buf<uint32_t> o_src, o_ms;       // accepted-block index and member scratch slice of every output block
+    icl_blocks dv{}, hv{};           // views into d_stage and into the pinned host staging (same layout)
+    size_t stage_members_at = 0, stage_bytes = 0;
     Buf<uint8_t> d_stage;
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0;
@@ -161,11 +163,22 @@ static int bits_for(int64_t maxval) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// input statistics (max loc1 / loc2, validity) — one warp-reduced atomic per warp
+// input statistics (max loc1 / loc2, validity) — one warp-reduced atomic per warp — and, per chromosome pair, the
+// number of points and the loc1 range: the layout of a comparison (pair offsets, dense row index, item order) is known
+// when icl_upload returns, so icl_dp never has to come back to the host for it
 // ------------------------------------------------------------------------------------------------
+#define ICL_HIST_SMEM_PAIRS 2048     // pairs whose three counters fit a CTA's shared memory
 #ifndef ICL_EMU
 __global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const int32_t *pair, const int32_t *l1,
-                                                     const int32_t *l2, const int32_t *gr, int32_t *stats) {
+                                                     const int32_t *l2, const int32_t *gr, int32_t *stats, int32_t *hist) {
+    // hist: [P] points, [P] smallest loc1, [P] largest loc1
+    __shared__ int32_t sh[3 * ICL_HIST_SMEM_PAIRS];
+    const bool staged = P <= ICL_HIST_SMEM_PAIRS;
+    if (staged) {
+        for (int32_t j = threadIdx.x; j < P; j += blockDim.x) { sh[j] = 0; sh[P + j] = 0x7fffffff; sh[2 * P + j] = -1; }
+        __syncthreads();
+    }
+    int32_t *cnt = staged ? sh : hist, *lo = cnt + P, *hi = lo + P;
     int32_t m1 = 0, m2 = 0, mg = 0, bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int32_t a = l1[i], b = l2[i], p = pair[i];
@@ -173,6 +186,16 @@ __global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const
         m1 = max(m1, a);
         m2 = max(m2, b);
         mg = max(mg, gr[i]);
+        if (p >= 0 && p < P) {
+            atomicAdd(&cnt[p], 1);
+            if (a < lo[p]) atomicMin(&lo[p], a);              // (the unsynchronised test only skips atomics that cannot change anything)
+            if (a > hi[p]) atomicMax(&hi[p], a);
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (int32_t j = threadIdx.x; j < P; j += blockDim.x)
+            if (sh[j]) { atomicAdd(&hist[j], sh[j]); atomicMin(&hist[P + j], sh[P + j]); atomicMax(&hist[2 * P + j], sh[2 * P + j]); }
     }
     m1 = __reduce_max_sync(0xffffffffu, m1);
     m2 = __reduce_max_sync(0xffffffffu, m2);
@@ -189,23 +212,85 @@ __global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const
 
 static int input_stats(icl_ctx *c) {
     Status &st = c->st;
+    const int32_t P = c->P;
+    if (c->pair_hist.reserve(st, 3 * (size_t)P + 1)) return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), c->stream));
+    {
+        int32_t *hist = c->pair_hist.p;
+        ICL_CUDA(st, foreach(c->stream, 3 * (int64_t)P, ICL_LAMBDA(int64_t j) { hist[j] = j < P ? 0 : j < 2 * (int64_t)P ? 0x7fffffff : -1; }));
+    }
 #ifndef ICL_EMU
     if (c->n > 0) {
         int64_t blocks = std::min<int64_t>((c->n + 255) / 256, 148 * 8);
-        k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, c->P, c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p, c->stats.p);
+        k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, P, c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p, c->stats.p,
+                                                                c->pair_hist.p);
         ICL_COUNT_KERNEL();
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
     for (int64_t i = 0; i < c->n; i++) {
         int32_t a = c->in_loc1.p[i], b = c->in_loc2.p[i], p = c->in_pair.p[i];
-        if (a < 0 || b < 0 || p < 0 || p >= c->P) c->stats.p[2] = 1;
+        if (a < 0 || b < 0 || p < 0 || p >= P) c->stats.p[2] = 1;
         c->stats.p[0] = std::max(c->stats.p[0], a);
         c->stats.p[1] = std::max(c->stats.p[1], b);
         c->stats.p[3] = std::max(c->stats.p[3], c->in_grad.p[i]);
+        if (p >= 0 && p < P) {
+            int32_t *h = c->pair_hist.p;
+            h[p]++;
+            h[P + p] = std::min(h[P + p], a);
+            h[2 * P + p] = std::max(h[2 * P + p], a);
+        }
     }
 #endif
+    return 0;
+}
+
+// The layout of the uploaded comparison, from the per-pair counts of input_stats: where every pair's points will stand
+// after the sort, its dense row range, the longest-processing-time order of pairs / (pair, direction) items.
+static int plan_layout(icl_ctx *c, const std::vector<int32_t> &hist, const char *who) {
+    Status &st = c->st;
+    const int64_t n = c->n;
+    const int32_t P = c->P;
+    cudaStream_t s = c->stream;
+    c->h_pair_off.assign(P + 1, 0);
+    c->h_rmin.assign(P + 1, 0);
+    c->h_nrows.assign(P + 1, 0);
+    for (int32_t p = 0; p < P; p++) {
+        c->h_pair_off[p + 1] = c->h_pair_off[p] + hist[p];
+        if (hist[p] > 0) { c->h_rmin[p] = hist[P + p]; c->h_nrows[p] = hist[2 * P + p] - hist[P + p] + 1; }
+    }
+    // dense row index: nrows[p] + 1 slots per pair
+    c->h_rb.assign(P + 1, 0);
+    for (int32_t p = 0; p < P; p++) c->h_rb[p + 1] = c->h_rb[p] + c->h_nrows[p] + 1;
+    c->R = c->h_rb[P];
+    for (int32_t p = 0; p < P; p++)
+        if (hist[p] >= (1 << 24)) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": a chromosome pair must hold fewer than 2^24 points");
+    if (2 * c->R >= (1ll << 31)) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": dense row index too large (sparse gene orders?)");
+    c->h_pair_order.resize(P);
+    std::iota(c->h_pair_order.begin(), c->h_pair_order.end(), 0);
+    const std::vector<int64_t> &po = c->h_pair_off;
+    std::stable_sort(c->h_pair_order.begin(), c->h_pair_order.end(),
+                     [&](int32_t a, int32_t b) { return po[a + 1] - po[a] > po[b + 1] - po[b]; });
+    c->h_item_order.resize(2 * (size_t)P);
+    for (int32_t j = 0; j < P; j++) {
+        c->h_item_order[2 * j] = c->h_pair_order[j];
+        c->h_item_order[2 * j + 1] = P + c->h_pair_order[j];
+    }
+    c->h_seg_off.resize(2 * (size_t)P + 1);
+    for (int32_t p = 0; p <= P; p++) { c->h_seg_off[p] = po[p]; c->h_seg_off[P + p] = n + po[p]; }
+    if (c->d_pair_off.reserve(st, P + 1) || c->d_rmin.reserve(st, P + 1) || c->d_nrows.reserve(st, P + 1) || c->d_rb.reserve(st, P + 1) ||
+        c->d_item_order.reserve(st, 2 * P + 1) || c->d_pair_order.reserve(st, P + 1) || c->d_seg_off.reserve(st, 2 * P + 1))
+        return st.code;
+    ICL_CUDA(st, h2d(c->d_pair_off.p, c->h_pair_off.data(), (size_t)(P + 1) * sizeof(int64_t), s));
+    ICL_CUDA(st, h2d(c->d_seg_off.p, c->h_seg_off.data(), (2 * (size_t)P + 1) * sizeof(int64_t), s));
+    ICL_CUDA(st, h2d(c->d_rb.p, c->h_rb.data(), (size_t)(P + 1) * sizeof(int64_t), s));
+    ICL_CUDA(st, h2d(c->d_rmin.p, c->h_rmin.data(), (size_t)(P + 1) * sizeof(int32_t), s));
+    ICL_CUDA(st, h2d(c->d_nrows.p, c->h_nrows.data(), (size_t)(P + 1) * sizeof(int32_t), s));
+    if (P > 0) {
+        ICL_CUDA(st, h2d(c->d_item_order.p, c->h_item_order.data(), (size_t)2 * P * sizeof(int32_t), s));
+        ICL_CUDA(st, h2d(c->d_pair_order.p, c->h_pair_order.data(), (size_t)P * sizeof(int32_t), s));
+    }
+    ICL_CUDA(st, dev_sync(s));                                 // the host vectors are pageable: the copies have left them
     return 0;
 }
 
@@ -270,13 +355,13 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->X1.release(); c->X2.release(); c->G.release(); c->itemof.release(); c->mmap.release(); c->imap.release();
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->tile_state.release(); c->tile_dst.release(); c->edge_stage.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
     c->S.release(); c->root.release(); c->hint.release(); c->big_trees.release(); c->small_trees.release(); c->pd.release(); c->used.release(); c->score32.release();
-    c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release(); c->members.release();
-    c->times.release(); c->tree_v.release(); c->acc_m.release(); c->acc_flag.release(); c->blkidx.release();
-    c->moff.release(); c->present.release(); c->b_top.release(); c->b_m.release(); c->b_L.release(); c->b_j0.release();
-    c->b_j1.release(); c->b_l2min.release(); c->b_l2max.release(); c->b_L1.release(); c->b_item.release();
-    c->b_N.release(); c->b_moff.release(); c->b_N1.release(); c->b_a.release();
-    c->o_flag.release(); c->o_bidx.release(); c->o_mcnt.release(); c->o_moff.release(); c->d_stage.release();
-    c->o_src.release(); c->o_mout.release(); c->o_moff2.release();
+    c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release();
+    c->times.release(); c->tree_v.release(); c->acc_m.release(); c->tri_in.release(); c->tri.release();
+    c->present.release(); c->b_j0.release();
+    c->b_j1.release(); c->b_l2min.release(); c->b_l2max.release();
+    c->b_N.release(); c->b_N1.release();
+    c->d_stage.release();
+    c->o_src.release(); c->o_ms.release();
     c->host_flag.release(); c->xs_chunk.release(); c->npscr.release();
 #ifndef ICL_EMU
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -354,7 +439,9 @@ static int upload_typed(icl_ctx *c, int64_t n, int32_t P, const void *const src[
     }
     if (input_stats(c)) return st.code;
     int32_t hs[4] = {0, 0, 0, 0};
+    std::vector<int32_t> hist(3 * (size_t)P + 1, 0);
     ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), c->stream));
+    if (P > 0) ICL_CUDA(st, d2h(hist.data(), c->pair_hist.p, 3 * (size_t)P * sizeof(int32_t), c->stream));
     ICL_CUDA(st, dev_sync(c->stream));
     if (hs[2]) return fail(c, ICL_ERR_ARG, std::string(who) + ": negative coordinate or pair id outside [0, n_pairs)");
     if (hs[0] >= (1 << 26) || hs[1] >= (1 << 26)) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": coordinates must be < 2^26");
@@ -364,6 +451,7 @@ static int upload_typed(icl_ctx *c, int64_t n, int32_t P, const void *const src[
     c->bits2 = bits_for(hs[1]);
     c->bitsp = bits_for(P > 0 ? P - 1 : 0);
     if (c->bits1 + c->bits2 + c->bitsp > 64) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": key does not fit 64 bits");
+    if (plan_layout(c, hist, who)) return st.code;
     c->uploaded = true;
     st.code = 0;
     return ICL_OK;
@@ -404,29 +492,40 @@ extern "C" int icl_set_grading_table(icl_ctx *c, int32_t n_classes, const int32_
 // ------------------------------------------------------------------------------------------------
 // phase: sort + layout
 // ------------------------------------------------------------------------------------------------
+struct SortedKeys {                  // the sorted (pair, loc1, loc2) keys, 64- or 32-bit
+    const void *p;
+    bool wide;
+    ICL_HD uint64_t operator[](int64_t i) const { return wide ? ((const uint64_t *)p)[i] : (uint64_t)((const uint32_t *)p)[i]; }
+};
+
 static int phase_sort(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n;
-    const int32_t P = c->P;
     cudaStream_t s = c->stream;
     if (c->key_a.reserve(st, n) || c->key_b.reserve(st, n) || c->idx_a.reserve(st, n) || c->perm.reserve(st, n) ||
-        c->loc1s.reserve(st, n) || c->loc2s.reserve(st, n) || c->pair_s.reserve(st, n) || c->G.reserve(st, 2 * n) ||
-        c->d_pair_off.reserve(st, P + 1) || c->d_rmin.reserve(st, P + 1) || c->d_nrows.reserve(st, P + 1))
+        c->loc1s.reserve(st, n) || c->loc2s.reserve(st, n) || c->pair_s.reserve(st, n) || c->G.reserve(st, 2 * n))
         return st.code;
     const int sh2 = c->bits2, shp = c->bits1 + c->bits2;
+    // (pair, loc1, loc2) of a Vitis- or wheat-sized comparison needs 31-32 bits: 32-bit keys then (a third less traffic per pass)
+    const bool wide = shp + c->bitsp > 32;
     {
         const int32_t *ip = c->in_pair.p, *i1 = c->in_loc1.p, *i2 = c->in_loc2.p;
         uint64_t *key = c->key_a.p;
+        uint32_t *key32 = (uint32_t *)c->key_a.p;
         uint32_t *idx = c->idx_a.p;
         ICL_CUDA(st, foreach(s, n, ICL_LAMBDA(int64_t i) {
-            key[i] = ((uint64_t)(uint32_t)ip[i] << shp) | ((uint64_t)(uint32_t)i1[i] << sh2) | (uint64_t)(uint32_t)i2[i];
+            const uint64_t k = ((uint64_t)(uint32_t)ip[i] << shp) | ((uint64_t)(uint32_t)i1[i] << sh2) | (uint64_t)(uint32_t)i2[i];
+            if (wide) key[i] = k; else key32[i] = (uint32_t)k;
             idx[i] = (uint32_t)i;
         }));
     }
     // stable LSD radix sort: equal (pair, loc1, loc2) keep upload order (run_colliearity.py:164-166)
-    if (n > 0 && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->perm.p, n, shp + c->bitsp, s)) return st.code;
+    if (n > 0 && wide && radix_sort_pairs(st, c->tmp, c->key_a.p, c->key_b.p, c->idx_a.p, c->perm.p, n, shp + c->bitsp, s)) return st.code;
+    if (n > 0 && !wide && radix_sort_pairs32(st, c->tmp, (const uint32_t *)c->key_a.p, (uint32_t *)c->key_b.p, c->idx_a.p, c->perm.p, n,
+                                             shp + c->bitsp, s))
+        return st.code;
     {
-        const uint64_t *key = c->key_b.p;
+        const SortedKeys key{c->key_b.p, wide};
         const uint32_t *perm = c->perm.p;
         const int32_t *ig = c->in_grad.p;
         int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p, *ps = c->pair_s.p, *G = c->G.p;
@@ -440,60 +539,6 @@ static int phase_sort(icl_ctx *c) {
             const int32_t g = ig[perm[i]];
             G[i] = gt.n ? gt.v[g] : g;                        // class id -> grading of this parameter set
         }));
-        int64_t *off = c->d_pair_off.p;
-        ICL_CUDA(st, foreach(s, (int64_t)P + 1, ICL_LAMBDA(int64_t p) {
-            // first sorted position whose pair id is >= p
-            int64_t lo = 0, hi = n;
-            while (lo < hi) {
-                int64_t mid = lo + ((hi - lo) >> 1);
-                if ((int64_t)(key[mid] >> shp) >= p) hi = mid; else lo = mid + 1;
-            }
-            off[p] = lo;
-        }));
-        int32_t *rmin = c->d_rmin.p, *nrows = c->d_nrows.p;
-        ICL_CUDA(st, foreach(s, (int64_t)P, ICL_LAMBDA(int64_t p) {
-            int64_t a = off[p], b = off[p + 1];
-            if (b > a) { rmin[p] = l1[a]; nrows[p] = l1[b - 1] - l1[a] + 1; }
-            else { rmin[p] = 0; nrows[p] = 0; }
-        }));
-    }
-    c->h_pair_off.assign(P + 1, 0);
-    c->h_rmin.assign(P + 1, 0);
-    c->h_nrows.assign(P + 1, 0);
-    ICL_CUDA(st, d2h(c->h_pair_off.data(), c->d_pair_off.p, (size_t)(P + 1) * sizeof(int64_t), s));
-    if (P > 0) {
-        ICL_CUDA(st, d2h(c->h_rmin.data(), c->d_rmin.p, (size_t)P * sizeof(int32_t), s));
-        ICL_CUDA(st, d2h(c->h_nrows.data(), c->d_nrows.p, (size_t)P * sizeof(int32_t), s));
-    }
-    ICL_CUDA(st, dev_sync(s));
-    // dense row index: nrows[p] + 1 slots per pair; longest-processing-time order of items / pairs
-    c->h_rb.assign(P + 1, 0);
-    for (int32_t p = 0; p < P; p++) c->h_rb[p + 1] = c->h_rb[p] + c->h_nrows[p] + 1;
-    c->R = c->h_rb[P];
-    for (int32_t p = 0; p < P; p++)
-        if (c->h_pair_off[p + 1] - c->h_pair_off[p] >= (1 << 24))
-            return fail(c, ICL_ERR_LIMIT, "icl_dp: a chromosome pair must hold fewer than 2^24 points");
-    if (2 * c->R >= (1ll << 31)) return fail(c, ICL_ERR_LIMIT, "icl_dp: dense row index too large (sparse gene orders?)");
-    c->h_pair_order.resize(P);
-    std::iota(c->h_pair_order.begin(), c->h_pair_order.end(), 0);
-    const std::vector<int64_t> &po = c->h_pair_off;
-    std::stable_sort(c->h_pair_order.begin(), c->h_pair_order.end(),
-                     [&](int32_t a, int32_t b) { return po[a + 1] - po[a] > po[b + 1] - po[b]; });
-    c->h_item_order.resize(2 * (size_t)P);
-    for (int32_t j = 0; j < P; j++) {
-        c->h_item_order[2 * j] = c->h_pair_order[j];
-        c->h_item_order[2 * j + 1] = P + c->h_pair_order[j];
-    }
-    c->h_seg_off.resize(2 * (size_t)P + 1);
-    for (int32_t p = 0; p <= P; p++) { c->h_seg_off[p] = po[p]; c->h_seg_off[P + p] = n + po[p]; }
-    if (c->d_rb.reserve(st, P + 1) || c->d_item_order.reserve(st, 2 * P + 1) || c->d_pair_order.reserve(st, P + 1) ||
-        c->d_seg_off.reserve(st, 2 * P + 1))
-        return st.code;
-    ICL_CUDA(st, h2d(c->d_seg_off.p, c->h_seg_off.data(), (2 * (size_t)P + 1) * sizeof(int64_t), s));
-    ICL_CUDA(st, h2d(c->d_rb.p, c->h_rb.data(), (size_t)(P + 1) * sizeof(int64_t), s));
-    if (P > 0) {
-        ICL_CUDA(st, h2d(c->d_item_order.p, c->h_item_order.data(), (size_t)2 * P * sizeof(int32_t), s));
-        ICL_CUDA(st, h2d(c->d_pair_order.p, c->h_pair_order.data(), (size_t)P * sizeof(int32_t), s));
     }
     return 0;
 }
@@ -1678,13 +1723,19 @@ __global__ void __launch_bounds__(256) k_tree_heads(TreeWalk W, int2 *smallq, in
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (int64_t b0 = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31); b0 < W.V; b0 += stride) {
         const int64_t t0 = b0 + lane;
-        bool head = false;
-        if (t0 < W.V) {
-            const uint32_t rt = W.key[t0];
-            head = rt < (uint32_t)W.V && (t0 == 0 || W.key[t0 - 1] != rt);
-        }
+        // a run ends where the key changes: most runs (a tree holds a few points) end inside the warp's 32 entries, where the
+        // ballot of the changes shows the end; only a run that reaches past them is searched (gallop + bisect)
+        const uint32_t rt = t0 < W.V ? W.key[t0] : 0xffffffffu;
+        uint32_t prev = __shfl_up_sync(0xffffffffu, rt, 1);
+        if (lane == 0) prev = t0 > 0 ? W.key[t0 - 1] : 0xffffffffu;
+        const bool change = t0 <= W.V && (t0 == 0 || t0 == W.V || prev != rt);
+        const uint32_t cm = __ballot_sync(0xffffffffu, change);
+        bool head = t0 < W.V && change && rt < (uint32_t)W.V;
         int64_t uend = 0;
-        if (head) uend = W.run_end(t0);
+        if (head) {
+            const uint32_t later = lane < 31 ? cm >> (lane + 1) : 0u;
+            uend = later ? t0 + __ffs(later) : W.run_end(t0);
+        }
         // a path is made of points of its tree: a tree with fewer used points than over_gap cannot yield a block (:129), and
         // nothing else looks at its `present` flags — most trees are such pairs of noise hits
         head = head && uend - t0 >= W.over_gap;
@@ -1845,6 +1896,68 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
 }
 #endif
 
+struct Stage {                               // bump allocator over the context's staging buffers
+    uint8_t *base;
+    size_t used;
+    template <class T> T *take(int64_t count) {
+        used = (used + 63) & ~(size_t)63;
+        T *p = (T *)(base + used);
+        used += (size_t)(count > 0 ? count : 1) * sizeof(T);
+        return p;
+    }
+};
+
+// Output staging for NBo blocks with NMo gene pairs: one device allocation and one page-locked host allocation of the same
+// layout — the per-block arrays first, the per-gene-pair arrays behind them (they are filled and copied separately).
+static int stage_layout(icl_ctx *c, int64_t NBo, int64_t NMo) {
+    Status &st = c->st;
+    size_t members_at = 0;
+    auto layout = [&](Stage &g, icl_blocks &o) {
+        o.pair = g.take<int32_t>(NBo); o.dir = g.take<int32_t>(NBo); o.score = g.take<int64_t>(NBo);
+        o.m = g.take<int32_t>(NBo); o.L = g.take<int32_t>(NBo); o.N = g.take<int32_t>(NBo); o.N1 = g.take<int64_t>(NBo);
+        o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo); o.p_raw = g.take<double>(NBo);
+        o.member_off = g.take<int64_t>(NBo + 1);
+        o.loc1 = g.take<int32_t>(NMo);
+        members_at = (size_t)((uint8_t *)o.loc1 - g.base);
+        o.loc2 = g.take<int32_t>(NMo);
+        o.member_idx = g.take<int32_t>(NMo);
+    };
+    Stage ds{nullptr, 0};
+    icl_blocks probe{};
+    layout(ds, probe);                                         // size only
+    const size_t bytes = ds.used + 64;
+    if (c->d_stage.reserve(st, bytes)) return st.code;
+    if (bytes > c->h_stage_cap) {
+#ifndef ICL_EMU
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_cap = 0;
+        ICL_CUDA(st, cudaHostAlloc((void **)&c->h_stage, bytes + bytes / 4, cudaHostAllocDefault));
+#else
+        free(c->h_stage);
+        c->h_stage = (uint8_t *)malloc(bytes + bytes / 4);
+        if (!c->h_stage) return fail(c, ICL_ERR_NOMEM, "icl_extract: out of host memory");
+#endif
+        c->h_stage_cap = bytes + bytes / 4;
+    }
+    ds = Stage{c->d_stage.p, 0};
+    Stage hs{c->h_stage, 0};
+    memset(&c->dv, 0, sizeof(c->dv));
+    memset(&c->hv, 0, sizeof(c->hv));
+    layout(ds, c->dv);
+    layout(hs, c->hv);
+    c->stage_members_at = members_at;
+    c->stage_bytes = ds.used;
+    return 0;
+}
+
+// position e of the pair-major emission order -> rank position t (V space, direction-major): the 2 np positions of pair p
+// are its forward rank positions followed by its anti-diagonal ones
+ICL_HD int64_t emission_pos(int64_t e, int64_t n, const int32_t *ps, const int64_t *off) {
+    const int32_t p = ps[e >> 1];
+    const int64_t a = off[p], np_ = off[p + 1] - a, r = e - 2 * a;
+    return r < np_ ? a + r : n + a + (r - np_);
+}
+
 static int phase_extract(icl_ctx *c) {
     Status &st = c->st;
     const int64_t n = c->n, V = 2 * n;
@@ -1852,8 +1965,8 @@ static int phase_extract(icl_ctx *c) {
     cudaStream_t s = c->stream;
     if (c->present.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) || c->acc_ms.reserve(st, V) ||
-        c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->acc_flag.reserve(st, V + 2) ||
-        c->blkidx.reserve(st, V + 2) || c->moff.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4) ||
+        c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->tri_in.reserve(st, V + 2) ||
+        c->tri.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4) ||
         c->big_trees.reserve(st, V / ICL_TREE_SMALL + 2) || c->small_trees.reserve(st, V + 2))
         return st.code;
     ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
@@ -1957,18 +2070,26 @@ static int phase_extract(icl_ctx *c) {
         }
 #endif
     }
-    // acceptance order = rank order: block index and member offset by prefix sums over rank positions
+    // Emission order (run_colliearity.py:118, collinearity.py:49-68): chromosome pair ascending, forward blocks before
+    // anti-diagonal ones, acceptance order = rank order inside a direction.  Rank positions are direction-major (V space),
+    // so the accepted positions are counted in the pair-major order t' -> t of emission_pos(): ONE scan numbers every
+    // accepted block, every block the caller wants (m >= min_members) and the gene pairs of those, all in emission order.
     {
         const uint32_t *acc_m = c->acc_m.p;
-        uint32_t *flag = c->acc_flag.p;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) { flag[t] = acc_m[t] ? 1u : 0u; }));
+        const int32_t *ps = c->pair_s.p;
+        const int64_t *off = c->d_pair_off.p;
+        Tri *in = c->tri_in.p;
+        const uint32_t minm = (uint32_t)(c->min_members < 1 ? 1 : c->min_members);
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t e) {
+            const uint32_t m = acc_m[emission_pos(e, n, ps, off)];
+            const bool want = m >= minm;
+            in[e] = Tri{m ? 1u : 0u, want ? 1u : 0u, want ? m : 0u};
+        }));
     }
-    if (exclusive_sum_u32(st, c->tmp, c->acc_flag.p, c->blkidx.p, V, s)) return st.code;
-    if (exclusive_sum_u32(st, c->tmp, c->acc_m.p, c->moff.p, V, s)) return st.code;
-    uint32_t tot[2] = {0, 0};
+    if (exclusive_sum_tri(st, c->tmp, c->tri_in.p, c->tri.p, V, s)) return st.code;
+    Tri tot = {0u, 0u, 0u};
     int32_t hs[4] = {0, 0, 0, 0};
-    ICL_CUDA(st, d2h(&tot[0], c->blkidx.p + V, sizeof(uint32_t), s));
-    ICL_CUDA(st, d2h(&tot[1], c->moff.p + V, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(&tot, c->tri.p + V, sizeof(Tri), s));
     ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), s));
     int32_t rank_any = 0;                                      // hand-back flag icl_rank_device left unread (no sync there)
     if (c->rank_flag_pending && c->order_on_device_used)
@@ -1977,50 +2098,82 @@ static int phase_extract(icl_ctx *c) {
     c->rank_flag_pending = false;
     if (rank_any) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
     if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_extract: argsort array is not a permutation of its pair segment");
-    c->NB = tot[0];
-    c->NM = tot[1];
-    const int64_t NB = c->NB;
-    if (c->members.reserve(st, c->NM) || c->b_top.reserve(st, NB) || c->b_m.reserve(st, NB) || c->b_L.reserve(st, NB) ||
-        c->b_moff.reserve(st, NB + 1) || c->b_j0.reserve(st, NB) || c->b_j1.reserve(st, NB) || c->b_l2min.reserve(st, NB) ||
-        c->b_l2max.reserve(st, NB) || c->b_L1.reserve(st, NB) || c->b_item.reserve(st, NB) || c->b_N.reserve(st, NB) ||
-        c->b_N1.reserve(st, NB))
+    c->NB = tot.b;
+    c->NBo = tot.s;
+    c->NMo = tot.m;
+    const int64_t NB = c->NB, NBo = c->NBo, NMo = c->NMo;
+    if (c->b_j0.reserve(st, NB) || c->b_j1.reserve(st, NB) || c->b_l2min.reserve(st, NB) || c->b_l2max.reserve(st, NB) ||
+        c->b_N.reserve(st, NB) || c->b_N1.reserve(st, NB) || c->o_src.reserve(st, NBo + 1) || c->o_ms.reserve(st, NBo + 1))
         return st.code;
+    if (stage_layout(c, NBo, NMo)) return st.code;
     {
-        // one thread per accepted block: members by loc1 ascending (:140), row slice of the bounding box
-        const uint32_t *acc_m = c->acc_m.p, *blkidx = c->blkidx.p, *moff = c->moff.p, *acc_ms = c->acc_ms.p;
-        const int32_t *acc_L = c->acc_L.p, *rowptr = c->rowptr.p, *mscr = c->mscr.p;
+        // one thread per accepted block: the row slice of its bounding box for the times / p-value pass, and — for a
+        // block the caller gets — its output record (everything but N, N1 and the p value, which follow that pass)
+        const uint32_t *acc_m = c->acc_m.p, *acc_ms = c->acc_ms.p;
+        const Tri *tri = c->tri.p;
+        const int32_t *acc_L = c->acc_L.p, *rowptr = c->rowptr.p, *S = c->S.p, *ps = c->pair_s.p;
         const int4 *acc_box = c->acc_box.p;
         const int32_t *rmin = c->d_rmin.p;
-        const int64_t *rb_ = c->d_rb.p;
-        const int32_t *itemof_pos = c->itemof.p;       // item of a V position == item of the point stored there
-        int32_t *members = c->members.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_j0 = c->b_j0.p, *b_N = c->b_N.p;
+        const int64_t *rb_ = c->d_rb.p, *off = c->d_pair_off.p;
+        int32_t *b_j0 = c->b_j0.p, *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_N = c->b_N.p;
         int64_t *b_N1 = c->b_N1.p;
-        int32_t *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_L1 = c->b_L1.p, *b_item = c->b_item.p;
-        uint32_t *b_moff = c->b_moff.p;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
+        uint32_t *o_src = c->o_src.p, *o_ms = c->o_ms.p;
+        const uint32_t minm = (uint32_t)(c->min_members < 1 ? 1 : c->min_members);
+        const icl_blocks o = c->dv;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t e) {
+            if (e == 0) o.member_off[NBo] = NMo;
+            const int32_t p = ps[e >> 1];
+            const int64_t t = emission_pos(e, n, ps, off);
             const uint32_t m = acc_m[t];
             if (!m) return;
-            const uint32_t b = blkidx[t], mo = moff[t], ms = acc_ms[t];
-            const int32_t it = itemof_pos[t];
-            const int32_t p = it >= P ? it - P : it;
-            // the walk went from the top towards the root: loc1 descending forward, ascending on the anti-diagonal
-            if (it >= P) for (uint32_t k = 0; k < m; k++) members[mo + k] = mscr[ms + k];
-            else for (uint32_t k = 0; k < m; k++) members[mo + k] = mscr[ms + m - 1 - k];
+            const Tri at = tri[e];
+            const uint32_t b = at.b;
             const int4 box = acc_box[t];
-            b_top[b] = rank2v[t];
             b_N[b] = 0;                                                         // (the p-value pass adds into these)
             b_N1[b] = 0;
-            b_m[b] = (int32_t)m;
-            b_L[b] = acc_L[t];
-            b_moff[b] = mo;
-            b_item[b] = it;
             b_l2min[b] = box.z;
             b_l2max[b] = box.w;
-            b_L1[b] = box.y - box.x + 1;
             b_j0[b] = rowptr[rb_[p] + (box.x - rmin[p])];
             b_j1[b] = rowptr[rb_[p] + (box.y - rmin[p]) + 1];
+            if (m < minm) return;
+            const uint32_t g = at.s;
+            o_src[g] = b;
+            o_ms[g] = acc_ms[t];
+            o.pair[g] = p;
+            o.dir[g] = t >= n ? 1 : 0;
+            o.score[g] = S[rank2v[t]];
+            o.m[g] = (int32_t)m;
+            o.L[g] = acc_L[t];
+            o.L1[g] = box.y - box.x + 1;
+            o.L2[g] = box.w - box.z + 1;
+            o.member_off[g] = at.m;
         }));
+        if (V == 0) ICL_CUDA(st, dev_memset(c->dv.member_off, 0, sizeof(int64_t), s));
     }
+    return 0;
+}
+
+// The gene pairs of the output blocks, one thread each (binary search for its block): the walk listed a block's members
+// from the top towards the root — loc1 descending forward, ascending on the anti-diagonal — and the output wants loc1
+// ascending (:140).  Independent of the times / p-value pass: issued on the side stream next to it, its copy behind it.
+static int phase_members(icl_ctx *c, cudaStream_t s) {
+    Status &st = c->st;
+    const int64_t NBo = c->NBo, NMo = c->NMo;
+    const uint32_t *o_ms = c->o_ms.p, *perm = c->perm.p;
+    const int32_t *mscr = c->mscr.p, *l1 = c->loc1s.p, *l2 = c->loc2s.p;
+    const icl_blocks o = c->dv;
+    ICL_CUDA(st, foreach(s, NMo, ICL_LAMBDA(int64_t t) {
+        int64_t lo = 0, hi = NBo - 1;                           // last block with member_off[g] <= t
+        while (lo < hi) {
+            int64_t mid = lo + ((hi - lo + 1) >> 1);
+            if (o.member_off[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int64_t k = t - o.member_off[lo], m = o.member_off[lo + 1] - o.member_off[lo];
+        const int32_t i = mscr[o_ms[lo] + (uint32_t)(o.dir[lo] ? k : m - 1 - k)];
+        o.loc1[t] = l1[i];
+        o.loc2[t] = l2[i];
+        o.member_idx[t] = (int32_t)perm[i];
+    }));
     return 0;
 }
 
@@ -2056,12 +2209,11 @@ ICL_HD double icl_p_raw(int64_t score, int32_t m, int32_t g0, int64_t N1, int32_
 struct PvalArgs {
     int64_t n;
     int32_t P, g0, smem_cap;
-    const int32_t *pair_order, *l2, *S, *b_top, *b_m, *b_j0, *b_j1, *b_l2min, *b_l2max, *b_L1;
+    const int32_t *pair_order, *l2, *b_j0, *b_j1, *b_l2min, *b_l2max;
     const int64_t *off;
-    const uint32_t *blkidx;
+    const Tri *tri;                  // .b: accepted blocks before an emission position (pair p: forward blocks from 2 off[p], anti-diagonal from 2 off[p] + np)
     int32_t *times, *b_N;
     int64_t *b_N1;
-    double *b_a;
 };
 
 #ifndef ICL_EMU
@@ -2080,7 +2232,7 @@ __device__ __forceinline__ void pvalue_pair(const PvalArgs &A, int32_t p, uint16
     __syncwarp();
     volatile int32_t *tg = A.times;
     for (int d = 0; d < 2; d++) {
-        const uint32_t b0 = A.blkidx[(d ? A.n : 0) + a], b1 = A.blkidx[(d ? A.n : 0) + a + np_];
+        const uint32_t b0 = A.tri[2 * a + d * np_].b, b1 = A.tri[2 * a + (d + 1) * np_].b;
         // block records are fetched 32 at a time (one per lane, coalesced) and handed out by shuffle
         int32_t rj0 = 0, rj1 = 0, rlo = 0, rhi = 0;
         if (b0 + lane < b1) { rj0 = A.b_j0[b0 + lane]; rj1 = A.b_j1[b0 + lane]; rlo = A.b_l2min[b0 + lane]; rhi = A.b_l2max[b0 + lane]; }
@@ -2124,7 +2276,7 @@ __global__ void __launch_bounds__(32) k_pvalue(PvalArgs A, int32_t l2_cap) {
     extern __shared__ __align__(16) unsigned char psm[];
     const int32_t p = A.pair_order[blockIdx.x];
     const int64_t np_ = A.off[p + 1] - A.off[p];
-    const uint32_t nb = A.blkidx[A.n + A.off[p + 1]] - A.blkidx[A.n + A.off[p]] + A.blkidx[A.off[p + 1]] - A.blkidx[A.off[p]];
+    const uint32_t nb = A.tri[2 * A.off[p + 1]].b - A.tri[2 * A.off[p]].b;
     if (nb == 0) return;
     uint16_t *tsm = (uint16_t *)psm;
     int32_t *l2sm = (int32_t *)(psm + (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15));
@@ -2149,7 +2301,7 @@ __global__ void __launch_bounds__(1024) k_pvalue_owned(PvalArgs A) {
     extern __shared__ __align__(16) unsigned char psm[];
     const int32_t p = A.pair_order[blockIdx.x];
     const int64_t a = A.off[p], np_ = A.off[p + 1] - a;
-    const uint32_t bf0 = A.blkidx[a], bf1 = A.blkidx[a + np_], br0 = A.blkidx[A.n + a], br1 = A.blkidx[A.n + a + np_];
+    const uint32_t bf0 = A.tri[2 * a].b, bf1 = A.tri[2 * a + np_].b, br0 = bf1, br1 = A.tri[2 * a + 2 * np_].b;
     if (bf1 - bf0 + br1 - br0 == 0) return;
     uint32_t *tsm = (uint32_t *)psm;                           // TS: one counter per point of the pair
     int32_t *l2sm = (int32_t *)(psm + (((size_t)np_ * 4 + 15) & ~(size_t)15));
@@ -2285,12 +2437,12 @@ static int phase_pvalue(icl_ctx *c) {
     const int64_t n = c->n, NB = c->NB;
     const int32_t P = c->P;
     cudaStream_t s = c->stream;
-    if (c->times.reserve(st, n) || c->b_N.reserve(st, NB) || c->b_N1.reserve(st, NB) || c->b_a.reserve(st, NB)) return st.code;
+    if (c->times.reserve(st, n) || c->b_N.reserve(st, NB) || c->b_N1.reserve(st, NB)) return st.code;
     PvalArgs A;
     A.n = n; A.P = P; A.g0 = c->prm.g0;
-    A.pair_order = c->d_pair_order.p; A.l2 = c->loc2s.p; A.S = c->S.p; A.b_top = c->b_top.p; A.b_m = c->b_m.p;
-    A.b_j0 = c->b_j0.p; A.b_j1 = c->b_j1.p; A.b_l2min = c->b_l2min.p; A.b_l2max = c->b_l2max.p; A.b_L1 = c->b_L1.p;
-    A.off = c->d_pair_off.p; A.blkidx = c->blkidx.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p; A.b_a = c->b_a.p;
+    A.pair_order = c->d_pair_order.p; A.l2 = c->loc2s.p;
+    A.b_j0 = c->b_j0.p; A.b_j1 = c->b_j1.p; A.b_l2min = c->b_l2min.p; A.b_l2max = c->b_l2max.p;
+    A.off = c->d_pair_off.p; A.tri = c->tri.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p;
     if (P == 0) return 0;
     // Small pairs (times and loc2 of the pair fit in shared memory, few blocks per pair) are fastest on the
     // sequential warp-per-pair kernel; large pairs serialise there and take the order-free incidence path.
@@ -2331,7 +2483,7 @@ static int phase_pvalue(icl_ctx *c) {
         int64_t a = A.off[p], np_ = A.off[p + 1] - a;
         for (int64_t i = 0; i < np_; i++) A.times[a + i] = 1;
         for (int d = 0; d < 2; d++) {
-            uint32_t b0 = A.blkidx[(d ? n : 0) + a], b1 = A.blkidx[(d ? n : 0) + a + np_];
+            uint32_t b0 = A.tri[2 * a + d * np_].b, b1 = A.tri[2 * a + (d + 1) * np_].b;
             for (uint32_t b = b0; b < b1; b++) {
                 int32_t N = 0, lo = A.b_l2min[b], hi = A.b_l2max[b];
                 int64_t N1 = 0;
@@ -2344,17 +2496,6 @@ static int phase_pvalue(icl_ctx *c) {
     }
 #endif
     }
-    {
-        // p value of every accepted block, one thread each (collinearity.py:152 in binary64, left to right)
-        const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;
-        const int32_t *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p;
-        const int64_t *b_N1 = c->b_N1.p;
-        double *b_a = c->b_a.p;
-        const int32_t g0 = c->prm.g0;
-        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
-            b_a[b] = icl_p_raw((int64_t)S[b_top[b]], b_m[b], g0, b_N1[b], b_N[b], b_L1[b], b_l2max[b] - b_l2min[b] + 1);
-        }));
-    }
     return 0;
 }
 
@@ -2365,16 +2506,6 @@ extern "C" void icl_free_blocks(icl_blocks *b) {
     if (b) memset(b, 0, sizeof(*b));        // the arrays live in page-locked staging owned by the context
 }
 
-struct Stage {                               // bump allocator over the context's pinned staging buffer
-    uint8_t *base;
-    size_t used;
-    template <class T> T *take(int64_t count) {
-        used = (used + 63) & ~(size_t)63;
-        T *p = (T *)(base + used);
-        used += (size_t)(count > 0 ? count : 1) * sizeof(T);
-        return p;
-    }
-};
 
 // ------------------------------------------------------------------------------------------------
 // numpy's SCALAR argsort, reproduced exactly on the device.
@@ -3854,7 +3985,6 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
 #endif
     cudaStream_t s = c->stream;
     const int64_t n = c->n, V = 2 * n;
-    const int32_t P = c->P;
     LaunchScope scope(c, 2);
     c->timers[ICL_T_EXTRACT].start(s);
     if (c->order_in.reserve(st, 2 * n) || c->rank2v.reserve(st, V)) return st.code;
@@ -3882,122 +4012,49 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
             rank2v[n + a + (np_ - 1 - j)] = mmap[a + (np_ - 1 - rr)];
         }));
     }
+    c->min_members = min_members;
     if (phase_extract(c)) return st.code;
     c->timers[ICL_T_EXTRACT].stop(s);
+    const int64_t NBo = c->NBo, NMo = c->NMo;
+    // the gene pairs of the output do not wait for the p values: gathered and copied on the side stream meanwhile
+    cudaStream_t s2 = c->stream2 ? c->stream2 : s;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));
+    ICL_CUDA(st, cudaStreamWaitEvent(s2, c->ev_fork, 0));
+#endif
+    if (phase_members(c, s2)) return st.code;
+    if (c->stage_bytes > c->stage_members_at)
+        ICL_CUDA(st, d2h(c->h_stage + c->stage_members_at, c->d_stage.p + c->stage_members_at, c->stage_bytes - c->stage_members_at, s2));
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaEventRecord(c->ev_join, s2));
+#endif
     c->timers[ICL_T_PVALUE].start(s);
     if (phase_pvalue(c)) return st.code;
     c->timers[ICL_T_PVALUE].stop(s);
     c->timers[ICL_T_GATHER].start(s);
-    // select the blocks the caller wants (m >= min_members); every accepted block has already bumped `times`
-    const int64_t NB = c->NB;
-    if (c->o_flag.reserve(st, NB + 2) || c->o_bidx.reserve(st, NB + 2) || c->o_mcnt.reserve(st, NB + 2) || c->o_moff.reserve(st, NB + 2))
-        return st.code;
     {
-        const int32_t *b_m = c->b_m.p;
-        uint32_t *flag = c->o_flag.p, *mcnt = c->o_mcnt.p;
-        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
-            bool keep = b_m[b] >= min_members;
-            flag[b] = keep ? 1u : 0u;
-            mcnt[b] = keep ? (uint32_t)b_m[b] : 0u;
-        }));
-    }
-    if (exclusive_sum_u32(st, c->tmp, c->o_flag.p, c->o_bidx.p, NB, s)) return st.code;
-    if (exclusive_sum_u32(st, c->tmp, c->o_mcnt.p, c->o_moff.p, NB, s)) return st.code;
-    uint32_t tot[2] = {0, 0};
-    ICL_CUDA(st, d2h(&tot[0], c->o_bidx.p + NB, sizeof(uint32_t), s));
-    ICL_CUDA(st, d2h(&tot[1], c->o_moff.p + NB, sizeof(uint32_t), s));
-    ICL_CUDA(st, dev_sync(s));
-    const int64_t NBo = tot[0], NMo = tot[1];
-    // device staging, one allocation, same layout as the pinned host staging
-    Stage ds{nullptr, 0}, hs{nullptr, 0};
-    auto layout = [&](Stage &g, icl_blocks &o) {
-        o.pair = g.take<int32_t>(NBo); o.dir = g.take<int32_t>(NBo); o.score = g.take<int64_t>(NBo);
-        o.m = g.take<int32_t>(NBo); o.L = g.take<int32_t>(NBo); o.N = g.take<int32_t>(NBo); o.N1 = g.take<int64_t>(NBo);
-        o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo); o.p_raw = g.take<double>(NBo);
-        o.member_off = g.take<int64_t>(NBo + 1); o.loc1 = g.take<int32_t>(NMo); o.loc2 = g.take<int32_t>(NMo);
-        o.member_idx = g.take<int32_t>(NMo);
-    };
-    icl_blocks dv{}, probe{};
-    layout(ds, probe);                                         // size only
-    const size_t bytes = ds.used + 64;
-    if (c->d_stage.reserve(st, bytes)) return st.code;
-    if (bytes > c->h_stage_cap) {
-#ifndef ICL_EMU
-        if (c->h_stage) cudaFreeHost(c->h_stage);
-        c->h_stage = nullptr; c->h_stage_cap = 0;
-        ICL_CUDA(st, cudaHostAlloc((void **)&c->h_stage, bytes + bytes / 4, cudaHostAllocDefault));
-#else
-        free(c->h_stage);
-        c->h_stage = (uint8_t *)malloc(bytes + bytes / 4);
-        if (!c->h_stage) return fail(c, ICL_ERR_NOMEM, "icl_extract: out of host memory");
-#endif
-        c->h_stage_cap = bytes + bytes / 4;
-    }
-    ds = Stage{c->d_stage.p, 0};
-    hs = Stage{c->h_stage, 0};
-    layout(ds, dv);
-    layout(hs, *out);
-    // Emission order is pair-major (pair, direction, acceptance order) while block indices are direction-major
-    // (V space): permute the selected blocks, then lay their members out with a prefix sum in output order.
-    if (c->o_src.reserve(st, NBo + 1) || c->o_mout.reserve(st, NBo + 2) || c->o_moff2.reserve(st, NBo + 2)) return st.code;
-    {
-        const uint32_t *flag = c->o_flag.p, *sel = c->o_bidx.p, *blkidx = c->blkidx.p;
-        const int32_t *b_m = c->b_m.p, *b_item = c->b_item.p;
-        const int64_t *off = c->d_pair_off.p;
-        uint32_t *o_src = c->o_src.p, *o_mout = c->o_mout.p;
-        ICL_CUDA(st, foreach(s, NB, ICL_LAMBDA(int64_t b) {
-            if (!flag[b]) return;
-            int32_t it = b_item[b];
-            uint32_t selF = sel[blkidx[n]];                      // selected forward blocks in total
-            uint32_t g;
-            if (it < P) g = (sel[blkidx[n + off[it]]] - selF) + sel[b];                 // anti-diagonal blocks of earlier pairs
-            else g = sel[blkidx[off[it - P + 1]]] + (sel[b] - selF);                    // forward blocks of pairs <= p
-            o_src[g] = (uint32_t)b;
-            o_mout[g] = (uint32_t)b_m[b];
-        }));
-    }
-    if (exclusive_sum_u32(st, c->tmp, c->o_mout.p, c->o_moff2.p, NBo, s)) return st.code;
-    {
-        const uint32_t *o_src = c->o_src.p, *omoff = c->o_moff2.p, *b_moff = c->b_moff.p, *perm = c->perm.p;
-        const int32_t *S = c->S.p, *b_top = c->b_top.p, *b_m = c->b_m.p, *b_L = c->b_L.p, *b_N = c->b_N.p, *b_L1 = c->b_L1.p;
-        const int32_t *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_item = c->b_item.p, *members = c->members.p;
-        const int32_t *l1 = c->loc1s.p, *l2 = c->loc2s.p;
+        // N, N1 and the p value (collinearity.py:152 in binary64, left to right) of the blocks the caller gets
+        const uint32_t *o_src = c->o_src.p;
+        const int32_t *b_N = c->b_N.p;
         const int64_t *b_N1 = c->b_N1.p;
-        const double *b_a = c->b_a.p;
-        icl_blocks o = dv;
+        const int32_t g0 = c->prm.g0;
+        const icl_blocks o = c->dv;
         ICL_CUDA(st, foreach(s, NBo, ICL_LAMBDA(int64_t g) {
-            if (g == NBo - 1) o.member_off[NBo] = NMo;
-            uint32_t b = o_src[g];
-            int32_t it = b_item[b];
-            o.pair[g] = it >= P ? it - P : it;
-            o.dir[g] = it >= P ? 1 : 0;
-            o.score[g] = S[b_top[b]];
-            o.m[g] = b_m[b];
-            o.L[g] = b_L[b];
-            o.N[g] = b_N[b];
-            o.N1[g] = b_N1[b];
-            o.L1[g] = b_L1[b];
-            o.L2[g] = b_l2max[b] - b_l2min[b] + 1;
-            o.p_raw[g] = b_a[b];
-            o.member_off[g] = omoff[g];
+            const uint32_t b = o_src[g];
+            const int32_t N = b_N[b];
+            const int64_t N1 = b_N1[b];
+            o.N[g] = N;
+            o.N1[g] = N1;
+            o.p_raw[g] = icl_p_raw(o.score[g], o.m[g], g0, N1, N, o.L1[g], o.L2[g]);
         }));
-        // members: one thread per gene pair of the output (binary search for its block)
-        ICL_CUDA(st, foreach(s, NMo, ICL_LAMBDA(int64_t t) {
-            int64_t lo = 0, hi = NBo - 1;                       // last block with omoff[g] <= t
-            while (lo < hi) {
-                int64_t mid = lo + ((hi - lo + 1) >> 1);
-                if ((int64_t)omoff[mid] <= t) lo = mid; else hi = mid - 1;
-            }
-            const int32_t i = members[b_moff[o_src[lo]] + (uint32_t)(t - omoff[lo])];
-            o.loc1[t] = l1[i];
-            o.loc2[t] = l2[i];
-            o.member_idx[t] = (int32_t)perm[i];
-        }));
-        if (NBo == 0) ICL_CUDA(st, dev_memset(dv.member_off, 0, sizeof(int64_t), s));
     }
-    ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, ds.used, s));
+    ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, c->stage_members_at, s));
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join, 0));
+#endif
     c->timers[ICL_T_GATHER].stop(s);
     ICL_CUDA(st, dev_sync(s));
+    *out = c->hv;
     out->n_blocks = NBo;
     out->n_members = NMo;
     return ICL_OK;

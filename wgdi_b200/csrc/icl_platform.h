@@ -41,6 +41,10 @@ static inline int4 make_int4(int32_t x, int32_t y, int32_t z, int32_t w) { int4 
 
 namespace icl {
 
+// three running counts of the extraction, scanned together in emission order: accepted blocks, blocks the caller
+// wants (m >= min_members) and the gene pairs of those
+struct Tri { uint32_t b, s, m; };
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -233,6 +237,19 @@ inline int exclusive_sum_u32(Status &st, Buf<uint8_t> &tmp, uint32_t *in, uint32
 struct MaxI32 {
     __host__ __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
 };
+struct TriSum {
+    __host__ __device__ __forceinline__ Tri operator()(const Tri &a, const Tri &b) const { return Tri{a.b + b.b, a.s + b.s, a.m + b.m}; }
+};
+// out[0..n] = exclusive prefix sums of the three counters of in[0..n), totals in out[n]; `in` must have n+1 slots
+inline int exclusive_sum_tri(Status &st, Buf<uint8_t> &tmp, Tri *in, Tri *out, int64_t n, cudaStream_t s) {
+    size_t bytes = 0;
+    ICL_CUDA(st, dev_memset(in + n, 0, sizeof(Tri), s));
+    ICL_CUDA(st, cub::DeviceScan::ExclusiveScan(nullptr, bytes, in, out, TriSum(), Tri{0u, 0u, 0u}, (int)(n + 1), s));
+    if (tmp.reserve(st, bytes)) return st.code;
+    ICL_CUDA(st, cub::DeviceScan::ExclusiveScan(tmp.p, bytes, in, out, TriSum(), Tri{0u, 0u, 0u}, (int)(n + 1), s));
+    ++launch_count().cub;
+    return 0;
+}
 // in place: a[i] = max(a[0..i])
 inline int inclusive_max_i32(Status &st, Buf<uint8_t> &tmp, int32_t *a, int64_t n, cudaStream_t s) {
     if (n <= 0) return 0;
@@ -290,6 +307,12 @@ inline int radix_sort_keys(Status &, Buf<uint8_t> &, const uint64_t *kin, uint64
 inline int exclusive_sum_u32(Status &, Buf<uint8_t> &, uint32_t *in, uint32_t *out, int64_t n, cudaStream_t) {
     uint32_t acc = 0;
     for (int64_t i = 0; i < n; i++) { uint32_t v = in[i]; out[i] = acc; acc += v; }
+    out[n] = acc;
+    return 0;
+}
+inline int exclusive_sum_tri(Status &, Buf<uint8_t> &, Tri *in, Tri *out, int64_t n, cudaStream_t) {
+    Tri acc = {0u, 0u, 0u};
+    for (int64_t i = 0; i < n; i++) { const Tri v = in[i]; out[i] = acc; acc.b += v.b; acc.s += v.s; acc.m += v.m; }
     out[n] = acc;
     return 0;
 }
