@@ -45,9 +45,10 @@ struct GradeTable {
 struct icl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;  // side stream: kernels of a phase that do not depend on each other (fork / join by events)
+    cudaStream_t stream2 = nullptr;  // side streams: kernels of a phase that do not depend on each other (fork / join by events)
+    cudaStream_t stream3 = nullptr;
 #ifndef ICL_EMU
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
 #endif
     Status st;
     int64_t n = 0;      // points
@@ -104,7 +105,8 @@ struct icl_ctx {
     // extraction
     Buf<int32_t> order_in, rank2v, acc_L, times, mscr;
     Buf<uint32_t> tree_v, acc_m, acc_ms;
-    Buf<Tri> tri_in, tri;            // per emission position: {accepted, wanted, members of wanted} and their exclusive sums
+    Buf<uint64_t> bs_in, bs;         // per emission position: accepted << 32 | wanted (m >= min_members) ... and the exclusive sums
+    Buf<uint32_t> mo_in, mo;         // ... gene pairs of a wanted block ... and the exclusive sum
     Buf<int4> acc_box;               // per accepted rank position: {loc1 min, loc1 max, loc2 min, loc2 max}
     Buf<uint8_t> seen;
     Buf<uint8_t> present;
@@ -122,6 +124,8 @@ struct icl_ctx {
     Buf<uint8_t> d_stage;
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0;
+    uint8_t *h_plan = nullptr;       // page-locked scratch of the upload: statistics down, layout up
+    size_t h_plan_cap = 0;
 
     Timer timers[ICL_T_COUNT];
     int64_t counters[4] = {0, 0, 0, 0};
@@ -169,8 +173,19 @@ static int bits_for(int64_t maxval) {
 // ------------------------------------------------------------------------------------------------
 #define ICL_HIST_SMEM_PAIRS 2048     // pairs whose three counters fit a CTA's shared memory
 #ifndef ICL_EMU
-__global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const int32_t *pair, const int32_t *l1,
-                                                     const int32_t *l2, const int32_t *gr, int32_t *stats, int32_t *hist) {
+struct InputArrays {                 // the four uploaded arrays as they crossed PCIe (1-, 2- or 4-byte elements) and their int32 homes
+    const void *raw[4];
+    int32_t *dst[4];
+    int32_t bytes[4];
+};
+__device__ __forceinline__ int32_t input_element(const InputArrays &A, int k, int64_t i) {
+    const int32_t b = A.bytes[k];
+    if (b == 4) return A.dst[k][i];                           // copied straight to its home
+    const int32_t v = b == 1 ? (int32_t)((const uint8_t *)A.raw[k])[i] : (int32_t)((const uint16_t *)A.raw[k])[i];
+    A.dst[k][i] = v;                                          // widened on the way through
+    return v;
+}
+__global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, InputArrays A, int32_t *stats, int32_t *hist) {
     // hist: [P] points, [P] smallest loc1, [P] largest loc1
     __shared__ int32_t sh[3 * ICL_HIST_SMEM_PAIRS];
     const bool staged = P <= ICL_HIST_SMEM_PAIRS;
@@ -181,11 +196,11 @@ __global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const
     int32_t *cnt = staged ? sh : hist, *lo = cnt + P, *hi = lo + P;
     int32_t m1 = 0, m2 = 0, mg = 0, bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int32_t a = l1[i], b = l2[i], p = pair[i];
+        const int32_t p = input_element(A, 0, i), a = input_element(A, 1, i), b = input_element(A, 2, i);
         bad |= (a < 0) | (b < 0) | (p < 0) | (p >= P);
         m1 = max(m1, a);
         m2 = max(m2, b);
-        mg = max(mg, gr[i]);
+        mg = max(mg, input_element(A, 3, i));
         if (p >= 0 && p < P) {
             atomicAdd(&cnt[p], 1);
             if (a < lo[p]) atomicMin(&lo[p], a);              // (the unsynchronised test only skips atomics that cannot change anything)
@@ -210,7 +225,7 @@ __global__ void __launch_bounds__(256) k_input_stats(int64_t n, int32_t P, const
 }
 #endif
 
-static int input_stats(icl_ctx *c) {
+static int input_stats(icl_ctx *c, const uint8_t *const raw[4], const int32_t bytes[4]) {
     Status &st = c->st;
     const int32_t P = c->P;
     if (c->pair_hist.reserve(st, 3 * (size_t)P + 1)) return st.code;
@@ -222,12 +237,20 @@ static int input_stats(icl_ctx *c) {
 #ifndef ICL_EMU
     if (c->n > 0) {
         int64_t blocks = std::min<int64_t>((c->n + 255) / 256, 148 * 8);
-        k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, P, c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p, c->stats.p,
-                                                                c->pair_hist.p);
+        InputArrays A;
+        int32_t *dst[4] = {c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p};
+        for (int k = 0; k < 4; k++) { A.raw[k] = raw[k]; A.dst[k] = dst[k]; A.bytes[k] = bytes[k]; }
+        k_input_stats<<<(unsigned)blocks, 256, 0, c->stream>>>(c->n, P, A, c->stats.p, c->pair_hist.p);
         ICL_COUNT_KERNEL();
         ICL_CUDA(st, cudaGetLastError());
     }
 #else
+    {
+        int32_t *dst[4] = {c->in_pair.p, c->in_loc1.p, c->in_loc2.p, c->in_grad.p};
+        for (int k = 0; k < 4; k++)
+            for (int64_t i = 0; i < c->n && bytes[k] != 4; i++)
+                dst[k][i] = bytes[k] == 1 ? (int32_t)raw[k][i] : (int32_t)((const uint16_t *)raw[k])[i];
+    }
     for (int64_t i = 0; i < c->n; i++) {
         int32_t a = c->in_loc1.p[i], b = c->in_loc2.p[i], p = c->in_pair.p[i];
         if (a < 0 || b < 0 || p < 0 || p >= P) c->stats.p[2] = 1;
@@ -245,9 +268,26 @@ static int input_stats(icl_ctx *c) {
     return 0;
 }
 
+// page-locked host scratch of the upload (grow-only)
+static int host_scratch(icl_ctx *c, size_t bytes) {
+    Status &st = c->st;
+    if (bytes <= c->h_plan_cap) return 0;
+#ifndef ICL_EMU
+    if (c->h_plan) cudaFreeHost(c->h_plan);
+    c->h_plan = nullptr; c->h_plan_cap = 0;
+    ICL_CUDA(st, cudaHostAlloc((void **)&c->h_plan, 2 * bytes, cudaHostAllocDefault));
+#else
+    free(c->h_plan);
+    c->h_plan = (uint8_t *)malloc(2 * bytes);
+    if (!c->h_plan) return fail(c, ICL_ERR_NOMEM, "icl_upload: out of host memory");
+#endif
+    c->h_plan_cap = 2 * bytes;
+    return 0;
+}
+
 // The layout of the uploaded comparison, from the per-pair counts of input_stats: where every pair's points will stand
 // after the sort, its dense row range, the longest-processing-time order of pairs / (pair, direction) items.
-static int plan_layout(icl_ctx *c, const std::vector<int32_t> &hist, const char *who) {
+static int plan_layout(icl_ctx *c, const int32_t *hist, const char *who) {
     Status &st = c->st;
     const int64_t n = c->n;
     const int32_t P = c->P;
@@ -281,16 +321,24 @@ static int plan_layout(icl_ctx *c, const std::vector<int32_t> &hist, const char 
     if (c->d_pair_off.reserve(st, P + 1) || c->d_rmin.reserve(st, P + 1) || c->d_nrows.reserve(st, P + 1) || c->d_rb.reserve(st, P + 1) ||
         c->d_item_order.reserve(st, 2 * P + 1) || c->d_pair_order.reserve(st, P + 1) || c->d_seg_off.reserve(st, 2 * P + 1))
         return st.code;
-    ICL_CUDA(st, h2d(c->d_pair_off.p, c->h_pair_off.data(), (size_t)(P + 1) * sizeof(int64_t), s));
-    ICL_CUDA(st, h2d(c->d_seg_off.p, c->h_seg_off.data(), (2 * (size_t)P + 1) * sizeof(int64_t), s));
-    ICL_CUDA(st, h2d(c->d_rb.p, c->h_rb.data(), (size_t)(P + 1) * sizeof(int64_t), s));
-    ICL_CUDA(st, h2d(c->d_rmin.p, c->h_rmin.data(), (size_t)(P + 1) * sizeof(int32_t), s));
-    ICL_CUDA(st, h2d(c->d_nrows.p, c->h_nrows.data(), (size_t)(P + 1) * sizeof(int32_t), s));
+    // the copies leave from the page-locked scratch (behind the counters just read): asynchronous, nothing to wait for —
+    // the scratch is next written by the next upload, which starts with a synchronisation of its own
+    uint8_t *at = c->h_plan + (((4 + 3 * (size_t)P) * sizeof(int32_t) + 15) & ~(size_t)15);
+    auto send = [&](void *dst, const void *src, size_t bytes) {
+        memcpy(at, src, bytes);
+        cudaError_t e = h2d(dst, at, bytes, s);
+        at += (bytes + 15) & ~(size_t)15;
+        return e;
+    };
+    ICL_CUDA(st, send(c->d_pair_off.p, c->h_pair_off.data(), (size_t)(P + 1) * sizeof(int64_t)));
+    ICL_CUDA(st, send(c->d_seg_off.p, c->h_seg_off.data(), (2 * (size_t)P + 1) * sizeof(int64_t)));
+    ICL_CUDA(st, send(c->d_rb.p, c->h_rb.data(), (size_t)(P + 1) * sizeof(int64_t)));
+    ICL_CUDA(st, send(c->d_rmin.p, c->h_rmin.data(), (size_t)(P + 1) * sizeof(int32_t)));
+    ICL_CUDA(st, send(c->d_nrows.p, c->h_nrows.data(), (size_t)(P + 1) * sizeof(int32_t)));
     if (P > 0) {
-        ICL_CUDA(st, h2d(c->d_item_order.p, c->h_item_order.data(), (size_t)2 * P * sizeof(int32_t), s));
-        ICL_CUDA(st, h2d(c->d_pair_order.p, c->h_pair_order.data(), (size_t)P * sizeof(int32_t), s));
+        ICL_CUDA(st, send(c->d_item_order.p, c->h_item_order.data(), (size_t)2 * P * sizeof(int32_t)));
+        ICL_CUDA(st, send(c->d_pair_order.p, c->h_pair_order.data(), (size_t)P * sizeof(int32_t)));
     }
-    ICL_CUDA(st, dev_sync(s));                                 // the host vectors are pageable: the copies have left them
     return 0;
 }
 
@@ -328,11 +376,13 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
     e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
 #endif
-    if (c->stats.reserve(c->st, 4)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
+    if (c->stats.reserve(c->st, 8)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
     const char *pvm = getenv("ICL_B200_PVALUE");
     if (pvm) c->pvalue_mode = !strcmp(pvm, "seq") ? 1 : !strcmp(pvm, "inc") ? 2 : !strcmp(pvm, "warp") ? 3 : 0;
@@ -356,7 +406,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->ecnt.release(); c->eoff.release(); c->edges.release(); c->tile_state.release(); c->tile_dst.release(); c->edge_stage.release(); c->chain_dbg.release(); c->inc_cnt.release(); c->inc_off.release(); c->inc_start.release();
     c->S.release(); c->root.release(); c->hint.release(); c->big_trees.release(); c->small_trees.release(); c->pd.release(); c->used.release(); c->score32.release();
     c->order_in.release(); c->mscr.release(); c->acc_ms.release(); c->acc_box.release(); c->seen.release(); c->rank2v.release(); c->acc_L.release();
-    c->times.release(); c->tree_v.release(); c->acc_m.release(); c->tri_in.release(); c->tri.release();
+    c->times.release(); c->tree_v.release(); c->acc_m.release(); c->bs_in.release(); c->bs.release(); c->mo_in.release(); c->mo.release();
     c->present.release(); c->b_j0.release();
     c->b_j1.release(); c->b_l2min.release(); c->b_l2max.release();
     c->b_N.release(); c->b_N1.release();
@@ -365,12 +415,18 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->host_flag.release(); c->xs_chunk.release(); c->npscr.release();
 #ifndef ICL_EMU
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_plan) cudaFreeHost(c->h_plan);
 #else
     free(c->h_stage);
+    free(c->h_plan);
 #endif
+    c->pair_hist.release();
     for (auto &t : c->timers) t.destroy();
 #ifndef ICL_EMU
     cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->stream3);
+    cudaEventDestroy(c->ev_join3);
+    cudaStreamDestroy(c->stream3);
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->stream2);
@@ -429,19 +485,20 @@ static int upload_typed(icl_ctx *c, int64_t n, int32_t P, const void *const src[
     for (int k = 0; k < 4; k++) if (bytes[k] != 4) narrow += ((size_t)n * bytes[k] + 15) & ~(size_t)15;
     if (narrow && c->in_raw.reserve(st, narrow)) return st.code;
     uint8_t *raw = c->in_raw.p;
+    const uint8_t *raws[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < 4; k++) {
         if (bytes[k] == 4) { ICL_CUDA(st, h2d(dst[k], src[k], (size_t)n * 4, c->stream)); continue; }
         ICL_CUDA(st, h2d(raw, src[k], (size_t)n * bytes[k], c->stream));
-        int32_t *o = dst[k];
-        if (bytes[k] == 1) { const uint8_t *r = raw; ICL_CUDA(st, foreach(c->stream, n, ICL_LAMBDA(int64_t i) { o[i] = r[i]; })); }
-        else { const uint16_t *r = (const uint16_t *)raw; ICL_CUDA(st, foreach(c->stream, n, ICL_LAMBDA(int64_t i) { o[i] = r[i]; })); }
+        raws[k] = raw;                                         // widened by the statistics pass
         raw += ((size_t)n * bytes[k] + 15) & ~(size_t)15;
     }
-    if (input_stats(c)) return st.code;
-    int32_t hs[4] = {0, 0, 0, 0};
-    std::vector<int32_t> hist(3 * (size_t)P + 1, 0);
-    ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), c->stream));
-    if (P > 0) ICL_CUDA(st, d2h(hist.data(), c->pair_hist.p, 3 * (size_t)P * sizeof(int32_t), c->stream));
+    // page-locked scratch for the statistics coming back and the layout going up: [4] stats, [3P] per-pair counters, plan
+    const size_t plan_bytes = (4 + 3 * (size_t)P) * sizeof(int32_t) + (4 * (size_t)P + 8) * sizeof(int64_t) + (5 * (size_t)P + 8) * sizeof(int32_t) + 256;
+    if (host_scratch(c, plan_bytes)) return st.code;
+    int32_t *hs = (int32_t *)c->h_plan, *hist = hs + 4;
+    if (input_stats(c, raws, bytes)) return st.code;
+    ICL_CUDA(st, d2h(hs, c->stats.p, 4 * sizeof(int32_t), c->stream));
+    if (P > 0) ICL_CUDA(st, d2h(hist, c->pair_hist.p, 3 * (size_t)P * sizeof(int32_t), c->stream));
     ICL_CUDA(st, dev_sync(c->stream));
     if (hs[2]) return fail(c, ICL_ERR_ARG, std::string(who) + ": negative coordinate or pair id outside [0, n_pairs)");
     if (hs[0] >= (1 << 26) || hs[1] >= (1 << 26)) return fail(c, ICL_ERR_LIMIT, std::string(who) + ": coordinates must be < 2^26");
@@ -1146,7 +1203,9 @@ __global__ void __launch_bounds__(64) k_chain_ring(ChainArgs A) {
                 const bool up = valid && sc > 0 && tx < cand;                // :87, ignoring the break for now
                 // sweep state before each record: ONE segmented scan over the would-update flags, min(dc) and
                 // max(dr) packed as two 16-bit halves {255 - dc, dr} combined with a per-halfword max; the steps
-                // beyond the longest segment of the round are skipped (warp-uniform)
+                // beyond the longest segment of the round are skipped (warp-uniform).  (Skipping per step — 1, 2, 4 — by
+                // the longest segment of the round was measured and is slower: 0.41 -> 0.47 ms on C2; the nested
+                // uniform branches cost more than the shuffles they save.)
                 uint32_t pk = up ? (((uint32_t)(255 - dc) << 16) | (uint32_t)dr) : 0u;
                 {
                     uint32_t po = __shfl_up_sync(FULLM, pk, 1);
@@ -1608,7 +1667,9 @@ extern "C" int icl_debug_dp(icl_ctx *c, int32_t dir, int32_t *score, int32_t *pr
 // ------------------------------------------------------------------------------------------------
 #define ICL_TREE_SMALL 32           // trees of at most this many used points: one thread each, on global memory
 #define ICL_TREE_CAP 2048            // larger ones up to this size: one warp each, staged in shared memory
-#define ICL_TREE_SMEM (ICL_TREE_CAP * 45 + 64)
+#define ICL_TREE_HUGE 256            // ... the ones above this size in a launch of their own (a power of two, like the cap:
+                                     // the hash of a tree has up to 2 * cap slots)
+#define ICL_TREE_SMEM(cap) ((cap) * 45 + 64)
 // One predecessor tree on global memory: its points are the sorted entries [t0, uend), in rank order.
 struct TreeWalk {
     int64_t n, V;
@@ -1717,12 +1778,15 @@ struct TreeWalk {
 };
 
 #ifndef ICL_EMU
-// heads of the sorted runs (one predecessor tree each) -> the queue of short trees (warp-aggregated push) or of long ones
-__global__ void __launch_bounds__(256) k_tree_heads(TreeWalk W, int2 *smallq, int2 *bigq, int32_t *stats) {
-    const int lane = threadIdx.x & 31;
+// heads of the sorted runs (one predecessor tree each) -> the queue of short trees or of long ones.  The queue of short
+// trees is pushed once per CTA and 256 entries (one atomic on the shared cursor per warp was the whole kernel: 119 k
+// same-address atomics, 65 us on C2).
+__global__ void __launch_bounds__(256) k_tree_heads(TreeWalk W, int2 *smallq, int2 *bigq, int64_t bigcap, int32_t *stats) {
+    __shared__ int32_t wcnt[8], cbase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * 256;
-    for (int64_t b0 = (int64_t)blockIdx.x * 256 + (threadIdx.x & ~31); b0 < W.V; b0 += stride) {
-        const int64_t t0 = b0 + lane;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < W.V; base += stride) {       // (CTA-uniform trip count)
+        const int64_t t0 = base + threadIdx.x;
         // a run ends where the key changes: most runs (a tree holds a few points) end inside the warp's 32 entries, where the
         // ballot of the changes shows the end; only a run that reaches past them is searched (gallop + bisect)
         const uint32_t rt = t0 < W.V ? W.key[t0] : 0xffffffffu;
@@ -1742,14 +1806,20 @@ __global__ void __launch_bounds__(256) k_tree_heads(TreeWalk W, int2 *smallq, in
         const bool big = head && uend - t0 > ICL_TREE_SMALL && uend - t0 <= ICL_TREE_CAP;
         const bool small = head && !big;
         const uint32_t ms = __ballot_sync(0xffffffffu, small);
-        if (ms) {
-            const int leader = __ffs(ms) - 1;
-            int32_t at = 0;
-            if (lane == leader) at = atomicAdd(&stats[3], __popc(ms));
-            at = __shfl_sync(0xffffffffu, at, leader);
-            if (small) smallq[at + __popc(ms & ((1u << lane) - 1u))] = make_int2((int32_t)t0, (int32_t)uend);
+        if (lane == 0) wcnt[warp] = __popc(ms);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const int32_t k = wcnt[w]; wcnt[w] = tot; tot += k; }
+            cbase = tot ? atomicAdd(&stats[3], tot) : 0;
         }
-        if (big) bigq[atomicAdd(&stats[1], 1)] = make_int2((int32_t)t0, (int32_t)uend);
+        __syncthreads();
+        if (small) smallq[cbase + wcnt[warp] + __popc(ms & ((1u << lane) - 1u))] = make_int2((int32_t)t0, (int32_t)uend);
+        // the staged walk lasts as long as its largest tree: the long ones queue from the far end and are taken first
+        if (big) {
+            if (uend - t0 > ICL_TREE_HUGE) bigq[bigcap - 1 - atomicAdd(&stats[4], 1)] = make_int2((int32_t)t0, (int32_t)uend);
+            else bigq[atomicAdd(&stats[1], 1)] = make_int2((int32_t)t0, (int32_t)uend);
+        }
     }
 }
 
@@ -1770,8 +1840,9 @@ struct TreeArgs {
     const int32_t *rank2v;
     const int2 *pd;
     const int32_t *imap, *l1, *l2;
-    const int2 *big;                 // queue of [t0, uend)
-    int32_t *stats;                  // [0] queue head (this kernel), [1] queue length (written by the tree-head pass)
+    const int2 *big;                 // queue of [t0, uend): the longest trees from the far end (slot bigcap - 1 downwards), the others from slot 0
+    int64_t bigcap;
+    int32_t *stats;                  // [0] / [5] queue heads (the two launches), [1] / [4] queue lengths (written by the tree-head pass)
     uint32_t *acc_m, *acc_ms;
     int32_t *acc_L, *mscr;
     int4 *acc_box;
@@ -1783,25 +1854,30 @@ struct TreeArgs {
 // in shared memory: the warp gathers its points once — rank position, forward position, loc2, path length, and the
 // predecessor as an index INTO the tree (through a hash of the tree's points) — and lane 0 then walks tops, paths and
 // members at shared-memory latency instead of one dependent DRAM round trip per hop.
+// Two launches share the code: trees of up to ICL_TREE_HUGE points (11.6 KB of shared memory per warp: the mass of the
+// staged points, spread over 16 warps per SM) and the few longer ones (92 KB per warp, 2 per SM), side by side.  One
+// launch with the large footprint for all of them ran 296 warps for ~1000 points each: 130 us on C2 whatever the
+// largest tree cost.
+template <int CAP, bool HUGE>
 __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
     extern __shared__ __align__(16) unsigned char tsm[];
     int32_t *s_t = (int32_t *)tsm;                             // rank position
-    int32_t *s_f = s_t + ICL_TREE_CAP;                         // forward sorted position of the point
-    int32_t *s_y = s_f + ICL_TREE_CAP;                         // loc2
-    int32_t *s_pl = s_y + ICL_TREE_CAP;                        // predecessor: index into the tree, -1 for the root
-    int32_t *s_L = s_pl + ICL_TREE_CAP;                        // path length
-    int32_t *s_x = s_L + ICL_TREE_CAP;                         // loc1
-    int32_t *s_mm = s_x + ICL_TREE_CAP;                        // per path length L <= N: the smallest m with (double) m / L > cov
-    int2 *s_h = (int2 *)(s_mm + ICL_TREE_CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
-    uint8_t *s_pres = (uint8_t *)(s_h + 2 * ICL_TREE_CAP);
+    int32_t *s_f = s_t + CAP;                         // forward sorted position of the point
+    int32_t *s_y = s_f + CAP;                         // loc2
+    int32_t *s_pl = s_y + CAP;                        // predecessor: index into the tree, -1 for the root
+    int32_t *s_L = s_pl + CAP;                        // path length
+    int32_t *s_x = s_L + CAP;                         // loc1
+    int32_t *s_mm = s_x + CAP;                        // per path length L <= N: the smallest m with (double) m / L > cov
+    int2 *s_h = (int2 *)(s_mm + CAP);                  // 2 * CAP slots: hash {point, index}, later the memo {depth, version}
+    uint8_t *s_pres = (uint8_t *)(s_h + 2 * CAP);
     const int lane = threadIdx.x;
     const uint32_t FULL = 0xffffffffu;
     for (;;) {
         int32_t qi = 0;
-        if (lane == 0) qi = atomicAdd(&T.stats[0], 1);
+        if (lane == 0) qi = atomicAdd(&T.stats[HUGE ? 5 : 0], 1);
         qi = __shfl_sync(FULL, qi, 0);
-        if (qi >= T.stats[1]) break;
-        const int2 rg = T.big[qi];
+        if (qi >= T.stats[HUGE ? 4 : 1]) break;
+        const int2 rg = HUGE ? T.big[T.bigcap - 1 - qi] : T.big[qi];
         const int32_t t0 = rg.x, N = rg.y - rg.x;
         int32_t hsz = 64;
         while (hsz < 2 * N) hsz <<= 1;
@@ -1856,14 +1932,26 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
         if (lane == 0) {
             int32_t ver = 0;                                   // accepted blocks of this tree so far
             uint32_t cursor = (uint32_t)t0;                    // member scratch: the tree's own slice
+            // The walk of a tree is sequential and its time is the kernel's (the largest tree of C2 has 678 points).  The
+            // per-point data that never changes — path length, predecessor, smallest accepted m of that length — is read
+            // two points ahead (the stores to `present` keep the compiler from moving any load up by itself), so an
+            // examined point costs one round of shared-memory latency (present + memo) instead of four.
+            int32_t Ln = s_L[0], pln = s_pl[0];                                // point u + 1 after the shift below
+            int32_t Lnn = N > 1 ? s_L[1] : 1, plnn = N > 1 ? s_pl[1] : -1;     // point u + 2
+            int32_t mmn = (Ln >= 1 && Ln <= N) ? s_mm[Ln - 1] : 0x7fffffff;
             for (int32_t u = 0; u < N; u++) {                  // the tree's points in rank order
-                if (!s_pres[u]) continue;
-                const int32_t L = s_L[u];
+                const int32_t L = Ln, pl = pln, mmL = mmn;
+                Ln = Lnn; pln = plnn;
+                mmn = (Ln >= 1 && Ln <= N) ? s_mm[Ln - 1] : 0x7fffffff;
+                if (u + 2 < N) { Lnn = s_L[u + 2]; plnn = s_pl[u + 2]; }
+                const uint8_t pres = s_pres[u];
+                const int2 memo = s_h[u];
+                if (!pres) continue;
                 int32_t m, q;
                 if (ver == 0) m = L;
-                else if (s_h[u].y == ver) m = L - s_h[u].x;
-                else { m = 1; q = s_pl[u]; while (q >= 0 && s_pres[q]) { m++; q = s_pl[q]; } }
-                if (L >= T.over_gap && L <= N && m >= s_mm[L - 1]) {              // :129
+                else if (memo.y == ver) m = L - memo.x;
+                else { m = 1; q = pl; while (q >= 0 && s_pres[q]) { m++; q = s_pl[q]; } }
+                if (L >= T.over_gap && L <= N && m >= mmL) {                      // :129
                     int32_t l2min = 0x7fffffff, l2max = -1, la = 0, lb = 0;
                     q = u;
                     for (int32_t k = 0; k < m; k++) {
@@ -1886,7 +1974,7 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
                     cursor += (uint32_t)m;
                 } else {
                     s_pres[u] = 0;                             // :143
-                    if (m > 1) s_h[s_pl[u]] = make_int2(L - m, ver);
+                    if (m > 1) s_h[pl] = make_int2(L - m, ver);
                 }
             }
         }
@@ -1965,11 +2053,11 @@ static int phase_extract(icl_ctx *c) {
     cudaStream_t s = c->stream;
     if (c->present.reserve(st, V) || c->key_a.reserve(st, V) || c->key_b.reserve(st, V) || c->idx_a.reserve(st, V) ||
         c->tree_v.reserve(st, V) || c->acc_m.reserve(st, V + 2) || c->acc_L.reserve(st, V) || c->acc_ms.reserve(st, V) ||
-        c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->tri_in.reserve(st, V + 2) ||
-        c->tri.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 4) ||
+        c->acc_box.reserve(st, V) || c->mscr.reserve(st, V) || c->seen.reserve(st, V) || c->bs_in.reserve(st, V + 2) ||
+        c->bs.reserve(st, V + 2) || c->mo_in.reserve(st, V + 2) || c->mo.reserve(st, V + 2) || c->hint.reserve(st, V) || c->stats.reserve(st, 8) ||
         c->big_trees.reserve(st, V / ICL_TREE_SMALL + 2) || c->small_trees.reserve(st, V + 2))
         return st.code;
-    ICL_CUDA(st, dev_memset(c->stats.p, 0, 4 * sizeof(int32_t), s));
+    ICL_CUDA(st, dev_memset(c->stats.p, 0, 8 * sizeof(int32_t), s));
     if (!c->order_on_device_used) {                            // (a device order initialises these in its key pass below)
         ICL_CUDA(st, dev_memset(c->acc_m.p, 0, (size_t)(V + 2) * sizeof(uint32_t), s));
         ICL_CUDA(st, dev_memset(c->hint.p, 0xFF, (size_t)V * sizeof(int2), s));
@@ -1981,9 +2069,20 @@ static int phase_extract(icl_ctx *c) {
     int32_t *stats = c->stats.p;
     // Rank positions are item-major and already in examination order, so a STABLE sort by tree root alone
     // groups every predecessor tree with its points in rank order.  Unused points sort behind everything.
-    const int vb = bits_for(V);
+    // The sort key is the root's position INSIDE its item (as many bits as the largest pair needs: 2 radix passes instead
+    // of 3 on C2, 2 instead of 4 on C4): equal keys of different items stay item-major — the sort is stable — so every
+    // (item, root) run is still contiguous and in rank order; the pass behind the sort turns the keys back into roots.
+    // (Trees then come out ordered by position-inside-the-item first: neighbouring threads of the short-tree walk work on
+    // different items and lose their shared cache lines — 93 -> 130 us on C2 — so the short key is used only where it
+    // saves two passes or more.)
+    int64_t maxnp = 1;
+    for (int32_t p = 0; p < P; p++) maxnp = std::max<int64_t>(maxnp, c->h_pair_off[p + 1] - c->h_pair_off[p]);
+    const bool rel = (bits_for(V) + 7) / 8 - (bits_for(maxnp) + 7) / 8 >= 2;
+    const int vb = rel ? bits_for(maxnp) : bits_for(V);
+    const uint32_t unused_key = rel ? (uint32_t)maxnp : (uint32_t)V;
+    const int64_t *seg_off = c->d_seg_off.p;
     {
-        uint32_t *key = (uint32_t *)c->key_a.p;                  // tree root < V < 2^31: 32-bit keys
+        uint32_t *key = (uint32_t *)c->key_a.p;                  // position inside the item < 2^24: 32-bit keys
         uint32_t *idx = c->idx_a.p;
         uint8_t *seen = c->seen.p;
         if (c->order_on_device_used) {
@@ -2006,25 +2105,35 @@ static int phase_extract(icl_ctx *c) {
                 const int32_t v = rev ? mmap[f] : (int32_t)f;
                 r2v[t] = v;
                 idx[t] = (uint32_t)t;
-                key[t] = used[v] ? (uint32_t)root[v] : (uint32_t)V;
+                key[t] = used[v] ? (uint32_t)(root[v] - (rel ? (rev ? n : 0) + a : 0)) : unused_key;
                 acc_m[t] = 0u;
                 hint[t] = make_int2(-1, -1);
                 present[t] = used[t];
             }));
         } else {
             ICL_CUDA(st, dev_memset(c->seen.p, 0, (size_t)V, s));
+            const int32_t *itemof = c->itemof.p;
             ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t t) {
                 idx[t] = (uint32_t)t;
                 const int32_t v = rank2v[t];
-                if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = (uint32_t)V; return; }   // not a permutation
+                if (v < 0 || v >= V || seen[v]) { atomic_or_i32(&stats[2], 1); key[t] = unused_key; return; }   // not a permutation
                 seen[v] = 1;
-                key[t] = used[v] ? (uint32_t)root[v] : (uint32_t)V;
+                key[t] = used[v] ? (uint32_t)(root[v] - (rel ? seg_off[itemof[t]] : 0)) : unused_key;   // (v lies in the item of t by construction)
             }));
             // a duplicate may slip through the unsynchronised test above, but then some point is never seen
             ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t v) { if (!seen[v]) atomic_or_i32(&stats[2], 1); }));
         }
     }
     if (V > 0 && radix_sort_pairs32(st, c->tmp, (uint32_t *)c->key_a.p, (uint32_t *)c->key_b.p, c->idx_a.p, c->tree_v.p, V, vb, s)) return st.code;
+    if (rel) {
+        uint32_t *key = (uint32_t *)c->key_b.p;
+        const uint32_t *tpos = c->tree_v.p;
+        const int32_t *itemof = c->itemof.p;
+        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t j) {
+            const uint32_t k = key[j];
+            key[j] = k == unused_key ? (uint32_t)V : (uint32_t)(seg_off[itemof[tpos[j]]] + k);
+        }));
+    }
     {
         const uint32_t *key = (const uint32_t *)c->key_b.p;
         const uint32_t *tpos = c->tree_v.p;            // rank position of every sorted entry
@@ -2052,44 +2161,57 @@ static int phase_extract(icl_ctx *c) {
             // tree heads -> two queues: trees of at most ICL_TREE_SMALL points (one thread each: compacted, so that every
             // lane of a warp has a tree to walk) and longer ones (one warp each, staged in shared memory)
             int2 *smallq = c->small_trees.p;
-            k_tree_heads<<<148 * 8, 256, 0, s>>>(W, smallq, big, stats);
+            const int64_t bigcap = V / ICL_TREE_SMALL + 2;
+            k_tree_heads<<<148 * 8, 256, 0, s>>>(W, smallq, big, bigcap, stats);
             ICL_COUNT_KERNEL();
             // the two walks touch different trees: the staged one (few long trees, one warp each) runs beside the short
             // ones on the side stream
             ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));
             ICL_CUDA(st, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-            TreeArgs T{n, V, key, tpos, rank2v, pd, imap, l1, l2, big, stats, acc_m, acc_ms, acc_L, mscr, acc_box, over_gap, cov};
-            ICL_CUDA(st, cudaFuncSetAttribute(k_tree_walk_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, ICL_TREE_SMEM));
-            k_tree_walk_staged<<<148 * 2, 32, ICL_TREE_SMEM, c->stream2>>>(T);
+            ICL_CUDA(st, cudaStreamWaitEvent(c->stream3, c->ev_fork, 0));
+            TreeArgs T{n, V, key, tpos, rank2v, pd, imap, l1, l2, big, bigcap, stats, acc_m, acc_ms, acc_L, mscr, acc_box, over_gap, cov};
+            ICL_CUDA(st, cudaFuncSetAttribute(k_tree_walk_staged<ICL_TREE_CAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              ICL_TREE_SMEM(ICL_TREE_CAP)));
+            k_tree_walk_staged<ICL_TREE_CAP, true><<<148 * 2, 32, ICL_TREE_SMEM(ICL_TREE_CAP), c->stream2>>>(T);
             ICL_COUNT_KERNEL();
+            k_tree_walk_staged<ICL_TREE_HUGE, false><<<148 * 16, 32, ICL_TREE_SMEM(ICL_TREE_HUGE), c->stream3>>>(T);
+            ICL_COUNT_KERNEL();
+            ICL_CUDA(st, cudaEventRecord(c->ev_join3, c->stream3));
             ICL_CUDA(st, cudaEventRecord(c->ev_join, c->stream2));
             k_tree_walk_small<<<148 * 16, 128, 0, s>>>(W, smallq, stats);
             ICL_COUNT_KERNEL();
             ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join, 0));
+            ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join3, 0));
             ICL_CUDA(st, cudaGetLastError());
         }
 #endif
     }
     // Emission order (run_colliearity.py:118, collinearity.py:49-68): chromosome pair ascending, forward blocks before
     // anti-diagonal ones, acceptance order = rank order inside a direction.  Rank positions are direction-major (V space),
-    // so the accepted positions are counted in the pair-major order t' -> t of emission_pos(): ONE scan numbers every
-    // accepted block, every block the caller wants (m >= min_members) and the gene pairs of those, all in emission order.
+    // so the accepted positions are counted in the pair-major order t' -> t of emission_pos(): prefix sums number every
+    // accepted block and every block the caller wants (m >= min_members; two 32-bit counts in one word) and the gene pairs
+    // of those, all in emission order.
     {
         const uint32_t *acc_m = c->acc_m.p;
         const int32_t *ps = c->pair_s.p;
         const int64_t *off = c->d_pair_off.p;
-        Tri *in = c->tri_in.p;
+        uint64_t *bs_in = c->bs_in.p;
+        uint32_t *mo_in = c->mo_in.p;
         const uint32_t minm = (uint32_t)(c->min_members < 1 ? 1 : c->min_members);
         ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t e) {
             const uint32_t m = acc_m[emission_pos(e, n, ps, off)];
             const bool want = m >= minm;
-            in[e] = Tri{m ? 1u : 0u, want ? 1u : 0u, want ? m : 0u};
+            bs_in[e] = ((uint64_t)(m ? 1u : 0u) << 32) | (want ? 1u : 0u);
+            mo_in[e] = want ? m : 0u;
         }));
     }
-    if (exclusive_sum_tri(st, c->tmp, c->tri_in.p, c->tri.p, V, s)) return st.code;
-    Tri tot = {0u, 0u, 0u};
+    if (exclusive_sum_u64(st, c->tmp, c->bs_in.p, c->bs.p, V, s)) return st.code;
+    if (exclusive_sum_u32(st, c->tmp, c->mo_in.p, c->mo.p, V, s)) return st.code;
+    uint64_t tot_bs = 0;
+    uint32_t tot_m = 0;
     int32_t hs[4] = {0, 0, 0, 0};
-    ICL_CUDA(st, d2h(&tot, c->tri.p + V, sizeof(Tri), s));
+    ICL_CUDA(st, d2h(&tot_bs, c->bs.p + V, sizeof(uint64_t), s));
+    ICL_CUDA(st, d2h(&tot_m, c->mo.p + V, sizeof(uint32_t), s));
     ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), s));
     int32_t rank_any = 0;                                      // hand-back flag icl_rank_device left unread (no sync there)
     if (c->rank_flag_pending && c->order_on_device_used)
@@ -2098,9 +2220,9 @@ static int phase_extract(icl_ctx *c) {
     c->rank_flag_pending = false;
     if (rank_any) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
     if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_extract: argsort array is not a permutation of its pair segment");
-    c->NB = tot.b;
-    c->NBo = tot.s;
-    c->NMo = tot.m;
+    c->NB = (int64_t)(tot_bs >> 32);
+    c->NBo = (int64_t)(uint32_t)tot_bs;
+    c->NMo = tot_m;
     const int64_t NB = c->NB, NBo = c->NBo, NMo = c->NMo;
     if (c->b_j0.reserve(st, NB) || c->b_j1.reserve(st, NB) || c->b_l2min.reserve(st, NB) || c->b_l2max.reserve(st, NB) ||
         c->b_N.reserve(st, NB) || c->b_N1.reserve(st, NB) || c->o_src.reserve(st, NBo + 1) || c->o_ms.reserve(st, NBo + 1))
@@ -2110,7 +2232,8 @@ static int phase_extract(icl_ctx *c) {
         // one thread per accepted block: the row slice of its bounding box for the times / p-value pass, and — for a
         // block the caller gets — its output record (everything but N, N1 and the p value, which follow that pass)
         const uint32_t *acc_m = c->acc_m.p, *acc_ms = c->acc_ms.p;
-        const Tri *tri = c->tri.p;
+        const uint64_t *bs = c->bs.p;
+        const uint32_t *mo = c->mo.p;
         const int32_t *acc_L = c->acc_L.p, *rowptr = c->rowptr.p, *S = c->S.p, *ps = c->pair_s.p;
         const int4 *acc_box = c->acc_box.p;
         const int32_t *rmin = c->d_rmin.p;
@@ -2126,8 +2249,8 @@ static int phase_extract(icl_ctx *c) {
             const int64_t t = emission_pos(e, n, ps, off);
             const uint32_t m = acc_m[t];
             if (!m) return;
-            const Tri at = tri[e];
-            const uint32_t b = at.b;
+            const uint64_t at = bs[e];
+            const uint32_t b = (uint32_t)(at >> 32);
             const int4 box = acc_box[t];
             b_N[b] = 0;                                                         // (the p-value pass adds into these)
             b_N1[b] = 0;
@@ -2136,7 +2259,7 @@ static int phase_extract(icl_ctx *c) {
             b_j0[b] = rowptr[rb_[p] + (box.x - rmin[p])];
             b_j1[b] = rowptr[rb_[p] + (box.y - rmin[p]) + 1];
             if (m < minm) return;
-            const uint32_t g = at.s;
+            const uint32_t g = (uint32_t)at;
             o_src[g] = b;
             o_ms[g] = acc_ms[t];
             o.pair[g] = p;
@@ -2146,7 +2269,7 @@ static int phase_extract(icl_ctx *c) {
             o.L[g] = acc_L[t];
             o.L1[g] = box.y - box.x + 1;
             o.L2[g] = box.w - box.z + 1;
-            o.member_off[g] = at.m;
+            o.member_off[g] = mo[e];
         }));
         if (V == 0) ICL_CUDA(st, dev_memset(c->dv.member_off, 0, sizeof(int64_t), s));
     }
@@ -2211,7 +2334,8 @@ struct PvalArgs {
     int32_t P, g0, smem_cap;
     const int32_t *pair_order, *l2, *b_j0, *b_j1, *b_l2min, *b_l2max;
     const int64_t *off;
-    const Tri *tri;                  // .b: accepted blocks before an emission position (pair p: forward blocks from 2 off[p], anti-diagonal from 2 off[p] + np)
+    const uint64_t *bs;              // high word: accepted blocks before an emission position (pair p: forward blocks from 2 off[p], anti-diagonal from 2 off[p] + np)
+    ICL_HD uint32_t blocks_before(int64_t e) const { return (uint32_t)(bs[e] >> 32); }
     int32_t *times, *b_N;
     int64_t *b_N1;
 };
@@ -2232,7 +2356,7 @@ __device__ __forceinline__ void pvalue_pair(const PvalArgs &A, int32_t p, uint16
     __syncwarp();
     volatile int32_t *tg = A.times;
     for (int d = 0; d < 2; d++) {
-        const uint32_t b0 = A.tri[2 * a + d * np_].b, b1 = A.tri[2 * a + (d + 1) * np_].b;
+        const uint32_t b0 = A.blocks_before(2 * a + d * np_), b1 = A.blocks_before(2 * a + (d + 1) * np_);
         // block records are fetched 32 at a time (one per lane, coalesced) and handed out by shuffle
         int32_t rj0 = 0, rj1 = 0, rlo = 0, rhi = 0;
         if (b0 + lane < b1) { rj0 = A.b_j0[b0 + lane]; rj1 = A.b_j1[b0 + lane]; rlo = A.b_l2min[b0 + lane]; rhi = A.b_l2max[b0 + lane]; }
@@ -2276,7 +2400,7 @@ __global__ void __launch_bounds__(32) k_pvalue(PvalArgs A, int32_t l2_cap) {
     extern __shared__ __align__(16) unsigned char psm[];
     const int32_t p = A.pair_order[blockIdx.x];
     const int64_t np_ = A.off[p + 1] - A.off[p];
-    const uint32_t nb = A.tri[2 * A.off[p + 1]].b - A.tri[2 * A.off[p]].b;
+    const uint32_t nb = A.blocks_before(2 * A.off[p + 1]) - A.blocks_before(2 * A.off[p]);
     if (nb == 0) return;
     uint16_t *tsm = (uint16_t *)psm;
     int32_t *l2sm = (int32_t *)(psm + (((size_t)A.smem_cap * 2 + 15) & ~(size_t)15));
@@ -2301,7 +2425,7 @@ __global__ void __launch_bounds__(1024) k_pvalue_owned(PvalArgs A) {
     extern __shared__ __align__(16) unsigned char psm[];
     const int32_t p = A.pair_order[blockIdx.x];
     const int64_t a = A.off[p], np_ = A.off[p + 1] - a;
-    const uint32_t bf0 = A.tri[2 * a].b, bf1 = A.tri[2 * a + np_].b, br0 = bf1, br1 = A.tri[2 * a + 2 * np_].b;
+    const uint32_t bf0 = A.blocks_before(2 * a), bf1 = A.blocks_before(2 * a + np_), br0 = bf1, br1 = A.blocks_before(2 * a + 2 * np_);
     if (bf1 - bf0 + br1 - br0 == 0) return;
     uint32_t *tsm = (uint32_t *)psm;                           // TS: one counter per point of the pair
     int32_t *l2sm = (int32_t *)(psm + (((size_t)np_ * 4 + 15) & ~(size_t)15));
@@ -2442,7 +2566,7 @@ static int phase_pvalue(icl_ctx *c) {
     A.n = n; A.P = P; A.g0 = c->prm.g0;
     A.pair_order = c->d_pair_order.p; A.l2 = c->loc2s.p;
     A.b_j0 = c->b_j0.p; A.b_j1 = c->b_j1.p; A.b_l2min = c->b_l2min.p; A.b_l2max = c->b_l2max.p;
-    A.off = c->d_pair_off.p; A.tri = c->tri.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p;
+    A.off = c->d_pair_off.p; A.bs = c->bs.p; A.times = c->times.p; A.b_N = c->b_N.p; A.b_N1 = c->b_N1.p;
     if (P == 0) return 0;
     // Small pairs (times and loc2 of the pair fit in shared memory, few blocks per pair) are fastest on the
     // sequential warp-per-pair kernel; large pairs serialise there and take the order-free incidence path.
@@ -2483,7 +2607,7 @@ static int phase_pvalue(icl_ctx *c) {
         int64_t a = A.off[p], np_ = A.off[p + 1] - a;
         for (int64_t i = 0; i < np_; i++) A.times[a + i] = 1;
         for (int d = 0; d < 2; d++) {
-            uint32_t b0 = A.tri[2 * a + d * np_].b, b1 = A.tri[2 * a + (d + 1) * np_].b;
+            uint32_t b0 = A.blocks_before(2 * a + d * np_), b1 = A.blocks_before(2 * a + (d + 1) * np_);
             for (uint32_t b = b0; b < b1; b++) {
                 int32_t N = 0, lo = A.b_l2min[b], hi = A.b_l2max[b];
                 int64_t N1 = 0;
