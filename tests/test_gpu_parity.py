@@ -804,3 +804,12 @@ def test_typed_upload_equals_int32_upload(gpu_engine):
     assert e.value.code == -4
     assert gpu_engine.lib.icl_upload_typed(gpu_engine.ctx, 2, 1, big[1].ctypes.data, 3, big[1].ctypes.data, 1, big[2].ctypes.data, 1,
                                            big[1].ctypes.data, 1) == -1              # element size 3
+
+
+@pytest.mark.gpu
+def test_min_members_selection_is_a_filter(gpu_engine):
+    """Full C2 size: the output for min_members = 5 (what the file writer takes) is the full result filtered."""
+    from test_host_logic import _assert_selection_is_a_filter
+    from bench import make_points, params_for
+    pts = make_points("C2")
+    _assert_selection_is_a_filter(gpu_engine, pts, params_for(pts["cfg"]), 5)

@@ -525,3 +525,34 @@ def test_place_blocks_equals_merge_blocks():
     for f in shard.BLOCK_FIELDS:
         n = len(getattr(exp, f))
         assert (out[f][:n] == getattr(exp, f)).all(), f
+
+
+def _assert_selection_is_a_filter(eng, pts, prm, min_members):
+    """The blocks returned for `min_members` are exactly the full result with the smaller blocks dropped — same order,
+    same fields (N / N1 / p still count every accepted block, collinearity.py:150), same gene pairs."""
+    full = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm, min_members=1)
+    part = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm, min_members=min_members)
+    keep = np.flatnonzero(full.m >= min_members)
+    assert 0 < len(keep) < len(full) and len(part) == len(keep)
+    for f in ("pair", "dir", "score", "m", "L", "N", "N1", "L1", "L2", "p_raw"):
+        assert (getattr(part, f) == getattr(full, f)[keep]).all(), f
+    assert (np.diff(part.member_off) == part.m).all() and part.member_off[0] == 0
+    sel = np.concatenate([np.arange(full.member_off[b], full.member_off[b + 1]) for b in keep])
+    for f in ("loc1", "loc2", "member_idx"):
+        assert (getattr(part, f) == getattr(full, f)[sel]).all(), f
+    # emission order: pair ascending, forward before anti-diagonal inside a pair (run_colliearity.py:118, collinearity.py:49-68)
+    order = part.pair.astype(np.int64) * 2 + part.dir
+    assert (np.diff(order) >= 0).all()
+
+
+def test_min_members_selection_is_a_filter_emu(emu_backend):
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    ds = synth.make_dataset("tiny")
+    pts = synth.graded_points(ds)
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        for mm in (4, 5, 9):
+            _assert_selection_is_a_filter(eng, pts, ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)), mm)
+    finally:
+        eng.close()
