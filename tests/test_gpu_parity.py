@@ -813,3 +813,48 @@ def test_min_members_selection_is_a_filter(gpu_engine):
     from bench import make_points, params_for
     pts = make_points("C2")
     _assert_selection_is_a_filter(gpu_engine, pts, params_for(pts["cfg"]), 5)
+
+
+def _random_pairs_points(n_pairs, n_points, span, seed, offset=0):
+    """Short diagonals and noise spread over many chromosome pairs (some pairs stay empty)."""
+    rng = np.random.default_rng(seed)
+    pair = rng.integers(0, n_pairs, n_points // 8, dtype=np.int64)
+    start1 = rng.integers(1, span, len(pair))
+    start2 = rng.integers(1, span, len(pair))
+    sign = rng.choice([-1, 1], len(pair))
+    k = np.arange(6)
+    p = np.repeat(pair, 6)
+    l1 = (start1[:, None] + k[None, :]).ravel()
+    l2 = (start2[:, None] + sign[:, None] * k[None, :]).ravel()
+    nz = n_points - len(p)
+    p = np.r_[p, rng.integers(0, n_pairs, nz)]
+    l1 = np.r_[l1, rng.integers(1, span, nz)]
+    l2 = np.r_[l2, rng.integers(1, span, nz)]
+    ok = l2 > 0
+    g = rng.choice([50, 30, 25], len(p))[ok]
+    return dict(pair_id=p[ok].astype(np.int32), loc1=(l1[ok] + offset).astype(np.int32), loc2=(l2[ok] + offset).astype(np.int32),
+                grading=g.astype(np.int32), n_pairs=n_pairs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["many_pairs", "wide_keys"])
+def test_upload_layout_paths(gpu_engine, case):
+    """The layout planned at upload, on its two other paths: more pairs than the shared-memory histogram of the validation
+    pass holds (2048: per-pair counters by global atomics) and coordinates that need 64-bit sort keys (loc up to 2^26 - 1);
+    blocks against the oracle, layout against a numpy sort."""
+    from wgdi_b200.engine import ChainParams
+    if case == "many_pairs":
+        pts = _random_pairs_points(2600, 60000, 400, 11)
+    else:
+        pts = _random_pairs_points(300, 40000, 900, 12, offset=(1 << 26) - 1000)
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    blocks = gpu_engine.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+    off, perm = gpu_engine.layout()
+    assert (off == np.r_[0, np.cumsum(np.bincount(pts["pair_id"], minlength=pts["n_pairs"]))]).all()
+    assert (perm == np.lexsort((pts["loc2"], pts["loc1"], pts["pair_id"]))).all()          # stable: ties keep upload order
+    exp = oracle_blocks(pts, prm)
+    assert len(exp) == len(blocks) and len(blocks) > 100
+    for b, (pair, d, l1, l2, a, sc) in enumerate(exp):
+        a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
+        assert blocks.pair[b] == pair and blocks.dir[b] == d and blocks.score[b] == sc and blocks.p_raw[b] == a
+        assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all()

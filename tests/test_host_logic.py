@@ -556,3 +556,27 @@ def test_min_members_selection_is_a_filter_emu(emu_backend):
             _assert_selection_is_a_filter(eng, pts, ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)), mm)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("case", ["many_pairs", "wide_keys"])
+def test_upload_layout_paths_emu(emu_backend, case):
+    """Host logic of the layout planned at upload (pair offsets, dense row ranges, item order) with many pairs / 64-bit keys."""
+    from conftest import oracle_blocks
+    from test_gpu_parity import _random_pairs_points
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = _random_pairs_points(2600, 20000, 300, 21) if case == "many_pairs" else _random_pairs_points(40, 8000, 500, 22, offset=(1 << 26) - 600)
+    prm = ChainParams(mg1=25, mg2=25, grading=(50, 30, 25))
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        blocks = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm)
+        off, perm = eng.layout()
+    finally:
+        eng.close()
+    assert (off == np.r_[0, np.cumsum(np.bincount(pts["pair_id"], minlength=pts["n_pairs"]))]).all()
+    assert (perm == np.lexsort((pts["loc2"], pts["loc1"], pts["pair_id"]))).all()
+    exp = oracle_blocks(pts, prm)
+    assert len(exp) == len(blocks) and len(blocks) > 50
+    for b, (pair, d, l1, l2, a, sc) in enumerate(exp):
+        a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
+        assert blocks.pair[b] == pair and blocks.dir[b] == d and blocks.score[b] == sc and blocks.p_raw[b] == a
+        assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all()

@@ -124,6 +124,8 @@ struct icl_ctx {
     Buf<uint8_t> d_stage;
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0;
+    uint64_t *h_small = nullptr;     // page-locked words for the counts a phase reads back (copies into stack variables are
+                                     // staged by the driver and block the host once each)
     uint8_t *h_plan = nullptr;       // page-locked scratch of the upload: statistics down, layout up
     size_t h_plan_cap = 0;
 
@@ -382,6 +384,12 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
 #endif
+#ifndef ICL_EMU
+    if (cudaHostAlloc((void **)&c->h_small, 64 * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) c->h_small = nullptr;
+#else
+    c->h_small = (uint64_t *)malloc(64 * sizeof(uint64_t));
+#endif
+    if (!c->h_small) { g_create_error = "icl_create: no page-locked host memory"; delete c; return ICL_ERR_CUDA; }
     if (c->stats.reserve(c->st, 8)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
     const char *pvm = getenv("ICL_B200_PVALUE");
@@ -416,7 +424,9 @@ extern "C" void icl_destroy(icl_ctx *c) {
 #ifndef ICL_EMU
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_plan) cudaFreeHost(c->h_plan);
+    if (c->h_small) cudaFreeHost(c->h_small);
 #else
+    free(c->h_small);
     free(c->h_stage);
     free(c->h_plan);
 #endif
@@ -941,9 +951,11 @@ static int phase_edges(icl_ctx *c) {
                     if (seg_off[it + 1] > a) eoff[a] = tile_dst[a >> 8] + first_local[it];
                 }));
             }
-            ICL_CUDA(st, d2h(&total, cursor, sizeof(uint64_t), s));
-            ICL_CUDA(st, d2h(&span, c->stats.p + 3, sizeof(int32_t), s));
+            ICL_CUDA(st, d2h(&c->h_small[0], cursor, sizeof(uint64_t), s));
+            ICL_CUDA(st, d2h(&c->h_small[1], c->stats.p + 3, sizeof(int32_t), s));
             ICL_CUDA(st, dev_sync(s));
+            total = c->h_small[0];
+            span = *(const int32_t *)&c->h_small[1];
             if (total <= want) break;
             want = total + total / 8 + 4096;                   // enumerate again into pools that hold everything
         }
@@ -2207,16 +2219,18 @@ static int phase_extract(icl_ctx *c) {
     }
     if (exclusive_sum_u64(st, c->tmp, c->bs_in.p, c->bs.p, V, s)) return st.code;
     if (exclusive_sum_u32(st, c->tmp, c->mo_in.p, c->mo.p, V, s)) return st.code;
-    uint64_t tot_bs = 0;
-    uint32_t tot_m = 0;
-    int32_t hs[4] = {0, 0, 0, 0};
-    ICL_CUDA(st, d2h(&tot_bs, c->bs.p + V, sizeof(uint64_t), s));
-    ICL_CUDA(st, d2h(&tot_m, c->mo.p + V, sizeof(uint32_t), s));
-    ICL_CUDA(st, d2h(hs, c->stats.p, sizeof(hs), s));
-    int32_t rank_any = 0;                                      // hand-back flag icl_rank_device left unread (no sync there)
-    if (c->rank_flag_pending && c->order_on_device_used)
-        ICL_CUDA(st, d2h(&rank_any, c->host_flag.p + c->rank_flag_slot, sizeof(int32_t), s));
+    // (read back through page-locked words: [0] blocks << 32 | wanted, [1] gene pairs, [2..3] stats, [4] rank hand-back flag)
+    c->h_small[4] = 0;
+    ICL_CUDA(st, d2h(&c->h_small[0], c->bs.p + V, sizeof(uint64_t), s));
+    ICL_CUDA(st, d2h(&c->h_small[1], c->mo.p + V, sizeof(uint32_t), s));
+    ICL_CUDA(st, d2h(&c->h_small[2], c->stats.p, 4 * sizeof(int32_t), s));
+    if (c->rank_flag_pending && c->order_on_device_used)       // hand-back flag icl_rank_device left unread (no sync there)
+        ICL_CUDA(st, d2h(&c->h_small[4], c->host_flag.p + c->rank_flag_slot, sizeof(int32_t), s));
     ICL_CUDA(st, dev_sync(s));
+    const uint64_t tot_bs = c->h_small[0];
+    const uint32_t tot_m = *(const uint32_t *)&c->h_small[1];
+    const int32_t *hs = (const int32_t *)&c->h_small[2];
+    const int32_t rank_any = *(const int32_t *)&c->h_small[4];
     c->rank_flag_pending = false;
     if (rank_any) return fail(c, ICL_ERR_STATE, "icl_rank_device: a segment needs the host rank (std::sort depth limit)");
     if (hs[2]) return fail(c, ICL_ERR_ARG, "icl_extract: argsort array is not a permutation of its pair segment");
