@@ -540,6 +540,7 @@ def main():
     # the host rank (numpy's argsort) is per-rank host work: split the box's cores between the ranks
     sort_threads = int(os.environ.get("ICL_BENCH_SORT_THREADS", 0)) or max(1, (os.cpu_count() or 1) // world)
     eng = IclEngine(local, sort_threads=sort_threads)
+    eng.fields = "writer"      # like the drop-in driver: what the collinearity file is written from comes back (icl_extract_fields)
     # inputs in page-locked host memory (the e2e leg copies them every step)
     # (in the narrowest element types that hold them, as the drop-in driver hands them over: params.compact_points)
     from wgdi_b200.params import compact_points
@@ -730,10 +731,12 @@ def main():
         streamed = bool(getattr(eng, "stream_rank", False)) and counters["chain_kernel"] == "ring" and not on_device
         bytes_pp = DP_BYTES_PER_POINT + (EXPORT_BYTES_PER_POINT if streamed else 0)
         achieved = bytes_pp * n_local / (chain_ms * 1e-3) / 1e9
-        # bytes that cross PCIe per e2e step: points in (4 int32 arrays); blocks out (64 B per block + 12 B per member) plus
-        # one flag per segment; with the host ranking also the score keys out (2 x 4 B per point: streamed by the DP kernel)
-        # and the argsort back in (2 x 4 B per point)
-        d2h = int(len(blocks) * 64 + len(blocks.loc1) * 12) + (8 * int(mine["n_pairs"]) if on_device else 8 * n_local)
+        # bytes that cross PCIe per e2e step: points in (the four arrays as handed over); blocks out — counted from the arrays
+        # that came back (field set "writer": 32 B per block + 8 B per gene pair; "all": 60 + 12) — plus the counts; with
+        # the host ranking also the score keys out (2 x 4 B per point: streamed by the DP kernel) and the argsort back in
+        from dataclasses import fields as dc_fields
+        d2h = sum(int(getattr(blocks, f.name).nbytes) for f in dc_fields(blocks) if getattr(blocks, f.name) is not None) + 64 + \
+            (0 if on_device else 8 * n_local)
         h2d = sum(int(v.nbytes) for v in host_in.values()) + (0 if on_device else 8 * n_local)
         line = {
             "metric": METRIC, "value": total_points * args.steps / t_res, "unit": "hits/s", "n_gpus": world,
@@ -744,6 +747,8 @@ def main():
                        "graded_hits": total_points, "chromosome_pairs": total_pairs, "blocks": n_blocks,
                        "mg": list(mine["cfg"].mg), "grading": list(mine["cfg"].grading),
                        "parallelism": f"chromosome pairs LPT-sharded over {world} GPU(s), no collective",
+                       "output": f"field set '{eng.fields}' of icl_extract_fields: " + ("pair, score, m, p_raw, member_off, loc1, loc2 "
+                                  "(what wgdi/run_colliearity.py:143-155,174-199 writes the file from)" if eng.fields == "writer" else "every array of icl_blocks"),
                        "l2": "flushed between steps (256 MiB memset, untimed); working set also exceeds L2",
                        "tie_order": (f"this process's numpy argsort ({eng.numpy_sort_kind()}) reproduced exactly on the device, checked against numpy at start-up: reference-exact"
                                      if getattr(eng, "rank_mode", "") == "auto" and hasattr(eng, "numpy_sort_kind") and eng.numpy_sort_kind()

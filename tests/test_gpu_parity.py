@@ -858,3 +858,11 @@ def test_upload_layout_paths(gpu_engine, case):
         a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
         assert blocks.pair[b] == pair and blocks.dir[b] == d and blocks.score[b] == sc and blocks.p_raw[b] == a
         assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all()
+
+
+@pytest.mark.gpu
+def test_writer_field_set(gpu_engine):
+    from test_host_logic import _assert_writer_fields
+    from bench import make_points, params_for
+    pts = make_points("C2")
+    _assert_writer_fields(gpu_engine, pts, params_for(pts["cfg"]))

@@ -580,3 +580,31 @@ def test_upload_layout_paths_emu(emu_backend, case):
         a0, a1 = blocks.member_off[b], blocks.member_off[b + 1]
         assert blocks.pair[b] == pair and blocks.dir[b] == d and blocks.score[b] == sc and blocks.p_raw[b] == a
         assert (blocks.loc1[a0:a1] == l1).all() and (blocks.loc2[a0:a1] == l2).all()
+
+
+def _assert_writer_fields(eng, pts, prm):
+    """icl_extract_fields(ICL_FIELDS_WRITER): the arrays the file is written from are those of the full result, the others
+    do not come back."""
+    eng.fields = "all"
+    full = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm, min_members=5)
+    eng.fields = "writer"
+    try:
+        lean = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm, min_members=5)
+    finally:
+        eng.fields = "all"
+    assert len(lean) == len(full) > 0
+    for f in ("pair", "score", "m", "p_raw", "member_off", "loc1", "loc2"):
+        assert (getattr(lean, f) == getattr(full, f)).all(), f
+    for f in ("dir", "L", "N", "N1", "L1", "L2", "member_idx"):
+        assert getattr(lean, f) is None and getattr(full, f) is not None, f
+
+
+def test_writer_field_set_emu(emu_backend):
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams, IclEngine
+    pts = synth.graded_points(synth.make_dataset("tiny"))
+    eng = IclEngine(0, sort_threads=2)
+    try:
+        _assert_writer_fields(eng, pts, ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))
+    finally:
+        eng.close()

@@ -60,6 +60,7 @@ def _declare(lib):
     lib.icl_debug_rank_keys.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.icl_debug_keys.argtypes = [vp, vp]
     lib.icl_extract.argtypes = [vp, vp, vp, i32, C.POINTER(icl_blocks)]
+    lib.icl_extract_fields.argtypes = [vp, vp, vp, i32, i32, C.POINTER(icl_blocks)]
     lib.icl_free_blocks.argtypes = [C.POINTER(icl_blocks)]
     lib.icl_free_blocks.restype = None
     lib.icl_debug_dp.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -71,7 +72,7 @@ def _declare(lib):
 
 
 EXPORTS = ("icl_backend", "icl_create", "icl_destroy", "icl_last_error", "icl_host_alloc", "icl_host_free",
-           "icl_upload", "icl_upload_typed", "icl_set_grading_table", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_debug_rank_keys", "icl_debug_keys", "icl_extract", "icl_free_blocks", "icl_debug_dp", "icl_timings",
+           "icl_upload", "icl_upload_typed", "icl_set_grading_table", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_debug_rank_keys", "icl_debug_keys", "icl_extract", "icl_extract_fields", "icl_free_blocks", "icl_debug_dp", "icl_timings",
            "icl_counters", "icl_stream")
 
 

@@ -118,9 +118,10 @@ struct icl_ctx {
     Buf<int32_t> b_j0, b_j1, b_l2min, b_l2max, b_N;    // per accepted block, emission order: what the times / p-value pass needs
     Buf<int64_t> b_N1;
     // output staging (blocks the caller gets, emission order)
-    Buf<uint32_t> o_src, o_ms;       // accepted-block index and member scratch slice of every output block
+    Buf<uint32_t> o_src, o_ms, o_e;  // accepted-block index, member scratch slice and emission position of every output block
     icl_blocks dv{}, hv{};           // views into d_stage and into the pinned host staging (same layout)
-    size_t stage_members_at = 0, stage_bytes = 0;
+    size_t stage_members_at = 0, stage_bytes = 0, stage_blocks_lean_end = 0, stage_members_lean_end = 0;
+    int32_t out_fields = 0;          // ICL_FIELDS_* of the current icl_extract_fields
     Buf<uint8_t> d_stage;
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0;
@@ -419,7 +420,7 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->b_j1.release(); c->b_l2min.release(); c->b_l2max.release();
     c->b_N.release(); c->b_N1.release();
     c->d_stage.release();
-    c->o_src.release(); c->o_ms.release();
+    c->o_src.release(); c->o_ms.release(); c->o_e.release();
     c->host_flag.release(); c->xs_chunk.release(); c->npscr.release();
 #ifndef ICL_EMU
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -934,10 +935,17 @@ static int phase_edges(icl_ctx *c) {
             k_edges_enum<<<tiles, 256, 0, s>>>(ee, V, es, stats);
             ICL_COUNT_KERNEL();
             ICL_CUDA(st, cudaGetLastError());
+            // total and window span are final here: they travel to the host on the side stream while the tile scan and the
+            // placement run, so the host is awake and the DP kernel queued by the time those finish
+            ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));
+            ICL_CUDA(st, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            ICL_CUDA(st, d2h(&c->h_small[0], cursor, sizeof(uint64_t), c->stream2));
+            ICL_CUDA(st, d2h(&c->h_small[1], c->stats.p + 3, sizeof(int32_t), c->stream2));
+            ICL_CUDA(st, cudaEventRecord(c->ev_join, c->stream2));
             if (exclusive_sum_u32(st, c->tmp, tile_cnt, c->tile_dst.p, tiles, s)) return st.code;
             const uint32_t *tile_dst = c->tile_dst.p;
             // (a pool that turned out too small holds nothing beyond its end: the placement is skipped on the device and the
-            // whole enumeration repeated below; total and window span are read once, behind everything)
+            // whole enumeration repeated below)
             k_edges_place<<<std::min<unsigned>(tiles, 148 * 8), 256, 0, s>>>(tiles, tile_cnt, tile_at, tile_dst, c->edge_stage.p, c->edges.p, cursor, want);
             ICL_COUNT_KERNEL();
             ICL_CUDA(st, cudaGetLastError());
@@ -951,9 +959,7 @@ static int phase_edges(icl_ctx *c) {
                     if (seg_off[it + 1] > a) eoff[a] = tile_dst[a >> 8] + first_local[it];
                 }));
             }
-            ICL_CUDA(st, d2h(&c->h_small[0], cursor, sizeof(uint64_t), s));
-            ICL_CUDA(st, d2h(&c->h_small[1], c->stats.p + 3, sizeof(int32_t), s));
-            ICL_CUDA(st, dev_sync(s));
+            ICL_CUDA(st, cudaEventSynchronize(c->ev_join));
             total = c->h_small[0];
             span = *(const int32_t *)&c->h_small[1];
             if (total <= want) break;
@@ -2011,16 +2017,20 @@ struct Stage {                               // bump allocator over the context'
 // layout — the per-block arrays first, the per-gene-pair arrays behind them (they are filled and copied separately).
 static int stage_layout(icl_ctx *c, int64_t NBo, int64_t NMo) {
     Status &st = c->st;
-    size_t members_at = 0;
+    // what the collinearity-file writer reads comes first in both parts, so that ICL_FIELDS_WRITER is two shorter copies
+    size_t members_at = 0, blocks_lean_end = 0, members_lean_end = 0;
     auto layout = [&](Stage &g, icl_blocks &o) {
-        o.pair = g.take<int32_t>(NBo); o.dir = g.take<int32_t>(NBo); o.score = g.take<int64_t>(NBo);
-        o.m = g.take<int32_t>(NBo); o.L = g.take<int32_t>(NBo); o.N = g.take<int32_t>(NBo); o.N1 = g.take<int64_t>(NBo);
-        o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo); o.p_raw = g.take<double>(NBo);
-        o.member_off = g.take<int64_t>(NBo + 1);
+        o.pair = g.take<int32_t>(NBo); o.score = g.take<int64_t>(NBo); o.m = g.take<int32_t>(NBo);
+        o.p_raw = g.take<double>(NBo); o.member_off = g.take<int64_t>(NBo + 1);
+        o.dir = g.take<int32_t>(NBo);
+        blocks_lean_end = (size_t)((uint8_t *)o.dir - g.base);
+        o.L = g.take<int32_t>(NBo); o.N = g.take<int32_t>(NBo); o.N1 = g.take<int64_t>(NBo);
+        o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo);
         o.loc1 = g.take<int32_t>(NMo);
         members_at = (size_t)((uint8_t *)o.loc1 - g.base);
         o.loc2 = g.take<int32_t>(NMo);
         o.member_idx = g.take<int32_t>(NMo);
+        members_lean_end = (size_t)((uint8_t *)o.member_idx - g.base);
     };
     Stage ds{nullptr, 0};
     icl_blocks probe{};
@@ -2047,6 +2057,8 @@ static int stage_layout(icl_ctx *c, int64_t NBo, int64_t NMo) {
     layout(hs, c->hv);
     c->stage_members_at = members_at;
     c->stage_bytes = ds.used;
+    c->stage_blocks_lean_end = blocks_lean_end;
+    c->stage_members_lean_end = members_lean_end;
     return 0;
 }
 
@@ -2219,14 +2231,31 @@ static int phase_extract(icl_ctx *c) {
     }
     if (exclusive_sum_u64(st, c->tmp, c->bs_in.p, c->bs.p, V, s)) return st.code;
     if (exclusive_sum_u32(st, c->tmp, c->mo_in.p, c->mo.p, V, s)) return st.code;
-    // (read back through page-locked words: [0] blocks << 32 | wanted, [1] gene pairs, [2..3] stats, [4] rank hand-back flag)
+    // the counts go to the host on the side stream (page-locked words: [0] blocks << 32 | wanted, [1] gene pairs, [2..3]
+    // stats, [4] rank hand-back flag); extract_counts() waits for them
     c->h_small[4] = 0;
-    ICL_CUDA(st, d2h(&c->h_small[0], c->bs.p + V, sizeof(uint64_t), s));
-    ICL_CUDA(st, d2h(&c->h_small[1], c->mo.p + V, sizeof(uint32_t), s));
-    ICL_CUDA(st, d2h(&c->h_small[2], c->stats.p, 4 * sizeof(int32_t), s));
+    cudaStream_t s2 = c->stream2 ? c->stream2 : s;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));
+    ICL_CUDA(st, cudaStreamWaitEvent(s2, c->ev_fork, 0));
+#endif
+    ICL_CUDA(st, d2h(&c->h_small[0], c->bs.p + V, sizeof(uint64_t), s2));
+    ICL_CUDA(st, d2h(&c->h_small[1], c->mo.p + V, sizeof(uint32_t), s2));
+    ICL_CUDA(st, d2h(&c->h_small[2], c->stats.p, 4 * sizeof(int32_t), s2));
     if (c->rank_flag_pending && c->order_on_device_used)       // hand-back flag icl_rank_device left unread (no sync there)
-        ICL_CUDA(st, d2h(&c->h_small[4], c->host_flag.p + c->rank_flag_slot, sizeof(int32_t), s));
-    ICL_CUDA(st, dev_sync(s));
+        ICL_CUDA(st, d2h(&c->h_small[4], c->host_flag.p + c->rank_flag_slot, sizeof(int32_t), s2));
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaEventRecord(c->ev_join, s2));
+#endif
+    return 0;
+}
+
+// Wait for the counts of phase_extract: accepted blocks, blocks / gene pairs the caller gets; errors the walk found.
+static int extract_counts(icl_ctx *c) {
+    Status &st = c->st;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaEventSynchronize(c->ev_join));
+#endif
     const uint64_t tot_bs = c->h_small[0];
     const uint32_t tot_m = *(const uint32_t *)&c->h_small[1];
     const int32_t *hs = (const int32_t *)&c->h_small[2];
@@ -2237,56 +2266,90 @@ static int phase_extract(icl_ctx *c) {
     c->NB = (int64_t)(tot_bs >> 32);
     c->NBo = (int64_t)(uint32_t)tot_bs;
     c->NMo = tot_m;
-    const int64_t NB = c->NB, NBo = c->NBo, NMo = c->NMo;
-    if (c->b_j0.reserve(st, NB) || c->b_j1.reserve(st, NB) || c->b_l2min.reserve(st, NB) || c->b_l2max.reserve(st, NB) ||
-        c->b_N.reserve(st, NB) || c->b_N1.reserve(st, NB) || c->o_src.reserve(st, NBo + 1) || c->o_ms.reserve(st, NBo + 1))
+    return 0;
+}
+
+// One thread per accepted block (emission order): the row slice of its bounding box for the times / p-value pass, and the
+// emission position of every block the caller gets.  `cap` blocks fit the arrays: the exact count when the host already
+// has it, else the bound of extract_block_bound() — the pass then runs (and the p-value kernel behind it) while the
+// counts are still on their way to the host.
+static int extract_block_slices(icl_ctx *c, int64_t cap) {
+    Status &st = c->st;
+    const int64_t n = c->n, V = 2 * n;
+    cudaStream_t s = c->stream;
+    if (c->b_j0.reserve(st, cap) || c->b_j1.reserve(st, cap) || c->b_l2min.reserve(st, cap) || c->b_l2max.reserve(st, cap) ||
+        c->b_N.reserve(st, cap) || c->b_N1.reserve(st, cap) || c->o_e.reserve(st, cap + 1))
         return st.code;
-    if (stage_layout(c, NBo, NMo)) return st.code;
-    {
-        // one thread per accepted block: the row slice of its bounding box for the times / p-value pass, and — for a
-        // block the caller gets — its output record (everything but N, N1 and the p value, which follow that pass)
-        const uint32_t *acc_m = c->acc_m.p, *acc_ms = c->acc_ms.p;
-        const uint64_t *bs = c->bs.p;
-        const uint32_t *mo = c->mo.p;
-        const int32_t *acc_L = c->acc_L.p, *rowptr = c->rowptr.p, *S = c->S.p, *ps = c->pair_s.p;
-        const int4 *acc_box = c->acc_box.p;
-        const int32_t *rmin = c->d_rmin.p;
-        const int64_t *rb_ = c->d_rb.p, *off = c->d_pair_off.p;
-        int32_t *b_j0 = c->b_j0.p, *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_N = c->b_N.p;
-        int64_t *b_N1 = c->b_N1.p;
-        uint32_t *o_src = c->o_src.p, *o_ms = c->o_ms.p;
-        const uint32_t minm = (uint32_t)(c->min_members < 1 ? 1 : c->min_members);
-        const icl_blocks o = c->dv;
-        ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t e) {
-            if (e == 0) o.member_off[NBo] = NMo;
-            const int32_t p = ps[e >> 1];
-            const int64_t t = emission_pos(e, n, ps, off);
-            const uint32_t m = acc_m[t];
-            if (!m) return;
-            const uint64_t at = bs[e];
-            const uint32_t b = (uint32_t)(at >> 32);
-            const int4 box = acc_box[t];
-            b_N[b] = 0;                                                         // (the p-value pass adds into these)
-            b_N1[b] = 0;
-            b_l2min[b] = box.z;
-            b_l2max[b] = box.w;
-            b_j0[b] = rowptr[rb_[p] + (box.x - rmin[p])];
-            b_j1[b] = rowptr[rb_[p] + (box.y - rmin[p]) + 1];
-            if (m < minm) return;
-            const uint32_t g = (uint32_t)at;
-            o_src[g] = b;
-            o_ms[g] = acc_ms[t];
-            o.pair[g] = p;
-            o.dir[g] = t >= n ? 1 : 0;
-            o.score[g] = S[rank2v[t]];
-            o.m[g] = (int32_t)m;
-            o.L[g] = acc_L[t];
-            o.L1[g] = box.y - box.x + 1;
-            o.L2[g] = box.w - box.z + 1;
-            o.member_off[g] = mo[e];
-        }));
-        if (V == 0) ICL_CUDA(st, dev_memset(c->dv.member_off, 0, sizeof(int64_t), s));
-    }
+    const uint32_t *acc_m = c->acc_m.p;
+    const uint64_t *bs = c->bs.p;
+    const int32_t *rowptr = c->rowptr.p, *ps = c->pair_s.p;
+    const int4 *acc_box = c->acc_box.p;
+    const int32_t *rmin = c->d_rmin.p;
+    const int64_t *rb_ = c->d_rb.p, *off = c->d_pair_off.p;
+    int32_t *b_j0 = c->b_j0.p, *b_j1 = c->b_j1.p, *b_l2min = c->b_l2min.p, *b_l2max = c->b_l2max.p, *b_N = c->b_N.p;
+    int64_t *b_N1 = c->b_N1.p;
+    uint32_t *o_e = c->o_e.p;
+    const uint32_t minm = (uint32_t)(c->min_members < 1 ? 1 : c->min_members);
+    ICL_CUDA(st, foreach(s, V, ICL_LAMBDA(int64_t e) {
+        const int32_t p = ps[e >> 1];
+        const int64_t t = emission_pos(e, n, ps, off);
+        const uint32_t m = acc_m[t];
+        if (!m) return;
+        const uint64_t at = bs[e];
+        const uint32_t b = (uint32_t)(at >> 32);
+        if ((int64_t)b >= cap) return;                                      // (cannot happen: cap is the count or its bound)
+        const int4 box = acc_box[t];
+        b_N[b] = 0;                                                         // (the p-value pass adds into these)
+        b_N1[b] = 0;
+        b_l2min[b] = box.z;
+        b_l2max[b] = box.w;
+        b_j0[b] = rowptr[rb_[p] + (box.x - rmin[p])];
+        b_j1[b] = rowptr[rb_[p] + (box.y - rmin[p]) + 1];
+        if (m >= minm) o_e[(uint32_t)at] = (uint32_t)e;
+    }));
+    return 0;
+}
+
+// No comparison accepts more blocks than this: a block takes m present points with m / L > coverage_ratio and
+// L >= over_gap (collinearity.py:129), i.e. at least the smallest m that passes for L = over_gap, and a point is taken once.
+static int64_t extract_block_bound(const icl_ctx *c) {
+    const int64_t V = 2 * c->n;
+    const int32_t L = c->prm.over_gap < 1 ? 1 : c->prm.over_gap;
+    int32_t mmin = 1;
+    while (mmin < L && !((double)mmin / (double)L > c->prm.coverage_ratio)) mmin++;
+    return V / mmin + 1;
+}
+
+// The output records of the blocks the caller gets (everything but N, N1 and the p value, which follow the times pass),
+// one thread each, on stream `s`.
+static int extract_output_records(icl_ctx *c, cudaStream_t s) {
+    Status &st = c->st;
+    const int64_t n = c->n, NBo = c->NBo, NMo = c->NMo;
+    if (c->o_src.reserve(st, NBo + 1) || c->o_ms.reserve(st, NBo + 1)) return st.code;
+    const uint32_t *acc_m = c->acc_m.p, *acc_ms = c->acc_ms.p, *o_e = c->o_e.p, *mo = c->mo.p;
+    const uint64_t *bs = c->bs.p;
+    const int32_t *acc_L = c->acc_L.p, *S = c->S.p, *ps = c->pair_s.p, *rank2v = c->rank2v.p;
+    const int4 *acc_box = c->acc_box.p;
+    const int64_t *off = c->d_pair_off.p;
+    uint32_t *o_src = c->o_src.p, *o_ms = c->o_ms.p;
+    const icl_blocks o = c->dv;
+    ICL_CUDA(st, foreach(s, NBo, ICL_LAMBDA(int64_t g) {
+        if (g == 0) o.member_off[NBo] = NMo;
+        const int64_t e = o_e[g];
+        const int64_t t = emission_pos(e, n, ps, off);
+        const int4 box = acc_box[t];
+        o_src[g] = (uint32_t)(bs[e] >> 32);
+        o_ms[g] = acc_ms[t];
+        o.pair[g] = ps[e >> 1];
+        o.dir[g] = t >= n ? 1 : 0;
+        o.score[g] = S[rank2v[t]];
+        o.m[g] = (int32_t)acc_m[t];
+        o.L[g] = acc_L[t];
+        o.L1[g] = box.y - box.x + 1;
+        o.L2[g] = box.w - box.z + 1;
+        o.member_off[g] = mo[e];
+    }));
+    if (NBo == 0) ICL_CUDA(st, dev_memset(c->dv.member_off, 0, sizeof(int64_t), s));
     return 0;
 }
 
@@ -4111,7 +4174,14 @@ extern "C" int icl_debug_order(icl_ctx *c, int32_t *argsort) {
 
 extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
                            icl_blocks *out) {
+    return icl_extract_fields(c, argsort_fwd, argsort_rev, min_members, ICL_FIELDS_ALL, out);
+}
+
+extern "C" int icl_extract_fields(icl_ctx *c, const int32_t *argsort_fwd, const int32_t *argsort_rev, int32_t min_members,
+                                  int32_t fields, icl_blocks *out) {
     if (!c) return ICL_ERR_ARG;
+    if (fields != ICL_FIELDS_ALL && fields != ICL_FIELDS_WRITER) return fail(c, ICL_ERR_ARG, "icl_extract_fields: unknown field set");
+    c->out_fields = fields;
     if (!c->dp_done) return fail(c, ICL_ERR_STATE, "icl_extract: icl_dp has not succeeded");
     const bool dev_order = !argsort_fwd && !argsort_rev && c->order_on_device;       // icl_rank_device ran
     if (!out || (c->n > 0 && !dev_order && (!argsort_fwd || !argsort_rev))) return fail(c, ICL_ERR_ARG, "icl_extract: null argument");
@@ -4152,24 +4222,52 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
     }
     c->min_members = min_members;
     if (phase_extract(c)) return st.code;
-    c->timers[ICL_T_EXTRACT].stop(s);
-    const int64_t NBo = c->NBo, NMo = c->NMo;
-    // the gene pairs of the output do not wait for the p values: gathered and copied on the side stream meanwhile
+    // With the device's own order (nothing of the caller's to validate) the times pass does not wait for the host: its
+    // inputs go into arrays sized by a bound, the kernel runs, and the host meanwhile receives the counts, sizes the output
+    // staging and queues the output passes on the side stream.  Otherwise: counts first, then the same passes.
     cudaStream_t s2 = c->stream2 ? c->stream2 : s;
+    const bool overlap = c->order_on_device_used && c->pvalue_mode != 2 && n > 0;
+    if (!overlap && extract_counts(c)) return st.code;
+    if (extract_block_slices(c, overlap ? extract_block_bound(c) : c->NB)) return st.code;
 #ifndef ICL_EMU
-    ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));
+    ICL_CUDA(st, cudaEventRecord(c->ev_fork, s));              // what the output passes on the side stream wait for
+#endif
+    c->timers[ICL_T_EXTRACT].stop(s);
+    if (overlap) {
+        c->timers[ICL_T_PVALUE].start(s);
+        c->NB = extract_block_bound(c);                        // (capacity of the per-block arrays; the kernels read the real lists)
+        if (phase_pvalue(c)) return st.code;
+        c->timers[ICL_T_PVALUE].stop(s);
+        if (extract_counts(c)) return st.code;
+    }
+    const int64_t NBo = c->NBo, NMo = c->NMo;
+    if (stage_layout(c, NBo, NMo)) return st.code;
+    // the gene pairs of the output do not wait for the p values: gathered and copied on the side stream meanwhile
+#ifndef ICL_EMU
     ICL_CUDA(st, cudaStreamWaitEvent(s2, c->ev_fork, 0));
 #endif
+    if (extract_output_records(c, s2)) return st.code;
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaEventRecord(c->ev_join3, s2));            // the records: the p values' pass below reads them
+#endif
     if (phase_members(c, s2)) return st.code;
-    if (c->stage_bytes > c->stage_members_at)
-        ICL_CUDA(st, d2h(c->h_stage + c->stage_members_at, c->d_stage.p + c->stage_members_at, c->stage_bytes - c->stage_members_at, s2));
+    {
+        const size_t end = c->out_fields == ICL_FIELDS_WRITER ? c->stage_members_lean_end : c->stage_bytes;
+        if (end > c->stage_members_at)
+            ICL_CUDA(st, d2h(c->h_stage + c->stage_members_at, c->d_stage.p + c->stage_members_at, end - c->stage_members_at, s2));
+    }
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaEventRecord(c->ev_join, s2));
 #endif
-    c->timers[ICL_T_PVALUE].start(s);
-    if (phase_pvalue(c)) return st.code;
-    c->timers[ICL_T_PVALUE].stop(s);
+    if (!overlap) {
+        c->timers[ICL_T_PVALUE].start(s);
+        if (phase_pvalue(c)) return st.code;
+        c->timers[ICL_T_PVALUE].stop(s);
+    }
     c->timers[ICL_T_GATHER].start(s);
+#ifndef ICL_EMU
+    ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join3, 0));
+#endif
     {
         // N, N1 and the p value (collinearity.py:152 in binary64, left to right) of the blocks the caller gets
         const uint32_t *o_src = c->o_src.p;
@@ -4186,13 +4284,15 @@ extern "C" int icl_extract(icl_ctx *c, const int32_t *argsort_fwd, const int32_t
             o.p_raw[g] = icl_p_raw(o.score[g], o.m[g], g0, N1, N, o.L1[g], o.L2[g]);
         }));
     }
-    ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, c->stage_members_at, s));
+    ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, c->out_fields == ICL_FIELDS_WRITER ? c->stage_blocks_lean_end : c->stage_members_at, s));
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join, 0));
 #endif
     c->timers[ICL_T_GATHER].stop(s);
     ICL_CUDA(st, dev_sync(s));
     *out = c->hv;
+    if (c->out_fields == ICL_FIELDS_WRITER)                    // not copied: not there
+        out->dir = out->L = out->N = out->L1 = out->L2 = out->member_idx = nullptr, out->N1 = nullptr;
     out->n_blocks = NBo;
     out->n_members = NMo;
     return ICL_OK;

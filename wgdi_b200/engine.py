@@ -23,6 +23,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import IclError, icl_blocks, icl_params
+
+FIELDS = {"all": 0, "writer": 1}         # ICL_FIELDS_ALL / ICL_FIELDS_WRITER of include/icl_b200.h
 from .params import ChainParams, nargsort_desc  # noqa: F401  (re-exported: the reference-facing names live in params.py)
 
 try:                                    # numpy's own argsort routine, GIL-free (wgdi_b200/csrc/npsort.c)
@@ -57,7 +59,9 @@ def _npsort_ok():
 
 @dataclass
 class Blocks:
-    """All accepted blocks of a comparison in the reference's emission order (see icl_blocks)."""
+    """All accepted blocks of a comparison in the reference's emission order (see icl_blocks).  With `IclEngine.fields =
+    "writer"` only what the collinearity file is written from comes back from the device (pair, score, m, p_raw,
+    member_off, loc1, loc2); the other arrays are None."""
     pair: np.ndarray
     dir: np.ndarray
     score: np.ndarray
@@ -122,6 +126,7 @@ class IclEngine:
         # AVX2 or scalar argsort, checked against the running numpy), else the host; "host" = always numpy on the host;
         # "numpy_scalar" / "numpy_avx512" / "numpy_avx2" = that device reproduction regardless of what numpy does here
         self.rank_mode = os.environ.get("ICL_B200_RANK", "auto")
+        self.fields = "all"              # what `extract` brings back: "all" arrays of icl_blocks, or what the file "writer" reads
         self.host_rank_fallbacks = 0        # comparisons the device rank handed back to numpy (std::sort's heap-sort branch)
         # ICL_B200_RANK_VERIFY=K (1 = 32): after every device rank, K segments (the longest four, the rest at random) are
         # re-sorted with the running numpy and compared; a difference sends this comparison — and from then on the process —
@@ -268,13 +273,16 @@ class IclEngine:
         out = icl_blocks()
         af = np.ascontiguousarray(argsort_fwd, np.int32)
         ar = np.ascontiguousarray(argsort_rev, np.int32)
-        self._check(self.lib.icl_extract(self.ctx, af.ctypes.data, ar.ctypes.data, int(min_members), C.byref(out)))
+        self._check(self.lib.icl_extract_fields(self.ctx, af.ctypes.data, ar.ctypes.data, int(min_members), FIELDS[self.fields],
+                                                C.byref(out)))
         return self._blocks_from(out, copy)
 
     def _blocks_from(self, out, copy):
         nb, nm = out.n_blocks, out.n_members
 
         def arr(ptr, n, dt):          # the staging is reused by the next call
+            if not ptr:
+                return None               # not part of the field set that was asked for (`fields = "writer"`)
             if n == 0:
                 return np.zeros(0, dt)
             a = np.ctypeslib.as_array(ptr, shape=(n,))
@@ -455,7 +463,7 @@ class IclEngine:
                 return by_numpy()
             # (the rank kernels report a segment they do not cover — std::sort's heap-sort branch — without stopping the
             # stream: the flag is read at icl_extract's first synchronisation, which then fails with the same code)
-            self._check(self.lib.icl_extract(self.ctx, None, None, int(min_members), C.byref(out)))
+            self._check(self.lib.icl_extract_fields(self.ctx, None, None, int(min_members), FIELDS[self.fields], C.byref(out)))
         except IclError as e:
             if e.code != -3 or mode == "stable":
                 raise

@@ -122,6 +122,7 @@ class mycollinearity():
                 blocks = chain_on_devices(pts, len(pts['pair_names']), params, self.devices, min_members=self.over_gap)
             else:
                 eng = IclEngine(self.devices[0])
+                eng.fields = "writer"     # only what the file is written from comes back: 32 B per block, 8 B per gene pair
                 # the points cross PCIe in the narrowest element types that hold them (7 instead of 16 bytes per point)
                 up = compact_points(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'])
                 # blocks are views of the engine's page-locked staging: written out before the engine is closed
