@@ -392,6 +392,7 @@ def strong_leg(args, rank, world, local, barrier, sort_threads):
     if rank != 0:
         hg = shard.HostGather(path, rank, world, P_all, cap_b, cap_m, create=False)
     eng = IclEngine(local, sort_threads=sort_threads)
+    eng.fields = "writer"      # every rank brings back and places what the file is written from
     from wgdi_b200.params import compact_points
     host_in = {}
     for k, arr in zip(("pair_id", "loc1", "loc2", "grading"), compact_points(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"])):

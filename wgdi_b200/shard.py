@@ -133,7 +133,7 @@ def place_blocks(blocks, global_pair, rows, block_base, member_base, out: dict):
     mo = blocks.member_off
     mdest0 = member_base[gp] + (mo[:-1] - mo[first])           # first member of every block in the merged arrays
     for f in BLOCK_FIELDS:
-        if f in MEMBER_FIELDS or f == "member_off":
+        if f in MEMBER_FIELDS or f == "member_off" or getattr(blocks, f) is None:   # (None: not in the engine's field set)
             continue
         out[f][dest] = gp if f == "pair" else getattr(blocks, f)
     out["member_off"][dest] = mdest0
@@ -141,7 +141,8 @@ def place_blocks(blocks, global_pair, rows, block_base, member_base, out: dict):
     mdest = shift + np.arange(len(shift))
     out["loc1"][mdest] = blocks.loc1
     out["loc2"][mdest] = blocks.loc2
-    out["member_idx"][mdest] = np.asarray(rows)[blocks.member_idx]
+    if blocks.member_idx is not None:
+        out["member_idx"][mdest] = np.asarray(rows)[blocks.member_idx]
 
 
 class HostGather:
@@ -206,7 +207,8 @@ class HostGather:
         self.barrier()                                           # every rank's blocks are in place
         if self.rank != 0:
             return None
-        return Blocks(*[self.out[f][:(nm if f in MEMBER_FIELDS else nb + 1 if f == "member_off" else nb)] for f in BLOCK_FIELDS])
+        return Blocks(*[None if getattr(blocks, f) is None else
+                        self.out[f][:(nm if f in MEMBER_FIELDS else nb + 1 if f == "member_off" else nb)] for f in BLOCK_FIELDS])
 
 
 def chain_on_devices(points: dict, n_pairs: int, params, devices, min_members: int = 1):
