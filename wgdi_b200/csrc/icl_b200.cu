@@ -2666,7 +2666,9 @@ static int phase_pvalue(icl_ctx *c) {
     } else {
         // warps per pair: enough that a warp's share of the blocks is short, few enough that several pairs fit an SM
         const bool ts = maxnp <= 27 * 1024;                    // counters + loc2 of the pair: 8 B per point in shared memory
-        const int threads = maxnp <= 4096 ? 128 : maxnp <= 12 * 1024 ? 256 : maxnp <= 40 * 1024 ? 512 : 1024;
+        static const int pv_threads = [] { const char *e = getenv("ICL_B200_PV_THREADS"); return e ? atoi(e) : 0; }();
+        const int threads = pv_threads >= 64 && pv_threads <= 1024 ? (pv_threads & ~31)
+                            : maxnp <= 4096 ? 128 : maxnp <= 12 * 1024 ? 256 : maxnp <= 40 * 1024 ? 512 : 1024;
         if (ts) {
             const size_t smem = (((size_t)maxnp * 4 + 15) & ~(size_t)15) + (size_t)maxnp * 4;
             ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue_owned<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
