@@ -1897,37 +1897,44 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
         if (qi >= T.stats[HUGE ? 4 : 1]) break;
         const int2 rg = HUGE ? T.big[T.bigcap - 1 - qi] : T.big[qi];
         const int32_t t0 = rg.x, N = rg.y - rg.x;
-        int32_t hsz = 64;
-        while (hsz < 2 * N) hsz <<= 1;
+        int32_t hsz = 64, hshift = 26;
+        while (hsz < 2 * N) { hsz <<= 1; hshift--; }
         for (int32_t i = lane; i < hsz; i += 32) s_h[i] = make_int2(-1, -1);
         __syncwarp();
+        // Gather of the tree, one level of the dependent chain (rank position -> point -> node record -> forward position
+        // -> coordinates) per pass, eight loads of a lane in flight at a time (ICL_TREE_GATHER: registers first, stores after
+        // — left as a plain loop the compiler keeps ONE load per lane in flight: 95 k cycles for the 678-point tree of C2;
+        // the round of two dependent 5-deep chains per lane before it: 49 k).
         bool rev = false;
-        for (int32_t j0 = lane; j0 < N; j0 += 64) {             // two independent load chains per lane and round
-            const int32_t j1 = j0 + 32;
-            const bool two = j1 < N;
-            const int32_t ta = (int32_t)T.tpos[t0 + j0], tb = two ? (int32_t)T.tpos[t0 + j1] : ta;
-            const int32_t va = T.rank2v[ta], vb = T.rank2v[tb];
-            const int2 na = T.pd[va], nb = T.pd[vb];
-            const int32_t ia = va >= T.n ? T.imap[va - T.n] : va, ib = vb >= T.n ? T.imap[vb - T.n] : vb;
-            const int32_t ya = T.l2[ia], yb = T.l2[ib], xa = T.l1[ia], xb = T.l1[ib];
-            if (j0 == 0) rev = va >= T.n;
-            for (int r = 0; r < (two ? 2 : 1); r++) {
-                const int32_t j = r ? j1 : j0, t = r ? tb : ta, v = r ? vb : va, i = r ? ib : ia;
-                const int2 nd = r ? nb : na;
-                s_t[j] = t; s_f[j] = i; s_y[j] = r ? yb : ya; s_x[j] = r ? xb : xa; s_pl[j] = nd.x; s_L[j] = nd.y; s_pres[j] = 1;
-                uint32_t h = ((uint32_t)v * 2654435761u) & (uint32_t)(hsz - 1);
-                int32_t tries = 0;                             // (bounded: a caller's broken order must not hang the GPU)
-                while (atomicCAS(&s_h[h].x, -1, v) != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
-                if (tries < hsz) s_h[h].y = j;
-            }
+#define ICL_TREE_GATHER(TYPE, LOAD, STORE)                                                                   \
+        for (int32_t j0 = lane; j0 < N; j0 += 256) {                                                        \
+            TYPE r_[8];                                                                                      \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) { const int32_t j = j0 + 32 * k_; if (j < N) { r_[k_] = LOAD; } } \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++) { const int32_t j = j0 + 32 * k_; if (j < N) { const TYPE r = r_[k_]; STORE; } } \
         }
+        ICL_TREE_GATHER(int32_t, (int32_t)T.tpos[t0 + j], s_t[j] = r)
+        ICL_TREE_GATHER(int32_t, T.rank2v[s_t[j]], s_x[j] = r)                              // (s_x: the point, until the last pass)
+        ICL_TREE_GATHER(int2, T.pd[s_x[j]], (s_pl[j] = r.x, s_L[j] = r.y))
+        ICL_TREE_GATHER(int32_t, (s_x[j] >= T.n ? T.imap[s_x[j] - T.n] : s_x[j]), s_f[j] = r)
+        ICL_TREE_GATHER(int32_t, T.l2[s_f[j]], s_y[j] = r)
+        if (lane == 0) rev = s_x[0] >= T.n;
+        for (int32_t j = lane; j < N; j += 32) {                   // hash of the tree's points (before s_x is overwritten)
+            const int32_t v = s_x[j];
+            uint32_t h = ((uint32_t)v * 2654435761u) >> hshift;    // (the HIGH bits of the product: the low ones repeat with the key's)
+            int32_t tries = 0;                                 // (bounded: a caller's broken order must not hang the GPU)
+            while (atomicCAS(&s_h[h].x, -1, v) != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
+            if (tries < hsz) s_h[h].y = j;
+        }
+        ICL_TREE_GATHER(int32_t, T.l1[s_f[j]], (s_x[j] = r, s_pres[j] = 1))
+#undef ICL_TREE_GATHER
+        for (int32_t j = N + lane; j < ((N + 15) & ~15); j += 32) s_pres[j] = 0;      // (the walk reads `present` 16 points at a time)
         rev = __shfl_sync(FULL, rev, 0);
         __syncwarp();
         for (int32_t j = lane; j < N; j += 32) {
             const int32_t p = s_pl[j];
             int32_t loc = -1;
             if (p >= 0) {                                      // the predecessor is a used point of the same tree
-                uint32_t h = ((uint32_t)p * 2654435761u) & (uint32_t)(hsz - 1);
+                uint32_t h = ((uint32_t)p * 2654435761u) >> hshift;
                 int32_t tries = 0;
                 while (s_h[h].x != p && s_h[h].x != -1 && ++tries < hsz) h = (h + 1) & (uint32_t)(hsz - 1);
                 loc = s_h[h].x == p ? s_h[h].y : -1;
@@ -1942,47 +1949,51 @@ __global__ void __launch_bounds__(32) k_tree_walk_staged(TreeArgs T) {
         for (int32_t L = lane + 1; L <= N; L += 32) {
             int32_t m = (int32_t)(T.cov * (double)L);
             m = m < 0 ? 0 : m > L ? L : m;
-            while (m <= L && !((double)m / (double)L > T.cov)) m++;
-            while (m > 0 && (double)(m - 1) / (double)L > T.cov) m--;
+            bool stepped = false;                              // (m - 1 is then known to fail: one division less, of ~260 cycles each)
+            while (m <= L && !((double)m / (double)L > T.cov)) { m++; stepped = true; }
+            while (!stepped && m > 0 && (double)(m - 1) / (double)L > T.cov) m--;
             s_mm[L - 1] = m;                                   // L + 1 when no m <= L passes (coverage_ratio >= 1)
         }
         __syncwarp();
         if (lane == 0) {
             int32_t ver = 0;                                   // accepted blocks of this tree so far
             uint32_t cursor = (uint32_t)t0;                    // member scratch: the tree's own slice
-            // The walk of a tree is sequential and its time is the kernel's (the largest tree of C2 has 678 points).  The
-            // per-point data that never changes — path length, predecessor, smallest accepted m of that length — is read
-            // two points ahead (the stores to `present` keep the compiler from moving any load up by itself), so an
-            // examined point costs one round of shared-memory latency (present + memo) instead of four.
-            int32_t Ln = s_L[0], pln = s_pl[0];                                // point u + 1 after the shift below
-            int32_t Lnn = N > 1 ? s_L[1] : 1, plnn = N > 1 ? s_pl[1] : -1;     // point u + 2
-            int32_t mmn = (Ln >= 1 && Ln <= N) ? s_mm[Ln - 1] : 0x7fffffff;
+            // The walk of a tree is sequential and the largest tree's time is the kernel's.  By the time their turn as a top
+            // comes most points are gone — taken as members of an earlier block (the 678-point tree of C2: one block of 546)
+            // — and a loop iteration per point cost 140 cycles each: the next PRESENT point is found 16 flags per load.
             for (int32_t u = 0; u < N; u++) {                  // the tree's points in rank order
-                const int32_t L = Ln, pl = pln, mmL = mmn;
-                Ln = Lnn; pln = plnn;
-                mmn = (Ln >= 1 && Ln <= N) ? s_mm[Ln - 1] : 0x7fffffff;
-                if (u + 2 < N) { Lnn = s_L[u + 2]; plnn = s_pl[u + 2]; }
-                const uint8_t pres = s_pres[u];
+                {
+                    const int32_t base = u & ~15, k = u & 15;
+                    const uint4 w = *(const uint4 *)(s_pres + base);
+                    unsigned long long lo = (unsigned long long)w.x | ((unsigned long long)w.y << 32);
+                    unsigned long long hi = (unsigned long long)w.z | ((unsigned long long)w.w << 32);
+                    if (k < 8) lo &= ~0ull << (8 * k); else { lo = 0ull; hi &= ~0ull << (8 * (k - 8)); }
+                    if (lo) u = base + ((__ffsll((long long)lo) - 1) >> 3);
+                    else if (hi) u = base + 8 + ((__ffsll((long long)hi) - 1) >> 3);
+                    else { u = base + 15; continue; }          // none of the 16: on to the next group
+                    if (u >= N) break;
+                }
+                const int32_t L = s_L[u], pl = s_pl[u];
                 const int2 memo = s_h[u];
-                if (!pres) continue;
+                const int32_t mmL = (L >= 1 && L <= N) ? s_mm[L - 1] : 0x7fffffff;
                 int32_t m, q;
                 if (ver == 0) m = L;
                 else if (memo.y == ver) m = L - memo.x;
                 else { m = 1; q = pl; while (q >= 0 && s_pres[q]) { m++; q = s_pl[q]; } }
                 if (L >= T.over_gap && L <= N && m >= mmL) {                      // :129
-                    int32_t l2min = 0x7fffffff, l2max = -1, la = 0, lb = 0;
+                    int32_t l2min = 0x7fffffff, l2max = -1, qlast = u;
                     q = u;
                     for (int32_t k = 0; k < m; k++) {
                         if (q < 0) break;                      // (only with a caller's broken order, reported by the caller)
+                        const int32_t qn = s_pl[q], yv = s_y[q];   // (the next hop first: it is the loop's dependent chain)
                         s_pres[q] = 0;
                         T.mscr[cursor + k] = s_f[q];
-                        const int32_t yv = s_y[q];
                         l2min = yv < l2min ? yv : l2min;
                         l2max = yv > l2max ? yv : l2max;
-                        if (k == 0) la = s_x[q];
-                        lb = s_x[q];
-                        q = s_pl[q];
+                        qlast = q;
+                        q = qn;
                     }
+                    const int32_t la = s_x[u], lb = s_x[qlast];
                     ver++;
                     const int32_t t = s_t[u];
                     T.acc_m[t] = (uint32_t)m;
@@ -2668,7 +2679,8 @@ static int phase_pvalue(icl_ctx *c) {
         const bool ts = maxnp <= 27 * 1024;                    // counters + loc2 of the pair: 8 B per point in shared memory
         static const int pv_threads = [] { const char *e = getenv("ICL_B200_PV_THREADS"); return e ? atoi(e) : 0; }();
         const int threads = pv_threads >= 64 && pv_threads <= 1024 ? (pv_threads & ~31)
-                            : maxnp <= 4096 ? 128 : maxnp <= 12 * 1024 ? 256 : maxnp <= 40 * 1024 ? 512 : 1024;
+                            : maxnp <= 1024 ? 128 : maxnp <= 4096 ? 512 : 1024;   // (sweep 128 / 256 / 512 / 1024 threads, ms: C2
+                                                                                    // 0.23 / 0.14 / 0.096 / 0.091, C4 0.84 / 0.46 / 0.28 / 0.24, C3 8.1 / 4.0 / 2.2 / 1.1)
         if (ts) {
             const size_t smem = (((size_t)maxnp * 4 + 15) & ~(size_t)15) + (size_t)maxnp * 4;
             ICL_CUDA(st, cudaFuncSetAttribute(k_pvalue_owned<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
