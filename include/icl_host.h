@@ -77,6 +77,25 @@ int icl_host_write_blocks(const char *path, int64_t n_sel,
                           const int32_t *strand_code2,
                           int32_t threads, char *err, int32_t errlen);
 
+/*
+ * One comparison sharded over several GPUs (the pairs of wgdi/run_colliearity.py:123-136 over ranks instead of worker
+ * processes): write one rank's blocks straight to their place in the merged, emission-ordered arrays — what the reference's
+ * parent process does when it concatenates the workers' texts in chunk order (:133-141).  A rank's blocks are pair-major, so
+ * a pair's run of blocks is contiguous on both sides:
+ *   block b of local pair q, global pair g = global_pair[q]:  destination block_base[g] + (b - first block of the run),
+ *   its gene pairs from member_base[g] + (member_off[b] - member_off[first block of the run]).
+ * block_base / member_base: exclusive sums over the per-pair counts of ALL ranks.  Per-block arrays (n_block_fields of
+ * block_bytes[k] bytes per element) and per-gene-pair arrays (n_member_fields) are copied as they are; out_pair receives
+ * the global pair ids, out_member_off the new member offsets, and member_idx (may be NULL) is mapped through `rows`
+ * (the rank's upload index -> the comparison's) into out_member_idx.  wgdi_b200/shard.py:place_blocks is the same in numpy.
+ */
+int icl_host_place_blocks(int64_t n_blocks, const int32_t *pair, const int32_t *global_pair,
+                          const int64_t *block_base, const int64_t *member_base, const int64_t *member_off,
+                          int32_t n_block_fields, const void *const *block_src, void *const *block_dst, const int32_t *block_bytes,
+                          int32_t n_member_fields, const void *const *member_src, void *const *member_dst, const int32_t *member_bytes,
+                          int32_t *out_pair, int64_t *out_member_off,
+                          const int32_t *member_idx, const int64_t *rows, int32_t *out_member_idx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ def test_host_library_exports_declared_symbols(host):
     lib = ctypes.CDLL(host.LIB_PATH)
     header = open(os.path.join(ROOT, "include", "icl_host.h")).read()
     declared = set(re.findall(r"\b(icl_host_[a-z_0-9]+)\s*\(", header))
-    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks"}
+    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks", "icl_host_place_blocks"}
     for name in declared:
         assert hasattr(lib, name)
 
@@ -147,3 +147,44 @@ def test_native_and_pandas_paths_write_the_same_file(host, emu_backend, case, tm
         assert texts["native"] == texts["pandas"] and len(texts["native"]) > 1000
     finally:
         os.chdir(cwd)
+
+
+def test_native_place_blocks_equals_numpy(host, monkeypatch):
+    """icl_host_place_blocks against the numpy placement of shard.place_blocks: two ranks with interleaved pairs, with and
+    without the optional arrays (field set "writer")."""
+    from wgdi_b200 import shard
+    from wgdi_b200.engine import Blocks
+    rng = np.random.default_rng(3)
+    P = 40
+    owner = rng.integers(0, 2, P)
+    parts, rows_of, gps = [], [], []
+    for r in range(2):
+        gp = np.flatnonzero(owner == r).astype(np.int32)
+        nb = 300
+        pair = np.sort(rng.integers(0, len(gp), nb)).astype(np.int32)
+        m = rng.integers(1, 30, nb).astype(np.int32)
+        mo = np.r_[0, np.cumsum(m)].astype(np.int64)
+        nm = int(mo[-1])
+        rows = rng.permutation(5000)[:2000].astype(np.int64)
+        f = lambda dt, n: rng.integers(0, 1000, n).astype(dt)
+        parts.append(Blocks(pair, f(np.int32, nb), f(np.int64, nb), m, f(np.int32, nb), f(np.int32, nb), f(np.int64, nb),
+                            f(np.int32, nb), f(np.int32, nb), rng.random(nb), mo, f(np.int32, nm), f(np.int32, nm),
+                            rng.integers(0, 2000, nm).astype(np.int32)))
+        rows_of.append(rows)
+        gps.append(gp)
+    for lean in (False, True):
+        use = [Blocks(*[None if (lean and f in ("dir", "L", "N", "N1", "L1", "L2", "member_idx")) else getattr(b, f)
+                        for f in shard.BLOCK_FIELDS]) for b in parts]
+        counts = [shard.pair_counts(b, gp, P) for b, gp in zip(use, gps)]
+        bb = np.r_[0, np.cumsum(sum(c[0] for c in counts))]
+        mb = np.r_[0, np.cumsum(sum(c[1] for c in counts))]
+        outs = []
+        for native in (True, False):
+            monkeypatch.setattr(host, "available", lambda native=native: native)
+            out = {f: np.zeros(int(mb[-1]) + 1 if f in shard.MEMBER_FIELDS else int(bb[-1]) + 2, shard.HostGather.DT[f])
+                   for f in shard.BLOCK_FIELDS}
+            for b, gp, rows in zip(use, gps, rows_of):
+                shard.place_blocks(b, gp, rows, bb, mb, out)
+            outs.append(out)
+        for f in shard.BLOCK_FIELDS:
+            assert (outs[0][f] == outs[1][f]).all(), (lean, f)

@@ -36,8 +36,43 @@ def load():
         lib.icl_host_grade.argtypes = [i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32]
         lib.icl_host_write_blocks.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
                                               vp, i64, vp, vp, vp, i32, vp, i32]
+        lib.icl_host_place_blocks.argtypes = [i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
         _LIB = lib
     return _LIB
+
+
+def place_blocks(pair, global_pair, block_base, member_base, member_off, block_fields, member_fields, out_pair, out_member_off,
+                 member_idx=None, rows=None, out_member_idx=None):
+    """icl_host_place_blocks: block_fields / member_fields = lists of (source array, destination array) of equal dtype."""
+    lib = load()
+
+    def table(fields):
+        n = len(fields)
+        src = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a, _ in fields])
+        dst = (C.c_void_p * max(n, 1))(*[d.ctypes.data for _, d in fields])
+        wid = (C.c_int32 * max(n, 1))(*[a.dtype.itemsize for a, _ in fields])
+        for a, d in fields:
+            if a.dtype != d.dtype or not a.flags.c_contiguous:
+                raise ValueError("place_blocks: source and destination arrays must be contiguous and of one dtype")
+        return n, src, dst, wid
+    nbf, bs, bd, bw = table(block_fields)
+    nmf, ms, md, mw = table(member_fields)
+    pair = np.ascontiguousarray(pair, np.int32)
+    global_pair = np.ascontiguousarray(global_pair, np.int32)
+    block_base = np.ascontiguousarray(block_base, np.int64)
+    member_base = np.ascontiguousarray(member_base, np.int64)
+    member_off = np.ascontiguousarray(member_off, np.int64)
+    with_idx = member_idx is not None and rows is not None and out_member_idx is not None
+    if with_idx:
+        member_idx = np.ascontiguousarray(member_idx, np.int32)
+        rows = np.ascontiguousarray(rows, np.int64)
+    rc = lib.icl_host_place_blocks(len(pair), pair.ctypes.data, global_pair.ctypes.data, block_base.ctypes.data,
+                                   member_base.ctypes.data, member_off.ctypes.data, nbf, bs, bd, bw, nmf, ms, md, mw,
+                                   out_pair.ctypes.data, out_member_off.ctypes.data,
+                                   member_idx.ctypes.data if with_idx else None, rows.ctypes.data if with_idx else None,
+                                   out_member_idx.ctypes.data if with_idx else None)
+    if rc:
+        raise RuntimeError(f"icl_host_place_blocks failed ({rc})")
 
 
 _COMPRESSED_EXT = (".gz", ".bz2", ".zip", ".xz", ".zst", ".tar", ".tar.gz", ".tar.xz", ".tar.bz2")

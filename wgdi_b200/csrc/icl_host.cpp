@@ -454,3 +454,38 @@ extern "C" int icl_host_write_blocks(const char *path, int64_t n_sel,
     if ((int64_t)w != total || rc != 0) { set_err(err, errlen, "short write"); return -2; }
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// host gather of a comparison sharded over GPUs: one rank's blocks to their place in the merged arrays
+// ------------------------------------------------------------------------------------------------
+extern "C" int icl_host_place_blocks(int64_t n_blocks, const int32_t *pair, const int32_t *global_pair,
+                                     const int64_t *block_base, const int64_t *member_base, const int64_t *member_off,
+                                     int32_t n_block_fields, const void *const *block_src, void *const *block_dst,
+                                     const int32_t *block_bytes, int32_t n_member_fields, const void *const *member_src,
+                                     void *const *member_dst, const int32_t *member_bytes, int32_t *out_pair,
+                                     int64_t *out_member_off, const int32_t *member_idx, const int64_t *rows,
+                                     int32_t *out_member_idx) {
+    if (n_blocks < 0 || (n_blocks > 0 && (!pair || !global_pair || !block_base || !member_base || !member_off || !out_pair || !out_member_off)))
+        return -1;
+    int64_t first = 0;                                         // first block of the current pair's run
+    for (int64_t b = 0; b < n_blocks; b++) {
+        if (b > 0 && pair[b] != pair[b - 1]) first = b;
+        const int32_t g = global_pair[pair[b]];
+        const int64_t dest = block_base[g] + (b - first);
+        const int64_t m0 = member_off[b], m1 = member_off[b + 1], mdest = member_base[g] + (m0 - member_off[first]);
+        out_pair[dest] = g;
+        out_member_off[dest] = mdest;
+        for (int32_t k = 0; k < n_block_fields; k++) {
+            const int32_t w = block_bytes[k];
+            memcpy((char *)block_dst[k] + dest * w, (const char *)block_src[k] + b * w, (size_t)w);
+        }
+        for (int32_t k = 0; k < n_member_fields; k++) {
+            const int32_t w = member_bytes[k];
+            memcpy((char *)member_dst[k] + mdest * w, (const char *)member_src[k] + m0 * w, (size_t)(m1 - m0) * w);
+        }
+        if (member_idx && rows && out_member_idx)
+            for (int64_t i = m0; i < m1; i++) out_member_idx[mdest + (i - m0)] = (int32_t)rows[member_idx[i]];
+    }
+    return 0;
+}

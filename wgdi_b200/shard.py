@@ -126,6 +126,17 @@ def place_blocks(blocks, global_pair, rows, block_base, member_base, out: dict):
     nb = len(blocks)
     if nb == 0:
         return
+    from . import _host
+    if _host.available() and out["pair"].dtype == np.int32 and out["member_off"].dtype == np.int64:
+        # the same placement by libicl_host.so (icl_host_place_blocks): one pass of memcpy per block instead of numpy's
+        # index arrays (half of C4's blocks: 3 ms in numpy, 0.1 ms native)
+        bf = [(np.ascontiguousarray(getattr(blocks, f)), out[f]) for f in BLOCK_FIELDS
+              if f not in MEMBER_FIELDS and f not in ("pair", "member_off") and getattr(blocks, f) is not None]
+        mf = [(np.ascontiguousarray(getattr(blocks, f)), out[f]) for f in ("loc1", "loc2")]
+        _host.place_blocks(blocks.pair, global_pair, block_base, member_base, blocks.member_off, bf, mf, out["pair"],
+                           out["member_off"], blocks.member_idx, rows if blocks.member_idx is not None else None,
+                           out["member_idx"] if blocks.member_idx is not None else None)
+        return
     gp = np.asarray(global_pair)[blocks.pair]
     new = np.r_[True, gp[1:] != gp[:-1]]
     first = np.flatnonzero(new)[np.cumsum(new) - 1]            # first block of the pair's run, per block
