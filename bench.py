@@ -559,11 +559,14 @@ def main():
     dev_ms = {}
 
     def step_resident():
-        blocks = eng.run_resident(prm, min_members=5, copy=False)       # what the file writer keeps (run_colliearity.py:178)
+        return eng.run_resident(prm, min_members=5, copy=False)         # what the file writer keeps (run_colliearity.py:178)
+
+    def read_phase_clocks():
+        # the library's CUDA events of the step that just ended (recorded inside the timed region on its stream); reading
+        # them is host work of the benchmark, not of the step: after the step's clock has stopped
         for k, v in eng.timings().items():
             dev_ms.setdefault(k, []).append(v)
         dev_ms.setdefault("host_rank", []).append(eng.host_ms["rank"])
-        return blocks
 
     def step_e2e():
         return eng.chain(host_in["pair_id"], host_in["loc1"], host_in["loc2"], host_in["grading"], pts["n_pairs"], prm, min_members=5, copy=False)
@@ -580,7 +583,7 @@ def main():
     # leaves that stream idle, so event time and wall time must agree; both are reported)
     estream = torch.cuda.ExternalStream(int(eng.lib.icl_stream(eng.ctx)), device=torch.device("cuda", local))
 
-    def timed(step):
+    def timed(step, after=None):
         wall, evms, out = 0.0, 0.0, None
         for _ in range(args.steps):
             flush_l2()
@@ -593,9 +596,11 @@ def main():
             torch.cuda.synchronize()
             wall += time.perf_counter() - t0
             evms += e0.elapsed_time(e1)
+            if after:
+                after()
         return wall, evms * 1e-3, out
 
-    t_res, ev_res, blocks = timed(step_resident)
+    t_res, ev_res, blocks = timed(step_resident, read_phase_clocks)
     # ---- e2e: host buffers in, blocks on the host out ----------------------------------------------------------
     for _ in range(2):
         step_e2e()
@@ -609,6 +614,7 @@ def main():
         dev_ms.clear()
         for _ in range(3):
             step_resident()
+            read_phase_clocks()
         dp_only_ms = float(np.mean(dev_ms["chain"]))
         eng.stream_rank = True
     # ---- the same steps with numpy itself ranking on the host (what every step did before the device reproduced numpy's
@@ -620,7 +626,7 @@ def main():
             eng.rank_mode = "host"
             for _ in range(2):
                 step_resident()
-            t_h, ev_h, _ = timed(step_resident)
+            t_h, ev_h, _ = timed(step_resident, read_phase_clocks)
             host_rank_ms = float(np.mean(dev_ms["host_rank"][-args.steps:]))
             if world > 1:
                 th = torch.tensor([t_h], dtype=torch.float64, device="cuda")

@@ -285,7 +285,8 @@ class IclEngine:
                 return None               # not part of the field set that was asked for (`fields = "writer"`)
             if n == 0:
                 return np.zeros(0, dt)
-            a = np.ctypeslib.as_array(ptr, shape=(n,))
+            # (np.frombuffer over the address: half the cost of np.ctypeslib.as_array, which is 3 us per array and step)
+            a = np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(C.cast(ptr, C.c_void_p).value), dt, n)
             return a.copy() if copy else a
         res = Blocks(arr(out.pair, nb, np.int32), arr(out.dir, nb, np.int32), arr(out.score, nb, np.int64),
                      arr(out.m, nb, np.int32), arr(out.L, nb, np.int32), arr(out.N, nb, np.int32),
