@@ -120,7 +120,7 @@ struct icl_ctx {
     // output staging (blocks the caller gets, emission order)
     Buf<uint32_t> o_src, o_ms, o_e;  // accepted-block index, member scratch slice and emission position of every output block
     icl_blocks dv{}, hv{};           // views into d_stage and into the pinned host staging (same layout)
-    size_t stage_members_at = 0, stage_bytes = 0, stage_blocks_lean_end = 0, stage_members_lean_end = 0;
+    size_t stage_members_at = 0, stage_bytes = 0, stage_blocks_lean_end = 0, stage_members_lean_end = 0, stage_praw_at = 0, stage_late_at = 0;
     int32_t out_fields = 0;          // ICL_FIELDS_* of the current icl_extract_fields
     Buf<uint8_t> d_stage;
     uint8_t *h_stage = nullptr;
@@ -2028,15 +2028,22 @@ struct Stage {                               // bump allocator over the context'
 // layout — the per-block arrays first, the per-gene-pair arrays behind them (they are filled and copied separately).
 static int stage_layout(icl_ctx *c, int64_t NBo, int64_t NMo) {
     Status &st = c->st;
-    // what the collinearity-file writer reads comes first in both parts, so that ICL_FIELDS_WRITER is two shorter copies
-    size_t members_at = 0, blocks_lean_end = 0, members_lean_end = 0;
+    // Order of the per-block arrays: what the collinearity-file writer reads first (ICL_FIELDS_WRITER copies less), and in
+    // both groups the arrays the times pass does not touch before the ones it fills — those leave early, on the side stream
+    // under that pass; only p_raw (and N, N1) are copied behind it:
+    //   [pair score m member_off | p_raw] [dir L L1 L2 | N N1] [loc1 loc2 | member_idx]
+    size_t members_at = 0, blocks_lean_end = 0, members_lean_end = 0, praw_at = 0, late_at = 0;
     auto layout = [&](Stage &g, icl_blocks &o) {
         o.pair = g.take<int32_t>(NBo); o.score = g.take<int64_t>(NBo); o.m = g.take<int32_t>(NBo);
-        o.p_raw = g.take<double>(NBo); o.member_off = g.take<int64_t>(NBo + 1);
+        o.member_off = g.take<int64_t>(NBo + 1);
+        o.p_raw = g.take<double>(NBo);
+        praw_at = (size_t)((uint8_t *)o.p_raw - g.base);
         o.dir = g.take<int32_t>(NBo);
         blocks_lean_end = (size_t)((uint8_t *)o.dir - g.base);
-        o.L = g.take<int32_t>(NBo); o.N = g.take<int32_t>(NBo); o.N1 = g.take<int64_t>(NBo);
-        o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo);
+        o.L = g.take<int32_t>(NBo); o.L1 = g.take<int32_t>(NBo); o.L2 = g.take<int32_t>(NBo);
+        o.N = g.take<int32_t>(NBo);
+        late_at = (size_t)((uint8_t *)o.N - g.base);
+        o.N1 = g.take<int64_t>(NBo);
         o.loc1 = g.take<int32_t>(NMo);
         members_at = (size_t)((uint8_t *)o.loc1 - g.base);
         o.loc2 = g.take<int32_t>(NMo);
@@ -2070,6 +2077,8 @@ static int stage_layout(icl_ctx *c, int64_t NBo, int64_t NMo) {
     c->stage_bytes = ds.used;
     c->stage_blocks_lean_end = blocks_lean_end;
     c->stage_members_lean_end = members_lean_end;
+    c->stage_praw_at = praw_at;
+    c->stage_late_at = late_at;
     return 0;
 }
 
@@ -4269,6 +4278,11 @@ extern "C" int icl_extract_fields(icl_ctx *c, const int32_t *argsort_fwd, const 
         const size_t end = c->out_fields == ICL_FIELDS_WRITER ? c->stage_members_lean_end : c->stage_bytes;
         if (end > c->stage_members_at)
             ICL_CUDA(st, d2h(c->h_stage + c->stage_members_at, c->d_stage.p + c->stage_members_at, end - c->stage_members_at, s2));
+        // ... and the per-block arrays the times pass does not fill (written by extract_output_records above)
+        if (c->stage_praw_at > 0) ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, c->stage_praw_at, s2));
+        if (c->out_fields != ICL_FIELDS_WRITER && c->stage_late_at > c->stage_blocks_lean_end)
+            ICL_CUDA(st, d2h(c->h_stage + c->stage_blocks_lean_end, c->d_stage.p + c->stage_blocks_lean_end,
+                             c->stage_late_at - c->stage_blocks_lean_end, s2));
     }
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaEventRecord(c->ev_join, s2));
@@ -4298,7 +4312,10 @@ extern "C" int icl_extract_fields(icl_ctx *c, const int32_t *argsort_fwd, const 
             o.p_raw[g] = icl_p_raw(o.score[g], o.m[g], g0, N1, N, o.L1[g], o.L2[g]);
         }));
     }
-    ICL_CUDA(st, d2h(c->h_stage, c->d_stage.p, c->out_fields == ICL_FIELDS_WRITER ? c->stage_blocks_lean_end : c->stage_members_at, s));
+    // behind the times pass: p_raw (and N, N1)
+    ICL_CUDA(st, d2h(c->h_stage + c->stage_praw_at, c->d_stage.p + c->stage_praw_at, c->stage_blocks_lean_end - c->stage_praw_at, s));
+    if (c->out_fields != ICL_FIELDS_WRITER)
+        ICL_CUDA(st, d2h(c->h_stage + c->stage_late_at, c->d_stage.p + c->stage_late_at, c->stage_members_at - c->stage_late_at, s));
 #ifndef ICL_EMU
     ICL_CUDA(st, cudaStreamWaitEvent(s, c->ev_join, 0));
 #endif
