@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEEP = ("k_chain_ring<true, false>", "k_chain_ring<(bool)1, (bool)0>", "k_edges_enum", "k_edges_place", "k_xss_argsort<unsigned short, 8, 8>",
         "k_xss_argsort<int, 8, 8>", "k_np_argsort<unsigned short>", "k_tree_heads", "k_tree_walk_small", "k_tree_walk_staged",
-        "k_pvalue_owned<true>", "k_pvalue_owned<(bool)1>", "k_input_stats")
+        "k_pvalue_owned<true>", "k_pvalue_owned<(bool)1>", "k_input_stats", "k_item", "k_block_stats")
 out = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "wgdi_b200", "libicl_b200.so")], capture_output=True, text=True).stdout
 rows = []
 for f in re.split(r"\n\s*Function : ", out)[1:]:
