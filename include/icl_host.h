@@ -9,6 +9,9 @@
  *   icl_host_grade         wgdi/run_colliearity.py:59-86 (deal_blast_for_genomes), except for queries whose tied
  *                          bit scores straddle a class boundary: those are reported and re-ranked by the caller
  *                          with numpy's own unstable argsort (SURVEY.md hazard H2)
+ *   icl_host_ingest_*      the whole ingest of `comparison = genomes` in one handle: icl_host_read_m8 + icl_host_grade +
+ *                          the point table of wgdi/run_colliearity.py:103-121,164-166 (chromosome pair, loc1, loc2,
+ *                          grading per kept hit), so that nothing per hit is touched by Python
  *   icl_host_write_blocks  wgdi/run_colliearity.py:143-155,181-199 (gene names, strands, text assembly, file)
  *
  * All functions return 0 or a negative code and fill `err` (NUL-terminated, truncated to errlen).
@@ -59,6 +62,46 @@ void icl_host_free_hits(icl_hits *hits);
 int icl_host_grade(int64_t n, const int32_t *query, const double *bits, int32_t n_query,
                    int32_t multiple, int32_t repeat_number, const int32_t *grading3,
                    int32_t *grade_out, uint8_t *ambiguous, int32_t threads, char *err, int32_t errlen);
+
+/*
+ * Fused ingest of one `comparison = genomes` run (wgdi/base.py:172-183 + wgdi/run_colliearity.py:59-86,103-121).
+ *
+ *   icl_host_ingest_open     parses and filters like icl_host_read_m8, removes the duplicates and grades like
+ *                            icl_host_grade with classes 1 / 2 / 3 (blue_extra = 4 for -icl: bluenum = 4 + rednum, :64).
+ *                            Queries whose classes depend on the order of tied bit scores are NOT graded: their hits
+ *                            (duplicates removed, file order) are set aside for the caller.
+ *   icl_host_ingest_ambiguous  amb_off[n_amb_queries + 1], amb_bits[n_amb_hits]: the bit scores of those queries, in the
+ *                            order `group.sort_values(by=11)` of :67 sees them.
+ *   icl_host_ingest_set_classes  amb_cls[n_amb_hits] in {0 (dropped), 1, 2, 3}: what the caller's numpy argsort — the
+ *                            reference's own unstable sort, hazard H2 — makes of them.
+ *   icl_host_ingest_count    present[nc1 * nc2] = 1 where a graded hit falls on (chromosome code 1, chromosome code 2);
+ *                            n_points = graded hits (class > 0).  chr1 / chr2: chromosome code per gene row.
+ *   icl_host_ingest_points   the points in file order: pair_id = pair_rank[chr1 * nc2 + chr2] (the caller numbers the
+ *                            present pairs in the string order of :118), loc1 / loc2 = order of the two genes,
+ *                            grading = grading3[class - 1], grade_class = class - 1.  Needs icl_host_ingest_count first.
+ */
+typedef struct icl_ingest icl_ingest;
+typedef struct icl_ingest_info {
+    int64_t n_hits;        /* rows that survive the filters of wgdi/base.py:178-180 */
+    int64_t n_rows_file;
+    int32_t bits_is_int;   /* as in icl_hits: the caller ranks the ambiguous queries on int64 keys when pandas would */
+    int64_t n_amb_queries;
+    int64_t n_amb_hits;
+} icl_ingest_info;
+
+int icl_host_ingest_open(const char *path, int32_t reverse, double min_score, double max_evalue,
+                         const char *ids1, const int64_t *off1, int64_t n1,
+                         const char *ids2, const int64_t *off2, int64_t n2,
+                         int32_t multiple, int32_t repeat_number, int32_t blue_extra,
+                         int32_t threads, icl_ingest **out, icl_ingest_info *info, char *err, int32_t errlen);
+int icl_host_ingest_ambiguous(const icl_ingest *h, int64_t *amb_off, double *amb_bits);
+int icl_host_ingest_set_classes(icl_ingest *h, const int8_t *amb_cls);
+int icl_host_ingest_count(icl_ingest *h, const int32_t *chr1, const int32_t *chr2, int32_t nc1, int32_t nc2,
+                          uint8_t *present, int64_t *n_points);
+int icl_host_ingest_points(const icl_ingest *h, const int32_t *chr1, const int64_t *order1, const int32_t *chr2,
+                           const int64_t *order2, int32_t nc2, const int32_t *pair_rank, const int32_t *grading3,
+                           int32_t *pair_id, int32_t *loc1, int32_t *loc2, int32_t *grading, int32_t *grade_class);
+void icl_host_ingest_close(icl_ingest *h);
 
 /*
  * Write the collinearity file.  For every selected block b (already filtered and ordered by the caller):

@@ -25,7 +25,9 @@ def test_host_library_exports_declared_symbols(host):
     lib = ctypes.CDLL(host.LIB_PATH)
     header = open(os.path.join(ROOT, "include", "icl_host.h")).read()
     declared = set(re.findall(r"\b(icl_host_[a-z_0-9]+)\s*\(", header))
-    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks", "icl_host_place_blocks"}
+    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks", "icl_host_place_blocks",
+                        "icl_host_ingest_open", "icl_host_ingest_ambiguous", "icl_host_ingest_set_classes",
+                        "icl_host_ingest_count", "icl_host_ingest_points", "icl_host_ingest_close"}
     for name in declared:
         assert hasattr(lib, name)
 
@@ -126,6 +128,84 @@ def test_native_grading_matches_oracle_with_ties(host):
         assert (got == icl_oracle.grade_hits(q, bits, mult, rn, [50, 30, 25])).all()
 
 
+def _random_m8(rng, path, genes, n_rows, sorted_by_query, tie_span):
+    """A BLAST-like table with duplicate pairs, self hits, unknown ids, sub-threshold rows and many tied bit scores."""
+    q = rng.integers(0, len(genes), n_rows)
+    if sorted_by_query:
+        q = np.sort(q)
+    s = rng.integers(0, len(genes) + 3, n_rows)                     # a few subjects are not in the gene table
+    bits = rng.integers(95, 100 + tie_span, n_rows)
+    ev = rng.choice(["1e-30", "2.5e-7", "0.0", "1e-5", "3e-4", "9.9e-06"], n_rows, p=[0.5, 0.2, 0.1, 0.05, 0.1, 0.05])
+    names = list(genes) + ["zz1", "zz2", "zz3"]
+    with open(path, "w") as f:
+        for a, b, e, sc in zip(q, s, ev, bits):
+            f.write("\t".join([genes[a], names[b], "90.1", "100", "1", "0", "1", "100", "1", "100", e, str(sc)]) + "\n")
+
+
+@pytest.mark.parametrize("sorted_by_query", [True, False])
+def test_fused_ingest_equals_the_pandas_readers(host, tmp_path, sorted_by_query):
+    """icl_host_ingest_* (parse + filters + duplicates + grading + point table in one handle) against the reference-like
+    pandas path and the oracle's grading, on tables full of boundary ties: query-grouped like BLAST writes them, and
+    shuffled (the grouping by query must not depend on the file order)."""
+    import pandas as pd
+    from wgdi_b200 import base
+    from wgdi_b200.ingest import classes_of_ambiguous, pair_ids, pair_table
+    rng = np.random.default_rng(5 + sorted_by_query)
+    n_amb = 0
+    for trial in range(12):
+        ng = int(rng.integers(3, 60))
+        genes = [f"gene{i:03d}_{'x' * int(rng.integers(0, 30))}" for i in range(ng)]     # ids longer than a map slot too
+        chrom = rng.integers(0, 4, ng)
+        order = rng.integers(1, 50, ng).astype(np.int64)
+        gff = pd.DataFrame({"chr": [f"c{c}" for c in chrom]}, index=pd.Index(genes))
+        p = tmp_path / f"t{trial}.m8"
+        _random_m8(rng, p, genes, int(rng.integers(1, 3000)), sorted_by_query, tie_span=int(rng.integers(2, 40)))
+        mult, rn = int(rng.integers(1, 4)), int(rng.integers(2, 30))
+        grading = [50, 30, 25]
+        # reference-like path
+        blast = base.newblast(str(p), 100, 1e-5, gff, gff, "false")
+        g1, g2, bits = blast["g1"].to_numpy(), blast["g2"].to_numpy(), blast[11].to_numpy()
+        grade = icl_oracle.grade_hits(g1, bits, mult, rn, [1, 2, 3])
+        ok = grade > 0
+        chr_names, chr_code = np.unique(np.array([f"c{c}" for c in chrom]), return_inverse=True)
+        pid, names = pair_ids(list(chr_names), list(chr_names), chr_code[g1[ok]], chr_code[g2[ok]])
+        # fused path
+        ids = host.pack_strings(genes)
+        with host.Ingest(str(p), False, 100, 1e-5, ids, ids, mult, rn, threads=int(rng.integers(1, 6))) as ing:
+            assert ing.n_hits == len(g1)
+            off, abits = ing.ambiguous()
+            assert abits.dtype == bits.dtype
+            n_amb += len(off) - 1
+            ing.set_classes(classes_of_ambiguous(off, abits, mult, rn))
+            present, n = ing.count(chr_code, chr_code, len(chr_names), len(chr_names))
+            assert n == int(ok.sum())
+            table, names2 = pair_table(list(chr_names), list(chr_names), present)
+            pts = ing.points(order, order, len(chr_names), table, grading)
+        assert names2 == names
+        assert (pts["pair_id"] == pid).all() and (pts["loc1"] == order[g1[ok]]).all() and (pts["loc2"] == order[g2[ok]]).all()
+        assert (pts["grade_class"] == grade[ok] - 1).all() and (pts["grading"] == np.asarray(grading)[grade[ok] - 1]).all()
+    assert n_amb > 20                                   # the numpy re-ranking was exercised
+
+
+def test_fused_ingest_errors_and_empty_inputs(host, tmp_path):
+    ids = host.pack_strings(["g0", "g1"])
+    _write(tmp_path / "bad.m8", "g0\tg1\t1\n")
+    with pytest.raises(host.HostError):
+        host.Ingest(str(tmp_path / "bad.m8"), False, 100, 1e-5, ids, ids, 1, 5)
+    with pytest.raises(host.HostError):
+        host.Ingest(str(tmp_path / "missing.m8"), False, 100, 1e-5, ids, ids, 1, 5)
+    _write(tmp_path / "empty.m8", "")
+    with host.Ingest(str(tmp_path / "empty.m8"), False, 100, 1e-5, ids, ids, 1, 5) as ing:
+        assert ing.n_hits == 0
+        off, bits = ing.ambiguous()
+        assert len(off) == 1 and len(bits) == 0
+        ing.set_classes(np.zeros(0, np.int8))
+        present, n = ing.count(np.zeros(2, np.int32), np.zeros(2, np.int32), 1, 1)
+        assert n == 0 and not present.any()
+        pts = ing.points(np.ones(2, np.int64), np.ones(2, np.int64), 1, np.zeros(1, np.int32), [50, 30, 25])
+        assert all(len(v) == 0 for v in pts.values())
+
+
 @pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev", "cross_chrom"])
 def test_native_and_pandas_paths_write_the_same_file(host, emu_backend, case, tmp_path):
     """conf in -> file out through the native parser / writer and through the pandas readers (fake device backend)."""
@@ -136,15 +216,15 @@ def test_native_and_pandas_paths_write_the_same_file(host, emu_backend, case, tm
     os.chdir(tmp_path)
     try:
         texts = {}
-        for mode in ("native", "pandas"):
+        for mode in ("native", "native-steps", "pandas"):
             opts = [(k, v if k != "savefile" else f"{mode}.txt") for k, v in base.load_conf("icl.conf", "collinearity")]
             with contextlib.redirect_stdout(io.StringIO()):
                 m = mycollinearity(opts + [("ingest", mode)])
-                assert m.native == (mode == "native")
+                assert m.native == (mode != "pandas")
                 with pytest.raises(SystemExit):
                     m.run()
             texts[mode] = open(f"{mode}.txt").read()
-        assert texts["native"] == texts["pandas"] and len(texts["native"]) > 1000
+        assert texts["native"] == texts["pandas"] == texts["native-steps"] and len(texts["native"]) > 1000
     finally:
         os.chdir(cwd)
 

@@ -21,6 +21,11 @@ class icl_hits(C.Structure):
                 ("bits", C.POINTER(C.c_double))]
 
 
+class icl_ingest_info(C.Structure):
+    _fields_ = [("n_hits", C.c_int64), ("n_rows_file", C.c_int64), ("bits_is_int", C.c_int32),
+                ("n_amb_queries", C.c_int64), ("n_amb_hits", C.c_int64)]
+
+
 def available():
     return os.path.exists(LIB_PATH)
 
@@ -36,6 +41,14 @@ def load():
         lib.icl_host_grade.argtypes = [i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32]
         lib.icl_host_write_blocks.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
                                               vp, i64, vp, vp, vp, i32, vp, i32]
+        lib.icl_host_ingest_open.argtypes = [C.c_char_p, i32, dbl, dbl, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32,
+                                             C.POINTER(vp), C.POINTER(icl_ingest_info), vp, i32]
+        lib.icl_host_ingest_ambiguous.argtypes = [vp, vp, vp]
+        lib.icl_host_ingest_set_classes.argtypes = [vp, vp]
+        lib.icl_host_ingest_count.argtypes = [vp, vp, vp, i32, i32, vp, C.POINTER(i64)]
+        lib.icl_host_ingest_points.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.icl_host_ingest_close.argtypes = [vp]
+        lib.icl_host_ingest_close.restype = None
         lib.icl_host_place_blocks.argtypes = [i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
         _LIB = lib
     return _LIB
@@ -106,8 +119,13 @@ def _call(fn, *args):
 
 def pack_strings(values):
     """(bytes, offsets[n+1]) of a sequence of str."""
-    enc = [str(v).encode() for v in values]
-    off = np.zeros(len(enc) + 1, np.int64)
+    vals = [str(v) for v in (values.tolist() if hasattr(values, "tolist") else values)]
+    off = np.zeros(len(vals) + 1, np.int64)
+    joined = "".join(vals).encode()
+    np.cumsum(np.fromiter(map(len, vals), np.int64, len(vals)), out=off[1:])
+    if int(off[-1]) == len(joined):                       # ASCII ids: characters are bytes
+        return joined, off
+    enc = [v.encode() for v in vals]
     np.cumsum([len(b) for b in enc], out=off[1:])
     return b"".join(enc), off
 
@@ -141,6 +159,85 @@ def read_m8(path, reverse, min_score, max_evalue, ids1, ids2, threads=None):
                     n_rows_file=int(out.n_rows_file))
     finally:
         lib.icl_host_free_hits(C.byref(out))
+
+
+class Ingest:
+    """The fused ingest of `comparison = genomes` (icl_host_ingest_*): m8 table -> graded points with nothing per hit
+    handled in Python.  Use as a context manager.
+
+        with Ingest(path, reverse, score, evalue, ids1, ids2, multiple, repeat_number) as ing:
+            off, bits = ing.ambiguous()          # queries whose classes depend on numpy's tie order (hazard H2)
+            ing.set_classes(cls)                 # the caller's numpy ranking of exactly those
+            present, n = ing.count(chr1, chr2, nc1, nc2)
+            pts = ing.points(order1, order2, nc2, pair_rank, grading)
+    """
+
+    def __init__(self, path, reverse, min_score, max_evalue, ids1, ids2, multiple, repeat_number, blue_extra=4, threads=None):
+        lib = load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        self.info = icl_ingest_info()
+        b1, o1 = ids1
+        b2, o2 = ids2
+        same = ids1 is ids2
+        p1 = C.cast(C.c_char_p(b1), C.c_void_p)
+        p2 = p1 if same else C.cast(C.c_char_p(b2), C.c_void_p)
+        _call(lib.icl_host_ingest_open, str(path).encode(), 1 if reverse else 0, float(min_score), float(max_evalue),
+              p1, o1.ctypes.data, len(o1) - 1, p2, (o1 if same else o2).ctypes.data, len(o2) - 1,
+              int(multiple), int(repeat_number), int(blue_extra), int(threads or threads_default()),
+              C.byref(self._h), C.byref(self.info))
+        self.n_hits = int(self.info.n_hits)
+        self._n_points = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if self._h:
+            self._lib.icl_host_ingest_close(self._h)
+            self._h = C.c_void_p()
+
+    def ambiguous(self):
+        """(offsets[n_queries + 1], bit scores typed like pandas would infer column 11) of the queries left ungraded."""
+        off = np.zeros(int(self.info.n_amb_queries) + 1, np.int64)
+        bits = np.zeros(int(self.info.n_amb_hits), np.float64)
+        if self._lib.icl_host_ingest_ambiguous(self._h, off.ctypes.data, bits.ctypes.data):
+            raise HostError("icl_host_ingest_ambiguous failed")
+        return off, (bits.astype(np.int64) if self.info.bits_is_int else bits)
+
+    def set_classes(self, cls):
+        cls = np.ascontiguousarray(cls, np.int8)
+        if len(cls) != int(self.info.n_amb_hits) or self._lib.icl_host_ingest_set_classes(self._h, cls.ctypes.data):
+            raise HostError("icl_host_ingest_set_classes: one class in 0..3 per ambiguous hit expected")
+
+    def count(self, chr1, chr2, nc1, nc2):
+        self._chr = (np.ascontiguousarray(chr1, np.int32), np.ascontiguousarray(chr2, np.int32))
+        present = np.zeros(max(int(nc1), 1) * max(int(nc2), 1), np.uint8)
+        n = C.c_int64(0)
+        rc = self._lib.icl_host_ingest_count(self._h, self._chr[0].ctypes.data, self._chr[1].ctypes.data, max(int(nc1), 1),
+                                             max(int(nc2), 1), present.ctypes.data, C.byref(n))
+        if rc:
+            raise HostError(f"icl_host_ingest_count failed ({rc})")
+        self._n_points = int(n.value)
+        return present, self._n_points
+
+    def points(self, order1, order2, nc2, pair_rank, grading):
+        """dict(pair_id, loc1, loc2, grading, grade_class), int32, file order — after `count`."""
+        n = self._n_points
+        o1 = np.ascontiguousarray(order1, np.int64)
+        o2 = np.ascontiguousarray(order2, np.int64)
+        rank = np.ascontiguousarray(pair_rank, np.int32)
+        g3 = np.ascontiguousarray(list(grading)[:3], np.int32)
+        out = {k: np.empty(n, np.int32) for k in ("pair_id", "loc1", "loc2", "grading", "grade_class")}
+        rc = self._lib.icl_host_ingest_points(self._h, self._chr[0].ctypes.data, o1.ctypes.data, self._chr[1].ctypes.data,
+                                              o2.ctypes.data, max(int(nc2), 1), rank.ctypes.data, g3.ctypes.data,
+                                              *[out[k].ctypes.data for k in ("pair_id", "loc1", "loc2", "grading", "grade_class")])
+        if rc:
+            raise HostError(f"icl_host_ingest_points failed ({rc})")
+        return out
 
 
 def grade(query, bits, n_query, multiple, repeat_number, grading, threads=None):

@@ -29,9 +29,11 @@ def newlens(file, position):
     return lens
 
 
-def newgff(file):
-    """wgdi/base.py:186-195 — frame indexed by gene id with chr (str), start, end, strand (str), order."""
-    gff = pd.read_csv(file, sep="\t", header=None, index_col=1)
+def newgff(file, usecols=None):
+    """wgdi/base.py:186-195 — frame indexed by gene id with chr (str), start, end, strand (str), order.
+    usecols: the columns to parse (the -icl driver passes the six the path reads; a seventh, free-text column costs a
+    third of the parse); None reads them all like the reference."""
+    gff = pd.read_csv(file, sep="\t", header=None, index_col=1, usecols=usecols)
     gff.rename(columns={0: "chr", 2: "start", 3: "end", 4: "strand", 5: "order"}, inplace=True)
     gff["chr"] = gff["chr"].astype(str)
     gff["start"] = gff["start"].astype(np.int64)

@@ -114,6 +114,36 @@ def grade_hits_native(q, bits, n_query, multiple, repeat_number, grading):
     return out
 
 
+def classes_of_ambiguous(off, bits, multiple, repeat_number, blue_extra=4):
+    """Rank class (0 dropped / 1 / 2 / 3) per hit of the queries the native ingest left ungraded (`_host.Ingest.ambiguous`):
+    every query's bit scores, duplicates removed and in file order, go through the reference's own call — pandas'
+    `sort_values(by=11, ascending=False)` = numpy's unstable argsort (wgdi/run_colliearity.py:67, hazard H2)."""
+    rn = int(repeat_number)
+    red = min(int(multiple), rn)
+    blue = min(int(blue_extra) + int(multiple), rn)
+    cls = np.zeros(len(bits), np.int8)
+    for q in range(len(off) - 1):
+        a, b = int(off[q]), int(off[q + 1])
+        ranked = nargsort_desc(bits[a:b])[:rn] + a
+        cls[ranked[:red]] = 1
+        cls[ranked[red:blue]] = 2
+        cls[ranked[blue:rn]] = 3
+    return cls
+
+
+def pair_table(chr1_names, chr2_names, present):
+    """From the chromosome pairs that hold a point (`present[c1 * nc2 + c2]`): (rank table over all codes, names in the
+    sorted (chr1, chr2) STRING order pandas' groupby iterates, wgdi/run_colliearity.py:118) — `pair_ids` for the native
+    ingest, which numbers the points itself."""
+    nc2 = max(len(chr2_names), 1)
+    uniq = np.flatnonzero(present)
+    names = [(str(chr1_names[u // nc2]), str(chr2_names[u % nc2])) for u in uniq]
+    order = sorted(range(len(uniq)), key=lambda i: names[i])
+    table = np.zeros(len(present), np.int32)
+    table[uniq[order]] = np.arange(len(uniq), dtype=np.int32)
+    return table, [names[i] for i in order]
+
+
 def grade_hits_chromosomes(name_rank, g1, g2, pair_code, bits, multiple, repeat_number, grading, classes=False):
     """`deal_blast_for_chromosomes` (wgdi/run_colliearity.py:42-57): stable sort by (query id string ascending,
     bit score descending) (:44); cumcount per subject gene inside each chromosome pair in that order (:46); keep

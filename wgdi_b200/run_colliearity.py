@@ -19,7 +19,8 @@ import numpy as np
 from . import _host, base
 from .engine import ChainParams, IclEngine
 from .params import compact_points
-from .ingest import grade_hits, grade_hits_chromosomes, grade_hits_native, pair_ids
+from .ingest import (classes_of_ambiguous, grade_hits, grade_hits_chromosomes, grade_hits_native, pair_ids,
+                     pair_table)
 
 
 class mycollinearity():
@@ -48,7 +49,11 @@ class mycollinearity():
         self.devices = [int(k) for k in str(getattr(self, 'devices', self.device)).split(',') if k.strip() != '']
         # extra, optional key: `ingest = pandas` forces the reference-like pandas readers of wgdi_b200.base;
         # the default uses the native parser / writer (libicl_host.so) when it is built.  Same results.
-        self.native = getattr(self, 'ingest', 'native').lower() != 'pandas' and _host.available()
+        # (`ingest = native-steps`: the native parser and grading as separate calls with numpy in between — the path the
+        # fused ingest is tested against.)
+        ingest = getattr(self, 'ingest', 'native').lower()
+        self.native = ingest != 'pandas' and _host.available()
+        self.fused = ingest != 'native-steps'
         # extra, optional key: `rank = device` takes the extraction order from a stable sort on the GPU instead of numpy's
         # unstable argsort on the host — NOT the reference's tie order (include/icl_b200.h, icl_rank_device); default numpy
         self.rank = str(getattr(self, 'rank', 'numpy')).strip().lower()
@@ -65,15 +70,18 @@ class mycollinearity():
         lens1 = base.newlens(self.lens1, 'order')
         lens2 = base.newlens(self.lens2, 'order')
         same = self.gff2 == self.gff1 and self.lens2 == self.lens1       # self comparison: parse the tables once
-        gff1 = base.newgff(self.gff1)
+        gff1 = base.newgff(self.gff1, usecols=range(6))
         gff1 = gff1[gff1['chr'].isin(lens1.index)]        # :96-97
-        gff2 = gff1 if same else base.newgff(self.gff2)
+        gff2 = gff1 if same else base.newgff(self.gff2, usecols=range(6))
         if not same:
             gff2 = gff2[gff2['chr'].isin(lens2.index)]
         mode = self.comparison.lower()                    # :108-111
         if mode not in ('genomes', 'chromosomes'):
             raise ValueError(f"comparison = {self.comparison}: expected 'genomes' or 'chromosomes'")
-        if self.native and not _host.is_compressed(self.blast):    # compressed tables: pandas decompresses (base.py:174)
+        native = self.native and not _host.is_compressed(self.blast)       # compressed tables: pandas decompresses (base.py:174)
+        if native and self.fused and mode == 'genomes':
+            return self._load_points_fused(gff1, gff2, same)
+        if native:
             ids1 = _host.pack_strings(gff1.index)
             ids2 = ids1 if same else _host.pack_strings(gff2.index)
             hits = _host.read_m8(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2)
@@ -104,6 +112,30 @@ class mycollinearity():
         pid, names = pair_ids(t1['chr_names'], t2['chr_names'], t1['chr_code'][g1], t2['chr_code'][g2])
         return dict(pair_id=pid, loc1=t1['order'][g1].astype(np.int32), loc2=t2['order'][g2].astype(np.int32),
                     grading=grade.astype(np.int32), grade_class=cls.astype(np.int32), pair_names=names, genes1=t1, genes2=t2)
+
+    def _load_points_fused(self, gff1, gff2, same):
+        """`load_points` for `comparison = genomes` through libicl_host.so's fused ingest (include/icl_host.h,
+        icl_host_ingest_*): parse, filters, duplicates, per-query grading and the point table are native and threaded;
+        Python sees the gene tables, the few queries with boundary ties (numpy ranks them, hazard H2) and the names of
+        the chromosome pairs."""
+        ids1 = _host.pack_strings(gff1.index)
+        ids2 = ids1 if same else _host.pack_strings(gff2.index)
+        t1 = _gene_table(gff1)
+        t2 = t1 if same else _gene_table(gff2)
+        with _host.Ingest(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2,
+                          int(self.multiple), int(self.repeat_number)) as ing:
+            off, bits = ing.ambiguous()
+            ing.set_classes(classes_of_ambiguous(off, bits, int(self.multiple), int(self.repeat_number)))
+            nc1, nc2 = len(t1['chr_names']), len(t2['chr_names'])
+            present, n = ing.count(t1['chr_code'], t2['chr_code'], nc1, nc2)
+            print(f"The filtered homologous gene pairs are {n}.\n")       # :112
+            if n < 1:
+                print("Stopped!\n\nIt may be that the id1 and id2 in the BLAST file do not match with (gff1, lens1) and (gff2, lens2).")
+                sys.exit(1)                               # :113-115
+            table, names = pair_table(t1['chr_names'], t2['chr_names'], present)
+            pts = ing.points(t1['order'], t2['order'], nc2, table, self.grading)
+        pts.update(pair_names=names, genes1=t1, genes2=t2)
+        return pts
 
     # ---- wgdi/run_colliearity.py:88-156 ----------------------------------------------------------
     def run(self):
