@@ -121,6 +121,25 @@ int icl_host_write_blocks(const char *path, int64_t n_sel,
                           int32_t threads, char *err, int32_t errlen);
 
 /*
+ * icl_host_write_blocks with the headers assembled natively (wgdi/run_colliearity.py:143-151,194-195):
+ *   "# Alignment <k>:" + the text " score=<score> pvalue=<ptext[pidx]> N=<members> <pair_text[pair]> plus|minus" cut at its
+ *   first ':' (the reference splits the finished header at ':' again, which truncates it for a chromosome name with one);
+ *   plus iff loc2 of the first gene pair < loc2 of the second.  ptext: the distinct p values as Python prints them
+ *   (the caller formats those few), pair_text: "<chr1>&<chr2>" per pair id.
+ */
+int icl_host_write_collinearity(const char *path, int64_t n_sel, const int64_t *score,
+                                const char *ptext, const int64_t *ptext_off, const int32_t *pidx,
+                                const char *pair_text, const int64_t *pair_text_off, const int32_t *pair,
+                                const int64_t *mem_begin, const int64_t *mem_end,
+                                const int32_t *loc1, const int32_t *loc2,
+                                const int32_t *chr1_code, const int32_t *chr2_code,
+                                const int64_t *row_of1, int64_t maxo1, const char *names1, const int64_t *name_off1,
+                                const int32_t *strand_code1,
+                                const int64_t *row_of2, int64_t maxo2, const char *names2, const int64_t *name_off2,
+                                const int32_t *strand_code2,
+                                int32_t threads, char *err, int32_t errlen);
+
+/*
  * One comparison sharded over several GPUs (the pairs of wgdi/run_colliearity.py:123-136 over ranks instead of worker
  * processes): write one rank's blocks straight to their place in the merged, emission-ordered arrays — what the reference's
  * parent process does when it concatenates the workers' texts in chunk order (:133-141).  A rank's blocks are pair-major, so

@@ -26,6 +26,7 @@ def test_host_library_exports_declared_symbols(host):
     header = open(os.path.join(ROOT, "include", "icl_host.h")).read()
     declared = set(re.findall(r"\b(icl_host_[a-z_0-9]+)\s*\(", header))
     assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks", "icl_host_place_blocks",
+                        "icl_host_write_collinearity",
                         "icl_host_ingest_open", "icl_host_ingest_ambiguous", "icl_host_ingest_set_classes",
                         "icl_host_ingest_count", "icl_host_ingest_points", "icl_host_ingest_close"}
     for name in declared:
@@ -204,6 +205,37 @@ def test_fused_ingest_errors_and_empty_inputs(host, tmp_path):
         assert n == 0 and not present.any()
         pts = ing.points(np.ones(2, np.int64), np.ones(2, np.int64), 1, np.zeros(1, np.int32), [50, 30, 25])
         assert all(len(v) == 0 for v in pts.values())
+
+
+def test_native_writer_equals_format_blocks(host, tmp_path):
+    """icl_host_write_collinearity (headers and body assembled natively) against the Python formatter on synthetic blocks:
+    p values of every printed form, the pvalue / over_gap filters, and a chromosome name with a ':' (the reference
+    re-cuts the finished header at ':', run_colliearity.py:147-151)."""
+    import pandas as pd
+    from types import SimpleNamespace
+    from wgdi_b200.run_colliearity import _gene_table, format_blocks, write_blocks_native
+    rng = np.random.default_rng(11)
+    def genome(chrs, per):
+        rows = [(c, f"{c.replace(':', '_')}g{i}", i + 1, "+-"[int(rng.integers(0, 2))]) for c in chrs for i in range(per)]
+        return pd.DataFrame({"chr": [r[0] for r in rows], "order": [r[2] for r in rows], "strand": [r[3] for r in rows]},
+                            index=pd.Index([r[1] for r in rows]))
+    g1, g2 = _gene_table(genome(["1", "2", "x:y"], 40)), _gene_table(genome(["A", "B:1"], 40))
+    pair_names = sorted((a, b) for a in g1["chr_names"] for b in g2["chr_names"])
+    nb = 60
+    m = rng.integers(2, 12, nb)
+    off = np.zeros(nb + 1, np.int64)
+    np.cumsum(m, out=off[1:])
+    blocks = SimpleNamespace(pair=np.sort(rng.integers(0, len(pair_names), nb)).astype(np.int32), score=rng.integers(100, 5000, nb),
+                             m=m.astype(np.int32), member_off=off,
+                             loc1=rng.integers(1, 41, off[-1]).astype(np.int32), loc2=rng.integers(1, 41, off[-1]).astype(np.int32),
+                             p_raw=rng.choice([0.0, 1e-9, 0.00004, 0.00005, 0.0001, 0.01234, 0.2, 0.99996, 1.0, 3.2], nb))
+    blocks.p_value = lambda: np.round(blocks.p_raw, 4)
+    for pvalue, over_gap in ((1.0, 2), (0.05, 5), (0.0, 2)):
+        text = format_blocks(blocks, pair_names, g1, g2, pvalue, over_gap)
+        path = tmp_path / f"w_{pvalue}_{over_gap}.txt"
+        write_blocks_native(str(path), blocks, pair_names, g1, g2, pvalue, over_gap)
+        assert open(path).read() == text
+    assert "x" in text and ":y" not in text.replace("# Alignment", "")       # the ':' cut happened
 
 
 @pytest.mark.parametrize("case", ["tiny", "cross", "tiny_rev", "cross_chrom"])

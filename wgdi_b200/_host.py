@@ -41,6 +41,8 @@ def load():
         lib.icl_host_grade.argtypes = [i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32]
         lib.icl_host_write_blocks.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
                                               vp, i64, vp, vp, vp, i32, vp, i32]
+        lib.icl_host_write_collinearity.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                    vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, i32]
         lib.icl_host_ingest_open.argtypes = [C.c_char_p, i32, dbl, dbl, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32,
                                              C.POINTER(vp), C.POINTER(icl_ingest_info), vp, i32]
         lib.icl_host_ingest_ambiguous.argtypes = [vp, vp, vp]
@@ -260,6 +262,27 @@ def write_blocks(path, headers, mem_begin, mem_end, loc1, loc2, chr1_code, chr2_
                                                   (loc2, np.int32), (chr1_code, np.int32), (chr2_code, np.int32))]
     _call(lib.icl_host_write_blocks, str(path).encode(), len(headers), C.cast(C.c_char_p(hb), C.c_void_p), ho.ctypes.data,
           *[x.ctypes.data for x in a],
+          genes1["row_of"].ctypes.data, int(genes1["maxo"]), C.cast(C.c_char_p(genes1["name_bytes"]), C.c_void_p),
+          genes1["name_off"].ctypes.data, genes1["strand_code"].ctypes.data,
+          genes2["row_of"].ctypes.data, int(genes2["maxo"]), C.cast(C.c_char_p(genes2["name_bytes"]), C.c_void_p),
+          genes2["name_off"].ctypes.data, genes2["strand_code"].ctypes.data,
+          int(threads or threads_default()))
+
+
+def write_collinearity(path, score, p_text, p_index, pair_text, pair, mem_begin, mem_end, loc1, loc2, chr1_code, chr2_code,
+                       genes1, genes2, threads=None):
+    """icl_host_write_collinearity: headers and body of the collinearity file from arrays (one entry per emitted block)."""
+    lib = load()
+    pb, po = pack_strings(p_text)
+    nb, no = pack_strings(pair_text)
+    a = [np.ascontiguousarray(x, dt) for x, dt in ((score, np.int64), (p_index, np.int32), (pair, np.int32),
+                                                  (mem_begin, np.int64), (mem_end, np.int64), (loc1, np.int32),
+                                                  (loc2, np.int32), (chr1_code, np.int32), (chr2_code, np.int32))]
+    sc, pi, pr, mb, me, l1, l2, c1, c2 = a
+    _call(lib.icl_host_write_collinearity, str(path).encode(), len(sc), sc.ctypes.data,
+          C.cast(C.c_char_p(pb), C.c_void_p), po.ctypes.data, pi.ctypes.data,
+          C.cast(C.c_char_p(nb), C.c_void_p), no.ctypes.data, pr.ctypes.data,
+          mb.ctypes.data, me.ctypes.data, l1.ctypes.data, l2.ctypes.data, c1.ctypes.data, c2.ctypes.data,
           genes1["row_of"].ctypes.data, int(genes1["maxo"]), C.cast(C.c_char_p(genes1["name_bytes"]), C.c_void_p),
           genes1["name_off"].ctypes.data, genes1["strand_code"].ctypes.data,
           genes2["row_of"].ctypes.data, int(genes2["maxo"]), C.cast(C.c_char_p(genes2["name_bytes"]), C.c_void_p),

@@ -876,6 +876,52 @@ extern "C" int icl_host_write_blocks(const char *path, int64_t n_sel,
 }
 
 
+// Headers assembled here instead of one Python f-string per block (run_colliearity.py:143-151, :194-195).
+extern "C" int icl_host_write_collinearity(const char *path, int64_t n_sel, const int64_t *score,
+                                           const char *ptext, const int64_t *ptext_off, const int32_t *pidx,
+                                           const char *pair_text, const int64_t *pair_text_off, const int32_t *pair,
+                                           const int64_t *mem_begin, const int64_t *mem_end,
+                                           const int32_t *loc1, const int32_t *loc2,
+                                           const int32_t *chr1_code, const int32_t *chr2_code,
+                                           const int64_t *row_of1, int64_t maxo1, const char *names1, const int64_t *name_off1,
+                                           const int32_t *strand_code1,
+                                           const int64_t *row_of2, int64_t maxo2, const char *names2, const int64_t *name_off2,
+                                           const int32_t *strand_code2,
+                                           int32_t threads, char *err, int32_t errlen) {
+    if (!path || n_sel < 0 || (n_sel > 0 && (!score || !ptext || !ptext_off || !pidx || !pair_text || !pair_text_off || !pair ||
+                                             !mem_begin || !mem_end || !loc2))) {
+        set_err(err, errlen, "icl_host_write_collinearity: bad argument");
+        return -1;
+    }
+    std::string headers;
+    std::vector<int64_t> off((size_t)n_sel + 1, 0);
+    headers.reserve((size_t)n_sel * 72);
+    std::string tail;
+    char num[32];
+    for (int64_t b = 0; b < n_sel; b++) {
+        if (mem_end[b] - mem_begin[b] < 2) { set_err(err, errlen, "icl_host_write_collinearity: a block of fewer than two gene pairs"); return -1; }
+        tail.assign(" score=");
+        tail.append(num, (size_t)(put_int(num, score[b]) - num));
+        tail.append(" pvalue=");
+        tail.append(ptext + ptext_off[pidx[b]], (size_t)(ptext_off[pidx[b] + 1] - ptext_off[pidx[b]]));
+        tail.append(" N=");
+        tail.append(num, (size_t)(put_int(num, mem_end[b] - mem_begin[b]) - num));
+        tail.push_back(' ');
+        tail.append(pair_text + pair_text_off[pair[b]], (size_t)(pair_text_off[pair[b] + 1] - pair_text_off[pair[b]]));
+        tail.append(loc2[mem_begin[b]] < loc2[mem_begin[b] + 1] ? " plus" : " minus");                   // :194-195
+        const size_t colon = tail.find(':');                  // :147-151 re-cuts the header at ':' (a chromosome name with one)
+        headers.append("# Alignment ");
+        headers.append(num, (size_t)(put_int(num, b + 1) - num));
+        headers.push_back(':');
+        headers.append(tail, 0, colon);
+        off[(size_t)b + 1] = (int64_t)headers.size();
+    }
+    return icl_host_write_blocks(path, n_sel, headers.data(), off.data(), mem_begin, mem_end, loc1, loc2, chr1_code, chr2_code,
+                                 row_of1, maxo1, names1, name_off1, strand_code1, row_of2, maxo2, names2, name_off2, strand_code2,
+                                 threads, err, errlen);
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // host gather of a comparison sharded over GPUs: one rank's blocks to their place in the merged arrays
 // ------------------------------------------------------------------------------------------------

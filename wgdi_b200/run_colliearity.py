@@ -216,15 +216,12 @@ def write_blocks_native(path, blocks, pair_names, genes1, genes2, pvalue, over_g
     pc1 = np.array([c1code[a] for a, _ in pair_names], np.int32)
     pc2 = np.array([c2code[b] for _, b in pair_names], np.int32)
     beg, end = blocks.member_off[emit], blocks.member_off[emit + 1]
-    y0, y1 = blocks.loc2[beg], blocks.loc2[beg + 1]      # emitted blocks have >= over_gap >= 2 members
-    headers = []
-    for num, (b, s, pv, m, a, c) in enumerate(zip(emit.tolist(), blocks.score[emit].tolist(), p[emit], (end - beg).tolist(),
-                                                  y0.tolist(), y1.tolist()), start=1):
-        chr1, chr2 = pair_names[blocks.pair[b]]
-        tail = f" score={s} pvalue={pv} N={m} {chr1}&{chr2} {'plus' if a < c else 'minus'}"
-        headers.append(f"# Alignment {num}:" + tail.split(':')[0])             # :147-151 re-cuts the header at ':'
-    _host.write_blocks(path, headers, beg, end, blocks.loc1, blocks.loc2, pc1[blocks.pair[emit]], pc2[blocks.pair[emit]],
-                       genes1, genes2)
+    # p values are round(a, 4) (collinearity.py:153): a few thousand distinct numbers, printed by Python itself
+    pu, pidx = np.unique(p[emit], return_inverse=True)
+    pair = np.asarray(blocks.pair)[emit]
+    _host.write_collinearity(path, np.asarray(blocks.score)[emit], [f"{v}" for v in pu], pidx,
+                             [f"{a}&{b}" for a, b in pair_names], pair, beg, end, blocks.loc1, blocks.loc2,
+                             pc1[pair], pc2[pair], genes1, genes2)
 
 
 def format_blocks(blocks, pair_names, genes1, genes2, pvalue, over_gap):
