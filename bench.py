@@ -617,6 +617,39 @@ def main():
             read_phase_clocks()
         dp_only_ms = float(np.mean(dev_ms["chain"]))
         eng.stream_rank = True
+    # ---- the DP kernel's critical path, measured by the kernel itself (ICL_B200_CHAIN_DEBUG: clock64 per work item, the
+    # <true, true> instantiation of k_chain_ring): one extra untimed pass.  The kernel ends with its slowest
+    # (chromosome pair, direction) item; an item is `rounds` dependent rounds of one warp.
+    critical_path = None
+    if rank == 0:
+        import tempfile
+        dbg = tempfile.NamedTemporaryFile(prefix="icl_chain_dbg_", suffix=".txt", delete=False)
+        dbg.close()
+        os.environ["ICL_B200_CHAIN_DEBUG"] = dbg.name
+        try:
+            step_resident()
+            rows = np.loadtxt(dbg.name, dtype=np.int64, ndmin=2) if os.path.getsize(dbg.name) else np.zeros((0, 8), np.int64)
+            rows = rows[rows[:, 4] > 0] if len(rows) else rows
+            if len(rows):
+                # columns: launch slot, item, points, rows, rounds, cycles, cycles waiting for staged data, records
+                h = rows[np.argmax(rows[:, 5])]
+                critical_path = {
+                    "items": int(len(rows)), "points_heaviest": int(h[2]), "records_heaviest": int(h[7]),
+                    "rounds_heaviest": int(h[4]), "cycles_heaviest": int(h[5]),
+                    "cycles_per_round": float(h[5]) / float(h[4]), "records_per_round": float(h[7]) / float(h[4]),
+                    "wait_share_heaviest": float(h[6]) / float(h[5]),
+                    "cycles_median_item": float(np.median(rows[:, 5])),
+                    "records_per_round_all_items": float(rows[:, 7].sum()) / float(rows[:, 4].sum()),
+                    "what": "per-item clock64 counters of one extra untimed pass (ICL_B200_CHAIN_DEBUG); kernel time = "
+                            "cycles_heaviest / SM clock (plus the launch and the clock reads of the debugging build)"}
+        except Exception as e:                         # diagnostics only
+            critical_path = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            os.environ.pop("ICL_B200_CHAIN_DEBUG", None)
+            try:
+                os.unlink(dbg.name)
+            except OSError:
+                pass
     # ---- the same steps with numpy itself ranking on the host (what every step did before the device reproduced numpy's
     # argsort, and what still happens where numpy sorts in a way the device does not know): for comparison
     host_ranked = None
@@ -784,6 +817,7 @@ def main():
                              "achieved": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9,
                              "frac": DP_BYTES_PER_POINT * n_local / (dp_only_ms * 1e-3) / 1e9 / peak,
                              "what": "same kernel with the streamed export off (ICL_B200_STREAM=0), 3 extra untimed passes"},
+                         "critical_path": critical_path,
                          "note": "order-exact integer DP: bound by the dependent rounds of the heaviest item, not by HBM; see DESIGN.md"},
             "phase_ms": res_ms, "batch": batch, "host_ranked": host_ranked, "device_rank_option": device_rank, "portable_numpy": portable,
             "avx2_numpy": avx2_leg,

@@ -267,6 +267,15 @@ int icl_timings(icl_ctx *ctx, double *ms, int32_t n_slots);
  * calls (radix sorts, scans) of the three together.  Returns the number of slots written (at most 8). */
 int icl_counters(icl_ctx *ctx, int64_t *out, int32_t n_slots);
 
+/* Device arrays and page-locked buffers of a destroyed (or regrown) context are not handed back to the driver: a
+ * process-wide cache keeps them for the next context — cudaMalloc / cudaFree of a comparison's gigabytes cost far more than
+ * its step, and drivers, batch runners and sharded runs create a context per comparison.  Limit: ICL_B200_CACHE_MB
+ * (default 16384, 0 = no cache); a failed allocation empties the cache and tries again.  A recycled device block is
+ * zeroed.  out[0] requests served from the cache, [1] requests that went to the driver, [2] bytes held now.  Returns the
+ * number of slots written (at most 3); icl_cache_trim gives everything held back to the driver. */
+int icl_cache_stats(int64_t *out, int32_t n_slots);
+void icl_cache_trim(void);
+
 /* The CUDA stream (cudaStream_t) every kernel and copy of `ctx` is issued on, for callers that bracket calls with
  * their own CUDA events (bench.py).  NULL in the emulation. */
 void *icl_stream(icl_ctx *ctx);

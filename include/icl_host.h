@@ -140,6 +140,30 @@ int icl_host_write_collinearity(const char *path, int64_t n_sel, const int64_t *
                                 int32_t threads, char *err, int32_t errlen);
 
 /*
+ * `-bi` input: a WGDI collinearity file (as -icl writes it) back into arrays — wgdi/base.py:120-141 (read_collinearity) plus
+ * what wgdi/block_info.py:18-75 derives per block member: the gene rows of the two names (-1: not in the gene table), the
+ * two positions as float(), and "_".join(str(int(position))) per block.  Blocks: header tokens 0 and 2 of
+ * re.findall(r'[\.\d+]+', header) (alignment number, p value) as text; a header without members is dropped like the
+ * reference drops it.  Returns 1 WITHOUT reading when the file is not the plain case (a byte that is not printable ASCII,
+ * ' ' or '\n', a position that is not a plain integer, a short line): the caller then uses its Python reader, which behaves
+ * — and fails — like the reference.
+ */
+typedef struct icl_collinearity {
+    int64_t n_blocks, n_members;
+    char *id_text; int64_t *id_off;             /* [n_blocks + 1] */
+    char *pv_text; int64_t *pv_off;
+    int64_t *off;                               /* [n_blocks + 1] members of block b: off[b] .. off[b + 1] */
+    int32_t *g1, *g2;                           /* [n_members] */
+    double *loc1, *loc2;                        /* [n_members] */
+    char *block1_text; int64_t *block1_off;     /* [n_blocks + 1] */
+    char *block2_text; int64_t *block2_off;
+} icl_collinearity;
+int icl_host_read_collinearity(const char *path, const char *ids1, const int64_t *off1, int64_t n1,
+                               const char *ids2, const int64_t *off2, int64_t n2,
+                               icl_collinearity *out, char *err, int32_t errlen);
+void icl_host_free_collinearity(icl_collinearity *c);
+
+/*
  * One comparison sharded over several GPUs (the pairs of wgdi/run_colliearity.py:123-136 over ranks instead of worker
  * processes): write one rank's blocks straight to their place in the merged, emission-ordered arrays — what the reference's
  * parent process does when it concatenates the workers' texts in chunk order (:133-141).  A rank's blocks are pair-major, so

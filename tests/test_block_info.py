@@ -215,3 +215,48 @@ def test_bi_cuda_on_icl_output_matches_oracle(tmp_path):
     got = open(os.path.join(d, "bi.csv")).read()
     assert got.count("\n") > 50
     assert got == bi_oracle.block_info_csv(bi)
+
+
+def test_native_collinearity_reader_equals_the_python_reader(tmp_path):
+    """icl_host_read_collinearity (the -bi input, include/icl_host.h) against `read_collinearity_flat`, which mirrors
+    wgdi/base.py:120-141: blocks, header tokens, gene rows, positions and the joined position strings; and its refusal of
+    everything that is not the plain text -icl writes (the Python reader then behaves like the reference)."""
+    import gzip
+    import pandas as pd
+    from wgdi_b200 import _host, build
+    from wgdi_b200.block_info import read_collinearity_flat
+    build.build_host()
+    for case in BI_CASES:
+        src = os.path.join(ROOT, "tests", "golden", f"e2e_{case}")
+        path = os.path.join(src, "expected.collinearity.txt")
+        ids, pvs, off, n1, l1, n2, l2 = read_collinearity_flat(path)
+        genes1 = sorted(set(n1))[::2] + ["not_in_the_file"]          # half of the names are unknown to the gene table
+        genes2 = sorted(set(n2))
+        t1, t2 = _host.pack_strings(genes1), _host.pack_strings(genes2)
+        nat = _host.read_collinearity(path, t1, t2)
+        assert nat is not None and nat["ids"] == ids and nat["pvalues"] == pvs and np.array_equal(nat["off"], off)
+        assert np.array_equal(nat["g1"], pd.Index(genes1).get_indexer(pd.Index(n1, dtype=object)))
+        assert np.array_equal(nat["g2"], pd.Index(genes2).get_indexer(pd.Index(n2, dtype=object)))
+        assert nat["loc1"].tolist() == [float(x) for x in l1] and nat["loc2"].tolist() == [float(x) for x in l2]
+        for b in range(len(ids)):
+            assert nat["block1"][b] == "_".join(str(int(float(x))) for x in l1[off[b]:off[b + 1]])
+            assert nat["block2"][b] == "_".join(str(int(float(x))) for x in l2[off[b]:off[b + 1]])
+    text = open(path).read()
+    t = _host.pack_strings(["a"])
+    variants = {"tab": text.replace(" ", "\t", 1), "crlf": text.replace("\n", "\r\n"), "float": re.sub(r"^(\S+) (\d+) ", r"\1 \2.0 ", text, count=1, flags=re.M),
+                "short": text + "lonely\n", "utf8": text.replace("&", "\u00e9", 1)}
+    for name, v in variants.items():
+        p = tmp_path / f"{name}.txt"
+        p.write_text(v, newline="")
+        assert _host.read_collinearity(str(p), t, t) is None, name
+    # leading / trailing blanks, members before the first header, a header without members, an empty file
+    p = tmp_path / "odd.txt"
+    p.write_text("x 1 y 2 1\n# Alignment 1: score=5 pvalue=0.5 N=2 a&b plus\n# Alignment 2: score=7.5 pvalue=0.25 N=2 a&b minus\n"
+                 "  a 3 a 4 1  \na 5 b 6 -1\n")
+    nat = _host.read_collinearity(str(p), t, t)
+    ref = read_collinearity_flat(str(p))
+    assert nat["ids"] == ref[0] == ["2"] and nat["pvalues"] == ref[1] == ["0.25"] and nat["off"].tolist() == [0, 2]
+    assert nat["g1"].tolist() == [0, 0] and nat["g2"].tolist() == [0, -1] and nat["block2"] == ["4_6"]
+    (tmp_path / "empty.txt").write_text("")
+    nat = _host.read_collinearity(str(tmp_path / "empty.txt"), t, t)
+    assert nat["ids"] == [] and nat["off"].tolist() == [0]

@@ -866,3 +866,12 @@ def test_writer_field_set(gpu_engine):
     from bench import make_points, params_for
     pts = make_points("C2")
     _assert_writer_fields(gpu_engine, pts, params_for(pts["cfg"]))
+
+
+def test_contexts_recycle_their_blocks(gpu_engine):
+    """The process-wide block cache on the device: a context built from another comparison's recycled blocks computes what
+    a context on fresh cudaMalloc memory computes (full-size C2 against a C1-sized comparison in between)."""
+    from test_host_logic import _assert_contexts_recycle_their_blocks
+    from bench import make_points, params_for
+    a, b = make_points("C2"), make_points("C1")
+    _assert_contexts_recycle_their_blocks(gpu_engine.lib, a, b, params_for(a["cfg"]))

@@ -608,3 +608,49 @@ def test_writer_field_set_emu(emu_backend):
         _assert_writer_fields(eng, pts, ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))
     finally:
         eng.close()
+
+
+def _assert_contexts_recycle_their_blocks(lib, pts_a, pts_b, prm):
+    """Contexts created one after the other (what the drop-in driver, the batch runner and the sharded runs do): the
+    second one is served from the process-wide block cache (include/icl_b200.h, icl_cache_stats) — recycled device blocks
+    arrive zeroed — and computes exactly what a fresh process would; icl_cache_trim hands everything back."""
+    from wgdi_b200.engine import IclEngine
+
+    def stats():
+        out = np.zeros(3, np.int64)
+        assert lib.icl_cache_stats(out.ctypes.data, 3) == 3
+        return out.tolist()
+
+    def run(pts):
+        eng = IclEngine(0, sort_threads=2)
+        try:
+            b = eng.chain(pts["pair_id"], pts["loc1"], pts["loc2"], pts["grading"], pts["n_pairs"], prm, min_members=1)
+            return {k: np.array(getattr(b, k), copy=True) for k in ("pair", "dir", "score", "m", "N", "N1", "p_raw", "member_off",
+                                                                    "loc1", "loc2")}
+        finally:
+            eng.close()
+    lib.icl_cache_trim()
+    assert stats()[2] == 0
+    first = run(pts_a)
+    h0, m0, held = stats()
+    assert held > 0                                          # the closed context's blocks are kept
+    other = run(pts_b)                                       # another comparison dirties the recycled blocks
+    again = run(pts_a)
+    h1, m1, _ = stats()
+    assert h1 > h0                                           # ... and they were reused
+    for k in first:
+        assert np.array_equal(first[k], again[k]), k
+    assert len(other["pair"]) > 0
+    lib.icl_cache_trim()
+    assert stats()[2] == 0
+    fresh = run(pts_a)                                       # straight from the driver again
+    for k in first:
+        assert np.array_equal(first[k], fresh[k]), k
+
+
+def test_contexts_recycle_their_blocks_emu(emu_backend):
+    from wgdi_b200 import synth
+    from wgdi_b200.engine import ChainParams
+    a = synth.graded_points(synth.make_dataset("tiny"))
+    b = synth.graded_points(synth.make_dataset("cross"))
+    _assert_contexts_recycle_their_blocks(emu_backend, a, b, ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))

@@ -21,6 +21,15 @@ class icl_hits(C.Structure):
                 ("bits", C.POINTER(C.c_double))]
 
 
+class icl_collinearity(C.Structure):
+    _fields_ = [("n_blocks", C.c_int64), ("n_members", C.c_int64),
+                ("id_text", C.c_void_p), ("id_off", C.POINTER(C.c_int64)), ("pv_text", C.c_void_p), ("pv_off", C.POINTER(C.c_int64)),
+                ("off", C.POINTER(C.c_int64)), ("g1", C.POINTER(C.c_int32)), ("g2", C.POINTER(C.c_int32)),
+                ("loc1", C.POINTER(C.c_double)), ("loc2", C.POINTER(C.c_double)),
+                ("block1_text", C.c_void_p), ("block1_off", C.POINTER(C.c_int64)),
+                ("block2_text", C.c_void_p), ("block2_off", C.POINTER(C.c_int64))]
+
+
 class icl_ingest_info(C.Structure):
     _fields_ = [("n_hits", C.c_int64), ("n_rows_file", C.c_int64), ("bits_is_int", C.c_int32),
                 ("n_amb_queries", C.c_int64), ("n_amb_hits", C.c_int64)]
@@ -43,6 +52,9 @@ def load():
                                               vp, i64, vp, vp, vp, i32, vp, i32]
         lib.icl_host_write_collinearity.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                     vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, i32, vp, i32]
+        lib.icl_host_read_collinearity.argtypes = [C.c_char_p, vp, vp, i64, vp, vp, i64, C.POINTER(icl_collinearity), vp, i32]
+        lib.icl_host_free_collinearity.argtypes = [C.POINTER(icl_collinearity)]
+        lib.icl_host_free_collinearity.restype = None
         lib.icl_host_ingest_open.argtypes = [C.c_char_p, i32, dbl, dbl, vp, vp, i64, vp, vp, i64, i32, i32, i32, i32,
                                              C.POINTER(vp), C.POINTER(icl_ingest_info), vp, i32]
         lib.icl_host_ingest_ambiguous.argtypes = [vp, vp, vp]
@@ -288,3 +300,39 @@ def write_collinearity(path, score, p_text, p_index, pair_text, pair, mem_begin,
           genes2["row_of"].ctypes.data, int(genes2["maxo"]), C.cast(C.c_char_p(genes2["name_bytes"]), C.c_void_p),
           genes2["name_off"].ctypes.data, genes2["strand_code"].ctypes.data,
           int(threads or threads_default()))
+
+
+def read_collinearity(path, ids1, ids2):
+    """icl_host_read_collinearity: dict(ids, pvalues, off, g1, g2, loc1, loc2, block1, block2) of a WGDI collinearity file, or
+    None when the file is not the plain case the native reader handles (the caller's Python reader takes over)."""
+    lib = load()
+    out = icl_collinearity()
+    b1, o1 = ids1
+    b2, o2 = ids2
+    same = ids1 is ids2
+    p1 = C.cast(C.c_char_p(b1), C.c_void_p)
+    p2 = p1 if same else C.cast(C.c_char_p(b2), C.c_void_p)
+    err = C.create_string_buffer(512)
+    rc = lib.icl_host_read_collinearity(str(path).encode(), p1, o1.ctypes.data, len(o1) - 1, p2,
+                                        (o1 if same else o2).ctypes.data, len(o2) - 1, C.byref(out), err, 512)
+    if rc == 1:
+        return None
+    if rc != 0:
+        raise HostError(f"icl_host error {rc}: {err.value.decode(errors='replace')}")
+    try:
+        nb, nm = int(out.n_blocks), int(out.n_members)
+
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+
+        def texts(ptr, offp):
+            off = arr(offp, nb + 1, np.int64)
+            raw = C.string_at(ptr, int(off[-1])).decode("ascii") if nb else ""
+            o = off.tolist()
+            return [raw[o[i]:o[i + 1]] for i in range(nb)]
+        return dict(ids=texts(out.id_text, out.id_off), pvalues=texts(out.pv_text, out.pv_off),
+                    off=arr(out.off, nb + 1, np.int64), g1=arr(out.g1, nm, np.int64), g2=arr(out.g2, nm, np.int64),
+                    loc1=arr(out.loc1, nm, np.float64), loc2=arr(out.loc2, nm, np.float64),
+                    block1=texts(out.block1_text, out.block1_off), block2=texts(out.block2_text, out.block2_off))
+    finally:
+        lib.icl_host_free_collinearity(C.byref(out))

@@ -66,6 +66,9 @@ def _declare(lib):
     lib.icl_debug_dp.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.icl_timings.argtypes = [vp, vp, i32]
     lib.icl_counters.argtypes = [vp, vp, i32]
+    lib.icl_cache_stats.argtypes = [vp, i32]
+    lib.icl_cache_trim.argtypes = []
+    lib.icl_cache_trim.restype = None
     lib.icl_stream.argtypes = [vp]
     lib.icl_stream.restype = vp
     return lib
@@ -73,7 +76,7 @@ def _declare(lib):
 
 EXPORTS = ("icl_backend", "icl_create", "icl_destroy", "icl_last_error", "icl_host_alloc", "icl_host_free",
            "icl_upload", "icl_upload_typed", "icl_set_grading_table", "icl_dp", "icl_dp_begin", "icl_dp_end", "icl_layout", "icl_rank_device", "icl_debug_order", "icl_debug_rank_keys", "icl_debug_keys", "icl_extract", "icl_extract_fields", "icl_free_blocks", "icl_debug_dp", "icl_timings",
-           "icl_counters", "icl_stream")
+           "icl_counters", "icl_stream", "icl_cache_stats", "icl_cache_trim")
 
 
 def load():

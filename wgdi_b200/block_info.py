@@ -95,24 +95,31 @@ class block_info():
         self.native = getattr(self, 'ingest', 'native').lower() != 'pandas' and _host.available()
         self.timing = {}
 
-    def auto_file(self):
-        """wgdi/block_info.py:167-180: only WGDI's own format is offered here."""
+    def auto_file(self, ids1=None, ids2=None):
+        """wgdi/block_info.py:167-180: only WGDI's own format is offered here.  With the packed gene tables (native host
+        library, no Ks file) the file is read by icl_host_read_collinearity — a dict, see `_host.read_collinearity` —
+        unless it is not the plain text -icl writes; then, and otherwise, `read_collinearity_flat`'s tuple."""
         with open(self.collinearity) as f:
             p = ' '.join(f.readlines()[0:30])
         if 'path length' in p or 'MAXIMUM GAP' in p or 'MATCH_SIZE' in p or '## Alignment' in p:
             raise NotImplementedError("only WGDI-format collinearity files (as written by -icl) are supported")
         if '# Alignment' in p:
+            if ids1 is not None:
+                nat = _host.read_collinearity(self.collinearity, ids1, ids2)
+                if nat is not None:
+                    return nat
             return read_collinearity_flat(self.collinearity)
         raise NotImplementedError("only WGDI-format collinearity files (as written by -icl) are supported")
 
-    def load_hits(self, gff1, gff2):
+    def load_hits(self, gff1, gff2, ids1=None, ids2=None):
         """base.newblast + blast_homo's trimming (block_info.py:149-150, :104-105): kept hits with their rank.
         The id columns are NEVER swapped here, whatever `blast_reverse` says: the reference turns the option into a bool
         (wgdi/block_info.py:16) and hands that bool to base.newblast, whose test is `reverse == 'true'` (base.py:176) —
         False for either bool.  Reproduced as is (drop-in; pinned by test_block_info_ignores_blast_reverse)."""
         if self.native and not _host.is_compressed(self.blast):
-            ids1 = _host.pack_strings(gff1.index)
-            ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
+            if ids1 is None:
+                ids1 = _host.pack_strings(gff1.index)
+                ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
             hits = _host.read_m8(self.blast, False, int(self.score), float(self.evalue), ids1, ids2)
             g1, g2, bits = hits['g1'], hits['g2'], hits['bits']
         else:
@@ -130,40 +137,55 @@ class block_info():
         gff2 = base.newgff(self.gff2)
         gff1 = gff1[gff1['chr'].isin(lens1.index)]
         gff2 = gff2[gff2['chr'].isin(lens2.index)]
-        g1, g2, rank = self.load_hits(gff1, gff2)
+        ids1 = ids2 = None
+        if self.native:
+            ids1 = _host.pack_strings(gff1.index)
+            ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
+        g1, g2, rank = self.load_hits(gff1, gff2, ids1, ids2)
         order2 = gff2['order'].to_numpy()
         o = np.lexsort((rank, g1))
         hit_off = np.zeros(len(gff1) + 1, np.int64)
         np.cumsum(np.bincount(g1, minlength=len(gff1)), out=hit_off[1:])
-        ids, pvs, off, n1, l1, n2, l2 = self.auto_file()
         ks = pd.Series([], dtype=float) if (not hasattr(self, 'ks') or self.ks == 'none' or self.ks == '') \
             else read_ks(self.ks, self.ks_col)
-        m1 = gff1.index.get_indexer(pd.Index(n1, dtype=object)) if n1 else np.zeros(0, np.int64)
-        m2 = gff2.index.get_indexer(pd.Index(n2, dtype=object)) if n2 else np.zeros(0, np.int64)
+        # the Ks columns are looked up by gene NAME (:77-86): with a Ks table the Python reader keeps the names
+        parsed = self.auto_file(ids1, ids2) if len(ks) == 0 else self.auto_file()
+        native = parsed if isinstance(parsed, dict) else None
+        if native is not None:
+            ids, pvs, off, m1, m2 = native['ids'], native['pvalues'], native['off'], native['g1'], native['g2']
+            n1 = l1 = n2 = l2 = None
+        else:
+            ids, pvs, off, n1, l1, n2, l2 = parsed
+            m1 = gff1.index.get_indexer(pd.Index(n1, dtype=object)) if n1 else np.zeros(0, np.int64)
+            m2 = gff2.index.get_indexer(pd.Index(n2, dtype=object)) if n2 else np.zeros(0, np.int64)
         mo2 = np.where(m2 >= 0, order2[np.maximum(m2, 0)], 0) if len(m2) else np.zeros(0, np.int64)
         t1 = time.perf_counter()
         homo_sum, homo_cnt, t_rows, t_uniq = _bi.block_stats(self.device, hit_off, g2[o], rank[o], order2[g2[o]] if len(o) else [],
                                                              off, m1, m2, mo2, self.repeat_number)
         t2 = time.perf_counter()
-        data = self.assemble(ids, pvs, off, n1, l1, n2, l2, m1, m2, gff1, gff2, ks, homo_sum, homo_cnt, t_rows, t_uniq)
+        data = self.assemble(ids, pvs, off, n1, l1, n2, l2, m1, m2, gff1, gff2, ks, homo_sum, homo_cnt, t_rows, t_uniq, native)
         data['class1'] = 0
         data['class2'] = 0
         data.to_csv(self.savefile, index=None)
         t3 = time.perf_counter()
         self.timing.update(ingest_s=t1 - t0, device_s=t2 - t1, write_s=t3 - t2, blocks=len(ids))
 
-    def assemble(self, ids, pvs, off, n1, l1, n2, l2, m1, m2, gff1, gff2, ks, homo_sum, homo_cnt, t_rows, t_uniq):
+    def assemble(self, ids, pvs, off, n1, l1, n2, l2, m1, m2, gff1, gff2, ks, homo_sum, homo_cnt, t_rows, t_uniq, native=None):
         """The frame of block_position (block_info.py:18-75), built from the same Python values in the same order so
         that pandas infers the same column types and `to_csv` prints the same text."""
         chr1_of, chr2_of = gff1['chr'].to_numpy(), gff2['chr'].to_numpy()
         have_ks = len(ks) > 0
         ksd = dict(zip(ks.index.tolist(), ks.to_numpy())) if have_ks else {}
         # float(k[1]) / int(float(k[1])) / str(...) of :31, :37-38, :51-52 for all members at once
-        f1 = np.asarray(l1, dtype=np.float64) if l1 else np.zeros(0)
-        f2 = np.asarray(l2, dtype=np.float64) if l2 else np.zeros(0)
-        s1 = f1.astype(np.int64).astype(str).tolist()
-        s2 = f2.astype(np.int64).astype(str).tolist()
-        f1, f2 = f1.tolist(), f2.tolist()
+        if native is not None:                                       # the same values, formed by icl_host_read_collinearity
+            f1, f2, blk1, blk2 = native['loc1'].tolist(), native['loc2'].tolist(), native['block1'], native['block2']
+        else:
+            f1 = np.asarray(l1, dtype=np.float64) if l1 else np.zeros(0)
+            f2 = np.asarray(l2, dtype=np.float64) if l2 else np.zeros(0)
+            s1 = f1.astype(np.int64).astype(str).tolist()
+            s2 = f2.astype(np.int64).astype(str).tolist()
+            f1, f2 = f1.tolist(), f2.tolist()
+            blk1 = blk2 = None
         # :98-100 mean over the pairs that are kept hits; :134 tandem ratio — same IEEE operations as the Python floats
         Ls = np.diff(off).astype(np.int64)
         with np.errstate(divide='ignore', invalid='ignore'):
@@ -191,7 +213,8 @@ class block_info():
                 ks_median, ks_average, blkks = -1, -1, '_'.join(['-1'] * L)
             homo = hmean[b] if cnts[b] > 0 else none5
             data.append([ids[b], chr1_of[m1[a0]], chr2_of[m2[a0]], f1[a0], f1[a1 - 1], f2[a0], f2[a1 - 1], pvs[b], L,
-                         ks_median, ks_average, *homo, '_'.join(s1[a0:a1]), '_'.join(s2[a0:a1]), blkks, tandem[b]])
+                         ks_median, ks_average, *homo, blk1[b] if blk1 is not None else '_'.join(s1[a0:a1]),
+                         blk2[b] if blk2 is not None else '_'.join(s2[a0:a1]), blkks, tandem[b]])
         data_df = pd.DataFrame(data, columns=[
             'id', 'chr1', 'chr2', 'start1', 'end1', 'start2', 'end2', 'pvalue', 'length',
             'ks_median', 'ks_average', 'homo1', 'homo2', 'homo3', 'homo4', 'homo5',

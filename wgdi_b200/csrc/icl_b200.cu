@@ -275,15 +275,12 @@ static int input_stats(icl_ctx *c, const uint8_t *const raw[4], const int32_t by
 static int host_scratch(icl_ctx *c, size_t bytes) {
     Status &st = c->st;
     if (bytes <= c->h_plan_cap) return 0;
-#ifndef ICL_EMU
-    if (c->h_plan) cudaFreeHost(c->h_plan);
+    if (c->h_plan) pin_free(c->h_plan);
     c->h_plan = nullptr; c->h_plan_cap = 0;
-    ICL_CUDA(st, cudaHostAlloc((void **)&c->h_plan, 2 * bytes, cudaHostAllocDefault));
-#else
-    free(c->h_plan);
-    c->h_plan = (uint8_t *)malloc(2 * bytes);
-    if (!c->h_plan) return fail(c, ICL_ERR_NOMEM, "icl_upload: out of host memory");
-#endif
+    if (pin_malloc((void **)&c->h_plan, 2 * bytes) != cudaSuccess || !c->h_plan) {
+        c->h_plan = nullptr;
+        return fail(c, ICL_ERR_NOMEM, "icl_upload: out of page-locked host memory");
+    }
     c->h_plan_cap = 2 * bytes;
     return 0;
 }
@@ -385,11 +382,7 @@ extern "C" int icl_create(int device, icl_ctx **out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete c; return ICL_ERR_CUDA; }
 #endif
-#ifndef ICL_EMU
-    if (cudaHostAlloc((void **)&c->h_small, 64 * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) c->h_small = nullptr;
-#else
-    c->h_small = (uint64_t *)malloc(64 * sizeof(uint64_t));
-#endif
+    if (pin_malloc((void **)&c->h_small, 64 * sizeof(uint64_t)) != cudaSuccess) c->h_small = nullptr;
     if (!c->h_small) { g_create_error = "icl_create: no page-locked host memory"; delete c; return ICL_ERR_CUDA; }
     if (c->stats.reserve(c->st, 8)) { g_create_error = c->st.msg; delete c; return ICL_ERR_CUDA; }
     const char *mode = getenv("ICL_B200_CHAIN");              // diagnostics: A/B the DP kernels
@@ -405,6 +398,8 @@ extern "C" void icl_destroy(icl_ctx *c) {
 #ifndef ICL_EMU
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream2);           // released blocks go to the process-wide cache (icl_platform.h): nothing of
+    cudaStreamSynchronize(c->stream3);           // this context may still be running when another context picks them up
 #endif
     c->in_pair.release(); c->in_loc1.release(); c->in_loc2.release(); c->in_grad.release(); c->stats.release(); c->in_raw.release();
     c->key_a.release(); c->key_b.release(); c->idx_a.release(); c->perm.release(); c->tmp.release();
@@ -422,15 +417,9 @@ extern "C" void icl_destroy(icl_ctx *c) {
     c->d_stage.release();
     c->o_src.release(); c->o_ms.release(); c->o_e.release();
     c->host_flag.release(); c->xs_chunk.release(); c->npscr.release();
-#ifndef ICL_EMU
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->h_plan) cudaFreeHost(c->h_plan);
-    if (c->h_small) cudaFreeHost(c->h_small);
-#else
-    free(c->h_small);
-    free(c->h_stage);
-    free(c->h_plan);
-#endif
+    if (c->h_stage) pin_free(c->h_stage);
+    if (c->h_plan) pin_free(c->h_plan);
+    if (c->h_small) pin_free(c->h_small);
     c->pair_hist.release();
     for (auto &t : c->timers) t.destroy();
 #ifndef ICL_EMU
@@ -454,21 +443,18 @@ extern "C" int icl_host_alloc(icl_ctx *c, int64_t bytes, void **ptr) {
     if (!c || !ptr || bytes < 0) return ICL_ERR_ARG;
 #ifndef ICL_EMU
     ICL_CUDA(c->st, cudaSetDevice(c->device));
-    ICL_CUDA(c->st, cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 16), cudaHostAllocDefault));
-#else
-    *ptr = malloc((size_t)(bytes ? bytes : 16));
-    if (!*ptr) return fail(c, ICL_ERR_NOMEM, "icl_host_alloc: out of memory");
 #endif
+    *ptr = nullptr;
+    if (pin_malloc(ptr, (size_t)(bytes ? bytes : 16)) != cudaSuccess || !*ptr) return fail(c, ICL_ERR_NOMEM, "icl_host_alloc: out of memory");
     return ICL_OK;
 }
 
 extern "C" int icl_host_free(icl_ctx *c, void *ptr) {
     if (!c) return ICL_ERR_ARG;
 #ifndef ICL_EMU
-    ICL_CUDA(c->st, cudaFreeHost(ptr));
-#else
-    free(ptr);
+    ICL_CUDA(c->st, cudaSetDevice(c->device));
 #endif
+    pin_free(ptr);
     return ICL_OK;
 }
 
@@ -2056,15 +2042,12 @@ static int stage_layout(icl_ctx *c, int64_t NBo, int64_t NMo) {
     const size_t bytes = ds.used + 64;
     if (c->d_stage.reserve(st, bytes)) return st.code;
     if (bytes > c->h_stage_cap) {
-#ifndef ICL_EMU
-        if (c->h_stage) cudaFreeHost(c->h_stage);
+        if (c->h_stage) pin_free(c->h_stage);
         c->h_stage = nullptr; c->h_stage_cap = 0;
-        ICL_CUDA(st, cudaHostAlloc((void **)&c->h_stage, bytes + bytes / 4, cudaHostAllocDefault));
-#else
-        free(c->h_stage);
-        c->h_stage = (uint8_t *)malloc(bytes + bytes / 4);
-        if (!c->h_stage) return fail(c, ICL_ERR_NOMEM, "icl_extract: out of host memory");
-#endif
+        if (pin_malloc((void **)&c->h_stage, bytes + bytes / 4) != cudaSuccess || !c->h_stage) {
+            c->h_stage = nullptr;
+            return fail(c, ICL_ERR_NOMEM, "icl_extract: out of page-locked host memory");
+        }
         c->h_stage_cap = bytes + bytes / 4;
     }
     ds = Stage{c->d_stage.p, 0};
@@ -4334,6 +4317,26 @@ extern "C" int icl_timings(icl_ctx *c, double *ms, int32_t n_slots) {
     int32_t k = n_slots < ICL_T_COUNT ? n_slots : ICL_T_COUNT;
     for (int32_t i = 0; i < k; i++) ms[i] = c->timers[i].ms();
     return k;
+}
+
+extern "C" int icl_cache_stats(int64_t *out, int32_t n_slots) {
+    if (!out) return ICL_ERR_ARG;
+    BlockCache &bc = BlockCache::get();
+    const int64_t v[3] = {bc.hits, bc.misses, (int64_t)bc.cached_bytes()};
+    int32_t k = n_slots < 3 ? n_slots : 3;
+    for (int32_t i = 0; i < k; i++) out[i] = v[i];
+    return k;
+}
+
+extern "C" void icl_cache_trim(void) {
+    BlockCache &bc = BlockCache::get();
+    std::lock_guard<std::mutex> lock(bc.mu);
+    for (auto &kv : bc.pools) {
+#ifndef ICL_EMU
+        if (kv.first >= 0) cudaSetDevice(kv.first);
+#endif
+        bc.trim(kv.first);
+    }
 }
 
 extern "C" int icl_counters(icl_ctx *c, int64_t *out, int32_t n_slots) {

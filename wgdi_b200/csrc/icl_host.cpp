@@ -955,3 +955,156 @@ extern "C" int icl_host_place_blocks(int64_t n_blocks, const int32_t *pair, cons
     }
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// `-bi`: the collinearity file back into arrays (wgdi/base.py:120-141 as wgdi/block_info.py:18-75 consumes it)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct TextColumn {
+    std::string text;
+    std::vector<int64_t> off{0};
+    void add(const char *p, size_t n) { text.append(p, n); off.push_back((int64_t)text.size()); }
+    void close() { off.push_back((int64_t)text.size()); }
+};
+template <class T>
+T *copy_out(const std::vector<T> &v) {
+    T *p = (T *)malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (p && !v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+    return p;
+}
+char *copy_out(const std::string &s) {
+    char *p = (char *)malloc(std::max<size_t>(s.size(), 1));
+    if (p && !s.empty()) memcpy(p, s.data(), s.size());
+    return p;
+}
+}  // namespace
+
+extern "C" void icl_host_free_collinearity(icl_collinearity *c) {
+    if (!c) return;
+    free(c->id_text); free(c->id_off); free(c->pv_text); free(c->pv_off); free(c->off); free(c->g1); free(c->g2);
+    free(c->loc1); free(c->loc2); free(c->block1_text); free(c->block1_off); free(c->block2_text); free(c->block2_off);
+    memset(c, 0, sizeof(*c));
+}
+
+extern "C" int icl_host_read_collinearity(const char *path, const char *ids1, const int64_t *off1, int64_t n1,
+                                          const char *ids2, const int64_t *off2, int64_t n2,
+                                          icl_collinearity *out, char *err, int32_t errlen) {
+    if (!path || !out || !off1 || !off2 || (n1 > 0 && !ids1) || (n2 > 0 && !ids2)) { set_err(err, errlen, "icl_host_read_collinearity: null argument"); return -1; }
+    memset(out, 0, sizeof(*out));
+    PhaseClock clk;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_err(err, errlen, std::string("cannot open ") + path + ": " + strerror(errno)); return -2; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); set_err(err, errlen, "fstat failed"); return -2; }
+    const size_t size = (size_t)sb.st_size;
+    const char *data = nullptr;
+    if (size > 0) {
+        data = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (data == MAP_FAILED) { close(fd); set_err(err, errlen, "mmap failed"); return -2; }
+    }
+    struct Unmap {
+        const char *d; size_t n; int fd;
+        ~Unmap() { if (d) munmap((void *)d, n); close(fd); }
+    } unmap{data, size, fd};
+    // only the plain case is handled here: printable ASCII, ' ' and '\n'.  Anything else (tabs, '\r', other white space the
+    // reference's re.split(r"\s") would cut at, non-ASCII text) is left to the Python reader: return 1.
+    for (size_t i = 0; i < size; i++) {
+        const unsigned char ch = (unsigned char)data[i];
+        if (ch != '\n' && (ch < 0x20 || ch > 0x7e)) return 1;
+    }
+    IdMap m1, m2;
+    m1.build(ids1, off1, n1);
+    const bool same = ids1 == ids2 && off1 == off2 && n1 == n2;
+    if (!same) m2.build(ids2, off2, n2);
+    const IdMap &map1 = m1, &map2 = same ? m1 : m2;
+    TextColumn idc, pvc, b1, b2;
+    std::vector<int64_t> boff{0};
+    std::vector<int32_t> g1, g2;
+    std::vector<double> l1, l2;
+    std::string cur_id, cur_pv;
+    bool in_blocks = false;
+    int64_t count = 0;
+    char num[32];
+    auto close_block = [&]() {
+        if (!count) return;
+        idc.add(cur_id.data(), cur_id.size());
+        pvc.add(cur_pv.data(), cur_pv.size());
+        boff.push_back(boff.back() + count);
+        b1.close(); b2.close();
+        count = 0;
+    };
+    auto plain_int = [](const char *p, const char *q, int64_t &v) {      // what float() -> int() -> str() leaves unchanged
+        if (p >= q || q - p > 15) return false;
+        v = 0;
+        for (; p < q; p++) {
+            if (*p < '0' || *p > '9') return false;
+            v = v * 10 + (*p - '0');
+        }
+        return true;
+    };
+    const char *p = data, *end = data + size;
+    while (p < end) {
+        const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = eol ? eol : end;
+        const char *next = eol ? eol + 1 : end;
+        const char *a = p, *b = le;
+        while (a < b && *a == ' ') a++;                                 // line.strip()
+        while (b > a && b[-1] == ' ') b--;
+        p = next;
+        if (b - a >= 11 && !memcmp(a, "# Alignment", 11)) {              // re.match(r"# Alignment", line)
+            in_blocks = true;
+            close_block();
+            // re.findall(r'[\.\d+]+', line): tokens 0 and 2
+            int tok = 0;
+            cur_id.clear(); cur_pv.clear();
+            for (const char *q = a; q < b;) {
+                auto is_tok = [](char ch) { return (ch >= '0' && ch <= '9') || ch == '.' || ch == '+'; };
+                if (!is_tok(*q)) { q++; continue; }
+                const char *t = q;
+                while (q < b && is_tok(*q)) q++;
+                if (tok == 0) cur_id.assign(t, (size_t)(q - t));
+                if (tok == 2) { cur_pv.assign(t, (size_t)(q - t)); tok++; break; }
+                tok++;
+            }
+            if (tok < 3) return 1;                                      // the Python reader raises what the reference raises
+            continue;
+        }
+        if (!in_blocks) continue;
+        // name1 loc1 name2 loc2 ...: str.split(' ') — consecutive blanks give empty fields, as in the reference
+        const char *f[5];
+        int nf = 0;
+        f[0] = a;
+        for (const char *q = a; q < b && nf < 4; q++)
+            if (*q == ' ') f[++nf] = q + 1;
+        if (nf < 3) return 1;
+        const char *e3 = nf >= 4 ? f[4] - 1 : b;
+        int64_t v1, v2;
+        if (!plain_int(f[1], f[2] - 1, v1) || !plain_int(f[3], e3, v2)) return 1;
+        g1.push_back(map1.find(f[0], (size_t)(f[1] - 1 - f[0])));
+        g2.push_back(map2.find(f[2], (size_t)(f[3] - 1 - f[2])));
+        l1.push_back((double)v1);
+        l2.push_back((double)v2);
+        if (count) { b1.text.push_back('_'); b2.text.push_back('_'); }
+        b1.text.append(num, (size_t)(put_int(num, v1) - num));
+        b2.text.append(num, (size_t)(put_int(num, v2) - num));
+        count++;
+    }
+    close_block();
+    out->n_blocks = (int64_t)boff.size() - 1;
+    out->n_members = (int64_t)g1.size();
+    out->id_text = copy_out(idc.text); out->id_off = copy_out(idc.off);
+    out->pv_text = copy_out(pvc.text); out->pv_off = copy_out(pvc.off);
+    out->off = copy_out(boff);
+    out->g1 = copy_out(g1); out->g2 = copy_out(g2);
+    out->loc1 = copy_out(l1); out->loc2 = copy_out(l2);
+    out->block1_text = copy_out(b1.text); out->block1_off = copy_out(b1.off);
+    out->block2_text = copy_out(b2.text); out->block2_off = copy_out(b2.off);
+    if (!out->id_text || !out->id_off || !out->pv_text || !out->pv_off || !out->off || !out->g1 || !out->g2 || !out->loc1 ||
+        !out->loc2 || !out->block1_text || !out->block1_off || !out->block2_text || !out->block2_off) {
+        icl_host_free_collinearity(out);
+        set_err(err, errlen, "out of memory");
+        return -5;
+    }
+    clk.lap("read_collinearity");
+    return 0;
+}

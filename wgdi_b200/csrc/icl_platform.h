@@ -8,7 +8,12 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
+#include <utility>
 
 #ifndef ICL_EMU
 #include <cuda_runtime.h>
@@ -67,23 +72,149 @@ struct Status {
 // ------------------------------------------------------------------------------------------------
 // memory
 // ------------------------------------------------------------------------------------------------
+// Raw allocations: device memory and page-locked host memory.
 #ifndef ICL_EMU
-inline cudaError_t dev_malloc(void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16); }
-inline cudaError_t dev_free(void *p) { return cudaFree(p); }
+inline cudaError_t raw_dev_malloc(void **p, size_t bytes) { return cudaMalloc(p, bytes); }
+inline cudaError_t raw_dev_free(void *p) { return cudaFree(p); }
+inline cudaError_t raw_pin_malloc(void **p, size_t bytes) { return cudaHostAlloc(p, bytes, cudaHostAllocDefault); }
+inline cudaError_t raw_pin_free(void *p) { return cudaFreeHost(p); }
+inline void raw_dev_zero(void *p, size_t bytes) { cudaMemsetAsync(p, 0, bytes, 0); cudaStreamSynchronize(0); }
+inline void raw_device_idle() { cudaDeviceSynchronize(); }
+inline int raw_current_device() { int d = 0; cudaGetDevice(&d); return d; }
+inline void raw_set_device(int d) { cudaSetDevice(d); }
+inline void raw_clear_error() { (void)cudaGetLastError(); }
 inline cudaError_t h2d(void *d, const void *h, size_t b, cudaStream_t s) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s); }
 inline cudaError_t d2h(void *h, const void *d, size_t b, cudaStream_t s) { return cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s); }
 inline cudaError_t d2d(void *d, const void *s_, size_t b, cudaStream_t s) { return cudaMemcpyAsync(d, s_, b, cudaMemcpyDeviceToDevice, s); }
 inline cudaError_t dev_memset(void *d, int v, size_t b, cudaStream_t s) { return cudaMemsetAsync(d, v, b, s); }
 inline cudaError_t dev_sync(cudaStream_t s) { return cudaStreamSynchronize(s); }
 #else
-inline int dev_malloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 16); return *p ? 0 : 1; }
-inline int dev_free(void *p) { free(p); return 0; }
+inline int raw_dev_malloc(void **p, size_t bytes) { *p = malloc(bytes); return *p ? 0 : 1; }
+inline int raw_dev_free(void *p) { free(p); return 0; }
+inline int raw_pin_malloc(void **p, size_t bytes) { *p = malloc(bytes); return *p ? 0 : 1; }
+inline int raw_pin_free(void *p) { free(p); return 0; }
+inline void raw_dev_zero(void *p, size_t bytes) { memset(p, 0, bytes); }
+inline void raw_device_idle() {}
+inline int raw_current_device() { return 0; }
+inline void raw_set_device(int) {}
+inline void raw_clear_error() {}
 inline int h2d(void *d, const void *h, size_t b, cudaStream_t) { memcpy(d, h, b); return 0; }
 inline int d2h(void *h, const void *d, size_t b, cudaStream_t) { memcpy(h, d, b); return 0; }
 inline int d2d(void *d, const void *s_, size_t b, cudaStream_t) { memcpy(d, s_, b); return 0; }
 inline int dev_memset(void *d, int v, size_t b, cudaStream_t) { memset(d, v, b); return 0; }
 inline int dev_sync(cudaStream_t) { return 0; }
 #endif
+
+// Process-wide cache of released blocks.  A context holds ~90 device arrays sized by its comparison; cudaMalloc and
+// cudaFree of gigabytes cost far more than the step that uses them (C4: 0.1-0.5 s to tear a context down, as much again
+// to build the next one, for an 8 ms step), and the drop-in driver, the batch runner and the sharded runs create one
+// context per comparison.  A released block is kept (per device / for page-locked memory) and handed to the next request
+// of about its size; nothing goes back to the driver before the process ends, unless the cache outgrows its limit
+// (ICL_B200_CACHE_MB, default 16384; 0 switches the cache off) or an allocation fails (everything cached is freed and
+// the allocation tried again).
+//  * release keeps cudaFree's guarantee: the device is idle before the block can be handed out again;
+//  * a recycled device block is zeroed before reuse — strictly more than cudaMalloc promises.
+struct BlockCache {
+    struct Pool {
+        std::multimap<size_t, void *> free_blocks;
+        size_t cached = 0;
+    };
+    std::mutex mu;
+    std::map<int, Pool> pools;                       // device id; -1 = page-locked host memory
+    std::unordered_map<void *, std::pair<int, size_t>> live;
+    size_t limit;
+    int64_t hits = 0, misses = 0;
+    BlockCache() {
+        const char *e = getenv("ICL_B200_CACHE_MB");
+        limit = (size_t)(e ? strtoull(e, nullptr, 10) : 16384ull) << 20;
+    }
+    static BlockCache &get() {
+        static BlockCache *c = new BlockCache();     // never destroyed: the driver may be gone before static destructors run
+        return *c;
+    }
+    static size_t round_up(size_t bytes) { return (std::max<size_t>(bytes, 16) + 511) & ~(size_t)511; }
+    void trim(int pool) {                            // everything cached in one pool back to the driver (mu held)
+        Pool &pl = pools[pool];
+        for (auto &kv : pl.free_blocks) {
+            if (pool < 0) raw_pin_free(kv.second); else raw_dev_free(kv.second);
+        }
+        pl.free_blocks.clear();
+        pl.cached = 0;
+    }
+    cudaError_t alloc(void **p, size_t bytes, bool pinned) {
+        bytes = round_up(bytes);
+        const int pool = pinned ? -1 : raw_current_device();
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            Pool &pl = pools[pool];
+            auto it = pl.free_blocks.lower_bound(bytes);
+            if (it != pl.free_blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
+                *p = it->second;
+                const size_t got = it->first;
+                pl.cached -= got;
+                pl.free_blocks.erase(it);
+                live[*p] = std::make_pair(pool, got);
+                hits++;
+                if (!pinned) raw_dev_zero(*p, got);
+                return cudaSuccess;
+            }
+            misses++;
+        }
+        cudaError_t e = pinned ? raw_pin_malloc(p, bytes) : raw_dev_malloc(p, bytes);
+        if (e != cudaSuccess) {                      // make room: the cache gives everything back, then once more
+            raw_clear_error();
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                trim(pool);
+            }
+            e = pinned ? raw_pin_malloc(p, bytes) : raw_dev_malloc(p, bytes);
+        }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(mu);
+            live[*p] = std::make_pair(pool, bytes);
+        }
+        return e;
+    }
+    cudaError_t release(void *p) {
+        if (!p) return cudaSuccess;
+        int pool = 0;
+        size_t bytes = 0;
+        bool known = false;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = live.find(p);
+            if (it != live.end()) { pool = it->second.first; bytes = it->second.second; known = true; live.erase(it); }
+        }
+        if (!known) return cudaSuccess;              // not ours (never happens: every block comes from alloc)
+        if (limit == 0) return pool < 0 ? raw_pin_free(p) : raw_dev_free(p);
+        if (pool >= 0) {                             // cudaFree's implicit guarantee, kept: nothing on the device uses the block
+            const int cur = raw_current_device();
+            if (cur != pool) raw_set_device(pool);
+            raw_device_idle();
+            if (cur != pool) raw_set_device(cur);
+        } else {
+            raw_device_idle();                       // page-locked: copies of the calling context's device have landed
+        }
+        std::lock_guard<std::mutex> lock(mu);
+        Pool &pl = pools[pool];
+        if (pl.cached + bytes > limit) trim(pool);
+        if (bytes > limit) return pool < 0 ? raw_pin_free(p) : raw_dev_free(p);
+        pl.free_blocks.emplace(bytes, p);
+        pl.cached += bytes;
+        return cudaSuccess;
+    }
+    size_t cached_bytes() {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t t = 0;
+        for (auto &kv : pools) t += kv.second.cached;
+        return t;
+    }
+};
+
+inline cudaError_t dev_malloc(void **p, size_t bytes) { return BlockCache::get().alloc(p, bytes, false); }
+inline cudaError_t dev_free(void *p) { return BlockCache::get().release(p); }
+inline cudaError_t pin_malloc(void **p, size_t bytes) { return BlockCache::get().alloc(p, bytes, true); }
+inline cudaError_t pin_free(void *p) { return BlockCache::get().release(p); }
 
 // grow-only device buffer
 template <class T>
