@@ -138,9 +138,36 @@ class mycollinearity():
         return pts
 
     # ---- wgdi/run_colliearity.py:88-156 ----------------------------------------------------------
+    def _engine_in_background(self):
+        """The device side of a run needs nothing from the input files to get ready: the CUDA context of a fresh process
+        (~1 s), the engine's streams and the start-up check of the device rank against the running numpy are started here and
+        proceed while the host parses and grades (the native ingest and the CUDA calls both run without the GIL)."""
+        if len(self.devices) != 1:
+            return None
+        from concurrent.futures import ThreadPoolExecutor
+
+        def make():
+            eng = IclEngine(self.devices[0])
+            if self.rank != 'device' and eng.rank_mode == 'auto':
+                eng.numpy_sort_kind()
+            return eng
+        pool = ThreadPoolExecutor(1)
+        fut = pool.submit(make)
+        pool.shutdown(wait=False)
+        return fut
+
     def run(self):
         t0 = time.perf_counter()
-        pts = self.load_points()
+        warm = self._engine_in_background()
+        try:
+            pts = self.load_points()
+        except BaseException:                             # sys.exit(1) of :113-115 included: no engine is left behind
+            if warm is not None:
+                try:
+                    warm.result().close()
+                except Exception:
+                    pass
+            raise
         t1 = time.perf_counter()
         params = ChainParams.from_options(self.options)
         for c1, c2 in pts['pair_names']:
@@ -153,7 +180,7 @@ class mycollinearity():
                 from .shard import chain_on_devices
                 blocks = chain_on_devices(pts, len(pts['pair_names']), params, self.devices, min_members=self.over_gap)
             else:
-                eng = IclEngine(self.devices[0])
+                eng = warm.result()
                 eng.fields = "writer"     # only what the file is written from comes back: 32 B per block, 8 B per gene pair
                 # the points cross PCIe in the narrowest element types that hold them (7 instead of 16 bytes per point)
                 up = compact_points(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'])
