@@ -129,7 +129,7 @@ def test_native_grading_matches_oracle_with_ties(host):
         assert (got == icl_oracle.grade_hits(q, bits, mult, rn, [50, 30, 25])).all()
 
 
-def _random_m8(rng, path, genes, n_rows, sorted_by_query, tie_span):
+def _random_m8(rng, path, genes, n_rows, sorted_by_query, tie_span, float_bits=False, crlf=False):
     """A BLAST-like table with duplicate pairs, self hits, unknown ids, sub-threshold rows and many tied bit scores."""
     q = rng.integers(0, len(genes), n_rows)
     if sorted_by_query:
@@ -138,9 +138,13 @@ def _random_m8(rng, path, genes, n_rows, sorted_by_query, tie_span):
     bits = rng.integers(95, 100 + tie_span, n_rows)
     ev = rng.choice(["1e-30", "2.5e-7", "0.0", "1e-5", "3e-4", "9.9e-06"], n_rows, p=[0.5, 0.2, 0.1, 0.05, 0.1, 0.05])
     names = list(genes) + ["zz1", "zz2", "zz3"]
-    with open(path, "w") as f:
-        for a, b, e, sc in zip(q, s, ev, bits):
-            f.write("\t".join([genes[a], names[b], "90.1", "100", "1", "0", "1", "100", "1", "100", e, str(sc)]) + "\n")
+    eol = "\r\n" if crlf else "\n"
+    with open(path, "w", newline="") as f:
+        for k, (a, b, e, sc) in enumerate(zip(q, s, ev, bits)):
+            sc = f"{sc}.5" if float_bits and k % 3 == 0 else str(sc)
+            f.write("\t".join([genes[a], names[b], "90.1", "100", "1", "0", "1", "100", "1", "100", e, sc]) + eol)
+            if crlf and k % 50 == 0:
+                f.write(eol)                                        # blank lines are skipped (pandas: skip_blank_lines)
 
 
 @pytest.mark.parametrize("sorted_by_query", [True, False])
@@ -160,11 +164,13 @@ def test_fused_ingest_equals_the_pandas_readers(host, tmp_path, sorted_by_query)
         order = rng.integers(1, 50, ng).astype(np.int64)
         gff = pd.DataFrame({"chr": [f"c{c}" for c in chrom]}, index=pd.Index(genes))
         p = tmp_path / f"t{trial}.m8"
-        _random_m8(rng, p, genes, int(rng.integers(1, 3000)), sorted_by_query, tie_span=int(rng.integers(2, 40)))
+        float_bits, crlf, reverse = trial % 3 == 1, trial % 4 == 2, trial % 5 == 3
+        _random_m8(rng, p, genes, int(rng.integers(1, 3000)), sorted_by_query, tie_span=int(rng.integers(2, 40)),
+                   float_bits=float_bits, crlf=crlf)
         mult, rn = int(rng.integers(1, 4)), int(rng.integers(2, 30))
         grading = [50, 30, 25]
         # reference-like path
-        blast = base.newblast(str(p), 100, 1e-5, gff, gff, "false")
+        blast = base.newblast(str(p), 100, 1e-5, gff, gff, "true" if reverse else "false")
         g1, g2, bits = blast["g1"].to_numpy(), blast["g2"].to_numpy(), blast[11].to_numpy()
         grade = icl_oracle.grade_hits(g1, bits, mult, rn, [1, 2, 3])
         ok = grade > 0
@@ -172,7 +178,7 @@ def test_fused_ingest_equals_the_pandas_readers(host, tmp_path, sorted_by_query)
         pid, names = pair_ids(list(chr_names), list(chr_names), chr_code[g1[ok]], chr_code[g2[ok]])
         # fused path
         ids = host.pack_strings(genes)
-        with host.Ingest(str(p), False, 100, 1e-5, ids, ids, mult, rn, threads=int(rng.integers(1, 6))) as ing:
+        with host.Ingest(str(p), reverse, 100, 1e-5, ids, ids, mult, rn, threads=int(rng.integers(1, 6))) as ing:
             assert ing.n_hits == len(g1)
             off, abits = ing.ambiguous()
             assert abits.dtype == bits.dtype
