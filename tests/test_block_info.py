@@ -260,3 +260,34 @@ def test_native_collinearity_reader_equals_the_python_reader(tmp_path):
     (tmp_path / "empty.txt").write_text("")
     nat = _host.read_collinearity(str(tmp_path / "empty.txt"), t, t)
     assert nat["ids"] == [] and nat["off"].tolist() == [0]
+
+
+def test_frame_to_csv_is_pandas_to_csv(tmp_path):
+    """The -bi CSV writer against `DataFrame.to_csv(index=None)` byte for byte: floats of every printed form, missing
+    values, integer and mixed columns, the frame `block_info.assemble` builds; and the cases it hands back to pandas."""
+    import pandas as pd
+    from wgdi_b200.block_info import frame_to_csv
+    rng = np.random.default_rng(3)
+    n = 500
+    floats = np.concatenate([rng.random(n - 12) * 10.0 ** rng.integers(-12, 18, n - 12),
+                             [0.0, -0.0, 1.0, 12.0, 1e16, 1e-5, 0.0001, 123456789012345680.0, np.nan, np.inf, -np.inf, 1 / 3]])
+    frames = {
+        "bi": pd.DataFrame([[str(i), f"c{i % 3}", "7", float(i), float(i + 5), 3.0, 9.0, f"0.{i:04d}", 6 + i % 4,
+                             -1 if i % 2 else 0.25, -1 if i % 2 else 0.5, *([-1, -1, -1, -1, -1] if i % 3 else [0.5, 1 / 3, 0.0, 1.0, -0.25]),
+                             "1_2_3", "4_5_6", "-1_-1_-1", floats[i]] for i in range(n)],
+                           columns=['id', 'chr1', 'chr2', 'start1', 'end1', 'start2', 'end2', 'pvalue', 'length', 'ks_median',
+                                    'ks_average', 'homo1', 'homo2', 'homo3', 'homo4', 'homo5', 'block1', 'block2', 'ks',
+                                    'tandem_ratio']),
+        "all_int_minus_one": pd.DataFrame({"a": [-1] * 5, "b": [1.5] * 5, "c": ["x"] * 5}),
+        "object_mix": pd.DataFrame({"a": pd.Series([1, 2.5, "s", None, float("nan")], dtype=object), "b": [1, 2, 3, 4, 5]}),
+        "empty": pd.DataFrame({"a": pd.Series([], dtype=float), "b": pd.Series([], dtype=object)}),
+        "needs_quotes": pd.DataFrame({"a": ["x,y", 'say "hi"', "plain"], "b": [1.0, 2.0, 3.0]}),
+        "bools": pd.DataFrame({"a": [True, False], "b": [1.0, np.nan]}),
+    }
+    frames["bi"]["density1"] = frames["bi"]["length"] / ((frames["bi"]["end1"] - frames["bi"]["start1"]).abs() + 1)
+    frames["bi"]["class1"] = 0
+    for name, df in frames.items():
+        a, b = tmp_path / f"{name}_ours.csv", tmp_path / f"{name}_pandas.csv"
+        frame_to_csv(df, str(a))
+        df.to_csv(str(b), index=None)
+        assert open(a, newline="").read() == open(b, newline="").read(), name
