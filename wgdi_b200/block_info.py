@@ -176,14 +176,16 @@ class block_info():
         t0 = time.perf_counter()
         lens1 = base.newlens(self.lens1, self.position)
         lens2 = base.newlens(self.lens2, self.position)
-        gff1 = base.newgff(self.gff1)
-        gff2 = base.newgff(self.gff2)
+        same = self.gff2 == self.gff1 and self.lens2 == self.lens1     # self comparison: the tables are parsed once
+        gff1 = base.newgff(self.gff1, usecols=range(6))
         gff1 = gff1[gff1['chr'].isin(lens1.index)]
-        gff2 = gff2[gff2['chr'].isin(lens2.index)]
+        gff2 = gff1 if same else base.newgff(self.gff2, usecols=range(6))
+        if not same:
+            gff2 = gff2[gff2['chr'].isin(lens2.index)]
         ids1 = ids2 = None
         if self.native:
             ids1 = _host.pack_strings(gff1.index)
-            ids2 = ids1 if self.gff2 == self.gff1 and self.lens2 == self.lens1 else _host.pack_strings(gff2.index)
+            ids2 = ids1 if same else _host.pack_strings(gff2.index)
         g1, g2, rank = self.load_hits(gff1, gff2, ids1, ids2)
         order2 = gff2['order'].to_numpy()
         o = np.lexsort((rank, g1))
