@@ -145,7 +145,12 @@ def pack_strings(values):
 
 
 def threads_default():
-    return min(32, os.cpu_count() or 1)
+    """Host threads of the native calls: the cores this process may run on (cgroup / affinity aware), at most 32."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(1, min(32, n))
 
 
 def read_m8(path, reverse, min_score, max_evalue, ids1, ids2, threads=None):

@@ -20,6 +20,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -50,17 +53,26 @@ void parallel_for(int64_t n, int threads, F f) {        // f(index) for index in
     if (threads < 1) threads = 1;
     if (threads > n) threads = (int)(n > 0 ? n : 1);
     std::atomic<int64_t> next(0);
+    std::exception_ptr failure;                         // the first exception of any worker, rethrown in the caller
+    std::mutex failure_lock;
     auto work = [&]() {
-        for (;;) {
-            int64_t i = next.fetch_add(1);
-            if (i >= n) break;
-            f(i);
+        try {
+            for (;;) {
+                int64_t i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> g(failure_lock);
+            if (!failure) failure = std::current_exception();
+            next.store(n);                              // nobody starts another index
         }
     };
     std::vector<std::thread> th;
     for (int t = 1; t < threads; t++) th.emplace_back(work);
     work();
     for (auto &t : th) t.join();
+    if (failure) std::rethrow_exception(failure);
 }
 
 inline uint64_t hash_bytes(const char *p, size_t n) {   // 8 bytes per multiplication; ids of >= 8 bytes end with an overlapping word
@@ -411,8 +423,8 @@ int parse_m8(const char *who, const char *path, int32_t reverse, double min_scor
     parallel_for(n_chunks, threads, [&](int64_t c) {
         ChunkOut &o = outs[c];
         const char *p = data + start[c], *end = data + start[c + 1];
-        {   // a row has at least 24 bytes: room for every row of the chunk, untouched pages cost nothing
-            const size_t room = (size_t)(end - p) / 24 + 1;
+        {   // BLAST rows are 50-70 bytes: room for every row of a typical chunk (untouched pages cost nothing), growth otherwise
+            const size_t room = (size_t)(end - p) / 40 + 1;
             if (want_row) o.row.reserve(room);
             o.g1.reserve(room); o.g2.reserve(room); o.bits.reserve(room);
         }
@@ -528,7 +540,7 @@ inline int64_t mark_group_duplicates(const int32_t *sub, int64_t m, std::vector<
 extern "C" int icl_host_read_m8(const char *path, int32_t reverse, double min_score, double max_evalue,
                                 const char *ids1, const int64_t *off1, int64_t n1,
                                 const char *ids2, const int64_t *off2, int64_t n2,
-                                int32_t threads, icl_hits *out, char *err, int32_t errlen) {
+                                int32_t threads, icl_hits *out, char *err, int32_t errlen) try {
     if (!path || !out || !off1 || !off2 || (n1 > 0 && !ids1) || (n2 > 0 && !ids2)) { set_err(err, errlen, "icl_host_read_m8: null argument"); return -1; }
     memset(out, 0, sizeof(*out));
     if (threads < 1) threads = 1;
@@ -577,6 +589,12 @@ extern "C" int icl_host_read_m8(const char *path, int32_t reverse, double min_sc
     out->n_rows_file = P.rows_file;
     out->bits_is_int = P.all_int ? 1 : 0;
     return 0;
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_read_m8: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_read_m8: ") + e.what());
+    return -6;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,20 +618,18 @@ extern "C" int icl_host_ingest_open(const char *path, int32_t reverse, double mi
                                     const char *ids1, const int64_t *off1, int64_t n1,
                                     const char *ids2, const int64_t *off2, int64_t n2,
                                     int32_t multiple, int32_t repeat_number, int32_t blue_extra,
-                                    int32_t threads, icl_ingest **out, icl_ingest_info *info, char *err, int32_t errlen) {
+                                    int32_t threads, icl_ingest **out, icl_ingest_info *info, char *err, int32_t errlen) try {
     if (!path || !out || !info || !off1 || !off2 || (n1 > 0 && !ids1) || (n2 > 0 && !ids2)) { set_err(err, errlen, "icl_host_ingest_open: null argument"); return -1; }
     *out = nullptr;
     memset(info, 0, sizeof(*info));
     if (threads < 1) threads = 1;
     PhaseClock clk;
-    icl_ingest *h = new (std::nothrow) icl_ingest();
-    if (!h) { set_err(err, errlen, "out of memory"); return -5; }
+    std::unique_ptr<icl_ingest> owner(new icl_ingest());    // released to the caller on success only
+    icl_ingest *h = owner.get();
     h->threads = threads; h->n1 = n1; h->n2 = n2;
     if (int rc = parse_m8("icl_host_ingest_open", path, reverse, min_score, max_evalue, ids1, off1, n1, ids2, off2, n2, threads, false,
-                          h->P, clk, err, errlen)) {
-        delete h;
+                          h->P, clk, err, errlen))
         return rc;
-    }
     const int64_t rn = repeat_number;
     const int64_t red = std::min<int64_t>(multiple, rn), blue = std::min<int64_t>((int64_t)blue_extra + (int64_t)multiple, rn);  // :64,:67
     h->red = red; h->blue = blue; h->rn = rn;
@@ -680,11 +696,17 @@ extern "C" int icl_host_ingest_open(const char *path, int32_t reverse, double mi
     info->bits_is_int = h->P.all_int ? 1 : 0;
     info->n_amb_queries = (int64_t)h->amb_off.size() - 1;
     info->n_amb_hits = (int64_t)h->amb_flat.size();
-    *out = h;
+    *out = owner.release();
     return 0;
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_ingest_open: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_ingest_open: ") + e.what());
+    return -6;
 }
 
-extern "C" int icl_host_ingest_ambiguous(const icl_ingest *h, int64_t *amb_off, double *amb_bits) {
+extern "C" int icl_host_ingest_ambiguous(const icl_ingest *h, int64_t *amb_off, double *amb_bits) try {
     if (!h || !amb_off) return -1;
     memcpy(amb_off, h->amb_off.data(), h->amb_off.size() * sizeof(int64_t));
     if (!h->amb_bits.empty()) {
@@ -692,19 +714,23 @@ extern "C" int icl_host_ingest_ambiguous(const icl_ingest *h, int64_t *amb_off, 
         memcpy(amb_bits, h->amb_bits.data(), h->amb_bits.size() * sizeof(double));
     }
     return 0;
+} catch (const std::exception &) {
+    return -5;
 }
 
-extern "C" int icl_host_ingest_set_classes(icl_ingest *h, const int8_t *amb_cls) {
+extern "C" int icl_host_ingest_set_classes(icl_ingest *h, const int8_t *amb_cls) try {
     if (!h || (!h->amb_flat.empty() && !amb_cls)) return -1;
     for (size_t j = 0; j < h->amb_flat.size(); j++) {
         if (amb_cls[j] < 0 || amb_cls[j] > 3) return -1;
         h->cls[(size_t)h->amb_flat[j]] = amb_cls[j];
     }
     return 0;
+} catch (const std::exception &) {
+    return -5;
 }
 
 extern "C" int icl_host_ingest_count(icl_ingest *h, const int32_t *chr1, const int32_t *chr2, int32_t nc1, int32_t nc2,
-                                     uint8_t *present, int64_t *n_points) {
+                                     uint8_t *present, int64_t *n_points) try {
     if (!h || !chr1 || !chr2 || !present || !n_points || nc1 < 1 || nc2 < 1) return -1;
     PhaseClock clk;
     const Parsed &P = h->P;
@@ -733,11 +759,13 @@ extern "C" int icl_host_ingest_count(icl_ingest *h, const int32_t *chr1, const i
     *n_points = h->kept_base[(size_t)P.n_chunks];
     clk.lap("ingest count");
     return 0;
+} catch (const std::exception &) {
+    return -5;
 }
 
 extern "C" int icl_host_ingest_points(const icl_ingest *h, const int32_t *chr1, const int64_t *order1, const int32_t *chr2,
                                       const int64_t *order2, int32_t nc2, const int32_t *pair_rank, const int32_t *grading3,
-                                      int32_t *pair_id, int32_t *loc1, int32_t *loc2, int32_t *grading, int32_t *grade_class) {
+                                      int32_t *pair_id, int32_t *loc1, int32_t *loc2, int32_t *grading, int32_t *grade_class) try {
     if (!h || !chr1 || !chr2 || !order1 || !order2 || !pair_rank || !grading3 || h->kept_base.empty()) return -1;
     const Parsed &P = h->P;
     if (h->kept_base[(size_t)P.n_chunks] > 0 && (!pair_id || !loc1 || !loc2 || !grading || !grade_class)) return -1;
@@ -760,11 +788,13 @@ extern "C" int icl_host_ingest_points(const icl_ingest *h, const int32_t *chr1, 
     });
     clk.lap("ingest points");
     return 0;
+} catch (const std::exception &) {
+    return -5;
 }
 
 extern "C" int icl_host_grade(int64_t n, const int32_t *query, const double *bits, int32_t n_query,
                               int32_t multiple, int32_t repeat_number, const int32_t *grading3,
-                              int32_t *grade_out, uint8_t *ambiguous, int32_t threads, char *err, int32_t errlen) {
+                              int32_t *grade_out, uint8_t *ambiguous, int32_t threads, char *err, int32_t errlen) try {
     if (n < 0 || n_query < 0 || (n > 0 && (!query || !bits || !grade_out)) || !grading3 || (n_query > 0 && !ambiguous)) {
         set_err(err, errlen, "icl_host_grade: bad argument");
         return -1;
@@ -796,6 +826,12 @@ extern "C" int icl_host_grade(int64_t n, const int32_t *query, const double *bit
         }
     });
     return 0;
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_grade: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_grade: ") + e.what());
+    return -6;
 }
 
 namespace {
@@ -826,7 +862,7 @@ extern "C" int icl_host_write_blocks(const char *path, int64_t n_sel,
                                      const int32_t *strand_code1,
                                      const int64_t *row_of2, int64_t maxo2, const char *names2, const int64_t *name_off2,
                                      const int32_t *strand_code2,
-                                     int32_t threads, char *err, int32_t errlen) {
+                                     int32_t threads, char *err, int32_t errlen) try {
     if (!path || n_sel < 0) { set_err(err, errlen, "icl_host_write_blocks: bad argument"); return -1; }
     std::vector<int64_t> size((size_t)n_sel + 1, 0);
     std::atomic<int> bad(0);
@@ -873,6 +909,12 @@ extern "C" int icl_host_write_blocks(const char *path, int64_t n_sel,
     int rc = fclose(f);
     if ((int64_t)w != total || rc != 0) { set_err(err, errlen, "short write"); return -2; }
     return 0;
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_write_blocks: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_write_blocks: ") + e.what());
+    return -6;
 }
 
 
@@ -887,7 +929,7 @@ extern "C" int icl_host_write_collinearity(const char *path, int64_t n_sel, cons
                                            const int32_t *strand_code1,
                                            const int64_t *row_of2, int64_t maxo2, const char *names2, const int64_t *name_off2,
                                            const int32_t *strand_code2,
-                                           int32_t threads, char *err, int32_t errlen) {
+                                           int32_t threads, char *err, int32_t errlen) try {
     if (!path || n_sel < 0 || (n_sel > 0 && (!score || !ptext || !ptext_off || !pidx || !pair_text || !pair_text_off || !pair ||
                                              !mem_begin || !mem_end || !loc2))) {
         set_err(err, errlen, "icl_host_write_collinearity: bad argument");
@@ -919,6 +961,12 @@ extern "C" int icl_host_write_collinearity(const char *path, int64_t n_sel, cons
     return icl_host_write_blocks(path, n_sel, headers.data(), off.data(), mem_begin, mem_end, loc1, loc2, chr1_code, chr2_code,
                                  row_of1, maxo1, names1, name_off1, strand_code1, row_of2, maxo2, names2, name_off2, strand_code2,
                                  threads, err, errlen);
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_write_collinearity: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_write_collinearity: ") + e.what());
+    return -6;
 }
 
 
@@ -931,7 +979,7 @@ extern "C" int icl_host_place_blocks(int64_t n_blocks, const int32_t *pair, cons
                                      const int32_t *block_bytes, int32_t n_member_fields, const void *const *member_src,
                                      void *const *member_dst, const int32_t *member_bytes, int32_t *out_pair,
                                      int64_t *out_member_off, const int32_t *member_idx, const int64_t *rows,
-                                     int32_t *out_member_idx) {
+                                     int32_t *out_member_idx) try {
     if (n_blocks < 0 || (n_blocks > 0 && (!pair || !global_pair || !block_base || !member_base || !member_off || !out_pair || !out_member_off)))
         return -1;
     int64_t first = 0;                                         // first block of the current pair's run
@@ -954,6 +1002,8 @@ extern "C" int icl_host_place_blocks(int64_t n_blocks, const int32_t *pair, cons
             for (int64_t i = m0; i < m1; i++) out_member_idx[mdest + (i - m0)] = (int32_t)rows[member_idx[i]];
     }
     return 0;
+} catch (const std::exception &) {
+    return -5;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -988,7 +1038,7 @@ extern "C" void icl_host_free_collinearity(icl_collinearity *c) {
 
 extern "C" int icl_host_read_collinearity(const char *path, const char *ids1, const int64_t *off1, int64_t n1,
                                           const char *ids2, const int64_t *off2, int64_t n2,
-                                          icl_collinearity *out, char *err, int32_t errlen) {
+                                          icl_collinearity *out, char *err, int32_t errlen) try {
     if (!path || !out || !off1 || !off2 || (n1 > 0 && !ids1) || (n2 > 0 && !ids2)) { set_err(err, errlen, "icl_host_read_collinearity: null argument"); return -1; }
     memset(out, 0, sizeof(*out));
     PhaseClock clk;
@@ -1107,4 +1157,10 @@ extern "C" int icl_host_read_collinearity(const char *path, const char *ids1, co
     }
     clk.lap("read_collinearity");
     return 0;
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_read_collinearity: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_read_collinearity: ") + e.what());
+    return -6;
 }
