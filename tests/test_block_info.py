@@ -291,3 +291,40 @@ def test_frame_to_csv_is_pandas_to_csv(tmp_path):
         frame_to_csv(df, str(a))
         df.to_csv(str(b), index=None)
         assert open(a, newline="").read() == open(b, newline="").read(), name
+
+
+@pytest.mark.parametrize("homo", ["none", "some", "all"])
+def test_columnwise_assemble_equals_the_row_loop(homo, monkeypatch, tmp_path):
+    """`block_info._assemble_columns` (no per-block Python loop) against the row loop that mirrors block_info.py:18-75: same
+    frame, same column types — a homo column of -1 only stays integer, one that mixes -1 with means is float — same CSV."""
+    import pandas as pd
+    from wgdi_b200.block_info import block_info, frame_to_csv
+    rng = np.random.default_rng({"none": 1, "some": 2, "all": 3}[homo])
+    ng = 40
+    gff1 = pd.DataFrame({"chr": [f"c{i % 3}" for i in range(ng)]}, index=pd.Index([f"a{i}" for i in range(ng)]))
+    gff2 = pd.DataFrame({"chr": [str(i % 2 + 1) for i in range(ng)]}, index=pd.Index([f"b{i}" for i in range(ng)]))
+    B = 60
+    m = rng.integers(1, 9, B)
+    off = np.zeros(B + 1, np.int64)
+    np.cumsum(m, out=off[1:])
+    M = int(off[-1])
+    m1, m2 = rng.integers(-1, ng, M).astype(np.int64), rng.integers(-1, ng, M).astype(np.int64)      # some first members unknown
+    loc1, loc2 = rng.integers(1, 500, M).astype(np.float64), rng.integers(1, 500, M).astype(np.float64)
+    native = dict(loc1=loc1, loc2=loc2,
+                  block1=["_".join(str(int(x)) for x in loc1[off[b]:off[b + 1]]) for b in range(B)],
+                  block2=["_".join(str(int(x)) for x in loc2[off[b]:off[b + 1]]) for b in range(B)])
+    ids, pvs = [str(b + 1) for b in range(B)], [f"0.{b:04d}" for b in range(B)]
+    cnt = {"none": np.zeros(B, np.int32), "some": rng.integers(0, 3, B).astype(np.int32), "all": rng.integers(1, 5, B).astype(np.int32)}[homo]
+    hs = rng.integers(-3, 9, (B, 5)).astype(np.int32)
+    rows, uniq = rng.integers(0, 6, B).astype(np.int64), rng.integers(0, 4, B).astype(np.int32)
+    bi = block_info.__new__(block_info)
+    frames = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ICL_BI_ROWS", mode)
+        frames[mode] = bi.assemble(ids, pvs, off, None, None, None, None, m1, m2, gff1, gff2, pd.Series([], dtype=float), hs, cnt,
+                                   rows, uniq, native)
+        frame_to_csv(frames[mode], str(tmp_path / f"{mode}.csv"))
+    assert list(frames["0"].dtypes) == list(frames["1"].dtypes)
+    assert frames["0"].equals(frames["1"])
+    assert open(tmp_path / "0.csv").read() == open(tmp_path / "1.csv").read()
+    assert 0 < len(frames["0"]) < B

@@ -8,6 +8,7 @@ the CSV are host work.  Extra optional key: `device = <cuda index>`.
 """
 from __future__ import annotations
 
+import os
 import re
 import time
 
@@ -235,7 +236,11 @@ class block_info():
         Ls = np.diff(off).astype(np.int64)
         with np.errstate(divide='ignore', invalid='ignore'):
             hmean = (homo_sum.astype(np.float64) / homo_cnt[:, None]).tolist()
-            tandem = (t_uniq / Ls * t_rows / (Ls + t_rows)).tolist()
+            tandem = (t_uniq / Ls * t_rows / (Ls + t_rows)).tolist() if len(Ls) else []
+        if native is not None and not have_ks and os.environ.get("ICL_BI_ROWS", "0") != "1":
+            frame = self._assemble_columns(ids, pvs, off, m1, m2, chr1_of, chr2_of, native, homo_sum, homo_cnt, tandem)
+            if frame is not None:
+                return self._with_densities(frame)
         cnts = homo_cnt.tolist()
         none5 = [-1, -1, -1, -1, -1]
         data = []
@@ -264,6 +269,40 @@ class block_info():
             'id', 'chr1', 'chr2', 'start1', 'end1', 'start2', 'end2', 'pvalue', 'length',
             'ks_median', 'ks_average', 'homo1', 'homo2', 'homo3', 'homo4', 'homo5',
             'block1', 'block2', 'ks', 'tandem_ratio'])
+        return self._with_densities(data_df)
+
+    @staticmethod
+    def _with_densities(data_df):
         data_df['density1'] = data_df['length'] / ((data_df['end1'] - data_df['start1']).abs() + 1)     # :71-72
         data_df['density2'] = data_df['length'] / ((data_df['end2'] - data_df['start2']).abs() + 1)
         return data_df
+
+    @staticmethod
+    def _assemble_columns(ids, pvs, off, m1, m2, chr1_of, chr2_of, native, homo_sum, homo_cnt, tandem):
+        """`assemble` without its per-block loop, for the common case (native reader, no Ks table): the same values column
+        by column.  pandas infers a column's type from its values, so a column that the row loop would fill with the int -1
+        only stays int64 and one that mixes -1 with means becomes float64 — as there.  None when no block survives (the row
+        loop handles that frame)."""
+        a0, a1 = off[:-1], off[1:]
+        vb = np.flatnonzero((m1[a0] >= 0) & (m2[a0] >= 0)) if len(a0) else np.zeros(0, np.int64)    # :24-25
+        if len(vb) == 0:
+            return None
+        a0, a1 = a0[vb], a1[vb]
+        f1, f2 = native['loc1'], native['loc2']
+        L = (a1 - a0).astype(np.int64)
+        cnt = homo_cnt[vb]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            hmean = homo_sum[vb].astype(np.float64) / cnt[:, None]
+        some = bool((cnt > 0).any())
+        vbl = vb.tolist()
+        ks_text = {n: '_'.join(['-1'] * n) for n in set(L.tolist())}
+        cols = {
+            'id': [ids[b] for b in vbl], 'chr1': chr1_of[m1[a0]].tolist(), 'chr2': chr2_of[m2[a0]].tolist(),
+            'start1': f1[a0], 'end1': f1[a1 - 1], 'start2': f2[a0], 'end2': f2[a1 - 1],
+            'pvalue': [pvs[b] for b in vbl], 'length': L,
+            'ks_median': np.full(len(vb), -1, np.int64), 'ks_average': np.full(len(vb), -1, np.int64)}
+        for j in range(5):
+            cols[f'homo{j + 1}'] = np.where(cnt > 0, hmean[:, j], -1.0) if some else np.full(len(vb), -1, np.int64)
+        cols.update({'block1': [native['block1'][b] for b in vbl], 'block2': [native['block2'][b] for b in vbl],
+                     'ks': [ks_text[n] for n in L.tolist()], 'tandem_ratio': np.asarray(tandem, np.float64)[vb]})
+        return pd.DataFrame(cols)
