@@ -38,14 +38,20 @@ def nargsort_desc(a: np.ndarray) -> np.ndarray:
     return (n - 1 - r)[::-1]
 
 
-def compact_points(pair_id, loc1, loc2, grading):
+def compact_points(pair_id, loc1, loc2, grading, bounds=None):
     """The four point arrays in the narrowest unsigned dtype that holds them (uint8 / uint16, else int32): what the ingest
     hands to `IclEngine.upload`, so that a point crosses PCIe in 7 bytes instead of 16 where gene orders and pair ids fit
-    16 bits and gradings 8 (include/icl_b200.h, icl_upload_typed).  Negative values stay int32 and are rejected by the upload."""
-    def narrow(x):
+    16 bits and gradings 8 (include/icl_b200.h, icl_upload_typed).  Negative values stay int32 and are rejected by the upload.
+    bounds: optional (lowest, highest) value per array that the caller knows to hold (the ingest does: pair ids are
+    0..pairs-1, positions are gene orders, gradings the conf's values) — saves the two passes that look for them."""
+    def narrow(x, b):
         x = np.asarray(x)
-        if len(x) == 0 or x.min() < 0:
+        if len(x) == 0:
             return np.ascontiguousarray(x, np.int32)
-        hi = int(x.max())
+        lo, hi = b if b is not None else (x.min(), x.max())
+        if lo < 0:
+            return np.ascontiguousarray(x, np.int32)
+        hi = int(hi)
         return np.ascontiguousarray(x, np.uint8 if hi < 256 else np.uint16 if hi < 65536 else np.int32)
-    return narrow(pair_id), narrow(loc1), narrow(loc2), narrow(grading)
+    b = bounds if bounds is not None else (None, None, None, None)
+    return narrow(pair_id, b[0]), narrow(loc1, b[1]), narrow(loc2, b[2]), narrow(grading, b[3])

@@ -111,7 +111,8 @@ class mycollinearity():
             sys.exit(1)                                   # :113-115
         pid, names = pair_ids(t1['chr_names'], t2['chr_names'], t1['chr_code'][g1], t2['chr_code'][g2])
         return dict(pair_id=pid, loc1=t1['order'][g1].astype(np.int32), loc2=t2['order'][g2].astype(np.int32),
-                    grading=grade.astype(np.int32), grade_class=cls.astype(np.int32), pair_names=names, genes1=t1, genes2=t2)
+                    grading=grade.astype(np.int32), grade_class=cls.astype(np.int32), pair_names=names, genes1=t1, genes2=t2,
+                    bounds=_point_bounds(len(names), t1, t2, self.grading))
 
     def _load_points_fused(self, gff1, gff2, same):
         """`load_points` for `comparison = genomes` through libicl_host.so's fused ingest (include/icl_host.h,
@@ -135,6 +136,7 @@ class mycollinearity():
             table, names = pair_table(t1['chr_names'], t2['chr_names'], present)
             pts = ing.points(t1['order'], t2['order'], nc2, table, self.grading)
         pts.update(pair_names=names, genes1=t1, genes2=t2)
+        pts['bounds'] = _point_bounds(len(names), t1, t2, self.grading)
         return pts
 
     # ---- wgdi/run_colliearity.py:88-156 ----------------------------------------------------------
@@ -183,7 +185,7 @@ class mycollinearity():
                 eng = warm.result()
                 eng.fields = "writer"     # only what the file is written from comes back: 32 B per block, 8 B per gene pair
                 # the points cross PCIe in the narrowest element types that hold them (7 instead of 16 bytes per point)
-                up = compact_points(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'])
+                up = compact_points(pts['pair_id'], pts['loc1'], pts['loc2'], pts['grading'], pts.get('bounds'))
                 # blocks are views of the engine's page-locked staging: written out before the engine is closed
                 if self.rank == 'device':
                     eng.upload(*up, len(pts['pair_names']))
@@ -207,6 +209,14 @@ class mycollinearity():
         t3 = time.perf_counter()
         self.timing.update(ingest_s=t1 - t0, chain_s=t2 - t1, write_s=t3 - t2)
         sys.exit(0)                                       # :156
+
+
+def _point_bounds(n_pairs, genes1, genes2, grading):
+    """(lowest, highest) value the four point arrays can hold, known without looking at them (`compact_points`)."""
+    def span(order):
+        return (int(order.min()), int(order.max())) if len(order) else (0, 0)
+    return ((0, max(int(n_pairs) - 1, 0)), span(genes1['order']), span(genes2['order']),
+            (min(int(g) for g in grading), max(int(g) for g in grading)))
 
 
 def _gene_table(gff):
