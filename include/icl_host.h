@@ -64,6 +64,16 @@ int icl_host_grade(int64_t n, const int32_t *query, const double *bits, int32_t 
                    int32_t *grade_out, uint8_t *ambiguous, int32_t threads, char *err, int32_t errlen);
 
 /*
+ * Per-query hit rank for `-bi` (`group.sort_values(by=11, ascending=False)[:repeat_number]`, wgdi/block_info.py:104-105):
+ * rank_out[i] = 0-based rank of hit i among its query's hits by bit score descending, -1 beyond the first repeat_number.
+ * Ties are broken by file order here; ambiguous[query] = 1 when a run of tied scores touches a rank below class_bound (the
+ * homo classes of :106-118 switch at ranks 1..10) or the cut at repeat_number: the caller re-ranks those queries with
+ * numpy's own unstable argsort (SURVEY.md hazard H2).
+ */
+int icl_host_rank(int64_t n, const int32_t *query, const double *bits, int32_t n_query, int32_t repeat_number,
+                  int32_t class_bound, int64_t *rank_out, uint8_t *ambiguous, int32_t threads, char *err, int32_t errlen);
+
+/*
  * Fused ingest of one `comparison = genomes` run (wgdi/base.py:172-183 + wgdi/run_colliearity.py:59-86,103-121).
  *
  *   icl_host_ingest_open     parses and filters like icl_host_read_m8, removes the duplicates and grades like

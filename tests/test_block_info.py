@@ -122,12 +122,15 @@ def test_bi_library_exports_declared_symbols():
 def test_rank_hits_is_the_reference_sort():
     """rank_hits == per-query pandas-style nargsort (numpy's unstable sort) trimmed to repeat_number, with heavy ties."""
     from wgdi_b200.engine import nargsort_desc
-    from wgdi_b200.ingest import rank_hits
+    from wgdi_b200 import build
+    from wgdi_b200.ingest import rank_hits, rank_hits_native
+    build.build_host()
     rng = np.random.default_rng(11)
     q = rng.integers(0, 400, 20000)
     for bits in (rng.integers(100, 112, len(q)).astype(np.int64), rng.integers(100, 112, len(q)).astype(np.float64) / 2):
         for rn in (3, 12, 20, 40):
             got = rank_hits(q, bits, rn)
+            assert (rank_hits_native(q, bits, 400, rn) == got).all()           # libicl_host.so + numpy for the tied queries
             exp = np.full(len(q), -1, np.int64)
             for g in np.unique(q):
                 rows = np.flatnonzero(q == g)

@@ -25,7 +25,7 @@ def test_host_library_exports_declared_symbols(host):
     lib = ctypes.CDLL(host.LIB_PATH)
     header = open(os.path.join(ROOT, "include", "icl_host.h")).read()
     declared = set(re.findall(r"\b(icl_host_[a-z_0-9]+)\s*\(", header))
-    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_write_blocks", "icl_host_place_blocks",
+    assert declared == {"icl_host_read_m8", "icl_host_free_hits", "icl_host_grade", "icl_host_rank", "icl_host_write_blocks", "icl_host_place_blocks",
                         "icl_host_write_collinearity", "icl_host_read_collinearity", "icl_host_free_collinearity",
                         "icl_host_ingest_open", "icl_host_ingest_ambiguous", "icl_host_ingest_set_classes",
                         "icl_host_ingest_count", "icl_host_ingest_points", "icl_host_ingest_close"}

@@ -48,6 +48,7 @@ def load():
         lib.icl_host_free_hits.argtypes = [C.POINTER(icl_hits)]
         lib.icl_host_free_hits.restype = None
         lib.icl_host_grade.argtypes = [i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i32]
+        lib.icl_host_rank.argtypes = [i64, vp, vp, i32, i32, i32, vp, vp, i32, vp, i32]
         lib.icl_host_write_blocks.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp,
                                               vp, i64, vp, vp, vp, i32, vp, i32]
         lib.icl_host_write_collinearity.argtypes = [C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
@@ -269,6 +270,18 @@ def grade(query, bits, n_query, multiple, repeat_number, grading, threads=None):
     amb = np.zeros(max(int(n_query), 1), np.uint8)
     _call(lib.icl_host_grade, len(q), q.ctypes.data, b.ctypes.data, int(n_query), int(multiple), int(repeat_number),
           g3.ctypes.data, out.ctypes.data, amb.ctypes.data, int(threads or threads_default()))
+    return out, amb[:n_query].astype(bool)
+
+
+def rank(query, bits, n_query, repeat_number, class_bound, threads=None):
+    """(rank per hit, ambiguous flag per query) — see icl_host_rank."""
+    lib = load()
+    q = np.ascontiguousarray(query, np.int32)
+    b = np.ascontiguousarray(bits, np.float64)
+    out = np.full(len(q), -1, np.int64)
+    amb = np.zeros(max(int(n_query), 1), np.uint8)
+    _call(lib.icl_host_rank, len(q), q.ctypes.data, b.ctypes.data, int(n_query), int(repeat_number), int(class_bound),
+          out.ctypes.data, amb.ctypes.data, int(threads or threads_default()))
     return out, amb[:n_query].astype(bool)
 
 

@@ -16,7 +16,7 @@ import numpy as np
 import pandas as pd
 
 from . import _bi, _host, base
-from .ingest import rank_hits
+from .ingest import rank_hits, rank_hits_native
 
 
 def str_to_bool(s):
@@ -169,7 +169,7 @@ class block_info():
         else:
             blast = base.newblast(self.blast, int(self.score), float(self.evalue), gff1, gff2, self.blast_reverse)
             g1, g2, bits = blast['g1'].to_numpy(), blast['g2'].to_numpy(), blast[11].to_numpy()
-        rank = rank_hits(g1, bits, self.repeat_number)
+        rank = rank_hits_native(g1, bits, len(gff1), self.repeat_number) if self.native else rank_hits(g1, bits, self.repeat_number)
         keep = rank >= 0
         return g1[keep], g2[keep], rank[keep]
 

@@ -834,6 +834,45 @@ extern "C" int icl_host_grade(int64_t n, const int32_t *query, const double *bit
     return -6;
 }
 
+// Per-query rank for `-bi` (wgdi/block_info.py:104-105): 0-based rank by bit score descending among a query's hits, -1 beyond
+// the first repeat_number; stable here, and a query is flagged when a run of tied scores touches a rank below `class_bound`
+// (the homo classes switch there) or the cut at repeat_number — the caller re-ranks exactly those with numpy (hazard H2).
+extern "C" int icl_host_rank(int64_t n, const int32_t *query, const double *bits, int32_t n_query, int32_t repeat_number,
+                             int32_t class_bound, int64_t *rank_out, uint8_t *ambiguous, int32_t threads,
+                             char *err, int32_t errlen) try {
+    if (n < 0 || n_query < 0 || (n > 0 && (!query || !bits || !rank_out)) || (n_query > 0 && !ambiguous)) {
+        set_err(err, errlen, "icl_host_rank: bad argument");
+        return -1;
+    }
+    for (int64_t i = 0; i < n; i++)
+        if (query[i] < 0 || query[i] >= n_query) { set_err(err, errlen, "icl_host_rank: query code out of range"); return -1; }
+    if (n_query > 0) memset(ambiguous, 0, (size_t)n_query);
+    const int64_t rn = repeat_number, tie_below = std::min<int64_t>(class_bound, rn);
+    std::vector<Seg> segs{Seg{query, nullptr, bits, n, 0, n_query > 0 ? n_query - 1 : 0}};
+    group_parts(segs, n_query, threads, true, [&](int64_t lo, int64_t hi, const std::vector<int64_t> &gs, const std::vector<int64_t> &flat,
+                                                  const std::vector<int32_t> &, const std::vector<double> &val) {
+        std::vector<int32_t> idx;
+        for (int64_t q = lo; q < hi; q++) {
+            const int64_t b = gs[(size_t)(q - lo)], m = gs[(size_t)(q - lo) + 1] - b;
+            if (m == 0) continue;
+            const double *v = val.data() + b;
+            idx.resize((size_t)m);
+            for (int64_t j = 0; j < m; j++) idx[(size_t)j] = (int32_t)j;
+            std::stable_sort(idx.begin(), idx.end(), [&](int32_t x, int32_t y) { return v[x] > v[y]; });
+            for (int64_t r = 0; r < m; r++) rank_out[flat[(size_t)(b + idx[(size_t)r])]] = r < rn ? r : -1;
+            for (int64_t r = 0; r + 1 < m; r++)             // element at rank r ties with the next one
+                if (v[idx[(size_t)r]] == v[idx[(size_t)r + 1]] && (r < tie_below || r == rn - 1)) { ambiguous[q] = 1; break; }
+        }
+    });
+    return 0;
+} catch (const std::bad_alloc &) {
+    set_err(err, errlen, "icl_host_rank: out of memory");
+    return -5;
+} catch (const std::exception &e) {
+    set_err(err, errlen, std::string("icl_host_rank: ") + e.what());
+    return -6;
+}
+
 namespace {
 inline char *put_int(char *p, int64_t v) {
     char tmp[24];

@@ -102,6 +102,19 @@ def rank_hits(q, bits, repeat_number, class_bound=10):
     return out
 
 
+def rank_hits_native(q, bits, n_query, repeat_number, class_bound=10):
+    """`rank_hits` with the per-query ranking done by libicl_host.so (stable order, all cores); the queries whose result
+    depends on numpy's tie permutation are re-ranked by `rank_hits` on exactly their hits."""
+    from . import _host
+    q = np.asarray(q)
+    bits = np.asarray(bits)
+    out, amb = _host.rank(q, bits, n_query, repeat_number, class_bound)
+    if amb.any():
+        sel = np.flatnonzero(amb[q])
+        out[sel] = rank_hits(q[sel], bits[sel], repeat_number, class_bound)
+    return out
+
+
 def grade_hits_native(q, bits, n_query, multiple, repeat_number, grading):
     """`grade_hits` with the per-query ranking done by libicl_host.so (stable order); queries whose class
     assignment depends on numpy's tie permutation are re-graded by `grade_hits` on exactly their hits."""
