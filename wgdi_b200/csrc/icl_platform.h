@@ -145,20 +145,26 @@ struct BlockCache {
         bytes = round_up(bytes);
         const int pool = pinned ? -1 : raw_current_device();
         {
-            std::lock_guard<std::mutex> lock(mu);
-            Pool &pl = pools[pool];
-            auto it = pl.free_blocks.lower_bound(bytes);
-            if (it != pl.free_blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
-                *p = it->second;
-                const size_t got = it->first;
-                pl.cached -= got;
-                pl.free_blocks.erase(it);
-                live[*p] = std::make_pair(pool, got);
-                hits++;
+            size_t got = 0;
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                Pool &pl = pools[pool];
+                auto it = pl.free_blocks.lower_bound(bytes);
+                if (it != pl.free_blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
+                    *p = it->second;
+                    got = it->first;
+                    pl.cached -= got;
+                    pl.free_blocks.erase(it);
+                    live[*p] = std::make_pair(pool, got);
+                    hits++;
+                } else {
+                    misses++;
+                }
+            }
+            if (got) {                               // zeroed outside the lock: other threads keep allocating meanwhile
                 if (!pinned) raw_dev_zero(*p, got);
                 return cudaSuccess;
             }
-            misses++;
         }
         cudaError_t e = pinned ? raw_pin_malloc(p, bytes) : raw_dev_malloc(p, bytes);
         if (e != cudaSuccess) {                      // make room: the cache gives everything back, then once more
