@@ -144,9 +144,20 @@ class mycollinearity():
         """The device side of a run needs nothing from the input files to get ready: the CUDA context of a fresh process
         (~1 s), the engine's streams and the start-up check of the device rank against the running numpy are started here and
         proceed while the host parses and grades (the native ingest and the CUDA calls both run without the GIL)."""
-        if len(self.devices) != 1:
-            return None
         from concurrent.futures import ThreadPoolExecutor
+        if len(self.devices) != 1:
+            # sharded run: every GPU's context is created now, side by side (chain_on_devices builds its engines later,
+            # from the cached blocks and on live contexts); a failure here is reported by the run itself
+            def touch(d):
+                try:
+                    IclEngine(d).close()
+                except Exception:
+                    pass
+            pool = ThreadPoolExecutor(len(set(self.devices)))
+            futs = [pool.submit(touch, d) for d in sorted(set(self.devices))]
+            pool.shutdown(wait=False)
+            self._warm_devices = futs
+            return None
 
         def make():
             eng = IclEngine(self.devices[0])
@@ -180,6 +191,8 @@ class mycollinearity():
                 if self.rank == 'device':
                     raise ValueError("rank = device is offered for a single device only")
                 from .shard import chain_on_devices
+                for f in getattr(self, '_warm_devices', ()):
+                    f.result()
                 blocks = chain_on_devices(pts, len(pts['pair_names']), params, self.devices, min_members=self.over_gap)
             else:
                 eng = warm.result()
