@@ -654,3 +654,24 @@ def test_contexts_recycle_their_blocks_emu(emu_backend):
     a = synth.graded_points(synth.make_dataset("tiny"))
     b = synth.graded_points(synth.make_dataset("cross"))
     _assert_contexts_recycle_their_blocks(emu_backend, a, b, ChainParams(mg1=25, mg2=25, grading=(50, 30, 25)))
+
+
+def test_compact_points_with_known_bounds():
+    """`compact_points` narrows by the bounds the ingest knows instead of scanning: same arrays whenever the bounds are the
+    real extremes, a wider (never a narrower) element type when they are only an upper bound."""
+    from wgdi_b200.params import compact_points
+    from wgdi_b200.run_colliearity import _point_bounds
+    rng = np.random.default_rng(2)
+    pair, l1, l2, g = rng.integers(0, 300, 1000), rng.integers(1, 200, 1000), rng.integers(1, 70000, 1000), rng.choice([50, 30, 25], 1000)
+    plain = compact_points(pair, l1, l2, g)
+    exact = compact_points(pair, l1, l2, g, ((pair.min(), pair.max()), (l1.min(), l1.max()), (l2.min(), l2.max()), (25, 50)))
+    assert [a.dtype for a in plain] == [a.dtype for a in exact] == [np.uint16, np.uint8, np.int32, np.uint8]
+    assert all((a == b).all() for a, b in zip(plain, exact))
+    genes1, genes2 = dict(order=np.arange(1, 1001)), dict(order=np.arange(1, 201))
+    b = _point_bounds(300, genes1, genes2, [50, 30, 25])
+    assert b == ((0, 299), (1, 1000), (1, 200), (25, 50))
+    wide = compact_points(pair, l1, np.minimum(l2, 200), g, b)
+    assert [a.dtype for a in wide] == [np.uint16, np.uint16, np.uint8, np.uint8] and (wide[1] == l1).all()
+    neg = compact_points(pair, l1, l2, g, ((0, 299), (-5, 10), (1, 70000), (25, 50)))
+    assert neg[1].dtype == np.int32                     # a possible negative value stays int32 (the upload rejects it)
+    assert all(len(a) == 0 and a.dtype == np.int32 for a in compact_points([], [], [], [], b))
