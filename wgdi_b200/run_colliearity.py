@@ -119,12 +119,20 @@ class mycollinearity():
         icl_host_ingest_*): parse, filters, duplicates, per-query grading and the point table are native and threaded;
         Python sees the gene tables, the few queries with boundary ties (numpy ranks them, hazard H2) and the names of
         the chromosome pairs."""
+        from concurrent.futures import ThreadPoolExecutor
         ids1 = _host.pack_strings(gff1.index)
         ids2 = ids1 if same else _host.pack_strings(gff2.index)
-        t1 = _gene_table(gff1)
-        t2 = t1 if same else _gene_table(gff2)
-        with _host.Ingest(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2,
-                          int(self.multiple), int(self.repeat_number)) as ing:
+        with ThreadPoolExecutor(1) as side:               # the gene tables are built while the library parses the m8 file
+            tables = side.submit(lambda: (_gene_table(gff1), None if same else _gene_table(gff2)))
+            ing = _host.Ingest(self.blast, self.blast_reverse == 'true', int(self.score), float(self.evalue), ids1, ids2,
+                               int(self.multiple), int(self.repeat_number))
+            try:
+                t1, t2 = tables.result()
+            except BaseException:
+                ing.close()
+                raise
+        t2 = t1 if same else t2
+        with ing:
             off, bits = ing.ambiguous()
             ing.set_classes(classes_of_ambiguous(off, bits, int(self.multiple), int(self.repeat_number)))
             nc1, nc2 = len(t1['chr_names']), len(t2['chr_names'])
