@@ -741,18 +741,18 @@ extern "C" int icl_host_ingest_count(icl_ingest *h, const int32_t *chr1, const i
     parallel_for(P.n_chunks, h->threads, [&](int64_t c) {
         const ChunkOut &o = P.outs[c];
         const int8_t *cls = h->cls.data() + P.cbase[c];
-        std::vector<uint8_t> seen((size_t)ncode, 0);
         int64_t kept = 0;
         for (size_t i = 0; i < o.g1.size(); i++) {
             if (!cls[i]) continue;
             const int32_t a = chr1[o.g1[i]], b = chr2[o.g2[i]];
             if (a < 0 || a >= nc1 || b < 0 || b >= nc2) { bad = 1; continue; }
-            seen[(size_t)a * nc2 + b] = 1;
+            // shared table, every writer stores the same value; read first, so that after the first hit of a pair the
+            // line is only read (no table per chunk: scaffold-level assemblies have millions of chromosome pairs)
+            uint8_t *cell = present + (size_t)a * nc2 + b;
+            if (!__atomic_load_n(cell, __ATOMIC_RELAXED)) __atomic_store_n(cell, (uint8_t)1, __ATOMIC_RELAXED);
             kept++;
         }
         h->kept_base[(size_t)c + 1] = kept;
-        for (int64_t k = 0; k < ncode; k++)
-            if (seen[(size_t)k]) present[k] = 1;           // every writer stores the same value
     });
     if (bad) return -4;
     for (int64_t c = 0; c < P.n_chunks; c++) h->kept_base[(size_t)c + 1] += h->kept_base[(size_t)c];
