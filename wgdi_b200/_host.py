@@ -220,6 +220,12 @@ class Ingest:
             self._lib.icl_host_ingest_close(self._h)
             self._h = C.c_void_p()
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def ambiguous(self):
         """(offsets[n_queries + 1], bit scores typed like pandas would infer column 11) of the queries left ungraded."""
         off = np.zeros(int(self.info.n_amb_queries) + 1, np.int64)
