@@ -675,3 +675,36 @@ def test_compact_points_with_known_bounds():
     neg = compact_points(pair, l1, l2, g, ((0, 299), (-5, 10), (1, 70000), (25, 50)))
     assert neg[1].dtype == np.int32                     # a possible negative value stays int32 (the upload rejects it)
     assert all(len(a) == 0 and a.dtype == np.int32 for a in compact_points([], [], [], [], b))
+
+
+def test_drop_in_driver_stops_like_the_reference_when_nothing_survives_emu(emu_backend, tmp_path, capsys):
+    """No hit passes the filters: the reference prints its message and exits with 1 (run_colliearity.py:113-115).  The
+    engine that the driver had started in the background while the files were read is closed, nothing is written."""
+    import contextlib
+    import io
+    from conftest import stage_e2e
+    from wgdi_b200 import base, engine
+    from wgdi_b200.run_colliearity import mycollinearity
+    stage_e2e("tiny", str(tmp_path))
+    closed = []
+    real_close = engine.IclEngine.close
+    def spy(self):
+        closed.append(self)
+        return real_close(self)
+    engine.IclEngine.close = spy
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for mode in ("native", "native-steps", "pandas"):
+            closed.clear()
+            opts = [(k, "1000000" if k == "score" else "none.txt" if k == "savefile" else v)
+                    for k, v in base.load_conf("icl.conf", "collinearity")] + [("ingest", mode)]
+            out = io.StringIO()
+            with contextlib.redirect_stdout(out), pytest.raises(SystemExit) as e:
+                mycollinearity(opts).run()
+            assert e.value.code == 1 and "Stopped!" in out.getvalue(), mode
+            assert len(closed) >= 1 and all(c.ctx is None for c in closed), mode
+            assert not os.path.exists("none.txt")
+    finally:
+        os.chdir(cwd)
+        engine.IclEngine.close = real_close
