@@ -859,6 +859,15 @@ def main():
                                                                                  gpu_blocks=blocks_copy)
                 except Exception as e:                      # noqa: BLE001
                     line["cpu_baseline"]["reference_sample"] = {"error": f"{type(e).__name__}: {e}"}
+        try:                                               # the library's block cache over the whole run (icl_cache_stats)
+            cs = np.zeros(3, np.int64)
+            if eng.lib.icl_cache_stats(cs.ctypes.data, 3) == 3:
+                line["block_cache"] = {"served_from_cache": int(cs[0]), "asked_from_driver": int(cs[1]),
+                                       "held_mb": round(float(cs[2]) / 2 ** 20, 1),
+                                       "what": "device / page-locked blocks of closed contexts reused by later ones in this "
+                                               "process (every leg and every -icl run builds its own context)"}
+        except Exception as e:                             # noqa: BLE001 — reporting only
+            line["block_cache"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
