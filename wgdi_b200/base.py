@@ -7,7 +7,19 @@ from __future__ import annotations
 import configparser
 
 import numpy as np
-import pandas as pd
+
+
+class _LazyPandas:
+    """pandas is imported at the first read, not with this module: its import takes about a second, and the drop-in driver
+    has by then started the CUDA context on a background thread (run_colliearity.mycollinearity.run) — the two seconds of a
+    fresh process overlap instead of adding up."""
+
+    def __getattr__(self, name):
+        import pandas
+        return getattr(pandas, name)
+
+
+pd = _LazyPandas()
 
 
 def load_conf(file, section):
