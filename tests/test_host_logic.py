@@ -708,3 +708,25 @@ def test_drop_in_driver_stops_like_the_reference_when_nothing_survives_emu(emu_b
     finally:
         os.chdir(cwd)
         engine.IclEngine.close = real_close
+
+
+def test_classes_of_ambiguous_fast_path_equals_the_loop(monkeypatch):
+    """The one-call ranking of the tie-ambiguous queries (numpy's own int64 argsort routine through the sort helper) gives
+    what the per-query loop over `nargsort_desc` gives; float bit scores and huge values take the loop."""
+    from wgdi_b200 import engine, ingest
+    if not engine._npsort_ok():
+        pytest.skip("_npsort helper not built")
+    rng = np.random.default_rng(8)
+    for trial in range(30):
+        lens = rng.integers(1, 260, int(rng.integers(1, 40)))
+        off = np.r_[0, np.cumsum(lens)].astype(np.int64)
+        bits = rng.integers(100, 100 + int(rng.integers(2, 30)), int(off[-1])).astype(np.int64)
+        mult, rn = int(rng.integers(1, 4)), int(rng.integers(2, 40))
+        fast = ingest.classes_of_ambiguous(off, bits, mult, rn)
+        with monkeypatch.context() as m:
+            m.setattr(engine, "_npsort_ok", lambda: False)
+            slow = ingest.classes_of_ambiguous(off, bits, mult, rn)
+        assert (fast == slow).all()
+        halves = ingest.classes_of_ambiguous(off, bits.astype(np.float64) / 2, mult, rn)      # float scores: the loop
+        assert sorted(halves.tolist()) == sorted(slow.tolist())                # same class sizes (tie order is per dtype)
+    assert len(ingest.classes_of_ambiguous(np.zeros(1, np.int64), np.zeros(0, np.int64), 1, 5)) == 0

@@ -135,6 +135,25 @@ def classes_of_ambiguous(off, bits, multiple, repeat_number, blue_extra=4):
     red = min(int(multiple), rn)
     blue = min(int(blue_extra) + int(multiple), rn)
     cls = np.zeros(len(bits), np.int8)
+    off = np.asarray(off, np.int64)
+    bits = np.asarray(bits)
+    if len(bits) and bits.dtype == np.int64 and int(bits.min()) > -2 ** 31 and int(bits.max()) < 2 ** 31:
+        # integer bit scores (pandas infers int64): all queries in one call of the sort helper, which runs numpy's own
+        # int64 argsort routine per segment without the GIL (csrc/npsort.c, checked against numpy.argsort at start-up)
+        from .engine import _npsort, _npsort_ok
+        if _npsort_ok():
+            lens = np.diff(off)
+            seg = np.repeat(np.arange(len(lens)), lens)
+            local = np.arange(len(bits), dtype=np.int64) - off[seg]
+            last = lens[seg] - 1
+            keys = np.ascontiguousarray(bits[off[seg] + last - local], np.int32)       # every query reversed: nargsort's first step
+            r = np.empty(len(bits), np.int32)
+            _npsort.seg_argsort(keys, off, np.arange(len(lens), dtype=np.int32), r, 4)
+            # nargsort_desc = (n - 1 - r)[::-1]: the element n-1-r[t] of a query has rank n-1-t
+            rank = last - local
+            elem = off[seg] + last - r
+            cls[elem] = np.where(rank < red, 1, np.where(rank < blue, 2, np.where(rank < rn, 3, 0)))
+            return cls
     for q in range(len(off) - 1):
         a, b = int(off[q]), int(off[q + 1])
         ranked = nargsort_desc(bits[a:b])[:rn] + a
